@@ -1,0 +1,823 @@
+/* abi.cu -- the futhark_* C ABI (include/tracer.h) and the lys_* extensions (include/lys_ext.h).
+ *
+ * Host-side restatement of the scalar parts of the reference program: src/lib.fut (entry points, camera
+ * presets, key handling), src/state.fut (the opaque state record), the per-frame camera basis of
+ * src/camera.fut:47-55,89-101 and the sky / flash spectra of src/spectrum.fut:64-91.  Everything that
+ * touches pixels, rays or triangles is launched on the GPU (lbvh.cu, wavefront.cu); there is no CPU
+ * fallback: without a CUDA device futhark_context_new() fails and every entry point returns an error.
+ */
+#include "../../include/tracer.h"
+#include "../../include/lys_ext.h"
+#include "lys_wavefront.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+using namespace lys;
+
+/* ------------------------------------------------------------------ objects */
+struct futhark_context_config { int device = 0; std::string device_name; int debugging = 0; int logging = 0; };
+
+struct futhark_context {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string error;
+    bool failed = false;
+    int path_len = 16, refit_mode = 0, rank = 0, world = 1;
+    uint64_t launches = 0;
+    int logging = 0;
+    std::multimap<size_t, void *> pool;          /* free device blocks by size */
+    PassBuffers bufs; BuildScratch scratch;
+    float4 *pts_pos = nullptr; float *pts_dist = nullptr; int64_t pts_cap = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+namespace {
+
+struct DevBlock {
+    futhark_context *ctx; void *p; size_t bytes;
+    DevBlock(futhark_context *c, void *q, size_t b) : ctx(c), p(q), bytes(b) {}
+    ~DevBlock() { if (p) ctx->pool.insert({bytes, p}); }
+};
+typedef std::shared_ptr<DevBlock> DevRef;
+
+bool set_error(futhark_context *ctx, const std::string &msg) { ctx->error = msg; return false; }
+bool cu_ok(futhark_context *ctx, cudaError_t e, const char *what) {
+    if (e == cudaSuccess) return true;
+    ctx->failed = true;
+    return set_error(ctx, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CU(ctx, call) do { if (!cu_ok(ctx, (call), #call)) return 1; } while (0)
+#define CUB(ctx, call) do { if (!cu_ok(ctx, (call), #call)) return false; } while (0)
+
+DevRef dev_alloc(futhark_context *ctx, size_t bytes) {
+    if (bytes == 0) bytes = 16;
+    bytes = (bytes + 255) & ~(size_t)255;
+    auto it = ctx->pool.find(bytes);
+    if (it != ctx->pool.end()) { void *p = it->second; ctx->pool.erase(it); return std::make_shared<DevBlock>(ctx, p, bytes); }
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) { cu_ok(ctx, e, "cudaMalloc"); return nullptr; }
+    return std::make_shared<DevBlock>(ctx, p, bytes);
+}
+template <class T> bool raw_alloc(futhark_context *ctx, T *&p, size_t count) {
+    void *q = nullptr;
+    if (!cu_ok(ctx, cudaMalloc(&q, sizeof(T) * (count ? count : 1)), "cudaMalloc")) return false;
+    p = (T *)q; return true;
+}
+template <class T> void raw_free(T *&p) { if (p) cudaFree(p); p = nullptr; }
+
+struct SceneHolder {
+    SceneDev d;
+    ~SceneHolder() {
+        raw_free(d.tris); raw_free(d.tri_mats); raw_free(d.mats); raw_free(d.leaf_tri); raw_free(d.leaf_box); raw_free(d.nodes);
+        raw_free(d.node_box); raw_free(d.left); raw_free(d.right); raw_free(d.parent); raw_free(d.height); raw_free(d.morton);
+        raw_free(d.sorted_idx); raw_free(d.bounds); raw_free(d.lights); raw_free(d.light_src);
+    }
+};
+
+/* ---- spectrum.fut (host) ---- */
+struct Spectrum { float k[12]; };
+float h_spectrum_lookup(float v, const Spectrum &s) { return spectrum_lookup12(v, s.k); }
+Spectrum h_uniform_spectrum(float x) { Spectrum s; s.k[0] = 0.0f; s.k[1] = x; for (int i = 1; i < 6; i++) { s.k[2 * i] = -1.0f; s.k[2 * i + 1] = 0.0f; } return s; } /* :81-87 */
+Spectrum h_blackbody(float T) {                                                   /* :64-72 */
+    const float c = 299792458.0f, h = 6.62606957e-34f, kb = 1.3806488e-23f;
+    const float nm[6] = {150.0f, 460.0f, 550.0f, 610.0f, 1000.0f, 2000.0f};
+    Spectrum s;
+    for (int i = 0; i < 6; i++) {
+        float l = nm[i] * 1e-9f;
+        float planck = (2 * h * c * c) / (powf(l, 5.0f) * (expf((h * c) / (l * kb * T)) - 1));
+        s.k[2 * i] = l * 1e9f; s.k[2 * i + 1] = planck;
+    }
+    return s;
+}
+Spectrum h_blackbody_normalized(float T) {                                        /* :74-79 */
+    Spectrum r = h_blackbody(T);
+    float lambda_max = (2.8977721e-3f / T) * 1e9f;
+    float mx = h_spectrum_lookup(lambda_max, r);
+    for (int i = 0; i < 6; i++) r.k[2 * i + 1] = r.k[2 * i + 1] / mx;
+    return r;
+}
+Spectrum h_scale(Spectrum s, float f) { for (int i = 0; i < 6; i++) s.k[2 * i + 1] = s.k[2 * i + 1] * f; return s; }
+
+/* ---- camera presets (lib.fut:10-33) ---- */
+struct CamConf {
+    float aperture, focal_dist, offset_radius, fov;
+    int n_sensor; float mu[3], sigma[3]; V3 vis[3];
+    int tx_kind; float tx_radius, tx_theta; Spectrum tx_emission;
+};
+float h_from_deg(float d) { return d * LYS_PI / 180.0f; }                         /* linalg.fut:53 */
+CamConf conf_visual() {
+    CamConf c{}; c.aperture = 0; c.focal_dist = 1; c.offset_radius = 1; c.fov = h_from_deg(80);
+    c.n_sensor = 3;
+    c.mu[0] = 455; c.sigma[0] = 22; c.vis[0] = v3(0, 0, 1);
+    c.mu[1] = 535; c.sigma[1] = 32; c.vis[1] = v3(0, 1, 0);
+    c.mu[2] = 610; c.sigma[2] = 26; c.vis[2] = v3(1, 0, 0);
+    c.tx_kind = 0; c.tx_radius = 0; c.tx_theta = 0; c.tx_emission = h_uniform_spectrum(0);
+    return c;
+}
+CamConf conf_flash() { CamConf c = conf_visual(); c.tx_kind = 1; c.tx_radius = 0.05f; c.tx_emission = h_scale(h_blackbody_normalized(5500.0f), 1000.0f); return c; }
+CamConf conf_lidar() {
+    CamConf c{}; c.aperture = 0; c.focal_dist = 1; c.offset_radius = 0.01f; c.fov = h_from_deg(90);
+    c.n_sensor = 1; c.mu[0] = 1550; c.sigma[0] = 10; c.vis[0] = v3(1, 0, 0);
+    c.tx_kind = 2; c.tx_radius = 0.01f; c.tx_theta = h_from_deg(3); c.tx_emission = h_uniform_spectrum(1500);
+    return c;
+}
+struct Camera { float pitch, yaw; V3 origin; CamConf conf; };
+V3 h_cam_dir(const Camera &c) { return normalise(v3(sinf(c.yaw), sinf(c.pitch), -(cosf(c.yaw)))); }     /* camera.fut:47-49 */
+V3 h_cam_right(const Camera &c) { return normalise(cross(h_cam_dir(c), v3(0, 1, 0))); }                /* :51-52 */
+V3 h_cam_up(const Camera &c) { return normalise(cross(h_cam_right(c), h_cam_dir(c))); }                /* :54-55 */
+Camera h_move(Camera cam, V3 m) {                                                                      /* :57-62 */
+    V3 d = h_cam_dir(cam); d.y = 0;
+    V3 fwd = normalise(d);
+    cam.origin = ((cam.origin + (0.1f * m.z) * fwd) + (0.1f * m.x) * h_cam_right(cam)) + (0.1f * m.y) * v3(0, 1, 0);
+    return cam;
+}
+Camera h_turn(Camera cam, float pitch, float yaw) {                                                    /* :64-66 */
+    cam.pitch = lys_fmaxf(-0.5f * LYS_PI, lys_fminf(0.5f * LYS_PI, cam.pitch + pitch));
+    cam.yaw = fmodf(cam.yaw + yaw, 2 * LYS_PI);
+    return cam;
+}
+
+} // namespace
+
+struct futhark_opaque_state {                          /* state.fut:8-19 */
+    uint32_t dim_w, dim_h, subsampling;
+    uint32_t rng;
+    DevRef img; uint32_t img_h, img_w;
+    uint32_t n_frames;
+    Spectrum ambience;
+    bool mode;
+    int render_mode;
+    uint32_t cam_conf_id;
+    Camera cam;
+    std::shared_ptr<SceneHolder> scene;
+};
+
+template <class T, int R> struct fut_array { DevRef mem; int64_t shape[R]; int64_t count() const { int64_t c = 1; for (int i = 0; i < R; i++) c *= shape[i]; return c; } T *ptr() const { return (T *)mem->p; } };
+struct futhark_f32_1d : fut_array<float, 1> {};
+struct futhark_f32_2d : fut_array<float, 2> {};
+struct futhark_f32_3d : fut_array<float, 3> {};
+struct futhark_u32_1d : fut_array<uint32_t, 1> {};
+struct futhark_i32_2d : fut_array<int32_t, 2> {};
+
+namespace {
+
+template <class A, class T> A *new_array(futhark_context *ctx, const T *data, const int64_t *shape, int rank, cudaMemcpyKind kind) {
+    if (!ctx) return nullptr;
+    A *a = new A();
+    int64_t c = 1;
+    for (int i = 0; i < rank; i++) { a->shape[i] = shape[i]; c *= shape[i]; }
+    if (c < 0) { delete a; set_error(ctx, "negative array dimension"); return nullptr; }
+    a->mem = dev_alloc(ctx, sizeof(T) * (size_t)c);
+    if (!a->mem) { delete a; return nullptr; }
+    if (c > 0 && data) {
+        if (!cu_ok(ctx, cudaMemcpyAsync(a->mem->p, data, sizeof(T) * (size_t)c, kind, ctx->stream), "cudaMemcpy") ||
+            !cu_ok(ctx, cudaStreamSynchronize(ctx->stream), "cudaStreamSynchronize")) { delete a; return nullptr; }
+    }
+    return a;
+}
+template <class A, class T> int array_values(futhark_context *ctx, A *a, T *out) {
+    if (!ctx || !a || !out) { if (ctx) set_error(ctx, "null argument"); return 1; }
+    CU(ctx, cudaMemcpyAsync(out, a->mem->p, sizeof(T) * (size_t)a->count(), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+void grid_dims(const futhark_opaque_state *s, uint32_t &gw, uint32_t &gh) {      /* integrator.fut:175-176 */
+    gw = (s->dim_w + s->subsampling - 1) / s->subsampling;
+    gh = (s->dim_h + s->subsampling - 1) / s->subsampling;
+}
+
+bool ensure_pass_buffers(futhark_context *ctx, int64_t n, bool probes) {
+    PassBuffers &b = ctx->bufs;
+    if (b.cap < n) {
+        raw_free(b.ray_o); raw_free(b.ray_d); raw_free(b.dist); raw_free(b.sum); raw_free(b.zsum); raw_free(b.best_d); raw_free(b.best_i);
+        raw_free(b.chan); raw_free(b.queue[0]); raw_free(b.queue[1]); raw_free(b.hit); raw_free(b.sh_o); raw_free(b.sh_d1); raw_free(b.sh_d2);
+        raw_free(b.sh_c); raw_free(b.probe_rad); raw_free(b.probe_dist);
+        b.cap = 0;
+        size_t c = (size_t)n;
+        if (!raw_alloc(ctx, b.ray_o, c) || !raw_alloc(ctx, b.ray_d, c) || !raw_alloc(ctx, b.dist, c) || !raw_alloc(ctx, b.sum, c) ||
+            !raw_alloc(ctx, b.zsum, c) || !raw_alloc(ctx, b.best_d, c) || !raw_alloc(ctx, b.best_i, c) || !raw_alloc(ctx, b.chan, c) ||
+            !raw_alloc(ctx, b.queue[0], c) || !raw_alloc(ctx, b.queue[1], c) || !raw_alloc(ctx, b.hit, c) || !raw_alloc(ctx, b.sh_o, c) ||
+            !raw_alloc(ctx, b.sh_d1, c) || !raw_alloc(ctx, b.sh_d2, c) || !raw_alloc(ctx, b.sh_c, c)) return false;
+        b.cap = n;
+    }
+    if (!b.counts) {
+        if (!raw_alloc(ctx, b.counts, LYS_MAX_PATH_LEN + 1) || !raw_alloc(ctx, b.stats, 4) || !raw_alloc(ctx, b.tx_lights, 8)) return false;
+        CUB(ctx, cudaMemsetAsync(b.stats, 0, 4 * sizeof(unsigned long long), ctx->stream));
+    }
+    if (probes && !b.probe_rad) {
+        if (!raw_alloc(ctx, b.probe_rad, (size_t)b.cap * 16) || !raw_alloc(ctx, b.probe_dist, (size_t)b.cap * 16)) return false;
+    }
+    return true;
+}
+bool ensure_scratch(futhark_context *ctx, int64_t n) {
+    BuildScratch &w = ctx->scratch;
+    if (w.cap >= n) return true;
+    raw_free(w.box_c); raw_free(w.box_h); raw_free(w.F); raw_free(w.keys[0]); raw_free(w.keys[1]); raw_free(w.vals[0]); raw_free(w.vals[1]);
+    raw_free(w.rs_hist); raw_free(w.rs_status); raw_free(w.leaf_parent); raw_free(w.visits);
+    w.cap = 0;
+    size_t c = (size_t)n, tiles = (c + 4095) / 4096;
+    if (!raw_alloc(ctx, w.box_c, c) || !raw_alloc(ctx, w.box_h, c) || !raw_alloc(ctx, w.F, 2 * c) || !raw_alloc(ctx, w.keys[0], c) ||
+        !raw_alloc(ctx, w.keys[1], c) || !raw_alloc(ctx, w.vals[0], c) || !raw_alloc(ctx, w.vals[1], c) || !raw_alloc(ctx, w.rs_hist, 1024) ||
+        !raw_alloc(ctx, w.rs_status, 4 * tiles * 256 + 4) || !raw_alloc(ctx, w.leaf_parent, c) || !raw_alloc(ctx, w.visits, c)) return false;
+    w.cap = n;
+    return true;
+}
+
+/* the per-pass constants; camera vectors exactly as camera.fut:82-101 derives them */
+bool make_frame_params(futhark_context *ctx, const futhark_opaque_state *s, uint32_t rng, float intensity_factor, FrameParams &fp) {
+    uint32_t gw, gh; grid_dims(s, gw, gh);
+    fp.gw = (int)gw; fp.gh = (int)gh; fp.fw = (float)gw; fp.fh = (float)gh;
+    fp.rank = ctx->rank; fp.world = ctx->world;
+    int rows = ((int)gh - ctx->rank + ctx->world - 1) / ctx->world;
+    if (rows < 0) rows = 0;
+    fp.n_local = rows * (int)gw;
+    fp.frame_rng = rng;
+    const Camera &cam = s->cam; const CamConf &cf = cam.conf;
+    float ratio = fp.fw / fp.fh;
+    fp.lens_radius = cf.aperture / 2;
+    float half_height = tanf(cf.fov / 2.0f);
+    float half_width = ratio * half_height;
+    V3 w = (-1.0f) * h_cam_dir(cam), u = h_cam_right(cam), v = h_cam_up(cam);
+    float focus = cf.focal_dist;
+    fp.cam_origin = cam.origin;
+    fp.llc = ((cam.origin - (half_width * focus) * u) - (half_height * focus) * v) - focus * w;
+    fp.horizontal = (2 * half_width * focus) * u;
+    fp.vertical = (2 * half_height * focus) * v;
+    fp.cam_u = u; fp.cam_v = v;
+    fp.offset_radius = cf.offset_radius;
+    fp.n_sensor = cf.n_sensor;
+    for (int i = 0; i < 3; i++) { fp.sensor_mu[i] = cf.mu[i]; fp.sensor_sigma[i] = cf.sigma[i]; fp.sensor_vis[i] = cf.vis[i]; }
+    fp.tx_kind = cf.tx_kind; fp.tx_radius = cf.tx_radius; fp.tx_theta = cf.tx_theta;
+    memcpy(fp.tx_emission, cf.tx_emission.k, sizeof(fp.tx_emission));
+    {   /* shapes.fut:18-28: a = 2*pi / n_sectors, angles a*i; rot_z b (1,0,0) */
+        float a = 2 * LYS_PI / (float)8;
+        for (int j = 0; j <= 8; j++) {
+            float bj = a * (float)j;
+            fp.sector_x[j] = 1.0f * cosf(bj) - 0.0f * sinf(bj);
+            fp.sector_y[j] = 1.0f * sinf(bj) + 0.0f * cosf(bj);
+        }
+    }
+    fp.n_scene_lights = (int)s->scene->d.n_lights;
+    memcpy(fp.ambience, s->ambience.k, sizeof(fp.ambience));
+    fp.path_len = ctx->path_len;
+    fp.render_mode = s->render_mode;
+    fp.intensity_factor = intensity_factor;
+    if (cf.tx_kind == 1) {
+        /* flash: disk c.origin (cam_dir c) radius 8 (camera.fut:116-118), identical for every ray */
+        LightRec recs[8];
+        V3 normal = h_cam_dir(cam);
+        V3 c = cross(normal, v3(0, 1, 0));
+        V3 right = (norm(c) == 0) ? v3(1, 0, 0) : normalise(c);
+        V3 up = normalise(cross(right, normal));
+        for (int k = 0; k < 8; k++) {
+            V3 v0 = fp.sector_x[k] * right + fp.sector_y[k] * up;
+            V3 v1 = fp.sector_x[k + 1] * right + fp.sector_y[k + 1] * up;
+            V3 A = cam.origin, B = cam.origin + cf.tx_radius * v1, C = cam.origin + cf.tx_radius * v0;
+            V3 e1 = B - A, e2 = C - A, nc = cross(e1, e2);
+            float area = norm(nc) / 2.0f; V3 n = normalise(nc);
+            LightRec &r = recs[k];
+            r.a[0] = A.x; r.a[1] = A.y; r.a[2] = A.z; r.area = area;
+            r.e1[0] = e1.x; r.e1[1] = e1.y; r.e1[2] = e1.z; r.inv_area = 1.0f / area;
+            r.e2[0] = e2.x; r.e2[1] = e2.y; r.e2[2] = e2.z; r.theta = 0.0f;
+            r.n[0] = n.x; r.n[1] = n.y; r.n[2] = n.z; r.kind = 0;
+            memcpy(r.emission, cf.tx_emission.k, sizeof(r.emission));
+            r.src_index = -1; r.pad[0] = r.pad[1] = r.pad[2] = 0;
+        }
+        CUB(ctx, cudaMemcpyAsync(ctx->bufs.tx_lights, recs, sizeof(recs), cudaMemcpyHostToDevice, ctx->stream));
+        CUB(ctx, cudaStreamSynchronize(ctx->stream));     /* recs is a stack buffer */
+    }
+    return true;
+}
+
+uint32_t h_advance_rng(uint32_t s) { return (48271u * s) % 2147483647u; }           /* rand.fut:11-12 */
+uint32_t h_rng_from_seed(int32_t seed) {                                            /* cpprandom rng_from_seed [seed] */
+    uint32_t sp = 1;
+    sp = ((sp >> 16) ^ sp) ^ ((uint32_t)seed ^ 0x1555u);
+    return h_advance_rng(sp);
+}
+
+futhark_opaque_state *clone_state(const futhark_opaque_state *s) { return new futhark_opaque_state(*s); }
+
+/* sample_frame / sample_frame_accum (integrator.fut:172-192) into `img` */
+bool sample_into(futhark_context *ctx, const futhark_opaque_state *s, uint32_t rng, const float *img_old, float *img_new, bool merge, float n_frames) {
+    FrameParams fp;
+    if (!ensure_pass_buffers(ctx, (int64_t)((s->dim_w + s->subsampling - 1) / s->subsampling) * ((s->dim_h + s->subsampling - 1) / s->subsampling), false)) return false;
+    if (!make_frame_params(ctx, s, rng, 1.0f, fp)) return false;
+    CUB(ctx, run_sample_pass(s->scene->d, fp, ctx->bufs, ctx->stream, &ctx->launches));
+    CUB(ctx, run_accumulate(fp, ctx->bufs, img_old, img_new, merge ? 1 : 0, n_frames, ctx->stream, &ctx->launches));
+    return true;
+}
+
+} // namespace
+
+/* ================================================================== C ABI */
+extern "C" {
+
+struct futhark_context_config *futhark_context_config_new(void) { return new futhark_context_config(); }
+void futhark_context_config_free(struct futhark_context_config *cfg) { delete cfg; }
+void futhark_context_config_set_device(struct futhark_context_config *cfg, const char *s) {
+    if (!cfg || !s) return;
+    const char *p = (*s == '#') ? s + 1 : s;
+    char *end = nullptr; long v = strtol(p, &end, 10);
+    if (end != p && *end == '\0') { cfg->device = (int)v; cfg->device_name.clear(); }
+    else cfg->device_name = s;
+}
+void futhark_context_config_set_debugging(struct futhark_context_config *cfg, int flag) { if (cfg) cfg->debugging = flag; }
+void futhark_context_config_set_logging(struct futhark_context_config *cfg, int flag) { if (cfg) cfg->logging = flag; }
+
+struct futhark_context *futhark_context_new(struct futhark_context_config *cfg) {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) {
+        fprintf(stderr, "libtracer: no CUDA device available (this library has no CPU path)\n");
+        return nullptr;
+    }
+    int dev = cfg ? cfg->device : 0;
+    if (cfg && !cfg->device_name.empty()) {
+        dev = -1;
+        for (int i = 0; i < count; i++) { cudaDeviceProp p; if (cudaGetDeviceProperties(&p, i) == cudaSuccess && strstr(p.name, cfg->device_name.c_str())) { dev = i; break; } }
+        if (dev < 0) { fprintf(stderr, "libtracer: no CUDA device matches '%s'\n", cfg->device_name.c_str()); return nullptr; }
+    }
+    if (dev < 0 || dev >= count) { fprintf(stderr, "libtracer: CUDA device %d out of range\n", dev); return nullptr; }
+    if (cudaSetDevice(dev) != cudaSuccess) return nullptr;
+    futhark_context *ctx = new futhark_context();
+    ctx->device = dev; ctx->logging = cfg ? cfg->logging : 0;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return nullptr; }
+    cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1);
+    const char *pl = getenv("LYS_PATH_LEN");
+    if (pl) { int v = atoi(pl); if (v >= 1 && v <= LYS_MAX_PATH_LEN) ctx->path_len = v; }
+    return ctx;
+}
+void futhark_context_free(struct futhark_context *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    PassBuffers &b = ctx->bufs;
+    raw_free(b.ray_o); raw_free(b.ray_d); raw_free(b.dist); raw_free(b.sum); raw_free(b.zsum); raw_free(b.best_d); raw_free(b.best_i);
+    raw_free(b.chan); raw_free(b.queue[0]); raw_free(b.queue[1]); raw_free(b.hit); raw_free(b.sh_o); raw_free(b.sh_d1); raw_free(b.sh_d2);
+    raw_free(b.sh_c); raw_free(b.counts); raw_free(b.stats); raw_free(b.tx_lights); raw_free(b.probe_rad); raw_free(b.probe_dist);
+    BuildScratch &w = ctx->scratch;
+    raw_free(w.box_c); raw_free(w.box_h); raw_free(w.F); raw_free(w.keys[0]); raw_free(w.keys[1]); raw_free(w.vals[0]); raw_free(w.vals[1]);
+    raw_free(w.rs_hist); raw_free(w.rs_status); raw_free(w.leaf_parent); raw_free(w.visits);
+    raw_free(ctx->pts_pos); raw_free(ctx->pts_dist);
+    for (auto &kv : ctx->pool) cudaFree(kv.second);
+    ctx->pool.clear();
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+int futhark_context_sync(struct futhark_context *ctx) {
+    if (!ctx) return 1;
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+int futhark_context_clear_caches(struct futhark_context *ctx) {
+    if (!ctx) return 1;
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    for (auto &kv : ctx->pool) cudaFree(kv.second);
+    ctx->pool.clear();
+    return 0;
+}
+char *futhark_context_get_error(struct futhark_context *ctx) {
+    if (!ctx) return nullptr;
+    char *r = strdup(ctx->error.c_str());
+    ctx->error.clear();
+    return r;
+}
+
+/* ---- arrays ---- */
+#define LYS_ARRAY_API(NAME, T, RANK, DIMS_DECL, DIMS_INIT)                                                            \
+    struct futhark_##NAME *futhark_new_##NAME(struct futhark_context *ctx, const T *data, DIMS_DECL) {                \
+        int64_t shape[RANK] = DIMS_INIT;                                                                              \
+        return new_array<futhark_##NAME, T>(ctx, data, shape, RANK, cudaMemcpyHostToDevice);                          \
+    }                                                                                                                 \
+    int futhark_free_##NAME(struct futhark_context *ctx, struct futhark_##NAME *arr) { (void)ctx; delete arr; return 0; } \
+    int futhark_values_##NAME(struct futhark_context *ctx, struct futhark_##NAME *arr, T *data) { return array_values(ctx, arr, data); } \
+    const int64_t *futhark_shape_##NAME(struct futhark_context *ctx, struct futhark_##NAME *arr) { (void)ctx; return arr ? arr->shape : nullptr; }
+#define LYS_D1 int64_t dim0
+#define LYS_D2 int64_t dim0, int64_t dim1
+#define LYS_D3 int64_t dim0, int64_t dim1, int64_t dim2
+#define LYS_I1 {dim0}
+#define LYS_I2 {dim0, dim1}
+#define LYS_I3 {dim0, dim1, dim2}
+LYS_ARRAY_API(f32_1d, float, 1, LYS_D1, LYS_I1)
+LYS_ARRAY_API(f32_2d, float, 2, LYS_D2, LYS_I2)
+LYS_ARRAY_API(f32_3d, float, 3, LYS_D3, LYS_I3)
+LYS_ARRAY_API(u32_1d, uint32_t, 1, LYS_D1, LYS_I1)
+LYS_ARRAY_API(i32_2d, int32_t, 2, LYS_D2, LYS_I2)
+
+int futhark_free_opaque_state(struct futhark_context *ctx, struct futhark_opaque_state *obj) { (void)ctx; delete obj; return 0; }
+
+/* ---- init (lib.fut:76-106) ---- */
+int futhark_entry_init(struct futhark_context *ctx, struct futhark_opaque_state **out0, const int32_t seed, const uint32_t h,
+                       const uint32_t w, const uint32_t cam_conf_id, const struct futhark_f32_3d *tri_geoms,
+                       const struct futhark_u32_1d *tri_mats, const struct futhark_f32_2d *mat_data, const float cam_pitch,
+                       const float cam_yaw, const struct futhark_f32_1d *cam_origin) {
+    if (!ctx) return 1;
+    if (!out0 || !tri_geoms || !tri_mats || !mat_data || !cam_origin) { set_error(ctx, "init: null argument"); return 1; }
+    cudaSetDevice(ctx->device);
+    const int64_t n = tri_geoms->shape[0], m = mat_data->shape[0];
+    if (tri_geoms->shape[1] != 3 || tri_geoms->shape[2] != 3) { set_error(ctx, "init: tri_geoms must be [n][3][3]"); return 1; }
+    if (tri_mats->shape[0] != n) { set_error(ctx, "init: tri_mats must be [n] (same n as tri_geoms)"); return 1; }
+    if (mat_data->shape[1] != 28) { set_error(ctx, "init: mat_data must be [m][28]"); return 1; }
+    if (cam_origin->shape[0] != 3) { set_error(ctx, "init: cam_origin must be [3]"); return 1; }
+    if (n < 2) { set_error(ctx, "init: at least 2 triangles are required (radix_tree.mk, radix_tree.fut:75)"); return 1; }
+    if (n >= (1ll << 30)) { set_error(ctx, "init: too many triangles"); return 1; }
+    if (m < 1) { set_error(ctx, "init: at least 1 material is required"); return 1; }
+
+    /* host copies of the small / index arrays: material table, material indices, camera origin */
+    std::vector<uint32_t> h_tm((size_t)n); std::vector<float> h_mats((size_t)m * 28); float org[3];
+    CU(ctx, cudaMemcpyAsync(h_tm.data(), tri_mats->mem->p, sizeof(uint32_t) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(h_mats.data(), mat_data->mem->p, sizeof(float) * (size_t)m * 28, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(org, cam_origin->mem->p, sizeof(org), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    std::vector<char> emissive((size_t)m, 0);
+    for (int64_t i = 0; i < m; i++)                                          /* nonzero_spectrum scene.fut:59-60 */
+        for (int k = 0; k < 6; k++) if (h_mats[i * 28 + 16 + 2 * k] >= 0 && h_mats[i * 28 + 16 + 2 * k + 1] > 0) emissive[i] = 1;
+    std::vector<int> light_src;
+    for (int64_t i = 0; i < n; i++) {
+        if (h_tm[i] >= (uint64_t)m) { set_error(ctx, "init: material index out of range"); return 1; }
+        if (emissive[h_tm[i]]) light_src.push_back((int)i);
+    }
+
+    auto holder = std::make_shared<SceneHolder>();
+    SceneDev &sc = holder->d;
+    sc.n_tris = n; sc.n_mats = m; sc.n_lights = (int64_t)light_src.size();
+    size_t c = (size_t)n;
+    if (!raw_alloc(ctx, sc.tris, 9 * c) || !raw_alloc(ctx, sc.tri_mats, c) || !raw_alloc(ctx, sc.mats, (size_t)m * 28) ||
+        !raw_alloc(ctx, sc.leaf_tri, 3 * c) || !raw_alloc(ctx, sc.leaf_box, 2 * c) || !raw_alloc(ctx, sc.nodes, 2 * c) ||
+        !raw_alloc(ctx, sc.node_box, 2 * c) || !raw_alloc(ctx, sc.left, c) || !raw_alloc(ctx, sc.right, c) || !raw_alloc(ctx, sc.parent, c) ||
+        !raw_alloc(ctx, sc.height, c) || !raw_alloc(ctx, sc.morton, c) || !raw_alloc(ctx, sc.sorted_idx, c) || !raw_alloc(ctx, sc.bounds, 8) ||
+        !raw_alloc(ctx, sc.lights, light_src.size()) || !raw_alloc(ctx, sc.light_src, light_src.size())) return 1;
+    CU(ctx, cudaMemcpyAsync(sc.tris, tri_geoms->mem->p, sizeof(float) * 9 * c, cudaMemcpyDeviceToDevice, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(sc.tri_mats, tri_mats->mem->p, sizeof(uint32_t) * c, cudaMemcpyDeviceToDevice, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(sc.mats, mat_data->mem->p, sizeof(float) * (size_t)m * 28, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (!light_src.empty()) {
+        CU(ctx, cudaMemcpyAsync(sc.light_src, light_src.data(), sizeof(int) * light_src.size(), cudaMemcpyHostToDevice, ctx->stream));
+        CU(ctx, build_lights(sc, sc.light_src, (int)light_src.size(), ctx->stream, &ctx->launches));
+    }
+    if (!ensure_scratch(ctx, n)) return 1;
+    CU(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    CU(ctx, build_lbvh(sc, ctx->scratch, ctx->refit_mode, ctx->stream, &ctx->launches));
+    CU(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaEventElapsedTime(&sc.build_ms, ctx->ev0, ctx->ev1);
+
+    futhark_opaque_state *s = new futhark_opaque_state();
+    s->dim_w = w; s->dim_h = h; s->subsampling = 1;
+    s->rng = h_rng_from_seed(seed);
+    s->img_h = h; s->img_w = w;
+    s->img = dev_alloc(ctx, sizeof(float) * 3 * (size_t)w * h);
+    if (!s->img) { delete s; return 1; }
+    CU(ctx, cudaMemsetAsync(s->img->p, 0, sizeof(float) * 3 * (size_t)w * h, ctx->stream));
+    s->n_frames = 0; s->ambience = h_uniform_spectrum(0); s->mode = false;                 /* no_sky spectrum.fut:91 */
+    if (cam_conf_id == 0) { s->render_mode = 0; s->cam.conf = conf_visual(); }
+    else if (cam_conf_id == 1) { s->render_mode = 0; s->cam.conf = conf_flash(); }
+    else { s->render_mode = 1; s->cam.conf = conf_lidar(); }
+    s->cam_conf_id = cam_conf_id;
+    s->cam.pitch = cam_pitch; s->cam.yaw = cam_yaw; s->cam.origin = v3(org[0], org[1], org[2]);
+    s->scene = holder;
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    *out0 = s;
+    return 0;
+}
+
+int futhark_entry_resize(struct futhark_context *ctx, struct futhark_opaque_state **out0, const uint32_t h, const uint32_t w,
+                         const struct futhark_opaque_state *s) {                 /* lib.fut:108-109 */
+    if (!ctx) return 1;
+    if (!out0 || !s) { set_error(ctx, "resize: null argument"); return 1; }
+    futhark_opaque_state *r = clone_state(s);
+    r->dim_w = w; r->dim_h = h; r->mode = false;
+    *out0 = r;
+    return 0;
+}
+
+int futhark_entry_key(struct futhark_context *ctx, struct futhark_opaque_state **out0, const int32_t e, const int32_t key,
+                      const struct futhark_opaque_state *s) {                    /* lib.fut:120-185; key codes src/sdl.fut */
+    if (!ctx) return 1;
+    if (!out0 || !s) { set_error(ctx, "key: null argument"); return 1; }
+    futhark_opaque_state *r = clone_state(s);
+    if (e == 0) {
+        switch (key) {
+            case 0x32: r->subsampling = s->subsampling + 1; r->n_frames = 0; break;                               /* SDLK_2 */
+            case 0x31: r->subsampling = (s->subsampling - 1u > 1u) ? s->subsampling - 1u : 1u; r->n_frames = 0; break; /* SDLK_1: u32.max 1 (sub-1) */
+            case 0x77: r->cam = h_move(s->cam, v3(0, 0, 1)); r->n_frames = 0; break;                              /* w */
+            case 0x61: r->cam = h_move(s->cam, v3(-1, 0, 0)); r->n_frames = 0; break;                             /* a */
+            case 0x73: r->cam = h_move(s->cam, v3(0, 0, -1)); r->n_frames = 0; break;                             /* s */
+            case 0x64: r->cam = h_move(s->cam, v3(1, 0, 0)); r->n_frames = 0; break;                              /* d */
+            case 0x40000052: r->cam = h_turn(s->cam, -0.1f, 0.0f); r->n_frames = 0; break;                        /* UP */
+            case 0x40000051: r->cam = h_turn(s->cam, 0.1f, 0.0f); r->n_frames = 0; break;                         /* DOWN */
+            case 0x4000004F: r->cam = h_turn(s->cam, 0.0f, 0.1f); r->n_frames = 0; break;                         /* RIGHT */
+            case 0x40000050: r->cam = h_turn(s->cam, 0.0f, -0.1f); r->n_frames = 0; break;                        /* LEFT */
+            case 0x78: r->cam = h_move(s->cam, v3(0, 1, 0)); r->n_frames = 0; break;                              /* x */
+            case 0x7A: r->cam = h_move(s->cam, v3(0, -1, 0)); r->n_frames = 0; break;                             /* z */
+            case 0x20: r->mode = !s->mode; r->n_frames = 0; break;                                                /* SPACE */
+            case 0x6E: r->mode = false; r->n_frames = 0; break;                                                   /* n */
+            case 0x6D: r->mode = true; break;                                                                     /* m */
+            case 0x69: r->cam.conf.aperture = lys_fminf(2.0f, s->cam.conf.aperture + 0.08f); break;               /* i */
+            case 0x6B: r->cam.conf.aperture = lys_fmaxf(0.0f, s->cam.conf.aperture - 0.08f); break;               /* k */
+            case 0x6F: r->cam.conf.focal_dist = s->cam.conf.focal_dist * 1.14f; break;                            /* o */
+            case 0x6C: r->cam.conf.focal_dist = lys_fmaxf(0.1f, s->cam.conf.focal_dist / 1.14f); break;           /* l */
+            case 0x74:                                                                                            /* t */
+                if (s->cam_conf_id == 0) { r->cam.conf = conf_flash(); r->cam_conf_id = 1; r->render_mode = 0; }
+                else if (s->cam_conf_id == 1) { r->cam.conf = conf_lidar(); r->cam_conf_id = 2; r->render_mode = 1; }
+                else { r->cam.conf = conf_visual(); r->cam_conf_id = 0; r->render_mode = 0; }
+                r->n_frames = 0; break;
+            case 0x70: r->ambience = (s->ambience.k[1] == 0) ? h_scale(h_blackbody_normalized(17000.0f), 5.0f) : h_uniform_spectrum(0); break; /* p */
+            default: break;
+        }
+    }
+    *out0 = r;
+    return 0;
+}
+
+int futhark_entry_step(struct futhark_context *ctx, struct futhark_opaque_state **out0, const struct futhark_opaque_state *s) { /* lib.fut:111-118 */
+    if (!ctx) return 1;
+    if (!out0 || !s) { set_error(ctx, "step: null argument"); return 1; }
+    cudaSetDevice(ctx->device);
+    uint32_t gw, gh; grid_dims(s, gw, gh);
+    bool accum = s->mode && s->n_frames > 0;
+    if (accum && (s->img_w != gw || s->img_h != gh)) { set_error(ctx, "step: accumulated image shape does not match the sample grid"); return 1; }
+    futhark_opaque_state *r = clone_state(s);
+    size_t bytes = sizeof(float) * 3 * (size_t)gw * gh;
+    r->img = dev_alloc(ctx, bytes);
+    if (!r->img) { delete r; return 1; }
+    if (ctx->world > 1 && cudaMemsetAsync(r->img->p, 0, bytes, ctx->stream) != cudaSuccess) { delete r; set_error(ctx, "memset failed"); return 1; }
+    r->img_w = gw; r->img_h = gh;
+    if (!sample_into(ctx, s, s->rng, (const float *)s->img->p, (float *)r->img->p, accum, (float)s->n_frames)) { delete r; return 1; }
+    r->rng = h_advance_rng(s->rng);                                                /* integrator.fut:116 */
+    r->n_frames = accum ? s->n_frames + 1 : 1;
+    *out0 = r;
+    return 0;
+}
+
+int futhark_entry_render(struct futhark_context *ctx, struct futhark_i32_2d **out0, const struct futhark_opaque_state *s) { /* lib.fut:187-196 */
+    if (!ctx) return 1;
+    if (!out0 || !s) { set_error(ctx, "render: null argument"); return 1; }
+    cudaSetDevice(ctx->device);
+    int64_t shape[2] = {(int64_t)s->dim_h, (int64_t)s->dim_w};
+    futhark_i32_2d *a = new_array<futhark_i32_2d, int32_t>(ctx, nullptr, shape, 2, cudaMemcpyDeviceToDevice);
+    if (!a) return 1;
+    if (!cu_ok(ctx, run_render((const float *)s->img->p, (int)s->img_h, (int)s->img_w, (int)s->dim_h, (int)s->dim_w, (int)s->subsampling,
+                               a->ptr(), ctx->stream, &ctx->launches), "render")) { delete a; return 1; }
+    *out0 = a;
+    return 0;
+}
+
+int lys_sample_n_frames_stats(struct futhark_context *ctx, struct futhark_f32_3d **out0, const struct futhark_opaque_state *s, uint32_t n,
+                              lys_pass_stats *stats) {                              /* lib.fut:67-74 */
+    if (!ctx) return 1;
+    if (!out0 || !s) { set_error(ctx, "sample_n_frames: null argument"); return 1; }
+    cudaSetDevice(ctx->device);
+    uint32_t gw, gh; grid_dims(s, gw, gh);
+    int64_t shape[3] = {(int64_t)gh, (int64_t)gw, 3};
+    futhark_f32_3d *a = new_array<futhark_f32_3d, float>(ctx, nullptr, shape, 3, cudaMemcpyDeviceToDevice);
+    if (!a) return 1;
+    uint64_t l0 = ctx->launches;
+    if (ctx->world > 1) CU(ctx, cudaMemsetAsync(a->ptr(), 0, sizeof(float) * 3 * (size_t)gw * gh, ctx->stream));
+    if (!ensure_pass_buffers(ctx, (int64_t)gw * gh, false)) { delete a; return 1; }
+    if (stats) CU(ctx, cudaMemsetAsync(ctx->bufs.stats, 0, 4 * sizeof(unsigned long long), ctx->stream));
+    CU(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    uint32_t rng = s->rng; uint32_t n_frames;
+    if (!sample_into(ctx, s, rng, nullptr, a->ptr(), false, 0.0f)) { delete a; return 1; }
+    rng = h_advance_rng(rng); n_frames = 1;
+    while (n_frames < n) {
+        if (!sample_into(ctx, s, rng, a->ptr(), a->ptr(), true, (float)n_frames)) { delete a; return 1; }
+        rng = h_advance_rng(rng); n_frames++;
+    }
+    CU(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    if (stats) {
+        unsigned long long hs[4];
+        CU(ctx, cudaMemcpyAsync(hs, ctx->bufs.stats, sizeof(hs), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        FrameParams fp; make_frame_params(ctx, s, s->rng, 1.0f, fp);
+        stats->paths = (uint64_t)fp.n_local * n_frames; stats->vertices = hs[0]; stats->shadow_rays = hs[2];
+        stats->closest_rays = 0; stats->launches = ctx->launches - l0;
+        cudaEventElapsedTime(&stats->device_ms, ctx->ev0, ctx->ev1);
+    }
+    *out0 = a;
+    return 0;
+}
+int futhark_entry_sample_n_frames(struct futhark_context *ctx, struct futhark_f32_3d **out0, const struct futhark_opaque_state *s, const uint32_t n) {
+    return lys_sample_n_frames_stats(ctx, out0, s, n, nullptr);
+}
+
+int futhark_entry_sample_points_n(struct futhark_context *ctx, struct futhark_opaque_state **out0, struct futhark_f32_3d **out1,
+                                  const struct futhark_opaque_state *s, const uint32_t spp) {       /* lib.fut:35-63 */
+    if (!ctx) return 1;
+    if (!out0 || !out1 || !s) { set_error(ctx, "sample_points_n: null argument"); return 1; }
+    cudaSetDevice(ctx->device);
+    uint32_t gw, gh; grid_dims(s, gw, gh);
+    int64_t np = (int64_t)gw * gh;
+    int64_t shape[3] = {(int64_t)gh, (int64_t)gw, 4};
+    futhark_f32_3d *a = new_array<futhark_f32_3d, float>(ctx, nullptr, shape, 3, cudaMemcpyDeviceToDevice);
+    if (!a) return 1;
+    if (ctx->pts_cap < np) {
+        raw_free(ctx->pts_pos); raw_free(ctx->pts_dist); ctx->pts_cap = 0;
+        if (!raw_alloc(ctx, ctx->pts_pos, (size_t)np) || !raw_alloc(ctx, ctx->pts_dist, (size_t)np)) { delete a; return 1; }
+        ctx->pts_cap = np;
+    }
+    if (!ensure_pass_buffers(ctx, np, false)) { delete a; return 1; }
+    if (ctx->world > 1) { CU(ctx, cudaMemsetAsync(ctx->pts_pos, 0, sizeof(float4) * (size_t)np, ctx->stream)); }
+    float factor = 1 / (float)spp;                                                 /* lib.fut:39 */
+    uint32_t rng = s->rng;
+    uint32_t passes = spp < 1 ? 1 : spp;                                           /* the first pass always runs (lib.fut:52) */
+    for (uint32_t k = 0; k < passes; k++) {
+        FrameParams fp;
+        if (!make_frame_params(ctx, s, rng, factor, fp)) { delete a; return 1; }
+        fp.render_mode = 1;
+        if (!cu_ok(ctx, run_sample_pass(s->scene->d, fp, ctx->bufs, ctx->stream, &ctx->launches), "sample pass") ||
+            !cu_ok(ctx, run_points_merge(fp, ctx->bufs, ctx->pts_pos, ctx->pts_dist, k == 0 ? 1 : 0, ctx->stream, &ctx->launches), "points merge")) { delete a; return 1; }
+        rng = h_advance_rng(rng);
+        if (k + 1 == passes) { if (!cu_ok(ctx, run_points_export(fp, ctx->pts_pos, a->ptr(), ctx->stream, &ctx->launches), "points export")) { delete a; return 1; } }
+    }
+    futhark_opaque_state *r = clone_state(s);
+    r->rng = rng;
+    *out0 = r; *out1 = a;
+    return 0;
+}
+
+/* ================================================================== extensions */
+int lys_context_set_path_len(struct futhark_context *ctx, int path_len) {
+    if (!ctx || path_len < 1 || path_len > LYS_MAX_PATH_LEN) { if (ctx) set_error(ctx, "path_len must be in 1..16"); return 1; }
+    ctx->path_len = path_len; return 0;
+}
+int lys_context_set_refit_mode(struct futhark_context *ctx, int mode) { if (!ctx) return 1; ctx->refit_mode = mode ? 1 : 0; return 0; }
+int lys_context_set_partition(struct futhark_context *ctx, int rank, int world_size) {
+    if (!ctx || world_size < 1 || rank < 0 || rank >= world_size) { if (ctx) set_error(ctx, "bad partition"); return 1; }
+    ctx->rank = rank; ctx->world = world_size; return 0;
+}
+int lys_context_device(struct futhark_context *ctx) { return ctx ? ctx->device : -1; }
+void *lys_context_stream(struct futhark_context *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+uint64_t lys_context_launch_count(struct futhark_context *ctx) { return ctx ? ctx->launches : 0; }
+
+void *lys_device_ptr_f32_3d(struct futhark_context *ctx, struct futhark_f32_3d *arr) { (void)ctx; return arr ? arr->mem->p : nullptr; }
+void *lys_state_image_device_ptr(struct futhark_context *ctx, struct futhark_opaque_state *s, uint32_t *img_h, uint32_t *img_w) {
+    (void)ctx; if (!s) return nullptr;
+    if (img_h) *img_h = s->img_h;
+    if (img_w) *img_w = s->img_w;
+    return s->img->p;
+}
+struct futhark_f32_3d *lys_new_f32_3d_from_device(struct futhark_context *ctx, const void *dev, int64_t d0, int64_t d1, int64_t d2) {
+    int64_t shape[3] = {d0, d1, d2};
+    return new_array<futhark_f32_3d, float>(ctx, (const float *)dev, shape, 3, cudaMemcpyDeviceToDevice);
+}
+struct futhark_u32_1d *lys_new_u32_1d_from_device(struct futhark_context *ctx, const void *dev, int64_t d0) {
+    int64_t shape[1] = {d0};
+    return new_array<futhark_u32_1d, uint32_t>(ctx, (const uint32_t *)dev, shape, 1, cudaMemcpyDeviceToDevice);
+}
+
+int lys_state_info_get(struct futhark_context *ctx, const struct futhark_opaque_state *s, lys_state_info *o) {
+    if (!ctx || !s || !o) return 1;
+    o->dim_w = s->dim_w; o->dim_h = s->dim_h; o->subsampling = s->subsampling; o->rng = s->rng; o->img_h = s->img_h; o->img_w = s->img_w;
+    o->n_frames = s->n_frames; o->cam_conf_id = s->cam_conf_id; o->mode = s->mode ? 1 : 0; o->render_mode = s->render_mode;
+    o->cam_pitch = s->cam.pitch; o->cam_yaw = s->cam.yaw; o->cam_origin[0] = s->cam.origin.x; o->cam_origin[1] = s->cam.origin.y; o->cam_origin[2] = s->cam.origin.z;
+    o->aperture = s->cam.conf.aperture; o->focal_dist = s->cam.conf.focal_dist;
+    memcpy(o->ambience, s->ambience.k, sizeof(o->ambience));
+    o->n_tris = s->scene->d.n_tris; o->n_mats = s->scene->d.n_mats; o->n_lights = s->scene->d.n_lights;
+    return 0;
+}
+int lys_state_image(struct futhark_context *ctx, const struct futhark_opaque_state *s, float *out) {
+    if (!ctx || !s || !out) return 1;
+    CU(ctx, cudaMemcpyAsync(out, s->img->p, sizeof(float) * 3 * (size_t)s->img_h * s->img_w, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+int lys_state_bvh_get(struct futhark_context *ctx, const struct futhark_opaque_state *s, float *bounds6, uint32_t *sorted_morton,
+                      int32_t *sorted_src_index, int32_t *left, int32_t *right, int32_t *parent, float *node_aabb, float *leaf_aabb,
+                      int32_t *node_height) {
+    if (!ctx || !s) return 1;
+    const SceneDev &d = s->scene->d;
+    size_t n = (size_t)d.n_tris, nn = n - 1;
+    auto get = [&](void *dst, const void *src, size_t bytes) -> bool {
+        return !dst || cu_ok(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpy");
+    };
+    std::vector<float4> nb, lb;
+    if (node_aabb) nb.resize(2 * nn);
+    if (leaf_aabb) lb.resize(2 * n);
+    if (!get(bounds6, d.bounds, 24) || !get(sorted_morton, d.morton, 4 * n) || !get(sorted_src_index, d.sorted_idx, 4 * n) ||
+        !get(left, d.left, 4 * nn) || !get(right, d.right, 4 * nn) || !get(parent, d.parent, 4 * nn) || !get(node_height, d.height, 4 * nn) ||
+        !get(node_aabb ? nb.data() : nullptr, d.node_box, 32 * nn) || !get(leaf_aabb ? lb.data() : nullptr, d.leaf_box, 32 * n)) return 1;
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    if (node_aabb) for (size_t i = 0; i < nn; i++) { float *p = node_aabb + 6 * i; p[0] = nb[2 * i].x; p[1] = nb[2 * i].y; p[2] = nb[2 * i].z; p[3] = nb[2 * i + 1].x; p[4] = nb[2 * i + 1].y; p[5] = nb[2 * i + 1].z; }
+    if (leaf_aabb) for (size_t i = 0; i < n; i++) { float *p = leaf_aabb + 6 * i; p[0] = lb[2 * i].x; p[1] = lb[2 * i].y; p[2] = lb[2 * i].z; p[3] = lb[2 * i + 1].x; p[4] = lb[2 * i + 1].y; p[5] = lb[2 * i + 1].z; }
+    return 0;
+}
+int lys_state_light_indices(struct futhark_context *ctx, const struct futhark_opaque_state *s, int32_t *src_index) {
+    if (!ctx || !s || !src_index) return 1;
+    const SceneDev &d = s->scene->d;
+    if (d.n_lights > 0) { CU(ctx, cudaMemcpyAsync(src_index, d.light_src, sizeof(int) * (size_t)d.n_lights, cudaMemcpyDeviceToHost, ctx->stream)); CU(ctx, cudaStreamSynchronize(ctx->stream)); }
+    return 0;
+}
+int lys_state_bvh_rebuild_timed(struct futhark_context *ctx, const struct futhark_opaque_state *s, int reps, float *ms) {
+    if (!ctx || !s || reps < 1) return 1;
+    cudaSetDevice(ctx->device);
+    SceneDev &d = s->scene->d;
+    if (!ensure_scratch(ctx, d.n_tris)) return 1;
+    float total = 0.0f;
+    for (int r = 0; r < reps; r++) {
+        CU(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+        CU(ctx, build_lbvh(d, ctx->scratch, ctx->refit_mode, ctx->stream, &ctx->launches));
+        CU(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        float t = 0.0f; cudaEventElapsedTime(&t, ctx->ev0, ctx->ev1); total += t;
+    }
+    if (ms) *ms = total / (float)reps;
+    return 0;
+}
+
+int lys_probe_primary(struct futhark_context *ctx, const struct futhark_opaque_state *s, int32_t *leaf, int32_t *src_tri, float *t) {
+    if (!ctx || !s || !leaf) return 1;
+    cudaSetDevice(ctx->device);
+    uint32_t gw, gh; grid_dims(s, gw, gh);
+    size_t np = (size_t)gw * gh;
+    if (!ensure_pass_buffers(ctx, (int64_t)np, false)) return 1;
+    FrameParams fp; if (!make_frame_params(ctx, s, s->rng, 1.0f, fp)) return 1;
+    if (ctx->world != 1) { set_error(ctx, "probe requires world_size 1"); return 1; }
+    DevRef dl = dev_alloc(ctx, 4 * np), ds = dev_alloc(ctx, 4 * np), dt = dev_alloc(ctx, 4 * np);
+    if (!dl || !ds || !dt) return 1;
+    CU(ctx, run_primary_probe(s->scene->d, fp, ctx->bufs, (int *)dl->p, (int *)ds->p, (float *)dt->p, ctx->stream, &ctx->launches));
+    CU(ctx, cudaMemcpyAsync(leaf, dl->p, 4 * np, cudaMemcpyDeviceToHost, ctx->stream));
+    if (src_tri) CU(ctx, cudaMemcpyAsync(src_tri, ds->p, 4 * np, cudaMemcpyDeviceToHost, ctx->stream));
+    if (t) CU(ctx, cudaMemcpyAsync(t, dt->p, 4 * np, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+int lys_probe_pass(struct futhark_context *ctx, const struct futhark_opaque_state *s, float *radiance, float *distance, int32_t *channel) {
+    if (!ctx || !s) return 1;
+    cudaSetDevice(ctx->device);
+    uint32_t gw, gh; grid_dims(s, gw, gh);
+    size_t np = (size_t)gw * gh;
+    if (ctx->world != 1) { set_error(ctx, "probe requires world_size 1"); return 1; }
+    if (!ensure_pass_buffers(ctx, (int64_t)np, true)) return 1;
+    FrameParams fp; if (!make_frame_params(ctx, s, s->rng, 1.0f, fp)) return 1;
+    PassBuffers b = ctx->bufs;
+    CU(ctx, run_sample_pass(s->scene->d, fp, b, ctx->stream, &ctx->launches));
+    if (radiance) CU(ctx, cudaMemcpyAsync(radiance, b.probe_rad, 4 * 16 * np, cudaMemcpyDeviceToHost, ctx->stream));
+    if (distance) CU(ctx, cudaMemcpyAsync(distance, b.probe_dist, 4 * 16 * np, cudaMemcpyDeviceToHost, ctx->stream));
+    std::vector<uint8_t> ch;
+    if (channel) { ch.resize(np); CU(ctx, cudaMemcpyAsync(ch.data(), b.chan, np, cudaMemcpyDeviceToHost, ctx->stream)); }
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    if (channel) for (size_t i = 0; i < np; i++) channel[i] = ch[i];
+    /* probes off again for the timed paths */
+    raw_free(ctx->bufs.probe_rad); raw_free(ctx->bufs.probe_dist);
+    return 0;
+}
+static int trace_common(struct futhark_context *ctx, const struct futhark_opaque_state *s, const float *rays, const float *tmax, int64_t n,
+                        int32_t *out_i, float *out_t, int any) {
+    if (!ctx || !s || !rays || !out_i || n < 0) return 1;
+    cudaSetDevice(ctx->device);
+    if (n == 0) return 0;
+    DevRef dr = dev_alloc(ctx, 24 * (size_t)n), dm = dev_alloc(ctx, 4 * (size_t)n), di = dev_alloc(ctx, 4 * (size_t)n), dt = dev_alloc(ctx, 4 * (size_t)n);
+    if (!dr || !dm || !di || !dt) return 1;
+    CU(ctx, cudaMemcpyAsync(dr->p, rays, 24 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    if (tmax) CU(ctx, cudaMemcpyAsync(dm->p, tmax, 4 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, run_trace_rays(s->scene->d, (const float *)dr->p, (const float *)dm->p, n, (int *)di->p, (float *)dt->p, any, ctx->stream, &ctx->launches));
+    CU(ctx, cudaMemcpyAsync(out_i, di->p, 4 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_t) CU(ctx, cudaMemcpyAsync(out_t, dt->p, 4 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+int lys_trace_closest(struct futhark_context *ctx, const struct futhark_opaque_state *s, const float *rays, int64_t n, int32_t *leaf, float *t) {
+    return trace_common(ctx, s, rays, nullptr, n, leaf, t, 0);
+}
+int lys_trace_any(struct futhark_context *ctx, const struct futhark_opaque_state *s, const float *rays, const float *tmax, int64_t n, int32_t *hit) {
+    if (!tmax) return 1;
+    return trace_common(ctx, s, rays, tmax, n, hit, nullptr, 1);
+}
+int lys_eval_math(struct futhark_context *ctx, int fn, const float *in, float *out, int64_t n) {
+    if (!ctx || !in || !out || n < 0) return 1;
+    cudaSetDevice(ctx->device);
+    if (n == 0) return 0;
+    DevRef di = dev_alloc(ctx, 4 * (size_t)n), dout = dev_alloc(ctx, 4 * (size_t)n);
+    if (!di || !dout) return 1;
+    CU(ctx, cudaMemcpyAsync(di->p, in, 4 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, run_eval_math(fn, (const float *)di->p, (float *)dout->p, n, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(out, dout->p, 4 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+int lys_material_probe(struct futhark_context *ctx, const float *mat28, float wavelen, const float *wo, const float *wi, const float *normal,
+                       uint32_t rng, float *out9) {
+    if (!ctx || !mat28 || !wo || !wi || !normal || !out9) return 1;
+    cudaSetDevice(ctx->device);
+    DevRef dm = dev_alloc(ctx, 28 * 4), dout = dev_alloc(ctx, 9 * 4);
+    if (!dm || !dout) return 1;
+    CU(ctx, cudaMemcpyAsync(dm->p, mat28, 28 * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, run_material_probe((const float *)dm->p, wavelen, v3(wo[0], wo[1], wo[2]), v3(wi[0], wi[1], wi[2]), v3(normal[0], normal[1], normal[2]), rng,
+                               (float *)dout->p, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(out9, dout->p, 9 * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+} // extern "C"

@@ -1,0 +1,54 @@
+/* lys_scene.h -- device-resident scene (HBM layout) shared by the build, the wavefront kernels and the ABI.
+ *
+ * All pointers are device pointers.  Layout (n triangles, m materials, L lights):
+ *   tris      [n][9]  f32   input triangles as uploaded (src/scene.fut:26-35)
+ *   tri_mats  [n]     u32
+ *   mats      [m][28] f32   material rows (src/scene.fut:37-53)
+ *   leaf_tri  [n][3]  float4  sorted leaves: (a.xyz | mat_ix), (e1.xyz | source index), (e2.xyz | 0)
+ *   leaf_box  [n][2]  float4  sorted leaf boxes (center | half_dims)
+ *   nodes     [n-1][2] float4 traversal nodes: (min.xyz | left), (max.xyz | right); one 32-byte sector
+ *   node_box  [n-1][2] float4 node boxes as the reference stores them (center | half_dims)
+ *   left/right/parent/height [n-1] i32; child encoding: internal i -> i, leaf i -> ~i
+ *   morton, sorted_idx [n] u32; bounds [6] f32 (center, half_dims)
+ *   lights    [L] LightRec
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace lys {
+
+struct LightRec {            /* 32 floats = 128 B, float4-aligned */
+    float a[3]; float area;                /* vertex a, triangle area (direct.fut:17-20) */
+    float e1[3]; float inv_area;           /* b - a, 1/area (direct.fut:22,42) */
+    float e2[3]; float theta;              /* c - a, frustum half-angle (light.fut:5) */
+    float n[3]; int kind;                  /* triangle_normal (shapes.fut:59-62); 0 diffuse, 1 frustum */
+    float emission[12];                    /* spectrum knots */
+    int src_index; int pad[3];
+};
+
+struct SceneDev {
+    int64_t n_tris = 0, n_mats = 0, n_lights = 0;
+    float *tris = nullptr; uint32_t *tri_mats = nullptr; float *mats = nullptr;
+    float4 *leaf_tri = nullptr, *leaf_box = nullptr, *nodes = nullptr, *node_box = nullptr;
+    int *left = nullptr, *right = nullptr, *parent = nullptr, *height = nullptr;
+    uint32_t *morton = nullptr, *sorted_idx = nullptr;
+    float *bounds = nullptr;
+    LightRec *lights = nullptr;
+    int *light_src = nullptr;
+    float build_ms = 0.0f;
+};
+
+struct BuildScratch {
+    int64_t cap = 0;
+    float4 *box_c = nullptr, *box_h = nullptr, *F = nullptr;
+    uint32_t *keys[2] = {nullptr, nullptr}, *vals[2] = {nullptr, nullptr};
+    uint32_t *rs_hist = nullptr, *rs_status = nullptr;
+    int *leaf_parent = nullptr; unsigned int *visits = nullptr;
+};
+
+cudaError_t build_lbvh(SceneDev &sc, BuildScratch &ws, int refit_mode, cudaStream_t stream, uint64_t *launches);
+/* lights: gathers emissive triangles (indices in input order) into LightRec */
+cudaError_t build_lights(SceneDev &sc, const int *light_src_dev, int n_lights, cudaStream_t stream, uint64_t *launches);
+
+} // namespace lys

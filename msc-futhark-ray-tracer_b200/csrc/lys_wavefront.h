@@ -1,0 +1,79 @@
+/* lys_wavefront.h -- per-pass parameters and work buffers of the wavefront path tracer. */
+#pragma once
+#include "lys_scene.h"
+#include "lys_device.cuh"
+
+namespace lys {
+
+/* Everything that is constant over one sample pass (one `sample_pixels` call, integrator.fut:103-116).
+ * Camera vectors are derived on the host exactly as camera.fut:81-101 does per pixel. */
+struct FrameParams {
+    int gw, gh;                 /* sample grid (integrator.fut:175-176) */
+    float fw, fh;
+    int rank, world;            /* row-interleaved partition */
+    int n_local;                /* pixels sampled by this rank */
+    uint32_t frame_rng;         /* state.rng */
+    V3 cam_origin, llc, horizontal, vertical, cam_u, cam_v;
+    float lens_radius, offset_radius;
+    int n_sensor;
+    float sensor_mu[3], sensor_sigma[3];
+    V3 sensor_vis[3];
+    int tx_kind;                /* 0 none, 1 flash, 2 scanning (camera.fut:30-32) */
+    float tx_radius, tx_theta;
+    float tx_emission[12];
+    float sector_x[9], sector_y[9];   /* rot_z (2*pi/8 * j) (1,0,0), host libm (shapes.fut:20-28) */
+    int n_scene_lights;
+    float ambience[12];
+    int path_len;
+    int render_mode;            /* 0 colour, 1 distance */
+    float intensity_factor;     /* 1, or 1/spp for sample_points_n (lib.fut:39,42) */
+};
+
+/* Work buffers, sized for `cap` paths.  Path state is indexed by path id (= local pixel index),
+ * queues and shadow records by queue slot. */
+struct PassBuffers {
+    int64_t cap = 0;
+    float4 *ray_o = nullptr;    /* origin.xyz | wavelength */
+    float4 *ray_d = nullptr;    /* dir.xyz    | rng state (bits) */
+    float *dist = nullptr;      /* cumulative distance (integrator.fut:54) */
+    float *sum = nullptr;       /* sum of vertex radiance            (integrator.fut:164-168) */
+    float *zsum = nullptr;      /* sum of vertex radiance * 0        (the other two channels)  */
+    float *best_d = nullptr;    /* nearest valid vertex (distance render / point cloud) */
+    float *best_i = nullptr;
+    uint8_t *chan = nullptr;
+    int *queue[2] = {nullptr, nullptr};
+    int *hit = nullptr;         /* per slot: sorted-leaf index or -1 */
+    float4 *sh_o = nullptr;     /* per slot: shadow origin.xyz | flags (bit0 ray1, bit1 ray2) */
+    float4 *sh_d1 = nullptr;    /* dir1.xyz | tmax1 */
+    float4 *sh_d2 = nullptr;    /* dir2.xyz | tmax2 */
+    float4 *sh_c = nullptr;     /* cL, cB, emission (vertex 0), vertex distance */
+    int *counts = nullptr;      /* [LYS_MAX_PATH_LEN + 1] active paths per bounce */
+    unsigned long long *stats = nullptr;   /* [4] vertices, closest rays, shadow rays, paths */
+    LightRec *tx_lights = nullptr;         /* [8] flash transmitter lights */
+    /* probes (optional) */
+    float *probe_rad = nullptr, *probe_dist = nullptr;   /* [cap][16] */
+};
+
+struct PassLaunchStats { uint64_t launches = 0; };
+
+/* one sample pass: generate, (extend, shade, connect) x path_len.  Results stay in bufs (sum, zsum, best_*). */
+cudaError_t run_sample_pass(const SceneDev &sc, const FrameParams &fp, PassBuffers &bufs, cudaStream_t stream, uint64_t *launches);
+/* resolve + merge into the image: mode 0 = replace (sample_frame), 1 = running average (sample_frame_accum) */
+cudaError_t run_accumulate(const FrameParams &fp, const PassBuffers &bufs, const float *img_old, float *img_new,
+                           int merge, float n_frames, cudaStream_t stream, uint64_t *launches);
+/* point cloud: resolve one pass into [gh][gw] (pos.xyz, distance, intensity) and merge (lib.fut:41-59) */
+cudaError_t run_points_merge(const FrameParams &fp, const PassBuffers &bufs, float4 *pos_int, float *dist, int first,
+                             cudaStream_t stream, uint64_t *launches);
+cudaError_t run_points_export(const FrameParams &fp, const float4 *pos_int, float *out, cudaStream_t stream, uint64_t *launches);
+/* render: upscale + pack ARGB (lib.fut:187-196) */
+cudaError_t run_render(const float *img, int img_h, int img_w, int full_h, int full_w, int subsampling, int32_t *out,
+                       cudaStream_t stream, uint64_t *launches);
+/* probes / tools */
+cudaError_t run_primary_probe(const SceneDev &sc, const FrameParams &fp, PassBuffers &bufs, int *leaf, int *src, float *t,
+                              cudaStream_t stream, uint64_t *launches);
+cudaError_t run_trace_rays(const SceneDev &sc, const float *rays, const float *tmax, int64_t n, int *out_leaf, float *out_t,
+                           int any_hit, cudaStream_t stream, uint64_t *launches);
+cudaError_t run_eval_math(int fn, const float *in, float *out, int64_t n, cudaStream_t stream);
+cudaError_t run_material_probe(const float *mat28_dev, float wavelen, V3 wo, V3 wi, V3 n, uint32_t rng, float *out9_dev, cudaStream_t stream);
+
+} // namespace lys

@@ -1,0 +1,557 @@
+/* wavefront.cu -- the sample pass as a wavefront path tracer on sm_100a.
+ *
+ * Replaces the per-pixel megakernel the Futhark compiler generates for `sample_pixels`
+ * (reference src/integrator.fut:103-116, one thread running `path_trace` :27-76 to completion) by
+ * queue-driven stages, one launch per stage and bounce:
+ *   k_generate   camera.fut:68-110, integrator.fut:78-93,109-115   wavelength + primary ray per pixel
+ *   k_extend     bvh.fut:123-145 (closest_hit)                      first hit of every live ray
+ *   k_shade      integrator.fut:46-76, direct.fut:32-122, material.fut   vertex shading; emits <= 2
+ *                                                                   shadow rays, the continuation ray,
+ *                                                                   and compacts live paths (warp ballot)
+ *   k_connect    direct.fut:7-15 + bvh.fut:149-167 (any_hit)        shadow rays, radiance accumulation
+ *   k_accumulate integrator.fut:133-192                             channel resolve + running average
+ *   k_render     lib.fut:187-196                                    upscale + ARGB pack
+ * Per-path arithmetic is the reference's, operation for operation; only the scheduling differs.
+ */
+#include "lys_wavefront.h"
+#include <cstdio>
+
+namespace lys {
+
+#define TRAV_STACK 64      /* delta() is in [0, 63] and strictly grows downwards -> height <= 64 */
+
+/* ------------------------------------------------------------------ BVH traversal
+ * The reference walks the tree without a stack: parent pointers, always left child first, a node's box
+ * tested once on entry against the CURRENT tmax, leaves never box-tested (bvh.fut:126-142).  A depth-first
+ * walk that pushes the right child while descending left takes exactly the same decisions in the same
+ * order, so hits, ties (strict t < tmax, shapes.fut:64) and culling are identical. */
+struct RayInv { V3 o, d, inv; };
+LYS_D bool slab_test(const RayInv &r, float4 lo, float4 hi, float tmax) {               /* hit_aabb shapes.fut:114-135 */
+    float tmin = 0.0f;
+    {
+        float t0 = (lo.x - r.o.x) * r.inv.x, t1 = (hi.x - r.o.x) * r.inv.x;
+        if (r.inv.x < 0.0f) { float s = t0; t0 = t1; t1 = s; }
+        t1 = t1 * (1.0f + 0.001f);
+        tmin = fmaxf(t0, tmin); tmax = fminf(t1, tmax);
+        if (tmax <= tmin) return false;
+    }
+    {
+        float t0 = (lo.y - r.o.y) * r.inv.y, t1 = (hi.y - r.o.y) * r.inv.y;
+        if (r.inv.y < 0.0f) { float s = t0; t0 = t1; t1 = s; }
+        t1 = t1 * (1.0f + 0.001f);
+        tmin = fmaxf(t0, tmin); tmax = fminf(t1, tmax);
+        if (tmax <= tmin) return false;
+    }
+    {
+        float t0 = (lo.z - r.o.z) * r.inv.z, t1 = (hi.z - r.o.z) * r.inv.z;
+        if (r.inv.z < 0.0f) { float s = t0; t0 = t1; t1 = s; }
+        t1 = t1 * (1.0f + 0.001f);
+        tmin = fmaxf(t0, tmin); tmax = fminf(t1, tmax);
+        if (tmax <= tmin) return false;
+    }
+    return true;
+}
+LYS_D bool leaf_test(const RayInv &r, const float4 *__restrict__ leaf_tri, int leaf, float tmax, float &t) {
+    float4 q0 = __ldg(leaf_tri + 3ll * leaf), q1 = __ldg(leaf_tri + 3ll * leaf + 1), q2 = __ldg(leaf_tri + 3ll * leaf + 2);
+    V3 nc;
+    return tri_test(r.o, r.d, v3(q0.x, q0.y, q0.z), v3(q1.x, q1.y, q1.z), v3(q2.x, q2.y, q2.z), tmax, t, nc);
+}
+template <bool ANY>
+LYS_D int traverse(const float4 *__restrict__ nodes, const float4 *__restrict__ leaf_tri, int n_nodes,
+                   V3 o, V3 d, float tmax, float &t_hit) {
+    RayInv r; r.o = o; r.d = d; r.inv = v3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    int stack[TRAV_STACK];
+    int sp = 0;
+    int closest = -1;
+    if (n_nodes <= 0) return -1;
+    int cur = 0;                    /* internal node to enter, or a leaf pointer (< 0) */
+    while (true) {
+        if (cur >= 0) {
+            float4 lo = __ldg(nodes + 2ll * cur), hi = __ldg(nodes + 2ll * cur + 1);
+            if (slab_test(r, lo, hi, tmax)) {
+                stack[sp++] = __float_as_int(hi.w);       /* right child waits */
+                cur = __float_as_int(lo.w);               /* left child first */
+                continue;
+            }
+        } else {
+            float t;
+            if (leaf_test(r, leaf_tri, ~cur, tmax, t)) {
+                closest = ~cur; tmax = t;
+                if (ANY) { t_hit = t; return closest; }
+            }
+        }
+        if (sp == 0) break;
+        cur = stack[--sp];
+    }
+    t_hit = tmax;
+    return closest;
+}
+
+/* ------------------------------------------------------------------ camera: camera.fut:68-110, integrator.fut:85-90 */
+LYS_D void camera_sample(const FrameParams &fp, int col, int row, uint32_t &rng, V3 &o, V3 &d, float &wavelen, int &chan) {
+    uint32_t x = lcg_next(rng);                                   /* random_select' rand.fut:39-42 */
+    chan = (int)(x % (uint32_t)fp.n_sensor);
+    float p = rng_unit(rng);
+    wavelen = fp.sensor_mu[chan] + fp.sensor_sigma[chan] * det_probitf(p);
+    float j = (float)(uint32_t)col;
+    float i = fp.fh - (float)(uint32_t)row - 1.0f;
+    uint32_t r1 = rng;                                            /* camera.fut:86: rng is only peeked */
+    float o0 = rng_unit(r1), o1 = rng_unit(r1);
+    float px = (j + fp.offset_radius * o0) / fp.fw;
+    float py = (i + fp.offset_radius * o1) / fp.fh;
+    uint32_t r2 = rng;                                            /* camera.fut:102: same draws again */
+    V3 dk = rng_unit_disk(r2);
+    V3 lens = fp.lens_radius * dk;
+    V3 lens_offset = lens.x * fp.cam_u + lens.y * fp.cam_v;
+    o = fp.cam_origin + lens_offset;
+    d = normalise(((fp.llc + px * fp.horizontal) + py * fp.vertical) - o);
+}
+LYS_D int local_to_pixel(const FrameParams &fp, int pid, int &col, int &row) {
+    int rl = pid / fp.gw; col = pid - rl * fp.gw; row = rl * fp.world + fp.rank;
+    return row * fp.gw + col;
+}
+
+__global__ void __launch_bounds__(256) k_generate(const __grid_constant__ FrameParams fp, PassBuffers b) {
+    int pid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pid == 0) {
+        b.counts[0] = fp.n_local;
+        for (int k = 1; k <= LYS_MAX_PATH_LEN; k++) b.counts[k] = 0;
+    }
+    if (pid >= fp.n_local) return;
+    int col, row; int ix = local_to_pixel(fp, pid, col, row);
+    uint32_t rng = fp.frame_rng ^ rng_split_hash((uint32_t)ix);   /* split_rng integrator.fut:109-114 */
+    V3 o, d; float wl; int ch;
+    camera_sample(fp, col, row, rng, o, d, wl, ch);
+    b.ray_o[pid] = make_float4(o.x, o.y, o.z, wl);
+    b.ray_d[pid] = make_float4(d.x, d.y, d.z, __uint_as_float(rng));
+    b.dist[pid] = 0.0f; b.sum[pid] = 0.0f; b.zsum[pid] = 0.0f;
+    b.best_d[pid] = LYS_INF; b.best_i[pid] = 0.0f;
+    b.chan[pid] = (uint8_t)ch;
+    b.queue[0][pid] = pid;
+    if (b.probe_rad) for (int k = 0; k < LYS_MAX_PATH_LEN; k++) { b.probe_rad[(size_t)pid * 16 + k] = 0.0f; b.probe_dist[(size_t)pid * 16 + k] = LYS_INF; }
+}
+
+/* ------------------------------------------------------------------ extend: closest hit per live ray */
+__global__ void __launch_bounds__(128) k_extend(SceneDev sc, PassBuffers b, int bounce) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int count = b.counts[bounce];
+    if (i >= count) return;
+    int pid = b.queue[bounce & 1][i];
+    float4 ro = b.ray_o[pid], rd = b.ray_d[pid];
+    float t;
+    b.hit[i] = traverse<false>(sc.nodes, sc.leaf_tri, (int)sc.n_tris - 1, v3(ro.x, ro.y, ro.z), v3(rd.x, rd.y, rd.z), FLT_MAX, t);
+}
+
+/* ------------------------------------------------------------------ lights */
+struct LightD { V3 a, e1, e2, n; float inv_area, theta; int kind; float em[12]; };
+LYS_D void load_light(const LightRec *__restrict__ L, LightD &l) {
+    const float4 *q = reinterpret_cast<const float4 *>(L);
+    float4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2), q3 = __ldg(q + 3);
+    l.a = v3(q0.x, q0.y, q0.z); l.e1 = v3(q1.x, q1.y, q1.z); l.inv_area = q1.w;
+    l.e2 = v3(q2.x, q2.y, q2.z); l.theta = q2.w; l.n = v3(q3.x, q3.y, q3.z); l.kind = __float_as_int(q3.w);
+    float4 e0 = __ldg(q + 4), e1 = __ldg(q + 5), e2 = __ldg(q + 6);
+    l.em[0] = e0.x; l.em[1] = e0.y; l.em[2] = e0.z; l.em[3] = e0.w; l.em[4] = e1.x; l.em[5] = e1.y; l.em[6] = e1.z; l.em[7] = e1.w;
+    l.em[8] = e2.x; l.em[9] = e2.y; l.em[10] = e2.z; l.em[11] = e2.w;
+}
+/* light k of the scanning transmitter for a primary ray direction (camera.fut:119-121, shapes.fut:17-35) */
+LYS_D void scanning_light(const FrameParams &fp, V3 prim_dir, int k, LightD &l) {
+    V3 c = cross(prim_dir, v3(0.0f, 1.0f, 0.0f));
+    V3 right = (norm(c) == 0.0f) ? v3(1.0f, 0.0f, 0.0f) : normalise(c);
+    V3 up = normalise(cross(right, prim_dir));
+    V3 v0 = fp.sector_x[k] * right + fp.sector_y[k] * up;
+    V3 v1 = fp.sector_x[k + 1] * right + fp.sector_y[k + 1] * up;
+    V3 A = fp.cam_origin, B = fp.cam_origin + fp.tx_radius * v1, C = fp.cam_origin + fp.tx_radius * v0;
+    l.a = A; l.e1 = B - A; l.e2 = C - A;
+    V3 nc = cross(l.e1, l.e2);
+    float area = norm(nc) / 2.0f;
+    l.inv_area = 1.0f / area; l.n = normalise(nc); l.theta = fp.tx_theta; l.kind = 1;
+#pragma unroll
+    for (int q = 0; q < 12; q++) l.em[q] = fp.tx_emission[q];
+}
+/* arealight_incident_radiance (light.fut:19-55) */
+LYS_D float incident_radiance(const LightD &l, V3 hitp, V3 lightp, float wavelen) {
+    V3 v = lightp - hitp;
+    V3 wi = normalise(v);
+    float d2 = quadrance(v);
+    float cl = dot(-wi, l.n);
+    float E = spectrum_lookup12(wavelen, l.em);
+    if (l.kind == 0) return lys_fmaxf(0.0f, E * cl / d2);
+    return (det_acosf(cl) <= l.theta) ? E / d2 : 0.0f;
+}
+LYS_D float balance1(float pf, float pg) { return 1.0f * pf / (1.0f * pf + 1.0f * pg); }   /* direct.fut:56-58, nf = ng = 1 */
+
+/* ------------------------------------------------------------------ shade */
+__global__ void __launch_bounds__(128) k_shade(SceneDev sc, const __grid_constant__ FrameParams fp, PassBuffers b, int bounce) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int count = b.counts[bounce];
+    bool alive = false;
+    int pid = -1;
+    unsigned n_vert = 0, n_shadow = 0;
+    if (i < count) {
+        pid = b.queue[bounce & 1][i];
+        float4 ro4 = b.ray_o[pid], rd4 = b.ray_d[pid];
+        V3 o = v3(ro4.x, ro4.y, ro4.z), d = v3(rd4.x, rd4.y, rd4.z);
+        float wavelen = ro4.w;
+        uint32_t rng = __float_as_uint(rd4.w);
+        int leaf = b.hit[i];
+        float4 rec_o = make_float4(0.0f, 0.0f, 0.0f, 0.0f), rec_d1 = rec_o, rec_d2 = rec_o, rec_c = rec_o;
+        if (leaf < 0) {
+            /* integrator.fut:76: the path ends on the ambience */
+            float amb = spectrum_lookup12(wavelen, fp.ambience);
+            rec_c = make_float4(0.0f, 0.0f, amb, LYS_INF);
+            rec_o.w = __int_as_float(4);       /* bit 2: miss vertex, radiance = rec_c.z */
+        } else {
+            n_vert = 1;
+            float4 q0 = __ldg(sc.leaf_tri + 3ll * leaf), q1 = __ldg(sc.leaf_tri + 3ll * leaf + 1), q2 = __ldg(sc.leaf_tri + 3ll * leaf + 2);
+            V3 ta = v3(q0.x, q0.y, q0.z), te1 = v3(q1.x, q1.y, q1.z), te2 = v3(q2.x, q2.y, q2.z);
+            const float *mrow = sc.mats + 28ll * (int)__float_as_uint(q0.w);
+            float t; V3 nc;
+            (void)tri_test(o, d, ta, te1, te2, FLT_MAX, t, nc);           /* bvh.fut:143-145 re-intersection */
+            V3 pos = o + t * d;
+            V3 n = normalise(nc);
+            rng_advance(rng);                                             /* integrator.fut:48 */
+            V3 wo = -d;
+            Onb onb = make_onb(n);
+            Mat1 m = material_at(mrow, wavelen);
+            V3 wo_l = to_local(onb, wo);
+            const int n_extra = (fp.tx_kind == 0) ? 0 : 8;
+            const int nl = fp.n_scene_lights + n_extra;
+            float cL = 0.0f, cB = 0.0f;
+            int flags = 0;
+            V3 so = pos + 0.001f * n;       /* mkray_adjust_acne with dot(w, n) > 0: same_side = 1 * n */
+            if (nl > 0) {                                                  /* direct.fut:116-122 */
+                uint32_t pick = lcg_next(rng) % (uint32_t)nl;
+                LightD l;
+                if ((int)pick < fp.n_scene_lights) load_light(sc.lights + pick, l);
+                else if (fp.tx_kind == 1) load_light(b.tx_lights + (pick - fp.n_scene_lights), l);
+                else {
+                    int col, row; int ix = local_to_pixel(fp, pid, col, row);
+                    uint32_t r0 = fp.frame_rng ^ rng_split_hash((uint32_t)ix);
+                    V3 po, pd; float pw; int pc;
+                    camera_sample(fp, col, row, r0, po, pd, pw, pc);
+                    scanning_light(fp, pd, (int)pick - fp.n_scene_lights, l);
+                }
+                /* light sample: sample_arealight peeks two draws (direct.fut:38,42) */
+                {
+                    uint32_t pk = rng;
+                    float u0 = rng_unit(pk), u1 = rng_unit(pk);
+                    float su = sqrtf(u0);
+                    float lu = 1.0f - su, lv = u1 * su;                    /* rand.fut:34-37 */
+                    V3 p = (l.a + lu * l.e1) + lv * l.e2;
+                    V3 vv = p - pos;
+                    V3 wi = normalise(vv);
+                    float in_rad = incident_radiance(l, pos, p, wavelen);
+                    float pdf = l.inv_area;
+                    bool facing = !(dot(wi, n) <= 0.0f);                   /* direct.fut:12 */
+                    if (facing && !(pdf == 0.0f || in_rad == 0.0f)) {      /* direct.fut:51-53,73-74 */
+                        float f, spdf;
+                        uber_eval(wo_l, to_local(onb, wi), m, f, spdf);
+                        f = f * lys_fabsf(dot(wi, n));
+                        float weight = balance1(pdf, spdf);
+                        cL = f * weight * in_rad / pdf;
+                        V3 sd = normalise(wi);
+                        rec_d1 = make_float4(sd.x, sd.y, sd.z, norm(vv) - 0.01f);
+                        flags |= 1;
+                    }
+                }
+                /* BSDF sample towards the same light (direct.fut:83-102) */
+                {
+                    DirSample s = sample_bsdf(wo, onb, m, rng);
+                    V3 bo, bd; ray_from_hit(pos, n, s.wi, bo, bd);
+                    float tl; V3 ncl;
+                    if (tri_test(bo, bd, l.a, l.e1, l.e2, FLT_MAX, tl, ncl)) {
+                        V3 lp = bo + tl * bd;
+                        V3 vv = lp - pos;
+                        V3 w = normalise(vv);
+                        if (!(dot(w, n) <= 0.0f) && s.kind != PDF_IMPOSSIBLE) {
+                            float in_rad = incident_radiance(l, pos, lp, wavelen);
+                            float f = s.bsdf * lys_fabsf(dot(s.wi, n));
+                            if (s.kind == PDF_DELTA) cB = f * in_rad;
+                            else { float weight = balance1(s.pdf, l.inv_area); cB = f * in_rad * weight / s.pdf; }
+                            V3 sd = normalise(w);
+                            rec_d2 = make_float4(sd.x, sd.y, sd.z, norm(vv) - 0.01f);
+                            flags |= 2;
+                        }
+                    }
+                }
+            }
+            float em = (bounce == 0) ? spectrum_lookup12(wavelen, mrow + 16) : 0.0f;   /* integrator.fut:51-53 */
+            float dist = b.dist[pid] + t;                                               /* :54 */
+            b.dist[pid] = dist;
+            rec_o = make_float4(so.x, so.y, so.z, __int_as_float(flags));
+            rec_c = make_float4(cL, cB, em, dist);
+            n_shadow = (flags & 1) + ((flags >> 1) & 1);
+            /* continuation (integrator.fut:56-75) */
+            DirSample s = sample_bsdf(wo, onb, m, rng);
+            float pdf = (s.kind == PDF_IMPOSSIBLE) ? 0.0f : ((s.kind == PDF_DELTA) ? 1.0f : s.pdf);
+            float cosf = lys_fabsf(dot(n, s.wi));
+            float p_term = 1.0f - s.bsdf * cosf / pdf;
+            bool terminate = rng_unit(rng) < p_term;
+            if (!(pdf == 0.0f || terminate) && bounce + 1 < fp.path_len) {
+                V3 no, nd; ray_from_hit(pos, n, s.wi, no, nd);
+                b.ray_o[pid] = make_float4(no.x, no.y, no.z, wavelen);
+                b.ray_d[pid] = make_float4(nd.x, nd.y, nd.z, __uint_as_float(rng));
+                alive = true;
+            }
+        }
+        b.sh_o[i] = rec_o; b.sh_d1[i] = rec_d1; b.sh_d2[i] = rec_d2; b.sh_c[i] = rec_c;
+    }
+    /* compaction of live paths: warp ballot + prefix popcount, one atomic per warp */
+    unsigned mask = __ballot_sync(0xffffffffu, alive);
+    int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == 0 && mask) base = atomicAdd(&b.counts[bounce + 1], __popc(mask));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (alive) b.queue[(bounce + 1) & 1][base + __popc(mask & ((1u << lane) - 1u))] = pid;
+    /* statistics */
+    unsigned vsum = __reduce_add_sync(0xffffffffu, n_vert), ssum = __reduce_add_sync(0xffffffffu, n_shadow);
+    if (lane == 0 && (vsum | ssum)) { atomicAdd(&b.stats[0], (unsigned long long)vsum); atomicAdd(&b.stats[2], (unsigned long long)ssum); }
+}
+
+/* ------------------------------------------------------------------ connect: shadow rays + accumulation */
+__global__ void __launch_bounds__(128) k_connect(SceneDev sc, const __grid_constant__ FrameParams fp, PassBuffers b, int bounce) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= b.counts[bounce]) return;
+    int pid = b.queue[bounce & 1][i];
+    float4 ro = b.sh_o[i], rc = b.sh_c[i];
+    int flags = __float_as_int(ro.w);
+    float r, dist = rc.w;
+    if (flags & 4) r = rc.z;                        /* miss vertex: {inf, ambience} */
+    else {
+        float L = 0.0f, B = 0.0f;
+        V3 o = v3(ro.x, ro.y, ro.z);
+        const int n_nodes = (int)sc.n_tris - 1;
+        if (flags & 1) {
+            float4 d1 = b.sh_d1[i]; float t;
+            if (traverse<true>(sc.nodes, sc.leaf_tri, n_nodes, o, v3(d1.x, d1.y, d1.z), d1.w, t) < 0) L = rc.x;
+        }
+        if (flags & 2) {
+            float4 d2 = b.sh_d2[i]; float t;
+            if (traverse<true>(sc.nodes, sc.leaf_tri, n_nodes, o, v3(d2.x, d2.y, d2.z), d2.w, t) < 0) B = rc.y;
+        }
+        const int nl = fp.n_scene_lights + ((fp.tx_kind == 0) ? 0 : 8);
+        float direct = 0.0f;
+        if (nl > 0) { float light_pdf = 1.0f / (float)nl; direct = (L + B) / light_pdf; }   /* direct.fut:121-122 */
+        r = direct + ((bounce == 0) ? rc.z : 0.0f);                                        /* integrator.fut:51-53 */
+    }
+    b.sum[pid] = b.sum[pid] + r * 1.0f;
+    b.zsum[pid] = b.zsum[pid] + r * 0.0f;
+    float inten = r * fp.intensity_factor;
+    if (inten > 0.0f && dist > 0.5f && dist < 10.0f && dist < b.best_d[pid]) { b.best_d[pid] = dist; b.best_i[pid] = inten; }
+    if (b.probe_rad) { b.probe_rad[(size_t)pid * 16 + bounce] = r; b.probe_dist[(size_t)pid * 16 + bounce] = dist; }
+}
+
+/* ------------------------------------------------------------------ resolve + accumulate */
+LYS_D V3 hue_to_rgb(float h) {                                       /* integrator.fut:139-148 */
+    float hp = h * 6.0f;
+    float x = 1.0f - lys_fabsf(fmodf(hp, 2.0f) - 1.0f);
+    switch (trunc_u32(hp)) {
+        case 0: return v3(1.0f, x, 0.0f); case 1: return v3(x, 1.0f, 0.0f); case 2: return v3(0.0f, 1.0f, x);
+        case 3: return v3(0.0f, x, 1.0f); case 4: return v3(x, 0.0f, 1.0f); default: return v3(1.0f, 0.0f, x);
+    }
+}
+LYS_D V3 resolve_pixel(const FrameParams &fp, const PassBuffers &b, int pid) {   /* visualize integrator.fut:150-168 */
+    if (fp.render_mode == 1) {
+        float bd = b.best_d[pid];
+        if (lys_isinff(bd)) return v3(0.0f, 0.0f, 0.0f);
+        return hue_to_rgb(0.85f * (bd - 0.5f) / (10.0f - 0.5f));
+    }
+    V3 vis = fp.sensor_vis[b.chan[pid]];
+    float s = b.sum[pid], z = b.zsum[pid];
+    float k = (float)fp.n_sensor;
+    return v3(k * (vis.x == 1.0f ? s : z), k * (vis.y == 1.0f ? s : z), k * (vis.z == 1.0f ? s : z));
+}
+__global__ void __launch_bounds__(256) k_accumulate(const __grid_constant__ FrameParams fp, PassBuffers b, const float *__restrict__ img_old,
+                                                    float *__restrict__ img_new, int merge, float n_frames) {
+    int pid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pid >= fp.n_local) return;
+    int col, row; int ix = local_to_pixel(fp, pid, col, row);
+    V3 c = resolve_pixel(fp, b, pid);
+    if (merge) {                                                      /* sample_frame_accum :180-192 */
+        V3 acc = v3(img_old[3ll * ix], img_old[3ll * ix + 1], img_old[3ll * ix + 2]);
+        if (fp.render_mode == 1) c = (norm(acc) > 0.0f) ? acc : c;
+        else c = ((n_frames - 1.0f) / n_frames) * acc + (1.0f / n_frames) * c;
+    }
+    img_new[3ll * ix] = c.x; img_new[3ll * ix + 1] = c.y; img_new[3ll * ix + 2] = c.z;
+}
+
+/* ------------------------------------------------------------------ point cloud (lib.fut:35-63) */
+__global__ void __launch_bounds__(256) k_points_merge(const __grid_constant__ FrameParams fp, PassBuffers b, float4 *__restrict__ pos_int,
+                                                      float *__restrict__ pdist, int first) {
+    int pid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pid >= fp.n_local) return;
+    int col, row; int ix = local_to_pixel(fp, pid, col, row);
+    float bd = b.best_d[pid];
+    float4 p2 = make_float4(-1.0f, -1.0f, -1.0f, 0.0f); float d2 = LYS_INF;     /* lib.fut:47 */
+    if (!lys_isinff(bd)) {
+        uint32_t r0 = fp.frame_rng ^ rng_split_hash((uint32_t)ix);
+        V3 o, d; float w; int c;
+        camera_sample(fp, col, row, r0, o, d, w, c);
+        V3 pp = o + bd * d;                                                      /* to_cloud_points integrator.fut:122-126 */
+        p2 = make_float4(pp.x, pp.y, pp.z, b.best_i[pid]); d2 = bd;
+    }
+    if (first || !(pdist[ix] < d2)) { pos_int[ix] = p2; pdist[ix] = d2; }        /* merge lib.fut:48-51 */
+}
+__global__ void k_points_export(int n, const float4 *__restrict__ pos_int, float4 *__restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = pos_int[i];
+}
+
+/* ------------------------------------------------------------------ render (lib.fut:187-196, matte argb.from_rgba) */
+LYS_D uint32_t chan8(float x) { float c = (x < 0.0f) ? 0.0f : ((x > 1.0f) ? 1.0f : x); return trunc_u32(c * 255.0f); }
+__global__ void __launch_bounds__(256) k_render(const float *__restrict__ img, int img_h, int img_w, int full_h, int full_w, int sub,
+                                                int32_t *__restrict__ out) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= full_h * full_w) return;
+    int i = k / full_w, j = k - i * full_w;
+    int ii = i / sub, jj = j / sub;
+    float r = 0.0f, g = 0.0f, bl = 0.0f;
+    if (ii < img_h && jj < img_w) { const float *p = img + 3ll * ((long long)ii * img_w + jj); r = p[0]; g = p[1]; bl = p[2]; }
+    out[k] = (int32_t)((chan8(1.0f) << 24) | (chan8(r) << 16) | (chan8(g) << 8) | chan8(bl));
+}
+
+/* ------------------------------------------------------------------ probes / tools */
+__global__ void k_primary_probe(SceneDev sc, PassBuffers b, int n, int *leaf, int *src, float *t) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 ro = b.ray_o[i], rd = b.ray_d[i];
+    float th;
+    int l = traverse<false>(sc.nodes, sc.leaf_tri, (int)sc.n_tris - 1, v3(ro.x, ro.y, ro.z), v3(rd.x, rd.y, rd.z), FLT_MAX, th);
+    leaf[i] = l;
+    if (src) src[i] = (l < 0) ? -1 : (int)__float_as_uint(sc.leaf_tri[3ll * l + 1].w);
+    if (t) t[i] = (l < 0) ? LYS_INF : th;
+}
+__global__ void k_trace_rays(SceneDev sc, const float *__restrict__ rays, const float *__restrict__ tmax, long long n,
+                             int *out_leaf, float *out_t, int any) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float *r = rays + 6 * i;
+    V3 o = v3(r[0], r[1], r[2]), d = v3(r[3], r[4], r[5]);
+    float th; int l;
+    if (any) l = traverse<true>(sc.nodes, sc.leaf_tri, (int)sc.n_tris - 1, o, d, tmax[i], th);
+    else l = traverse<false>(sc.nodes, sc.leaf_tri, (int)sc.n_tris - 1, o, d, FLT_MAX, th);
+    out_leaf[i] = any ? (l >= 0 ? 1 : 0) : l;
+    if (out_t) out_t[i] = (l < 0) ? LYS_INF : th;
+}
+__global__ void k_eval_math(int fn, const float *__restrict__ in, float *__restrict__ out, long long n) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float x = in[i], y;
+    switch (fn) {
+        case 0: y = det_sinf(x); break; case 1: y = det_cosf(x); break; case 2: y = det_expf(x); break;
+        case 3: y = det_logf(x); break; case 4: y = det_pow5f(x); break; case 5: y = det_acosf(x); break;
+        case 6: y = det_probitf(x); break; default: y = 0.0f;
+    }
+    out[i] = y;
+}
+__global__ void k_material_probe(const float *mat28, float wavelen, V3 wo, V3 wi, V3 n, uint32_t rng, float *out) {
+    Onb onb = make_onb(n);
+    Mat1 m = material_at(mat28, wavelen);
+    float f, pdf;
+    uber_eval(to_local(onb, wo), to_local(onb, wi), m, f, pdf);
+    out[0] = f; out[1] = pdf;
+    DirSample s = sample_bsdf(wo, onb, m, rng);
+    out[2] = s.wi.x; out[3] = s.wi.y; out[4] = s.wi.z; out[5] = s.bsdf; out[6] = (float)s.kind; out[7] = s.pdf;
+    out[8] = __uint_as_float(rng);
+}
+
+/* ------------------------------------------------------------------ host launchers */
+static inline int cdiv(long long a, int b) { return (int)((a + b - 1) / b); }
+
+cudaError_t run_sample_pass(const SceneDev &sc, const FrameParams &fp, PassBuffers &bufs, cudaStream_t stream, uint64_t *launches) {
+    const int n = fp.n_local;
+    if (n <= 0) return cudaSuccess;
+    uint64_t nl = 0;
+    k_generate<<<cdiv(n, 256), 256, 0, stream>>>(fp, bufs); nl++;
+    for (int bnc = 0; bnc < fp.path_len; bnc++) {
+        k_extend<<<cdiv(n, 128), 128, 0, stream>>>(sc, bufs, bnc); nl++;
+        k_shade<<<cdiv(n, 128), 128, 0, stream>>>(sc, fp, bufs, bnc); nl++;
+        k_connect<<<cdiv(n, 128), 128, 0, stream>>>(sc, fp, bufs, bnc); nl++;
+    }
+    if (launches) *launches += nl;
+    return cudaGetLastError();
+}
+cudaError_t run_accumulate(const FrameParams &fp, const PassBuffers &bufs, const float *img_old, float *img_new, int merge,
+                           float n_frames, cudaStream_t stream, uint64_t *launches) {
+    if (fp.n_local <= 0) return cudaSuccess;
+    k_accumulate<<<cdiv(fp.n_local, 256), 256, 0, stream>>>(fp, bufs, img_old, img_new, merge, n_frames);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+cudaError_t run_points_merge(const FrameParams &fp, const PassBuffers &bufs, float4 *pos_int, float *dist, int first,
+                             cudaStream_t stream, uint64_t *launches) {
+    if (fp.n_local <= 0) return cudaSuccess;
+    k_points_merge<<<cdiv(fp.n_local, 256), 256, 0, stream>>>(fp, bufs, pos_int, dist, first);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+cudaError_t run_points_export(const FrameParams &fp, const float4 *pos_int, float *out, cudaStream_t stream, uint64_t *launches) {
+    int n = fp.gw * fp.gh;
+    k_points_export<<<cdiv(n, 256), 256, 0, stream>>>(n, pos_int, reinterpret_cast<float4 *>(out));
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+cudaError_t run_render(const float *img, int img_h, int img_w, int full_h, int full_w, int subsampling, int32_t *out,
+                       cudaStream_t stream, uint64_t *launches) {
+    long long n = (long long)full_h * full_w;
+    if (n <= 0) return cudaSuccess;
+    k_render<<<cdiv(n, 256), 256, 0, stream>>>(img, img_h, img_w, full_h, full_w, subsampling, out);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+cudaError_t run_primary_probe(const SceneDev &sc, const FrameParams &fp, PassBuffers &bufs, int *leaf, int *src, float *t,
+                              cudaStream_t stream, uint64_t *launches) {
+    const int n = fp.n_local;
+    if (n <= 0) return cudaSuccess;
+    k_generate<<<cdiv(n, 256), 256, 0, stream>>>(fp, bufs);
+    k_primary_probe<<<cdiv(n, 128), 128, 0, stream>>>(sc, bufs, n, leaf, src, t);
+    if (launches) *launches += 2;
+    return cudaGetLastError();
+}
+cudaError_t run_trace_rays(const SceneDev &sc, const float *rays, const float *tmax, int64_t n, int *out_leaf, float *out_t,
+                           int any_hit, cudaStream_t stream, uint64_t *launches) {
+    if (n <= 0) return cudaSuccess;
+    k_trace_rays<<<cdiv(n, 128), 128, 0, stream>>>(sc, rays, tmax, n, out_leaf, out_t, any_hit);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+cudaError_t run_eval_math(int fn, const float *in, float *out, int64_t n, cudaStream_t stream) {
+    if (n <= 0) return cudaSuccess;
+    k_eval_math<<<cdiv(n, 256), 256, 0, stream>>>(fn, in, out, n);
+    return cudaGetLastError();
+}
+cudaError_t run_material_probe(const float *mat28_dev, float wavelen, V3 wo, V3 wi, V3 n, uint32_t rng, float *out9_dev, cudaStream_t stream) {
+    k_material_probe<<<1, 1, 0, stream>>>(mat28_dev, wavelen, wo, wi, n, rng, out9_dev);
+    return cudaGetLastError();
+}
+
+/* ------------------------------------------------------------------ lights (scene.fut:58-66) */
+__global__ void k_build_lights(const float *__restrict__ tris, const uint32_t *__restrict__ tri_mats, const float *__restrict__ mats,
+                               const int *__restrict__ src, int n_lights, LightRec *__restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_lights) return;
+    int s = src[i];
+    const float *t = tris + 9ll * s;
+    V3 a = v3(t[0], t[1], t[2]), bb = v3(t[3], t[4], t[5]), c = v3(t[6], t[7], t[8]);
+    V3 e1 = bb - a, e2 = c - a;
+    V3 nc = cross(e1, e2);
+    float area = norm(nc) / 2.0f;                       /* direct.fut:17-20,37 */
+    V3 n = normalise(nc);                               /* triangle_normal shapes.fut:59-62 */
+    LightRec r;
+    r.a[0] = a.x; r.a[1] = a.y; r.a[2] = a.z; r.area = area;
+    r.e1[0] = e1.x; r.e1[1] = e1.y; r.e1[2] = e1.z; r.inv_area = 1.0f / area;
+    r.e2[0] = e2.x; r.e2[1] = e2.y; r.e2[2] = e2.z; r.theta = 0.0f;
+    r.n[0] = n.x; r.n[1] = n.y; r.n[2] = n.z; r.kind = 0;
+    const float *em = mats + 28ll * tri_mats[s] + 16;
+    for (int k = 0; k < 12; k++) r.emission[k] = em[k];
+    r.src_index = s; r.pad[0] = r.pad[1] = r.pad[2] = 0;
+    out[i] = r;
+}
+cudaError_t build_lights(SceneDev &sc, const int *light_src_dev, int n_lights, cudaStream_t stream, uint64_t *launches) {
+    if (n_lights <= 0) return cudaSuccess;
+    k_build_lights<<<cdiv(n_lights, 128), 128, 0, stream>>>(sc.tris, sc.tri_mats, sc.mats, light_src_dev, n_lights, sc.lights);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+} // namespace lys
