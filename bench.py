@@ -1,0 +1,300 @@
+#!/usr/bin/env python
+"""bench.py -- Mpaths/s of the sample/accumulate hot path (BASELINE.json metric) on N B200s.
+
+Workload (config.workload): assets/CornellBox-Original (44 triangles) at 1920x1080, 1 sample per pixel per pass,
+path length 16 (the reference constant), cam_conf_id 0, seed 0, camera (0,0.8,1.8) -- the configuration the
+metric is quoted on.  One STEP = one futhark_entry_sample_n_frames(state, PASSES) call = PASSES sample passes
+accumulated on the device.  A path = one pixel sample (one `sample_pixel`, integrator.fut:78-101).
+
+  value      paths/s with the state (scene + BVH) resident in HBM and the result left on the device.
+  e2e        the same through the C ABI from HOST buffers: futhark_new_* (H2D of the triangle / material arrays),
+             futhark_entry_init (LBVH build), futhark_entry_sample_n_frames, futhark_values_f32_3d (D2H framebuffer),
+             every step, inside the timed region.
+  roofline   dominant kernel class (closest-hit `k_extend`), device time from CUDA events recorded by the
+             library around every launch (separate profiling step), algorithmic bytes from the oracle's
+             counters for the same workload: 32 B per box test + 40 B per triangle test.
+  cpu_baseline  the CPU restatement of the reference (oracle/, OpenMP over pixel rows) on a bounded sample.
+
+N > 1 (torchrun): one process per GPU, scene replicated, each rank renders its own PASSES passes of the full
+frame (disjoint pass ranges of one N*PASSES-pass render), one NCCL sum-reduce of the framebuffer to rank 0 per
+step inside the timed region; per-GPU work is fixed, so "scaling" is "weak".
+
+--impl reference: times the oracle (the reference itself cannot be built here: no futhark compiler, Futhark
+packages not vendored) on the host cores for the same metric/config, one pass per step.
+"""
+import argparse
+import importlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H, PASSES = 1920, 1080, 16
+SCENE = 'cornell'
+WORKLOAD = 'CornellBox-Original 44 tris, 1920x1080, 1 spp/pass, path_len 16, %d passes/step' % PASSES
+
+
+def load_scene(name=SCENE):
+    d = np.load(os.path.join(ROOT, 'tests', 'golden', 'scenes', name + '.npz'))
+    return d['tris'], d['tri_mats'], d['mats']
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        return float(json.load(open(p))['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+            'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q, '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(',')])
+
+    def stop(self):
+        if not self.proc:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        self.th.join(timeout=2)
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace('.', '').isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace('.', '').isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith('active')})
+        return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': max(mx) if mx else None, 'reasons': reasons,
+                'samples': len(sm)}
+
+
+def cpu_baseline(oracle, scene, passes, threads=0):
+    """Oracle Mpaths/s on the host cores + work counters for the algorithmic-bytes figure (bounded sample)."""
+    t, tm, m = scene
+    oracle.set_threads(threads)
+    s = oracle.State.init(t, tm, m, H, W)
+    oracle.counters_reset()
+    t0 = time.perf_counter()
+    s.sample_n_frames(passes)
+    dt = time.perf_counter() - t0
+    c = oracle.counters()
+    return {'value': W * H * passes / dt / 1e6, 'unit': 'Mpaths/s', 'cores': oracle.get_threads(), 'kind': 'port',
+            'sample': '%d pass(es) of the same 1920x1080 CornellBox workload (%.1f s of CPU work)' % (passes, dt)}, c
+
+
+def run_reference(args):
+    """--impl reference: the CPU restatement timed on the host cores (rank 0 only)."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    from lysref import oracle
+    t, tm, m = load_scene()
+    oracle.set_threads(0)
+    s = oracle.State.init(t, tm, m, H, W)
+    for _ in range(args.warmup):
+        s.sample_n_frames(1)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        s.sample_n_frames(1)
+    dt = time.perf_counter() - t0
+    v = W * H * args.steps / dt / 1e6
+    line = {'impl': 'reference', 'metric': 'Mpaths/s', 'value': v, 'unit': 'Mpaths/s', 'n_gpus': args.gpus, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': dt / args.steps * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32', 'data': 'bundled scene arrays (tests/golden/scenes/cornell.npz), synthetic camera path',
+            'config': {'workload': 'CornellBox-Original 44 tris, 1920x1080, 1 spp/pass, path_len 16, 1 pass/step (bounded sample)'},
+            'cpu_baseline': {'value': v, 'unit': 'Mpaths/s', 'cores': oracle.get_threads(), 'kind': 'port',
+                             'sample': 'CPU restatement of the reference (oracle/), OpenMP over pixel rows; 1 pass of 1920x1080 per step'},
+            'e2e': {'value': v, 'unit': 'Mpaths/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200')
+    ap.add_argument('--cpu-passes', type=int, default=2, help='passes of the CPU baseline sample')
+    ap.add_argument('--no-cpu', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != 'reference' else args.warmup
+    if args.impl == 'reference':
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    pkg = importlib.import_module('msc-futhark-ray-tracer_b200')
+    par = importlib.import_module('msc-futhark-ray-tracer_b200.parallel')
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device; the product has no CPU path')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', rank=rank, world_size=world, device_id=dev)
+    if not os.path.exists(pkg.lib_path()):
+        pkg.build()
+
+    t, tm, m = load_scene()
+    ctx = pkg.Context(device=local)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    base = pkg.State.init(ctx, t, tm, m, H, W)
+    state = base.advance_rng(rank * PASSES) if world > 1 else base      # disjoint pass ranges per rank
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def step_resident():
+        h, ptr, shape, _ = state.sample_n_frames_device(PASSES, want_stats=False)
+        if world > 1:
+            with torch.cuda.stream(stream):
+                par.reduce_framebuffer(par.as_torch(ptr, shape, dev), dst=0)
+        return h
+
+    # ---- value: state resident in HBM, result left on the device ------------------------------------------
+    for _ in range(args.warmup):
+        state.free_f32_3d(step_resident())
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = ctx.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    handles = [step_resident() for _ in range(args.steps)]
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = ctx.launches - l0
+    clocks = sampler.stop() if rank == 0 else None
+    for h in handles:
+        state.free_f32_3d(h)
+    tms = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms = float(tms.item())
+    paths_per_step = W * H * PASSES * world
+    value = paths_per_step * args.steps / (ms * 1e-3) / 1e6
+
+    # ---- e2e: host buffers through the C ABI, every step -------------------------------------------------
+    pin = [torch.from_numpy(a.copy()).pin_memory() for a in (t.reshape(-1), tm.view(np.int32), m.reshape(-1))]
+    host = (pin[0].numpy().reshape(-1, 3, 3), pin[1].numpy().view(np.uint32), pin[2].numpy().reshape(-1, 28))
+    out_pin = torch.empty((H, W, 3), dtype=torch.float32).pin_memory()
+
+    def step_e2e():
+        s = pkg.State.init(ctx, host[0], host[1], host[2], H, W)        # futhark_new_* (H2D) + futhark_entry_init
+        if world > 1:
+            s2 = s.advance_rng(rank * PASSES)
+            s.free()
+            s = s2
+        hnd, ptr, shape, _ = s.sample_n_frames_device(PASSES, want_stats=False)
+        if world > 1:
+            with torch.cuda.stream(stream):
+                par.reduce_framebuffer(par.as_torch(ptr, shape, dev), dst=0)
+        if rank == 0:
+            ctx.check(ctx._L.futhark_values_f32_3d(ctx._ctx, hnd, out_pin.data_ptr()), 'futhark_values_f32_3d')   # blocking D2H
+        else:
+            ctx.sync()
+        s.free_f32_3d(hnd)
+        s.free()
+
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    barrier()
+    dt = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    e2e_value = paths_per_step * args.steps / float(dt.item()) / 1e6
+    h2d = int(t.nbytes + tm.nbytes + m.nbytes + 12)
+    d2h = int(H * W * 3 * 4)
+
+    line = None
+    if rank == 0:
+        # ---- roofline: kernel-class device time (library events) + oracle counters -------------------------
+        ctx.set_profiling(True)
+        ctx.profile(reset=True)
+        hnd = step_resident() if world == 1 else state.sample_n_frames_device(PASSES, want_stats=False)[0]
+        prof = ctx.profile(reset=True)
+        ctx.set_profiling(False)
+        state.free_f32_3d(hnd)
+        build_ms = base.bvh_rebuild_ms(5)
+        build_1m = None
+        if world == 1:
+            st, sm = pkg.scenes.synthetic_cornell(t, tm, 151)           # BASELINE config 5: 1 003 244 triangles
+            big = pkg.State.init(ctx, st, sm, m, 64, 64)
+            big.bvh_rebuild_ms(2)
+            build_1m = big.bvh_rebuild_ms(10)
+            big.free()
+        cpu, roof = None, None
+        peak, peak_src = peaks()
+        if not args.no_cpu:
+            sys.path.insert(0, os.path.join(ROOT, 'tests'))
+            from lysref import oracle
+            cpu, c = cpu_baseline(oracle, (t, tm, m), args.cpu_passes)
+            per_path = {k: c[k] / c['paths'] for k in c}
+            ext_bytes = (32 * per_path['closest_box'] + 40 * per_path['closest_tri']) * W * H * PASSES       # all k_extend launches of a step
+            con_bytes = (32 * per_path['shadow_box'] + 40 * per_path['shadow_tri']) * W * H * PASSES
+            b_path = 24 + 32 * per_path['box_tests'] + 40 * per_path['tri_tests'] + 112 * per_path['vertices']
+            ext_ms, ext_n = prof['extend']
+            tot_ms = sum(v[0] for v in prof.values())
+            achieved = ext_bytes / (ext_ms * 1e-3) / 1e9
+            roof = {'bound': 'hbm', 'kernel': 'k_extend (closest hit, all bounces of a step)', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+                    'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src,
+                    'algorithmic_bytes_per_launch': ext_bytes / max(ext_n, 1), 'avg_launch_ms': ext_ms / max(ext_n, 1), 'launches': ext_n,
+                    'share_of_step': ext_ms / tot_ms if tot_ms else None,
+                    'b_path_bytes': b_path, 'whole_pass_algorithmic_gbs': b_path * W * H * PASSES / (tot_ms * 1e-3) / 1e9,
+                    'connect_achieved_gbs': con_bytes / (prof['connect'][0] * 1e-3) / 1e9 if prof['connect'][0] else None,
+                    'per_path': {k: round(per_path[k], 3) for k in ('vertices', 'closest_rays', 'shadow_rays', 'closest_box', 'closest_tri', 'shadow_box', 'shadow_tri')},
+                    'class_ms': {k: round(v[0], 3) for k, v in prof.items()},
+                    'note': 'scene (3.6 KB BVH) is L1/L2 resident: this path is issue/latency bound, the HBM fraction is reported as the contract asks'}
+        line = {'metric': 'Mpaths/s', 'value': value, 'unit': 'Mpaths/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+                'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+                'data': 'bundled scene arrays (tests/golden/scenes/cornell.npz), synthetic camera path',
+                'config': {'workload': WORKLOAD, 'parallelism': 'scene replicated, %d x %d passes, 1 NCCL reduce/step' % (world, PASSES) if world > 1 else 'single GPU',
+                           'l2': 'per-pass path-state working set ~0.4 GB > 126 MB L2 (no flush needed); the 3.6 KB scene is cache-resident by construction'},
+                'e2e': {'value': e2e_value, 'unit': 'Mpaths/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
+                'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roof, 'cpu_baseline': cpu,
+                'lbvh_build_ms': {'cornell_44_tris': build_ms, 'synthetic_1003244_tris': build_1m}}
+        print(json.dumps(line), flush=True)
+    barrier()
+    base.free()
+    if state is not base:
+        state.free()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

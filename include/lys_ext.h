@@ -28,6 +28,15 @@ void *lys_context_stream(struct futhark_context *ctx);
 /* number of kernel launches issued by this context so far */
 uint64_t lys_context_launch_count(struct futhark_context *ctx);
 
+/* Kernel-class device timing (CUDA events around every launch of the sample pass).  Off by default: the
+ * extra event records perturb throughput, so it is used for a separate profiling step, never the timed run.
+ * Classes: 0 generate, 1 extend (closest hit), 2 shade, 3 connect (shadow rays), 4 accumulate. */
+#define LYS_PROFILE_CLASSES 5
+int lys_context_set_profiling(struct futhark_context *ctx, int on);
+int lys_context_profile_get(struct futhark_context *ctx, float *ms /* [5] */, uint64_t *launches /* [5] */, int reset);
+/* A copy of `s` whose frame rng is advanced k steps (k sample passes ahead): pass-split multi-GPU rendering. */
+int lys_state_advance_rng(struct futhark_context *ctx, struct futhark_opaque_state **out0, const struct futhark_opaque_state *s, uint32_t k);
+
 /* ---- device-resident access ------------------------------------------------------------- */
 /* Raw device pointers (valid until the array / state is freed). */
 void *lys_device_ptr_f32_3d(struct futhark_context *ctx, struct futhark_f32_3d *arr);

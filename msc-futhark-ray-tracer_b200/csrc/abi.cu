@@ -36,6 +36,7 @@ struct futhark_context {
     PassBuffers bufs; BuildScratch scratch;
     float4 *pts_pos = nullptr; float *pts_dist = nullptr; int64_t pts_cap = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    LaunchTimer timer;
 };
 
 namespace {
@@ -221,11 +222,11 @@ bool ensure_pass_buffers(futhark_context *ctx, int64_t n, bool probes) {
 bool ensure_scratch(futhark_context *ctx, int64_t n) {
     BuildScratch &w = ctx->scratch;
     if (w.cap >= n) return true;
-    raw_free(w.box_c); raw_free(w.box_h); raw_free(w.F); raw_free(w.keys[0]); raw_free(w.keys[1]); raw_free(w.vals[0]); raw_free(w.vals[1]);
+    raw_free(w.box_c); raw_free(w.box_h); raw_free(w.F); raw_free(w.chunk_lo); raw_free(w.chunk_hi); raw_free(w.keys[0]); raw_free(w.keys[1]); raw_free(w.vals[0]); raw_free(w.vals[1]);
     raw_free(w.rs_hist); raw_free(w.rs_status); raw_free(w.leaf_parent); raw_free(w.visits);
     w.cap = 0;
     size_t c = (size_t)n, tiles = (c + 4095) / 4096;
-    if (!raw_alloc(ctx, w.box_c, c) || !raw_alloc(ctx, w.box_h, c) || !raw_alloc(ctx, w.F, 2 * c) || !raw_alloc(ctx, w.keys[0], c) ||
+    if (!raw_alloc(ctx, w.chunk_lo, (c + 255) / 256) || !raw_alloc(ctx, w.chunk_hi, (c + 255) / 256) || !raw_alloc(ctx, w.box_c, c) || !raw_alloc(ctx, w.box_h, c) || !raw_alloc(ctx, w.F, 2 * c) || !raw_alloc(ctx, w.keys[0], c) ||
         !raw_alloc(ctx, w.keys[1], c) || !raw_alloc(ctx, w.vals[0], c) || !raw_alloc(ctx, w.vals[1], c) || !raw_alloc(ctx, w.rs_hist, 1024) ||
         !raw_alloc(ctx, w.rs_status, 4 * tiles * 256 + 4) || !raw_alloc(ctx, w.leaf_parent, c) || !raw_alloc(ctx, w.visits, c)) return false;
     w.cap = n;
@@ -312,8 +313,9 @@ bool sample_into(futhark_context *ctx, const futhark_opaque_state *s, uint32_t r
     FrameParams fp;
     if (!ensure_pass_buffers(ctx, (int64_t)((s->dim_w + s->subsampling - 1) / s->subsampling) * ((s->dim_h + s->subsampling - 1) / s->subsampling), false)) return false;
     if (!make_frame_params(ctx, s, rng, 1.0f, fp)) return false;
-    CUB(ctx, run_sample_pass(s->scene->d, fp, ctx->bufs, ctx->stream, &ctx->launches));
-    CUB(ctx, run_accumulate(fp, ctx->bufs, img_old, img_new, merge ? 1 : 0, n_frames, ctx->stream, &ctx->launches));
+    CUB(ctx, run_sample_pass(s->scene->d, fp, ctx->bufs, ctx->stream, &ctx->launches, &ctx->timer));
+    CUB(ctx, run_accumulate(fp, ctx->bufs, img_old, img_new, merge ? 1 : 0, n_frames, ctx->stream, &ctx->launches, &ctx->timer));
+    if (ctx->timer.on && ctx->timer.used > 3000) ctx->timer.resolve(ctx->stream);
     return true;
 }
 
@@ -365,7 +367,7 @@ void futhark_context_free(struct futhark_context *ctx) {
     raw_free(b.chan); raw_free(b.queue[0]); raw_free(b.queue[1]); raw_free(b.hit); raw_free(b.sh_o); raw_free(b.sh_d1); raw_free(b.sh_d2);
     raw_free(b.sh_c); raw_free(b.counts); raw_free(b.stats); raw_free(b.tx_lights); raw_free(b.probe_rad); raw_free(b.probe_dist);
     BuildScratch &w = ctx->scratch;
-    raw_free(w.box_c); raw_free(w.box_h); raw_free(w.F); raw_free(w.keys[0]); raw_free(w.keys[1]); raw_free(w.vals[0]); raw_free(w.vals[1]);
+    raw_free(w.box_c); raw_free(w.box_h); raw_free(w.F); raw_free(w.chunk_lo); raw_free(w.chunk_hi); raw_free(w.keys[0]); raw_free(w.keys[1]); raw_free(w.vals[0]); raw_free(w.vals[1]);
     raw_free(w.rs_hist); raw_free(w.rs_status); raw_free(w.leaf_parent); raw_free(w.visits);
     raw_free(ctx->pts_pos); raw_free(ctx->pts_dist);
     for (auto &kv : ctx->pool) cudaFree(kv.second);
@@ -655,6 +657,21 @@ int lys_context_set_refit_mode(struct futhark_context *ctx, int mode) { if (!ctx
 int lys_context_set_partition(struct futhark_context *ctx, int rank, int world_size) {
     if (!ctx || world_size < 1 || rank < 0 || rank >= world_size) { if (ctx) set_error(ctx, "bad partition"); return 1; }
     ctx->rank = rank; ctx->world = world_size; return 0;
+}
+int lys_context_set_profiling(struct futhark_context *ctx, int on) { if (!ctx) return 1; ctx->timer.resolve(ctx->stream); ctx->timer.on = on != 0; return 0; }
+int lys_context_profile_get(struct futhark_context *ctx, float *ms, uint64_t *launches, int reset) {
+    if (!ctx) return 1;
+    ctx->timer.resolve(ctx->stream);
+    for (int i = 0; i < LYS_PROFILE_CLASSES; i++) { if (ms) ms[i] = ctx->timer.ms[i]; if (launches) launches[i] = ctx->timer.n[i]; }
+    if (reset) ctx->timer.reset();
+    return 0;
+}
+int lys_state_advance_rng(struct futhark_context *ctx, struct futhark_opaque_state **out0, const struct futhark_opaque_state *s, uint32_t k) {
+    if (!ctx || !out0 || !s) return 1;
+    futhark_opaque_state *r = clone_state(s);
+    for (uint32_t i = 0; i < k; i++) r->rng = h_advance_rng(r->rng);
+    *out0 = r;
+    return 0;
 }
 int lys_context_device(struct futhark_context *ctx) { return ctx ? ctx->device : -1; }
 void *lys_context_stream(struct futhark_context *ctx) { return ctx ? (void *)ctx->stream : nullptr; }

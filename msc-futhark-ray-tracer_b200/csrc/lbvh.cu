@@ -2,7 +2,7 @@
  *
  * Replaces `obj_bvh.build` (reference src/bvh.fut:86-121) and `radix_tree.mk`
  * (src/radix_tree.fut:21-89):
- *   k_tri_boxes      bvh.fut:87          per-triangle AABB (center, half)
+ *   k_tri_boxes      bvh.fut:87          per-triangle AABB (center, half) + exact corner union per 256-triangle chunk
  *   k_bounds_fold    bvh.fut:88-90       scene bounds = LEFT FOLD of containing_aabb, reproduced
  *                                        exactly by a speculative block-skip fold (see below)
  *   k_morton         bvh.fut:91-94       30-bit Morton code of the normalised box centre
@@ -22,73 +22,133 @@
 
 namespace lys {
 
-/* ------------------------------------------------------------------ boxes */
-__global__ void k_tri_boxes(const float *__restrict__ tris, int n, float4 *__restrict__ box_c, float4 *__restrict__ box_h) {
+/* ------------------------------------------------------------------ boxes + per-chunk exact unions */
+#define BOX_CHUNK 256        /* triangles per chunk == threads per block of k_tri_boxes */
+__device__ __forceinline__ float warp_min(float v) { for (int o = 16; o; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o)); return v; }
+__device__ __forceinline__ float warp_max(float v) { for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o)); return v; }
+/* One triangle per thread: its AABB (bvh.fut:87), and per block the exact min/max over the block of the
+ * corners (center - half, center + half) exactly as containing_aabb derives them (shapes.fut:97-98);
+ * a NaN corner poisons the chunk union so that the fold never skips the chunk. */
+__global__ void __launch_bounds__(BOX_CHUNK) k_tri_boxes(const float *__restrict__ tris, int n, float4 *__restrict__ box_c,
+                                                         float4 *__restrict__ box_h, float4 *__restrict__ chunk_lo, float4 *__restrict__ chunk_hi) {
+    __shared__ float red[6][BOX_CHUNK / 32];
+    __shared__ int poison;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const float *t = tris + 9ll * i;
-    Box b = triangle_box(v3(t[0], t[1], t[2]), v3(t[3], t[4], t[5]), v3(t[6], t[7], t[8]));
-    box_c[i] = make_float4(b.c.x, b.c.y, b.c.z, 0.0f);
-    box_h[i] = make_float4(b.h.x, b.h.y, b.h.z, 0.0f);
+    if (threadIdx.x == 0) poison = 0;
+    __syncthreads();
+    float lo[3] = {LYS_INF, LYS_INF, LYS_INF}, hi[3] = {-LYS_INF, -LYS_INF, -LYS_INF};
+    if (i < n) {
+        const float *t = tris + 9ll * i;
+        Box b = triangle_box(v3(t[0], t[1], t[2]), v3(t[3], t[4], t[5]), v3(t[6], t[7], t[8]));
+        box_c[i] = make_float4(b.c.x, b.c.y, b.c.z, 0.0f);
+        box_h[i] = make_float4(b.h.x, b.h.y, b.h.z, 0.0f);
+        V3 l = b.c - b.h, h = b.c + b.h;
+        lo[0] = l.x; lo[1] = l.y; lo[2] = l.z; hi[0] = h.x; hi[1] = h.y; hi[2] = h.z;
+        if (l.x != l.x || l.y != l.y || l.z != l.z || h.x != h.x || h.y != h.y || h.z != h.z) poison = 1;
+    }
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        float a = warp_min(lo[k]), b = warp_max(hi[k]);
+        if (lane == 0) { red[k][warp] = a; red[3 + k][warp] = b; }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float r[6];
+        for (int k = 0; k < 3; k++) {
+            float a = red[k][0], b = red[3 + k][0];
+            for (int w = 1; w < BOX_CHUNK / 32; w++) { a = fminf(a, red[k][w]); b = fmaxf(b, red[3 + k][w]); }
+            r[k] = a; r[3 + k] = b;
+        }
+        if (poison) { float q = lys_u2f(0x7fc00000u); for (int k = 0; k < 6; k++) r[k] = q; }
+        chunk_lo[blockIdx.x] = make_float4(r[0], r[1], r[2], 0.0f);
+        chunk_hi[blockIdx.x] = make_float4(r[3], r[4], r[5], 0.0f);
+    }
 }
 
 /* ------------------------------------------------------------------ exact left fold of the scene bounds
- * S_k = containing_aabb(S_{k-1}, box_k) is not associative in f32 (center/half are re-derived from
- * the corners at every step), so a tree reduction does not reproduce the reference's `c`-backend
- * result.  The fold is emulated exactly: one CTA walks the boxes in order, 1024 at a time; every
- * thread evaluates contain(S, box_k) against the CURRENT state S; if no thread's result differs from
- * S bit-for-bit, S is a fixed point for all 1024 steps and the chunk is skipped.  Otherwise the first
- * differing element is applied and the remaining elements of the chunk are re-tested against the new
- * state.  If a chunk changes the state more than FOLD_MAX_EVENTS times, thread 0 folds the rest of the
- * chunk sequentially from shared memory.  The result equals the sequential fold for any input. */
-#define FOLD_THREADS 1024
-#define FOLD_MAX_EVENTS 12
+ * S_k = containing_aabb(S_{k-1}, box_k) (bvh.fut:88-90) is not associative in f32: center/half are
+ * re-derived from the corners at every step, so a tree reduction does not reproduce the reference's
+ * sequential (`c` backend) result.  It is emulated exactly:
+ *   - an element leaves S unchanged iff contain(S, box) == S bit-for-bit;
+ *   - if S is a fixed point of the re-derivation (contain(S, S) == S) and a whole chunk's exact corner
+ *     union lies inside S's corners, every element of the chunk leaves S unchanged -> the chunk is
+ *     skipped after a 6-comparison test on its precomputed union (32 chunks per warp step);
+ *   - any other chunk is staged in shared memory and folded by warp 0 in order, 32 elements per step:
+ *     the lanes test their element against the current S, the first lane whose result differs
+ *     commits it, and the step restarts behind that element.
+ * State changes are rare (a few hundred per million triangles), so the walk is O(#chunks/32) warp
+ * steps plus the dirty chunks.  The result equals the sequential fold for any input. */
+#define FOLD_THREADS BOX_CHUNK
+__device__ __forceinline__ Box shfl_box(Box b, int src) {
+    Box r;
+    r.c.x = __shfl_sync(0xffffffffu, b.c.x, src); r.c.y = __shfl_sync(0xffffffffu, b.c.y, src); r.c.z = __shfl_sync(0xffffffffu, b.c.z, src);
+    r.h.x = __shfl_sync(0xffffffffu, b.h.x, src); r.h.y = __shfl_sync(0xffffffffu, b.h.y, src); r.h.z = __shfl_sync(0xffffffffu, b.h.z, src);
+    return r;
+}
 __global__ void __launch_bounds__(FOLD_THREADS, 1)
-k_bounds_fold(const float4 *__restrict__ box_c, const float4 *__restrict__ box_h, int n, float *__restrict__ bounds_out /* 6 */) {
-    __shared__ float4 sc[FOLD_THREADS], sh[FOLD_THREADS];
-    __shared__ Box S;
-    __shared__ int first;
-    const int tid = threadIdx.x;
-    if (tid == 0) { S.c = v3(0.0f, 0.0f, 0.0f); S.h = v3(-LYS_INF, -LYS_INF, -LYS_INF); }   /* bvh.fut:88-89 */
-    __syncthreads();
-    for (int base = 0; base < n; base += FOLD_THREADS) {
-        int k = base + tid;
-        Box mine; mine.c = v3(0, 0, 0); mine.h = v3(0, 0, 0);
-        if (k < n) {
-            float4 c = box_c[k], h = box_h[k];
-            sc[tid] = c; sh[tid] = h;
-            mine.c = v3(c.x, c.y, c.z); mine.h = v3(h.x, h.y, h.z);
-        }
-        int start = 0, events = 0;
-        int limit = min(FOLD_THREADS, n - base);
-        while (true) {
-            if (tid == 0) first = 0x7fffffff;
-            __syncthreads();
-            Box cur = S;
-            Box ns = cur;
-            bool changed = false;
-            if (tid >= start && tid < limit) { ns = contain(cur, mine); changed = !box_bits_equal(ns, cur); }
-            if (changed) atomicMin(&first, tid);
-            __syncthreads();
-            int f = first;
-            if (f == 0x7fffffff) break;
-            if (tid == f) S = ns;
-            start = f + 1; events++;
-            if (events >= FOLD_MAX_EVENTS) {
-                __syncthreads();
-                if (tid == 0) {
-                    Box s = S;
-                    for (int j = start; j < limit; j++) {
-                        Box b; b.c = v3(sc[j].x, sc[j].y, sc[j].z); b.h = v3(sh[j].x, sh[j].y, sh[j].z);
-                        s = contain(s, b);
+k_bounds_fold(const float4 *__restrict__ box_c, const float4 *__restrict__ box_h, const float4 *__restrict__ chunk_lo,
+              const float4 *__restrict__ chunk_hi, int n, float *__restrict__ bounds_out /* 6 */) {
+    __shared__ float4 sc[BOX_CHUNK], sh[BOX_CHUNK];
+    __shared__ Box S_sh;
+    __shared__ int next_chunk;       /* first chunk (>= cursor) that must be folded element-wise, or n_chunks */
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n_chunks = (n + BOX_CHUNK - 1) / BOX_CHUNK;
+    Box S; S.c = v3(0.0f, 0.0f, 0.0f); S.h = v3(-LYS_INF, -LYS_INF, -LYS_INF);            /* bvh.fut:88-89 */
+    int cursor = 0;
+    while (cursor < n_chunks) {
+        /* warp 0: skip clean chunks, 32 at a time (all threads hold the same S) */
+        if (warp == 0) {
+            bool stable = box_bits_equal(contain(S, S), S);
+            V3 slo = S.c - S.h, shi = S.c + S.h;
+            int c = cursor;
+            if (stable) {
+                while (c < n_chunks) {
+                    int j = c + lane;
+                    bool dirty = false;
+                    if (j < n_chunks) {
+                        float4 l = __ldg(chunk_lo + j), h = __ldg(chunk_hi + j);
+                        dirty = !(l.x >= slo.x && l.y >= slo.y && l.z >= slo.z && h.x <= shi.x && h.y <= shi.y && h.z <= shi.z);
                     }
-                    S = s;
+                    unsigned m = __ballot_sync(0xffffffffu, dirty);
+                    if (m) { c += __ffs(m) - 1; break; }
+                    c += 32;
                 }
-                __syncthreads();
-                break;
+                if (c > n_chunks) c = n_chunks;
             }
-            __syncthreads();
+            if (lane == 0) next_chunk = c;
         }
+        __syncthreads();
+        cursor = next_chunk;
+        if (cursor >= n_chunks) break;
+        /* stage the dirty chunk */
+        const int base = cursor * BOX_CHUNK;
+        const int limit = min(BOX_CHUNK, n - base);
+        if (tid < limit) { sc[tid] = box_c[base + tid]; sh[tid] = box_h[base + tid]; }
+        __syncthreads();
+        if (warp == 0) {
+            Box s = S;
+            int p = 0;
+            while (p < limit) {
+                int e = p + lane;
+                Box ns = s; bool ch = false;
+                if (e < limit) {
+                    float4 c4 = sc[e], h4 = sh[e];
+                    Box b; b.c = v3(c4.x, c4.y, c4.z); b.h = v3(h4.x, h4.y, h4.z);
+                    ns = contain(s, b);
+                    ch = !box_bits_equal(ns, s);
+                }
+                unsigned m = __ballot_sync(0xffffffffu, ch);
+                if (!m) { p += 32; continue; }
+                int k = __ffs(m) - 1;
+                s = shfl_box(ns, k);
+                p += k + 1;
+            }
+            if (lane == 0) S_sh = s;
+        }
+        __syncthreads();
+        S = S_sh;
+        cursor++;
         __syncthreads();
     }
     if (tid == 0) {
@@ -387,8 +447,8 @@ cudaError_t build_lbvh(SceneDev &sc, BuildScratch &ws, int refit_mode, cudaStrea
     const int n_nodes = n - 1;
     const int T = 256;
     uint64_t nl = 0;
-    k_tri_boxes<<<cdiv(n, T), T, 0, stream>>>(sc.tris, n, ws.box_c, ws.box_h); nl++;
-    k_bounds_fold<<<1, FOLD_THREADS, 0, stream>>>(ws.box_c, ws.box_h, n, sc.bounds); nl++;
+    k_tri_boxes<<<cdiv(n, BOX_CHUNK), BOX_CHUNK, 0, stream>>>(sc.tris, n, ws.box_c, ws.box_h, ws.chunk_lo, ws.chunk_hi); nl++;
+    k_bounds_fold<<<1, FOLD_THREADS, 0, stream>>>(ws.box_c, ws.box_h, ws.chunk_lo, ws.chunk_hi, n, sc.bounds); nl++;
     k_morton<<<cdiv(n, T), T, 0, stream>>>(ws.box_c, n, sc.bounds, ws.keys[0], ws.vals[0]); nl++;
     /* radix sort */
     const int tiles = cdiv(n, RS_TILE);

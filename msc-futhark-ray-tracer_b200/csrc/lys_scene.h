@@ -41,7 +41,7 @@ struct SceneDev {
 
 struct BuildScratch {
     int64_t cap = 0;
-    float4 *box_c = nullptr, *box_h = nullptr, *F = nullptr;
+    float4 *box_c = nullptr, *box_h = nullptr, *F = nullptr, *chunk_lo = nullptr, *chunk_hi = nullptr;
     uint32_t *keys[2] = {nullptr, nullptr}, *vals[2] = {nullptr, nullptr};
     uint32_t *rs_hist = nullptr, *rs_status = nullptr;
     int *leaf_parent = nullptr; unsigned int *visits = nullptr;

@@ -2,6 +2,7 @@
 #pragma once
 #include "lys_scene.h"
 #include "lys_device.cuh"
+#include <vector>
 
 namespace lys {
 
@@ -54,13 +55,32 @@ struct PassBuffers {
     float *probe_rad = nullptr, *probe_dist = nullptr;   /* [cap][16] */
 };
 
-struct PassLaunchStats { uint64_t launches = 0; };
+/* optional per-launch timing: events are recorded around each launch and resolved by the owner */
+struct LaunchTimer {
+    bool on = false;
+    std::vector<cudaEvent_t> ev0, ev1; std::vector<int> cls; size_t used = 0;
+    float ms[5] = {0, 0, 0, 0, 0}; uint64_t n[5] = {0, 0, 0, 0, 0};
+    void begin(int c, cudaStream_t st) {
+        if (!on) return;
+        if (used == ev0.size()) { cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b); ev0.push_back(a); ev1.push_back(b); cls.push_back(0); }
+        cls[used] = c; cudaEventRecord(ev0[used], st);
+    }
+    void end(cudaStream_t st) { if (!on) return; cudaEventRecord(ev1[used], st); used++; }
+    void resolve(cudaStream_t st) {
+        if (!used) return;
+        cudaStreamSynchronize(st);
+        for (size_t i = 0; i < used; i++) { float t = 0; cudaEventElapsedTime(&t, ev0[i], ev1[i]); ms[cls[i]] += t; n[cls[i]]++; }
+        used = 0;
+    }
+    void reset() { for (int i = 0; i < 5; i++) { ms[i] = 0; n[i] = 0; } used = 0; }
+    ~LaunchTimer() { for (auto e : ev0) cudaEventDestroy(e); for (auto e : ev1) cudaEventDestroy(e); }
+};
 
 /* one sample pass: generate, (extend, shade, connect) x path_len.  Results stay in bufs (sum, zsum, best_*). */
-cudaError_t run_sample_pass(const SceneDev &sc, const FrameParams &fp, PassBuffers &bufs, cudaStream_t stream, uint64_t *launches);
+cudaError_t run_sample_pass(const SceneDev &sc, const FrameParams &fp, PassBuffers &bufs, cudaStream_t stream, uint64_t *launches, LaunchTimer *timer = nullptr);
 /* resolve + merge into the image: mode 0 = replace (sample_frame), 1 = running average (sample_frame_accum) */
 cudaError_t run_accumulate(const FrameParams &fp, const PassBuffers &bufs, const float *img_old, float *img_new,
-                           int merge, float n_frames, cudaStream_t stream, uint64_t *launches);
+                           int merge, float n_frames, cudaStream_t stream, uint64_t *launches, LaunchTimer *timer = nullptr);
 /* point cloud: resolve one pass into [gh][gw] (pos.xyz, distance, intensity) and merge (lib.fut:41-59) */
 cudaError_t run_points_merge(const FrameParams &fp, const PassBuffers &bufs, float4 *pos_int, float *dist, int first,
                              cudaStream_t stream, uint64_t *launches);

@@ -458,23 +458,26 @@ __global__ void k_material_probe(const float *mat28, float wavelen, V3 wo, V3 wi
 /* ------------------------------------------------------------------ host launchers */
 static inline int cdiv(long long a, int b) { return (int)((a + b - 1) / b); }
 
-cudaError_t run_sample_pass(const SceneDev &sc, const FrameParams &fp, PassBuffers &bufs, cudaStream_t stream, uint64_t *launches) {
+cudaError_t run_sample_pass(const SceneDev &sc, const FrameParams &fp, PassBuffers &bufs, cudaStream_t stream, uint64_t *launches, LaunchTimer *timer) {
     const int n = fp.n_local;
     if (n <= 0) return cudaSuccess;
     uint64_t nl = 0;
-    k_generate<<<cdiv(n, 256), 256, 0, stream>>>(fp, bufs); nl++;
+    LaunchTimer none; LaunchTimer &tm = timer ? *timer : none;
+    tm.begin(0, stream); k_generate<<<cdiv(n, 256), 256, 0, stream>>>(fp, bufs); tm.end(stream); nl++;
     for (int bnc = 0; bnc < fp.path_len; bnc++) {
-        k_extend<<<cdiv(n, 128), 128, 0, stream>>>(sc, bufs, bnc); nl++;
-        k_shade<<<cdiv(n, 128), 128, 0, stream>>>(sc, fp, bufs, bnc); nl++;
-        k_connect<<<cdiv(n, 128), 128, 0, stream>>>(sc, fp, bufs, bnc); nl++;
+        tm.begin(1, stream); k_extend<<<cdiv(n, 128), 128, 0, stream>>>(sc, bufs, bnc); tm.end(stream); nl++;
+        tm.begin(2, stream); k_shade<<<cdiv(n, 128), 128, 0, stream>>>(sc, fp, bufs, bnc); tm.end(stream); nl++;
+        tm.begin(3, stream); k_connect<<<cdiv(n, 128), 128, 0, stream>>>(sc, fp, bufs, bnc); tm.end(stream); nl++;
     }
     if (launches) *launches += nl;
     return cudaGetLastError();
 }
 cudaError_t run_accumulate(const FrameParams &fp, const PassBuffers &bufs, const float *img_old, float *img_new, int merge,
-                           float n_frames, cudaStream_t stream, uint64_t *launches) {
+                           float n_frames, cudaStream_t stream, uint64_t *launches, LaunchTimer *timer) {
     if (fp.n_local <= 0) return cudaSuccess;
+    if (timer) timer->begin(4, stream);
     k_accumulate<<<cdiv(fp.n_local, 256), 256, 0, stream>>>(fp, bufs, img_old, img_new, merge, n_frames);
+    if (timer) timer->end(stream);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }

@@ -92,6 +92,9 @@ def _load():
     L.lys_context_set_path_len.argtypes = [vp, C.c_int]
     L.lys_context_set_refit_mode.argtypes = [vp, C.c_int]
     L.lys_context_set_partition.argtypes = [vp, C.c_int, C.c_int]
+    L.lys_context_set_profiling.argtypes = [vp, C.c_int]
+    L.lys_context_profile_get.argtypes = [vp, vp, vp, C.c_int]
+    L.lys_state_advance_rng.argtypes = [vp, C.POINTER(vp), vp, C.c_uint32]
     L.lys_context_device.argtypes = [vp]
     L.lys_context_stream.restype = vp
     L.lys_context_stream.argtypes = [vp]
@@ -199,6 +202,16 @@ class Context:
     def set_partition(self, rank, world):
         self.check(self._L.lys_context_set_partition(self._ctx, int(rank), int(world)), 'lys_context_set_partition')
 
+    def set_profiling(self, on):
+        self.check(self._L.lys_context_set_profiling(self._ctx, int(bool(on))), 'lys_context_set_profiling')
+
+    def profile(self, reset=True):
+        """-> {class: (device ms, launches)} for generate / extend / shade / connect / accumulate."""
+        ms = np.zeros(5, np.float32)
+        n = np.zeros(5, np.uint64)
+        self.check(self._L.lys_context_profile_get(self._ctx, _ptr(ms), _ptr(n), int(reset)), 'lys_context_profile_get')
+        return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(('generate', 'extend', 'shade', 'connect', 'accumulate'))}
+
     @property
     def device(self):
         return int(self._L.lys_context_device(self._ctx))
@@ -277,6 +290,9 @@ class State:
 
     def resize(self, h, w):
         return State(self.ctx, self._entry('futhark_entry_resize', h, w, self._p))
+
+    def advance_rng(self, k):
+        return State(self.ctx, self._entry('lys_state_advance_rng', self._p, k))
 
     def _take(self, arr, nm, dtype):
         L = self.ctx._L

@@ -54,7 +54,7 @@ inline float f_lerp(float a, float b, float t) { return a + (b - a) * t; }
 
 /* ------------------------------------------------------------------ counters */
 struct Counters { uint64_t paths = 0, vertices = 0, closest_rays = 0, shadow_rays = 0, node_visits = 0,
-                  box_tests = 0, tri_tests = 0, loop_iters = 0; };
+                  box_tests = 0, tri_tests = 0, loop_iters = 0, closest_box = 0, closest_tri = 0, shadow_box = 0, shadow_tri = 0; };
 Counters g_counters;
 thread_local Counters t_counters;
 void flush_counters() {
@@ -64,6 +64,8 @@ void flush_counters() {
         g_counters.closest_rays += t_counters.closest_rays; g_counters.shadow_rays += t_counters.shadow_rays;
         g_counters.node_visits += t_counters.node_visits; g_counters.box_tests += t_counters.box_tests;
         g_counters.tri_tests += t_counters.tri_tests; g_counters.loop_iters += t_counters.loop_iters;
+        g_counters.closest_box += t_counters.closest_box; g_counters.closest_tri += t_counters.closest_tri;
+        g_counters.shadow_box += t_counters.shadow_box; g_counters.shadow_tri += t_counters.shadow_tri;
     }
     t_counters = Counters();
 }
@@ -385,6 +387,7 @@ struct trav_hit { int32_t leaf; hit h; };
 /* closest_hit (bvh.fut:123-145): stackless parent-pointer walk, always left first */
 bool bvh_closest_hit(float tmax_in, const ray &r, const bvh_t &bvh, trav_hit &out) {
     t_counters.closest_rays++;
+    const uint64_t box0 = t_counters.box_tests, tri0 = t_counters.tri_tests;
     int32_t closest = -1; float tmax = tmax_in; int32_t current = 0; int32_t prev = PREV_NONE;
     if (bvh.nodes.empty()) current = -1;
     while (current != -1) {
@@ -400,13 +403,15 @@ bool bvh_closest_hit(float tmax_in, const ray &r, const bvh_t &bvh, trav_hit &ou
         if (hit_triangle(tmax, r, bvh.leaves[i].geom, h)) { closest = i; tmax = h.t; }
         prev = rec_child;
     }
+    t_counters.closest_box += t_counters.box_tests - box0; t_counters.closest_tri += t_counters.tri_tests - tri0;
     if (closest < 0) return false;
     out.leaf = closest;
-    return hit_triangle(tmax_in, r, bvh.leaves[closest].geom, out.h);         /* :143-145 (outer tmax) */
+    { const uint64_t keep = t_counters.tri_tests; bool ok = hit_triangle(tmax_in, r, bvh.leaves[closest].geom, out.h); t_counters.tri_tests = keep; return ok; } /* :143-145 (outer tmax); not counted as traversal work */
 }
 /* any_hit (bvh.fut:149-167) */
 bool bvh_any_hit(float tmax, const ray &r, const bvh_t &bvh) {
     t_counters.shadow_rays++;
+    const uint64_t box0 = t_counters.box_tests, tri0 = t_counters.tri_tests;
     bool found = false; int32_t current = 0; int32_t prev = PREV_NONE;
     if (bvh.nodes.empty()) current = -1;
     while (!found && current != -1) {
@@ -421,6 +426,7 @@ bool bvh_any_hit(float tmax, const ray &r, const bvh_t &bvh) {
         if (hit_triangle(tmax, r, bvh.leaves[ptr_leaf_ix(rec_child)].geom, h)) found = true;
         prev = rec_child;
     }
+    t_counters.shadow_box += t_counters.box_tests - box0; t_counters.shadow_tri += t_counters.tri_tests - tri0;
     return found;
 }
 
@@ -1074,6 +1080,7 @@ orc_state *orc_sample_points_n(const orc_state *s0, uint32_t spp, float *out) { 
     }
     return res;
 }
+orc_state *orc_advance_rng(const orc_state *s, uint32_t k) { orc_state *r = new orc_state(*s); for (uint32_t i = 0; i < k; i++) advance_rng(r->rng); return r; }
 void orc_free_state(orc_state *s) { delete s; }
 
 void orc_state_dims(const orc_state *s, uint32_t *w, uint32_t *h, uint32_t *gw, uint32_t *gh) {
@@ -1211,6 +1218,7 @@ void orc_counters_get(orc_counters *out) {
     out->paths = g_counters.paths; out->vertices = g_counters.vertices; out->closest_rays = g_counters.closest_rays;
     out->shadow_rays = g_counters.shadow_rays; out->node_visits = g_counters.node_visits; out->box_tests = g_counters.box_tests;
     out->tri_tests = g_counters.tri_tests; out->loop_iters = g_counters.loop_iters;
+    out->closest_box = g_counters.closest_box; out->closest_tri = g_counters.closest_tri; out->shadow_box = g_counters.shadow_box; out->shadow_tri = g_counters.shadow_tri;
 }
 
 } // extern "C"

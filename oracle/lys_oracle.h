@@ -42,6 +42,7 @@ orc_state *orc_step(const orc_state *s);
 void orc_render(const orc_state *s, int32_t *out /* [h][w] */);
 void orc_sample_n_frames(const orc_state *s, uint32_t n, float *out /* [gh][gw][3] */);
 orc_state *orc_sample_points_n(const orc_state *s, uint32_t spp, float *out /* [gh][gw][4] */);
+orc_state *orc_advance_rng(const orc_state *s, uint32_t k);   /* k x advance_rng on the frame rng (rand.fut:11-12) */
 void orc_free_state(orc_state *s);
 
 /* state introspection */
@@ -87,6 +88,7 @@ void orc_any_hits(const orc_state *s, const float *rays, const float *tmax, int6
 /* Work counters accumulated since the last reset (define the algorithmic-bytes figure). */
 typedef struct {
     uint64_t paths, vertices, closest_rays, shadow_rays, node_visits, box_tests, tri_tests, loop_iters;
+    uint64_t closest_box, closest_tri, shadow_box, shadow_tri;   /* box / triangle tests split by ray type */
 } orc_counters;
 void orc_counters_reset(void);
 void orc_counters_get(orc_counters *out);

@@ -16,7 +16,7 @@ i32p = np.ctypeslib.ndpointer(np.int32, flags='C_CONTIGUOUS')
 
 class Counters(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ('paths', 'vertices', 'closest_rays', 'shadow_rays', 'node_visits',
-                                           'box_tests', 'tri_tests', 'loop_iters')]
+                                           'box_tests', 'tri_tests', 'loop_iters', 'closest_box', 'closest_tri', 'shadow_box', 'shadow_tri')]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
@@ -45,6 +45,8 @@ def lib():
                        ('orc_step', [vp]), ('orc_sample_points_n', [vp, C.c_uint32, f32p])):
         getattr(L, name).restype = vp
         getattr(L, name).argtypes = args
+    L.orc_advance_rng.restype = vp
+    L.orc_advance_rng.argtypes = [vp, C.c_uint32]
     L.orc_render.argtypes = [vp, i32p]
     L.orc_sample_n_frames.argtypes = [vp, C.c_uint32, f32p]
     L.orc_free_state.argtypes = [vp]
@@ -165,6 +167,9 @@ class State:
 
     def resize(self, h, w):
         return State(lib().orc_resize(h, w, self._p))
+
+    def advance_rng(self, k):
+        return State(lib().orc_advance_rng(self._p, k))
 
     def dims(self):
         v = [C.c_uint32() for _ in range(4)]

@@ -1,0 +1,235 @@
+"""GPU parity: the sm_100a library, called through its C ABI, against the CPU oracle on identical inputs.
+Bit-exact everywhere (integers, indices AND f32 results): the arithmetic contract makes that a meaningful bar."""
+import numpy as np
+import pytest
+from conftest import SCENE_NAMES, bits_equal
+
+pytestmark = pytest.mark.gpu
+K = dict(SPACE=0x20, K1=0x31, K2=0x32, m=0x6D, t=0x74, p=0x70, w=0x77, UP=0x40000052, i=0x69)
+
+
+def both(orc, pkg, gpu, scene, h, w, **kw):
+    t, tm, m = scene
+    return orc.State.init(t, tm, m, h, w, **kw), pkg.State.init(gpu, t, tm, m, h, w, **kw)
+
+
+def test_math_contract_bits(orc, gpu):
+    rng = np.random.default_rng(1)
+    for fn, lo, hi in (('sin', 0, 6.3), ('cos', 0, 6.3), ('exp', -110, 89), ('log', 0, 4), ('pow5', 0, 1), ('acos', -1, 1), ('probit', 0, 1)):
+        x = rng.uniform(lo, hi, 1 << 20).astype(np.float32)
+        x[:4] = [lo, hi, 0.0, 1.0]
+        assert bits_equal(gpu.eval_math(fn, x), orc.eval_math(fn, x)), fn
+
+
+@pytest.mark.parametrize('name', SCENE_NAMES)
+def test_lbvh_bit_exact(orc, pkg, gpu, scenes, name):
+    so, sg = both(orc, pkg, gpu, scenes[name], 8, 8)
+    bo, bg = so.bvh(), sg.bvh()
+    for k in ('bounds', 'morton', 'src_index', 'left', 'right', 'parent', 'node_aabb', 'leaf_aabb'):
+        assert bits_equal(bo[k], bg[k]), k
+    assert bits_equal(so.light_indices(), sg.light_indices())
+
+
+@pytest.mark.parametrize('k', [2, 9, 40])
+def test_lbvh_synthetic_bit_exact(orc, pkg, gpu, scenes, k):
+    t, tm, m = scenes['cornell']
+    st, sm = pkg.scenes.synthetic_cornell(t, tm, k)
+    so, sg = orc.State.init(st, sm, m, 8, 8), pkg.State.init(gpu, st, sm, m, 8, 8)
+    bo, bg = so.bvh(), sg.bvh()
+    for key in ('bounds', 'morton', 'src_index', 'left', 'right', 'parent', 'node_aabb'):
+        assert bits_equal(bo[key], bg[key]), key
+
+
+def test_lbvh_edge_cases(orc, pkg, gpu, scenes):
+    m = scenes['cornell'][2]
+    rng = np.random.default_rng(7)
+    cases = {
+        'two': rng.random((2, 3, 3)),
+        'duplicates': np.repeat(rng.random((3, 3, 3)), 50, axis=0),                  # equal Morton codes -> index tie-break
+        'flat_z': np.concatenate([rng.random((300, 3, 2)), np.zeros((300, 3, 1))], axis=2),   # zero extent on z -> NaN axis
+        'ragged_4097': rng.random((4097, 3, 3)) * 10 - 5,                            # one key past a sort tile
+        'clustered': np.concatenate([rng.random((500, 3, 3)) * 1e-3, rng.random((500, 3, 3)) * 1e-3 + 100]),
+        'sweep': np.cumsum(rng.random((3000, 1, 3)), axis=0) + rng.random((3000, 3, 3)),  # every triangle extends the bounds
+    }
+    for name, tri in cases.items():
+        tri = np.ascontiguousarray(tri, np.float32)
+        tm = np.zeros(len(tri), np.uint32)
+        so, sg = orc.State.init(tri, tm, m, 4, 4), pkg.State.init(gpu, tri, tm, m, 4, 4)
+        bo, bg = so.bvh(), sg.bvh()
+        for key in ('bounds', 'morton', 'src_index', 'left', 'right', 'parent', 'node_aabb'):
+            assert bits_equal(bo[key], bg[key]), (name, key)
+
+
+def test_refit_converged_mode(orc, pkg, gpu, scenes):
+    t, tm, m = scenes['spectrumsphere']
+    orc.set_refit_mode(1)
+    gpu.set_refit_mode(1)
+    try:
+        bo, bg = orc.State.init(t, tm, m, 4, 4).bvh(), pkg.State.init(gpu, t, tm, m, 4, 4).bvh()
+    finally:
+        orc.set_refit_mode(0)
+        gpu.set_refit_mode(0)
+    assert bits_equal(bo['node_aabb'], bg['node_aabb'])
+    # converged boxes enclose their children
+    for side in ('left', 'right'):
+        c = bg[side]
+        child = np.where(c[:, None] >= 0, bg['node_aabb'][np.maximum(c, 0)], bg['leaf_aabb'][np.maximum(~c, 0)])
+        lo_p, hi_p = bg['node_aabb'][:, :3] - bg['node_aabb'][:, 3:], bg['node_aabb'][:, :3] + bg['node_aabb'][:, 3:]
+        lo_c, hi_c = child[:, :3] - child[:, 3:], child[:, :3] + child[:, 3:]
+        assert (lo_c >= lo_p - 1e-5).all() and (hi_c <= hi_p + 1e-5).all()
+
+
+@pytest.mark.parametrize('name', SCENE_NAMES)
+def test_first_hit_bit_exact(orc, pkg, gpu, scenes, name):
+    so, sg = both(orc, pkg, gpu, scenes[name], 120, 160)
+    po, pg = so.probe_primary(), sg.probe_primary()
+    assert bits_equal(po['leaf'], pg['leaf']) and bits_equal(po['src_tri'], pg['src_tri']) and bits_equal(po['t'], pg['t'])
+    assert (po['leaf'] >= 0).mean() > 0.5
+
+
+@pytest.mark.parametrize('name', SCENE_NAMES)
+@pytest.mark.parametrize('conf', [0, 1, 2])
+def test_pass_radiance_bit_exact(orc, pkg, gpu, scenes, name, conf):
+    so, sg = both(orc, pkg, gpu, scenes[name], 72, 96, cam_conf_id=conf)
+    qo, qg = so.probe_pass(), sg.probe_pass()
+    assert bits_equal(qo['channel'], qg['channel'])
+    assert bits_equal(qo['distance'], qg['distance'])
+    assert bits_equal(qo['radiance'], qg['radiance'])          # stronger than the 1e-4 relative bar of the north star
+    assert qo['radiance'].max() > 0
+
+
+def test_random_rays(orc, pkg, gpu, scenes):
+    from test_oracle_scene import random_rays
+    for name in ('cornell', 'spectrumspherehigh'):
+        so, sg = both(orc, pkg, gpu, scenes[name], 4, 4)
+        rays = random_rays(50000, seed=11)
+        lo, to = so.closest_hits(rays)
+        lg, tg = sg.trace_closest(rays)
+        assert bits_equal(lo, lg) and bits_equal(to, tg)
+        tmax = np.random.default_rng(2).uniform(0.0, 2.5, len(rays)).astype(np.float32)
+        assert bits_equal(so.any_hits(rays, tmax), sg.trace_any(rays, tmax))
+
+
+def test_material_probe_bits(orc, gpu, scenes):
+    rng = np.random.default_rng(5)
+    out_o = np.empty(9, np.float32)
+    rows = np.concatenate([scenes['spectrumsphere'][2], scenes['mirrorbox'][2]])
+    for it in range(300):
+        row = rows[it % len(rows)].copy()
+        if it % 3 == 0:
+            row[12:16] = [rng.random(), rng.random(), 1 + rng.random(), rng.random()]
+        n = rng.normal(size=3); n /= np.linalg.norm(n)
+        wo = rng.normal(size=3); wo /= np.linalg.norm(wo)
+        wi = rng.normal(size=3); wi /= np.linalg.norm(wi)
+        wl = float(rng.uniform(380, 700)); seed = int(rng.integers(1, 2 ** 31 - 2))
+        a = [np.ascontiguousarray(v, np.float32) for v in (row, wo, wi, n)]
+        orc.lib().orc_material_probe(a[0], wl, a[1], a[2], a[3], seed, out_o)
+        out_g = gpu.material_probe(a[0], wl, a[1], a[2], a[3], seed)
+        assert bits_equal(out_o, out_g), it
+
+
+@pytest.mark.parametrize('name', ['cornell', 'mirrorbox', 'spectrumsphere'])
+def test_entry_points_bit_exact(orc, pkg, gpu, scenes, name):
+    so, sg = both(orc, pkg, gpu, scenes[name], 60, 80)
+    assert bits_equal(so.sample_n_frames(5), sg.sample_n_frames(5))
+    so, sg = so.key(K['m']), sg.key(K['m'])
+    for _ in range(4):
+        so, sg = so.step(), sg.step()
+    assert bits_equal(so.image(), sg.image()) and bits_equal(so.render(), sg.render())
+    io, ig = so.scalars(), sg.info()
+    assert io['rng'] == ig['rng'] and io['n_frames'] == ig['n_frames'] == 4
+    # camera keys, subsampling, sky, aperture (thin lens -> sin/cos on the device), resize
+    for seq in ([K['w'], K['UP']], [K['K2']], [K['p']], [K['i'], K['i']], [K['t']], [K['t'], K['t']]):
+        a, b = so, sg
+        for k in seq:
+            a, b = a.key(k), b.key(k)
+        a, b = a.step().step(), b.step().step()
+        assert bits_equal(a.image(), b.image()), seq
+        assert bits_equal(a.render(), b.render()), seq
+    a, b = so.resize(33, 47).step(), sg.resize(33, 47).step()
+    assert bits_equal(a.image(), b.image()) and a.image().shape == (33, 47, 3)
+
+
+def test_sample_points_bit_exact(orc, pkg, gpu, scenes):
+    for name in ('cornell', 'spectrumsphere'):
+        so, sg = both(orc, pkg, gpu, scenes[name], 48, 64, cam_conf_id=2)     # demo-save uses cam_conf_id 2 (wrapper.rs:50)
+        (no, po), (ng, pg) = so.sample_points_n(4), sg.sample_points_n(4)
+        assert bits_equal(po, pg) and no.scalars()['rng'] == ng.info()['rng']
+        assert (po[..., 3] > 0).any()
+
+
+def test_path_len_knob(orc, pkg, gpu, scenes):
+    so, sg = both(orc, pkg, gpu, scenes['mirrorbox'], 40, 40)
+    orc.set_path_len(5)
+    gpu.set_path_len(5)
+    try:
+        assert bits_equal(so.probe_pass()['radiance'], sg.probe_pass()['radiance'])
+        assert bits_equal(so.sample_n_frames(3), sg.sample_n_frames(3))
+    finally:
+        orc.set_path_len(16)
+        gpu.set_path_len(16)
+
+
+def test_row_partition_sums_to_full_image(pkg, gpu, scenes):
+    """Multi-GPU split emulated on one device: ranks 0..2 of a world of 3 each render their rows; the sum equals
+    the single-GPU image bit-for-bit (every pixel is non-zero on exactly one rank)."""
+    t, tm, m = scenes['spectrumsphere']
+    full = pkg.State.init(gpu, t, tm, m, 50, 64).sample_n_frames(3)
+    acc = np.zeros_like(full)
+    for r in range(3):
+        c = pkg.Context()
+        c.set_partition(r, 3)
+        part = pkg.State.init(c, t, tm, m, 50, 64).sample_n_frames(3)
+        assert not part[np.arange(50) % 3 != r].any()
+        acc += part
+        c.close()
+    assert bits_equal(acc, full)
+
+
+def test_error_behaviour(pkg, gpu, scenes):
+    t, tm, m = scenes['cornell']
+    with pytest.raises(pkg.TracerError, match='at least 2 triangles'):
+        pkg.State.init(gpu, t[:1], tm[:1], m, 8, 8)
+    with pytest.raises(pkg.TracerError, match='material index'):
+        pkg.State.init(gpu, t, tm + 100, m, 8, 8)
+    import ctypes as C
+    L = gpu._L
+    a = L.futhark_new_f32_3d(gpu._ctx, t.ctypes.data_as(C.c_void_p), len(t), 3, 3)
+    bad = L.futhark_new_f32_2d(gpu._ctx, m.ctypes.data_as(C.c_void_p), 4, 56)       # wrong inner dimension
+    tmv = L.futhark_new_u32_1d(gpu._ctx, tm.ctypes.data_as(C.c_void_p), len(tm))
+    org = L.futhark_new_f32_1d(gpu._ctx, np.zeros(3, np.float32).ctypes.data_as(C.c_void_p), 3)
+    out = C.c_void_p()
+    rc = L.futhark_entry_init(gpu._ctx, C.byref(out), 0, 8, 8, 0, a, tmv, bad, 0.0, 0.0, org)
+    assert rc != 0
+    msg = C.string_at(L.futhark_context_get_error(gpu._ctx)).decode()
+    assert '[m][28]' in msg
+    # the context stays usable after an error
+    assert pkg.State.init(gpu, t, tm, m, 8, 8).step().image().shape == (8, 8, 3)
+
+
+def test_full_size_properties(orc, pkg, gpu, scenes):
+    """BASELINE sizes, through size-independent properties: determinism, partition additivity, and the oracle on a sample of rows."""
+    t, tm, m = scenes['cornell']
+    s = pkg.State.init(gpu, t, tm, m, 1080, 1920)
+    a, b = s.sample_n_frames(2), s.sample_n_frames(2)
+    assert bits_equal(a, b) and np.isfinite(a).all() and a.max() > 0
+    so = orc.State.init(t, tm, m, 1080, 1920)
+    assert bits_equal(so.sample_n_frames(2), a)                       # 2 x 2M paths: a few seconds on the host
+
+
+def test_million_triangle_bvh(orc, pkg, gpu, scenes):
+    t, tm, m = scenes['cornell']
+    st, sm = pkg.scenes.synthetic_cornell(t, tm, 151)
+    sg = pkg.State.init(gpu, st, sm, m, 64, 64)
+    bg = sg.bvh()
+    assert np.all(np.diff(bg['morton'].astype(np.int64)) >= 0)
+    assert np.array_equal(np.sort(bg['src_index']), np.arange(len(st)))
+    same = bg['morton'][1:] == bg['morton'][:-1]
+    assert np.all(bg['src_index'][1:][same] > bg['src_index'][:-1][same])
+    so = orc.State.init(st, sm, m, 64, 64)
+    bo = so.bvh()
+    for key in ('bounds', 'morton', 'src_index', 'left', 'right', 'parent', 'node_aabb'):
+        assert bits_equal(bo[key], bg[key]), key
+    po, pg = so.probe_primary(), sg.probe_primary()
+    assert bits_equal(po['src_tri'], pg['src_tri']) and bits_equal(po['t'], pg['t'])
+    assert bits_equal(so.sample_n_frames(2), sg.sample_n_frames(2))
