@@ -64,7 +64,7 @@ class ClockSampler:
         q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
         try:
-            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q, '--format=csv,noheader,nounits', '-lms', '100'],
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q, '--format=csv,noheader,nounits', '-lms', '20'],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -73,19 +73,26 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(',')])
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(',')]))
+
+    def window(self, t0, t1):
+        self.t0, self.t1 = t0, t1
 
     def stop(self):
         if not self.proc:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.05)
         self.proc.terminate()
         self.th.join(timeout=2)
-        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace('.', '').isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace('.', '').isdigit()]
+        t0, t1 = getattr(self, 't0', 0.0), getattr(self, 't1', float('inf'))
+        inwin = [r for ts, r in self.rows if t0 <= ts <= t1 + 0.03 and len(r) >= 7]
+        rows = inwin if inwin else [r for _, r in self.rows if len(r) >= 7]      # very short regions: fall back to the whole run
+        sm = [float(r[0]) for r in rows if r[0].replace('.', '').isdigit()]
+        mx = [float(r[1]) for r in rows if r[1].replace('.', '').isdigit()]
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith('active')})
+        reasons = sorted({names[i] for r in rows for i in range(4) if r[3 + i].lower().startswith('active')})
         return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': max(mx) if mx else None, 'reasons': reasons,
-                'samples': len(sm)}
+                'samples': len(sm), 'samples_in_timed_region': len(inwin)}
 
 
 def cpu_baseline(oracle, scene, passes, threads=0):
@@ -132,7 +139,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200')
     ap.add_argument('--cpu-passes', type=int, default=2, help='passes of the CPU baseline sample')
@@ -178,19 +185,21 @@ def main():
         return h
 
     # ---- value: state resident in HBM, result left on the device ------------------------------------------
-    for _ in range(args.warmup):
-        state.free_f32_3d(step_resident())
-    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        state.free_f32_3d(step_resident())
+    barrier()
     l0 = ctx.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    tw0 = time.perf_counter()
     e0.record(stream)
     handles = [step_resident() for _ in range(args.steps)]
     e1.record(stream)
     barrier()
+    sampler.window(tw0, time.perf_counter())
     ms = e0.elapsed_time(e1)
     launches = ctx.launches - l0
     clocks = sampler.stop() if rank == 0 else None

@@ -17,7 +17,8 @@ extern "C" {
 /* ---- knobs (per context) ---------------------------------------------------------------- */
 /* Maximum number of path vertices; the reference constant is 16 (integrator.fut:23); 1..16. */
 int lys_context_set_path_len(struct futhark_context *ctx, int path_len);
-/* 0 = reference-exact truncated Jacobi refit (bvh.fut:109-120), 1 = converged boxes. */
+/* 0 = reference-exact truncated Jacobi refit (bvh.fut:109-120), 1 = converged boxes,
+ * 2 = reference-exact through the literal sweeps (slower; the overflow fallback, exposed for cross-checks). */
 int lys_context_set_refit_mode(struct futhark_context *ctx, int mode);
 /* Row-interleaved pixel partition for multi-GPU rendering: this context samples grid rows r with
  * r % world_size == rank; other pixels stay zero so that a sum-reduce over ranks is exact. */

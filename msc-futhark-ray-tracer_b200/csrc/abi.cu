@@ -14,6 +14,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <map>
 #include <memory>
 #include <string>
@@ -223,12 +224,16 @@ bool ensure_scratch(futhark_context *ctx, int64_t n) {
     BuildScratch &w = ctx->scratch;
     if (w.cap >= n) return true;
     raw_free(w.box_c); raw_free(w.box_h); raw_free(w.F); raw_free(w.chunk_lo); raw_free(w.chunk_hi); raw_free(w.keys[0]); raw_free(w.keys[1]); raw_free(w.vals[0]); raw_free(w.vals[1]);
-    raw_free(w.rs_hist); raw_free(w.rs_status); raw_free(w.leaf_parent); raw_free(w.visits);
+    raw_free(w.rs_hist); raw_free(w.rs_status); raw_free(w.leaf_parent); raw_free(w.visits); raw_free(w.crown_box); raw_free(w.crown_cnt);
+    if (w.crown_pairs) { cudaFree(w.crown_pairs); w.crown_pairs = nullptr; }
     w.cap = 0;
     size_t c = (size_t)n, tiles = (c + 4095) / 4096;
     if (!raw_alloc(ctx, w.chunk_lo, (c + 255) / 256) || !raw_alloc(ctx, w.chunk_hi, (c + 255) / 256) || !raw_alloc(ctx, w.box_c, c) || !raw_alloc(ctx, w.box_h, c) || !raw_alloc(ctx, w.F, 2 * c) || !raw_alloc(ctx, w.keys[0], c) ||
         !raw_alloc(ctx, w.keys[1], c) || !raw_alloc(ctx, w.vals[0], c) || !raw_alloc(ctx, w.vals[1], c) || !raw_alloc(ctx, w.rs_hist, 1024) ||
         !raw_alloc(ctx, w.rs_status, 4 * tiles * 256 + 4) || !raw_alloc(ctx, w.leaf_parent, c) || !raw_alloc(ctx, w.visits, c)) return false;
+    w.crown_cap = (int)std::min<size_t>(2 * c + 1024, (size_t)1 << 30);
+    { char *cp = nullptr; if (!raw_alloc(ctx, cp, (size_t)w.crown_cap * 12)) return false; w.crown_pairs = cp; }
+    if (!raw_alloc(ctx, w.crown_box, (size_t)2 * w.crown_cap) || !raw_alloc(ctx, w.crown_cnt, 64)) return false;
     w.cap = n;
     return true;
 }
@@ -308,6 +313,18 @@ uint32_t h_rng_from_seed(int32_t seed) {                                        
 
 futhark_opaque_state *clone_state(const futhark_opaque_state *s) { return new futhark_opaque_state(*s); }
 
+/* LBVH build; if the crown pair buffer overflowed, redo the refit with the literal Jacobi sweeps (always exact) */
+bool build_scene_bvh(futhark_context *ctx, SceneDev &sc, bool check_overflow) {
+    CUB(ctx, build_lbvh(sc, ctx->scratch, ctx->refit_mode, ctx->stream, &ctx->launches));
+    if (check_overflow && ctx->refit_mode == 0) {
+        int ovf = 0;
+        CUB(ctx, cudaMemcpyAsync(&ovf, ctx->scratch.crown_cnt + 63, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CUB(ctx, cudaStreamSynchronize(ctx->stream));
+        if (ovf) CUB(ctx, build_lbvh(sc, ctx->scratch, 2, ctx->stream, &ctx->launches));
+    }
+    return true;
+}
+
 /* sample_frame / sample_frame_accum (integrator.fut:172-192) into `img` */
 bool sample_into(futhark_context *ctx, const futhark_opaque_state *s, uint32_t rng, const float *img_old, float *img_new, bool merge, float n_frames) {
     FrameParams fp;
@@ -368,7 +385,8 @@ void futhark_context_free(struct futhark_context *ctx) {
     raw_free(b.sh_c); raw_free(b.counts); raw_free(b.stats); raw_free(b.tx_lights); raw_free(b.probe_rad); raw_free(b.probe_dist);
     BuildScratch &w = ctx->scratch;
     raw_free(w.box_c); raw_free(w.box_h); raw_free(w.F); raw_free(w.chunk_lo); raw_free(w.chunk_hi); raw_free(w.keys[0]); raw_free(w.keys[1]); raw_free(w.vals[0]); raw_free(w.vals[1]);
-    raw_free(w.rs_hist); raw_free(w.rs_status); raw_free(w.leaf_parent); raw_free(w.visits);
+    raw_free(w.rs_hist); raw_free(w.rs_status); raw_free(w.leaf_parent); raw_free(w.visits); raw_free(w.crown_box); raw_free(w.crown_cnt);
+    if (w.crown_pairs) cudaFree(w.crown_pairs);
     raw_free(ctx->pts_pos); raw_free(ctx->pts_dist);
     for (auto &kv : ctx->pool) cudaFree(kv.second);
     ctx->pool.clear();
@@ -469,7 +487,7 @@ int futhark_entry_init(struct futhark_context *ctx, struct futhark_opaque_state 
     }
     if (!ensure_scratch(ctx, n)) return 1;
     CU(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-    CU(ctx, build_lbvh(sc, ctx->scratch, ctx->refit_mode, ctx->stream, &ctx->launches));
+    if (!build_scene_bvh(ctx, sc, true)) return 1;
     CU(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     cudaEventElapsedTime(&sc.build_ms, ctx->ev0, ctx->ev1);
@@ -653,7 +671,7 @@ int lys_context_set_path_len(struct futhark_context *ctx, int path_len) {
     if (!ctx || path_len < 1 || path_len > LYS_MAX_PATH_LEN) { if (ctx) set_error(ctx, "path_len must be in 1..16"); return 1; }
     ctx->path_len = path_len; return 0;
 }
-int lys_context_set_refit_mode(struct futhark_context *ctx, int mode) { if (!ctx) return 1; ctx->refit_mode = mode ? 1 : 0; return 0; }
+int lys_context_set_refit_mode(struct futhark_context *ctx, int mode) { if (!ctx || mode < 0 || mode > 2) return 1; ctx->refit_mode = mode; return 0; }
 int lys_context_set_partition(struct futhark_context *ctx, int rank, int world_size) {
     if (!ctx || world_size < 1 || rank < 0 || rank >= world_size) { if (ctx) set_error(ctx, "bad partition"); return 1; }
     ctx->rank = rank; ctx->world = world_size; return 0;
@@ -743,7 +761,7 @@ int lys_state_bvh_rebuild_timed(struct futhark_context *ctx, const struct futhar
     float total = 0.0f;
     for (int r = 0; r < reps; r++) {
         CU(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-        CU(ctx, build_lbvh(d, ctx->scratch, ctx->refit_mode, ctx->stream, &ctx->launches));
+        if (!build_scene_bvh(ctx, d, false)) return 1;
         CU(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
         CU(ctx, cudaStreamSynchronize(ctx->stream));
         float t = 0.0f; cudaEventElapsedTime(&t, ctx->ev0, ctx->ev1); total += t;

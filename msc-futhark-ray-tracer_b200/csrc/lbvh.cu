@@ -11,9 +11,9 @@
  *   k_gather_leaves  bvh.fut:95 (unzip3) sorted triangles / boxes
  *   k_karras         radix_tree.fut:31-88 internal nodes + parent pointers
  *   k_refit          bvh.fut:105-120     converged boxes F and node heights, atomic bottom-up
- *   k_crown_fixup    bvh.fut:109,118-120 the reference stops after floor(log2 n)+2 Jacobi sweeps from
+ *   k_crown_*        bvh.fut:109,118-120 the reference stops after floor(log2 n)+2 Jacobi sweeps from
  *                                        zero boxes; nodes higher than that keep truncated boxes,
- *                                        recomputed here exactly
+ *                                        recomputed here exactly through level-synchronous worklists
  *   k_pack_nodes                         traversal layout: 2 x float4 per node (min|left, max|right)
  */
 #include "lys_scene.h"
@@ -79,40 +79,64 @@ __global__ void __launch_bounds__(BOX_CHUNK) k_tri_boxes(const float *__restrict
  *     commits it, and the step restarts behind that element.
  * State changes are rare (a few hundred per million triangles), so the walk is O(#chunks/32) warp
  * steps plus the dirty chunks.  The result equals the sequential fold for any input. */
-#define FOLD_THREADS BOX_CHUNK
-__device__ __forceinline__ Box shfl_box(Box b, int src) {
-    Box r;
-    r.c.x = __shfl_sync(0xffffffffu, b.c.x, src); r.c.y = __shfl_sync(0xffffffffu, b.c.y, src); r.c.z = __shfl_sync(0xffffffffu, b.c.z, src);
-    r.h.x = __shfl_sync(0xffffffffu, b.h.x, src); r.h.y = __shfl_sync(0xffffffffu, b.h.y, src); r.h.z = __shfl_sync(0xffffffffu, b.h.z, src);
-    return r;
+#define FOLD_THREADS 1024
+#define FOLD_GRANULE 1024      /* elements staged per dirty step = 4 chunks */
+#define FOLD_MAX_SUPER 1024    /* super-chunk (32 chunks) unions kept in shared memory */
+struct Corner { float lo[3], hi[3]; };
+__device__ __forceinline__ bool corners_inside(const float4 &l, const float4 &h, const V3 &slo, const V3 &shi) {
+    return l.x >= slo.x && l.y >= slo.y && l.z >= slo.z && h.x <= shi.x && h.y <= shi.y && h.z <= shi.z;   /* false on NaN */
 }
 __global__ void __launch_bounds__(FOLD_THREADS, 1)
 k_bounds_fold(const float4 *__restrict__ box_c, const float4 *__restrict__ box_h, const float4 *__restrict__ chunk_lo,
               const float4 *__restrict__ chunk_hi, int n, float *__restrict__ bounds_out /* 6 */) {
-    __shared__ float4 sc[BOX_CHUNK], sh[BOX_CHUNK];
+    __shared__ float4 sup_lo[FOLD_MAX_SUPER], sup_hi[FOLD_MAX_SUPER];
     __shared__ Box S_sh;
-    __shared__ int next_chunk;       /* first chunk (>= cursor) that must be folded element-wise, or n_chunks */
+    __shared__ int next_chunk, first_changed;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n_chunks = (n + BOX_CHUNK - 1) / BOX_CHUNK;
+    const int n_super = (n_chunks + 31) / 32;
+    const int n_super_sm = min(n_super, FOLD_MAX_SUPER);
+    /* prologue: unions of 32 chunk unions (8192 triangles) */
+    for (int sidx = warp; sidx < n_super_sm; sidx += FOLD_THREADS / 32) {
+        int j = sidx * 32 + lane;
+        float4 l = make_float4(LYS_INF, LYS_INF, LYS_INF, 0.0f), h = make_float4(-LYS_INF, -LYS_INF, -LYS_INF, 0.0f);
+        bool bad = false;
+        if (j < n_chunks) { l = __ldg(chunk_lo + j); h = __ldg(chunk_hi + j); bad = (l.x != l.x); }
+        l.x = warp_min(l.x); l.y = warp_min(l.y); l.z = warp_min(l.z); h.x = warp_max(h.x); h.y = warp_max(h.y); h.z = warp_max(h.z);
+        if (__ballot_sync(0xffffffffu, bad)) { float q = lys_u2f(0x7fc00000u); l = make_float4(q, q, q, 0.0f); h = l; }
+        if (lane == 0) { sup_lo[sidx] = l; sup_hi[sidx] = h; }
+    }
     Box S; S.c = v3(0.0f, 0.0f, 0.0f); S.h = v3(-LYS_INF, -LYS_INF, -LYS_INF);            /* bvh.fut:88-89 */
+    __syncthreads();
     int cursor = 0;
     while (cursor < n_chunks) {
-        /* warp 0: skip clean chunks, 32 at a time (all threads hold the same S) */
+        /* warp 0: find the first chunk >= cursor that S does not provably absorb */
         if (warp == 0) {
-            bool stable = box_bits_equal(contain(S, S), S);
-            V3 slo = S.c - S.h, shi = S.c + S.h;
             int c = cursor;
-            if (stable) {
+            if (box_bits_equal(contain(S, S), S)) {
+                V3 slo = S.c - S.h, shi = S.c + S.h;
                 while (c < n_chunks) {
-                    int j = c + lane;
-                    bool dirty = false;
-                    if (j < n_chunks) {
-                        float4 l = __ldg(chunk_lo + j), h = __ldg(chunk_hi + j);
-                        dirty = !(l.x >= slo.x && l.y >= slo.y && l.z >= slo.z && h.x <= shi.x && h.y <= shi.y && h.z <= shi.z);
+                    if ((c & 31) == 0 && (c >> 5) < n_super_sm) {          /* aligned + indexed: try whole super-chunks first */
+                        int s0 = c >> 5;
+                        bool found = false;
+                        while (s0 < n_super_sm) {
+                            int sj = s0 + lane;
+                            bool dirty = (sj < n_super_sm) && !corners_inside(sup_lo[sj], sup_hi[sj], slo, shi);
+                            unsigned m = __ballot_sync(0xffffffffu, dirty);
+                            if (m) { s0 += __ffs(m) - 1; found = true; break; }
+                            s0 += 32;
+                        }
+                        c = min(s0, n_super_sm) << 5;
+                        if (!found && n_super_sm == n_super) { c = n_chunks; break; }
+                        if (c >= n_chunks) { c = n_chunks; break; }
                     }
+                    /* chunk level inside the current (dirty or unindexed) super-chunk */
+                    int j = (c & ~31) + lane;
+                    bool dirty = false;
+                    if (j >= c && j < n_chunks) dirty = !corners_inside(__ldg(chunk_lo + j), __ldg(chunk_hi + j), slo, shi);
                     unsigned m = __ballot_sync(0xffffffffu, dirty);
-                    if (m) { c += __ffs(m) - 1; break; }
-                    c += 32;
+                    if (m) { c = (c & ~31) + __ffs(m) - 1; break; }
+                    c = (c & ~31) + 32;
                 }
                 if (c > n_chunks) c = n_chunks;
             }
@@ -121,35 +145,28 @@ k_bounds_fold(const float4 *__restrict__ box_c, const float4 *__restrict__ box_h
         __syncthreads();
         cursor = next_chunk;
         if (cursor >= n_chunks) break;
-        /* stage the dirty chunk */
+        /* fold a granule of FOLD_GRANULE elements starting at the dirty chunk, all threads testing in parallel */
         const int base = cursor * BOX_CHUNK;
-        const int limit = min(BOX_CHUNK, n - base);
-        if (tid < limit) { sc[tid] = box_c[base + tid]; sh[tid] = box_h[base + tid]; }
-        __syncthreads();
-        if (warp == 0) {
-            Box s = S;
-            int p = 0;
-            while (p < limit) {
-                int e = p + lane;
-                Box ns = s; bool ch = false;
-                if (e < limit) {
-                    float4 c4 = sc[e], h4 = sh[e];
-                    Box b; b.c = v3(c4.x, c4.y, c4.z); b.h = v3(h4.x, h4.y, h4.z);
-                    ns = contain(s, b);
-                    ch = !box_bits_equal(ns, s);
-                }
-                unsigned m = __ballot_sync(0xffffffffu, ch);
-                if (!m) { p += 32; continue; }
-                int k = __ffs(m) - 1;
-                s = shfl_box(ns, k);
-                p += k + 1;
-            }
-            if (lane == 0) S_sh = s;
+        const int limit = min(FOLD_GRANULE, n - base);
+        Box mine; mine.c = v3(0.0f, 0.0f, 0.0f); mine.h = mine.c;
+        if (tid < limit) { float4 c4 = box_c[base + tid], h4 = box_h[base + tid]; mine.c = v3(c4.x, c4.y, c4.z); mine.h = v3(h4.x, h4.y, h4.z); }
+        int start = 0;
+        while (true) {
+            if (tid == 0) first_changed = 0x7fffffff;
+            __syncthreads();
+            Box ns = S; bool ch = false;
+            if (tid >= start && tid < limit) { ns = contain(S, mine); ch = !box_bits_equal(ns, S); }
+            unsigned m = __ballot_sync(0xffffffffu, ch);
+            if (m && lane == __ffs(m) - 1) atomicMin(&first_changed, tid);
+            __syncthreads();
+            int f = first_changed;
+            if (f == 0x7fffffff) break;
+            if (tid == f) S_sh = ns;
+            __syncthreads();
+            S = S_sh;
+            start = f + 1;
         }
-        __syncthreads();
-        S = S_sh;
-        cursor++;
-        __syncthreads();
+        cursor += (limit + BOX_CHUNK - 1) / BOX_CHUNK;
     }
     if (tid == 0) {
         bounds_out[0] = S.c.x; bounds_out[1] = S.c.y; bounds_out[2] = S.c.z;
@@ -377,55 +394,83 @@ __global__ void k_refit(const int *__restrict__ left, const int *__restrict__ ri
 }
 
 /* ------------------------------------------------------------------ truncated-Jacobi fix-up
- * After `depth` sweeps from zero boxes a node of height <= depth holds its converged box F; a taller
- * node holds A_depth(v) with A_k(v) = contain(A_{k-1}(left), A_{k-1}(right)), A_0 = {0,0}, leaves exact. */
-struct CrownFrame { int node, k, stage; Box lbox; };
-__device__ Box crown_eval(int root, int depth, const int *left, const int *right, const float4 *leaf_box,
-                          const float4 *F, const int *height) {
-    CrownFrame st[40];                 /* depth <= 33 for n < 2^31 */
-    int sp = 0;
-    st[0].node = root; st[0].k = depth; st[0].stage = 0;
-    Box ret; ret.c = v3(0.0f, 0.0f, 0.0f); ret.h = v3(0.0f, 0.0f, 0.0f);
-    bool have_ret = false;
-    while (true) {
-        CrownFrame &f = st[sp];
-        if (have_ret) {
-            have_ret = false;
-            if (f.stage == 0) { f.lbox = ret; f.stage = 1; }
-            else {
-                ret = contain(f.lbox, ret);            /* bvh.fut:115-116: (left, right) */
-                if (sp == 0) return ret;
-                sp--; have_ret = true;
-                continue;
+ * The reference runs `depth` = floor(log2 n)+2 Jacobi sweeps from zero boxes (bvh.fut:105-120).  After them a
+ * node of height <= depth holds its converged box F; a taller ("crown") node holds A_depth(v) with
+ *     A_k(v) = contain(A_{k-1}(left), A_{k-1}(right)),  A_0(internal) = {0,0},  A_k(leaf) = leaf box,
+ * and A_k(u) = F(u) whenever height(u) <= k.  The (node, k) pairs that are NOT resolved by those rules are
+ * discovered top-down from the crown nodes, one level per launch (k_crown_expand), then evaluated bottom-up
+ * (k_crown_eval).  Level j holds the pairs with k = depth - j; level sizes live on the device.
+ * If the pair buffer overflows (adversarially deep trees) the literal Jacobi sweeps are run instead. */
+struct CrownPair { int node; int child[2]; };    /* child slot (absolute) or -1 = resolved by rule */
+__device__ __forceinline__ int crown_level_base(const int *cnt, int level) { int b = 0; for (int q = 0; q < level; q++) b += cnt[q]; return b; }
+__global__ void k_crown_find(const float4 *__restrict__ F, const int *__restrict__ height, int n_nodes, int depth,
+                             float4 *__restrict__ A, CrownPair *pairs, int *cnt, int cap, int *overflow) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_nodes) return;
+    A[2ll * i] = F[2ll * i]; A[2ll * i + 1] = F[2ll * i + 1];
+    if (height[i] > depth) {
+        int slot = atomicAdd(&cnt[0], 1);
+        if (slot < cap) { pairs[slot].node = i; pairs[slot].child[0] = -1; pairs[slot].child[1] = -1; } else *overflow = 1;
+    }
+}
+__global__ void k_crown_expand(const int *__restrict__ left, const int *__restrict__ right, const int *__restrict__ height,
+                               CrownPair *pairs, int *cnt, int level, int depth, int cap, int *overflow) {
+    const int base = crown_level_base(cnt, level), count = min(cnt[level], max(cap - base, 0));
+    const int next_base = base + cnt[level];
+    const int k = depth - level;                 /* pairs of this level carry k; children carry k - 1 */
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < count; p += gridDim.x * blockDim.x) {
+        CrownPair pr = pairs[base + p];
+        int ch[2] = {left[pr.node], right[pr.node]};
+#pragma unroll
+        for (int sde = 0; sde < 2; sde++) {
+            int c = ch[sde], slot = -1;
+            if (c >= 0 && k - 1 >= 1 && height[c] > k - 1) {
+                slot = next_base + atomicAdd(&cnt[level + 1], 1);
+                if (slot < cap) { pairs[slot].node = c; pairs[slot].child[0] = -1; pairs[slot].child[1] = -1; } else { *overflow = 1; slot = -1; }
             }
-        }
-        int child = (f.stage == 0) ? left[f.node] : right[f.node];
-        int ck = f.k - 1;
-        if (child < 0) {
-            float4 c = leaf_box[2ll * (~child)], h = leaf_box[2ll * (~child) + 1];
-            ret.c = v3(c.x, c.y, c.z); ret.h = v3(h.x, h.y, h.z); have_ret = true;
-        } else if (height[child] <= ck) {
-            float4 c = F[2ll * child], h = F[2ll * child + 1];
-            ret.c = v3(c.x, c.y, c.z); ret.h = v3(h.x, h.y, h.z); have_ret = true;
-        } else if (ck == 0) {
-            ret.c = v3(0.0f, 0.0f, 0.0f); ret.h = v3(0.0f, 0.0f, 0.0f); have_ret = true;   /* bvh.fut:105-107 */
-        } else {
-            sp++;
-            st[sp].node = child; st[sp].k = ck; st[sp].stage = 0;
+            pairs[base + p].child[sde] = slot;
         }
     }
 }
-__global__ void k_crown_fixup(const int *__restrict__ left, const int *__restrict__ right, const float4 *__restrict__ leaf_box,
-                              const float4 *__restrict__ F, const int *__restrict__ height, int n_nodes, int depth,
-                              float4 *__restrict__ A /* [n-1][2] */, int converged) {
+__device__ __forceinline__ Box crown_child_box(int c, int slot, int ck, const float4 *leaf_box, const float4 *F, const float4 *pbox) {
+    const float4 *src;
+    if (c < 0) src = leaf_box + 2ll * (~c);
+    else if (slot >= 0) src = pbox + 2ll * slot;
+    else if (ck == 0) { Box z; z.c = v3(0.0f, 0.0f, 0.0f); z.h = v3(0.0f, 0.0f, 0.0f); return z; }   /* bvh.fut:105-107 */
+    else src = F + 2ll * c;                          /* height(c) <= ck: converged */
+    float4 a = src[0], b = src[1];
+    Box r; r.c = v3(a.x, a.y, a.z); r.h = v3(b.x, b.y, b.z); return r;
+}
+__global__ void k_crown_eval(const int *__restrict__ left, const int *__restrict__ right, const float4 *__restrict__ leaf_box,
+                             const float4 *__restrict__ F, const CrownPair *__restrict__ pairs, float4 *pbox, const int *__restrict__ cnt,
+                             int level, int depth, int cap, float4 *__restrict__ A) {
+    const int base = crown_level_base(cnt, level), count = min(cnt[level], max(cap - base, 0));
+    const int k = depth - level;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < count; p += gridDim.x * blockDim.x) {
+        CrownPair pr = pairs[base + p];
+        int l = left[pr.node], r = right[pr.node];
+        Box b = contain(crown_child_box(l, pr.child[0], k - 1, leaf_box, F, pbox), crown_child_box(r, pr.child[1], k - 1, leaf_box, F, pbox));
+        float4 c4 = make_float4(b.c.x, b.c.y, b.c.z, 0.0f), h4 = make_float4(b.h.x, b.h.y, b.h.z, 0.0f);
+        pbox[2ll * (base + p)] = c4; pbox[2ll * (base + p) + 1] = h4;
+        if (level == 0) { A[2ll * pr.node] = c4; A[2ll * pr.node + 1] = h4; }
+    }
+}
+/* the reference's own sweep (bvh.fut:114-120), ping-pong; used when the pair buffer overflows */
+__global__ void k_jacobi_sweep(const int *__restrict__ left, const int *__restrict__ right, const float4 *__restrict__ leaf_box,
+                               const float4 *__restrict__ in, float4 *__restrict__ out, int n_nodes) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_nodes) return;
-    float4 c = F[2ll * i], h = F[2ll * i + 1];
-    if (!converged && height[i] > depth) {
-        Box b = crown_eval(i, depth, left, right, leaf_box, F, height);
-        c = make_float4(b.c.x, b.c.y, b.c.z, 0.0f); h = make_float4(b.h.x, b.h.y, b.h.z, 0.0f);
-    }
-    A[2ll * i] = c; A[2ll * i + 1] = h;
+    int l = left[i], r = right[i];
+    const float4 *pl = (l < 0) ? leaf_box + 2ll * (~l) : in + 2ll * l;
+    const float4 *pr = (r < 0) ? leaf_box + 2ll * (~r) : in + 2ll * r;
+    float4 a = pl[0], b = pl[1], c = pr[0], d = pr[1];
+    Box bl, br; bl.c = v3(a.x, a.y, a.z); bl.h = v3(b.x, b.y, b.z); br.c = v3(c.x, c.y, c.z); br.h = v3(d.x, d.y, d.z);
+    Box o = contain(bl, br);
+    out[2ll * i] = make_float4(o.c.x, o.c.y, o.c.z, 0.0f); out[2ll * i + 1] = make_float4(o.h.x, o.h.y, o.h.z, 0.0f);
+}
+__global__ void k_copy_f4(const float4 *__restrict__ in, float4 *__restrict__ out, long long n) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i];
 }
 
 /* traversal layout: node i -> (min.xyz | left), (max.xyz | right); min/max as hit_aabb derives them (shapes.fut:120) */
@@ -471,8 +516,21 @@ cudaError_t build_lbvh(SceneDev &sc, BuildScratch &ws, int refit_mode, cudaStrea
     k_karras<<<cdiv(n_nodes, T), T, 0, stream>>>(sc.morton, n, sc.left, sc.right, sc.parent, ws.leaf_parent); nl++;
     cudaMemsetAsync(ws.visits, 0, (size_t)n_nodes * sizeof(unsigned int), stream);
     k_refit<<<cdiv(n, T), T, 0, stream>>>(sc.left, sc.right, sc.parent, ws.leaf_parent, sc.leaf_box, ws.F, sc.height, ws.visits, n); nl++;
-    int depth = (int)(log2f((float)n)) + 2;                                 /* bvh.fut:109 */
-    k_crown_fixup<<<cdiv(n_nodes, T), T, 0, stream>>>(sc.left, sc.right, sc.leaf_box, ws.F, sc.height, n_nodes, depth, sc.node_box, refit_mode); nl++;
+    const int depth = (int)(log2f((float)n)) + 2;                           /* bvh.fut:109 */
+    if (refit_mode == 1) {                                                  /* converged boxes */
+        k_copy_f4<<<cdiv(2ll * n_nodes, T), T, 0, stream>>>(ws.F, sc.node_box, 2ll * n_nodes); nl++;
+    } else if (refit_mode == 2) {                                           /* literal Jacobi sweeps (fallback / cross-check) */
+        cudaMemsetAsync(ws.F, 0, (size_t)2 * n_nodes * sizeof(float4), stream);     /* zero boxes, bvh.fut:105-107 */
+        float4 *a = ws.F, *b = sc.node_box;
+        for (int it = 0; it < depth; it++) { k_jacobi_sweep<<<cdiv(n_nodes, T), T, 0, stream>>>(sc.left, sc.right, sc.leaf_box, a, b, n_nodes); nl++; float4 *t = a; a = b; b = t; }
+        if (a != sc.node_box) { k_copy_f4<<<cdiv(2ll * n_nodes, T), T, 0, stream>>>(a, sc.node_box, 2ll * n_nodes); nl++; }
+    } else {
+        cudaMemsetAsync(ws.crown_cnt, 0, 64 * sizeof(int), stream);
+        k_crown_find<<<cdiv(n_nodes, T), T, 0, stream>>>(ws.F, sc.height, n_nodes, depth, sc.node_box, (CrownPair *)ws.crown_pairs, ws.crown_cnt, ws.crown_cap, ws.crown_cnt + 63); nl++;
+        const int G = 148 * 4;
+        for (int lv = 0; lv < depth - 1; lv++) { k_crown_expand<<<G, T, 0, stream>>>(sc.left, sc.right, sc.height, (CrownPair *)ws.crown_pairs, ws.crown_cnt, lv, depth, ws.crown_cap, ws.crown_cnt + 63); nl++; }
+        for (int lv = depth - 1; lv >= 0; lv--) { k_crown_eval<<<G, T, 0, stream>>>(sc.left, sc.right, sc.leaf_box, ws.F, (const CrownPair *)ws.crown_pairs, ws.crown_box, ws.crown_cnt, lv, depth, ws.crown_cap, sc.node_box); nl++; }
+    }
     k_pack_nodes<<<cdiv(n_nodes, T), T, 0, stream>>>(sc.node_box, sc.left, sc.right, n_nodes, sc.nodes); nl++;
     if (launches) *launches += nl;
     return cudaGetLastError();

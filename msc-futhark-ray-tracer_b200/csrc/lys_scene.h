@@ -45,8 +45,10 @@ struct BuildScratch {
     uint32_t *keys[2] = {nullptr, nullptr}, *vals[2] = {nullptr, nullptr};
     uint32_t *rs_hist = nullptr, *rs_status = nullptr;
     int *leaf_parent = nullptr; unsigned int *visits = nullptr;
+    void *crown_pairs = nullptr; float4 *crown_box = nullptr; int *crown_cnt = nullptr; int crown_cap = 0;   /* cnt[0..62] level sizes, cnt[63] overflow flag */
 };
 
+/* refit_mode: 0 reference-exact (truncated Jacobi via crown worklists), 1 converged, 2 reference-exact via literal sweeps */
 cudaError_t build_lbvh(SceneDev &sc, BuildScratch &ws, int refit_mode, cudaStream_t stream, uint64_t *launches);
 /* lights: gathers emissive triangles (indices in input order) into LightRec */
 cudaError_t build_lights(SceneDev &sc, const int *light_src_dev, int n_lights, cudaStream_t stream, uint64_t *launches);

@@ -8,8 +8,14 @@ pytestmark = pytest.mark.gpu
 K = dict(SPACE=0x20, K1=0x31, K2=0x32, m=0x6D, t=0x74, p=0x70, w=0x77, UP=0x40000052, i=0x69)
 
 
-def both(orc, pkg, gpu, scene, h, w, **kw):
+# The default camera (0, 0.8, 1.8) is OUTSIDE MirrorBox's front wall and sees nothing; its tests look from inside.
+ORIGIN = {'mirrorbox': (0.0, 0.8, 0.6)}
+
+
+def both(orc, pkg, gpu, scene, h, w, name=None, **kw):
     t, tm, m = scene
+    if name in ORIGIN:
+        kw.setdefault('origin', ORIGIN[name])
     return orc.State.init(t, tm, m, h, w, **kw), pkg.State.init(gpu, t, tm, m, h, w, **kw)
 
 
@@ -79,9 +85,23 @@ def test_refit_converged_mode(orc, pkg, gpu, scenes):
         assert (lo_c >= lo_p - 1e-5).all() and (hi_c <= hi_p + 1e-5).all()
 
 
+def test_refit_literal_sweeps_equal_worklists(pkg, gpu, scenes):
+    """refit mode 2 (the reference's own Jacobi sweeps, also the overflow fallback) == mode 0 (crown worklists)."""
+    t, tm, m = scenes['cornell']
+    st, sm = pkg.scenes.synthetic_cornell(t, tm, 40)
+    for tris, mats_ix, mm in ((scenes['spectrumspherehigh'][0], scenes['spectrumspherehigh'][1], scenes['spectrumspherehigh'][2]), (st, sm, m)):
+        a = pkg.State.init(gpu, tris, mats_ix, mm, 4, 4).bvh()['node_aabb']
+        gpu.set_refit_mode(2)
+        try:
+            b = pkg.State.init(gpu, tris, mats_ix, mm, 4, 4).bvh()['node_aabb']
+        finally:
+            gpu.set_refit_mode(0)
+        assert bits_equal(a, b)
+
+
 @pytest.mark.parametrize('name', SCENE_NAMES)
 def test_first_hit_bit_exact(orc, pkg, gpu, scenes, name):
-    so, sg = both(orc, pkg, gpu, scenes[name], 120, 160)
+    so, sg = both(orc, pkg, gpu, scenes[name], 120, 160, name=name)
     po, pg = so.probe_primary(), sg.probe_primary()
     assert bits_equal(po['leaf'], pg['leaf']) and bits_equal(po['src_tri'], pg['src_tri']) and bits_equal(po['t'], pg['t'])
     assert (po['leaf'] >= 0).mean() > 0.5
@@ -90,7 +110,7 @@ def test_first_hit_bit_exact(orc, pkg, gpu, scenes, name):
 @pytest.mark.parametrize('name', SCENE_NAMES)
 @pytest.mark.parametrize('conf', [0, 1, 2])
 def test_pass_radiance_bit_exact(orc, pkg, gpu, scenes, name, conf):
-    so, sg = both(orc, pkg, gpu, scenes[name], 72, 96, cam_conf_id=conf)
+    so, sg = both(orc, pkg, gpu, scenes[name], 72, 96, name=name, cam_conf_id=conf)
     qo, qg = so.probe_pass(), sg.probe_pass()
     assert bits_equal(qo['channel'], qg['channel'])
     assert bits_equal(qo['distance'], qg['distance'])
@@ -130,8 +150,9 @@ def test_material_probe_bits(orc, gpu, scenes):
 
 @pytest.mark.parametrize('name', ['cornell', 'mirrorbox', 'spectrumsphere'])
 def test_entry_points_bit_exact(orc, pkg, gpu, scenes, name):
-    so, sg = both(orc, pkg, gpu, scenes[name], 60, 80)
-    assert bits_equal(so.sample_n_frames(5), sg.sample_n_frames(5))
+    so, sg = both(orc, pkg, gpu, scenes[name], 60, 80, name=name)
+    io5 = so.sample_n_frames(5)
+    assert bits_equal(io5, sg.sample_n_frames(5)) and io5.max() > 0
     so, sg = so.key(K['m']), sg.key(K['m'])
     for _ in range(4):
         so, sg = so.step(), sg.step()
@@ -159,7 +180,7 @@ def test_sample_points_bit_exact(orc, pkg, gpu, scenes):
 
 
 def test_path_len_knob(orc, pkg, gpu, scenes):
-    so, sg = both(orc, pkg, gpu, scenes['mirrorbox'], 40, 40)
+    so, sg = both(orc, pkg, gpu, scenes['mirrorbox'], 40, 40, name='mirrorbox')
     orc.set_path_len(5)
     gpu.set_path_len(5)
     try:

@@ -33,8 +33,9 @@ def main():
     for name in scenes:
         d = np.load(os.path.join(ROOT, 'tests', 'golden', 'scenes', name + '.npz'))
         h, w = 96, 128
-        so = oracle.State.init(d['tris'], d['tri_mats'], d['mats'], h, w)
-        sg = pkg.State.init(ctx, d['tris'], d['tri_mats'], d['mats'], h, w)
+        kw = {'origin': (0.0, 0.8, 0.6)} if name == 'mirrorbox' else {}
+        so = oracle.State.init(d['tris'], d['tri_mats'], d['mats'], h, w, **kw)
+        sg = pkg.State.init(ctx, d['tris'], d['tri_mats'], d['mats'], h, w, **kw)
         bo, bg = so.bvh(), sg.bvh()
         r = {k: bool(beq(bo[k], bg[k])) for k in ('bounds', 'morton', 'src_index', 'left', 'right', 'parent', 'node_aabb', 'leaf_aabb')}
         if not r['node_aabb']:
