@@ -12,6 +12,7 @@
 #include "../../include/lys_detmath.h"
 
 #define LYS_D __device__ __forceinline__
+#define LYS_DN static __device__ __noinline__     /* big shading routines: keep k_shade inside the instruction cache */
 #define LYS_HDI __host__ __device__ __forceinline__
 
 #define LYS_PI 3.14159265358979323846f
@@ -172,7 +173,7 @@ LYS_D float schlick(V3 wo, const Mat1 &m) {                                     
     return r0 + (1.0f - r0) * det_pow5f(1.0f - wo.z);
 }
 /* Torrance-Sparrow reflection value (:264-266) and its pdf (:298-302), sharing D(wh). */
-LYS_D void reflection_terms(V3 wo, V3 wi, const Mat1 &m, float &bsdf, float &pdf) {
+LYS_DN void reflection_terms(V3 wo, V3 wi, const Mat1 &m, float &bsdf, float &pdf) {
     float alpha = beckmann_alpha(m.roughness);
     V3 wh = normalise(wi + wo);
     float D = beckmann_d(alpha, wh);
@@ -181,7 +182,7 @@ LYS_D void reflection_terms(V3 wo, V3 wi, const Mat1 &m, float &bsdf, float &pdf
     pdf = same_hemi(wo, wi) ? (D * lys_fabsf(wh.z)) / (4.0f * dot(wo, wh)) : 0.0f;
 }
 /* uber_bsdf (:357-358) and uber_pdf (:360-361, operands as written in the reference) in local space */
-LYS_D void uber_eval(V3 wo, V3 wi, const Mat1 &m, float &f, float &pdf) {
+LYS_DN void uber_eval(V3 wo, V3 wi, const Mat1 &m, float &f, float &pdf) {
     float refl_f, refl_pdf;
     reflection_terms(wo, wi, m, refl_f, refl_pdf);
     float refr_f = lerpf(0.0f, m.color * LYS_INV_PI, m.opacity);                              /* :187-188 */
@@ -195,7 +196,7 @@ LYS_D void uber_eval(V3 wo, V3 wi, const Mat1 &m, float &f, float &pdf) {
     pdf = lerpf(refl_pdf, diel_pdf, m.metalness);
 }
 /* dielectric_reflection_sample_dir (:305-315), with sample_wh (:283-296) */
-LYS_D DirSample sample_reflection(V3 wo, const Mat1 &m, uint32_t &rng) {
+LYS_DN DirSample sample_reflection(V3 wo, const Mat1 &m, uint32_t &rng) {
     float u0 = rng_unit(rng), u1 = rng_unit(rng);
     float ls = det_logf(1.0f - u0);
     V3 wh; float pdf_wh;
@@ -220,7 +221,7 @@ LYS_D DirSample sample_reflection(V3 wo, const Mat1 &m, uint32_t &rng) {
     return s;
 }
 /* dielectric_refraction_sample_dir (:195-200): Lambert (:106-129) or delta transmission (:132-183) */
-LYS_D DirSample sample_refraction(V3 wo, const Mat1 &m, uint32_t &rng) {
+LYS_DN DirSample sample_refraction(V3 wo, const Mat1 &m, uint32_t &rng) {
     DirSample s;
     float p = rng_unit(rng);
     if (p < m.opacity) {
@@ -242,17 +243,17 @@ LYS_D DirSample sample_refraction(V3 wo, const Mat1 &m, uint32_t &rng) {
     return s;
 }
 /* sample_dir (:406-410) = uber_sample_dir (:365-370) in the local frame */
-LYS_D DirSample sample_bsdf(V3 wo_world, const Onb &onb, const Mat1 &m, uint32_t &rng) {
+LYS_DN DirSample sample_bsdf(V3 wo_world, const Onb &onb, const Mat1 &m, uint32_t &rng) {
     V3 wo = to_local(onb, wo_world);
     DirSample s;
     float p = rng_unit(rng);
-    if (p < m.metalness) { s = sample_reflection(wo, m, rng); s.bsdf = m.color * s.bsdf; }      /* metal :352-355 */
-    else if (wo.z <= 0.0f) s = sample_refraction(wo, m, rng);                                  /* :338-339 */
-    else {
-        float r = schlick(wo, m);
-        float q = rng_unit(rng);
-        s = (q < r) ? sample_reflection(wo, m, rng) : sample_refraction(wo, m, rng);           /* :340-344 */
-    }
+    bool metal = p < m.metalness;                                                              /* metal :352-355 */
+    bool reflect;
+    if (metal) reflect = true;
+    else if (wo.z <= 0.0f) reflect = false;                                                    /* :338-339 */
+    else { float r = schlick(wo, m); float q = rng_unit(rng); reflect = q < r; }               /* :340-344 */
+    if (reflect) { s = sample_reflection(wo, m, rng); if (metal) s.bsdf = m.color * s.bsdf; }
+    else s = sample_refraction(wo, m, rng);
     s.wi = to_world(onb, s.wi);
     return s;
 }

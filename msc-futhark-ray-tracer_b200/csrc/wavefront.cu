@@ -4,17 +4,19 @@
  * (reference src/integrator.fut:103-116, one thread running `path_trace` :27-76 to completion) by
  * queue-driven stages, one launch per stage and bounce:
  *   k_generate   camera.fut:68-110, integrator.fut:78-93,109-115   wavelength + primary ray per pixel
- *   k_extend     bvh.fut:123-145 (closest_hit)                      first hit of every live ray
+ *   k_trace      bvh.fut:123-145 (closest_hit), bvh.fut:149-167 (any_hit): extend of bounce b+1 and connect of
+ *                bounce b in ONE persistent launch (grid = SMs x resident CTAs, grid-stride over device-side counts)
  *   k_shade      integrator.fut:46-76, direct.fut:32-122, material.fut   vertex shading; emits <= 2
  *                                                                   shadow rays, the continuation ray,
  *                                                                   and compacts live paths (warp ballot)
- *   k_connect    direct.fut:7-15 + bvh.fut:149-167 (any_hit)        shadow rays, radiance accumulation
+ *   connect_item direct.fut:7-15 + bvh.fut:149-167 (any_hit)        shadow rays, radiance accumulation (inside k_trace)
  *   k_accumulate integrator.fut:133-192                             channel resolve + running average
  *   k_render     lib.fut:187-196                                    upscale + ARGB pack
  * Per-path arithmetic is the reference's, operation for operation; only the scheduling differs.
  */
 #include "lys_wavefront.h"
 #include <cstdio>
+#include <cstdlib>
 
 namespace lys {
 
@@ -88,7 +90,7 @@ LYS_D int traverse(const float4 *__restrict__ nodes, const float4 *__restrict__ 
 }
 
 /* ------------------------------------------------------------------ camera: camera.fut:68-110, integrator.fut:85-90 */
-LYS_D void camera_sample(const FrameParams &fp, int col, int row, uint32_t &rng, V3 &o, V3 &d, float &wavelen, int &chan) {
+LYS_DN void camera_sample(const FrameParams &fp, int col, int row, uint32_t &rng, V3 &o, V3 &d, float &wavelen, int &chan) {
     uint32_t x = lcg_next(rng);                                   /* random_select' rand.fut:39-42 */
     chan = (int)(x % (uint32_t)fp.n_sensor);
     float p = rng_unit(rng);
@@ -131,17 +133,6 @@ __global__ void __launch_bounds__(256) k_generate(const __grid_constant__ FrameP
     if (b.probe_rad) for (int k = 0; k < LYS_MAX_PATH_LEN; k++) { b.probe_rad[(size_t)pid * 16 + k] = 0.0f; b.probe_dist[(size_t)pid * 16 + k] = LYS_INF; }
 }
 
-/* ------------------------------------------------------------------ extend: closest hit per live ray */
-__global__ void __launch_bounds__(128) k_extend(SceneDev sc, PassBuffers b, int bounce) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    int count = b.counts[bounce];
-    if (i >= count) return;
-    int pid = b.queue[bounce & 1][i];
-    float4 ro = b.ray_o[pid], rd = b.ray_d[pid];
-    float t;
-    b.hit[i] = traverse<false>(sc.nodes, sc.leaf_tri, (int)sc.n_tris - 1, v3(ro.x, ro.y, ro.z), v3(rd.x, rd.y, rd.z), FLT_MAX, t);
-}
-
 /* ------------------------------------------------------------------ lights */
 struct LightD { V3 a, e1, e2, n; float inv_area, theta; int kind; float em[12]; };
 LYS_D void load_light(const LightRec *__restrict__ L, LightD &l) {
@@ -154,7 +145,7 @@ LYS_D void load_light(const LightRec *__restrict__ L, LightD &l) {
     l.em[8] = e2.x; l.em[9] = e2.y; l.em[10] = e2.z; l.em[11] = e2.w;
 }
 /* light k of the scanning transmitter for a primary ray direction (camera.fut:119-121, shapes.fut:17-35) */
-LYS_D void scanning_light(const FrameParams &fp, V3 prim_dir, int k, LightD &l) {
+LYS_DN void scanning_light(const FrameParams &fp, V3 prim_dir, int k, LightD &l) {
     V3 c = cross(prim_dir, v3(0.0f, 1.0f, 0.0f));
     V3 right = (norm(c) == 0.0f) ? v3(1.0f, 0.0f, 0.0f) : normalise(c);
     V3 up = normalise(cross(right, prim_dir));
@@ -169,7 +160,7 @@ LYS_D void scanning_light(const FrameParams &fp, V3 prim_dir, int k, LightD &l) 
     for (int q = 0; q < 12; q++) l.em[q] = fp.tx_emission[q];
 }
 /* arealight_incident_radiance (light.fut:19-55) */
-LYS_D float incident_radiance(const LightD &l, V3 hitp, V3 lightp, float wavelen) {
+LYS_DN float incident_radiance(const LightD &l, V3 hitp, V3 lightp, float wavelen) {
     V3 v = lightp - hitp;
     V3 wi = normalise(v);
     float d2 = quadrance(v);
@@ -182,8 +173,12 @@ LYS_D float balance1(float pf, float pg) { return 1.0f * pf / (1.0f * pf + 1.0f 
 
 /* ------------------------------------------------------------------ shade */
 __global__ void __launch_bounds__(128) k_shade(SceneDev sc, const __grid_constant__ FrameParams fp, PassBuffers b, int bounce) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int count = b.counts[bounce];
+    const int lane = threadIdx.x & 31;
+    const int stride = gridDim.x * blockDim.x;
+    /* persistent grid: warp-uniform trip count so that the ballot compaction below sees whole warps */
+    for (int i0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31); i0 < count; i0 += stride) {
+    const int i = i0 + lane;
     bool alive = false;
     int pid = -1;
     unsigned n_vert = 0, n_shadow = 0;
@@ -298,7 +293,6 @@ __global__ void __launch_bounds__(128) k_shade(SceneDev sc, const __grid_constan
     }
     /* compaction of live paths: warp ballot + prefix popcount, one atomic per warp */
     unsigned mask = __ballot_sync(0xffffffffu, alive);
-    int lane = threadIdx.x & 31;
     int base = 0;
     if (lane == 0 && mask) base = atomicAdd(&b.counts[bounce + 1], __popc(mask));
     base = __shfl_sync(0xffffffffu, base, 0);
@@ -306,39 +300,168 @@ __global__ void __launch_bounds__(128) k_shade(SceneDev sc, const __grid_constan
     /* statistics */
     unsigned vsum = __reduce_add_sync(0xffffffffu, n_vert), ssum = __reduce_add_sync(0xffffffffu, n_shadow);
     if (lane == 0 && (vsum | ssum)) { atomicAdd(&b.stats[0], (unsigned long long)vsum); atomicAdd(&b.stats[2], (unsigned long long)ssum); }
+    }
 }
 
-/* ------------------------------------------------------------------ connect: shadow rays + accumulation */
-__global__ void __launch_bounds__(128) k_connect(SceneDev sc, const __grid_constant__ FrameParams fp, PassBuffers b, int bounce) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= b.counts[bounce]) return;
-    int pid = b.queue[bounce & 1][i];
-    float4 ro = b.sh_o[i], rc = b.sh_c[i];
-    int flags = __float_as_int(ro.w);
-    float r, dist = rc.w;
-    if (flags & 4) r = rc.z;                        /* miss vertex: {inf, ambience} */
+/* ------------------------------------------------------------------ trace: all BVH traversal of one bounce boundary
+ * One persistent launch resolves the shadow rays of bounce `bounce` (connect) and the closest hits of bounce
+ * `bounce + 1` (extend); both only read the scene and touch disjoint path state.  bounce = -1: primary rays only.
+ *
+ * Every lane runs a small state machine: one BVH node visit (box test or triangle test) per step, with the same
+ * left-first order as traverse<>.  Rays need very different numbers of steps, so a lane that finishes its item
+ * does not wait for the warp: when fewer than TRACE_REFILL lanes are busy the idle lanes pull the next items of
+ * the warp's own contiguous slice of the work list (ballot + prefix popcount; no atomics, no shared memory).
+ * A connect item carries up to two shadow rays; they are traced back to back by the same lane, then the vertex
+ * radiance is accumulated (direct.fut:121-122, integrator.fut:51-55). */
+#define TRACE_REFILL 20
+struct LaneState {
+    int item;            /* work index, -1 = idle */
+    int phase;           /* 0 extend ray, 1 first shadow ray, 2 second shadow ray */
+    int cur, sp, closest;
+    float tmax;
+    V3 o, d, inv;
+    int flags; float cL, cB, em, dist, L;      /* connect item */
+};
+LYS_D void lane_start_ray(LaneState &st, V3 o, V3 d, float tmax) {
+    st.o = o; st.d = d; st.inv = v3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    st.tmax = tmax; st.cur = 0; st.sp = 0; st.closest = -1;
+}
+LYS_D void connect_finish(const FrameParams &fp, const PassBuffers &b, int bounce, int slot, int flags, float L, float B, float em, float dist, float miss_r) {
+    int pid = b.queue[bounce & 1][slot];
+    float r;
+    if (flags & 4) r = miss_r;                        /* miss vertex: {inf, ambience} (integrator.fut:76) */
     else {
-        float L = 0.0f, B = 0.0f;
-        V3 o = v3(ro.x, ro.y, ro.z);
-        const int n_nodes = (int)sc.n_tris - 1;
-        if (flags & 1) {
-            float4 d1 = b.sh_d1[i]; float t;
-            if (traverse<true>(sc.nodes, sc.leaf_tri, n_nodes, o, v3(d1.x, d1.y, d1.z), d1.w, t) < 0) L = rc.x;
-        }
-        if (flags & 2) {
-            float4 d2 = b.sh_d2[i]; float t;
-            if (traverse<true>(sc.nodes, sc.leaf_tri, n_nodes, o, v3(d2.x, d2.y, d2.z), d2.w, t) < 0) B = rc.y;
-        }
         const int nl = fp.n_scene_lights + ((fp.tx_kind == 0) ? 0 : 8);
         float direct = 0.0f;
         if (nl > 0) { float light_pdf = 1.0f / (float)nl; direct = (L + B) / light_pdf; }   /* direct.fut:121-122 */
-        r = direct + ((bounce == 0) ? rc.z : 0.0f);                                        /* integrator.fut:51-53 */
+        r = direct + ((bounce == 0) ? em : 0.0f);                                          /* integrator.fut:51-53 */
     }
     b.sum[pid] = b.sum[pid] + r * 1.0f;
     b.zsum[pid] = b.zsum[pid] + r * 0.0f;
     float inten = r * fp.intensity_factor;
     if (inten > 0.0f && dist > 0.5f && dist < 10.0f && dist < b.best_d[pid]) { b.best_d[pid] = dist; b.best_i[pid] = inten; }
     if (b.probe_rad) { b.probe_rad[(size_t)pid * 16 + bounce] = r; b.probe_dist[(size_t)pid * 16 + bounce] = dist; }
+}
+__global__ void __launch_bounds__(128) k_trace_refill(SceneDev sc, const __grid_constant__ FrameParams fp, PassBuffers b, int bounce) {
+    const int n_ext = (bounce + 1 < fp.path_len) ? b.counts[bounce + 1] : 0;
+    const int n_con = (bounce >= 0) ? b.counts[bounce] : 0;
+    const int total = n_ext + n_con;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const int n_warps = gridDim.x * (blockDim.x >> 5);
+    const int gwarp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int per = (total + n_warps - 1) / n_warps;
+    per = max(32, (per + 31) & ~31);
+    long long beg = (long long)gwarp * per;
+    if (beg >= total) return;
+    int cursor = (int)beg;
+    const int range_end = (int)min((long long)total, beg + per);
+    const float4 *__restrict__ nodes = sc.nodes;
+    const float4 *__restrict__ leaf_tri = sc.leaf_tri;
+    int stack[TRAV_STACK];
+    LaneState st; st.item = -1; st.phase = 0; st.cur = 0; st.sp = 0; st.closest = -1; st.tmax = 0.0f;
+    st.o = v3(0, 0, 0); st.d = st.o; st.inv = st.o; st.flags = 0; st.cL = st.cB = st.em = st.dist = st.L = 0.0f;
+    while (true) {
+        /* ---- refill idle lanes from the warp's slice */
+        for (int round = 0; round < 4; round++) {
+            unsigned idle = __ballot_sync(0xffffffffu, st.item < 0);
+            if (!idle || cursor >= range_end) break;
+            int mine = cursor + __popc(idle & lt_mask);
+            cursor = min(range_end, cursor + __popc(idle));
+            if (st.item < 0 && mine < range_end) {
+                if (mine < n_ext) {                                        /* extend item of bounce + 1 */
+                    int pid = b.queue[(bounce + 1) & 1][mine];
+                    float4 ro = b.ray_o[pid], rd = b.ray_d[pid];
+                    st.item = mine; st.phase = 0;
+                    lane_start_ray(st, v3(ro.x, ro.y, ro.z), v3(rd.x, rd.y, rd.z), FLT_MAX);
+                } else {                                                   /* connect item of bounce */
+                    int slot = mine - n_ext;
+                    float4 ro = b.sh_o[slot], rc = b.sh_c[slot];
+                    int flags = __float_as_int(ro.w);
+                    if ((flags & 4) || !(flags & 3)) connect_finish(fp, b, bounce, slot, flags, 0.0f, 0.0f, rc.z, rc.w, rc.z);
+                    else {
+                        st.item = mine; st.flags = flags; st.cL = rc.x; st.cB = rc.y; st.em = rc.z; st.dist = rc.w; st.L = 0.0f;
+                        float4 dd = (flags & 1) ? b.sh_d1[slot] : b.sh_d2[slot];
+                        st.phase = (flags & 1) ? 1 : 2;
+                        lane_start_ray(st, v3(ro.x, ro.y, ro.z), v3(dd.x, dd.y, dd.z), dd.w);
+                    }
+                }
+            }
+        }
+        unsigned busy = __ballot_sync(0xffffffffu, st.item >= 0);
+        if (!busy) { if (cursor >= range_end) break; else continue; }
+        /* ---- traversal steps until too many lanes have gone idle (or to completion once the slice is empty) */
+        const int keep = (cursor >= range_end) ? 1 : TRACE_REFILL;
+        do {
+            if (st.item >= 0) {
+                bool done = false;
+                if (st.cur >= 0) {
+                    float4 lo = __ldg(nodes + 2ll * st.cur), hi = __ldg(nodes + 2ll * st.cur + 1);
+                    RayInv r; r.o = st.o; r.d = st.d; r.inv = st.inv;
+                    if (slab_test(r, lo, hi, st.tmax)) { stack[st.sp++] = __float_as_int(hi.w); st.cur = __float_as_int(lo.w); }
+                    else if (st.sp == 0) done = true;
+                    else st.cur = stack[--st.sp];
+                } else {
+                    RayInv r; r.o = st.o; r.d = st.d; r.inv = st.inv;
+                    float t;
+                    bool hit = leaf_test(r, leaf_tri, ~st.cur, st.tmax, t);
+                    if (hit) { st.closest = ~st.cur; st.tmax = t; }
+                    if (hit && st.phase != 0) done = true;                 /* any_hit stops at the first hit (bvh.fut:152) */
+                    else if (st.sp == 0) done = true;
+                    else st.cur = stack[--st.sp];
+                }
+                if (done) {
+                    if (st.phase == 0) { b.hit[st.item] = st.closest; st.item = -1; }
+                    else {
+                        const int slot = st.item - n_ext;
+                        const bool visible = st.closest < 0;
+                        if (st.phase == 1) {
+                            st.L = visible ? st.cL : 0.0f;
+                            if (st.flags & 2) {
+                                float4 d2 = b.sh_d2[slot];
+                                st.phase = 2;
+                                lane_start_ray(st, st.o, v3(d2.x, d2.y, d2.z), d2.w);
+                            } else { connect_finish(fp, b, bounce, slot, st.flags, st.L, 0.0f, st.em, st.dist, 0.0f); st.item = -1; }
+                        } else {
+                            connect_finish(fp, b, bounce, slot, st.flags, st.L, visible ? st.cB : 0.0f, st.em, st.dist, 0.0f);
+                            st.item = -1;
+                        }
+                    }
+                }
+            }
+            busy = __ballot_sync(0xffffffffu, st.item >= 0);
+        } while (__popc(busy) >= keep);
+    }
+}
+
+/* The default variant: one item per thread and grid-stride iteration, plain traverse<> loops.  Measured on B200
+ * (CornellBox 1080p) it beats the refill variant above, whose every refill stalls the warp on dependent
+ * queue -> ray loads; the refill kernel is kept selectable (LYS_TRACE_MODE=1) and is parity-tested too. */
+__global__ void __launch_bounds__(128) k_trace(SceneDev sc, const __grid_constant__ FrameParams fp, PassBuffers b, int bounce) {
+    const int n_ext = (bounce + 1 < fp.path_len) ? b.counts[bounce + 1] : 0;
+    const int n_con = (bounce >= 0) ? b.counts[bounce] : 0;
+    const int total = n_ext + n_con;
+    const int stride = gridDim.x * blockDim.x;
+    const int n_nodes = (int)sc.n_tris - 1;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        if (i < n_ext) {
+            int pid = b.queue[(bounce + 1) & 1][i];
+            float4 ro = b.ray_o[pid], rd = b.ray_d[pid];
+            float t;
+            b.hit[i] = traverse<false>(sc.nodes, sc.leaf_tri, n_nodes, v3(ro.x, ro.y, ro.z), v3(rd.x, rd.y, rd.z), FLT_MAX, t);
+        } else {
+            const int slot = i - n_ext;
+            float4 ro = b.sh_o[slot], rc = b.sh_c[slot];
+            const int flags = __float_as_int(ro.w);
+            float L = 0.0f, B = 0.0f, t;
+            V3 o = v3(ro.x, ro.y, ro.z);
+            if (!(flags & 4)) {
+                if (flags & 1) { float4 d1 = b.sh_d1[slot]; if (traverse<true>(sc.nodes, sc.leaf_tri, n_nodes, o, v3(d1.x, d1.y, d1.z), d1.w, t) < 0) L = rc.x; }
+                if (flags & 2) { float4 d2 = b.sh_d2[slot]; if (traverse<true>(sc.nodes, sc.leaf_tri, n_nodes, o, v3(d2.x, d2.y, d2.z), d2.w, t) < 0) B = rc.y; }
+            }
+            connect_finish(fp, b, bounce, slot, flags, L, B, rc.z, rc.w, rc.z);
+        }
+    }
 }
 
 /* ------------------------------------------------------------------ resolve + accumulate */
@@ -458,16 +581,39 @@ __global__ void k_material_probe(const float *mat28, float wavelen, V3 wo, V3 wi
 /* ------------------------------------------------------------------ host launchers */
 static inline int cdiv(long long a, int b) { return (int)((a + b - 1) / b); }
 
+/* persistent grids: SM count x resident CTAs per SM of each kernel (queried once per device) */
+struct GridSizes { int trace = 0, shade = 0, refill = 0; int mode = 0; };
+static GridSizes grid_sizes() {
+    static GridSizes g[64];
+    int dev = 0; cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (!g[dev].trace) {
+        int sms = 148, bt = 8, bs = 4;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bt, k_trace, 128, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bs, k_shade, 128, 0);
+        int br = 8; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&br, k_trace_refill, 128, 0);
+        g[dev].trace = sms * (bt > 0 ? bt : 1); g[dev].shade = sms * (bs > 0 ? bs : 1); g[dev].refill = sms * (br > 0 ? br : 1);
+        const char *e = getenv("LYS_TRACE_MODE"); g[dev].mode = (e && atoi(e) == 1) ? 1 : 0;
+    }
+    return g[dev];
+}
 cudaError_t run_sample_pass(const SceneDev &sc, const FrameParams &fp, PassBuffers &bufs, cudaStream_t stream, uint64_t *launches, LaunchTimer *timer) {
     const int n = fp.n_local;
     if (n <= 0) return cudaSuccess;
     uint64_t nl = 0;
     LaunchTimer none; LaunchTimer &tm = timer ? *timer : none;
+    const GridSizes gs = grid_sizes();
+    const int g_trace = min(gs.mode ? gs.refill : gs.trace, cdiv(2ll * n, 128)), g_shade = min(gs.shade, cdiv(n, 128));
     tm.begin(0, stream); k_generate<<<cdiv(n, 256), 256, 0, stream>>>(fp, bufs); tm.end(stream); nl++;
+    tm.begin(1, stream);
+    if (gs.mode) k_trace_refill<<<g_trace, 128, 0, stream>>>(sc, fp, bufs, -1); else k_trace<<<g_trace, 128, 0, stream>>>(sc, fp, bufs, -1);
+    tm.end(stream); nl++;
     for (int bnc = 0; bnc < fp.path_len; bnc++) {
-        tm.begin(1, stream); k_extend<<<cdiv(n, 128), 128, 0, stream>>>(sc, bufs, bnc); tm.end(stream); nl++;
-        tm.begin(2, stream); k_shade<<<cdiv(n, 128), 128, 0, stream>>>(sc, fp, bufs, bnc); tm.end(stream); nl++;
-        tm.begin(3, stream); k_connect<<<cdiv(n, 128), 128, 0, stream>>>(sc, fp, bufs, bnc); tm.end(stream); nl++;
+        tm.begin(2, stream); k_shade<<<g_shade, 128, 0, stream>>>(sc, fp, bufs, bnc); tm.end(stream); nl++;
+        tm.begin(1, stream);
+        if (gs.mode) k_trace_refill<<<g_trace, 128, 0, stream>>>(sc, fp, bufs, bnc); else k_trace<<<g_trace, 128, 0, stream>>>(sc, fp, bufs, bnc);
+        tm.end(stream); nl++;
     }
     if (launches) *launches += nl;
     return cudaGetLastError();

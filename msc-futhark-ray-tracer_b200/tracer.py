@@ -206,11 +206,11 @@ class Context:
         self.check(self._L.lys_context_set_profiling(self._ctx, int(bool(on))), 'lys_context_set_profiling')
 
     def profile(self, reset=True):
-        """-> {class: (device ms, launches)} for generate / extend / shade / connect / accumulate."""
+        """-> {class: (device ms, launches)} for generate / trace / shade / accumulate."""
         ms = np.zeros(5, np.float32)
         n = np.zeros(5, np.uint64)
         self.check(self._L.lys_context_profile_get(self._ctx, _ptr(ms), _ptr(n), int(reset)), 'lys_context_profile_get')
-        return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(('generate', 'extend', 'shade', 'connect', 'accumulate'))}
+        return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(('generate', 'trace', 'shade', 'unused', 'accumulate'))}
 
     @property
     def device(self):
