@@ -95,10 +95,17 @@ class ClockSampler:
                 'samples': len(sm), 'samples_in_timed_region': len(inwin)}
 
 
-def cpu_baseline(oracle, scene, passes, threads=0):
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_baseline(oracle, scene, passes, threads=None):
     """Oracle Mpaths/s on the host cores + work counters for the algorithmic-bytes figure (bounded sample)."""
     t, tm, m = scene
-    oracle.set_threads(threads)
+    oracle.set_threads(threads or host_threads())      # explicit: torchrun exports OMP_NUM_THREADS=1
     s = oracle.State.init(t, tm, m, H, W)
     oracle.counters_reset()
     t0 = time.perf_counter()
@@ -117,7 +124,7 @@ def run_reference(args):
     sys.path.insert(0, os.path.join(ROOT, 'tests'))
     from lysref import oracle
     t, tm, m = load_scene()
-    oracle.set_threads(0)
+    oracle.set_threads(host_threads())                 # all host threads, explicit: torchrun exports OMP_NUM_THREADS=1
     s = oracle.State.init(t, tm, m, H, W)
     for _ in range(args.warmup):
         s.sample_n_frames(1)
@@ -267,7 +274,7 @@ def main():
             big.free()
         cpu, roof = None, None
         peak, peak_src = peaks()
-        if not args.no_cpu:
+        if not args.no_cpu and world == 1:                 # cpu_baseline / roofline: rank 0 at N=1 only
             sys.path.insert(0, os.path.join(ROOT, 'tests'))
             from lysref import oracle
             cpu, c = cpu_baseline(oracle, (t, tm, m), args.cpu_passes)
