@@ -35,6 +35,8 @@ uint64_t lys_context_launch_count(struct futhark_context *ctx);
 #define LYS_PROFILE_CLASSES 5
 int lys_context_set_profiling(struct futhark_context *ctx, int on);
 int lys_context_profile_get(struct futhark_context *ctx, float *ms /* [5] */, uint64_t *launches /* [5] */, int reset);
+/* per-bounce device ms: ms36[0..17] = k_trace for bounce -1..16, ms36[18..35] = k_shade (index bounce + 1); call before a reset */
+int lys_context_profile_detail(struct futhark_context *ctx, float *ms36);
 /* A copy of `s` whose frame rng is advanced k steps (k sample passes ahead): pass-split multi-GPU rendering. */
 int lys_state_advance_rng(struct futhark_context *ctx, struct futhark_opaque_state **out0, const struct futhark_opaque_state *s, uint32_t k);
 

@@ -36,8 +36,13 @@ struct futhark_context {
     std::multimap<size_t, void *> pool;          /* free device blocks by size */
     PassBuffers bufs; BuildScratch scratch;
     float4 *pts_pos = nullptr; float *pts_dist = nullptr; int64_t pts_cap = 0;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr;
     LaunchTimer timer;
+    /* pass pipelining: independent sample passes run on their own streams / buffer sets; only the accumulate
+     * (or point-cloud merge) kernels are ordered, so one pass's latency-bound tail overlaps the next pass's head */
+    struct PassSlot { cudaStream_t stream = nullptr; PassBuffers bufs; cudaEvent_t done = nullptr; };
+    std::vector<PassSlot> slots;
+    int pipeline = 8;
 };
 
 namespace {
@@ -197,8 +202,7 @@ void grid_dims(const futhark_opaque_state *s, uint32_t &gw, uint32_t &gh) {     
     gh = (s->dim_h + s->subsampling - 1) / s->subsampling;
 }
 
-bool ensure_pass_buffers(futhark_context *ctx, int64_t n, bool probes) {
-    PassBuffers &b = ctx->bufs;
+bool ensure_bufs(futhark_context *ctx, PassBuffers &b, int64_t n, bool probes) {
     if (b.cap < n) {
         raw_free(b.ray_o); raw_free(b.ray_d); raw_free(b.dist); raw_free(b.sum); raw_free(b.zsum); raw_free(b.best_d); raw_free(b.best_i);
         raw_free(b.chan); raw_free(b.queue[0]); raw_free(b.queue[1]); raw_free(b.hit); raw_free(b.sh_o); raw_free(b.sh_d1); raw_free(b.sh_d2);
@@ -212,12 +216,33 @@ bool ensure_pass_buffers(futhark_context *ctx, int64_t n, bool probes) {
         b.cap = n;
     }
     if (!b.counts) {
-        if (!raw_alloc(ctx, b.counts, LYS_MAX_PATH_LEN + 1) || !raw_alloc(ctx, b.stats, 4) || !raw_alloc(ctx, b.tx_lights, 8)) return false;
+        if (!raw_alloc(ctx, b.counts, LYS_MAX_PATH_LEN + 1) || !raw_alloc(ctx, b.stats, 4)) return false;
         CUB(ctx, cudaMemsetAsync(b.stats, 0, 4 * sizeof(unsigned long long), ctx->stream));
     }
+    if (!ctx->bufs.tx_lights && !raw_alloc(ctx, ctx->bufs.tx_lights, 8)) return false;
+    b.tx_lights = ctx->bufs.tx_lights;          /* one copy shared by all buffer sets */
     if (probes && !b.probe_rad) {
         if (!raw_alloc(ctx, b.probe_rad, (size_t)b.cap * 16) || !raw_alloc(ctx, b.probe_dist, (size_t)b.cap * 16)) return false;
     }
+    return true;
+}
+bool ensure_pass_buffers(futhark_context *ctx, int64_t n, bool probes) { return ensure_bufs(ctx, ctx->bufs, n, probes); }
+void free_bufs(PassBuffers &b, bool owns_tx) {
+    raw_free(b.ray_o); raw_free(b.ray_d); raw_free(b.dist); raw_free(b.sum); raw_free(b.zsum); raw_free(b.best_d); raw_free(b.best_i);
+    raw_free(b.chan); raw_free(b.queue[0]); raw_free(b.queue[1]); raw_free(b.hit); raw_free(b.sh_o); raw_free(b.sh_d1); raw_free(b.sh_d2);
+    raw_free(b.sh_c); raw_free(b.counts); raw_free(b.stats); raw_free(b.probe_rad); raw_free(b.probe_dist);
+    if (owns_tx) raw_free(b.tx_lights);
+    b.cap = 0;
+}
+/* `want` pipeline slots with buffers for n paths each */
+bool ensure_slots(futhark_context *ctx, int want, int64_t n) {
+    while ((int)ctx->slots.size() < want) {
+        futhark_context::PassSlot sl;
+        if (!cu_ok(ctx, cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking), "cudaStreamCreate") ||
+            !cu_ok(ctx, cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming), "cudaEventCreate")) return false;
+        ctx->slots.push_back(sl);
+    }
+    for (int i = 0; i < want; i++) if (!ensure_bufs(ctx, ctx->slots[i].bufs, n, false)) return false;
     return true;
 }
 bool ensure_scratch(futhark_context *ctx, int64_t n) {
@@ -367,10 +392,17 @@ struct futhark_context *futhark_context_new(struct futhark_context_config *cfg) 
     }
     if (dev < 0 || dev >= count) { fprintf(stderr, "libtracer: CUDA device %d out of range\n", dev); return nullptr; }
     if (cudaSetDevice(dev) != cudaSuccess) return nullptr;
+    /* the sample pass alternates kernels with different local-memory footprints (traversal stacks, shading
+     * temporaries); without this flag the driver may shrink / regrow the local-memory pool between launches */
+    if (!getenv("LYS_NO_LMEM_FLAG")) {
+        unsigned int flags = 0;
+        if (cudaGetDeviceFlags(&flags) == cudaSuccess && !(flags & cudaDeviceLmemResizeToMax)) { cudaSetDeviceFlags(flags | cudaDeviceLmemResizeToMax); cudaGetLastError(); }
+    }
     futhark_context *ctx = new futhark_context();
     ctx->device = dev; ctx->logging = cfg ? cfg->logging : 0;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return nullptr; }
-    cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1);
+    cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1); cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
+    { const char *pe = getenv("LYS_PIPELINE"); if (pe) { int v = atoi(pe); if (v >= 1 && v <= 16) ctx->pipeline = v; } }
     const char *pl = getenv("LYS_PATH_LEN");
     if (pl) { int v = atoi(pl); if (v >= 1 && v <= LYS_MAX_PATH_LEN) ctx->path_len = v; }
     return ctx;
@@ -379,10 +411,9 @@ void futhark_context_free(struct futhark_context *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    PassBuffers &b = ctx->bufs;
-    raw_free(b.ray_o); raw_free(b.ray_d); raw_free(b.dist); raw_free(b.sum); raw_free(b.zsum); raw_free(b.best_d); raw_free(b.best_i);
-    raw_free(b.chan); raw_free(b.queue[0]); raw_free(b.queue[1]); raw_free(b.hit); raw_free(b.sh_o); raw_free(b.sh_d1); raw_free(b.sh_d2);
-    raw_free(b.sh_c); raw_free(b.counts); raw_free(b.stats); raw_free(b.tx_lights); raw_free(b.probe_rad); raw_free(b.probe_dist);
+    for (auto &sl : ctx->slots) { cudaStreamSynchronize(sl.stream); free_bufs(sl.bufs, false); cudaStreamDestroy(sl.stream); cudaEventDestroy(sl.done); }
+    ctx->slots.clear();
+    free_bufs(ctx->bufs, true);
     BuildScratch &w = ctx->scratch;
     raw_free(w.box_c); raw_free(w.box_h); raw_free(w.F); raw_free(w.chunk_lo); raw_free(w.chunk_hi); raw_free(w.keys[0]); raw_free(w.keys[1]); raw_free(w.vals[0]); raw_free(w.vals[1]);
     raw_free(w.rs_hist); raw_free(w.rs_status); raw_free(w.leaf_parent); raw_free(w.visits); raw_free(w.crown_box); raw_free(w.crown_cnt);
@@ -392,6 +423,7 @@ void futhark_context_free(struct futhark_context *ctx) {
     ctx->pool.clear();
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -604,23 +636,38 @@ int lys_sample_n_frames_stats(struct futhark_context *ctx, struct futhark_f32_3d
     if (!a) return 1;
     uint64_t l0 = ctx->launches;
     if (ctx->world > 1) CU(ctx, cudaMemsetAsync(a->ptr(), 0, sizeof(float) * 3 * (size_t)gw * gh, ctx->stream));
-    if (!ensure_pass_buffers(ctx, (int64_t)gw * gh, false)) { delete a; return 1; }
-    if (stats) CU(ctx, cudaMemsetAsync(ctx->bufs.stats, 0, 4 * sizeof(unsigned long long), ctx->stream));
+    const uint32_t passes = n < 1 ? 1 : n;                               /* the first sample_frame always runs (lib.fut:68) */
+    const int S = ctx->timer.on ? 1 : (int)std::min<uint32_t>((uint32_t)ctx->pipeline, passes);
+    if (!ensure_slots(ctx, S, (int64_t)gw * gh)) { delete a; return 1; }
+    FrameParams fp;
+    if (!make_frame_params(ctx, s, s->rng, 1.0f, fp)) { delete a; return 1; }      /* uploads the flash lights once */
+    for (int i = 0; i < S; i++) CU(ctx, cudaMemsetAsync(ctx->slots[i].bufs.stats, 0, 4 * sizeof(unsigned long long), ctx->stream));
     CU(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-    uint32_t rng = s->rng; uint32_t n_frames;
-    if (!sample_into(ctx, s, rng, nullptr, a->ptr(), false, 0.0f)) { delete a; return 1; }
-    rng = h_advance_rng(rng); n_frames = 1;
-    while (n_frames < n) {
-        if (!sample_into(ctx, s, rng, a->ptr(), a->ptr(), true, (float)n_frames)) { delete a; return 1; }
-        rng = h_advance_rng(rng); n_frames++;
+    CU(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+    for (int i = 0; i < S; i++) CU(ctx, cudaStreamWaitEvent(ctx->slots[i].stream, ctx->ev_fork, 0));
+    uint32_t rng = s->rng;
+    cudaEvent_t prev = nullptr;
+    for (uint32_t k = 0; k < passes; k++) {
+        futhark_context::PassSlot &sl = ctx->slots[k % S];
+        fp.frame_rng = rng;
+        CU(ctx, run_sample_pass(s->scene->d, fp, sl.bufs, sl.stream, &ctx->launches, &ctx->timer));
+        if (prev) CU(ctx, cudaStreamWaitEvent(sl.stream, prev, 0));             /* running average is order dependent */
+        CU(ctx, run_accumulate(fp, sl.bufs, a->ptr(), a->ptr(), k > 0 ? 1 : 0, (float)k, sl.stream, &ctx->launches, &ctx->timer));
+        CU(ctx, cudaEventRecord(sl.done, sl.stream));
+        prev = sl.done;
+        rng = h_advance_rng(rng);
     }
+    CU(ctx, cudaStreamWaitEvent(ctx->stream, prev, 0));
     CU(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    if (ctx->timer.on) ctx->timer.resolve(ctx->stream);
     if (stats) {
-        unsigned long long hs[4];
-        CU(ctx, cudaMemcpyAsync(hs, ctx->bufs.stats, sizeof(hs), cudaMemcpyDeviceToHost, ctx->stream));
-        CU(ctx, cudaStreamSynchronize(ctx->stream));
-        FrameParams fp; make_frame_params(ctx, s, s->rng, 1.0f, fp);
-        stats->paths = (uint64_t)fp.n_local * n_frames; stats->vertices = hs[0]; stats->shadow_rays = hs[2];
+        unsigned long long hs[4] = {0, 0, 0, 0}, one[4];
+        for (int i = 0; i < S; i++) {
+            CU(ctx, cudaMemcpyAsync(one, ctx->slots[i].bufs.stats, sizeof(one), cudaMemcpyDeviceToHost, ctx->stream));
+            CU(ctx, cudaStreamSynchronize(ctx->stream));
+            for (int q = 0; q < 4; q++) hs[q] += one[q];
+        }
+        stats->paths = (uint64_t)fp.n_local * passes; stats->vertices = hs[0]; stats->shadow_rays = hs[2];
         stats->closest_rays = 0; stats->launches = ctx->launches - l0;
         cudaEventElapsedTime(&stats->device_ms, ctx->ev0, ctx->ev1);
     }
@@ -646,20 +693,30 @@ int futhark_entry_sample_points_n(struct futhark_context *ctx, struct futhark_op
         if (!raw_alloc(ctx, ctx->pts_pos, (size_t)np) || !raw_alloc(ctx, ctx->pts_dist, (size_t)np)) { delete a; return 1; }
         ctx->pts_cap = np;
     }
-    if (!ensure_pass_buffers(ctx, np, false)) { delete a; return 1; }
     if (ctx->world > 1) { CU(ctx, cudaMemsetAsync(ctx->pts_pos, 0, sizeof(float4) * (size_t)np, ctx->stream)); }
     float factor = 1 / (float)spp;                                                 /* lib.fut:39 */
     uint32_t rng = s->rng;
     uint32_t passes = spp < 1 ? 1 : spp;                                           /* the first pass always runs (lib.fut:52) */
+    const int S = (int)std::min<uint32_t>((uint32_t)ctx->pipeline, passes);
+    if (!ensure_slots(ctx, S, np)) { delete a; return 1; }
+    FrameParams fp;
+    if (!make_frame_params(ctx, s, rng, factor, fp)) { delete a; return 1; }
+    fp.render_mode = 1;
+    CU(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+    for (int i = 0; i < S; i++) CU(ctx, cudaStreamWaitEvent(ctx->slots[i].stream, ctx->ev_fork, 0));
+    cudaEvent_t prev = nullptr;
     for (uint32_t k = 0; k < passes; k++) {
-        FrameParams fp;
-        if (!make_frame_params(ctx, s, rng, factor, fp)) { delete a; return 1; }
-        fp.render_mode = 1;
-        if (!cu_ok(ctx, run_sample_pass(s->scene->d, fp, ctx->bufs, ctx->stream, &ctx->launches), "sample pass") ||
-            !cu_ok(ctx, run_points_merge(fp, ctx->bufs, ctx->pts_pos, ctx->pts_dist, k == 0 ? 1 : 0, ctx->stream, &ctx->launches), "points merge")) { delete a; return 1; }
+        futhark_context::PassSlot &sl = ctx->slots[k % S];
+        fp.frame_rng = rng;
+        if (!cu_ok(ctx, run_sample_pass(s->scene->d, fp, sl.bufs, sl.stream, &ctx->launches), "sample pass")) { delete a; return 1; }
+        if (prev) CU(ctx, cudaStreamWaitEvent(sl.stream, prev, 0));                /* merge keeps the earlier point on ties (lib.fut:51) */
+        if (!cu_ok(ctx, run_points_merge(fp, sl.bufs, ctx->pts_pos, ctx->pts_dist, k == 0 ? 1 : 0, sl.stream, &ctx->launches), "points merge")) { delete a; return 1; }
+        CU(ctx, cudaEventRecord(sl.done, sl.stream));
+        prev = sl.done;
         rng = h_advance_rng(rng);
-        if (k + 1 == passes) { if (!cu_ok(ctx, run_points_export(fp, ctx->pts_pos, a->ptr(), ctx->stream, &ctx->launches), "points export")) { delete a; return 1; } }
     }
+    CU(ctx, cudaStreamWaitEvent(ctx->stream, prev, 0));
+    if (!cu_ok(ctx, run_points_export(fp, ctx->pts_pos, a->ptr(), ctx->stream, &ctx->launches), "points export")) { delete a; return 1; }
     futhark_opaque_state *r = clone_state(s);
     r->rng = rng;
     *out0 = r; *out1 = a;
@@ -682,6 +739,12 @@ int lys_context_profile_get(struct futhark_context *ctx, float *ms, uint64_t *la
     ctx->timer.resolve(ctx->stream);
     for (int i = 0; i < LYS_PROFILE_CLASSES; i++) { if (ms) ms[i] = ctx->timer.ms[i]; if (launches) launches[i] = ctx->timer.n[i]; }
     if (reset) ctx->timer.reset();
+    return 0;
+}
+int lys_context_profile_detail(struct futhark_context *ctx, float *ms36) {
+    if (!ctx || !ms36) return 1;
+    ctx->timer.resolve(ctx->stream);
+    memcpy(ms36, ctx->timer.detail, sizeof(float) * 36);
     return 0;
 }
 int lys_state_advance_rng(struct futhark_context *ctx, struct futhark_opaque_state **out0, const struct futhark_opaque_state *s, uint32_t k) {

@@ -58,21 +58,23 @@ struct PassBuffers {
 /* optional per-launch timing: events are recorded around each launch and resolved by the owner */
 struct LaunchTimer {
     bool on = false;
-    std::vector<cudaEvent_t> ev0, ev1; std::vector<int> cls; size_t used = 0;
+    std::vector<cudaEvent_t> ev0, ev1; std::vector<int> cls, bnc; size_t used = 0; int cur_bounce = 0;
     float ms[5] = {0, 0, 0, 0, 0}; uint64_t n[5] = {0, 0, 0, 0, 0};
+    float detail[2][18] = {};          /* [0] trace, [1] shade; index = bounce + 1 */
     void begin(int c, cudaStream_t st) {
         if (!on) return;
-        if (used == ev0.size()) { cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b); ev0.push_back(a); ev1.push_back(b); cls.push_back(0); }
-        cls[used] = c; cudaEventRecord(ev0[used], st);
+        if (used == ev0.size()) { cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b); ev0.push_back(a); ev1.push_back(b); cls.push_back(0); bnc.push_back(0); }
+        cls[used] = c; bnc[used] = cur_bounce; cudaEventRecord(ev0[used], st);
     }
     void end(cudaStream_t st) { if (!on) return; cudaEventRecord(ev1[used], st); used++; }
     void resolve(cudaStream_t st) {
         if (!used) return;
         cudaStreamSynchronize(st);
-        for (size_t i = 0; i < used; i++) { float t = 0; cudaEventElapsedTime(&t, ev0[i], ev1[i]); ms[cls[i]] += t; n[cls[i]]++; }
+        for (size_t i = 0; i < used; i++) { float t = 0; cudaEventElapsedTime(&t, ev0[i], ev1[i]); ms[cls[i]] += t; n[cls[i]]++;
+            if ((cls[i] == 1 || cls[i] == 2) && bnc[i] >= -1 && bnc[i] < 17) detail[cls[i] - 1][bnc[i] + 1] += t; }
         used = 0;
     }
-    void reset() { for (int i = 0; i < 5; i++) { ms[i] = 0; n[i] = 0; } used = 0; }
+    void reset() { for (int i = 0; i < 5; i++) { ms[i] = 0; n[i] = 0; } for (int i = 0; i < 18; i++) { detail[0][i] = 0; detail[1][i] = 0; } used = 0; }
     ~LaunchTimer() { for (auto e : ev0) cudaEventDestroy(e); for (auto e : ev1) cudaEventDestroy(e); }
 };
 

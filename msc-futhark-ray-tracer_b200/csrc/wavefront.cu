@@ -172,7 +172,7 @@ LYS_DN float incident_radiance(const LightD &l, V3 hitp, V3 lightp, float wavele
 LYS_D float balance1(float pf, float pg) { return 1.0f * pf / (1.0f * pf + 1.0f * pg); }   /* direct.fut:56-58, nf = ng = 1 */
 
 /* ------------------------------------------------------------------ shade */
-__global__ void __launch_bounds__(128) k_shade(SceneDev sc, const __grid_constant__ FrameParams fp, PassBuffers b, int bounce) {
+__global__ void __launch_bounds__(128, 8) k_shade(SceneDev sc, const __grid_constant__ FrameParams fp, PassBuffers b, int bounce) {
     const int count = b.counts[bounce];
     const int lane = threadIdx.x & 31;
     const int stride = gridDim.x * blockDim.x;
@@ -606,10 +606,12 @@ cudaError_t run_sample_pass(const SceneDev &sc, const FrameParams &fp, PassBuffe
     const GridSizes gs = grid_sizes();
     const int g_trace = min(gs.mode ? gs.refill : gs.trace, cdiv(2ll * n, 128)), g_shade = min(gs.shade, cdiv(n, 128));
     tm.begin(0, stream); k_generate<<<cdiv(n, 256), 256, 0, stream>>>(fp, bufs); tm.end(stream); nl++;
+    tm.cur_bounce = -1;
     tm.begin(1, stream);
     if (gs.mode) k_trace_refill<<<g_trace, 128, 0, stream>>>(sc, fp, bufs, -1); else k_trace<<<g_trace, 128, 0, stream>>>(sc, fp, bufs, -1);
     tm.end(stream); nl++;
     for (int bnc = 0; bnc < fp.path_len; bnc++) {
+        tm.cur_bounce = bnc;
         tm.begin(2, stream); k_shade<<<g_shade, 128, 0, stream>>>(sc, fp, bufs, bnc); tm.end(stream); nl++;
         tm.begin(1, stream);
         if (gs.mode) k_trace_refill<<<g_trace, 128, 0, stream>>>(sc, fp, bufs, bnc); else k_trace<<<g_trace, 128, 0, stream>>>(sc, fp, bufs, bnc);

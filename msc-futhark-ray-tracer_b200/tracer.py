@@ -94,6 +94,7 @@ def _load():
     L.lys_context_set_partition.argtypes = [vp, C.c_int, C.c_int]
     L.lys_context_set_profiling.argtypes = [vp, C.c_int]
     L.lys_context_profile_get.argtypes = [vp, vp, vp, C.c_int]
+    L.lys_context_profile_detail.argtypes = [vp, vp]
     L.lys_state_advance_rng.argtypes = [vp, C.POINTER(vp), vp, C.c_uint32]
     L.lys_context_device.argtypes = [vp]
     L.lys_context_stream.restype = vp
@@ -211,6 +212,11 @@ class Context:
         n = np.zeros(5, np.uint64)
         self.check(self._L.lys_context_profile_get(self._ctx, _ptr(ms), _ptr(n), int(reset)), 'lys_context_profile_get')
         return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(('generate', 'trace', 'shade', 'unused', 'accumulate'))}
+
+    def profile_detail(self):
+        ms = np.zeros(36, np.float32)
+        self.check(self._L.lys_context_profile_detail(self._ctx, _ptr(ms)), 'lys_context_profile_detail')
+        return {'trace': ms[:18].tolist(), 'shade': ms[18:].tolist()}
 
     @property
     def device(self):

@@ -10,7 +10,15 @@ passes = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 d = np.load(os.path.join(ROOT, 'tests', 'golden', 'scenes', name + '.npz'))
 ctx = pkg.Context()
 kw = {'origin': (0.0, 0.8, 0.6)} if name == 'mirrorbox' else {}
-s = pkg.State.init(ctx, d['tris'], d['tri_mats'], d['mats'], 1080, 1920, **kw)
+H, W = (int(os.environ.get('LYS_H', 1080)), int(os.environ.get('LYS_W', 1920)))
+s = pkg.State.init(ctx, d['tris'], d['tri_mats'], d['mats'], H, W, **kw)
 h, ptr, shape, st = s.sample_n_frames_device(passes)
 ctx.sync()
 print(name, shape, st)
+if os.environ.get('LYS_DETAIL'):
+    ctx.set_profiling(True); ctx.profile(reset=True)
+    s.sample_n_frames_device(passes)
+    d = ctx.profile_detail(); pr = ctx.profile()
+    print('per-pass us  trace:', [round(x * 1000 / passes, 1) for x in d['trace']])
+    print('per-pass us  shade:', [round(x * 1000 / passes, 1) for x in d['shade']])
+    print({k: round(v[0] * 1000 / passes, 1) for k, v in pr.items()})
