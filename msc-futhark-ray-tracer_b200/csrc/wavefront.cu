@@ -88,7 +88,6 @@ LYS_D int traverse(const float4 *__restrict__ nodes, const float4 *__restrict__ 
     t_hit = tmax;
     return closest;
 }
-
 /* ------------------------------------------------------------------ camera: camera.fut:68-110, integrator.fut:85-90 */
 LYS_DN void camera_sample(const FrameParams &fp, int col, int row, uint32_t &rng, V3 &o, V3 &d, float &wavelen, int &chan) {
     uint32_t x = lcg_next(rng);                                   /* random_select' rand.fut:39-42 */
