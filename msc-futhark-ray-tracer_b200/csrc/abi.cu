@@ -206,13 +206,13 @@ bool ensure_bufs(futhark_context *ctx, PassBuffers &b, int64_t n, bool probes) {
     if (b.cap < n) {
         raw_free(b.ray_o); raw_free(b.ray_d); raw_free(b.dist); raw_free(b.sum); raw_free(b.zsum); raw_free(b.best_d); raw_free(b.best_i);
         raw_free(b.chan); raw_free(b.queue[0]); raw_free(b.queue[1]); raw_free(b.hit); raw_free(b.sh_o); raw_free(b.sh_d1); raw_free(b.sh_d2);
-        raw_free(b.sh_c); raw_free(b.probe_rad); raw_free(b.probe_dist);
+        raw_free(b.sh_c); raw_free(b.tmp_a); raw_free(b.tmp_b); raw_free(b.probe_rad); raw_free(b.probe_dist);
         b.cap = 0;
         size_t c = (size_t)n;
         if (!raw_alloc(ctx, b.ray_o, c) || !raw_alloc(ctx, b.ray_d, c) || !raw_alloc(ctx, b.dist, c) || !raw_alloc(ctx, b.sum, c) ||
             !raw_alloc(ctx, b.zsum, c) || !raw_alloc(ctx, b.best_d, c) || !raw_alloc(ctx, b.best_i, c) || !raw_alloc(ctx, b.chan, c) ||
             !raw_alloc(ctx, b.queue[0], c) || !raw_alloc(ctx, b.queue[1], c) || !raw_alloc(ctx, b.hit, c) || !raw_alloc(ctx, b.sh_o, c) ||
-            !raw_alloc(ctx, b.sh_d1, c) || !raw_alloc(ctx, b.sh_d2, c) || !raw_alloc(ctx, b.sh_c, c)) return false;
+            !raw_alloc(ctx, b.sh_d1, c) || !raw_alloc(ctx, b.sh_d2, c) || !raw_alloc(ctx, b.sh_c, c) || !raw_alloc(ctx, b.tmp_a, c) || !raw_alloc(ctx, b.tmp_b, c)) return false;
         b.cap = n;
     }
     if (!b.counts) {
@@ -230,7 +230,7 @@ bool ensure_pass_buffers(futhark_context *ctx, int64_t n, bool probes) { return 
 void free_bufs(PassBuffers &b, bool owns_tx) {
     raw_free(b.ray_o); raw_free(b.ray_d); raw_free(b.dist); raw_free(b.sum); raw_free(b.zsum); raw_free(b.best_d); raw_free(b.best_i);
     raw_free(b.chan); raw_free(b.queue[0]); raw_free(b.queue[1]); raw_free(b.hit); raw_free(b.sh_o); raw_free(b.sh_d1); raw_free(b.sh_d2);
-    raw_free(b.sh_c); raw_free(b.counts); raw_free(b.stats); raw_free(b.probe_rad); raw_free(b.probe_dist);
+    raw_free(b.sh_c); raw_free(b.tmp_a); raw_free(b.tmp_b); raw_free(b.counts); raw_free(b.stats); raw_free(b.probe_rad); raw_free(b.probe_dist);
     if (owns_tx) raw_free(b.tx_lights);
     b.cap = 0;
 }

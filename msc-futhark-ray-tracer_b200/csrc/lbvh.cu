@@ -4,7 +4,7 @@
  * (src/radix_tree.fut:21-89):
  *   k_tri_boxes      bvh.fut:87          per-triangle AABB (center, half) + exact corner union per 256-triangle chunk
  *   k_bounds_fold    bvh.fut:88-90       scene bounds = LEFT FOLD of containing_aabb, reproduced
- *                                        exactly by a speculative block-skip fold (see below)
+ *                                        exactly by a per-axis speculative chunk-skipping fold (see below)
  *   k_morton         bvh.fut:91-94       30-bit Morton code of the normalised box centre
  *   k_hist/k_onesweep bvh.fut:95-97      stable LSD radix sort of (key, index): onesweep, 8-bit digits,
  *                                        decoupled look-back, 4 passes
@@ -19,6 +19,7 @@
 #include "lys_scene.h"
 #include "lys_device.cuh"
 #include <cstdio>
+#include <cstdlib>
 
 namespace lys {
 
@@ -80,48 +81,65 @@ __global__ void __launch_bounds__(BOX_CHUNK) k_tri_boxes(const float *__restrict
  * State changes are rare (a few hundred per million triangles), so the walk is O(#chunks/32) warp
  * steps plus the dirty chunks.  The result equals the sequential fold for any input. */
 #define FOLD_THREADS 1024
-#define FOLD_GRANULE 1024      /* elements staged per dirty step = 4 chunks */
+#define FOLD_GRANULE 1024      /* elements tested per dirty step = 4 chunks */
 #define FOLD_MAX_SUPER 1024    /* super-chunk (32 chunks) unions kept in shared memory */
-struct Corner { float lo[3], hi[3]; };
-__device__ __forceinline__ bool corners_inside(const float4 &l, const float4 &h, const V3 &slo, const V3 &shi) {
-    return l.x >= slo.x && l.y >= slo.y && l.z >= slo.z && h.x <= shi.x && h.y <= shi.y && h.z <= shi.z;   /* false on NaN */
+/* containing_aabb (shapes.fut:96-101) acts on each axis independently, so the fold is three independent scalar
+ * automata: CTA `axis` folds (center[axis], half[axis]).  Splitting them also splits the state changes
+ * (185 / 2 / 151 on the 1M-triangle scene instead of 335 jointly), and the three CTAs run concurrently. */
+struct Box1 { float c, h; };
+__device__ __forceinline__ Box1 contain1(Box1 a, Box1 b) {
+    float mn = lys_fminf(a.c - a.h, b.c - b.h);
+    float mx = lys_fmaxf(a.c + a.h, b.c + b.h);
+    Box1 r; r.c = 0.5f * (mn + mx); r.h = mx - r.c; return r;
 }
+__device__ __forceinline__ bool box1_equal(Box1 a, Box1 b) { return lys_f2u(a.c) == lys_f2u(b.c) && lys_f2u(a.h) == lys_f2u(b.h); }
+__device__ __forceinline__ float f4_axis(const float4 &v, int axis) { return axis == 0 ? v.x : (axis == 1 ? v.y : v.z); }
+/* dynamic shared memory: the first `n_chunk_sm` chunk unions of this axis (lo then hi) */
 __global__ void __launch_bounds__(FOLD_THREADS, 1)
 k_bounds_fold(const float4 *__restrict__ box_c, const float4 *__restrict__ box_h, const float4 *__restrict__ chunk_lo,
-              const float4 *__restrict__ chunk_hi, int n, float *__restrict__ bounds_out /* 6 */) {
-    __shared__ float4 sup_lo[FOLD_MAX_SUPER], sup_hi[FOLD_MAX_SUPER];
-    __shared__ Box S_sh;
-    __shared__ int next_chunk, first_changed;
+              const float4 *__restrict__ chunk_hi, int n, int n_chunk_sm, float *__restrict__ bounds_out /* 6 */) {
+    extern __shared__ float chunk_sm[];
+    __shared__ float sup_lo[FOLD_MAX_SUPER], sup_hi[FOLD_MAX_SUPER];
+    __shared__ Box1 S_sh;
+    __shared__ int next_chunk, first_changed[2];
+    const int axis = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n_chunks = (n + BOX_CHUNK - 1) / BOX_CHUNK;
     const int n_super = (n_chunks + 31) / 32;
     const int n_super_sm = min(n_super, FOLD_MAX_SUPER);
-    /* prologue: unions of 32 chunk unions (8192 triangles) */
+    float *clo_sm = chunk_sm, *chi_sm = chunk_sm + n_chunk_sm;
+    for (int j = tid; j < n_chunk_sm; j += FOLD_THREADS) { clo_sm[j] = f4_axis(__ldg(chunk_lo + j), axis); chi_sm[j] = f4_axis(__ldg(chunk_hi + j), axis); }
+    if (tid < 2) first_changed[tid] = 0x7fffffff;
+    __syncthreads();
+    /* prologue: unions of 32 chunk unions (8192 triangles); NaN poisons */
     for (int sidx = warp; sidx < n_super_sm; sidx += FOLD_THREADS / 32) {
         int j = sidx * 32 + lane;
-        float4 l = make_float4(LYS_INF, LYS_INF, LYS_INF, 0.0f), h = make_float4(-LYS_INF, -LYS_INF, -LYS_INF, 0.0f);
-        bool bad = false;
-        if (j < n_chunks) { l = __ldg(chunk_lo + j); h = __ldg(chunk_hi + j); bad = (l.x != l.x); }
-        l.x = warp_min(l.x); l.y = warp_min(l.y); l.z = warp_min(l.z); h.x = warp_max(h.x); h.y = warp_max(h.y); h.z = warp_max(h.z);
-        if (__ballot_sync(0xffffffffu, bad)) { float q = lys_u2f(0x7fc00000u); l = make_float4(q, q, q, 0.0f); h = l; }
+        float l = LYS_INF, h = -LYS_INF;
+        if (j < n_chunks) {
+            if (j < n_chunk_sm) { l = clo_sm[j]; h = chi_sm[j]; } else { l = f4_axis(__ldg(chunk_lo + j), axis); h = f4_axis(__ldg(chunk_hi + j), axis); }
+        }
+        bool bad = (l != l) || (h != h);
+        l = warp_min(l); h = warp_max(h);
+        if (__ballot_sync(0xffffffffu, bad)) { l = lys_u2f(0x7fc00000u); h = l; }
         if (lane == 0) { sup_lo[sidx] = l; sup_hi[sidx] = h; }
     }
-    Box S; S.c = v3(0.0f, 0.0f, 0.0f); S.h = v3(-LYS_INF, -LYS_INF, -LYS_INF);            /* bvh.fut:88-89 */
+    Box1 S; S.c = 0.0f; S.h = -LYS_INF;                                                     /* bvh.fut:88-89 */
     __syncthreads();
-    int cursor = 0;
+    int cursor = 0, round = 0;
+    int pre_base = -1; float pre_c = 0.0f, pre_h = 0.0f;                                    /* prefetched element of the next granule */
     while (cursor < n_chunks) {
         /* warp 0: find the first chunk >= cursor that S does not provably absorb */
         if (warp == 0) {
             int c = cursor;
-            if (box_bits_equal(contain(S, S), S)) {
-                V3 slo = S.c - S.h, shi = S.c + S.h;
+            if (box1_equal(contain1(S, S), S)) {
+                const float slo = S.c - S.h, shi = S.c + S.h;
                 while (c < n_chunks) {
                     if ((c & 31) == 0 && (c >> 5) < n_super_sm) {          /* aligned + indexed: try whole super-chunks first */
                         int s0 = c >> 5;
                         bool found = false;
                         while (s0 < n_super_sm) {
                             int sj = s0 + lane;
-                            bool dirty = (sj < n_super_sm) && !corners_inside(sup_lo[sj], sup_hi[sj], slo, shi);
+                            bool dirty = (sj < n_super_sm) && !(sup_lo[sj] >= slo && sup_hi[sj] <= shi);
                             unsigned m = __ballot_sync(0xffffffffu, dirty);
                             if (m) { s0 += __ffs(m) - 1; found = true; break; }
                             s0 += 32;
@@ -133,7 +151,11 @@ k_bounds_fold(const float4 *__restrict__ box_c, const float4 *__restrict__ box_h
                     /* chunk level inside the current (dirty or unindexed) super-chunk */
                     int j = (c & ~31) + lane;
                     bool dirty = false;
-                    if (j >= c && j < n_chunks) dirty = !corners_inside(__ldg(chunk_lo + j), __ldg(chunk_hi + j), slo, shi);
+                    if (j >= c && j < n_chunks) {
+                        float l, h;
+                        if (j < n_chunk_sm) { l = clo_sm[j]; h = chi_sm[j]; } else { l = f4_axis(__ldg(chunk_lo + j), axis); h = f4_axis(__ldg(chunk_hi + j), axis); }
+                        dirty = !(l >= slo && h <= shi);
+                    }
                     unsigned m = __ballot_sync(0xffffffffu, dirty);
                     if (m) { c = (c & ~31) + __ffs(m) - 1; break; }
                     c = (c & ~31) + 32;
@@ -148,18 +170,24 @@ k_bounds_fold(const float4 *__restrict__ box_c, const float4 *__restrict__ box_h
         /* fold a granule of FOLD_GRANULE elements starting at the dirty chunk, all threads testing in parallel */
         const int base = cursor * BOX_CHUNK;
         const int limit = min(FOLD_GRANULE, n - base);
-        Box mine; mine.c = v3(0.0f, 0.0f, 0.0f); mine.h = mine.c;
-        if (tid < limit) { float4 c4 = box_c[base + tid], h4 = box_h[base + tid]; mine.c = v3(c4.x, c4.y, c4.z); mine.h = v3(h4.x, h4.y, h4.z); }
+        Box1 mine; mine.c = 0.0f; mine.h = 0.0f;
+        if (tid < limit) {
+            if (pre_base == base) { mine.c = pre_c; mine.h = pre_h; }
+            else { mine.c = f4_axis(box_c[base + tid], axis); mine.h = f4_axis(box_h[base + tid], axis); }
+        }
+        pre_base = base + FOLD_GRANULE;                                    /* dirty granules come in runs */
+        if (pre_base + tid < n) { pre_c = f4_axis(box_c[pre_base + tid], axis); pre_h = f4_axis(box_h[pre_base + tid], axis); }
         int start = 0;
         while (true) {
-            if (tid == 0) first_changed = 0x7fffffff;
-            __syncthreads();
-            Box ns = S; bool ch = false;
-            if (tid >= start && tid < limit) { ns = contain(S, mine); ch = !box_bits_equal(ns, S); }
+            /* two barriers per round; the `first_changed` slot of the NEXT round is reset between them */
+            Box1 ns = S; bool ch = false;
+            if (tid >= start && tid < limit) { ns = contain1(S, mine); ch = !box1_equal(ns, S); }
             unsigned m = __ballot_sync(0xffffffffu, ch);
-            if (m && lane == __ffs(m) - 1) atomicMin(&first_changed, tid);
+            if (m && lane == __ffs(m) - 1) atomicMin(&first_changed[round & 1], tid);
             __syncthreads();
-            int f = first_changed;
+            int f = first_changed[round & 1];
+            if (tid == 0) first_changed[(round + 1) & 1] = 0x7fffffff;
+            round++;
             if (f == 0x7fffffff) break;
             if (tid == f) S_sh = ns;
             __syncthreads();
@@ -168,10 +196,7 @@ k_bounds_fold(const float4 *__restrict__ box_c, const float4 *__restrict__ box_h
         }
         cursor += (limit + BOX_CHUNK - 1) / BOX_CHUNK;
     }
-    if (tid == 0) {
-        bounds_out[0] = S.c.x; bounds_out[1] = S.c.y; bounds_out[2] = S.c.z;
-        bounds_out[3] = S.h.x; bounds_out[4] = S.h.y; bounds_out[5] = S.h.z;
-    }
+    if (tid == 0) { bounds_out[axis] = S.c; bounds_out[3 + axis] = S.h; }
 }
 
 /* ------------------------------------------------------------------ Morton keys */
@@ -402,7 +427,20 @@ __global__ void k_refit(const int *__restrict__ left, const int *__restrict__ ri
  * (k_crown_eval).  Level j holds the pairs with k = depth - j; level sizes live on the device.
  * If the pair buffer overflows (adversarially deep trees) the literal Jacobi sweeps are run instead. */
 struct CrownPair { int node; int child[2]; };    /* child slot (absolute) or -1 = resolved by rule */
-__device__ __forceinline__ int crown_level_base(const int *cnt, int level) { int b = 0; for (int q = 0; q < level; q++) b += cnt[q]; return b; }
+/* cnt[0..31] = pairs per level, cnt[32..62] = first slot of each level (cnt[32] = 0), cnt[63] = overflow flag.
+ * Every block derives its level range with three L2 loads by one thread (data written by the previous level). */
+__device__ __forceinline__ void crown_level_range(int *cnt, int level, int cap, int &base, int &count, int &next_base) {
+    __shared__ int range[3];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        volatile int *vc = cnt;
+        int b = vc[32 + level], c = vc[level];
+        range[0] = b; range[1] = min(c, max(cap - b, 0)); range[2] = b + c;
+        if (level + 1 < 31) vc[32 + level + 1] = b + c;          /* same value from every block */
+    }
+    __syncthreads();
+    base = range[0]; count = range[1]; next_base = range[2];
+}
 __global__ void k_crown_find(const float4 *__restrict__ F, const int *__restrict__ height, int n_nodes, int depth,
                              float4 *__restrict__ A, CrownPair *pairs, int *cnt, int cap, int *overflow) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -413,47 +451,78 @@ __global__ void k_crown_find(const float4 *__restrict__ F, const int *__restrict
         if (slot < cap) { pairs[slot].node = i; pairs[slot].child[0] = -1; pairs[slot].child[1] = -1; } else *overflow = 1;
     }
 }
-__global__ void k_crown_expand(const int *__restrict__ left, const int *__restrict__ right, const int *__restrict__ height,
+__device__ __forceinline__ void crown_expand_level(const int *__restrict__ left, const int *__restrict__ right, const int *__restrict__ height,
                                CrownPair *pairs, int *cnt, int level, int depth, int cap, int *overflow) {
-    const int base = crown_level_base(cnt, level), count = min(cnt[level], max(cap - base, 0));
-    const int next_base = base + cnt[level];
+    int base, count, next_base; crown_level_range(cnt, level, cap, base, count, next_base);
     const int k = depth - level;                 /* pairs of this level carry k; children carry k - 1 */
-    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < count; p += gridDim.x * blockDim.x) {
-        CrownPair pr = pairs[base + p];
-        int ch[2] = {left[pr.node], right[pr.node]};
-#pragma unroll
-        for (int sde = 0; sde < 2; sde++) {
-            int c = ch[sde], slot = -1;
-            if (c >= 0 && k - 1 >= 1 && height[c] > k - 1) {
-                slot = next_base + atomicAdd(&cnt[level + 1], 1);
-                if (slot < cap) { pairs[slot].node = c; pairs[slot].child[0] = -1; pairs[slot].child[1] = -1; } else { *overflow = 1; slot = -1; }
-            }
-            pairs[base + p].child[sde] = slot;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    /* warp-uniform trip count: slots of the next level are claimed with ONE atomic per warp (ballot + popcount) */
+    for (int p0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31); p0 < count; p0 += gridDim.x * blockDim.x) {
+        const int p = p0 + lane;
+        const bool valid = p < count;
+        int node = 0, cl = -1, cr = -1;
+        bool needl = false, needr = false;
+        if (valid) {
+            node = __ldcg(&pairs[base + p].node);
+            cl = left[node]; cr = right[node];
+            needl = cl >= 0 && k - 1 >= 1 && height[cl] > k - 1;
+            needr = cr >= 0 && k - 1 >= 1 && height[cr] > k - 1;
         }
+        const unsigned ml = __ballot_sync(0xffffffffu, needl), mr = __ballot_sync(0xffffffffu, needr);
+        int wbase = 0;
+        if (lane == 0 && (ml | mr)) wbase = atomicAdd(&cnt[level + 1], __popc(ml) + __popc(mr));
+        wbase = __shfl_sync(0xffffffffu, wbase, 0);
+        int sl = -1, sr = -1;
+        if (needl) { sl = next_base + wbase + __popc(ml & lt); if (sl < cap) { pairs[sl].node = cl; pairs[sl].child[0] = -1; pairs[sl].child[1] = -1; } else { *overflow = 1; sl = -1; } }
+        if (needr) { sr = next_base + wbase + __popc(ml) + __popc(mr & lt); if (sr < cap) { pairs[sr].node = cr; pairs[sr].child[0] = -1; pairs[sr].child[1] = -1; } else { *overflow = 1; sr = -1; } }
+        if (valid) { pairs[base + p].child[0] = sl; pairs[base + p].child[1] = sr; }
     }
 }
 __device__ __forceinline__ Box crown_child_box(int c, int slot, int ck, const float4 *leaf_box, const float4 *F, const float4 *pbox) {
     const float4 *src;
     if (c < 0) src = leaf_box + 2ll * (~c);
-    else if (slot >= 0) src = pbox + 2ll * slot;
+    else if (slot >= 0) { float4 a = __ldcg(pbox + 2ll * slot), b = __ldcg(pbox + 2ll * slot + 1); Box r; r.c = v3(a.x, a.y, a.z); r.h = v3(b.x, b.y, b.z); return r; }
     else if (ck == 0) { Box z; z.c = v3(0.0f, 0.0f, 0.0f); z.h = v3(0.0f, 0.0f, 0.0f); return z; }   /* bvh.fut:105-107 */
     else src = F + 2ll * c;                          /* height(c) <= ck: converged */
     float4 a = src[0], b = src[1];
     Box r; r.c = v3(a.x, a.y, a.z); r.h = v3(b.x, b.y, b.z); return r;
 }
-__global__ void k_crown_eval(const int *__restrict__ left, const int *__restrict__ right, const float4 *__restrict__ leaf_box,
-                             const float4 *__restrict__ F, const CrownPair *__restrict__ pairs, float4 *pbox, const int *__restrict__ cnt,
+__device__ __forceinline__ void crown_eval_level(const int *__restrict__ left, const int *__restrict__ right, const float4 *__restrict__ leaf_box,
+                             const float4 *__restrict__ F, const CrownPair *pairs, float4 *pbox, int *cnt,
                              int level, int depth, int cap, float4 *__restrict__ A) {
-    const int base = crown_level_base(cnt, level), count = min(cnt[level], max(cap - base, 0));
+    int base, count, next_base; crown_level_range(cnt, level, cap, base, count, next_base); (void)next_base;
     const int k = depth - level;
     for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < count; p += gridDim.x * blockDim.x) {
-        CrownPair pr = pairs[base + p];
+        CrownPair pr; pr.node = __ldcg(&pairs[base + p].node); pr.child[0] = __ldcg(&pairs[base + p].child[0]); pr.child[1] = __ldcg(&pairs[base + p].child[1]);
         int l = left[pr.node], r = right[pr.node];
         Box b = contain(crown_child_box(l, pr.child[0], k - 1, leaf_box, F, pbox), crown_child_box(r, pr.child[1], k - 1, leaf_box, F, pbox));
         float4 c4 = make_float4(b.c.x, b.c.y, b.c.z, 0.0f), h4 = make_float4(b.h.x, b.h.y, b.h.z, 0.0f);
         pbox[2ll * (base + p)] = c4; pbox[2ll * (base + p) + 1] = h4;
         if (level == 0) { A[2ll * pr.node] = c4; A[2ll * pr.node + 1] = h4; }
     }
+}
+__global__ void k_crown_expand(const int *__restrict__ left, const int *__restrict__ right, const int *__restrict__ height,
+                               CrownPair *pairs, int *cnt, int level, int depth, int cap, int *overflow) {
+    crown_expand_level(left, right, height, pairs, cnt, level, depth, cap, overflow);
+}
+__global__ void k_crown_eval(const int *__restrict__ left, const int *__restrict__ right, const float4 *__restrict__ leaf_box,
+                             const float4 *__restrict__ F, const CrownPair *pairs, float4 *pbox, int *cnt,
+                             int level, int depth, int cap, float4 *__restrict__ A) {
+    crown_eval_level(left, right, leaf_box, F, pairs, pbox, cnt, level, depth, cap, A);
+}
+/* The top levels are small (67, 92, 133, ... pairs on the 1M-triangle scene) and a launch per level costs ~6 us of
+ * pure latency, so one CTA walks them with block barriers in between; loads of data written earlier in the same
+ * kernel go through L2 (ld.cg / volatile; __syncthreads orders them within the CTA).  Only the last CROWN_TAIL_LEVELS (large) levels get their own launches. */
+#define CROWN_TAIL_LEVELS 8
+__global__ void __launch_bounds__(1024) k_crown_top_expand(const int *__restrict__ left, const int *__restrict__ right, const int *__restrict__ height,
+                                                           CrownPair *pairs, int *cnt, int n_levels, int depth, int cap, int *overflow) {
+    for (int lv = 0; lv < n_levels; lv++) { crown_expand_level(left, right, height, pairs, cnt, lv, depth, cap, overflow); __syncthreads(); }
+}
+__global__ void __launch_bounds__(1024) k_crown_top_eval(const int *__restrict__ left, const int *__restrict__ right, const float4 *__restrict__ leaf_box,
+                                                         const float4 *__restrict__ F, const CrownPair *pairs, float4 *pbox, int *cnt,
+                                                         int first_level, int depth, int cap, float4 *__restrict__ A) {
+    for (int lv = first_level; lv >= 0; lv--) { crown_eval_level(left, right, leaf_box, F, pairs, pbox, cnt, lv, depth, cap, A); __syncthreads(); }
 }
 /* the reference's own sweep (bvh.fut:114-120), ping-pong; used when the pair buffer overflows */
 __global__ void k_jacobi_sweep(const int *__restrict__ left, const int *__restrict__ right, const float4 *__restrict__ leaf_box,
@@ -493,7 +562,13 @@ cudaError_t build_lbvh(SceneDev &sc, BuildScratch &ws, int refit_mode, cudaStrea
     const int T = 256;
     uint64_t nl = 0;
     k_tri_boxes<<<cdiv(n, BOX_CHUNK), BOX_CHUNK, 0, stream>>>(sc.tris, n, ws.box_c, ws.box_h, ws.chunk_lo, ws.chunk_hi); nl++;
-    k_bounds_fold<<<1, FOLD_THREADS, 0, stream>>>(ws.box_c, ws.box_h, ws.chunk_lo, ws.chunk_hi, n, sc.bounds); nl++;
+    {
+        static bool attr_set = false;
+        const int max_chunk_sm = 24576;                                    /* 24576 x 8 B = 192 KB of dynamic shared memory (6.3 M triangles) */
+        if (!attr_set) { cudaFuncSetAttribute(k_bounds_fold, cudaFuncAttributeMaxDynamicSharedMemorySize, max_chunk_sm * 8); attr_set = true; }
+        const int n_chunk_sm = min(cdiv(n, BOX_CHUNK), max_chunk_sm);
+        k_bounds_fold<<<3, FOLD_THREADS, (size_t)n_chunk_sm * 8, stream>>>(ws.box_c, ws.box_h, ws.chunk_lo, ws.chunk_hi, n, n_chunk_sm, sc.bounds); nl++;
+    }
     k_morton<<<cdiv(n, T), T, 0, stream>>>(ws.box_c, n, sc.bounds, ws.keys[0], ws.vals[0]); nl++;
     /* radix sort */
     const int tiles = cdiv(n, RS_TILE);
@@ -527,9 +602,13 @@ cudaError_t build_lbvh(SceneDev &sc, BuildScratch &ws, int refit_mode, cudaStrea
     } else {
         cudaMemsetAsync(ws.crown_cnt, 0, 64 * sizeof(int), stream);
         k_crown_find<<<cdiv(n_nodes, T), T, 0, stream>>>(ws.F, sc.height, n_nodes, depth, sc.node_box, (CrownPair *)ws.crown_pairs, ws.crown_cnt, ws.crown_cap, ws.crown_cnt + 63); nl++;
+        /* expand levels 0 .. depth-2 (level lv creates level lv+1); eval levels depth-1 .. 0 */
         const int G = 148 * 4;
-        for (int lv = 0; lv < depth - 1; lv++) { k_crown_expand<<<G, T, 0, stream>>>(sc.left, sc.right, sc.height, (CrownPair *)ws.crown_pairs, ws.crown_cnt, lv, depth, ws.crown_cap, ws.crown_cnt + 63); nl++; }
-        for (int lv = depth - 1; lv >= 0; lv--) { k_crown_eval<<<G, T, 0, stream>>>(sc.left, sc.right, sc.leaf_box, ws.F, (const CrownPair *)ws.crown_pairs, ws.crown_box, ws.crown_cnt, lv, depth, ws.crown_cap, sc.node_box); nl++; }
+        const int n_top = max(0, (depth - 1) - CROWN_TAIL_LEVELS);            /* expand levels handled by the single CTA */
+        if (n_top > 0) { k_crown_top_expand<<<1, 1024, 0, stream>>>(sc.left, sc.right, sc.height, (CrownPair *)ws.crown_pairs, ws.crown_cnt, n_top, depth, ws.crown_cap, ws.crown_cnt + 63); nl++; }
+        for (int lv = n_top; lv < depth - 1; lv++) { k_crown_expand<<<G, T, 0, stream>>>(sc.left, sc.right, sc.height, (CrownPair *)ws.crown_pairs, ws.crown_cnt, lv, depth, ws.crown_cap, ws.crown_cnt + 63); nl++; }
+        for (int lv = depth - 1; lv > n_top; lv--) { k_crown_eval<<<G, T, 0, stream>>>(sc.left, sc.right, sc.leaf_box, ws.F, (const CrownPair *)ws.crown_pairs, ws.crown_box, ws.crown_cnt, lv, depth, ws.crown_cap, sc.node_box); nl++; }
+        k_crown_top_eval<<<1, 1024, 0, stream>>>(sc.left, sc.right, sc.leaf_box, ws.F, (const CrownPair *)ws.crown_pairs, ws.crown_box, ws.crown_cnt, min(n_top, depth - 1), depth, ws.crown_cap, sc.node_box); nl++;
     }
     k_pack_nodes<<<cdiv(n_nodes, T), T, 0, stream>>>(sc.node_box, sc.left, sc.right, n_nodes, sc.nodes); nl++;
     if (launches) *launches += nl;

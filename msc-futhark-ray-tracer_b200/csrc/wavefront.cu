@@ -170,135 +170,223 @@ LYS_DN float incident_radiance(const LightD &l, V3 hitp, V3 lightp, float wavele
 }
 LYS_D float balance1(float pf, float pg) { return 1.0f * pf / (1.0f * pf + 1.0f * pg); }   /* direct.fut:56-58, nf = ng = 1 */
 
-/* ------------------------------------------------------------------ shade */
-__global__ void __launch_bounds__(128, 8) k_shade(SceneDev sc, const __grid_constant__ FrameParams fp, PassBuffers b, int bounce) {
-    const int count = b.counts[bounce];
-    const int lane = threadIdx.x & 31;
-    const int stride = gridDim.x * blockDim.x;
-    /* persistent grid: warp-uniform trip count so that the ballot compaction below sees whole warps */
-    for (int i0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31); i0 < count; i0 += stride) {
-    const int i = i0 + lane;
-    bool alive = false;
-    int pid = -1;
-    unsigned n_vert = 0, n_shadow = 0;
-    if (i < count) {
-        pid = b.queue[bounce & 1][i];
-        float4 ro4 = b.ray_o[pid], rd4 = b.ray_d[pid];
-        V3 o = v3(ro4.x, ro4.y, ro4.z), d = v3(rd4.x, rd4.y, rd4.z);
-        float wavelen = ro4.w;
-        uint32_t rng = __float_as_uint(rd4.w);
-        int leaf = b.hit[i];
-        float4 rec_o = make_float4(0.0f, 0.0f, 0.0f, 0.0f), rec_d1 = rec_o, rec_d2 = rec_o, rec_c = rec_o;
-        if (leaf < 0) {
-            /* integrator.fut:76: the path ends on the ambience */
-            float amb = spectrum_lookup12(wavelen, fp.ambience);
-            rec_c = make_float4(0.0f, 0.0f, amb, LYS_INF);
-            rec_o.w = __int_as_float(4);       /* bit 2: miss vertex, radiance = rec_c.z */
-        } else {
-            n_vert = 1;
-            float4 q0 = __ldg(sc.leaf_tri + 3ll * leaf), q1 = __ldg(sc.leaf_tri + 3ll * leaf + 1), q2 = __ldg(sc.leaf_tri + 3ll * leaf + 2);
-            V3 ta = v3(q0.x, q0.y, q0.z), te1 = v3(q1.x, q1.y, q1.z), te2 = v3(q2.x, q2.y, q2.z);
-            const float *mrow = sc.mats + 28ll * (int)__float_as_uint(q0.w);
-            float t; V3 nc;
-            (void)tri_test(o, d, ta, te1, te2, FLT_MAX, t, nc);           /* bvh.fut:143-145 re-intersection */
-            V3 pos = o + t * d;
-            V3 n = normalise(nc);
-            rng_advance(rng);                                             /* integrator.fut:48 */
-            V3 wo = -d;
-            Onb onb = make_onb(n);
-            Mat1 m = material_at(mrow, wavelen);
-            V3 wo_l = to_local(onb, wo);
-            const int n_extra = (fp.tx_kind == 0) ? 0 : 8;
-            const int nl = fp.n_scene_lights + n_extra;
-            float cL = 0.0f, cB = 0.0f;
-            int flags = 0;
-            V3 so = pos + 0.001f * n;       /* mkray_adjust_acne with dot(w, n) > 0: same_side = 1 * n */
-            if (nl > 0) {                                                  /* direct.fut:116-122 */
-                uint32_t pick = lcg_next(rng) % (uint32_t)nl;
-                LightD l;
-                if ((int)pick < fp.n_scene_lights) load_light(sc.lights + pick, l);
-                else if (fp.tx_kind == 1) load_light(b.tx_lights + (pick - fp.n_scene_lights), l);
-                else {
-                    int col, row; int ix = local_to_pixel(fp, pid, col, row);
-                    uint32_t r0 = fp.frame_rng ^ rng_split_hash((uint32_t)ix);
-                    V3 po, pd; float pw; int pc;
-                    camera_sample(fp, col, row, r0, po, pd, pw, pc);
-                    scanning_light(fp, pd, (int)pick - fp.n_scene_lights, l);
-                }
-                /* light sample: sample_arealight peeks two draws (direct.fut:38,42) */
-                {
-                    uint32_t pk = rng;
-                    float u0 = rng_unit(pk), u1 = rng_unit(pk);
-                    float su = sqrtf(u0);
-                    float lu = 1.0f - su, lv = u1 * su;                    /* rand.fut:34-37 */
-                    V3 p = (l.a + lu * l.e1) + lv * l.e2;
-                    V3 vv = p - pos;
-                    V3 wi = normalise(vv);
-                    float in_rad = incident_radiance(l, pos, p, wavelen);
-                    float pdf = l.inv_area;
-                    bool facing = !(dot(wi, n) <= 0.0f);                   /* direct.fut:12 */
-                    if (facing && !(pdf == 0.0f || in_rad == 0.0f)) {      /* direct.fut:51-53,73-74 */
-                        float f, spdf;
-                        uber_eval(wo_l, to_local(onb, wi), m, f, spdf);
-                        f = f * lys_fabsf(dot(wi, n));
-                        float weight = balance1(pdf, spdf);
-                        cL = f * weight * in_rad / pdf;
-                        V3 sd = normalise(wi);
-                        rec_d1 = make_float4(sd.x, sd.y, sd.z, norm(vv) - 0.01f);
-                        flags |= 1;
-                    }
-                }
-                /* BSDF sample towards the same light (direct.fut:83-102) */
-                {
-                    DirSample s = sample_bsdf(wo, onb, m, rng);
-                    V3 bo, bd; ray_from_hit(pos, n, s.wi, bo, bd);
-                    float tl; V3 ncl;
-                    if (tri_test(bo, bd, l.a, l.e1, l.e2, FLT_MAX, tl, ncl)) {
-                        V3 lp = bo + tl * bd;
-                        V3 vv = lp - pos;
-                        V3 w = normalise(vv);
-                        if (!(dot(w, n) <= 0.0f) && s.kind != PDF_IMPOSSIBLE) {
-                            float in_rad = incident_radiance(l, pos, lp, wavelen);
-                            float f = s.bsdf * lys_fabsf(dot(s.wi, n));
-                            if (s.kind == PDF_DELTA) cB = f * in_rad;
-                            else { float weight = balance1(s.pdf, l.inv_area); cB = f * in_rad * weight / s.pdf; }
-                            V3 sd = normalise(w);
-                            rec_d2 = make_float4(sd.x, sd.y, sd.z, norm(vv) - 0.01f);
-                            flags |= 2;
-                        }
-                    }
-                }
-            }
-            float em = (bounce == 0) ? spectrum_lookup12(wavelen, mrow + 16) : 0.0f;   /* integrator.fut:51-53 */
-            float dist = b.dist[pid] + t;                                               /* :54 */
-            b.dist[pid] = dist;
-            rec_o = make_float4(so.x, so.y, so.z, __int_as_float(flags));
-            rec_c = make_float4(cL, cB, em, dist);
-            n_shadow = (flags & 1) + ((flags >> 1) & 1);
-            /* continuation (integrator.fut:56-75) */
-            DirSample s = sample_bsdf(wo, onb, m, rng);
-            float pdf = (s.kind == PDF_IMPOSSIBLE) ? 0.0f : ((s.kind == PDF_DELTA) ? 1.0f : s.pdf);
-            float cosf = lys_fabsf(dot(n, s.wi));
-            float p_term = 1.0f - s.bsdf * cosf / pdf;
-            bool terminate = rng_unit(rng) < p_term;
-            if (!(pdf == 0.0f || terminate) && bounce + 1 < fp.path_len) {
-                V3 no, nd; ray_from_hit(pos, n, s.wi, no, nd);
-                b.ray_o[pid] = make_float4(no.x, no.y, no.z, wavelen);
-                b.ray_d[pid] = make_float4(nd.x, nd.y, nd.z, __uint_as_float(rng));
-                alive = true;
-            }
-        }
-        b.sh_o[i] = rec_o; b.sh_d1[i] = rec_d1; b.sh_d2[i] = rec_d2; b.sh_c[i] = rec_c;
+/* ------------------------------------------------------------------ shade
+ * One vertex = prologue (re-intersection, material, frame) + light sample + BSDF-MIS sample + continuation.
+ * The monolithic kernel k_shade runs all of it; its executed code (~43 KB of SASS) does not fit the instruction
+ * cache and it stalls on instruction fetch (profiles/README.md 4.2).  For the populated early bounces the work is
+ * therefore also available as three phase kernels (k_shade_light / k_shade_bsdf / k_shade_cont) that each redo the
+ * small prologue and exchange their partial results through per-slot scratch; arithmetic is identical. */
+struct VertexCtx {
+    int pid, leaf;
+    V3 o, d, pos, n, wo, wo_l;
+    float wavelen, t;
+    uint32_t rng;                 /* state after the per-vertex advance_rng (integrator.fut:48) */
+    Onb onb; Mat1 m; const float *mrow;
+};
+LYS_D bool shade_prologue(const SceneDev &sc, const PassBuffers &b, int bounce, int i, VertexCtx &v) {
+    v.pid = b.queue[bounce & 1][i];
+    float4 ro4 = b.ray_o[v.pid], rd4 = b.ray_d[v.pid];
+    v.o = v3(ro4.x, ro4.y, ro4.z); v.d = v3(rd4.x, rd4.y, rd4.z);
+    v.wavelen = ro4.w;
+    v.rng = __float_as_uint(rd4.w);
+    v.leaf = b.hit[i];
+    if (v.leaf < 0) return false;
+    float4 q0 = __ldg(sc.leaf_tri + 3ll * v.leaf), q1 = __ldg(sc.leaf_tri + 3ll * v.leaf + 1), q2 = __ldg(sc.leaf_tri + 3ll * v.leaf + 2);
+    v.mrow = sc.mats + 28ll * (int)__float_as_uint(q0.w);
+    V3 nc;
+    (void)tri_test(v.o, v.d, v3(q0.x, q0.y, q0.z), v3(q1.x, q1.y, q1.z), v3(q2.x, q2.y, q2.z), FLT_MAX, v.t, nc);   /* bvh.fut:143-145 */
+    v.pos = v.o + v.t * v.d;
+    v.n = normalise(nc);
+    rng_advance(v.rng);                                                   /* integrator.fut:48 */
+    v.wo = -v.d;
+    v.onb = make_onb(v.n);
+    v.m = material_at(v.mrow, v.wavelen);
+    v.wo_l = to_local(v.onb, v.wo);
+    return true;
+}
+/* direct.fut:116-119: one raw draw picks the light (scene lights, then the 8 transmitter lights of this ray) */
+LYS_D void shade_pick_light(const SceneDev &sc, const FrameParams &fp, const PassBuffers &b, VertexCtx &v, int nl, LightD &l) {
+    uint32_t pick = lcg_next(v.rng) % (uint32_t)nl;
+    if ((int)pick < fp.n_scene_lights) load_light(sc.lights + pick, l);
+    else if (fp.tx_kind == 1) load_light(b.tx_lights + (pick - fp.n_scene_lights), l);
+    else {
+        int col, row; int ix = local_to_pixel(fp, v.pid, col, row);
+        uint32_t r0 = fp.frame_rng ^ rng_split_hash((uint32_t)ix);
+        V3 po, pd; float pw; int pc;
+        camera_sample(fp, col, row, r0, po, pd, pw, pc);
+        scanning_light(fp, pd, (int)pick - fp.n_scene_lights, l);
     }
-    /* compaction of live paths: warp ballot + prefix popcount, one atomic per warp */
+}
+/* light sample: sample_arealight peeks two draws (direct.fut:32-42), MIS weight (direct.fut:70-78) */
+LYS_D void shade_light_sample(const VertexCtx &v, const LightD &l, float &cL, float4 &rec_d1, int &flags) {
+    uint32_t pk = v.rng;
+    float u0 = rng_unit(pk), u1 = rng_unit(pk);
+    float su = sqrtf(u0);
+    float lu = 1.0f - su, lv = u1 * su;                                    /* rand.fut:34-37 */
+    V3 p = (l.a + lu * l.e1) + lv * l.e2;
+    V3 vv = p - v.pos;
+    V3 wi = normalise(vv);
+    float in_rad = incident_radiance(l, v.pos, p, v.wavelen);
+    float pdf = l.inv_area;
+    bool facing = !(dot(wi, v.n) <= 0.0f);                                 /* direct.fut:12 */
+    if (facing && !(pdf == 0.0f || in_rad == 0.0f)) {                      /* direct.fut:51-53,73-74 */
+        float f, spdf;
+        uber_eval(v.wo_l, to_local(v.onb, wi), v.m, f, spdf);
+        f = f * lys_fabsf(dot(wi, v.n));
+        float weight = balance1(pdf, spdf);
+        cL = f * weight * in_rad / pdf;
+        V3 sd = normalise(wi);
+        rec_d1 = make_float4(sd.x, sd.y, sd.z, norm(vv) - 0.01f);
+        flags |= 1;
+    }
+}
+/* BSDF sample towards the same light (direct.fut:83-102); advances v.rng */
+LYS_D void shade_bsdf_light_sample(VertexCtx &v, const LightD &l, float &cB, float4 &rec_d2, int &flags) {
+    DirSample s = sample_bsdf(v.wo, v.onb, v.m, v.rng);
+    V3 bo, bd; ray_from_hit(v.pos, v.n, s.wi, bo, bd);
+    float tl; V3 ncl;
+    if (tri_test(bo, bd, l.a, l.e1, l.e2, FLT_MAX, tl, ncl)) {
+        V3 lp = bo + tl * bd;
+        V3 vv = lp - v.pos;
+        V3 w = normalise(vv);
+        if (!(dot(w, v.n) <= 0.0f) && s.kind != PDF_IMPOSSIBLE) {
+            float in_rad = incident_radiance(l, v.pos, lp, v.wavelen);
+            float f = s.bsdf * lys_fabsf(dot(s.wi, v.n));
+            if (s.kind == PDF_DELTA) cB = f * in_rad;
+            else { float weight = balance1(s.pdf, l.inv_area); cB = f * in_rad * weight / s.pdf; }
+            V3 sd = normalise(w);
+            rec_d2 = make_float4(sd.x, sd.y, sd.z, norm(vv) - 0.01f);
+            flags |= 2;
+        }
+    }
+}
+/* emission, distance, shadow record, continuation + roulette (integrator.fut:51-75); returns true if the path lives on */
+LYS_D bool shade_finish(const FrameParams &fp, const PassBuffers &b, int bounce, int i, VertexCtx &v, float cL, float cB, int flags) {
+    float em = (bounce == 0) ? spectrum_lookup12(v.wavelen, v.mrow + 16) : 0.0f;      /* integrator.fut:51-53 */
+    float dist = b.dist[v.pid] + v.t;                                                   /* :54 */
+    b.dist[v.pid] = dist;
+    V3 so = v.pos + 0.001f * v.n;       /* mkray_adjust_acne with dot(w, n) > 0: same_side = 1 * n */
+    b.sh_o[i] = make_float4(so.x, so.y, so.z, __int_as_float(flags));
+    b.sh_c[i] = make_float4(cL, cB, em, dist);
+    DirSample s = sample_bsdf(v.wo, v.onb, v.m, v.rng);
+    float pdf = (s.kind == PDF_IMPOSSIBLE) ? 0.0f : ((s.kind == PDF_DELTA) ? 1.0f : s.pdf);
+    float cosf = lys_fabsf(dot(v.n, s.wi));
+    float p_term = 1.0f - s.bsdf * cosf / pdf;
+    bool terminate = rng_unit(v.rng) < p_term;
+    if (!(pdf == 0.0f || terminate) && bounce + 1 < fp.path_len) {
+        V3 no, nd; ray_from_hit(v.pos, v.n, s.wi, no, nd);
+        b.ray_o[v.pid] = make_float4(no.x, no.y, no.z, v.wavelen);
+        b.ray_d[v.pid] = make_float4(nd.x, nd.y, nd.z, __uint_as_float(v.rng));
+        return true;
+    }
+    return false;
+}
+LYS_D void shade_miss(const FrameParams &fp, const PassBuffers &b, int i, const VertexCtx &v) {
+    float amb = spectrum_lookup12(v.wavelen, fp.ambience);                 /* integrator.fut:76 */
+    b.sh_o[i] = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(4));          /* bit 2: miss vertex, radiance = sh_c.z */
+    b.sh_c[i] = make_float4(0.0f, 0.0f, amb, LYS_INF);
+}
+/* compaction of live paths (warp ballot + prefix popcount, one atomic per warp) and statistics */
+LYS_D void shade_compact(const PassBuffers &b, int bounce, bool alive, int pid, unsigned n_vert, unsigned n_shadow) {
+    const int lane = threadIdx.x & 31;
     unsigned mask = __ballot_sync(0xffffffffu, alive);
     int base = 0;
     if (lane == 0 && mask) base = atomicAdd(&b.counts[bounce + 1], __popc(mask));
     base = __shfl_sync(0xffffffffu, base, 0);
     if (alive) b.queue[(bounce + 1) & 1][base + __popc(mask & ((1u << lane) - 1u))] = pid;
-    /* statistics */
     unsigned vsum = __reduce_add_sync(0xffffffffu, n_vert), ssum = __reduce_add_sync(0xffffffffu, n_shadow);
     if (lane == 0 && (vsum | ssum)) { atomicAdd(&b.stats[0], (unsigned long long)vsum); atomicAdd(&b.stats[2], (unsigned long long)ssum); }
+}
+
+/* monolithic: everything for one vertex in one thread */
+__global__ void __launch_bounds__(128, 8) k_shade(SceneDev sc, const __grid_constant__ FrameParams fp, PassBuffers b, int bounce) {
+    const int count = b.counts[bounce];
+    const int lane = threadIdx.x & 31;
+    const int stride = gridDim.x * blockDim.x;
+    const int nl = fp.n_scene_lights + ((fp.tx_kind == 0) ? 0 : 8);
+    /* persistent grid: warp-uniform trip count so that the ballot compaction sees whole warps */
+    for (int i0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31); i0 < count; i0 += stride) {
+        const int i = i0 + lane;
+        bool alive = false; int pid = -1; unsigned n_vert = 0, n_shadow = 0;
+        if (i < count) {
+            VertexCtx v;
+            if (shade_prologue(sc, b, bounce, i, v)) {
+                float cL = 0.0f, cB = 0.0f; int flags = 0;
+                float4 rec_d1 = make_float4(0.0f, 0.0f, 0.0f, 0.0f), rec_d2 = rec_d1;
+                if (nl > 0) {
+                    LightD l;
+                    shade_pick_light(sc, fp, b, v, nl, l);
+                    shade_light_sample(v, l, cL, rec_d1, flags);
+                    shade_bsdf_light_sample(v, l, cB, rec_d2, flags);
+                }
+                b.sh_d1[i] = rec_d1; b.sh_d2[i] = rec_d2;
+                alive = shade_finish(fp, b, bounce, i, v, cL, cB, flags);
+                n_vert = 1; n_shadow = (flags & 1) + ((flags >> 1) & 1);
+            } else shade_miss(fp, b, i, v);
+            pid = v.pid;
+        }
+        shade_compact(b, bounce, alive, pid, n_vert, n_shadow);
+    }
+}
+/* phase kernels: light sample */
+__global__ void __launch_bounds__(128, 8) k_shade_light(SceneDev sc, const __grid_constant__ FrameParams fp, PassBuffers b, int bounce) {
+    const int count = b.counts[bounce];
+    const int stride = gridDim.x * blockDim.x;
+    const int nl = fp.n_scene_lights + ((fp.tx_kind == 0) ? 0 : 8);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+        VertexCtx v;
+        float cL = 0.0f; int flags = 0;
+        float4 rec_d1 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (shade_prologue(sc, b, bounce, i, v)) {
+            LightD l;
+            shade_pick_light(sc, fp, b, v, nl, l);
+            shade_light_sample(v, l, cL, rec_d1, flags);
+        }
+        b.sh_d1[i] = rec_d1;
+        b.tmp_a[i] = make_float2(cL, __int_as_float(flags));
+    }
+}
+/* phase kernels: BSDF-MIS sample (advances the rng; the new state travels in tmp_b.z) */
+__global__ void __launch_bounds__(128, 8) k_shade_bsdf(SceneDev sc, const __grid_constant__ FrameParams fp, PassBuffers b, int bounce) {
+    const int count = b.counts[bounce];
+    const int stride = gridDim.x * blockDim.x;
+    const int nl = fp.n_scene_lights + ((fp.tx_kind == 0) ? 0 : 8);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+        VertexCtx v;
+        float cB = 0.0f; int flags = 0;
+        float4 rec_d2 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (shade_prologue(sc, b, bounce, i, v)) {
+            LightD l;
+            shade_pick_light(sc, fp, b, v, nl, l);
+            shade_bsdf_light_sample(v, l, cB, rec_d2, flags);
+        }
+        b.sh_d2[i] = rec_d2;
+        b.tmp_b[i] = make_float4(cB, __int_as_float(flags), __uint_as_float(v.rng), 0.0f);
+    }
+}
+/* phase kernels: records + continuation + compaction; `split` = the two kernels above ran for this bounce */
+__global__ void __launch_bounds__(128, 8) k_shade_cont(SceneDev sc, const __grid_constant__ FrameParams fp, PassBuffers b, int bounce, int split) {
+    const int count = b.counts[bounce];
+    const int lane = threadIdx.x & 31;
+    const int stride = gridDim.x * blockDim.x;
+    for (int i0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31); i0 < count; i0 += stride) {
+        const int i = i0 + lane;
+        bool alive = false; int pid = -1; unsigned n_vert = 0, n_shadow = 0;
+        if (i < count) {
+            VertexCtx v;
+            if (shade_prologue(sc, b, bounce, i, v)) {
+                float cL = 0.0f, cB = 0.0f; int flags = 0;
+                if (split) {
+                    float2 ta = b.tmp_a[i]; float4 tb = b.tmp_b[i];
+                    cL = ta.x; cB = tb.x; flags = __float_as_int(ta.y) | __float_as_int(tb.y);
+                    v.rng = __float_as_uint(tb.z);
+                } else { b.sh_d1[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f); b.sh_d2[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f); }
+                alive = shade_finish(fp, b, bounce, i, v, cL, cB, flags);
+                n_vert = 1; n_shadow = (flags & 1) + ((flags >> 1) & 1);
+            } else shade_miss(fp, b, i, v);
+            pid = v.pid;
+        }
+        shade_compact(b, bounce, alive, pid, n_vert, n_shadow);
     }
 }
 
@@ -581,7 +669,7 @@ __global__ void k_material_probe(const float *mat28, float wavelen, V3 wo, V3 wi
 static inline int cdiv(long long a, int b) { return (int)((a + b - 1) / b); }
 
 /* persistent grids: SM count x resident CTAs per SM of each kernel (queried once per device) */
-struct GridSizes { int trace = 0, shade = 0, refill = 0; int mode = 0; };
+struct GridSizes { int trace = 0, shade = 0, refill = 0, sl = 0, sb = 0, sc = 0; int mode = 0, split_bounces = 0; };
 static GridSizes grid_sizes() {
     static GridSizes g[64];
     int dev = 0; cudaGetDevice(&dev);
@@ -594,6 +682,11 @@ static GridSizes grid_sizes() {
         int br = 8; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&br, k_trace_refill, 128, 0);
         g[dev].trace = sms * (bt > 0 ? bt : 1); g[dev].shade = sms * (bs > 0 ? bs : 1); g[dev].refill = sms * (br > 0 ? br : 1);
         const char *e = getenv("LYS_TRACE_MODE"); g[dev].mode = (e && atoi(e) == 1) ? 1 : 0;
+        int b1 = 8, b2 = 8, b3 = 8;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, k_shade_light, 128, 0); cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b2, k_shade_bsdf, 128, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b3, k_shade_cont, 128, 0);
+        g[dev].sl = sms * (b1 > 0 ? b1 : 1); g[dev].sb = sms * (b2 > 0 ? b2 : 1); g[dev].sc = sms * (b3 > 0 ? b3 : 1);
+        const char *sp = getenv("LYS_SHADE_SPLIT"); if (sp) g[dev].split_bounces = atoi(sp);     /* phase kernels for bounces < this */
     }
     return g[dev];
 }
@@ -611,7 +704,16 @@ cudaError_t run_sample_pass(const SceneDev &sc, const FrameParams &fp, PassBuffe
     tm.end(stream); nl++;
     for (int bnc = 0; bnc < fp.path_len; bnc++) {
         tm.cur_bounce = bnc;
-        tm.begin(2, stream); k_shade<<<g_shade, 128, 0, stream>>>(sc, fp, bufs, bnc); tm.end(stream); nl++;
+        tm.begin(2, stream);
+        if (bnc < gs.split_bounces) {
+            const int nlights = fp.n_scene_lights + ((fp.tx_kind == 0) ? 0 : 8);
+            if (nlights > 0) {
+                k_shade_light<<<min(gs.sl, cdiv(n, 128)), 128, 0, stream>>>(sc, fp, bufs, bnc);
+                k_shade_bsdf<<<min(gs.sb, cdiv(n, 128)), 128, 0, stream>>>(sc, fp, bufs, bnc); nl += 2;
+            }
+            k_shade_cont<<<min(gs.sc, cdiv(n, 128)), 128, 0, stream>>>(sc, fp, bufs, bnc, nlights > 0 ? 1 : 0);
+        } else k_shade<<<g_shade, 128, 0, stream>>>(sc, fp, bufs, bnc);
+        tm.end(stream); nl++;
         tm.begin(1, stream);
         if (gs.mode) k_trace_refill<<<g_trace, 128, 0, stream>>>(sc, fp, bufs, bnc); else k_trace<<<g_trace, 128, 0, stream>>>(sc, fp, bufs, bnc);
         tm.end(stream); nl++;
