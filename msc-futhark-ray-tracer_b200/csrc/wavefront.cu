@@ -298,27 +298,34 @@ LYS_D void shade_compact(const PassBuffers &b, int bounce, bool alive, int pid, 
     if (lane == 0 && (vsum | ssum)) { atomicAdd(&b.stats[0], (unsigned long long)vsum); atomicAdd(&b.stats[2], (unsigned long long)ssum); }
 }
 
-/* monolithic: everything for one vertex in one thread */
-__global__ void __launch_bounds__(128, 8) k_shade(SceneDev sc, const __grid_constant__ FrameParams fp, PassBuffers b, int bounce) {
+/* monolithic: everything for one vertex in one thread.  The kernel's code is larger than the instruction cache, so
+ * the warps of a CTA are kept in lockstep with block barriers between the phases (block-uniform loop): they then
+ * fetch the same code lines together instead of each warp missing on its own. */
+#ifndef SHADE_THREADS
+#define SHADE_THREADS 512
+#endif
+__global__ void __launch_bounds__(SHADE_THREADS, 2048 / SHADE_THREADS / 2) k_shade(SceneDev sc, const __grid_constant__ FrameParams fp, PassBuffers b, int bounce) {
     const int count = b.counts[bounce];
-    const int lane = threadIdx.x & 31;
     const int stride = gridDim.x * blockDim.x;
     const int nl = fp.n_scene_lights + ((fp.tx_kind == 0) ? 0 : 8);
-    /* persistent grid: warp-uniform trip count so that the ballot compaction sees whole warps */
-    for (int i0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31); i0 < count; i0 += stride) {
-        const int i = i0 + lane;
-        bool alive = false; int pid = -1; unsigned n_vert = 0, n_shadow = 0;
-        if (i < count) {
-            VertexCtx v;
-            if (shade_prologue(sc, b, bounce, i, v)) {
-                float cL = 0.0f, cB = 0.0f; int flags = 0;
-                float4 rec_d1 = make_float4(0.0f, 0.0f, 0.0f, 0.0f), rec_d2 = rec_d1;
-                if (nl > 0) {
-                    LightD l;
-                    shade_pick_light(sc, fp, b, v, nl, l);
-                    shade_light_sample(v, l, cL, rec_d1, flags);
-                    shade_bsdf_light_sample(v, l, cB, rec_d2, flags);
-                }
+    for (int b0 = blockIdx.x * blockDim.x; b0 < count; b0 += stride) {
+        const int i = b0 + threadIdx.x;
+        const bool valid = i < count;
+        bool alive = false, hit = false; int pid = -1; unsigned n_vert = 0, n_shadow = 0;
+        VertexCtx v;
+        float cL = 0.0f, cB = 0.0f; int flags = 0;
+        float4 rec_d1 = make_float4(0.0f, 0.0f, 0.0f, 0.0f), rec_d2 = rec_d1;
+        LightD l;
+        if (valid) hit = shade_prologue(sc, b, bounce, i, v);
+        const bool lit = hit && nl > 0;
+        __syncthreads();
+        if (lit) shade_pick_light(sc, fp, b, v, nl, l);
+        if (lit) shade_light_sample(v, l, cL, rec_d1, flags);
+        __syncthreads();
+        if (lit) shade_bsdf_light_sample(v, l, cB, rec_d2, flags);
+        __syncthreads();
+        if (valid) {
+            if (hit) {
                 b.sh_d1[i] = rec_d1; b.sh_d2[i] = rec_d2;
                 alive = shade_finish(fp, b, bounce, i, v, cL, cB, flags);
                 n_vert = 1; n_shadow = (flags & 1) + ((flags >> 1) & 1);
@@ -678,7 +685,7 @@ static GridSizes grid_sizes() {
         int sms = 148, bt = 8, bs = 4;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bt, k_trace, 128, 0);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bs, k_shade, 128, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bs, k_shade, SHADE_THREADS, 0);
         int br = 8; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&br, k_trace_refill, 128, 0);
         g[dev].trace = sms * (bt > 0 ? bt : 1); g[dev].shade = sms * (bs > 0 ? bs : 1); g[dev].refill = sms * (br > 0 ? br : 1);
         const char *e = getenv("LYS_TRACE_MODE"); g[dev].mode = (e && atoi(e) == 1) ? 1 : 0;
@@ -696,7 +703,7 @@ cudaError_t run_sample_pass(const SceneDev &sc, const FrameParams &fp, PassBuffe
     uint64_t nl = 0;
     LaunchTimer none; LaunchTimer &tm = timer ? *timer : none;
     const GridSizes gs = grid_sizes();
-    const int g_trace = min(gs.mode ? gs.refill : gs.trace, cdiv(2ll * n, 128)), g_shade = min(gs.shade, cdiv(n, 128));
+    const int g_trace = min(gs.mode ? gs.refill : gs.trace, cdiv(2ll * n, 128)), g_shade = min(gs.shade, cdiv(n, SHADE_THREADS));
     tm.begin(0, stream); k_generate<<<cdiv(n, 256), 256, 0, stream>>>(fp, bufs); tm.end(stream); nl++;
     tm.cur_bounce = -1;
     tm.begin(1, stream);
@@ -712,7 +719,7 @@ cudaError_t run_sample_pass(const SceneDev &sc, const FrameParams &fp, PassBuffe
                 k_shade_bsdf<<<min(gs.sb, cdiv(n, 128)), 128, 0, stream>>>(sc, fp, bufs, bnc); nl += 2;
             }
             k_shade_cont<<<min(gs.sc, cdiv(n, 128)), 128, 0, stream>>>(sc, fp, bufs, bnc, nlights > 0 ? 1 : 0);
-        } else k_shade<<<g_shade, 128, 0, stream>>>(sc, fp, bufs, bnc);
+        } else k_shade<<<g_shade, SHADE_THREADS, 0, stream>>>(sc, fp, bufs, bnc);
         tm.end(stream); nl++;
         tm.begin(1, stream);
         if (gs.mode) k_trace_refill<<<g_trace, 128, 0, stream>>>(sc, fp, bufs, bnc); else k_trace<<<g_trace, 128, 0, stream>>>(sc, fp, bufs, bnc);
