@@ -191,6 +191,39 @@ def test_path_len_knob(orc, pkg, gpu, scenes):
         gpu.set_path_len(16)
 
 
+def test_edge_configurations(orc, pkg, gpu, scenes):
+    """Ragged / degenerate inputs: 1x1 and odd-sized frames, odd subsampling, a scene without lights (direct_radiance
+    consumes no draws, direct.fut:116-117), sky ambience, path_len 1, huge and tiny coordinates."""
+    t, tm, m = scenes['cornell']
+    for h, w in ((1, 1), (1, 37), (33, 1), (67, 129)):
+        so, sg = both(orc, pkg, gpu, (t, tm, m), h, w)
+        assert bits_equal(so.sample_n_frames(3), sg.sample_n_frames(3)), (h, w)
+    so, sg = both(orc, pkg, gpu, (t, tm, m), 45, 71)
+    so, sg = so.key(0x32).key(0x32).key(0x6D), sg.key(0x32).key(0x32).key(0x6D)          # subsampling 3: grid 15 x 24
+    so, sg = so.step().step(), sg.step().step()
+    assert so.image().shape == (15, 24, 3) and bits_equal(so.image(), sg.image()) and bits_equal(so.render(), sg.render())
+    dark = m.copy(); dark[:, 16:] = np.tile(np.array([-1, 0], np.float32), 6)             # no emissive material -> no lights
+    so, sg = both(orc, pkg, gpu, (t, tm, dark), 40, 56)
+    assert sg.info()['n_lights'] == 0
+    so, sg = so.key(0x70), sg.key(0x70)                                                   # sky on: radiance only from misses
+    qo, qg = so.probe_pass(), sg.probe_pass()
+    assert bits_equal(qo['radiance'], qg['radiance']) and qo['radiance'].max() > 0
+    orc.set_path_len(1); gpu.set_path_len(1)
+    try:
+        so, sg = both(orc, pkg, gpu, (t, tm, m), 40, 56)
+        assert bits_equal(so.sample_n_frames(2), sg.sample_n_frames(2))
+    finally:
+        orc.set_path_len(16); gpu.set_path_len(16)
+    for scale, off in ((1e4, 3e5), (1e-3, 0.0)):
+        ts = (t * np.float32(scale) + np.float32(off)).astype(np.float32)
+        org = tuple(np.float32(v) * np.float32(scale) + np.float32(off) for v in (0.0, 0.8, 1.8))
+        so, sg = both(orc, pkg, gpu, (ts, tm, m), 36, 48, origin=org)
+        bo, bg = so.bvh(), sg.bvh()
+        for k in ('bounds', 'morton', 'src_index', 'left', 'right', 'node_aabb'):
+            assert bits_equal(bo[k], bg[k]), (scale, k)
+        assert bits_equal(so.probe_pass()['radiance'], sg.probe_pass()['radiance']), scale
+
+
 def test_row_partition_sums_to_full_image(pkg, gpu, scenes):
     """Multi-GPU split emulated on one device: ranks 0..2 of a world of 3 each render their rows; the sum equals
     the single-GPU image bit-for-bit (every pixel is non-zero on exactly one rank)."""
