@@ -80,12 +80,15 @@ template <class T> bool raw_alloc(futhark_context *ctx, T *&p, size_t count) {
 }
 template <class T> void raw_free(T *&p) { if (p) cudaFree(p); p = nullptr; }
 
+/* scene buffers come from (and go back to) the context's block pool: re-initialising a scene of the same size
+ * (the e2e benchmark does it every step) costs no cudaMalloc / cudaFree (cudaFree synchronises the device) */
 struct SceneHolder {
     SceneDev d;
-    ~SceneHolder() {
-        raw_free(d.tris); raw_free(d.tri_mats); raw_free(d.mats); raw_free(d.leaf_tri); raw_free(d.leaf_box); raw_free(d.nodes);
-        raw_free(d.node_box); raw_free(d.left); raw_free(d.right); raw_free(d.parent); raw_free(d.height); raw_free(d.morton);
-        raw_free(d.sorted_idx); raw_free(d.bounds); raw_free(d.lights); raw_free(d.light_src);
+    std::vector<DevRef> blocks;
+    template <class T> bool take(futhark_context *ctx, T *&p, size_t count) {
+        DevRef r = dev_alloc(ctx, sizeof(T) * (count ? count : 1));
+        if (!r) return false;
+        p = (T *)r->p; blocks.push_back(r); return true;
     }
 };
 
@@ -505,11 +508,12 @@ int futhark_entry_init(struct futhark_context *ctx, struct futhark_opaque_state 
     SceneDev &sc = holder->d;
     sc.n_tris = n; sc.n_mats = m; sc.n_lights = (int64_t)light_src.size();
     size_t c = (size_t)n;
-    if (!raw_alloc(ctx, sc.tris, 9 * c) || !raw_alloc(ctx, sc.tri_mats, c) || !raw_alloc(ctx, sc.mats, (size_t)m * 28) ||
-        !raw_alloc(ctx, sc.leaf_tri, 3 * c) || !raw_alloc(ctx, sc.leaf_box, 2 * c) || !raw_alloc(ctx, sc.nodes, 2 * c) ||
-        !raw_alloc(ctx, sc.node_box, 2 * c) || !raw_alloc(ctx, sc.left, c) || !raw_alloc(ctx, sc.right, c) || !raw_alloc(ctx, sc.parent, c) ||
-        !raw_alloc(ctx, sc.height, c) || !raw_alloc(ctx, sc.morton, c) || !raw_alloc(ctx, sc.sorted_idx, c) || !raw_alloc(ctx, sc.bounds, 8) ||
-        !raw_alloc(ctx, sc.lights, light_src.size()) || !raw_alloc(ctx, sc.light_src, light_src.size())) return 1;
+    SceneHolder &H = *holder;
+    if (!H.take(ctx, sc.tris, 9 * c) || !H.take(ctx, sc.tri_mats, c) || !H.take(ctx, sc.mats, (size_t)m * 28) ||
+        !H.take(ctx, sc.leaf_tri, 3 * c) || !H.take(ctx, sc.leaf_box, 2 * c) || !H.take(ctx, sc.nodes, 2 * c) ||
+        !H.take(ctx, sc.node_box, 2 * c) || !H.take(ctx, sc.left, c) || !H.take(ctx, sc.right, c) || !H.take(ctx, sc.parent, c) ||
+        !H.take(ctx, sc.height, c) || !H.take(ctx, sc.morton, c) || !H.take(ctx, sc.sorted_idx, c) || !H.take(ctx, sc.bounds, 8) ||
+        !H.take(ctx, sc.lights, light_src.size()) || !H.take(ctx, sc.light_src, light_src.size())) return 1;
     CU(ctx, cudaMemcpyAsync(sc.tris, tri_geoms->mem->p, sizeof(float) * 9 * c, cudaMemcpyDeviceToDevice, ctx->stream));
     CU(ctx, cudaMemcpyAsync(sc.tri_mats, tri_mats->mem->p, sizeof(uint32_t) * c, cudaMemcpyDeviceToDevice, ctx->stream));
     CU(ctx, cudaMemcpyAsync(sc.mats, mat_data->mem->p, sizeof(float) * (size_t)m * 28, cudaMemcpyDeviceToDevice, ctx->stream));
