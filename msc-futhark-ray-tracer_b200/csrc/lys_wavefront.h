@@ -34,13 +34,13 @@ struct FrameParams {
  * queues and shadow records by queue slot. */
 struct PassBuffers {
     int64_t cap = 0;
-    float4 *ray_o = nullptr;    /* origin.xyz | wavelength */
-    float4 *ray_d = nullptr;    /* dir.xyz    | rng state (bits) */
+    /* rays live at QUEUE SLOTS (ping-pong per bounce): written coalesced at the compacted slot by k_shade, read
+     * coalesced by k_trace / k_shade of the next bounce; everything else per path is indexed by path id */
+    float4 *ray_o[2] = {nullptr, nullptr};    /* origin.xyz | wavelength */
+    float4 *ray_d[2] = {nullptr, nullptr};    /* dir.xyz    | rng state (bits) */
     float *dist = nullptr;      /* cumulative distance (integrator.fut:54) */
-    float *sum = nullptr;       /* sum of vertex radiance            (integrator.fut:164-168) */
-    float *zsum = nullptr;      /* sum of vertex radiance * 0        (the other two channels)  */
-    float *best_d = nullptr;    /* nearest valid vertex (distance render / point cloud) */
-    float *best_i = nullptr;
+    float4 *acc = nullptr;      /* x: sum of vertex radiance (integrator.fut:164-168), y: sum of radiance * 0 (the other
+                                   channels), z: distance of the nearest valid vertex (inf = none), w: its intensity */
     uint8_t *chan = nullptr;
     int *queue[2] = {nullptr, nullptr};
     int *hit = nullptr;         /* per slot: sorted-leaf index or -1 */
@@ -80,7 +80,7 @@ struct LaunchTimer {
     ~LaunchTimer() { for (auto e : ev0) cudaEventDestroy(e); for (auto e : ev1) cudaEventDestroy(e); }
 };
 
-/* one sample pass: generate, (extend, shade, connect) x path_len.  Results stay in bufs (sum, zsum, best_*). */
+/* one sample pass: generate, (extend, shade, connect) x path_len.  Results stay in bufs.acc. */
 cudaError_t run_sample_pass(const SceneDev &sc, const FrameParams &fp, PassBuffers &bufs, cudaStream_t stream, uint64_t *launches, LaunchTimer *timer = nullptr);
 /* resolve + merge into the image: mode 0 = replace (sample_frame), 1 = running average (sample_frame_accum) */
 cudaError_t run_accumulate(const FrameParams &fp, const PassBuffers &bufs, const float *img_old, float *img_new,

@@ -123,10 +123,10 @@ __global__ void __launch_bounds__(256) k_generate(const __grid_constant__ FrameP
     uint32_t rng = fp.frame_rng ^ rng_split_hash((uint32_t)ix);   /* split_rng integrator.fut:109-114 */
     V3 o, d; float wl; int ch;
     camera_sample(fp, col, row, rng, o, d, wl, ch);
-    b.ray_o[pid] = make_float4(o.x, o.y, o.z, wl);
-    b.ray_d[pid] = make_float4(d.x, d.y, d.z, __uint_as_float(rng));
-    b.dist[pid] = 0.0f; b.sum[pid] = 0.0f; b.zsum[pid] = 0.0f;
-    b.best_d[pid] = LYS_INF; b.best_i[pid] = 0.0f;
+    b.ray_o[0][pid] = make_float4(o.x, o.y, o.z, wl);          /* bounce 0: slot == path id */
+    b.ray_d[0][pid] = make_float4(d.x, d.y, d.z, __uint_as_float(rng));
+    b.dist[pid] = 0.0f;
+    b.acc[pid] = make_float4(0.0f, 0.0f, LYS_INF, 0.0f);
     b.chan[pid] = (uint8_t)ch;
     b.queue[0][pid] = pid;
     if (b.probe_rad) for (int k = 0; k < LYS_MAX_PATH_LEN; k++) { b.probe_rad[(size_t)pid * 16 + k] = 0.0f; b.probe_dist[(size_t)pid * 16 + k] = LYS_INF; }
@@ -185,7 +185,7 @@ struct VertexCtx {
 };
 LYS_D bool shade_prologue(const SceneDev &sc, const PassBuffers &b, int bounce, int i, VertexCtx &v) {
     v.pid = b.queue[bounce & 1][i];
-    float4 ro4 = b.ray_o[v.pid], rd4 = b.ray_d[v.pid];
+    float4 ro4 = b.ray_o[bounce & 1][i], rd4 = b.ray_d[bounce & 1][i];
     v.o = v3(ro4.x, ro4.y, ro4.z); v.d = v3(rd4.x, rd4.y, rd4.z);
     v.wavelen = ro4.w;
     v.rng = __float_as_uint(rd4.w);
@@ -261,7 +261,8 @@ LYS_D void shade_bsdf_light_sample(VertexCtx &v, const LightD &l, float &cB, flo
     }
 }
 /* emission, distance, shadow record, continuation + roulette (integrator.fut:51-75); returns true if the path lives on */
-LYS_D bool shade_finish(const FrameParams &fp, const PassBuffers &b, int bounce, int i, VertexCtx &v, float cL, float cB, int flags) {
+LYS_D bool shade_finish(const FrameParams &fp, const PassBuffers &b, int bounce, int i, VertexCtx &v, float cL, float cB, int flags,
+                        float4 &next_o, float4 &next_d) {
     float em = (bounce == 0) ? spectrum_lookup12(v.wavelen, v.mrow + 16) : 0.0f;      /* integrator.fut:51-53 */
     float dist = b.dist[v.pid] + v.t;                                                   /* :54 */
     b.dist[v.pid] = dist;
@@ -275,8 +276,8 @@ LYS_D bool shade_finish(const FrameParams &fp, const PassBuffers &b, int bounce,
     bool terminate = rng_unit(v.rng) < p_term;
     if (!(pdf == 0.0f || terminate) && bounce + 1 < fp.path_len) {
         V3 no, nd; ray_from_hit(v.pos, v.n, s.wi, no, nd);
-        b.ray_o[v.pid] = make_float4(no.x, no.y, no.z, v.wavelen);
-        b.ray_d[v.pid] = make_float4(nd.x, nd.y, nd.z, __uint_as_float(v.rng));
+        next_o = make_float4(no.x, no.y, no.z, v.wavelen);
+        next_d = make_float4(nd.x, nd.y, nd.z, __uint_as_float(v.rng));
         return true;
     }
     return false;
@@ -287,13 +288,17 @@ LYS_D void shade_miss(const FrameParams &fp, const PassBuffers &b, int i, const 
     b.sh_c[i] = make_float4(0.0f, 0.0f, amb, LYS_INF);
 }
 /* compaction of live paths (warp ballot + prefix popcount, one atomic per warp) and statistics */
-LYS_D void shade_compact(const PassBuffers &b, int bounce, bool alive, int pid, unsigned n_vert, unsigned n_shadow) {
+LYS_D void shade_compact(const PassBuffers &b, int bounce, bool alive, int pid, float4 next_o, float4 next_d, unsigned n_vert, unsigned n_shadow) {
     const int lane = threadIdx.x & 31;
     unsigned mask = __ballot_sync(0xffffffffu, alive);
     int base = 0;
     if (lane == 0 && mask) base = atomicAdd(&b.counts[bounce + 1], __popc(mask));
     base = __shfl_sync(0xffffffffu, base, 0);
-    if (alive) b.queue[(bounce + 1) & 1][base + __popc(mask & ((1u << lane) - 1u))] = pid;
+    if (alive) {
+        const int slot = base + __popc(mask & ((1u << lane) - 1u));
+        b.queue[(bounce + 1) & 1][slot] = pid;
+        b.ray_o[(bounce + 1) & 1][slot] = next_o; b.ray_d[(bounce + 1) & 1][slot] = next_d;       /* coalesced: consecutive lanes, consecutive slots */
+    }
     unsigned vsum = __reduce_add_sync(0xffffffffu, n_vert), ssum = __reduce_add_sync(0xffffffffu, n_shadow);
     if (lane == 0 && (vsum | ssum)) { atomicAdd(&b.stats[0], (unsigned long long)vsum); atomicAdd(&b.stats[2], (unsigned long long)ssum); }
 }
@@ -312,6 +317,7 @@ __global__ void __launch_bounds__(SHADE_THREADS, 2048 / SHADE_THREADS / 2) k_sha
         const int i = b0 + threadIdx.x;
         const bool valid = i < count;
         bool alive = false, hit = false; int pid = -1; unsigned n_vert = 0, n_shadow = 0;
+        float4 next_o = make_float4(0.0f, 0.0f, 0.0f, 0.0f), next_d = next_o;
         VertexCtx v;
         float cL = 0.0f, cB = 0.0f; int flags = 0;
         float4 rec_d1 = make_float4(0.0f, 0.0f, 0.0f, 0.0f), rec_d2 = rec_d1;
@@ -327,12 +333,12 @@ __global__ void __launch_bounds__(SHADE_THREADS, 2048 / SHADE_THREADS / 2) k_sha
         if (valid) {
             if (hit) {
                 b.sh_d1[i] = rec_d1; b.sh_d2[i] = rec_d2;
-                alive = shade_finish(fp, b, bounce, i, v, cL, cB, flags);
+                alive = shade_finish(fp, b, bounce, i, v, cL, cB, flags, next_o, next_d);
                 n_vert = 1; n_shadow = (flags & 1) + ((flags >> 1) & 1);
             } else shade_miss(fp, b, i, v);
             pid = v.pid;
         }
-        shade_compact(b, bounce, alive, pid, n_vert, n_shadow);
+        shade_compact(b, bounce, alive, pid, next_o, next_d, n_vert, n_shadow);
     }
 }
 /* phase kernels: light sample */
@@ -379,6 +385,7 @@ __global__ void __launch_bounds__(128, 8) k_shade_cont(SceneDev sc, const __grid
     for (int i0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31); i0 < count; i0 += stride) {
         const int i = i0 + lane;
         bool alive = false; int pid = -1; unsigned n_vert = 0, n_shadow = 0;
+        float4 next_o = make_float4(0.0f, 0.0f, 0.0f, 0.0f), next_d = next_o;
         if (i < count) {
             VertexCtx v;
             if (shade_prologue(sc, b, bounce, i, v)) {
@@ -388,12 +395,12 @@ __global__ void __launch_bounds__(128, 8) k_shade_cont(SceneDev sc, const __grid
                     cL = ta.x; cB = tb.x; flags = __float_as_int(ta.y) | __float_as_int(tb.y);
                     v.rng = __float_as_uint(tb.z);
                 } else { b.sh_d1[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f); b.sh_d2[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f); }
-                alive = shade_finish(fp, b, bounce, i, v, cL, cB, flags);
+                alive = shade_finish(fp, b, bounce, i, v, cL, cB, flags, next_o, next_d);
                 n_vert = 1; n_shadow = (flags & 1) + ((flags >> 1) & 1);
             } else shade_miss(fp, b, i, v);
             pid = v.pid;
         }
-        shade_compact(b, bounce, alive, pid, n_vert, n_shadow);
+        shade_compact(b, bounce, alive, pid, next_o, next_d, n_vert, n_shadow);
     }
 }
 
@@ -430,10 +437,12 @@ LYS_D void connect_finish(const FrameParams &fp, const PassBuffers &b, int bounc
         if (nl > 0) { float light_pdf = 1.0f / (float)nl; direct = (L + B) / light_pdf; }   /* direct.fut:121-122 */
         r = direct + ((bounce == 0) ? em : 0.0f);                                          /* integrator.fut:51-53 */
     }
-    b.sum[pid] = b.sum[pid] + r * 1.0f;
-    b.zsum[pid] = b.zsum[pid] + r * 0.0f;
+    float4 a = b.acc[pid];
+    a.x = a.x + r * 1.0f;
+    a.y = a.y + r * 0.0f;
     float inten = r * fp.intensity_factor;
-    if (inten > 0.0f && dist > 0.5f && dist < 10.0f && dist < b.best_d[pid]) { b.best_d[pid] = dist; b.best_i[pid] = inten; }
+    if (inten > 0.0f && dist > 0.5f && dist < 10.0f && dist < a.z) { a.z = dist; a.w = inten; }
+    b.acc[pid] = a;
     if (b.probe_rad) { b.probe_rad[(size_t)pid * 16 + bounce] = r; b.probe_dist[(size_t)pid * 16 + bounce] = dist; }
 }
 __global__ void __launch_bounds__(128) k_trace_refill(SceneDev sc, const __grid_constant__ FrameParams fp, PassBuffers b, int bounce) {
@@ -464,8 +473,7 @@ __global__ void __launch_bounds__(128) k_trace_refill(SceneDev sc, const __grid_
             cursor = min(range_end, cursor + __popc(idle));
             if (st.item < 0 && mine < range_end) {
                 if (mine < n_ext) {                                        /* extend item of bounce + 1 */
-                    int pid = b.queue[(bounce + 1) & 1][mine];
-                    float4 ro = b.ray_o[pid], rd = b.ray_d[pid];
+                    float4 ro = b.ray_o[(bounce + 1) & 1][mine], rd = b.ray_d[(bounce + 1) & 1][mine];
                     st.item = mine; st.phase = 0;
                     lane_start_ray(st, v3(ro.x, ro.y, ro.z), v3(rd.x, rd.y, rd.z), FLT_MAX);
                 } else {                                                   /* connect item of bounce */
@@ -539,8 +547,7 @@ __global__ void __launch_bounds__(128) k_trace(SceneDev sc, const __grid_constan
     const int n_nodes = (int)sc.n_tris - 1;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
         if (i < n_ext) {
-            int pid = b.queue[(bounce + 1) & 1][i];
-            float4 ro = b.ray_o[pid], rd = b.ray_d[pid];
+            float4 ro = b.ray_o[(bounce + 1) & 1][i], rd = b.ray_d[(bounce + 1) & 1][i];
             float t;
             b.hit[i] = traverse<false>(sc.nodes, sc.leaf_tri, n_nodes, v3(ro.x, ro.y, ro.z), v3(rd.x, rd.y, rd.z), FLT_MAX, t);
         } else {
@@ -569,12 +576,13 @@ LYS_D V3 hue_to_rgb(float h) {                                       /* integrat
 }
 LYS_D V3 resolve_pixel(const FrameParams &fp, const PassBuffers &b, int pid) {   /* visualize integrator.fut:150-168 */
     if (fp.render_mode == 1) {
-        float bd = b.best_d[pid];
+        float bd = b.acc[pid].z;
         if (lys_isinff(bd)) return v3(0.0f, 0.0f, 0.0f);
         return hue_to_rgb(0.85f * (bd - 0.5f) / (10.0f - 0.5f));
     }
     V3 vis = fp.sensor_vis[b.chan[pid]];
-    float s = b.sum[pid], z = b.zsum[pid];
+    const float4 a = b.acc[pid];
+    float s = a.x, z = a.y;
     float k = (float)fp.n_sensor;
     return v3(k * (vis.x == 1.0f ? s : z), k * (vis.y == 1.0f ? s : z), k * (vis.z == 1.0f ? s : z));
 }
@@ -598,14 +606,15 @@ __global__ void __launch_bounds__(256) k_points_merge(const __grid_constant__ Fr
     int pid = blockIdx.x * blockDim.x + threadIdx.x;
     if (pid >= fp.n_local) return;
     int col, row; int ix = local_to_pixel(fp, pid, col, row);
-    float bd = b.best_d[pid];
+    const float4 acc = b.acc[pid];
+    float bd = acc.z;
     float4 p2 = make_float4(-1.0f, -1.0f, -1.0f, 0.0f); float d2 = LYS_INF;     /* lib.fut:47 */
     if (!lys_isinff(bd)) {
         uint32_t r0 = fp.frame_rng ^ rng_split_hash((uint32_t)ix);
         V3 o, d; float w; int c;
         camera_sample(fp, col, row, r0, o, d, w, c);
         V3 pp = o + bd * d;                                                      /* to_cloud_points integrator.fut:122-126 */
-        p2 = make_float4(pp.x, pp.y, pp.z, b.best_i[pid]); d2 = bd;
+        p2 = make_float4(pp.x, pp.y, pp.z, acc.w); d2 = bd;
     }
     if (first || !(pdist[ix] < d2)) { pos_int[ix] = p2; pdist[ix] = d2; }        /* merge lib.fut:48-51 */
 }
@@ -631,7 +640,7 @@ __global__ void __launch_bounds__(256) k_render(const float *__restrict__ img, i
 __global__ void k_primary_probe(SceneDev sc, PassBuffers b, int n, int *leaf, int *src, float *t) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    float4 ro = b.ray_o[i], rd = b.ray_d[i];
+    float4 ro = b.ray_o[0][i], rd = b.ray_d[0][i];
     float th;
     int l = traverse<false>(sc.nodes, sc.leaf_tri, (int)sc.n_tris - 1, v3(ro.x, ro.y, ro.z), v3(rd.x, rd.y, rd.z), FLT_MAX, th);
     leaf[i] = l;
