@@ -107,17 +107,25 @@ LYS_HDI float spectrum_lookup12(float v, const float *k /* 6 x (wavelength, valu
 struct Hit { float t; V3 pos, n; };
 /* hit_triangle (shapes.fut:66-86) on a triangle stored as vertex a and edges e1 = b - a, e2 = c - a */
 LYS_D bool tri_test(V3 o, V3 d, V3 a, V3 e1, V3 e2, float tmax, float &t_out, V3 &ncross) {
+    /* The reference computes (t, u, v) = (1/det) * (n.s, m.e2, -(m.e1)) and then tests
+     * `u >= 0 && v >= 0 && u + v <= 1 && t < tmax && t > 0`.  The values and the boolean below are identical; only
+     * the order of evaluation is chosen so that the common rejections leave early:
+     *  - t = fl(inv * dn) with sign(inv) == sign(det): if dn == 0 or the signs differ, t is <= 0 or -0 -> reject
+     *    before the IEEE division;
+     *  - t is tested against (0, tmax) before u and v are computed. */
     V3 n = cross(e1, e2);
     float det = -(dot(n, d));
     if (det > -0.00001f && det < 0.00001f) return false;                                /* approx_zero common.fut:35 */
     V3 s = o - a;
-    V3 m = cross(s, d);
+    float dn = dot(n, s);
+    if (!((dn > 0.0f && det > 0.0f) || (dn < 0.0f && det < 0.0f))) return false;        /* t > 0 impossible */
     float inv = 1.0f / det;
-    float t = inv * dot(n, s);
+    float t = inv * dn;
+    if (!(t < tmax && t > 0.0f)) return false;                                          /* in_bounds :64 */
+    V3 m = cross(s, d);
     float u = inv * dot(m, e2);
     float v = inv * (-(dot(m, e1)));
     if (!(u >= 0.0f && v >= 0.0f && u + v <= 1.0f)) return false;
-    if (!(t < tmax && t > 0.0f)) return false;                                          /* in_bounds :64 */
     t_out = t; ncross = n;
     return true;
 }

@@ -309,6 +309,9 @@ LYS_D void shade_compact(const PassBuffers &b, int bounce, bool alive, int pid, 
 #ifndef SHADE_THREADS
 #define SHADE_THREADS 512
 #endif
+#ifndef SHADE_BARRIERS
+#define SHADE_BARRIERS 3
+#endif
 __global__ void __launch_bounds__(SHADE_THREADS, 2048 / SHADE_THREADS / 2) k_shade(SceneDev sc, const __grid_constant__ FrameParams fp, PassBuffers b, int bounce) {
     const int count = b.counts[bounce];
     const int stride = gridDim.x * blockDim.x;
@@ -324,12 +327,18 @@ __global__ void __launch_bounds__(SHADE_THREADS, 2048 / SHADE_THREADS / 2) k_sha
         LightD l;
         if (valid) hit = shade_prologue(sc, b, bounce, i, v);
         const bool lit = hit && nl > 0;
+#if SHADE_BARRIERS >= 1
         __syncthreads();
+#endif
         if (lit) shade_pick_light(sc, fp, b, v, nl, l);
         if (lit) shade_light_sample(v, l, cL, rec_d1, flags);
+#if SHADE_BARRIERS >= 2
         __syncthreads();
+#endif
         if (lit) shade_bsdf_light_sample(v, l, cB, rec_d2, flags);
+#if SHADE_BARRIERS >= 3
         __syncthreads();
+#endif
         if (valid) {
             if (hit) {
                 b.sh_d1[i] = rec_d1; b.sh_d2[i] = rec_d2;

@@ -1204,6 +1204,15 @@ void orc_closest_hits(const orc_state *s, const float *rays, int64_t n, int32_t 
         leaf[k] = ok ? th.leaf : -1; if (t) t[k] = ok ? th.h.t : F32_INF;
     }
 }
+void orc_closest_hits_steps(const orc_state *s, const float *rays, int64_t n, int32_t *box_tests, int32_t *tri_tests) {
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int64_t k = 0; k < n; k++) {
+        ray r = {{rays[6 * k], rays[6 * k + 1], rays[6 * k + 2]}, {rays[6 * k + 3], rays[6 * k + 4], rays[6 * k + 5]}};
+        uint64_t b0 = t_counters.box_tests, t0 = t_counters.tri_tests;
+        trav_hit th; (void)bvh_closest_hit(F32_HIGHEST, r, s->scene->objs, th);
+        box_tests[k] = (int32_t)(t_counters.box_tests - b0); tri_tests[k] = (int32_t)(t_counters.tri_tests - t0);
+    }
+}
 void orc_any_hits(const orc_state *s, const float *rays, const float *tmax, int64_t n, int32_t *hit_out) {
 #pragma omp parallel for schedule(dynamic, 64)
     for (int64_t k = 0; k < n; k++) {

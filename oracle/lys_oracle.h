@@ -83,6 +83,8 @@ void orc_probe_pass(const orc_state *s, float *radiance, float *distance, int32_
 /* brute-force closest hit over all triangles (mk_fake_bvh semantics, bvh.fut:31-39) for rays [n][6] */
 void orc_brute_force_hits(const orc_state *s, const float *rays, int64_t n, int32_t *src_tri, float *t);
 void orc_closest_hits(const orc_state *s, const float *rays, int64_t n, int32_t *leaf, float *t);
+/* per-ray work of the closest-hit walk: box tests and triangle tests (divergence studies) */
+void orc_closest_hits_steps(const orc_state *s, const float *rays, int64_t n, int32_t *box_tests, int32_t *tri_tests);
 void orc_any_hits(const orc_state *s, const float *rays, const float *tmax, int64_t n, int32_t *hit);
 
 /* Work counters accumulated since the last reset (define the algorithmic-bytes figure). */
