@@ -38,7 +38,7 @@ struct PassBuffers {
      * coalesced by k_trace / k_shade of the next bounce; everything else per path is indexed by path id */
     float4 *ray_o[2] = {nullptr, nullptr};    /* origin.xyz | wavelength */
     float4 *ray_d[2] = {nullptr, nullptr};    /* dir.xyz    | rng state (bits) */
-    float *dist = nullptr;      /* cumulative distance (integrator.fut:54) */
+    float *dist[2] = {nullptr, nullptr};      /* cumulative distance (integrator.fut:54), slot-indexed like the rays */
     float4 *acc = nullptr;      /* x: sum of vertex radiance (integrator.fut:164-168), y: sum of radiance * 0 (the other
                                    channels), z: distance of the nearest valid vertex (inf = none), w: its intensity */
     uint8_t *chan = nullptr;

@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(256) k_generate(const __grid_constant__ FrameP
     camera_sample(fp, col, row, rng, o, d, wl, ch);
     b.ray_o[0][pid] = make_float4(o.x, o.y, o.z, wl);          /* bounce 0: slot == path id */
     b.ray_d[0][pid] = make_float4(d.x, d.y, d.z, __uint_as_float(rng));
-    b.dist[pid] = 0.0f;
+    b.dist[0][pid] = 0.0f;
     b.acc[pid] = make_float4(0.0f, 0.0f, LYS_INF, 0.0f);
     b.chan[pid] = (uint8_t)ch;
     b.queue[0][pid] = pid;
@@ -262,10 +262,10 @@ LYS_D void shade_bsdf_light_sample(VertexCtx &v, const LightD &l, float &cB, flo
 }
 /* emission, distance, shadow record, continuation + roulette (integrator.fut:51-75); returns true if the path lives on */
 LYS_D bool shade_finish(const FrameParams &fp, const PassBuffers &b, int bounce, int i, VertexCtx &v, float cL, float cB, int flags,
-                        float4 &next_o, float4 &next_d) {
+                        float4 &next_o, float4 &next_d, float &next_dist) {
     float em = (bounce == 0) ? spectrum_lookup12(v.wavelen, v.mrow + 16) : 0.0f;      /* integrator.fut:51-53 */
-    float dist = b.dist[v.pid] + v.t;                                                   /* :54 */
-    b.dist[v.pid] = dist;
+    const float dist = b.dist[bounce & 1][i] + v.t;                                     /* :54 */
+    next_dist = dist;
     V3 so = v.pos + 0.001f * v.n;       /* mkray_adjust_acne with dot(w, n) > 0: same_side = 1 * n */
     b.sh_o[i] = make_float4(so.x, so.y, so.z, __int_as_float(flags));
     b.sh_c[i] = make_float4(cL, cB, em, dist);
@@ -288,7 +288,7 @@ LYS_D void shade_miss(const FrameParams &fp, const PassBuffers &b, int i, const 
     b.sh_c[i] = make_float4(0.0f, 0.0f, amb, LYS_INF);
 }
 /* compaction of live paths (warp ballot + prefix popcount, one atomic per warp) and statistics */
-LYS_D void shade_compact(const PassBuffers &b, int bounce, bool alive, int pid, float4 next_o, float4 next_d, unsigned n_vert, unsigned n_shadow) {
+LYS_D void shade_compact(const PassBuffers &b, int bounce, bool alive, int pid, float4 next_o, float4 next_d, float next_dist, unsigned n_vert, unsigned n_shadow) {
     const int lane = threadIdx.x & 31;
     unsigned mask = __ballot_sync(0xffffffffu, alive);
     int base = 0;
@@ -297,7 +297,7 @@ LYS_D void shade_compact(const PassBuffers &b, int bounce, bool alive, int pid, 
     if (alive) {
         const int slot = base + __popc(mask & ((1u << lane) - 1u));
         b.queue[(bounce + 1) & 1][slot] = pid;
-        b.ray_o[(bounce + 1) & 1][slot] = next_o; b.ray_d[(bounce + 1) & 1][slot] = next_d;       /* coalesced: consecutive lanes, consecutive slots */
+        b.ray_o[(bounce + 1) & 1][slot] = next_o; b.ray_d[(bounce + 1) & 1][slot] = next_d; b.dist[(bounce + 1) & 1][slot] = next_dist;       /* coalesced: consecutive lanes, consecutive slots */
     }
     unsigned vsum = __reduce_add_sync(0xffffffffu, n_vert), ssum = __reduce_add_sync(0xffffffffu, n_shadow);
     if (lane == 0 && (vsum | ssum)) { atomicAdd(&b.stats[0], (unsigned long long)vsum); atomicAdd(&b.stats[2], (unsigned long long)ssum); }
@@ -320,7 +320,7 @@ __global__ void __launch_bounds__(SHADE_THREADS, 2048 / SHADE_THREADS / 2) k_sha
         const int i = b0 + threadIdx.x;
         const bool valid = i < count;
         bool alive = false, hit = false; int pid = -1; unsigned n_vert = 0, n_shadow = 0;
-        float4 next_o = make_float4(0.0f, 0.0f, 0.0f, 0.0f), next_d = next_o;
+        float4 next_o = make_float4(0.0f, 0.0f, 0.0f, 0.0f), next_d = next_o; float next_dist = 0.0f;
         VertexCtx v;
         float cL = 0.0f, cB = 0.0f; int flags = 0;
         float4 rec_d1 = make_float4(0.0f, 0.0f, 0.0f, 0.0f), rec_d2 = rec_d1;
@@ -342,12 +342,12 @@ __global__ void __launch_bounds__(SHADE_THREADS, 2048 / SHADE_THREADS / 2) k_sha
         if (valid) {
             if (hit) {
                 b.sh_d1[i] = rec_d1; b.sh_d2[i] = rec_d2;
-                alive = shade_finish(fp, b, bounce, i, v, cL, cB, flags, next_o, next_d);
+                alive = shade_finish(fp, b, bounce, i, v, cL, cB, flags, next_o, next_d, next_dist);
                 n_vert = 1; n_shadow = (flags & 1) + ((flags >> 1) & 1);
             } else shade_miss(fp, b, i, v);
             pid = v.pid;
         }
-        shade_compact(b, bounce, alive, pid, next_o, next_d, n_vert, n_shadow);
+        shade_compact(b, bounce, alive, pid, next_o, next_d, next_dist, n_vert, n_shadow);
     }
 }
 /* phase kernels: light sample */
@@ -394,7 +394,7 @@ __global__ void __launch_bounds__(128, 8) k_shade_cont(SceneDev sc, const __grid
     for (int i0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31); i0 < count; i0 += stride) {
         const int i = i0 + lane;
         bool alive = false; int pid = -1; unsigned n_vert = 0, n_shadow = 0;
-        float4 next_o = make_float4(0.0f, 0.0f, 0.0f, 0.0f), next_d = next_o;
+        float4 next_o = make_float4(0.0f, 0.0f, 0.0f, 0.0f), next_d = next_o; float next_dist = 0.0f;
         if (i < count) {
             VertexCtx v;
             if (shade_prologue(sc, b, bounce, i, v)) {
@@ -404,12 +404,12 @@ __global__ void __launch_bounds__(128, 8) k_shade_cont(SceneDev sc, const __grid
                     cL = ta.x; cB = tb.x; flags = __float_as_int(ta.y) | __float_as_int(tb.y);
                     v.rng = __float_as_uint(tb.z);
                 } else { b.sh_d1[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f); b.sh_d2[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f); }
-                alive = shade_finish(fp, b, bounce, i, v, cL, cB, flags, next_o, next_d);
+                alive = shade_finish(fp, b, bounce, i, v, cL, cB, flags, next_o, next_d, next_dist);
                 n_vert = 1; n_shadow = (flags & 1) + ((flags >> 1) & 1);
             } else shade_miss(fp, b, i, v);
             pid = v.pid;
         }
-        shade_compact(b, bounce, alive, pid, next_o, next_d, n_vert, n_shadow);
+        shade_compact(b, bounce, alive, pid, next_o, next_d, next_dist, n_vert, n_shadow);
     }
 }
 
