@@ -510,7 +510,7 @@ int futhark_entry_init(struct futhark_context *ctx, struct futhark_opaque_state 
     size_t c = (size_t)n;
     SceneHolder &H = *holder;
     if (!H.take(ctx, sc.tris, 9 * c) || !H.take(ctx, sc.tri_mats, c) || !H.take(ctx, sc.mats, (size_t)m * 28) ||
-        !H.take(ctx, sc.leaf_tri, 3 * c) || !H.take(ctx, sc.leaf_box, 2 * c) || !H.take(ctx, sc.nodes, 2 * c) ||
+        !H.take(ctx, sc.leaf_tri, 4 * c) || !H.take(ctx, sc.leaf_box, 2 * c) || !H.take(ctx, sc.nodes, 2 * c) ||
         !H.take(ctx, sc.node_box, 2 * c) || !H.take(ctx, sc.left, c) || !H.take(ctx, sc.right, c) || !H.take(ctx, sc.parent, c) ||
         !H.take(ctx, sc.height, c) || !H.take(ctx, sc.morton, c) || !H.take(ctx, sc.sorted_idx, c) || !H.take(ctx, sc.bounds, 8) ||
         !H.take(ctx, sc.lights, light_src.size()) || !H.take(ctx, sc.light_src, light_src.size())) return 1;

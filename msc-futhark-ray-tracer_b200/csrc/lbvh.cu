@@ -342,16 +342,18 @@ k_rs_onesweep(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__
 __global__ void k_gather_leaves(const float *__restrict__ tris, const uint32_t *__restrict__ tri_mats,
                                 const float4 *__restrict__ box_c, const float4 *__restrict__ box_h,
                                 const uint32_t *__restrict__ sorted_idx, int n,
-                                float4 *__restrict__ leaf_tri /* [n][3] */, float4 *__restrict__ leaf_box /* [n][2] */) {
+                                float4 *__restrict__ leaf_tri /* [n][4] */, float4 *__restrict__ leaf_box /* [n][2] */) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t s = sorted_idx[i];
     const float *t = tris + 9ll * s;
     V3 a = v3(t[0], t[1], t[2]), b = v3(t[3], t[4], t[5]), c = v3(t[6], t[7], t[8]);
     V3 e1 = b - a, e2 = c - a;                                          /* shapes.fut:69-70 */
-    leaf_tri[3ll * i + 0] = make_float4(a.x, a.y, a.z, __uint_as_float(tri_mats[s]));
-    leaf_tri[3ll * i + 1] = make_float4(e1.x, e1.y, e1.z, __uint_as_float(s));
-    leaf_tri[3ll * i + 2] = make_float4(e2.x, e2.y, e2.z, 0.0f);
+    V3 nc = cross(e1, e2);                                              /* shapes.fut:71: ray independent, stored once */
+    leaf_tri[4ll * i + 0] = make_float4(a.x, a.y, a.z, __uint_as_float(tri_mats[s]));
+    leaf_tri[4ll * i + 1] = make_float4(nc.x, nc.y, nc.z, __uint_as_float(s));
+    leaf_tri[4ll * i + 2] = make_float4(e1.x, e1.y, e1.z, 0.0f);
+    leaf_tri[4ll * i + 3] = make_float4(e2.x, e2.y, e2.z, 0.0f);
     leaf_box[2ll * i + 0] = box_c[s];
     leaf_box[2ll * i + 1] = box_h[s];
 }

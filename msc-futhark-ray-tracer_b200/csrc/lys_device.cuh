@@ -129,6 +129,26 @@ LYS_D bool tri_test(V3 o, V3 d, V3 a, V3 e1, V3 e2, float tmax, float &t_out, V3
     t_out = t; ncross = n;
     return true;
 }
+/* The same test split for the traversal loop: the plane part on (a, n = e1 x e2 precomputed by the build with the
+ * same three products and differences), then the barycentric part on the edges.  Same values, same boolean. */
+LYS_D bool tri_plane_test(V3 o, V3 d, V3 a, V3 n, float tmax, float &t_out, float &inv_out, V3 &s_out) {
+    float det = -(dot(n, d));
+    if (det > -0.00001f && det < 0.00001f) return false;                                /* approx_zero common.fut:35 */
+    V3 s = o - a;
+    float dn = dot(n, s);
+    if (!((dn > 0.0f && det > 0.0f) || (dn < 0.0f && det < 0.0f))) return false;        /* t > 0 impossible */
+    float inv = 1.0f / det;
+    float t = inv * dn;
+    if (!(t < tmax && t > 0.0f)) return false;                                          /* in_bounds :64 */
+    t_out = t; inv_out = inv; s_out = s;
+    return true;
+}
+LYS_D bool tri_uv_test(V3 d, V3 s, float inv, V3 e1, V3 e2) {
+    V3 m = cross(s, d);
+    float u = inv * dot(m, e2);
+    float v = inv * (-(dot(m, e1)));
+    return u >= 0.0f && v >= 0.0f && u + v <= 1.0f;
+}
 /* mkray_adjust_acne (shapes.fut:41-46) */
 LYS_D void ray_from_hit(V3 pos, V3 n, V3 wi, V3 &o, V3 &d) {
     o = pos + 0.001f * same_side(wi, n);
@@ -249,6 +269,16 @@ LYS_DN DirSample sample_refraction(V3 wo, const Mat1 &m, uint32_t &rng) {
     else { float ctt = sqrtf(1.0f - s2t); wi = (-eta) * wo + (eta * ci - ctt) * n; }
     s.wi = wi; s.bsdf = 1.0f / lys_fabsf(wi.z); s.kind = PDF_DELTA; s.pdf = 0.0f;
     return s;
+}
+/* The draws of uber_sample_dir (:365-370) that come before its branch: metal (:352-355), else Fresnel coin (:338-344).
+ * Returns true for the reflection branch; rng is left where the chosen sampler starts. */
+LYS_D bool bsdf_choose(V3 wo, const Mat1 &m, uint32_t &rng, bool &metal) {
+    float p = rng_unit(rng);
+    metal = p < m.metalness;
+    if (metal) return true;
+    if (wo.z <= 0.0f) return false;
+    float r = schlick(wo, m); float q = rng_unit(rng);
+    return q < r;
 }
 /* sample_dir (:406-410) = uber_sample_dir (:365-370) in the local frame */
 LYS_DN DirSample sample_bsdf(V3 wo_world, const Onb &onb, const Mat1 &m, uint32_t &rng) {

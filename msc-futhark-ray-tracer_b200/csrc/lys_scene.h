@@ -4,7 +4,8 @@
  *   tris      [n][9]  f32   input triangles as uploaded (src/scene.fut:26-35)
  *   tri_mats  [n]     u32
  *   mats      [m][28] f32   material rows (src/scene.fut:37-53)
- *   leaf_tri  [n][3]  float4  sorted leaves: (a.xyz | mat_ix), (e1.xyz | source index), (e2.xyz | 0)
+ *   leaf_tri  [n][4]  float4  sorted leaves, 64 B: (a.xyz | mat_ix), (e1 x e2 | source index) = the plane test's sector,
+ *                             then (e1.xyz | 0), (e2.xyz | 0) for the barycentric test
  *   leaf_box  [n][2]  float4  sorted leaf boxes (center | half_dims)
  *   nodes     [n-1][2] float4 traversal nodes: (min.xyz | left), (max.xyz | right); one 32-byte sector
  *   node_box  [n-1][2] float4 node boxes as the reference stores them (center | half_dims)

@@ -28,63 +28,77 @@ namespace lys {
  * walk that pushes the right child while descending left takes exactly the same decisions in the same
  * order, so hits, ties (strict t < tmax, shapes.fut:64) and culling are identical. */
 struct RayInv { V3 o, d, inv; };
-LYS_D bool slab_test(const RayInv &r, float4 lo, float4 hi, float tmax) {               /* hit_aabb shapes.fut:114-135 */
+/* hit_aabb (shapes.fut:114-135).  The reference leaves after the first axis with tmax <= tmin; tmin only grows and
+ * tmax only shrinks from axis to axis (fmaxf/fminf drop NaN operands), so an axis that fails keeps failing and the
+ * single test after the third axis gives the same boolean.  No per-axis branch: the lanes of a warp stay together. */
+LYS_D bool slab_test(const RayInv &r, float4 lo, float4 hi, float tmax) {
     float tmin = 0.0f;
     {
         float t0 = (lo.x - r.o.x) * r.inv.x, t1 = (hi.x - r.o.x) * r.inv.x;
         if (r.inv.x < 0.0f) { float s = t0; t0 = t1; t1 = s; }
         t1 = t1 * (1.0f + 0.001f);
         tmin = fmaxf(t0, tmin); tmax = fminf(t1, tmax);
-        if (tmax <= tmin) return false;
     }
     {
         float t0 = (lo.y - r.o.y) * r.inv.y, t1 = (hi.y - r.o.y) * r.inv.y;
         if (r.inv.y < 0.0f) { float s = t0; t0 = t1; t1 = s; }
         t1 = t1 * (1.0f + 0.001f);
         tmin = fmaxf(t0, tmin); tmax = fminf(t1, tmax);
-        if (tmax <= tmin) return false;
     }
     {
         float t0 = (lo.z - r.o.z) * r.inv.z, t1 = (hi.z - r.o.z) * r.inv.z;
         if (r.inv.z < 0.0f) { float s = t0; t0 = t1; t1 = s; }
         t1 = t1 * (1.0f + 0.001f);
         tmin = fmaxf(t0, tmin); tmax = fminf(t1, tmax);
-        if (tmax <= tmin) return false;
     }
-    return true;
+    return !(tmax <= tmin);
 }
+/* hit_triangle (shapes.fut:66-86) against sorted leaf `leaf`: the plane part needs only (a, n = e1 x e2), one 32-byte
+ * sector; the edges are fetched only by the lanes whose t lies in (0, tmax). */
 LYS_D bool leaf_test(const RayInv &r, const float4 *__restrict__ leaf_tri, int leaf, float tmax, float &t) {
-    float4 q0 = __ldg(leaf_tri + 3ll * leaf), q1 = __ldg(leaf_tri + 3ll * leaf + 1), q2 = __ldg(leaf_tri + 3ll * leaf + 2);
-    V3 nc;
-    return tri_test(r.o, r.d, v3(q0.x, q0.y, q0.z), v3(q1.x, q1.y, q1.z), v3(q2.x, q2.y, q2.z), tmax, t, nc);
+    const float4 *q = leaf_tri + 4ll * leaf;
+    float4 q0 = __ldg(q), q1 = __ldg(q + 1);
+    float inv; V3 s;
+    if (!tri_plane_test(r.o, r.d, v3(q0.x, q0.y, q0.z), v3(q1.x, q1.y, q1.z), tmax, t, inv, s)) return false;
+    float4 q2 = __ldg(q + 2), q3 = __ldg(q + 3);
+    return tri_uv_test(r.d, s, inv, v3(q2.x, q2.y, q2.z), v3(q3.x, q3.y, q3.z));
 }
-template <bool ANY>
-LYS_D int traverse(const float4 *__restrict__ nodes, const float4 *__restrict__ leaf_tri, int n_nodes,
+/* One loop iteration = NB box stages, then one triangle stage, then a warp vote.  A lane takes part in a stage if its
+ * next visit has that type, so a node whose left child is a leaf is box-tested and the leaf triangle-tested in the
+ * same iteration, and the lanes of a warp meet in few, well filled stages (model: tools/simt_model.py; a loop in which
+ * each lane does ONE visit per iteration issues the triangle block for 4-5 lanes in every second iteration, a
+ * while-while loop makes the lanes at leaves wait for the slowest descent).  The vote keeps the warp converged at the
+ * loop head -- without it the compiler threads "still at an internal node" back into the box stage, i.e. builds
+ * while-while.  ALL 32 LANES OF A WARP MUST CALL THIS TOGETHER; lanes without a ray pass active = false.
+ * stack[0] holds the end marker: popping needs no empty check.  Visits, their order and every comparison are those
+ * of the reference's walk (see above), only the interleaving between lanes differs. */
+#define TRAV_DONE ((int)0x80000000)
+template <bool ANY, int NB>
+LYS_D int traverse(const float4 *__restrict__ nodes, const float4 *__restrict__ leaf_tri, int n_nodes, bool active,
                    V3 o, V3 d, float tmax, float &t_hit) {
     RayInv r; r.o = o; r.d = d; r.inv = v3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
-    int stack[TRAV_STACK];
-    int sp = 0;
+    int stack[TRAV_STACK + 1];
     int closest = -1;
-    if (n_nodes <= 0) return -1;
-    int cur = 0;                    /* internal node to enter, or a leaf pointer (< 0) */
-    while (true) {
-        if (cur >= 0) {
-            float4 lo = __ldg(nodes + 2ll * cur), hi = __ldg(nodes + 2ll * cur + 1);
-            if (slab_test(r, lo, hi, tmax)) {
-                stack[sp++] = __float_as_int(hi.w);       /* right child waits */
-                cur = __float_as_int(lo.w);               /* left child first */
-                continue;
-            }
-        } else {
-            float t;
-            if (leaf_test(r, leaf_tri, ~cur, tmax, t)) {
-                closest = ~cur; tmax = t;
-                if (ANY) { t_hit = t; return closest; }
+    stack[0] = TRAV_DONE;
+    int sp = 1;
+    int cur = (active && n_nodes > 0) ? 0 : TRAV_DONE;   /* internal node to enter (>= 0), leaf pointer (~leaf) or TRAV_DONE */
+    do {
+#pragma unroll
+        for (int k = 0; k < NB; k++) {
+            if (cur >= 0) {
+                float4 lo = __ldg(nodes + 2ll * cur), hi = __ldg(nodes + 2ll * cur + 1);
+                if (slab_test(r, lo, hi, tmax)) {
+                    stack[sp++] = __float_as_int(hi.w);       /* right child waits */
+                    cur = __float_as_int(lo.w);               /* left child first */
+                } else cur = stack[--sp];
             }
         }
-        if (sp == 0) break;
-        cur = stack[--sp];
-    }
+        if ((unsigned)cur > (unsigned)TRAV_DONE) {            /* a leaf pointer */
+            float t;
+            if (leaf_test(r, leaf_tri, ~cur, tmax, t)) { closest = ~cur; tmax = t; }
+            cur = (ANY && closest >= 0) ? TRAV_DONE : stack[--sp];      /* any_hit stops at the first hit (bvh.fut:152) */
+        }
+    } while (__any_sync(0xffffffffu, cur != TRAV_DONE));
     t_hit = tmax;
     return closest;
 }
@@ -191,10 +205,11 @@ LYS_D bool shade_prologue(const SceneDev &sc, const PassBuffers &b, int bounce, 
     v.rng = __float_as_uint(rd4.w);
     v.leaf = b.hit[i];
     if (v.leaf < 0) return false;
-    float4 q0 = __ldg(sc.leaf_tri + 3ll * v.leaf), q1 = __ldg(sc.leaf_tri + 3ll * v.leaf + 1), q2 = __ldg(sc.leaf_tri + 3ll * v.leaf + 2);
+    const float4 *lq = sc.leaf_tri + 4ll * v.leaf;
+    float4 q0 = __ldg(lq), q1 = __ldg(lq + 1);
     v.mrow = sc.mats + 28ll * (int)__float_as_uint(q0.w);
-    V3 nc;
-    (void)tri_test(v.o, v.d, v3(q0.x, q0.y, q0.z), v3(q1.x, q1.y, q1.z), v3(q2.x, q2.y, q2.z), FLT_MAX, v.t, nc);   /* bvh.fut:143-145 */
+    V3 nc = v3(q1.x, q1.y, q1.z);                                          /* e1 x e2, stored by the build */
+    { float inv; V3 s; (void)tri_plane_test(v.o, v.d, v3(q0.x, q0.y, q0.z), nc, FLT_MAX, v.t, inv, s); }   /* bvh.fut:143-145: t of the winner */
     v.pos = v.o + v.t * v.d;
     v.n = normalise(nc);
     rng_advance(v.rng);                                                   /* integrator.fut:48 */
@@ -240,9 +255,8 @@ LYS_D void shade_light_sample(const VertexCtx &v, const LightD &l, float &cL, fl
         flags |= 1;
     }
 }
-/* BSDF sample towards the same light (direct.fut:83-102); advances v.rng */
-LYS_D void shade_bsdf_light_sample(VertexCtx &v, const LightD &l, float &cB, float4 &rec_d2, int &flags) {
-    DirSample s = sample_bsdf(v.wo, v.onb, v.m, v.rng);
+/* BSDF sample towards the same light (direct.fut:83-102) for an already drawn sample s (world space) */
+LYS_D void shade_bsdf_light_use(const VertexCtx &v, const LightD &l, const DirSample &s, float &cB, float4 &rec_d2, int &flags) {
     V3 bo, bd; ray_from_hit(v.pos, v.n, s.wi, bo, bd);
     float tl; V3 ncl;
     if (tri_test(bo, bd, l.a, l.e1, l.e2, FLT_MAX, tl, ncl)) {
@@ -260,16 +274,20 @@ LYS_D void shade_bsdf_light_sample(VertexCtx &v, const LightD &l, float &cB, flo
         }
     }
 }
+/* the same with the sample drawn here; advances v.rng */
+LYS_D void shade_bsdf_light_sample(VertexCtx &v, const LightD &l, float &cB, float4 &rec_d2, int &flags) {
+    DirSample s = sample_bsdf(v.wo, v.onb, v.m, v.rng);
+    shade_bsdf_light_use(v, l, s, cB, rec_d2, flags);
+}
 /* emission, distance, shadow record, continuation + roulette (integrator.fut:51-75); returns true if the path lives on */
-LYS_D bool shade_finish(const FrameParams &fp, const PassBuffers &b, int bounce, int i, VertexCtx &v, float cL, float cB, int flags,
-                        float4 &next_o, float4 &next_d, float &next_dist) {
+LYS_D bool shade_finish_use(const FrameParams &fp, const PassBuffers &b, int bounce, int i, VertexCtx &v, const DirSample &s, float cL, float cB, int flags,
+                            float4 &next_o, float4 &next_d, float &next_dist) {
     float em = (bounce == 0) ? spectrum_lookup12(v.wavelen, v.mrow + 16) : 0.0f;      /* integrator.fut:51-53 */
     const float dist = b.dist[bounce & 1][i] + v.t;                                     /* :54 */
     next_dist = dist;
     V3 so = v.pos + 0.001f * v.n;       /* mkray_adjust_acne with dot(w, n) > 0: same_side = 1 * n */
     b.sh_o[i] = make_float4(so.x, so.y, so.z, __int_as_float(flags));
     b.sh_c[i] = make_float4(cL, cB, em, dist);
-    DirSample s = sample_bsdf(v.wo, v.onb, v.m, v.rng);
     float pdf = (s.kind == PDF_IMPOSSIBLE) ? 0.0f : ((s.kind == PDF_DELTA) ? 1.0f : s.pdf);
     float cosf = lys_fabsf(dot(v.n, s.wi));
     float p_term = 1.0f - s.bsdf * cosf / pdf;
@@ -281,6 +299,11 @@ LYS_D bool shade_finish(const FrameParams &fp, const PassBuffers &b, int bounce,
         return true;
     }
     return false;
+}
+LYS_D bool shade_finish(const FrameParams &fp, const PassBuffers &b, int bounce, int i, VertexCtx &v, float cL, float cB, int flags,
+                        float4 &next_o, float4 &next_d, float &next_dist) {
+    DirSample s = sample_bsdf(v.wo, v.onb, v.m, v.rng);       /* integrator.fut:56 */
+    return shade_finish_use(fp, b, bounce, i, v, s, cL, cB, flags, next_o, next_d, next_dist);
 }
 LYS_D void shade_miss(const FrameParams &fp, const PassBuffers &b, int i, const VertexCtx &v) {
     float amb = spectrum_lookup12(v.wavelen, fp.ambience);                 /* integrator.fut:76 */
@@ -303,16 +326,57 @@ LYS_D void shade_compact(const PassBuffers &b, int bounce, bool alive, int pid, 
     if (lane == 0 && (vsum | ssum)) { atomicAdd(&b.stats[0], (unsigned long long)vsum); atomicAdd(&b.stats[2], (unsigned long long)ssum); }
 }
 
-/* monolithic: everything for one vertex in one thread.  The kernel's code is larger than the instruction cache, so
- * the warps of a CTA are kept in lockstep with block barriers between the phases (block-uniform loop): they then
- * fetch the same code lines together instead of each warp missing on its own. */
-#ifndef SHADE_THREADS
-#define SHADE_THREADS 512
-#endif
-#ifndef SHADE_BARRIERS
-#define SHADE_BARRIERS 3
-#endif
-__global__ void __launch_bounds__(SHADE_THREADS, 2048 / SHADE_THREADS / 2) k_shade(SceneDev sc, const __grid_constant__ FrameParams fp, PassBuffers b, int bounce) {
+/* monolithic: everything for one vertex in one thread, with two CTA-level arrangements (profiles/README.md 4.2, 4.5):
+ *  - the kernel's code is larger than the instruction cache, so the warps of a CTA are kept in lockstep with block
+ *    barriers between the phases (block-uniform loop) and fetch the same code lines together;
+ *  - the reflection branch of uber_sample_dir (material.fut:365-370) is taken by a few percent of the vertices of a
+ *    dielectric scene, i.e. by one or two lanes of almost every warp, and costs ~560 instructions (sample_wh,
+ *    Torrance-Sparrow terms).  Both sample_dir calls of a vertex therefore only DECIDE their branch in place
+ *    (bsdf_choose); refraction samples are drawn in place, reflection samples are queued in shared memory and drawn
+ *    after a barrier by the first threads of the CTA, one queue entry per thread (dense warps).  Same inputs, same
+ *    arithmetic, another thread.  The rng state after a reflection sample is its two draws further (:283-286). */
+template <int T>
+struct ShadeShared {
+    float res[6][2 * T];      /* slot k * T + tid: sample k of the thread (in: wo_l, roughness, rng; out: DirSample local) */
+    unsigned short q[2 * T];  /* slots waiting for a reflection sample */
+    int qn;
+};
+template <class SH>
+LYS_D void shade_put_sample(SH &sh, int slot, const DirSample &s) {
+    sh.res[0][slot] = s.wi.x; sh.res[1][slot] = s.wi.y; sh.res[2][slot] = s.wi.z;
+    sh.res[3][slot] = s.bsdf; sh.res[4][slot] = __int_as_float(s.kind); sh.res[5][slot] = s.pdf;
+}
+template <class SH>
+LYS_D DirSample shade_get_sample(const SH &sh, int slot) {
+    DirSample s;
+    s.wi = v3(sh.res[0][slot], sh.res[1][slot], sh.res[2][slot]);
+    s.bsdf = sh.res[3][slot]; s.kind = __float_as_int(sh.res[4][slot]); s.pdf = sh.res[5][slot];
+    return s;
+}
+/* one sample_dir call up to its branch: refraction sample drawn here, reflection sample queued.  Warp-collective. */
+template <class SH>
+LYS_D void shade_draw_or_queue(SH &sh, bool want, int slot, const VertexCtx &v, uint32_t &rng, bool &metal) {
+    bool reflect = false; metal = false;
+    if (want) {
+        reflect = bsdf_choose(v.wo_l, v.m, rng, metal);
+        if (reflect) {
+            sh.res[0][slot] = v.wo_l.x; sh.res[1][slot] = v.wo_l.y; sh.res[2][slot] = v.wo_l.z;
+            sh.res[3][slot] = v.m.roughness; sh.res[4][slot] = __uint_as_float(rng);
+            (void)lcg_next(rng); (void)lcg_next(rng);                 /* u0, u1 of sample_wh */
+        } else shade_put_sample(sh, slot, sample_refraction(v.wo_l, v.m, rng));
+    }
+    const unsigned mask = __ballot_sync(0xffffffffu, reflect);
+    if (mask) {
+        const int lane = threadIdx.x & 31;
+        int base = 0;
+        if (lane == __ffs(mask) - 1) base = atomicAdd(&sh.qn, __popc(mask));
+        base = __shfl_sync(0xffffffffu, base, __ffs(mask) - 1);
+        if (reflect) sh.q[base + __popc(mask & ((1u << lane) - 1u))] = (unsigned short)slot;
+    }
+}
+template <int SHADE_THREADS>
+__global__ void __launch_bounds__(SHADE_THREADS, 2048 / SHADE_THREADS / 2) k_shade(SceneDev sc, const __grid_constant__ FrameParams fp, PassBuffers b, int bounce, int bars) {
+    __shared__ ShadeShared<SHADE_THREADS> sh;
     const int count = b.counts[bounce];
     const int stride = gridDim.x * blockDim.x;
     const int nl = fp.n_scene_lights + ((fp.tx_kind == 0) ? 0 : 8);
@@ -325,29 +389,44 @@ __global__ void __launch_bounds__(SHADE_THREADS, 2048 / SHADE_THREADS / 2) k_sha
         float cL = 0.0f, cB = 0.0f; int flags = 0;
         float4 rec_d1 = make_float4(0.0f, 0.0f, 0.0f, 0.0f), rec_d2 = rec_d1;
         LightD l;
+        if (threadIdx.x == 0) sh.qn = 0;
         if (valid) hit = shade_prologue(sc, b, bounce, i, v);
         const bool lit = hit && nl > 0;
-#if SHADE_BARRIERS >= 1
-        __syncthreads();
-#endif
+        if (bars & 1) __syncthreads();                                    /* lockstep only (instruction cache) */
         if (lit) shade_pick_light(sc, fp, b, v, nl, l);
         if (lit) shade_light_sample(v, l, cL, rec_d1, flags);
-#if SHADE_BARRIERS >= 2
+        if (bars & 2) __syncthreads();                                    /* lockstep only */
+        /* both sample_dir calls of the vertex: the MIS sample (direct.fut:83) and the continuation (integrator.fut:56) */
+        bool metal1, metal2;
+        shade_draw_or_queue(sh, lit, threadIdx.x, v, v.rng, metal1);
+        shade_draw_or_queue(sh, hit, SHADE_THREADS + threadIdx.x, v, v.rng, metal2);
         __syncthreads();
-#endif
-        if (lit) shade_bsdf_light_sample(v, l, cB, rec_d2, flags);
-#if SHADE_BARRIERS >= 3
+        for (int j = threadIdx.x; j < sh.qn; j += SHADE_THREADS) {
+            const int slot = sh.q[j];
+            Mat1 m; m.color = 0.0f; m.roughness = sh.res[3][slot]; m.metalness = 0.0f; m.ref_ix = 0.0f; m.opacity = 0.0f;
+            uint32_t rng = __float_as_uint(sh.res[4][slot]);
+            shade_put_sample(sh, slot, sample_reflection(v3(sh.res[0][slot], sh.res[1][slot], sh.res[2][slot]), m, rng));
+        }
         __syncthreads();
-#endif
+        if (lit) {
+            DirSample s = shade_get_sample(sh, threadIdx.x);
+            if (metal1) s.bsdf = v.m.color * s.bsdf;                      /* metal :352-355 */
+            s.wi = to_world(v.onb, s.wi);
+            shade_bsdf_light_use(v, l, s, cB, rec_d2, flags);
+        }
         if (valid) {
             if (hit) {
+                DirSample s = shade_get_sample(sh, SHADE_THREADS + threadIdx.x);
+                if (metal2) s.bsdf = v.m.color * s.bsdf;
+                s.wi = to_world(v.onb, s.wi);
                 b.sh_d1[i] = rec_d1; b.sh_d2[i] = rec_d2;
-                alive = shade_finish(fp, b, bounce, i, v, cL, cB, flags, next_o, next_d, next_dist);
+                alive = shade_finish_use(fp, b, bounce, i, v, s, cL, cB, flags, next_o, next_d, next_dist);
                 n_vert = 1; n_shadow = (flags & 1) + ((flags >> 1) & 1);
             } else shade_miss(fp, b, i, v);
             pid = v.pid;
         }
         shade_compact(b, bounce, alive, pid, next_o, next_d, next_dist, n_vert, n_shadow);
+        __syncthreads();                                                  /* sh is reused by the next iteration */
     }
 }
 /* phase kernels: light sample */
@@ -548,28 +627,46 @@ __global__ void __launch_bounds__(128) k_trace_refill(SceneDev sc, const __grid_
 /* The default variant: one item per thread and grid-stride iteration, plain traverse<> loops.  Measured on B200
  * (CornellBox 1080p) it beats the refill variant above, whose every refill stalls the warp on dependent
  * queue -> ray loads; the refill kernel is kept selectable (LYS_TRACE_MODE=1) and is parity-tested too. */
+template <int NB>
 __global__ void __launch_bounds__(128) k_trace(SceneDev sc, const __grid_constant__ FrameParams fp, PassBuffers b, int bounce) {
     const int n_ext = (bounce + 1 < fp.path_len) ? b.counts[bounce + 1] : 0;
     const int n_con = (bounce >= 0) ? b.counts[bounce] : 0;
     const int total = n_ext + n_con;
     const int stride = gridDim.x * blockDim.x;
     const int n_nodes = (int)sc.n_tris - 1;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-        if (i < n_ext) {
-            float4 ro = b.ray_o[(bounce + 1) & 1][i], rd = b.ray_d[(bounce + 1) & 1][i];
+    const int lane = threadIdx.x & 31;
+    /* warp-uniform loop (traverse<> votes): a warp owns 32 consecutive items; only the warp that straddles n_ext mixes kinds */
+    for (int i0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31); i0 < total; i0 += stride) {
+        const int i = i0 + lane;
+        const bool is_ext = i < n_ext, is_con = !is_ext && i < total;
+        if (i0 < n_ext) {
+            float4 ro = make_float4(0.0f, 0.0f, 0.0f, 0.0f), rd = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
+            if (is_ext) { ro = b.ray_o[(bounce + 1) & 1][i]; rd = b.ray_d[(bounce + 1) & 1][i]; }
             float t;
-            b.hit[i] = traverse<false>(sc.nodes, sc.leaf_tri, n_nodes, v3(ro.x, ro.y, ro.z), v3(rd.x, rd.y, rd.z), FLT_MAX, t);
-        } else {
+            int h = traverse<false, NB>(sc.nodes, sc.leaf_tri, n_nodes, is_ext, v3(ro.x, ro.y, ro.z), v3(rd.x, rd.y, rd.z), FLT_MAX, t);
+            if (is_ext) b.hit[i] = h;
+        }
+        if (i0 + 31 >= n_ext) {
             const int slot = i - n_ext;
-            float4 ro = b.sh_o[slot], rc = b.sh_c[slot];
+            float4 ro = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(4)), rc = ro;
+            if (is_con) { ro = b.sh_o[slot]; rc = b.sh_c[slot]; }
             const int flags = __float_as_int(ro.w);
             float L = 0.0f, B = 0.0f, t;
             V3 o = v3(ro.x, ro.y, ro.z);
-            if (!(flags & 4)) {
-                if (flags & 1) { float4 d1 = b.sh_d1[slot]; if (traverse<true>(sc.nodes, sc.leaf_tri, n_nodes, o, v3(d1.x, d1.y, d1.z), d1.w, t) < 0) L = rc.x; }
-                if (flags & 2) { float4 d2 = b.sh_d2[slot]; if (traverse<true>(sc.nodes, sc.leaf_tri, n_nodes, o, v3(d2.x, d2.y, d2.z), d2.w, t) < 0) B = rc.y; }
+            const bool need1 = is_con && !(flags & 4) && (flags & 1), need2 = is_con && !(flags & 4) && (flags & 2);
+            if (__any_sync(0xffffffffu, need1)) {
+                float4 d1 = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
+                if (need1) d1 = b.sh_d1[slot];
+                int h = traverse<true, NB>(sc.nodes, sc.leaf_tri, n_nodes, need1, o, v3(d1.x, d1.y, d1.z), d1.w, t);
+                if (need1 && h < 0) L = rc.x;
             }
-            connect_finish(fp, b, bounce, slot, flags, L, B, rc.z, rc.w, rc.z);
+            if (__any_sync(0xffffffffu, need2)) {
+                float4 d2 = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
+                if (need2) d2 = b.sh_d2[slot];
+                int h = traverse<true, NB>(sc.nodes, sc.leaf_tri, n_nodes, need2, o, v3(d2.x, d2.y, d2.z), d2.w, t);
+                if (need2 && h < 0) B = rc.y;
+            }
+            if (is_con) connect_finish(fp, b, bounce, slot, flags, L, B, rc.z, rc.w, rc.z);
         }
     }
 }
@@ -648,23 +745,26 @@ __global__ void __launch_bounds__(256) k_render(const float *__restrict__ img, i
 /* ------------------------------------------------------------------ probes / tools */
 __global__ void k_primary_probe(SceneDev sc, PassBuffers b, int n, int *leaf, int *src, float *t) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    float4 ro = b.ray_o[0][i], rd = b.ray_d[0][i];
+    const bool act = i < n;                                          /* no early return: traverse<> votes per warp */
+    float4 ro = make_float4(0.0f, 0.0f, 0.0f, 0.0f), rd = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
+    if (act) { ro = b.ray_o[0][i]; rd = b.ray_d[0][i]; }
     float th;
-    int l = traverse<false>(sc.nodes, sc.leaf_tri, (int)sc.n_tris - 1, v3(ro.x, ro.y, ro.z), v3(rd.x, rd.y, rd.z), FLT_MAX, th);
+    int l = traverse<false, 1>(sc.nodes, sc.leaf_tri, (int)sc.n_tris - 1, act, v3(ro.x, ro.y, ro.z), v3(rd.x, rd.y, rd.z), FLT_MAX, th);
+    if (!act) return;
     leaf[i] = l;
-    if (src) src[i] = (l < 0) ? -1 : (int)__float_as_uint(sc.leaf_tri[3ll * l + 1].w);
+    if (src) src[i] = (l < 0) ? -1 : (int)__float_as_uint(sc.leaf_tri[4ll * l + 1].w);
     if (t) t[i] = (l < 0) ? LYS_INF : th;
 }
 __global__ void k_trace_rays(SceneDev sc, const float *__restrict__ rays, const float *__restrict__ tmax, long long n,
                              int *out_leaf, float *out_t, int any) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const float *r = rays + 6 * i;
-    V3 o = v3(r[0], r[1], r[2]), d = v3(r[3], r[4], r[5]);
+    const bool act = i < n;                                          /* no early return: traverse<> votes per warp */
+    V3 o = v3(0.0f, 0.0f, 0.0f), d = v3(1.0f, 1.0f, 1.0f);
+    if (act) { const float *r = rays + 6 * i; o = v3(r[0], r[1], r[2]); d = v3(r[3], r[4], r[5]); }
     float th; int l;
-    if (any) l = traverse<true>(sc.nodes, sc.leaf_tri, (int)sc.n_tris - 1, o, d, tmax[i], th);
-    else l = traverse<false>(sc.nodes, sc.leaf_tri, (int)sc.n_tris - 1, o, d, FLT_MAX, th);
+    if (any) l = traverse<true, 1>(sc.nodes, sc.leaf_tri, (int)sc.n_tris - 1, act, o, d, act ? tmax[i] : 0.0f, th);
+    else l = traverse<false, 1>(sc.nodes, sc.leaf_tri, (int)sc.n_tris - 1, act, o, d, FLT_MAX, th);
+    if (!act) return;
     out_leaf[i] = any ? (l >= 0 ? 1 : 0) : l;
     if (out_t) out_t[i] = (l < 0) ? LYS_INF : th;
 }
@@ -694,7 +794,7 @@ __global__ void k_material_probe(const float *mat28, float wavelen, V3 wo, V3 wi
 static inline int cdiv(long long a, int b) { return (int)((a + b - 1) / b); }
 
 /* persistent grids: SM count x resident CTAs per SM of each kernel (queried once per device) */
-struct GridSizes { int trace = 0, shade = 0, refill = 0, sl = 0, sb = 0, sc = 0; int mode = 0, split_bounces = 0; };
+struct GridSizes { int trace = 0, shade = 0, refill = 0, sl = 0, sb = 0, sc = 0; int mode = 0, split_bounces = 0, nb = 2, bars = 0, shade_threads = 256; };
 static GridSizes grid_sizes() {
     static GridSizes g[64];
     int dev = 0; cudaGetDevice(&dev);
@@ -702,18 +802,31 @@ static GridSizes grid_sizes() {
     if (!g[dev].trace) {
         int sms = 148, bt = 8, bs = 4;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bt, k_trace, 128, 0);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bs, k_shade, SHADE_THREADS, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bt, k_trace<2>, 128, 0);
+        const char *sth = getenv("LYS_SHADE_THREADS"); if (sth && (atoi(sth) == 512 || atoi(sth) == 128)) g[dev].shade_threads = atoi(sth);
+        if (g[dev].shade_threads == 256) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bs, k_shade<256>, 256, 0);
+        else if (g[dev].shade_threads == 128) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bs, k_shade<128>, 128, 0);
+        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bs, k_shade<512>, 512, 0);
         int br = 8; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&br, k_trace_refill, 128, 0);
         g[dev].trace = sms * (bt > 0 ? bt : 1); g[dev].shade = sms * (bs > 0 ? bs : 1); g[dev].refill = sms * (br > 0 ? br : 1);
+        /* experiment knobs: persistent grids as a fraction of the resident maximum (co-residency of kernels of different streams) */
+        const char *gt = getenv("LYS_TRACE_GRID_PCT"); if (gt && atoi(gt) > 0) g[dev].trace = max(sms, g[dev].trace * atoi(gt) / 100);
+        const char *gsh = getenv("LYS_SHADE_GRID_PCT"); if (gsh && atoi(gsh) > 0) g[dev].shade = max(sms, g[dev].shade * atoi(gsh) / 100);
         const char *e = getenv("LYS_TRACE_MODE"); g[dev].mode = (e && atoi(e) == 1) ? 1 : 0;
+        const char *nb = getenv("LYS_TRACE_NB"); g[dev].nb = (nb && atoi(nb) == 1) ? 1 : 2;      /* box stages per loop iteration */
         int b1 = 8, b2 = 8, b3 = 8;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, k_shade_light, 128, 0); cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b2, k_shade_bsdf, 128, 0);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b3, k_shade_cont, 128, 0);
         g[dev].sl = sms * (b1 > 0 ? b1 : 1); g[dev].sb = sms * (b2 > 0 ? b2 : 1); g[dev].sc = sms * (b3 > 0 ? b3 : 1);
+        const char *sbar = getenv("LYS_SHADE_BARS"); if (sbar) g[dev].bars = atoi(sbar) & 3;     /* optional lockstep barriers of k_shade */
         const char *sp = getenv("LYS_SHADE_SPLIT"); if (sp) g[dev].split_bounces = atoi(sp);     /* phase kernels for bounces < this */
     }
     return g[dev];
+}
+static void launch_trace(const GridSizes &gs, int grid, const SceneDev &sc, const FrameParams &fp, PassBuffers &bufs, int bounce, cudaStream_t stream) {
+    if (gs.mode) k_trace_refill<<<grid, 128, 0, stream>>>(sc, fp, bufs, bounce);
+    else if (gs.nb == 1) k_trace<1><<<grid, 128, 0, stream>>>(sc, fp, bufs, bounce);
+    else k_trace<2><<<grid, 128, 0, stream>>>(sc, fp, bufs, bounce);
 }
 cudaError_t run_sample_pass(const SceneDev &sc, const FrameParams &fp, PassBuffers &bufs, cudaStream_t stream, uint64_t *launches, LaunchTimer *timer) {
     const int n = fp.n_local;
@@ -721,11 +834,11 @@ cudaError_t run_sample_pass(const SceneDev &sc, const FrameParams &fp, PassBuffe
     uint64_t nl = 0;
     LaunchTimer none; LaunchTimer &tm = timer ? *timer : none;
     const GridSizes gs = grid_sizes();
-    const int g_trace = min(gs.mode ? gs.refill : gs.trace, cdiv(2ll * n, 128)), g_shade = min(gs.shade, cdiv(n, SHADE_THREADS));
+    const int g_trace = min(gs.mode ? gs.refill : gs.trace, cdiv(2ll * n, 128)), g_shade = min(gs.shade, cdiv(n, gs.shade_threads));
     tm.begin(0, stream); k_generate<<<cdiv(n, 256), 256, 0, stream>>>(fp, bufs); tm.end(stream); nl++;
     tm.cur_bounce = -1;
     tm.begin(1, stream);
-    if (gs.mode) k_trace_refill<<<g_trace, 128, 0, stream>>>(sc, fp, bufs, -1); else k_trace<<<g_trace, 128, 0, stream>>>(sc, fp, bufs, -1);
+    launch_trace(gs, g_trace, sc, fp, bufs, -1, stream);
     tm.end(stream); nl++;
     for (int bnc = 0; bnc < fp.path_len; bnc++) {
         tm.cur_bounce = bnc;
@@ -737,10 +850,12 @@ cudaError_t run_sample_pass(const SceneDev &sc, const FrameParams &fp, PassBuffe
                 k_shade_bsdf<<<min(gs.sb, cdiv(n, 128)), 128, 0, stream>>>(sc, fp, bufs, bnc); nl += 2;
             }
             k_shade_cont<<<min(gs.sc, cdiv(n, 128)), 128, 0, stream>>>(sc, fp, bufs, bnc, nlights > 0 ? 1 : 0);
-        } else k_shade<<<g_shade, SHADE_THREADS, 0, stream>>>(sc, fp, bufs, bnc);
+        } else if (gs.shade_threads == 256) k_shade<256><<<g_shade, 256, 0, stream>>>(sc, fp, bufs, bnc, gs.bars);
+        else if (gs.shade_threads == 128) k_shade<128><<<g_shade, 128, 0, stream>>>(sc, fp, bufs, bnc, gs.bars);
+        else k_shade<512><<<g_shade, 512, 0, stream>>>(sc, fp, bufs, bnc, gs.bars);
         tm.end(stream); nl++;
         tm.begin(1, stream);
-        if (gs.mode) k_trace_refill<<<g_trace, 128, 0, stream>>>(sc, fp, bufs, bnc); else k_trace<<<g_trace, 128, 0, stream>>>(sc, fp, bufs, bnc);
+        launch_trace(gs, g_trace, sc, fp, bufs, bnc, stream);
         tm.end(stream); nl++;
     }
     if (launches) *launches += nl;

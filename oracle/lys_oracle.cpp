@@ -800,6 +800,8 @@ float direct_radiance(rnge &rng, vec3 wo, const interaction &i, const light_list
 
 /* ------------------------------------------------------------------ integrator.fut */
 struct path_vertex { float distance, radiance; };
+static thread_local float *t_ray_dump = nullptr;      /* divergence studies: [MAX_PATH_LEN][6] rays of the current path */
+static thread_local int32_t *t_ray_dump_n = nullptr;
 void path_trace(ray r, float wavelen, const scene_t &scene, const light_list &lights, const spectrum &ambience_s,
                 rnge rng, path_vertex *path) {                                 /* :27-76 */
     const float tmax = F32_HIGHEST;
@@ -809,6 +811,7 @@ void path_trace(ray r, float wavelen, const scene_t &scene, const light_list &li
     t_counters.paths++;
     while (should_continue && i < g_path_len) {
         interaction inter;
+        if (t_ray_dump) { float *p = t_ray_dump + 6 * i; p[0] = r.origin.x; p[1] = r.origin.y; p[2] = r.origin.z; p[3] = r.dir.x; p[4] = r.dir.y; p[5] = r.dir.z; *t_ray_dump_n = i + 1; }
         if (closest_interaction(tmax, r, wavelen, scene, inter)) {
             t_counters.vertices++;
             advance_rng(rng);                                                  /* :48 */
@@ -1211,6 +1214,47 @@ void orc_closest_hits_steps(const orc_state *s, const float *rays, int64_t n, in
         uint64_t b0 = t_counters.box_tests, t0 = t_counters.tri_tests;
         trav_hit th; (void)bvh_closest_hit(F32_HIGHEST, r, s->scene->objs, th);
         box_tests[k] = (int32_t)(t_counters.box_tests - b0); tri_tests[k] = (int32_t)(t_counters.tri_tests - t0);
+    }
+}
+/* the closest-hit rays of every path of the state's NEXT pass: rays [gh][gw][MAX_PATH_LEN][6], n_rays [gh][gw] */
+void orc_probe_path_rays(const orc_state *s, float *rays, int32_t *n_rays) {
+    uint32_t gw, gh; grid_dims(*s, gw, gh);
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int64_t i = 0; i < (int64_t)gh; i++)
+        for (int64_t j = 0; j < (int64_t)gw; j++) {
+            int32_t ix = (int32_t)(i * (int64_t)gw + j);
+            rnge r = s->rng ^ rng_hash(ix);
+            pixel_out px;
+            n_rays[ix] = 0;
+            t_ray_dump = rays + (size_t)ix * MAX_PATH_LEN * 6; t_ray_dump_n = n_rays + ix;
+            sample_pixel(*s->scene, s->cam, s->ambience, (float)gw, (float)gh, (uint32_t)j, (uint32_t)i, r, px);
+            t_ray_dump = nullptr; t_ray_dump_n = nullptr;
+        }
+}
+/* per-ray visit pattern of the closest-hit walk in left-first order: 0 = box test failed, 1 = box test passed,
+ * 2 = triangle test missed, 3 = triangle test hit (closest updated); at most max_steps entries per ray, len = true length */
+void orc_closest_hits_pattern(const orc_state *s, const float *rays, int64_t n, int32_t max_steps, uint8_t *pattern, int32_t *len) {
+    const bvh_t &bvh = s->scene->objs;
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int64_t k = 0; k < n; k++) {
+        ray r = {{rays[6 * k], rays[6 * k + 1], rays[6 * k + 2]}, {rays[6 * k + 3], rays[6 * k + 4], rays[6 * k + 5]}};
+        uint8_t *pat = pattern + (size_t)k * max_steps; int32_t m = 0;
+        float tmax = F32_HIGHEST;
+        std::vector<int32_t> stack; int32_t cur = bvh.nodes.empty() ? -1 : 0; bool go = !bvh.nodes.empty();
+        while (go) {                                   /* same decisions as bvh_closest_hit, written as a DFS */
+            uint8_t code;
+            if (!ptr_is_leaf(cur)) {
+                const node &nd = bvh.nodes[cur];
+                if (hit_aabb(tmax, r, nd.box)) { code = 1; stack.push_back(nd.right); cur = nd.left; if (m < max_steps) pat[m] = code; m++; continue; }
+                code = 0;
+            } else {
+                hit h;
+                if (hit_triangle(tmax, r, bvh.leaves[ptr_leaf_ix(cur)].geom, h)) { tmax = h.t; code = 3; } else code = 2;
+            }
+            if (m < max_steps) pat[m] = code; m++;
+            if (stack.empty()) go = false; else { cur = stack.back(); stack.pop_back(); }
+        }
+        len[k] = m;
     }
 }
 void orc_any_hits(const orc_state *s, const float *rays, const float *tmax, int64_t n, int32_t *hit_out) {

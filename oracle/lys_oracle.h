@@ -86,6 +86,9 @@ void orc_closest_hits(const orc_state *s, const float *rays, int64_t n, int32_t 
 /* per-ray work of the closest-hit walk: box tests and triangle tests (divergence studies) */
 void orc_closest_hits_steps(const orc_state *s, const float *rays, int64_t n, int32_t *box_tests, int32_t *tri_tests);
 void orc_any_hits(const orc_state *s, const float *rays, const float *tmax, int64_t n, int32_t *hit);
+/* divergence studies (tools/simt_model.py): closest-hit rays of every path of the NEXT pass, and per-ray visit patterns */
+void orc_probe_path_rays(const orc_state *s, float *rays /* [gh][gw][16][6] */, int32_t *n_rays /* [gh][gw] */);
+void orc_closest_hits_pattern(const orc_state *s, const float *rays, int64_t n, int32_t max_steps, uint8_t *pattern, int32_t *len);
 
 /* Work counters accumulated since the last reset (define the algorithmic-bytes figure). */
 typedef struct {
