@@ -514,6 +514,7 @@ int futhark_entry_init(struct futhark_context *ctx, struct futhark_opaque_state 
         !H.take(ctx, sc.node_box, 2 * c) || !H.take(ctx, sc.left, c) || !H.take(ctx, sc.right, c) || !H.take(ctx, sc.parent, c) ||
         !H.take(ctx, sc.height, c) || !H.take(ctx, sc.morton, c) || !H.take(ctx, sc.sorted_idx, c) || !H.take(ctx, sc.bounds, 8) ||
         !H.take(ctx, sc.lights, light_src.size()) || !H.take(ctx, sc.light_src, light_src.size())) return 1;
+    if (n - 1 <= LYS_OCT_MAX_NODES && n >= 2 && !H.take(ctx, sc.nodes_oct, 16 * c)) return 1;
     CU(ctx, cudaMemcpyAsync(sc.tris, tri_geoms->mem->p, sizeof(float) * 9 * c, cudaMemcpyDeviceToDevice, ctx->stream));
     CU(ctx, cudaMemcpyAsync(sc.tri_mats, tri_mats->mem->p, sizeof(uint32_t) * c, cudaMemcpyDeviceToDevice, ctx->stream));
     CU(ctx, cudaMemcpyAsync(sc.mats, mat_data->mem->p, sizeof(float) * (size_t)m * 28, cudaMemcpyDeviceToDevice, ctx->stream));

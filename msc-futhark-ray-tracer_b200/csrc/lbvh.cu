@@ -546,13 +546,23 @@ __global__ void k_copy_f4(const float4 *__restrict__ in, float4 *__restrict__ ou
 
 /* traversal layout: node i -> (min.xyz | left), (max.xyz | right); min/max as hit_aabb derives them (shapes.fut:120) */
 __global__ void k_pack_nodes(const float4 *__restrict__ A, const int *__restrict__ left, const int *__restrict__ right,
-                             int n_nodes, float4 *__restrict__ nodes) {
+                             int n_nodes, float4 *__restrict__ nodes, float4 *__restrict__ nodes_oct) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_nodes) return;
     float4 c = A[2ll * i], h = A[2ll * i + 1];
     V3 mn = v3(c.x, c.y, c.z) - v3(h.x, h.y, h.z), mx = v3(c.x, c.y, c.z) + v3(h.x, h.y, h.z);
-    nodes[2ll * i + 0] = make_float4(mn.x, mn.y, mn.z, __int_as_float(left[i]));
-    nodes[2ll * i + 1] = make_float4(mx.x, mx.y, mx.z, __int_as_float(right[i]));
+    const float l = __int_as_float(left[i]), r = __int_as_float(right[i]);
+    nodes[2ll * i + 0] = make_float4(mn.x, mn.y, mn.z, l);
+    nodes[2ll * i + 1] = make_float4(mx.x, mx.y, mx.z, r);
+    if (nodes_oct) {
+        /* octant o: axis with 1/dir < 0 enters through max and leaves through min (the swap of shapes.fut:124-126) */
+#pragma unroll
+        for (int o = 0; o < 8; o++) {
+            float4 *q = nodes_oct + 2ll * ((long long)o * n_nodes + i);
+            q[0] = make_float4((o & 4) ? mx.x : mn.x, (o & 2) ? mx.y : mn.y, (o & 1) ? mx.z : mn.z, l);
+            q[1] = make_float4((o & 4) ? mn.x : mx.x, (o & 2) ? mn.y : mx.y, (o & 1) ? mn.z : mx.z, r);
+        }
+    }
 }
 
 /* ------------------------------------------------------------------ host driver */
@@ -612,7 +622,7 @@ cudaError_t build_lbvh(SceneDev &sc, BuildScratch &ws, int refit_mode, cudaStrea
         for (int lv = depth - 1; lv > n_top; lv--) { k_crown_eval<<<G, T, 0, stream>>>(sc.left, sc.right, sc.leaf_box, ws.F, (const CrownPair *)ws.crown_pairs, ws.crown_box, ws.crown_cnt, lv, depth, ws.crown_cap, sc.node_box); nl++; }
         k_crown_top_eval<<<1, 1024, 0, stream>>>(sc.left, sc.right, sc.leaf_box, ws.F, (const CrownPair *)ws.crown_pairs, ws.crown_box, ws.crown_cnt, min(n_top, depth - 1), depth, ws.crown_cap, sc.node_box); nl++;
     }
-    k_pack_nodes<<<cdiv(n_nodes, T), T, 0, stream>>>(sc.node_box, sc.left, sc.right, n_nodes, sc.nodes); nl++;
+    k_pack_nodes<<<cdiv(n_nodes, T), T, 0, stream>>>(sc.node_box, sc.left, sc.right, n_nodes, sc.nodes, sc.nodes_oct); nl++;
     if (launches) *launches += nl;
     return cudaGetLastError();
 }

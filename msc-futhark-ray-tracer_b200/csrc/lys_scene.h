@@ -8,6 +8,9 @@
  *                             then (e1.xyz | 0), (e2.xyz | 0) for the barycentric test
  *   leaf_box  [n][2]  float4  sorted leaf boxes (center | half_dims)
  *   nodes     [n-1][2] float4 traversal nodes: (min.xyz | left), (max.xyz | right); one 32-byte sector
+ *   nodes_oct [8][n-1][2] float4 (scenes up to LYS_OCT_MAX_NODES nodes) the same nodes once per ray-direction octant:
+ *                             (near.xyz | left), (far.xyz | right) with near/far already picked per axis as hit_aabb's
+ *                             swap would (octant bit 2/1/0 = 1/dir.x, .y, .z < 0), so the box test needs no select
  *   node_box  [n-1][2] float4 node boxes as the reference stores them (center | half_dims)
  *   left/right/parent/height [n-1] i32; child encoding: internal i -> i, leaf i -> ~i
  *   morton, sorted_idx [n] u32; bounds [6] f32 (center, half_dims)
@@ -18,6 +21,8 @@
 #include <stdint.h>
 
 namespace lys {
+
+#define LYS_OCT_MAX_NODES (1 << 17)      /* 8 x 4 MB of octant nodes at most: stays L2 resident */
 
 struct LightRec {            /* 32 floats = 128 B, float4-aligned */
     float a[3]; float area;                /* vertex a, triangle area (direct.fut:17-20) */
@@ -32,6 +37,7 @@ struct SceneDev {
     int64_t n_tris = 0, n_mats = 0, n_lights = 0;
     float *tris = nullptr; uint32_t *tri_mats = nullptr; float *mats = nullptr;
     float4 *leaf_tri = nullptr, *leaf_box = nullptr, *nodes = nullptr, *node_box = nullptr;
+    float4 *nodes_oct = nullptr;           /* null for scenes above LYS_OCT_MAX_NODES */
     int *left = nullptr, *right = nullptr, *parent = nullptr, *height = nullptr;
     uint32_t *morton = nullptr, *sorted_idx = nullptr;
     float *bounds = nullptr;

@@ -53,15 +53,25 @@ LYS_D bool slab_test(const RayInv &r, float4 lo, float4 hi, float tmax) {
     }
     return !(tmax <= tmin);
 }
+/* the same test on an octant node (lys_scene.h: near/far picked at build time as the swap above would) */
+LYS_D bool slab_test_oct(const RayInv &r, float4 nr, float4 fr, float tmax) {
+    float tmin = 0.0f;
+    tmin = fmaxf((nr.x - r.o.x) * r.inv.x, tmin); tmax = fminf(((fr.x - r.o.x) * r.inv.x) * (1.0f + 0.001f), tmax);
+    tmin = fmaxf((nr.y - r.o.y) * r.inv.y, tmin); tmax = fminf(((fr.y - r.o.y) * r.inv.y) * (1.0f + 0.001f), tmax);
+    tmin = fmaxf((nr.z - r.o.z) * r.inv.z, tmin); tmax = fminf(((fr.z - r.o.z) * r.inv.z) * (1.0f + 0.001f), tmax);
+    return !(tmax <= tmin);
+}
 /* hit_triangle (shapes.fut:66-86) against sorted leaf `leaf`: the plane part needs only (a, n = e1 x e2), one 32-byte
  * sector; the edges are fetched only by the lanes whose t lies in (0, tmax). */
-LYS_D bool leaf_test(const RayInv &r, const float4 *__restrict__ leaf_tri, int leaf, float tmax, float &t) {
-    const float4 *q = leaf_tri + 4ll * leaf;
+LYS_D bool leaf_test_at(const RayInv &r, const float4 *__restrict__ q, float tmax, float &t) {
     float4 q0 = __ldg(q), q1 = __ldg(q + 1);
     float inv; V3 s;
     if (!tri_plane_test(r.o, r.d, v3(q0.x, q0.y, q0.z), v3(q1.x, q1.y, q1.z), tmax, t, inv, s)) return false;
     float4 q2 = __ldg(q + 2), q3 = __ldg(q + 3);
     return tri_uv_test(r.d, s, inv, v3(q2.x, q2.y, q2.z), v3(q3.x, q3.y, q3.z));
+}
+LYS_D bool leaf_test(const RayInv &r, const float4 *__restrict__ leaf_tri, int leaf, float tmax, float &t) {
+    return leaf_test_at(r, leaf_tri + 4ll * leaf, tmax, t);
 }
 /* One loop iteration = NB box stages, then one triangle stage, then a warp vote.  A lane takes part in a stage if its
  * next visit has that type, so a node whose left child is a leaf is box-tested and the leaf triangle-tested in the
@@ -73,10 +83,13 @@ LYS_D bool leaf_test(const RayInv &r, const float4 *__restrict__ leaf_tri, int l
  * stack[0] holds the end marker: popping needs no empty check.  Visits, their order and every comparison are those
  * of the reference's walk (see above), only the interleaving between lanes differs. */
 #define TRAV_DONE ((int)0x80000000)
-template <bool ANY, int NB>
+template <bool ANY, int NB, bool OCT>
 LYS_D int traverse(const float4 *__restrict__ nodes, const float4 *__restrict__ leaf_tri, int n_nodes, bool active,
                    V3 o, V3 d, float tmax, float &t_hit) {
     RayInv r; r.o = o; r.d = d; r.inv = v3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    unsigned long long nbase = reinterpret_cast<unsigned long long>(nodes);            /* per-lane base: node i at nbase + 32 i */
+    if (OCT) nbase += 32ull * (unsigned)n_nodes * (unsigned)(((r.inv.x < 0.0f) ? 4 : 0) | ((r.inv.y < 0.0f) ? 2 : 0) | ((r.inv.z < 0.0f) ? 1 : 0));   /* `nodes` = nodes_oct */
+    asm volatile("" : "+l"(nbase));      /* keep the sum in a register pair: one IMAD.WIDE per node address */
     int stack[TRAV_STACK + 1];
     int closest = -1;
     stack[0] = TRAV_DONE;
@@ -86,8 +99,9 @@ LYS_D int traverse(const float4 *__restrict__ nodes, const float4 *__restrict__ 
 #pragma unroll
         for (int k = 0; k < NB; k++) {
             if (cur >= 0) {
-                float4 lo = __ldg(nodes + 2ll * cur), hi = __ldg(nodes + 2ll * cur + 1);
-                if (slab_test(r, lo, hi, tmax)) {
+                const float4 *q = reinterpret_cast<const float4 *>(nbase + 32ull * (unsigned)cur);
+                float4 lo = __ldg(q), hi = __ldg(q + 1);
+                if (OCT ? slab_test_oct(r, lo, hi, tmax) : slab_test(r, lo, hi, tmax)) {
                     stack[sp++] = __float_as_int(hi.w);       /* right child waits */
                     cur = __float_as_int(lo.w);               /* left child first */
                 } else cur = stack[--sp];
@@ -627,7 +641,7 @@ __global__ void __launch_bounds__(128) k_trace_refill(SceneDev sc, const __grid_
 /* The default variant: one item per thread and grid-stride iteration, plain traverse<> loops.  Measured on B200
  * (CornellBox 1080p) it beats the refill variant above, whose every refill stalls the warp on dependent
  * queue -> ray loads; the refill kernel is kept selectable (LYS_TRACE_MODE=1) and is parity-tested too. */
-template <int NB>
+template <int NB, bool OCT>
 __global__ void __launch_bounds__(128) k_trace(SceneDev sc, const __grid_constant__ FrameParams fp, PassBuffers b, int bounce) {
     const int n_ext = (bounce + 1 < fp.path_len) ? b.counts[bounce + 1] : 0;
     const int n_con = (bounce >= 0) ? b.counts[bounce] : 0;
@@ -635,6 +649,7 @@ __global__ void __launch_bounds__(128) k_trace(SceneDev sc, const __grid_constan
     const int stride = gridDim.x * blockDim.x;
     const int n_nodes = (int)sc.n_tris - 1;
     const int lane = threadIdx.x & 31;
+    const float4 *__restrict__ nodes = OCT ? sc.nodes_oct : sc.nodes;
     /* warp-uniform loop (traverse<> votes): a warp owns 32 consecutive items; only the warp that straddles n_ext mixes kinds */
     for (int i0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31); i0 < total; i0 += stride) {
         const int i = i0 + lane;
@@ -643,7 +658,7 @@ __global__ void __launch_bounds__(128) k_trace(SceneDev sc, const __grid_constan
             float4 ro = make_float4(0.0f, 0.0f, 0.0f, 0.0f), rd = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
             if (is_ext) { ro = b.ray_o[(bounce + 1) & 1][i]; rd = b.ray_d[(bounce + 1) & 1][i]; }
             float t;
-            int h = traverse<false, NB>(sc.nodes, sc.leaf_tri, n_nodes, is_ext, v3(ro.x, ro.y, ro.z), v3(rd.x, rd.y, rd.z), FLT_MAX, t);
+            int h = traverse<false, NB, OCT>(nodes, sc.leaf_tri, n_nodes, is_ext, v3(ro.x, ro.y, ro.z), v3(rd.x, rd.y, rd.z), FLT_MAX, t);
             if (is_ext) b.hit[i] = h;
         }
         if (i0 + 31 >= n_ext) {
@@ -657,13 +672,13 @@ __global__ void __launch_bounds__(128) k_trace(SceneDev sc, const __grid_constan
             if (__any_sync(0xffffffffu, need1)) {
                 float4 d1 = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
                 if (need1) d1 = b.sh_d1[slot];
-                int h = traverse<true, NB>(sc.nodes, sc.leaf_tri, n_nodes, need1, o, v3(d1.x, d1.y, d1.z), d1.w, t);
+                int h = traverse<true, NB, OCT>(nodes, sc.leaf_tri, n_nodes, need1, o, v3(d1.x, d1.y, d1.z), d1.w, t);
                 if (need1 && h < 0) L = rc.x;
             }
             if (__any_sync(0xffffffffu, need2)) {
                 float4 d2 = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
                 if (need2) d2 = b.sh_d2[slot];
-                int h = traverse<true, NB>(sc.nodes, sc.leaf_tri, n_nodes, need2, o, v3(d2.x, d2.y, d2.z), d2.w, t);
+                int h = traverse<true, NB, OCT>(nodes, sc.leaf_tri, n_nodes, need2, o, v3(d2.x, d2.y, d2.z), d2.w, t);
                 if (need2 && h < 0) B = rc.y;
             }
             if (is_con) connect_finish(fp, b, bounce, slot, flags, L, B, rc.z, rc.w, rc.z);
@@ -749,7 +764,7 @@ __global__ void k_primary_probe(SceneDev sc, PassBuffers b, int n, int *leaf, in
     float4 ro = make_float4(0.0f, 0.0f, 0.0f, 0.0f), rd = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
     if (act) { ro = b.ray_o[0][i]; rd = b.ray_d[0][i]; }
     float th;
-    int l = traverse<false, 1>(sc.nodes, sc.leaf_tri, (int)sc.n_tris - 1, act, v3(ro.x, ro.y, ro.z), v3(rd.x, rd.y, rd.z), FLT_MAX, th);
+    int l = traverse<false, 1, false>(sc.nodes, sc.leaf_tri, (int)sc.n_tris - 1, act, v3(ro.x, ro.y, ro.z), v3(rd.x, rd.y, rd.z), FLT_MAX, th);
     if (!act) return;
     leaf[i] = l;
     if (src) src[i] = (l < 0) ? -1 : (int)__float_as_uint(sc.leaf_tri[4ll * l + 1].w);
@@ -762,8 +777,8 @@ __global__ void k_trace_rays(SceneDev sc, const float *__restrict__ rays, const 
     V3 o = v3(0.0f, 0.0f, 0.0f), d = v3(1.0f, 1.0f, 1.0f);
     if (act) { const float *r = rays + 6 * i; o = v3(r[0], r[1], r[2]); d = v3(r[3], r[4], r[5]); }
     float th; int l;
-    if (any) l = traverse<true, 1>(sc.nodes, sc.leaf_tri, (int)sc.n_tris - 1, act, o, d, act ? tmax[i] : 0.0f, th);
-    else l = traverse<false, 1>(sc.nodes, sc.leaf_tri, (int)sc.n_tris - 1, act, o, d, FLT_MAX, th);
+    if (any) l = traverse<true, 1, false>(sc.nodes, sc.leaf_tri, (int)sc.n_tris - 1, act, o, d, act ? tmax[i] : 0.0f, th);
+    else l = traverse<false, 1, false>(sc.nodes, sc.leaf_tri, (int)sc.n_tris - 1, act, o, d, FLT_MAX, th);
     if (!act) return;
     out_leaf[i] = any ? (l >= 0 ? 1 : 0) : l;
     if (out_t) out_t[i] = (l < 0) ? LYS_INF : th;
@@ -794,7 +809,7 @@ __global__ void k_material_probe(const float *mat28, float wavelen, V3 wo, V3 wi
 static inline int cdiv(long long a, int b) { return (int)((a + b - 1) / b); }
 
 /* persistent grids: SM count x resident CTAs per SM of each kernel (queried once per device) */
-struct GridSizes { int trace = 0, shade = 0, refill = 0, sl = 0, sb = 0, sc = 0; int mode = 0, split_bounces = 0, nb = 2, bars = 0, shade_threads = 256; };
+struct GridSizes { int trace = 0, shade = 0, refill = 0, sl = 0, sb = 0, sc = 0; int mode = 0, split_bounces = 0, nb = 2, bars = 0, shade_threads = 256, oct = 1; };
 static GridSizes grid_sizes() {
     static GridSizes g[64];
     int dev = 0; cudaGetDevice(&dev);
@@ -802,7 +817,7 @@ static GridSizes grid_sizes() {
     if (!g[dev].trace) {
         int sms = 148, bt = 8, bs = 4;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bt, k_trace<2>, 128, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bt, k_trace<2, true>, 128, 0);
         const char *sth = getenv("LYS_SHADE_THREADS"); if (sth && (atoi(sth) == 512 || atoi(sth) == 128)) g[dev].shade_threads = atoi(sth);
         if (g[dev].shade_threads == 256) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bs, k_shade<256>, 256, 0);
         else if (g[dev].shade_threads == 128) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bs, k_shade<128>, 128, 0);
@@ -813,6 +828,7 @@ static GridSizes grid_sizes() {
         const char *gt = getenv("LYS_TRACE_GRID_PCT"); if (gt && atoi(gt) > 0) g[dev].trace = max(sms, g[dev].trace * atoi(gt) / 100);
         const char *gsh = getenv("LYS_SHADE_GRID_PCT"); if (gsh && atoi(gsh) > 0) g[dev].shade = max(sms, g[dev].shade * atoi(gsh) / 100);
         const char *e = getenv("LYS_TRACE_MODE"); g[dev].mode = (e && atoi(e) == 1) ? 1 : 0;
+        const char *oc = getenv("LYS_TRACE_OCT"); if (oc) g[dev].oct = atoi(oc) ? 1 : 0;          /* 0: always the select-based box test */
         const char *nb = getenv("LYS_TRACE_NB"); g[dev].nb = (nb && atoi(nb) == 1) ? 1 : 2;      /* box stages per loop iteration */
         int b1 = 8, b2 = 8, b3 = 8;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, k_shade_light, 128, 0); cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b2, k_shade_bsdf, 128, 0);
@@ -825,8 +841,9 @@ static GridSizes grid_sizes() {
 }
 static void launch_trace(const GridSizes &gs, int grid, const SceneDev &sc, const FrameParams &fp, PassBuffers &bufs, int bounce, cudaStream_t stream) {
     if (gs.mode) k_trace_refill<<<grid, 128, 0, stream>>>(sc, fp, bufs, bounce);
-    else if (gs.nb == 1) k_trace<1><<<grid, 128, 0, stream>>>(sc, fp, bufs, bounce);
-    else k_trace<2><<<grid, 128, 0, stream>>>(sc, fp, bufs, bounce);
+    else if (sc.nodes_oct && gs.oct) { if (gs.nb == 1) k_trace<1, true><<<grid, 128, 0, stream>>>(sc, fp, bufs, bounce); else k_trace<2, true><<<grid, 128, 0, stream>>>(sc, fp, bufs, bounce); }
+    else if (gs.nb == 1) k_trace<1, false><<<grid, 128, 0, stream>>>(sc, fp, bufs, bounce);
+    else k_trace<2, false><<<grid, 128, 0, stream>>>(sc, fp, bufs, bounce);
 }
 cudaError_t run_sample_pass(const SceneDev &sc, const FrameParams &fp, PassBuffers &bufs, cudaStream_t stream, uint64_t *launches, LaunchTimer *timer) {
     const int n = fp.n_local;
