@@ -31,7 +31,7 @@ uint64_t lys_context_launch_count(struct futhark_context *ctx);
 
 /* Kernel-class device timing (CUDA events around every launch of the sample pass).  Off by default: the
  * extra event records perturb throughput, so it is used for a separate profiling step, never the timed run.
- * Classes: 0 generate, 1 trace (closest hits of bounce b+1 + shadow rays of bounce b), 2 shade, 3 unused, 4 accumulate. */
+ * Classes: 0 generate, 1 trace (closest hits of bounce b+1 + shadow rays of bounce b), 2 shade, 3 tail (k_tail: all bounces from the first sparse one on, in one launch), 4 accumulate. */
 #define LYS_PROFILE_CLASSES 5
 int lys_context_set_profiling(struct futhark_context *ctx, int on);
 int lys_context_profile_get(struct futhark_context *ctx, float *ms /* [5] */, uint64_t *launches /* [5] */, int reset);

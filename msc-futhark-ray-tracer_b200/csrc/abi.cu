@@ -43,6 +43,7 @@ struct futhark_context {
     struct PassSlot { cudaStream_t stream = nullptr; PassBuffers bufs; cudaEvent_t done = nullptr; };
     std::vector<PassSlot> slots;
     int pipeline = 8;
+    int *h_counts = nullptr;             /* pinned: queue lengths of a recent pass (grid sizing only, see run_sample_pass) */
 };
 
 namespace {
@@ -358,7 +359,7 @@ bool sample_into(futhark_context *ctx, const futhark_opaque_state *s, uint32_t r
     FrameParams fp;
     if (!ensure_pass_buffers(ctx, (int64_t)((s->dim_w + s->subsampling - 1) / s->subsampling) * ((s->dim_h + s->subsampling - 1) / s->subsampling), false)) return false;
     if (!make_frame_params(ctx, s, rng, 1.0f, fp)) return false;
-    CUB(ctx, run_sample_pass(s->scene->d, fp, ctx->bufs, ctx->stream, &ctx->launches, &ctx->timer));
+    CUB(ctx, run_sample_pass(s->scene->d, fp, ctx->bufs, ctx->stream, &ctx->launches, &ctx->timer, ctx->h_counts));
     CUB(ctx, run_accumulate(fp, ctx->bufs, img_old, img_new, merge ? 1 : 0, n_frames, ctx->stream, &ctx->launches, &ctx->timer));
     if (ctx->timer.on && ctx->timer.used > 3000) ctx->timer.resolve(ctx->stream);
     return true;
@@ -406,6 +407,9 @@ struct futhark_context *futhark_context_new(struct futhark_context_config *cfg) 
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return nullptr; }
     cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1); cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
     { const char *pe = getenv("LYS_PIPELINE"); if (pe) { int v = atoi(pe); if (v >= 1 && v <= 16) ctx->pipeline = v; } }
+    if (cudaHostAlloc((void **)&ctx->h_counts, sizeof(int) * (LYS_MAX_PATH_LEN + 1), cudaHostAllocDefault) == cudaSuccess) {
+        for (int k = 0; k <= LYS_MAX_PATH_LEN; k++) ctx->h_counts[k] = -1;          /* no estimate yet */
+    } else { ctx->h_counts = nullptr; cudaGetLastError(); }
     const char *pl = getenv("LYS_PATH_LEN");
     if (pl) { int v = atoi(pl); if (v >= 1 && v <= LYS_MAX_PATH_LEN) ctx->path_len = v; }
     return ctx;
@@ -422,6 +426,7 @@ void futhark_context_free(struct futhark_context *ctx) {
     raw_free(w.rs_hist); raw_free(w.rs_status); raw_free(w.leaf_parent); raw_free(w.visits); raw_free(w.crown_box); raw_free(w.crown_cnt);
     if (w.crown_pairs) cudaFree(w.crown_pairs);
     raw_free(ctx->pts_pos); raw_free(ctx->pts_dist);
+    if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
     for (auto &kv : ctx->pool) cudaFree(kv.second);
     ctx->pool.clear();
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -655,7 +660,7 @@ int lys_sample_n_frames_stats(struct futhark_context *ctx, struct futhark_f32_3d
     for (uint32_t k = 0; k < passes; k++) {
         futhark_context::PassSlot &sl = ctx->slots[k % S];
         fp.frame_rng = rng;
-        CU(ctx, run_sample_pass(s->scene->d, fp, sl.bufs, sl.stream, &ctx->launches, &ctx->timer));
+        CU(ctx, run_sample_pass(s->scene->d, fp, sl.bufs, sl.stream, &ctx->launches, &ctx->timer, ctx->h_counts));
         if (prev) CU(ctx, cudaStreamWaitEvent(sl.stream, prev, 0));             /* running average is order dependent */
         CU(ctx, run_accumulate(fp, sl.bufs, a->ptr(), a->ptr(), k > 0 ? 1 : 0, (float)k, sl.stream, &ctx->launches, &ctx->timer));
         CU(ctx, cudaEventRecord(sl.done, sl.stream));
@@ -713,7 +718,7 @@ int futhark_entry_sample_points_n(struct futhark_context *ctx, struct futhark_op
     for (uint32_t k = 0; k < passes; k++) {
         futhark_context::PassSlot &sl = ctx->slots[k % S];
         fp.frame_rng = rng;
-        if (!cu_ok(ctx, run_sample_pass(s->scene->d, fp, sl.bufs, sl.stream, &ctx->launches), "sample pass")) { delete a; return 1; }
+        if (!cu_ok(ctx, run_sample_pass(s->scene->d, fp, sl.bufs, sl.stream, &ctx->launches, nullptr, ctx->h_counts), "sample pass")) { delete a; return 1; }
         if (prev) CU(ctx, cudaStreamWaitEvent(sl.stream, prev, 0));                /* merge keeps the earlier point on ties (lib.fut:51) */
         if (!cu_ok(ctx, run_points_merge(fp, sl.bufs, ctx->pts_pos, ctx->pts_dist, k == 0 ? 1 : 0, sl.stream, &ctx->launches), "points merge")) { delete a; return 1; }
         CU(ctx, cudaEventRecord(sl.done, sl.stream));

@@ -81,7 +81,11 @@ struct LaunchTimer {
 };
 
 /* one sample pass: generate, (extend, shade, connect) x path_len.  Results stay in bufs.acc. */
-cudaError_t run_sample_pass(const SceneDev &sc, const FrameParams &fp, PassBuffers &bufs, cudaStream_t stream, uint64_t *launches, LaunchTimer *timer = nullptr);
+/* est_counts (host, pinned, may be null): queue lengths per bounce of an earlier pass of the same frame; they only size the
+ * persistent grids of the sparse late bounces (any grid size is correct: all kernels are grid-stride over device-side counts),
+ * and the pass leaves its own counts there (async copy) for the next one */
+cudaError_t run_sample_pass(const SceneDev &sc, const FrameParams &fp, PassBuffers &bufs, cudaStream_t stream, uint64_t *launches, LaunchTimer *timer = nullptr,
+                            int *est_counts = nullptr);
 /* resolve + merge into the image: mode 0 = replace (sample_frame), 1 = running average (sample_frame_accum) */
 cudaError_t run_accumulate(const FrameParams &fp, const PassBuffers &bufs, const float *img_old, float *img_new,
                            int merge, float n_frames, cudaStream_t stream, uint64_t *launches, LaunchTimer *timer = nullptr);

@@ -686,6 +686,103 @@ __global__ void __launch_bounds__(128) k_trace(SceneDev sc, const __grid_constan
     }
 }
 
+/* ------------------------------------------------------------------ tail: all remaining bounces in one launch
+ * Past the first few bounces a pass carries a fraction of a percent of its paths, but every bounce still costs two
+ * launches (measured: ~2.3 us of GPU throughput each, whatever the grid size; profiles/README.md 4.6).  k_tail runs
+ * shade(b), trace(b) for b = bounce0 .. path_len-1 inside one launch: each CTA owns a contiguous chunk of the
+ * bounce-bounce0 queue and keeps wavefronting it on its own, with block barriers between the stages and a CTA-local
+ * compaction (live paths stay inside the chunk's slot range of the ping-pong buffers, so the very same per-slot device
+ * routines are used).  Per-path arithmetic is unchanged; the host picks bounce0 from an earlier pass's queue lengths
+ * and any choice is correct. */
+template <bool OCT>
+__global__ void __launch_bounds__(128) k_tail(SceneDev sc, const __grid_constant__ FrameParams fp, PassBuffers b, int bounce0) {
+    __shared__ int s_next;
+    const int count0 = b.counts[bounce0];
+    const int per = (((count0 + (int)gridDim.x - 1) / (int)gridDim.x) + 31) & ~31;
+    const int base = blockIdx.x * per;
+    int n_cur = max(0, min(per, count0 - base));
+    const int nl = fp.n_scene_lights + ((fp.tx_kind == 0) ? 0 : 8);
+    const int n_nodes = (int)sc.n_tris - 1;
+    const int lane = threadIdx.x & 31;
+    const float4 *__restrict__ nodes = OCT ? sc.nodes_oct : sc.nodes;
+    for (int bounce = bounce0; bounce < fp.path_len && n_cur > 0; bounce++) {
+        if (threadIdx.x == 0) s_next = 0;
+        __syncthreads();
+        /* ---- shade(bounce): one vertex per thread (the CTA-wide reflection queue of k_shade does not pay for a handful of paths) */
+        for (int r0 = 0; r0 < n_cur; r0 += blockDim.x) {
+            const int i = base + r0 + threadIdx.x;
+            const bool valid = r0 + (int)threadIdx.x < n_cur;
+            bool alive = false; int pid = -1; unsigned n_vert = 0, n_shadow = 0;
+            float4 next_o = make_float4(0.0f, 0.0f, 0.0f, 0.0f), next_d = next_o; float next_dist = 0.0f;
+            if (valid) {
+                VertexCtx v;
+                if (shade_prologue(sc, b, bounce, i, v)) {
+                    float cL = 0.0f, cB = 0.0f; int flags = 0;
+                    float4 rec_d1 = make_float4(0.0f, 0.0f, 0.0f, 0.0f), rec_d2 = rec_d1;
+                    if (nl > 0) {
+                        LightD l;
+                        shade_pick_light(sc, fp, b, v, nl, l);
+                        shade_light_sample(v, l, cL, rec_d1, flags);
+                        shade_bsdf_light_sample(v, l, cB, rec_d2, flags);
+                    }
+                    b.sh_d1[i] = rec_d1; b.sh_d2[i] = rec_d2;
+                    alive = shade_finish(fp, b, bounce, i, v, cL, cB, flags, next_o, next_d, next_dist);
+                    n_vert = 1; n_shadow = (flags & 1) + ((flags >> 1) & 1);
+                } else shade_miss(fp, b, i, v);
+                pid = v.pid;
+            }
+            const unsigned mask = __ballot_sync(0xffffffffu, alive);
+            int off = 0;
+            if (lane == 0 && mask) off = atomicAdd(&s_next, __popc(mask));
+            off = __shfl_sync(0xffffffffu, off, 0);
+            if (alive) {
+                const int slot = base + off + __popc(mask & ((1u << lane) - 1u));
+                b.queue[(bounce + 1) & 1][slot] = pid;
+                b.ray_o[(bounce + 1) & 1][slot] = next_o; b.ray_d[(bounce + 1) & 1][slot] = next_d; b.dist[(bounce + 1) & 1][slot] = next_dist;
+            }
+            unsigned vsum = __reduce_add_sync(0xffffffffu, n_vert), ssum = __reduce_add_sync(0xffffffffu, n_shadow);
+            if (lane == 0 && (vsum | ssum)) { atomicAdd(&b.stats[0], (unsigned long long)vsum); atomicAdd(&b.stats[2], (unsigned long long)ssum); }
+        }
+        __syncthreads();
+        const int n_next = (bounce + 1 < fp.path_len) ? s_next : 0;
+        /* ---- trace(bounce): closest hits of bounce + 1, then the shadow rays of this bounce */
+        for (int j0 = threadIdx.x & ~31; j0 < n_next; j0 += blockDim.x) {
+            const bool act = j0 + lane < n_next;
+            const int i = base + j0 + lane;
+            float4 ro = make_float4(0.0f, 0.0f, 0.0f, 0.0f), rd = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
+            if (act) { ro = b.ray_o[(bounce + 1) & 1][i]; rd = b.ray_d[(bounce + 1) & 1][i]; }
+            float t;
+            int h = traverse<false, 2, OCT>(nodes, sc.leaf_tri, n_nodes, act, v3(ro.x, ro.y, ro.z), v3(rd.x, rd.y, rd.z), FLT_MAX, t);
+            if (act) b.hit[i] = h;
+        }
+        for (int j0 = threadIdx.x & ~31; j0 < n_cur; j0 += blockDim.x) {
+            const bool act = j0 + lane < n_cur;
+            const int slot = base + j0 + lane;
+            float4 ro = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(4)), rc = ro;
+            if (act) { ro = b.sh_o[slot]; rc = b.sh_c[slot]; }
+            const int flags = __float_as_int(ro.w);
+            float L = 0.0f, B = 0.0f, t;
+            V3 o = v3(ro.x, ro.y, ro.z);
+            const bool need1 = act && !(flags & 4) && (flags & 1), need2 = act && !(flags & 4) && (flags & 2);
+            if (__any_sync(0xffffffffu, need1)) {
+                float4 d1 = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
+                if (need1) d1 = b.sh_d1[slot];
+                int h = traverse<true, 2, OCT>(nodes, sc.leaf_tri, n_nodes, need1, o, v3(d1.x, d1.y, d1.z), d1.w, t);
+                if (need1 && h < 0) L = rc.x;
+            }
+            if (__any_sync(0xffffffffu, need2)) {
+                float4 d2 = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
+                if (need2) d2 = b.sh_d2[slot];
+                int h = traverse<true, 2, OCT>(nodes, sc.leaf_tri, n_nodes, need2, o, v3(d2.x, d2.y, d2.z), d2.w, t);
+                if (need2 && h < 0) B = rc.y;
+            }
+            if (act) connect_finish(fp, b, bounce, slot, flags, L, B, rc.z, rc.w, rc.z);
+        }
+        __syncthreads();
+        n_cur = n_next;
+    }
+}
+
 /* ------------------------------------------------------------------ resolve + accumulate */
 LYS_D V3 hue_to_rgb(float h) {                                       /* integrator.fut:139-148 */
     float hp = h * 6.0f;
@@ -809,7 +906,7 @@ __global__ void k_material_probe(const float *mat28, float wavelen, V3 wo, V3 wi
 static inline int cdiv(long long a, int b) { return (int)((a + b - 1) / b); }
 
 /* persistent grids: SM count x resident CTAs per SM of each kernel (queried once per device) */
-struct GridSizes { int trace = 0, shade = 0, refill = 0, sl = 0, sb = 0, sc = 0; int mode = 0, split_bounces = 0, nb = 2, bars = 0, shade_threads = 256, oct = 1; };
+struct GridSizes { int trace = 0, shade = 0, refill = 0, sl = 0, sb = 0, sc = 0; int mode = 0, split_bounces = 0, nb = 2, bars = 0, shade_threads = 256, oct = 1, adaptive = 1, sms = 148, tail_max = 8192, tail_items = 128, profile_tail = 0; };
 static GridSizes grid_sizes() {
     static GridSizes g[64];
     int dev = 0; cudaGetDevice(&dev);
@@ -828,6 +925,11 @@ static GridSizes grid_sizes() {
         const char *gt = getenv("LYS_TRACE_GRID_PCT"); if (gt && atoi(gt) > 0) g[dev].trace = max(sms, g[dev].trace * atoi(gt) / 100);
         const char *gsh = getenv("LYS_SHADE_GRID_PCT"); if (gsh && atoi(gsh) > 0) g[dev].shade = max(sms, g[dev].shade * atoi(gsh) / 100);
         const char *e = getenv("LYS_TRACE_MODE"); g[dev].mode = (e && atoi(e) == 1) ? 1 : 0;
+        g[dev].sms = sms;
+        const char *tit = getenv("LYS_TAIL_ITEMS"); if (tit && atoi(tit) > 0) g[dev].tail_items = atoi(tit);
+        const char *ptl = getenv("LYS_PROFILE_TAIL"); if (ptl) g[dev].profile_tail = atoi(ptl) ? 1 : 0;
+        const char *tmx = getenv("LYS_TAIL_MAX"); if (tmx) g[dev].tail_max = atoi(tmx);          /* 0: no fused tail */
+        const char *ad = getenv("LYS_ADAPTIVE_GRIDS"); if (ad) g[dev].adaptive = atoi(ad) ? 1 : 0;
         const char *oc = getenv("LYS_TRACE_OCT"); if (oc) g[dev].oct = atoi(oc) ? 1 : 0;          /* 0: always the select-based box test */
         const char *nb = getenv("LYS_TRACE_NB"); g[dev].nb = (nb && atoi(nb) == 1) ? 1 : 2;      /* box stages per loop iteration */
         int b1 = 8, b2 = 8, b3 = 8;
@@ -845,19 +947,39 @@ static void launch_trace(const GridSizes &gs, int grid, const SceneDev &sc, cons
     else if (gs.nb == 1) k_trace<1, false><<<grid, 128, 0, stream>>>(sc, fp, bufs, bounce);
     else k_trace<2, false><<<grid, 128, 0, stream>>>(sc, fp, bufs, bounce);
 }
-cudaError_t run_sample_pass(const SceneDev &sc, const FrameParams &fp, PassBuffers &bufs, cudaStream_t stream, uint64_t *launches, LaunchTimer *timer) {
+cudaError_t run_sample_pass(const SceneDev &sc, const FrameParams &fp, PassBuffers &bufs, cudaStream_t stream, uint64_t *launches, LaunchTimer *timer,
+                            int *est_counts) {
     const int n = fp.n_local;
     if (n <= 0) return cudaSuccess;
     uint64_t nl = 0;
     LaunchTimer none; LaunchTimer &tm = timer ? *timer : none;
     const GridSizes gs = grid_sizes();
     const int g_trace = min(gs.mode ? gs.refill : gs.trace, cdiv(2ll * n, 128)), g_shade = min(gs.shade, cdiv(n, gs.shade_threads));
+    /* queue-length estimates: a snapshot of what an earlier pass left (the copy below may be updating it: harmless, the
+     * numbers only size grids); valid if it is about the same sample grid */
+    int est[LYS_MAX_PATH_LEN + 2];
+    bool have_est = false;
+    if (est_counts && gs.adaptive) {
+        for (int k = 0; k <= LYS_MAX_PATH_LEN; k++) est[k] = est_counts[k];
+        est[LYS_MAX_PATH_LEN + 1] = 0;
+        have_est = est[0] == n;
+        for (int k = 1; k <= LYS_MAX_PATH_LEN && have_est; k++) if (est[k] < 0 || est[k] > n) have_est = false;
+    }
+    const int g_min = max(1, gs.sms);                    /* never below one CTA per SM: a stale estimate costs at most ~10x on one pass */
+    auto sized = [&](long long items, int threads, int g_full) {
+        if (!have_est) return g_full;
+        return (int)max((long long)g_min, min((long long)g_full, (2 * items + 4096 + threads - 1) / threads));
+    };
+    /* first bounce whose queue was short enough in the earlier pass: from there on one k_tail launch */
+    int b_tail = fp.path_len;
+    if (have_est && gs.tail_max > 0 && !gs.mode && !(tm.on && !gs.profile_tail))      /* per-class timing wants every ray in the trace class */
+        for (int k = 1; k < fp.path_len; k++) if (est[k] <= gs.tail_max) { b_tail = k; break; }
     tm.begin(0, stream); k_generate<<<cdiv(n, 256), 256, 0, stream>>>(fp, bufs); tm.end(stream); nl++;
     tm.cur_bounce = -1;
     tm.begin(1, stream);
     launch_trace(gs, g_trace, sc, fp, bufs, -1, stream);
     tm.end(stream); nl++;
-    for (int bnc = 0; bnc < fp.path_len; bnc++) {
+    for (int bnc = 0; bnc < b_tail; bnc++) {
         tm.cur_bounce = bnc;
         tm.begin(2, stream);
         if (bnc < gs.split_bounces) {
@@ -867,13 +989,28 @@ cudaError_t run_sample_pass(const SceneDev &sc, const FrameParams &fp, PassBuffe
                 k_shade_bsdf<<<min(gs.sb, cdiv(n, 128)), 128, 0, stream>>>(sc, fp, bufs, bnc); nl += 2;
             }
             k_shade_cont<<<min(gs.sc, cdiv(n, 128)), 128, 0, stream>>>(sc, fp, bufs, bnc, nlights > 0 ? 1 : 0);
-        } else if (gs.shade_threads == 256) k_shade<256><<<g_shade, 256, 0, stream>>>(sc, fp, bufs, bnc, gs.bars);
-        else if (gs.shade_threads == 128) k_shade<128><<<g_shade, 128, 0, stream>>>(sc, fp, bufs, bnc, gs.bars);
-        else k_shade<512><<<g_shade, 512, 0, stream>>>(sc, fp, bufs, bnc, gs.bars);
+        } else {
+            const int g = sized(have_est ? est[bnc] : 0, gs.shade_threads, g_shade);
+            if (gs.shade_threads == 512) k_shade<512><<<g, 512, 0, stream>>>(sc, fp, bufs, bnc, gs.bars);
+            else if (gs.shade_threads == 128) k_shade<128><<<g, 128, 0, stream>>>(sc, fp, bufs, bnc, gs.bars);
+            else k_shade<256><<<g, 256, 0, stream>>>(sc, fp, bufs, bnc, gs.bars);
+        }
         tm.end(stream); nl++;
         tm.begin(1, stream);
-        launch_trace(gs, g_trace, sc, fp, bufs, bnc, stream);
+        launch_trace(gs, sized(have_est ? (long long)est[bnc] + est[bnc + 1] : 0, 128, g_trace), sc, fp, bufs, bnc, stream);
         tm.end(stream); nl++;
+    }
+    if (b_tail < fp.path_len) {
+        const int g = (int)max(1ll, min((long long)gs.sms * 4, (long long)((est[b_tail] + est[b_tail] / 4 + gs.tail_items - 1) / gs.tail_items)));   /* few, well filled CTAs: they stay resident for all the remaining bounces */
+        tm.cur_bounce = b_tail;
+        tm.begin(3, stream);
+        if (sc.nodes_oct && gs.oct) k_tail<true><<<g, 128, 0, stream>>>(sc, fp, bufs, b_tail);
+        else k_tail<false><<<g, 128, 0, stream>>>(sc, fp, bufs, b_tail);
+        tm.end(stream); nl++;
+    }
+    if (est_counts && gs.adaptive) {
+        cudaError_t e = cudaMemcpyAsync(est_counts, bufs.counts, sizeof(int) * (LYS_MAX_PATH_LEN + 1), cudaMemcpyDeviceToHost, stream);
+        if (e != cudaSuccess) return e;
     }
     if (launches) *launches += nl;
     return cudaGetLastError();

@@ -211,7 +211,7 @@ class Context:
         ms = np.zeros(5, np.float32)
         n = np.zeros(5, np.uint64)
         self.check(self._L.lys_context_profile_get(self._ctx, _ptr(ms), _ptr(n), int(reset)), 'lys_context_profile_get')
-        return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(('generate', 'trace', 'shade', 'unused', 'accumulate'))}
+        return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(('generate', 'trace', 'shade', 'tail', 'accumulate'))}
 
     def profile_detail(self):
         ms = np.zeros(36, np.float32)

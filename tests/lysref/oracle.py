@@ -82,6 +82,9 @@ def lib():
     L.orc_brute_force_hits.argtypes = [vp, f32p, C.c_int64, i32p, f32p]
     L.orc_closest_hits.argtypes = [vp, f32p, C.c_int64, i32p, f32p]
     L.orc_any_hits.argtypes = [vp, f32p, f32p, C.c_int64, i32p]
+    L.orc_closest_hits_steps.argtypes = [vp, f32p, C.c_int64, i32p, i32p]
+    L.orc_probe_path_rays.argtypes = [vp, C.c_void_p, i32p]
+    L.orc_closest_hits_pattern.argtypes = [vp, f32p, C.c_int64, C.c_int32, C.c_void_p, i32p]
     L.orc_counters_get.argtypes = [C.POINTER(Counters)]
     _lib = L
     return L
@@ -260,6 +263,30 @@ class State:
         t = np.empty(len(rays), np.float32)
         lib().orc_closest_hits(self._p, rays.reshape(-1), len(rays), leaf, t)
         return leaf, t
+
+    def closest_hits_steps(self, rays):
+        """box tests and triangle tests of every ray's closest-hit walk"""
+        rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 6)
+        box = np.empty(len(rays), np.int32)
+        tri = np.empty(len(rays), np.int32)
+        lib().orc_closest_hits_steps(self._p, rays.reshape(-1), len(rays), box, tri)
+        return box, tri
+
+    def closest_hits_pattern(self, rays, max_steps=256):
+        """visit pattern of every ray's walk (0 box fail, 1 box pass, 2 triangle miss, 3 triangle hit, 255 padding) and its length"""
+        rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 6)
+        pat = np.full((len(rays), max_steps), 255, np.uint8)
+        ln = np.empty(len(rays), np.int32)
+        lib().orc_closest_hits_pattern(self._p, rays.reshape(-1), len(rays), max_steps, pat.ctypes.data_as(C.c_void_p), ln)
+        return pat, ln
+
+    def probe_path_rays(self):
+        """closest-hit rays of every path of the next pass: rays [gh][gw][16][6], count [gh][gw]"""
+        _, _, gw, gh = self.dims()
+        rays = np.zeros((gh, gw, 16, 6), np.float32)
+        n = np.zeros((gh, gw), np.int32)
+        lib().orc_probe_path_rays(self._p, rays.ctypes.data_as(C.c_void_p), n.reshape(-1))
+        return rays, n
 
     def any_hits(self, rays, tmax):
         rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 6)

@@ -1,10 +1,12 @@
 """GPU parity: the sm_100a library, called through its C ABI, against the CPU oracle on identical inputs.
 Bit-exact everywhere (integers, indices AND f32 results): the arithmetic contract makes that a meaningful bar."""
+import os
 import numpy as np
 import pytest
 from conftest import SCENE_NAMES, bits_equal
 
 pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 K = dict(SPACE=0x20, K1=0x31, K2=0x32, m=0x6D, t=0x74, p=0x70, w=0x77, UP=0x40000052, i=0x69)
 
 
@@ -287,3 +289,35 @@ def test_million_triangle_bvh(orc, pkg, gpu, scenes):
     po, pg = so.probe_primary(), sg.probe_primary()
     assert bits_equal(po['src_tri'], pg['src_tri']) and bits_equal(po['t'], pg['t'])
     assert bits_equal(so.sample_n_frames(2), sg.sample_n_frames(2))
+
+
+@pytest.mark.parametrize('env', [
+    {'LYS_TRACE_OCT': '0'},            # select-based box test on the plain node array (what scenes above 128K nodes use)
+    {'LYS_TRACE_NB': '1'},             # one box stage per loop iteration
+    {'LYS_SHADE_THREADS': '512'}, {'LYS_SHADE_THREADS': '128'}, {'LYS_SHADE_BARS': '3'},
+    {'LYS_TAIL_MAX': '0'},             # no fused tail kernel: one launch per stage and bounce
+    {'LYS_TAIL_MAX': '100000000'},     # fused tail from bounce 1 on (every queue is 'short')
+    {'LYS_TAIL_MAX': '100000000', 'LYS_TRACE_OCT': '0'},
+    {'LYS_TRACE_MODE': '1'},           # refill variant of the trace kernel
+    {'LYS_SHADE_SPLIT': '2'},          # phase-split shading kernels for the first two bounces
+], ids=lambda e: ','.join(f'{k}={v}' for k, v in e.items()))
+def test_kernel_variants_bit_exact(env):
+    """Every selectable kernel variant (environment knobs read once per process) gives the oracle's bits: the sweep of
+    tools/gpu_parity_quick.py (BVH, first hits, per-vertex radiance, 4 accumulated passes, step/render) in a subprocess."""
+    import json
+    import subprocess
+    import sys
+    e = dict(os.environ)
+    e.update(env)
+    out = subprocess.check_output([sys.executable, os.path.join(ROOT, 'tools', 'gpu_parity_quick.py'), 'cornell', 'spectrumsphere'],
+                                  env=e, text=True, timeout=600)
+    seen = 0
+    for line in out.splitlines():
+        name, _, js = line.partition(' ')
+        if name in ('cornell', 'spectrumsphere'):
+            r = json.loads(js)
+            seen += 1
+            for key in ('first_hit_leaf', 'first_hit_t', 'pass_radiance_bits', 'pass_distance_bits', 'pass_channel', 'img4_bits',
+                        'step3_img_bits', 'render_bits'):
+                assert r[key], (env, name, key)
+    assert seen == 2

@@ -84,3 +84,26 @@ def test_shadow_rays_agree_with_closest(orc, scenes):
     tmax = np.full(len(rays), 0.7, np.float32)
     anyh = s.any_hits(rays, tmax)
     assert np.array_equal(anyh == 1, (leaf >= 0) & (tt < 0.7))
+
+
+def test_divergence_probes_are_consistent(orc, scenes):
+    """The study probes used by tools/simt_model.py restate the same walk: the pattern's box / triangle visits equal the
+    step counters, its last triangle hit is the closest hit, and the dumped bounce-0 rays are the camera rays."""
+    t, tm, m = scenes['spectrumsphere']
+    s = orc.State.init(t, tm, m, 24, 32)
+    rays, n = s.probe_path_rays()
+    prim = s.probe_primary(want_rays=True)
+    assert n.min() >= 1 and n.max() <= 16
+    assert np.array_equal(rays[:, :, 0].view(np.uint32), prim['rays'].view(np.uint32))
+    hit0 = prim['leaf'] >= 0
+    assert np.all((n > 1) <= hit0)                                     # a path continues only from a hit vertex
+    live = np.nonzero(n.reshape(-1) > 1)[0]
+    r1 = rays.reshape(-1, 16, 6)[live, 1]
+    pat, ln = s.closest_hits_pattern(r1, 400)
+    box, tri = s.closest_hits_steps(r1)
+    assert np.array_equal(((pat == 0) | (pat == 1)).sum(axis=1), box)
+    assert np.array_equal(((pat == 2) | (pat == 3)).sum(axis=1), tri)
+    assert np.array_equal(ln, box + tri)
+    leaf, _ = s.closest_hits(r1)
+    assert np.array_equal((pat == 3).any(axis=1), leaf >= 0)
+    assert np.all(pat[:, 0] <= 1)                                       # every walk starts with the root's box
