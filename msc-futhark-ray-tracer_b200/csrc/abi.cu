@@ -44,6 +44,7 @@ struct futhark_context {
     std::vector<PassSlot> slots;
     int pipeline = 8;
     int *h_counts = nullptr;             /* pinned: queue lengths of a recent pass (grid sizing only, see run_sample_pass) */
+    uint64_t est_tag = 0;                /* what the estimates are about: scene, camera, path length */
 };
 
 namespace {
@@ -277,6 +278,14 @@ bool make_frame_params(futhark_context *ctx, const futhark_opaque_state *s, uint
     fp.n_local = rows * (int)gw;
     fp.frame_rng = rng;
     const Camera &cam = s->cam; const CamConf &cf = cam.conf;
+    if (ctx->h_counts) {        /* queue-length estimates are only kept for the same scene seen by the same camera */
+        uint64_t tag = 1469598103934665603ull;
+        auto mix = [&tag](uint64_t x) { tag = (tag ^ x) * 1099511628211ull; };
+        mix((uint64_t)(uintptr_t)s->scene.get()); mix((uint64_t)ctx->path_len); mix((uint64_t)s->cam_conf_id);
+        uint32_t w[5]; memcpy(&w[0], &cam.origin.x, 4); memcpy(&w[1], &cam.origin.y, 4); memcpy(&w[2], &cam.origin.z, 4); memcpy(&w[3], &cam.pitch, 4); memcpy(&w[4], &cam.yaw, 4);
+        for (int k = 0; k < 5; k++) mix(w[k]);
+        if (tag != ctx->est_tag) { for (int k = 0; k <= LYS_MAX_PATH_LEN; k++) ctx->h_counts[k] = -1; ctx->est_tag = tag; }
+    }
     float ratio = fp.fw / fp.fh;
     fp.lens_radius = cf.aperture / 2;
     float half_height = tanf(cf.fov / 2.0f);

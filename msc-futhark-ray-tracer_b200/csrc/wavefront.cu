@@ -745,6 +745,7 @@ __global__ void __launch_bounds__(128) k_tail(SceneDev sc, const __grid_constant
         }
         __syncthreads();
         const int n_next = (bounce + 1 < fp.path_len) ? s_next : 0;
+        if (threadIdx.x == 0 && n_next > 0) atomicAdd(&b.counts[bounce + 1], n_next);     /* the next pass sizes itself from the true queue lengths */
         /* ---- trace(bounce): closest hits of bounce + 1, then the shadow rays of this bounce */
         for (int j0 = threadIdx.x & ~31; j0 < n_next; j0 += blockDim.x) {
             const bool act = j0 + lane < n_next;
@@ -906,7 +907,7 @@ __global__ void k_material_probe(const float *mat28, float wavelen, V3 wo, V3 wi
 static inline int cdiv(long long a, int b) { return (int)((a + b - 1) / b); }
 
 /* persistent grids: SM count x resident CTAs per SM of each kernel (queried once per device) */
-struct GridSizes { int trace = 0, shade = 0, refill = 0, sl = 0, sb = 0, sc = 0; int mode = 0, split_bounces = 0, nb = 2, bars = 0, shade_threads = 256, oct = 1, adaptive = 1, sms = 148, tail_max = 8192, tail_items = 128, profile_tail = 0; };
+struct GridSizes { int trace = 0, shade = 0, refill = 0, sl = 0, sb = 0, sc = 0; int mode = 0, split_bounces = 0, nb = 0, bars = 0, shade_threads = 256, oct = 1, adaptive = 1, sms = 148, tail_max = 8192, tail_items = 128, profile_tail = 0; };
 static GridSizes grid_sizes() {
     static GridSizes g[64];
     int dev = 0; cudaGetDevice(&dev);
@@ -931,7 +932,7 @@ static GridSizes grid_sizes() {
         const char *tmx = getenv("LYS_TAIL_MAX"); if (tmx) g[dev].tail_max = atoi(tmx);          /* 0: no fused tail */
         const char *ad = getenv("LYS_ADAPTIVE_GRIDS"); if (ad) g[dev].adaptive = atoi(ad) ? 1 : 0;
         const char *oc = getenv("LYS_TRACE_OCT"); if (oc) g[dev].oct = atoi(oc) ? 1 : 0;          /* 0: always the select-based box test */
-        const char *nb = getenv("LYS_TRACE_NB"); g[dev].nb = (nb && atoi(nb) == 1) ? 1 : 2;      /* box stages per loop iteration */
+        const char *nb = getenv("LYS_TRACE_NB"); g[dev].nb = nb ? ((atoi(nb) == 1) ? 1 : 2) : 0;      /* box stages per loop iteration; 0 = by scene size */
         int b1 = 8, b2 = 8, b3 = 8;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, k_shade_light, 128, 0); cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b2, k_shade_bsdf, 128, 0);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b3, k_shade_cont, 128, 0);
@@ -941,7 +942,11 @@ static GridSizes grid_sizes() {
     }
     return g[dev];
 }
-static void launch_trace(const GridSizes &gs, int grid, const SceneDev &sc, const FrameParams &fp, PassBuffers &bufs, int bounce, cudaStream_t stream) {
+static void launch_trace(const GridSizes &gs0, int grid, const SceneDev &sc, const FrameParams &fp, PassBuffers &bufs, int bounce, cudaStream_t stream) {
+    GridSizes gs = gs0;
+    /* box stages per loop iteration: 2 for small, cache-resident trees (issue bound: fewer, fuller iterations), 1 for large
+     * ones (two dependent node loads per lock-step iteration cost more than they save); measured in profiles/README.md 4.5 */
+    if (gs.nb == 0) gs.nb = (sc.n_tris <= 4096) ? 2 : 1;
     if (gs.mode) k_trace_refill<<<grid, 128, 0, stream>>>(sc, fp, bufs, bounce);
     else if (sc.nodes_oct && gs.oct) { if (gs.nb == 1) k_trace<1, true><<<grid, 128, 0, stream>>>(sc, fp, bufs, bounce); else k_trace<2, true><<<grid, 128, 0, stream>>>(sc, fp, bufs, bounce); }
     else if (gs.nb == 1) k_trace<1, false><<<grid, 128, 0, stream>>>(sc, fp, bufs, bounce);
@@ -1001,7 +1006,7 @@ cudaError_t run_sample_pass(const SceneDev &sc, const FrameParams &fp, PassBuffe
         tm.end(stream); nl++;
     }
     if (b_tail < fp.path_len) {
-        const int g = (int)max(1ll, min((long long)gs.sms * 4, (long long)((est[b_tail] + est[b_tail] / 4 + gs.tail_items - 1) / gs.tail_items)));   /* few, well filled CTAs: they stay resident for all the remaining bounces */
+        const int g = (int)max((long long)gs.sms, min((long long)gs.sms * 4, (long long)((est[b_tail] + est[b_tail] / 4 + gs.tail_items - 1) / gs.tail_items)));   /* few, well filled CTAs (they stay resident for all the remaining bounces), never fewer than one per SM: a stale estimate must not serialise a long queue */
         tm.cur_bounce = b_tail;
         tm.begin(3, stream);
         if (sc.nodes_oct && gs.oct) k_tail<true><<<g, 128, 0, stream>>>(sc, fp, bufs, b_tail);

@@ -61,19 +61,23 @@ def run(ctx, label, tris, tm, mats, h, w, passes, path_len=16, origin=(0.0, 0.8,
 def main():
     ctx = pkg.Context()
     out = []
+    only = sys.argv[1:]                                   # optional: config labels to run, by prefix ("5", "2b", "metric")
+    want = lambda label: not only or any(label.startswith(p) for p in only)
     c = scene('cornell')
-    out.append(run(ctx, '1a cornell 512x512 path_len 5', *c, 512, 512, 64, path_len=5, cpu_passes=4))
-    out.append(run(ctx, '1b cornell 512x512 path_len 16', *c, 512, 512, 64, cpu_passes=4))
-    out.append(run(ctx, 'metric cornell 1080p', *c, 1080, 1920, 16))
+    if want('1a'): out.append(run(ctx, '1a cornell 512x512 path_len 5', *c, 512, 512, 64, path_len=5, cpu_passes=4))
+    if want('1b'): out.append(run(ctx, '1b cornell 512x512 path_len 16', *c, 512, 512, 64, cpu_passes=4))
+    if want('metric'): out.append(run(ctx, 'metric cornell 1080p', *c, 1080, 1920, 16))
     m = scene('mirrorbox')
-    out.append(run(ctx, '2a mirrorbox 1080p default camera (outside the box)', *m, 1080, 1920, 64))
-    out.append(run(ctx, '2b mirrorbox 1080p camera inside (0,0.8,0.6)', *m, 1080, 1920, 64, origin=(0.0, 0.8, 0.6)))
-    out.append(run(ctx, '3 spectrumsphere 1080p 256 passes', *scene('spectrumsphere'), 1080, 1920, 256, reps=1))
-    out.append(run(ctx, '4 spectrumspherehigh 1080p', *scene('spectrumspherehigh'), 1080, 1920, 16))
-    st, sm = pkg.scenes.synthetic_cornell(c[0], c[1], 151)
-    out.append(run(ctx, '5 synthetic 1003244 tris 4K (16 of 1024 passes)', st, sm, c[2], 2160, 3840, 16, reps=2))
+    if want('2a'): out.append(run(ctx, '2a mirrorbox 1080p default camera (outside the box)', *m, 1080, 1920, 64))
+    if want('2b'): out.append(run(ctx, '2b mirrorbox 1080p camera inside (0,0.8,0.6)', *m, 1080, 1920, 64, origin=(0.0, 0.8, 0.6)))
+    if want('3'): out.append(run(ctx, '3 spectrumsphere 1080p 256 passes', *scene('spectrumsphere'), 1080, 1920, 256, reps=1))
+    if want('4'): out.append(run(ctx, '4 spectrumspherehigh 1080p', *scene('spectrumspherehigh'), 1080, 1920, 16))
+    if want('5'):
+        st, sm = pkg.scenes.synthetic_cornell(c[0], c[1], 151)
+        out.append(run(ctx, '5 synthetic 1003244 tris 4K (16 of 1024 passes)', st, sm, c[2], 2160, 3840, 16, reps=2))
     os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
-    json.dump(out, open(os.path.join(ROOT, 'gpurun_out', 'configs.json'), 'w'), indent=1)
+    if not only:
+        json.dump(out, open(os.path.join(ROOT, 'gpurun_out', 'configs.json'), 'w'), indent=1)
 
 
 if __name__ == '__main__':

@@ -12,6 +12,8 @@ ctx = pkg.Context()
 kw = {'origin': (0.0, 0.8, 0.6)} if name == 'mirrorbox' else {}
 H, W = (int(os.environ.get('LYS_H', 1080)), int(os.environ.get('LYS_W', 1920)))
 s = pkg.State.init(ctx, d['tris'], d['tri_mats'], d['mats'], H, W, **kw)
+if os.environ.get('LYS_WARM', '1') != '0':
+    s.sample_n_frames_device(1)      # leaves the queue-length estimates that size the late grids / pick the fused tail
 h, ptr, shape, st = s.sample_n_frames_device(passes)
 ctx.sync()
 print(name, shape, st)
