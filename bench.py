@@ -102,6 +102,17 @@ def host_threads():
         return os.cpu_count() or 1
 
 
+def ncu_traffic():
+    """DRAM bytes per k_trace launch from the committed ncu launch list of this workload (profiles/, see tools/ncu_pass_summary.py);
+    measured under the profiler once per round, not in this run."""
+    p = os.path.join(ROOT, 'profiles', 'r1_k_trace_dram.json')
+    try:
+        d = json.load(open(p))
+        return d['per_bounce_sequence']['dram_bytes_per_launch'], 'profiles/r1_k_trace_dram.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean over the 17 k_trace launches of a pass)'
+    except Exception:
+        return None, None
+
+
 def cpu_baseline(oracle, scene, passes, threads=None):
     """Oracle Mpaths/s on the host cores + work counters for the algorithmic-bytes figure (bounded sample)."""
     t, tm, m = scene
@@ -285,8 +296,9 @@ def main():
             tr_bytes = ext_bytes + con_bytes
             tot_ms = sum(v[0] for v in prof.values())
             achieved = tr_bytes / (tr_ms * 1e-3) / 1e9
+            traffic, traffic_src = ncu_traffic()
             roof = {'bound': 'hbm', 'kernel': 'k_trace (closest hits + shadow rays, all launches of a step)', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-                    'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src,
+                    'frac': achieved / peak, 'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': peak_src,
                     'algorithmic_bytes_per_launch': tr_bytes / max(tr_n, 1), 'avg_launch_ms': tr_ms / max(tr_n, 1), 'launches': tr_n,
                     'share_of_step': tr_ms / tot_ms if tot_ms else None,
                     'b_path_bytes': b_path, 'whole_pass_algorithmic_gbs': b_path * W * H * PASSES / (tot_ms * 1e-3) / 1e9,

@@ -161,18 +161,20 @@ __global__ void __launch_bounds__(256) k_generate(const __grid_constant__ FrameP
 }
 
 /* ------------------------------------------------------------------ lights */
-struct LightD { V3 a, e1, e2, n; float inv_area, theta; int kind; float em[12]; };
-LYS_D void load_light(const LightRec *__restrict__ L, LightD &l) {
+/* one light as a vertex sees it: geometry + E = emission at the path's wavelength (light.fut:25,38; the lookup depends on
+ * the light and the wavelength only, so it is done once per vertex instead of once per incident_radiance call) */
+struct LightD { V3 a, e1, e2, n; float inv_area, theta; int kind; float E; };
+LYS_D void load_light(const LightRec *__restrict__ L, float wavelen, LightD &l) {
     const float4 *q = reinterpret_cast<const float4 *>(L);
     float4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2), q3 = __ldg(q + 3);
     l.a = v3(q0.x, q0.y, q0.z); l.e1 = v3(q1.x, q1.y, q1.z); l.inv_area = q1.w;
     l.e2 = v3(q2.x, q2.y, q2.z); l.theta = q2.w; l.n = v3(q3.x, q3.y, q3.z); l.kind = __float_as_int(q3.w);
     float4 e0 = __ldg(q + 4), e1 = __ldg(q + 5), e2 = __ldg(q + 6);
-    l.em[0] = e0.x; l.em[1] = e0.y; l.em[2] = e0.z; l.em[3] = e0.w; l.em[4] = e1.x; l.em[5] = e1.y; l.em[6] = e1.z; l.em[7] = e1.w;
-    l.em[8] = e2.x; l.em[9] = e2.y; l.em[10] = e2.z; l.em[11] = e2.w;
+    float em[12] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w, e2.x, e2.y, e2.z, e2.w};
+    l.E = spectrum_lookup12(wavelen, em);
 }
 /* light k of the scanning transmitter for a primary ray direction (camera.fut:119-121, shapes.fut:17-35) */
-LYS_DN void scanning_light(const FrameParams &fp, V3 prim_dir, int k, LightD &l) {
+LYS_DN void scanning_light(const FrameParams &fp, V3 prim_dir, int k, float wavelen, LightD &l) {
     V3 c = cross(prim_dir, v3(0.0f, 1.0f, 0.0f));
     V3 right = (norm(c) == 0.0f) ? v3(1.0f, 0.0f, 0.0f) : normalise(c);
     V3 up = normalise(cross(right, prim_dir));
@@ -183,16 +185,15 @@ LYS_DN void scanning_light(const FrameParams &fp, V3 prim_dir, int k, LightD &l)
     V3 nc = cross(l.e1, l.e2);
     float area = norm(nc) / 2.0f;
     l.inv_area = 1.0f / area; l.n = normalise(nc); l.theta = fp.tx_theta; l.kind = 1;
-#pragma unroll
-    for (int q = 0; q < 12; q++) l.em[q] = fp.tx_emission[q];
+    l.E = spectrum_lookup12(wavelen, fp.tx_emission);
 }
 /* arealight_incident_radiance (light.fut:19-55) */
-LYS_DN float incident_radiance(const LightD &l, V3 hitp, V3 lightp, float wavelen) {
+LYS_D float incident_radiance(const LightD &l, V3 hitp, V3 lightp) {
     V3 v = lightp - hitp;
     V3 wi = normalise(v);
     float d2 = quadrance(v);
     float cl = dot(-wi, l.n);
-    float E = spectrum_lookup12(wavelen, l.em);
+    const float E = l.E;
     if (l.kind == 0) return lys_fmaxf(0.0f, E * cl / d2);
     return (det_acosf(cl) <= l.theta) ? E / d2 : 0.0f;
 }
@@ -236,14 +237,14 @@ LYS_D bool shade_prologue(const SceneDev &sc, const PassBuffers &b, int bounce, 
 /* direct.fut:116-119: one raw draw picks the light (scene lights, then the 8 transmitter lights of this ray) */
 LYS_D void shade_pick_light(const SceneDev &sc, const FrameParams &fp, const PassBuffers &b, VertexCtx &v, int nl, LightD &l) {
     uint32_t pick = lcg_next(v.rng) % (uint32_t)nl;
-    if ((int)pick < fp.n_scene_lights) load_light(sc.lights + pick, l);
-    else if (fp.tx_kind == 1) load_light(b.tx_lights + (pick - fp.n_scene_lights), l);
+    if ((int)pick < fp.n_scene_lights) load_light(sc.lights + pick, v.wavelen, l);
+    else if (fp.tx_kind == 1) load_light(b.tx_lights + (pick - fp.n_scene_lights), v.wavelen, l);
     else {
         int col, row; int ix = local_to_pixel(fp, v.pid, col, row);
         uint32_t r0 = fp.frame_rng ^ rng_split_hash((uint32_t)ix);
         V3 po, pd; float pw; int pc;
         camera_sample(fp, col, row, r0, po, pd, pw, pc);
-        scanning_light(fp, pd, (int)pick - fp.n_scene_lights, l);
+        scanning_light(fp, pd, (int)pick - fp.n_scene_lights, v.wavelen, l);
     }
 }
 /* light sample: sample_arealight peeks two draws (direct.fut:32-42), MIS weight (direct.fut:70-78) */
@@ -255,7 +256,7 @@ LYS_D void shade_light_sample(const VertexCtx &v, const LightD &l, float &cL, fl
     V3 p = (l.a + lu * l.e1) + lv * l.e2;
     V3 vv = p - v.pos;
     V3 wi = normalise(vv);
-    float in_rad = incident_radiance(l, v.pos, p, v.wavelen);
+    float in_rad = incident_radiance(l, v.pos, p);
     float pdf = l.inv_area;
     bool facing = !(dot(wi, v.n) <= 0.0f);                                 /* direct.fut:12 */
     if (facing && !(pdf == 0.0f || in_rad == 0.0f)) {                      /* direct.fut:51-53,73-74 */
@@ -278,7 +279,7 @@ LYS_D void shade_bsdf_light_use(const VertexCtx &v, const LightD &l, const DirSa
         V3 vv = lp - v.pos;
         V3 w = normalise(vv);
         if (!(dot(w, v.n) <= 0.0f) && s.kind != PDF_IMPOSSIBLE) {
-            float in_rad = incident_radiance(l, v.pos, lp, v.wavelen);
+            float in_rad = incident_radiance(l, v.pos, lp);
             float f = s.bsdf * lys_fabsf(dot(s.wi, v.n));
             if (s.kind == PDF_DELTA) cB = f * in_rad;
             else { float weight = balance1(s.pdf, l.inv_area); cB = f * in_rad * weight / s.pdf; }
