@@ -12,8 +12,26 @@
 #include "../../include/lys_detmath.h"
 
 #define LYS_D __device__ __forceinline__
-#define LYS_DN static __device__ __noinline__     /* big shading routines: keep k_shade inside the instruction cache */
+/* The big shading routines.  They were out of line while k_shade was instruction-fetch bound (6000 SASS instructions with
+ * a one-lane reflection path in every warp); with that path compacted (wavefront.cu) inlining wins again: no caller-saved
+ * spills around the calls, 2643 -> 2794 Mpaths/s (profiles/README.md 4.5).  -DLYS_DN=... restores the calls for experiments. */
+#ifndef LYS_DN
+#define LYS_DN static __device__ __forceinline__
+#endif
 #define LYS_HDI __host__ __device__ __forceinline__
+/* per-routine choice (experiments: -DLYS_DN_REFR=LYS_D ...) */
+#ifndef LYS_DN_REFR
+#define LYS_DN_REFR LYS_DN
+#endif
+#ifndef LYS_DN_UBER
+#define LYS_DN_UBER LYS_DN
+#endif
+#ifndef LYS_DN_SREFL
+#define LYS_DN_SREFL LYS_DN
+#endif
+#ifndef LYS_DN_RTERMS
+#define LYS_DN_RTERMS LYS_DN
+#endif
 
 #define LYS_PI 3.14159265358979323846f
 #define LYS_INV_PI (1.0f / LYS_PI)          /* linalg.fut:55 */
@@ -201,7 +219,7 @@ LYS_D float schlick(V3 wo, const Mat1 &m) {                                     
     return r0 + (1.0f - r0) * det_pow5f(1.0f - wo.z);
 }
 /* Torrance-Sparrow reflection value (:264-266) and its pdf (:298-302), sharing D(wh). */
-LYS_DN void reflection_terms(V3 wo, V3 wi, const Mat1 &m, float &bsdf, float &pdf) {
+LYS_DN_RTERMS void reflection_terms(V3 wo, V3 wi, const Mat1 &m, float &bsdf, float &pdf) {
     float alpha = beckmann_alpha(m.roughness);
     V3 wh = normalise(wi + wo);
     float D = beckmann_d(alpha, wh);
@@ -210,7 +228,7 @@ LYS_DN void reflection_terms(V3 wo, V3 wi, const Mat1 &m, float &bsdf, float &pd
     pdf = same_hemi(wo, wi) ? (D * lys_fabsf(wh.z)) / (4.0f * dot(wo, wh)) : 0.0f;
 }
 /* uber_bsdf (:357-358) and uber_pdf (:360-361, operands as written in the reference) in local space */
-LYS_DN void uber_eval(V3 wo, V3 wi, const Mat1 &m, float &f, float &pdf) {
+LYS_DN_UBER void uber_eval(V3 wo, V3 wi, const Mat1 &m, float &f, float &pdf) {
     float refl_f, refl_pdf;
     reflection_terms(wo, wi, m, refl_f, refl_pdf);
     float refr_f = lerpf(0.0f, m.color * LYS_INV_PI, m.opacity);                              /* :187-188 */
@@ -224,7 +242,7 @@ LYS_DN void uber_eval(V3 wo, V3 wi, const Mat1 &m, float &f, float &pdf) {
     pdf = lerpf(refl_pdf, diel_pdf, m.metalness);
 }
 /* dielectric_reflection_sample_dir (:305-315), with sample_wh (:283-296) */
-LYS_DN DirSample sample_reflection(V3 wo, const Mat1 &m, uint32_t &rng) {
+LYS_DN_SREFL DirSample sample_reflection(V3 wo, const Mat1 &m, uint32_t &rng) {
     float u0 = rng_unit(rng), u1 = rng_unit(rng);
     float ls = det_logf(1.0f - u0);
     V3 wh; float pdf_wh;
@@ -249,7 +267,7 @@ LYS_DN DirSample sample_reflection(V3 wo, const Mat1 &m, uint32_t &rng) {
     return s;
 }
 /* dielectric_refraction_sample_dir (:195-200): Lambert (:106-129) or delta transmission (:132-183) */
-LYS_DN DirSample sample_refraction(V3 wo, const Mat1 &m, uint32_t &rng) {
+LYS_DN_REFR DirSample sample_refraction(V3 wo, const Mat1 &m, uint32_t &rng) {
     DirSample s;
     float p = rng_unit(rng);
     if (p < m.opacity) {

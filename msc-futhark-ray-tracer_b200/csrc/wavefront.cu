@@ -410,6 +410,7 @@ __global__ void __launch_bounds__(SHADE_THREADS, 2048 / SHADE_THREADS / 2) k_sha
         if (bars & 1) __syncthreads();                                    /* lockstep only (instruction cache) */
         if (lit) shade_pick_light(sc, fp, b, v, nl, l);
         if (lit) shade_light_sample(v, l, cL, rec_d1, flags);
+        if (hit) b.sh_d1[i] = rec_d1;                                     /* records leave the registers as soon as they are complete */
         if (bars & 2) __syncthreads();                                    /* lockstep only */
         /* both sample_dir calls of the vertex: the MIS sample (direct.fut:83) and the continuation (integrator.fut:56) */
         bool metal1, metal2;
@@ -429,12 +430,12 @@ __global__ void __launch_bounds__(SHADE_THREADS, 2048 / SHADE_THREADS / 2) k_sha
             s.wi = to_world(v.onb, s.wi);
             shade_bsdf_light_use(v, l, s, cB, rec_d2, flags);
         }
+        if (hit) b.sh_d2[i] = rec_d2;
         if (valid) {
             if (hit) {
                 DirSample s = shade_get_sample(sh, SHADE_THREADS + threadIdx.x);
                 if (metal2) s.bsdf = v.m.color * s.bsdf;
                 s.wi = to_world(v.onb, s.wi);
-                b.sh_d1[i] = rec_d1; b.sh_d2[i] = rec_d2;
                 alive = shade_finish_use(fp, b, bounce, i, v, s, cL, cB, flags, next_o, next_d, next_dist);
                 n_vert = 1; n_shadow = (flags & 1) + ((flags >> 1) & 1);
             } else shade_miss(fp, b, i, v);

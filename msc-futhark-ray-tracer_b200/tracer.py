@@ -11,7 +11,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, 'libtracer.so')
+_SO = os.environ.get('LYS_LIBTRACER') or os.path.join(_HERE, 'libtracer.so')     # override: development builds only
 _LJUS = os.path.join(_HERE, 'libljus.so')
 
 # src/sdl.fut key codes used by lib.fut:120-185
