@@ -389,8 +389,11 @@ LYS_D void shade_draw_or_queue(SH &sh, bool want, int slot, const VertexCtx &v, 
         if (reflect) sh.q[base + __popc(mask & ((1u << lane) - 1u))] = (unsigned short)slot;
     }
 }
+#ifndef LYS_SHADE_MINB
+#define LYS_SHADE_MINB(T) ((T) == 256 ? 3 : 2048 / (T) / 2)      /* 256 threads: 3 CTAs / 80 registers (no spills) measured best; else 64 registers */
+#endif
 template <int SHADE_THREADS>
-__global__ void __launch_bounds__(SHADE_THREADS, 2048 / SHADE_THREADS / 2) k_shade(SceneDev sc, const __grid_constant__ FrameParams fp, PassBuffers b, int bounce, int bars) {
+__global__ void __launch_bounds__(SHADE_THREADS, LYS_SHADE_MINB(SHADE_THREADS)) k_shade(SceneDev sc, const __grid_constant__ FrameParams fp, PassBuffers b, int bounce, int bars) {
     __shared__ ShadeShared<SHADE_THREADS> sh;
     const int count = b.counts[bounce];
     const int stride = gridDim.x * blockDim.x;
@@ -643,8 +646,11 @@ __global__ void __launch_bounds__(128) k_trace_refill(SceneDev sc, const __grid_
 /* The default variant: one item per thread and grid-stride iteration, plain traverse<> loops.  Measured on B200
  * (CornellBox 1080p) it beats the refill variant above, whose every refill stalls the warp on dependent
  * queue -> ray loads; the refill kernel is kept selectable (LYS_TRACE_MODE=1) and is parity-tested too. */
+#ifndef LYS_TRACE_MINB
+#define LYS_TRACE_MINB 1
+#endif
 template <int NB, bool OCT>
-__global__ void __launch_bounds__(128) k_trace(SceneDev sc, const __grid_constant__ FrameParams fp, PassBuffers b, int bounce) {
+__global__ void __launch_bounds__(128, LYS_TRACE_MINB) k_trace(SceneDev sc, const __grid_constant__ FrameParams fp, PassBuffers b, int bounce) {
     const int n_ext = (bounce + 1 < fp.path_len) ? b.counts[bounce + 1] : 0;
     const int n_con = (bounce >= 0) ? b.counts[bounce] : 0;
     const int total = n_ext + n_con;
