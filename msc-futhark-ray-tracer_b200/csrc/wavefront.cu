@@ -145,6 +145,7 @@ __global__ void __launch_bounds__(256) k_generate(const __grid_constant__ FrameP
     if (pid == 0) {
         b.counts[0] = fp.n_local;
         for (int k = 1; k <= LYS_MAX_PATH_LEN; k++) b.counts[k] = 0;
+        for (int k = 0; k < 2 * (LYS_MAX_PATH_LEN + 1); k++) b.split[k] = 0;
     }
     if (pid >= fp.n_local) return;
     int col, row; int ix = local_to_pixel(fp, pid, col, row);
@@ -399,8 +400,8 @@ __global__ void __launch_bounds__(SHADE_THREADS, LYS_SHADE_MINB(SHADE_THREADS)) 
     const int stride = gridDim.x * blockDim.x;
     const int nl = fp.n_scene_lights + ((fp.tx_kind == 0) ? 0 : 8);
     for (int b0 = blockIdx.x * blockDim.x; b0 < count; b0 += stride) {
-        const int i = b0 + threadIdx.x;
-        const bool valid = i < count;
+        const bool valid = b0 + (int)threadIdx.x < count;
+        const int i = !valid ? 0 : (bars & 4) ? b.order[b0 + threadIdx.x] : b0 + (int)threadIdx.x;      /* hits first: warps are all-hit or all-miss */
         bool alive = false, hit = false; int pid = -1; unsigned n_vert = 0, n_shadow = 0;
         float4 next_o = make_float4(0.0f, 0.0f, 0.0f, 0.0f), next_d = next_o; float next_dist = 0.0f;
         VertexCtx v;
@@ -647,7 +648,7 @@ __global__ void __launch_bounds__(128) k_trace_refill(SceneDev sc, const __grid_
  * (CornellBox 1080p) it beats the refill variant above, whose every refill stalls the warp on dependent
  * queue -> ray loads; the refill kernel is kept selectable (LYS_TRACE_MODE=1) and is parity-tested too. */
 #ifndef LYS_TRACE_MINB
-#define LYS_TRACE_MINB 1
+#define LYS_TRACE_MINB 10     /* <= 51 registers: 10 CTAs of 128 threads per SM */
 #endif
 template <int NB, bool OCT>
 __global__ void __launch_bounds__(128, LYS_TRACE_MINB) k_trace(SceneDev sc, const __grid_constant__ FrameParams fp, PassBuffers b, int bounce) {
@@ -668,6 +669,17 @@ __global__ void __launch_bounds__(128, LYS_TRACE_MINB) k_trace(SceneDev sc, cons
             float t;
             int h = traverse<false, NB, OCT>(nodes, sc.leaf_tri, n_nodes, is_ext, v3(ro.x, ro.y, ro.z), v3(rd.x, rd.y, rd.z), FLT_MAX, t);
             if (is_ext) b.hit[i] = h;
+            /* processing order of shade(bounce + 1): hits from the front, misses from the back (one atomic per warp and kind) */
+            if (bounce >= 0) {                 /* not for camera rays: their misses are whole warps already, shade(0) walks the slots in order */
+                const bool isH = is_ext && h >= 0, isM = is_ext && h < 0;
+                const unsigned mh = __ballot_sync(0xffffffffu, isH), mm = __ballot_sync(0xffffffffu, isM);
+                int bh = 0, bm = 0;
+                if (lane == 0) { if (mh) bh = atomicAdd(&b.split[2 * (bounce + 1)], __popc(mh)); if (mm) bm = atomicAdd(&b.split[2 * (bounce + 1) + 1], __popc(mm)); }
+                bh = __shfl_sync(0xffffffffu, bh, 0); bm = __shfl_sync(0xffffffffu, bm, 0);
+                const unsigned lt = (1u << lane) - 1u;
+                if (isH) b.order[bh + __popc(mh & lt)] = i;
+                if (isM) b.order[n_ext - 1 - (bm + __popc(mm & lt))] = i;
+            }
         }
         if (i0 + 31 >= n_ext) {
             const int slot = i - n_ext;
@@ -915,7 +927,7 @@ __global__ void k_material_probe(const float *mat28, float wavelen, V3 wo, V3 wi
 static inline int cdiv(long long a, int b) { return (int)((a + b - 1) / b); }
 
 /* persistent grids: SM count x resident CTAs per SM of each kernel (queried once per device) */
-struct GridSizes { int trace = 0, shade = 0, refill = 0, sl = 0, sb = 0, sc = 0; int mode = 0, split_bounces = 0, nb = 0, bars = 0, shade_threads = 256, oct = 1, adaptive = 1, sms = 148, tail_max = 8192, tail_items = 128, profile_tail = 0; };
+struct GridSizes { int trace = 0, shade = 0, refill = 0, sl = 0, sb = 0, sc = 0; int mode = 0, split_bounces = 0, nb = 0, bars = 0, shade_threads = 256, oct = 1, adaptive = 1, sms = 148, tail_max = 8192, tail_items = 128, profile_tail = 0, order = 1; };
 static GridSizes grid_sizes() {
     static GridSizes g[64];
     int dev = 0; cudaGetDevice(&dev);
@@ -935,6 +947,7 @@ static GridSizes grid_sizes() {
         const char *gsh = getenv("LYS_SHADE_GRID_PCT"); if (gsh && atoi(gsh) > 0) g[dev].shade = max(sms, g[dev].shade * atoi(gsh) / 100);
         const char *e = getenv("LYS_TRACE_MODE"); g[dev].mode = (e && atoi(e) == 1) ? 1 : 0;
         g[dev].sms = sms;
+        const char *ord = getenv("LYS_SHADE_ORDER"); if (ord) g[dev].order = atoi(ord) ? 1 : 0;      /* 0: k_shade walks the slots in queue order */
         const char *tit = getenv("LYS_TAIL_ITEMS"); if (tit && atoi(tit) > 0) g[dev].tail_items = atoi(tit);
         const char *ptl = getenv("LYS_PROFILE_TAIL"); if (ptl) g[dev].profile_tail = atoi(ptl) ? 1 : 0;
         const char *tmx = getenv("LYS_TAIL_MAX"); if (tmx) g[dev].tail_max = atoi(tmx);          /* 0: no fused tail */
@@ -1004,9 +1017,10 @@ cudaError_t run_sample_pass(const SceneDev &sc, const FrameParams &fp, PassBuffe
             k_shade_cont<<<min(gs.sc, cdiv(n, 128)), 128, 0, stream>>>(sc, fp, bufs, bnc, nlights > 0 ? 1 : 0);
         } else {
             const int g = sized(have_est ? est[bnc] : 0, gs.shade_threads, g_shade);
-            if (gs.shade_threads == 512) k_shade<512><<<g, 512, 0, stream>>>(sc, fp, bufs, bnc, gs.bars);
-            else if (gs.shade_threads == 128) k_shade<128><<<g, 128, 0, stream>>>(sc, fp, bufs, bnc, gs.bars);
-            else k_shade<256><<<g, 256, 0, stream>>>(sc, fp, bufs, bnc, gs.bars);
+            const int fl = gs.bars | ((gs.order && !gs.mode && bnc > 0) ? 4 : 0);       /* bit 2: follow b.order (written by k_trace, not by the refill variant) */
+            if (gs.shade_threads == 512) k_shade<512><<<g, 512, 0, stream>>>(sc, fp, bufs, bnc, fl);
+            else if (gs.shade_threads == 128) k_shade<128><<<g, 128, 0, stream>>>(sc, fp, bufs, bnc, fl);
+            else k_shade<256><<<g, 256, 0, stream>>>(sc, fp, bufs, bnc, fl);
         }
         tm.end(stream); nl++;
         tm.begin(1, stream);
