@@ -210,13 +210,13 @@ void grid_dims(const futhark_opaque_state *s, uint32_t &gw, uint32_t &gh) {     
 bool ensure_bufs(futhark_context *ctx, PassBuffers &b, int64_t n, bool probes) {
     if (b.cap < n) {
         raw_free(b.ray_o[0]); raw_free(b.ray_o[1]); raw_free(b.ray_d[0]); raw_free(b.ray_d[1]); raw_free(b.dist[0]); raw_free(b.dist[1]); raw_free(b.acc);
-        raw_free(b.chan); raw_free(b.queue[0]); raw_free(b.queue[1]); raw_free(b.hit); raw_free(b.order); raw_free(b.sh_o); raw_free(b.sh_d1); raw_free(b.sh_d2);
+        raw_free(b.chan); raw_free(b.queue[0]); raw_free(b.queue[1]); raw_free(b.hit); raw_free(b.order[0]); raw_free(b.order[1]); raw_free(b.sh_o); raw_free(b.sh_d1); raw_free(b.sh_d2);
         raw_free(b.sh_c); raw_free(b.tmp_a); raw_free(b.tmp_b); raw_free(b.probe_rad); raw_free(b.probe_dist);
         b.cap = 0;
         size_t c = (size_t)n;
         if (!raw_alloc(ctx, b.ray_o[0], c) || !raw_alloc(ctx, b.ray_o[1], c) || !raw_alloc(ctx, b.ray_d[0], c) || !raw_alloc(ctx, b.ray_d[1], c) ||
             !raw_alloc(ctx, b.dist[0], c) || !raw_alloc(ctx, b.dist[1], c) || !raw_alloc(ctx, b.acc, c) || !raw_alloc(ctx, b.chan, c) ||
-            !raw_alloc(ctx, b.queue[0], c) || !raw_alloc(ctx, b.queue[1], c) || !raw_alloc(ctx, b.hit, c) || !raw_alloc(ctx, b.order, c) || !raw_alloc(ctx, b.sh_o, c) ||
+            !raw_alloc(ctx, b.queue[0], c) || !raw_alloc(ctx, b.queue[1], c) || !raw_alloc(ctx, b.hit, c) || !raw_alloc(ctx, b.order[0], c) || !raw_alloc(ctx, b.order[1], c) || !raw_alloc(ctx, b.sh_o, c) ||
             !raw_alloc(ctx, b.sh_d1, c) || !raw_alloc(ctx, b.sh_d2, c) || !raw_alloc(ctx, b.sh_c, c) || !raw_alloc(ctx, b.tmp_a, c) || !raw_alloc(ctx, b.tmp_b, c)) return false;
         b.cap = n;
     }
@@ -234,7 +234,7 @@ bool ensure_bufs(futhark_context *ctx, PassBuffers &b, int64_t n, bool probes) {
 bool ensure_pass_buffers(futhark_context *ctx, int64_t n, bool probes) { return ensure_bufs(ctx, ctx->bufs, n, probes); }
 void free_bufs(PassBuffers &b, bool owns_tx) {
     raw_free(b.ray_o[0]); raw_free(b.ray_o[1]); raw_free(b.ray_d[0]); raw_free(b.ray_d[1]); raw_free(b.dist[0]); raw_free(b.dist[1]); raw_free(b.acc);
-    raw_free(b.chan); raw_free(b.queue[0]); raw_free(b.queue[1]); raw_free(b.hit); raw_free(b.order); raw_free(b.sh_o); raw_free(b.sh_d1); raw_free(b.sh_d2);
+    raw_free(b.chan); raw_free(b.queue[0]); raw_free(b.queue[1]); raw_free(b.hit); raw_free(b.order[0]); raw_free(b.order[1]); raw_free(b.sh_o); raw_free(b.sh_d1); raw_free(b.sh_d2);
     raw_free(b.sh_c); raw_free(b.tmp_a); raw_free(b.tmp_b); raw_free(b.counts); raw_free(b.stats); raw_free(b.split); raw_free(b.probe_rad); raw_free(b.probe_dist);
     if (owns_tx) raw_free(b.tx_lights);
     b.cap = 0;

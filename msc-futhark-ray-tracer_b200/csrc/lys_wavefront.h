@@ -44,8 +44,9 @@ struct PassBuffers {
     uint8_t *chan = nullptr;
     int *queue[2] = {nullptr, nullptr};
     int *hit = nullptr;         /* per slot: sorted-leaf index or -1 */
-    int *order = nullptr;       /* processing order of k_shade: the slots of the current bounce, hits first (from the front),
-                                   misses last (from the back), written by k_trace with the hits; warps of k_shade are then all-hit or all-miss */
+    int *order[2] = {nullptr, nullptr};   /* processing order (ping-pong per bounce): the slots of a bounce, hits first (from the front),
+                                   misses last (from the back), written by k_trace with the hits; k_shade and the shadow-ray
+                                   part of k_trace walk it, so their warps are all-hit or all-miss */
     int *split = nullptr;       /* [2][LYS_MAX_PATH_LEN + 1] hits / misses appended per bounce */
     float4 *sh_o = nullptr;     /* per slot: shadow origin.xyz | flags (bit0 ray1, bit1 ray2) */
     float4 *sh_d1 = nullptr;    /* dir1.xyz | tmax1 */

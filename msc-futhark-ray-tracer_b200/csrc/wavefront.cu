@@ -401,7 +401,7 @@ __global__ void __launch_bounds__(SHADE_THREADS, LYS_SHADE_MINB(SHADE_THREADS)) 
     const int nl = fp.n_scene_lights + ((fp.tx_kind == 0) ? 0 : 8);
     for (int b0 = blockIdx.x * blockDim.x; b0 < count; b0 += stride) {
         const bool valid = b0 + (int)threadIdx.x < count;
-        const int i = !valid ? 0 : (bars & 4) ? b.order[b0 + threadIdx.x] : b0 + (int)threadIdx.x;      /* hits first: warps are all-hit or all-miss */
+        const int i = !valid ? 0 : (bars & 4) ? b.order[bounce & 1][b0 + threadIdx.x] : b0 + (int)threadIdx.x;      /* hits first: warps are all-hit or all-miss */
         bool alive = false, hit = false; int pid = -1; unsigned n_vert = 0, n_shadow = 0;
         float4 next_o = make_float4(0.0f, 0.0f, 0.0f, 0.0f), next_d = next_o; float next_dist = 0.0f;
         VertexCtx v;
@@ -651,7 +651,7 @@ __global__ void __launch_bounds__(128) k_trace_refill(SceneDev sc, const __grid_
 #define LYS_TRACE_MINB 10     /* <= 51 registers: 10 CTAs of 128 threads per SM */
 #endif
 template <int NB, bool OCT>
-__global__ void __launch_bounds__(128, LYS_TRACE_MINB) k_trace(SceneDev sc, const __grid_constant__ FrameParams fp, PassBuffers b, int bounce) {
+__global__ void __launch_bounds__(128, LYS_TRACE_MINB) k_trace(SceneDev sc, const __grid_constant__ FrameParams fp, PassBuffers b, int bounce, int ordered) {
     const int n_ext = (bounce + 1 < fp.path_len) ? b.counts[bounce + 1] : 0;
     const int n_con = (bounce >= 0) ? b.counts[bounce] : 0;
     const int total = n_ext + n_con;
@@ -670,19 +670,20 @@ __global__ void __launch_bounds__(128, LYS_TRACE_MINB) k_trace(SceneDev sc, cons
             int h = traverse<false, NB, OCT>(nodes, sc.leaf_tri, n_nodes, is_ext, v3(ro.x, ro.y, ro.z), v3(rd.x, rd.y, rd.z), FLT_MAX, t);
             if (is_ext) b.hit[i] = h;
             /* processing order of shade(bounce + 1): hits from the front, misses from the back (one atomic per warp and kind) */
-            if (bounce >= 0) {                 /* not for camera rays: their misses are whole warps already, shade(0) walks the slots in order */
+            if (ordered) {                     /* not for camera rays (their misses are whole warps already: shade(0) walks the slots in order) */
                 const bool isH = is_ext && h >= 0, isM = is_ext && h < 0;
                 const unsigned mh = __ballot_sync(0xffffffffu, isH), mm = __ballot_sync(0xffffffffu, isM);
                 int bh = 0, bm = 0;
                 if (lane == 0) { if (mh) bh = atomicAdd(&b.split[2 * (bounce + 1)], __popc(mh)); if (mm) bm = atomicAdd(&b.split[2 * (bounce + 1) + 1], __popc(mm)); }
                 bh = __shfl_sync(0xffffffffu, bh, 0); bm = __shfl_sync(0xffffffffu, bm, 0);
                 const unsigned lt = (1u << lane) - 1u;
-                if (isH) b.order[bh + __popc(mh & lt)] = i;
-                if (isM) b.order[n_ext - 1 - (bm + __popc(mm & lt))] = i;
+                if (isH) b.order[(bounce + 1) & 1][bh + __popc(mh & lt)] = i;
+                if (isM) b.order[(bounce + 1) & 1][n_ext - 1 - (bm + __popc(mm & lt))] = i;
             }
         }
         if (i0 + 31 >= n_ext) {
-            const int slot = i - n_ext;
+            /* vertices of this bounce in the order shade(bounce) took them: hit vertices (shadow rays) first, miss vertices last */
+            const int slot = !is_con ? 0 : (ordered && bounce >= 1) ? b.order[bounce & 1][i - n_ext] : i - n_ext;
             float4 ro = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(4)), rc = ro;
             if (is_con) { ro = b.sh_o[slot]; rc = b.sh_c[slot]; }
             const int flags = __float_as_int(ro.w);
@@ -968,10 +969,11 @@ static void launch_trace(const GridSizes &gs0, int grid, const SceneDev &sc, con
     /* box stages per loop iteration: 2 for small, cache-resident trees (issue bound: fewer, fuller iterations), 1 for large
      * ones (two dependent node loads per lock-step iteration cost more than they save); measured in profiles/README.md 4.5 */
     if (gs.nb == 0) gs.nb = (sc.n_tris <= 4096) ? 2 : 1;
-    if (gs.mode) k_trace_refill<<<grid, 128, 0, stream>>>(sc, fp, bufs, bounce);
-    else if (sc.nodes_oct && gs.oct) { if (gs.nb == 1) k_trace<1, true><<<grid, 128, 0, stream>>>(sc, fp, bufs, bounce); else k_trace<2, true><<<grid, 128, 0, stream>>>(sc, fp, bufs, bounce); }
-    else if (gs.nb == 1) k_trace<1, false><<<grid, 128, 0, stream>>>(sc, fp, bufs, bounce);
-    else k_trace<2, false><<<grid, 128, 0, stream>>>(sc, fp, bufs, bounce);
+    if (gs.mode) { k_trace_refill<<<grid, 128, 0, stream>>>(sc, fp, bufs, bounce); return; }
+    const int ordered = (gs.order && bounce >= 0) ? 1 : 0;      /* write the hits-first order of bounce + 1, walk the one of bounce */
+    if (sc.nodes_oct && gs.oct) { if (gs.nb == 1) k_trace<1, true><<<grid, 128, 0, stream>>>(sc, fp, bufs, bounce, ordered); else k_trace<2, true><<<grid, 128, 0, stream>>>(sc, fp, bufs, bounce, ordered); }
+    else if (gs.nb == 1) k_trace<1, false><<<grid, 128, 0, stream>>>(sc, fp, bufs, bounce, ordered);
+    else k_trace<2, false><<<grid, 128, 0, stream>>>(sc, fp, bufs, bounce, ordered);
 }
 cudaError_t run_sample_pass(const SceneDev &sc, const FrameParams &fp, PassBuffers &bufs, cudaStream_t stream, uint64_t *launches, LaunchTimer *timer,
                             int *est_counts) {
