@@ -928,7 +928,7 @@ __global__ void k_material_probe(const float *mat28, float wavelen, V3 wo, V3 wi
 static inline int cdiv(long long a, int b) { return (int)((a + b - 1) / b); }
 
 /* persistent grids: SM count x resident CTAs per SM of each kernel (queried once per device) */
-struct GridSizes { int trace = 0, shade = 0, refill = 0, sl = 0, sb = 0, sc = 0; int mode = 0, split_bounces = 0, nb = 0, bars = 0, shade_threads = 256, oct = 1, adaptive = 1, sms = 148, tail_max = 8192, tail_items = 128, profile_tail = 0, order = 1; };
+struct GridSizes { int trace = 0, shade = 0, refill = 0, sl = 0, sb = 0, sc = 0; int mode = 0, split_bounces = 0, nb = 0, bars = 0, shade_threads = 256, oct = 1, adaptive = 1, sms = 148, tail_max = 8192, tail_items = 128, profile_tail = 0, order = 1, tail_min = 148; };
 static GridSizes grid_sizes() {
     static GridSizes g[64];
     int dev = 0; cudaGetDevice(&dev);
@@ -949,6 +949,8 @@ static GridSizes grid_sizes() {
         const char *e = getenv("LYS_TRACE_MODE"); g[dev].mode = (e && atoi(e) == 1) ? 1 : 0;
         g[dev].sms = sms;
         const char *ord = getenv("LYS_SHADE_ORDER"); if (ord) g[dev].order = atoi(ord) ? 1 : 0;      /* 0: k_shade walks the slots in queue order */
+        g[dev].tail_min = sms;
+        const char *tmn = getenv("LYS_TAIL_MIN_CTAS"); if (tmn && atoi(tmn) > 0) g[dev].tail_min = atoi(tmn);
         const char *tit = getenv("LYS_TAIL_ITEMS"); if (tit && atoi(tit) > 0) g[dev].tail_items = atoi(tit);
         const char *ptl = getenv("LYS_PROFILE_TAIL"); if (ptl) g[dev].profile_tail = atoi(ptl) ? 1 : 0;
         const char *tmx = getenv("LYS_TAIL_MAX"); if (tmx) g[dev].tail_max = atoi(tmx);          /* 0: no fused tail */
@@ -1030,7 +1032,7 @@ cudaError_t run_sample_pass(const SceneDev &sc, const FrameParams &fp, PassBuffe
         tm.end(stream); nl++;
     }
     if (b_tail < fp.path_len) {
-        const int g = (int)max((long long)gs.sms, min((long long)gs.sms * 4, (long long)((est[b_tail] + est[b_tail] / 4 + gs.tail_items - 1) / gs.tail_items)));   /* few, well filled CTAs (they stay resident for all the remaining bounces), never fewer than one per SM: a stale estimate must not serialise a long queue */
+        const int g = (int)max((long long)gs.tail_min, min((long long)gs.sms * 4, (long long)((est[b_tail] + est[b_tail] / 4 + gs.tail_items - 1) / gs.tail_items)));   /* few, well filled CTAs (they stay resident for all the remaining bounces), never fewer than one per SM: a stale estimate must not serialise a long queue */
         tm.cur_bounce = b_tail;
         tm.begin(3, stream);
         if (sc.nodes_oct && gs.oct) k_tail<true><<<g, 128, 0, stream>>>(sc, fp, bufs, b_tail);
