@@ -399,6 +399,8 @@ __global__ void __launch_bounds__(SHADE_THREADS, LYS_SHADE_MINB(SHADE_THREADS)) 
     const int count = b.counts[bounce];
     const int stride = gridDim.x * blockDim.x;
     const int nl = fp.n_scene_lights + ((fp.tx_kind == 0) ? 0 : 8);
+    if (threadIdx.x == 0) sh.qn = 0;
+    __syncthreads();
     for (int b0 = blockIdx.x * blockDim.x; b0 < count; b0 += stride) {
         const bool valid = b0 + (int)threadIdx.x < count;
         const int i = !valid ? 0 : (bars & 4) ? b.order[bounce & 1][b0 + threadIdx.x] : b0 + (int)threadIdx.x;      /* hits first: warps are all-hit or all-miss */
@@ -408,7 +410,6 @@ __global__ void __launch_bounds__(SHADE_THREADS, LYS_SHADE_MINB(SHADE_THREADS)) 
         float cL = 0.0f, cB = 0.0f; int flags = 0;
         float4 rec_d1 = make_float4(0.0f, 0.0f, 0.0f, 0.0f), rec_d2 = rec_d1;
         LightD l;
-        if (threadIdx.x == 0) sh.qn = 0;
         if (valid) hit = shade_prologue(sc, b, bounce, i, v);
         const bool lit = hit && nl > 0;
         if (bars & 1) __syncthreads();                                    /* lockstep only (instruction cache) */
@@ -428,6 +429,7 @@ __global__ void __launch_bounds__(SHADE_THREADS, LYS_SHADE_MINB(SHADE_THREADS)) 
             shade_put_sample(sh, slot, sample_reflection(v3(sh.res[0][slot], sh.res[1][slot], sh.res[2][slot]), m, rng));
         }
         __syncthreads();
+        if (threadIdx.x == 0) sh.qn = 0;        /* queue drained: empty it for the next iteration (ordered by the barrier that ends this one) */
         if (lit) {
             DirSample s = shade_get_sample(sh, threadIdx.x);
             if (metal1) s.bsdf = v.m.color * s.bsdf;                      /* metal :352-355 */
