@@ -709,6 +709,37 @@ __global__ void __launch_bounds__(128, LYS_TRACE_MINB) k_trace(SceneDev sc, cons
     }
 }
 
+/* ------------------------------------------------------------------ generate + trace(-1) in one launch
+ * The camera ray of a pixel goes straight from the registers into the traversal loop: one launch less per pass and no
+ * read-back of the 32-byte ray records just written (k_shade(0) still needs them, so they are written once). */
+template <int NB, bool OCT>
+__global__ void __launch_bounds__(128, LYS_TRACE_MINB) k_generate_trace(SceneDev sc, const __grid_constant__ FrameParams fp, PassBuffers b) {
+    const int pid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pid == 0) {
+        b.counts[0] = fp.n_local;
+        for (int k = 1; k <= LYS_MAX_PATH_LEN; k++) b.counts[k] = 0;
+        for (int k = 0; k < 2 * (LYS_MAX_PATH_LEN + 1); k++) b.split[k] = 0;
+    }
+    const bool act = pid < fp.n_local;                     /* no early return: traverse<> votes per warp */
+    V3 o = v3(0.0f, 0.0f, 0.0f), d = v3(1.0f, 1.0f, 1.0f);
+    if (act) {
+        int col, row; int ix = local_to_pixel(fp, pid, col, row);
+        uint32_t rng = fp.frame_rng ^ rng_split_hash((uint32_t)ix);   /* split_rng integrator.fut:109-114 */
+        float wl; int ch;
+        camera_sample(fp, col, row, rng, o, d, wl, ch);
+        b.ray_o[0][pid] = make_float4(o.x, o.y, o.z, wl);          /* bounce 0: slot == path id */
+        b.ray_d[0][pid] = make_float4(d.x, d.y, d.z, __uint_as_float(rng));
+        b.dist[0][pid] = 0.0f;
+        b.acc[pid] = make_float4(0.0f, 0.0f, LYS_INF, 0.0f);
+        b.chan[pid] = (uint8_t)ch;
+        b.queue[0][pid] = pid;
+        if (b.probe_rad) for (int k = 0; k < LYS_MAX_PATH_LEN; k++) { b.probe_rad[(size_t)pid * 16 + k] = 0.0f; b.probe_dist[(size_t)pid * 16 + k] = LYS_INF; }
+    }
+    float t;
+    const int h = traverse<false, NB, OCT>(OCT ? sc.nodes_oct : sc.nodes, sc.leaf_tri, (int)sc.n_tris - 1, act, o, d, FLT_MAX, t);
+    if (act) b.hit[pid] = h;
+}
+
 /* ------------------------------------------------------------------ tail: all remaining bounces in one launch
  * Past the first few bounces a pass carries a fraction of a percent of its paths, but every bounce still costs two
  * launches (measured: ~2.3 us of GPU throughput each, whatever the grid size; profiles/README.md 4.6).  k_tail runs
@@ -930,7 +961,7 @@ __global__ void k_material_probe(const float *mat28, float wavelen, V3 wo, V3 wi
 static inline int cdiv(long long a, int b) { return (int)((a + b - 1) / b); }
 
 /* persistent grids: SM count x resident CTAs per SM of each kernel (queried once per device) */
-struct GridSizes { int trace = 0, shade = 0, refill = 0, sl = 0, sb = 0, sc = 0; int mode = 0, split_bounces = 0, nb = 0, bars = 0, shade_threads = 256, oct = 1, adaptive = 1, sms = 148, tail_max = 8192, tail_items = 128, profile_tail = 0, order = 1, tail_min = 148; };
+struct GridSizes { int trace = 0, shade = 0, refill = 0, sl = 0, sb = 0, sc = 0; int mode = 0, split_bounces = 0, nb = 0, bars = 0, shade_threads = 256, oct = 1, adaptive = 1, sms = 148, tail_max = 8192, tail_items = 128, profile_tail = 0, order = 1, tail_min = 148, fuse_gen = 1; };
 static GridSizes grid_sizes() {
     static GridSizes g[64];
     int dev = 0; cudaGetDevice(&dev);
@@ -953,6 +984,7 @@ static GridSizes grid_sizes() {
         const char *ord = getenv("LYS_SHADE_ORDER"); if (ord) g[dev].order = atoi(ord) ? 1 : 0;      /* 0: k_shade walks the slots in queue order */
         g[dev].tail_min = sms;
         const char *tmn = getenv("LYS_TAIL_MIN_CTAS"); if (tmn && atoi(tmn) > 0) g[dev].tail_min = atoi(tmn);
+        const char *fg = getenv("LYS_FUSE_GENERATE"); if (fg) g[dev].fuse_gen = atoi(fg) ? 1 : 0;    /* 0: k_generate and k_trace(-1) as two launches */
         const char *tit = getenv("LYS_TAIL_ITEMS"); if (tit && atoi(tit) > 0) g[dev].tail_items = atoi(tit);
         const char *ptl = getenv("LYS_PROFILE_TAIL"); if (ptl) g[dev].profile_tail = atoi(ptl) ? 1 : 0;
         const char *tmx = getenv("LYS_TAIL_MAX"); if (tmx) g[dev].tail_max = atoi(tmx);          /* 0: no fused tail */
@@ -1006,11 +1038,20 @@ cudaError_t run_sample_pass(const SceneDev &sc, const FrameParams &fp, PassBuffe
     int b_tail = fp.path_len;
     if (have_est && gs.tail_max > 0 && !gs.mode && !(tm.on && !gs.profile_tail))      /* per-class timing wants every ray in the trace class */
         for (int k = 1; k < fp.path_len; k++) if (est[k] <= gs.tail_max) { b_tail = k; break; }
-    tm.begin(0, stream); k_generate<<<cdiv(n, 256), 256, 0, stream>>>(fp, bufs); tm.end(stream); nl++;
-    tm.cur_bounce = -1;
-    tm.begin(1, stream);
-    launch_trace(gs, g_trace, sc, fp, bufs, -1, stream);
-    tm.end(stream); nl++;
+    if (gs.fuse_gen && !gs.mode && !tm.on) {                /* per-class timing keeps the two launches apart */
+        const int nb = gs.nb ? gs.nb : ((sc.n_tris <= 4096) ? 2 : 1);
+        const int g = cdiv(n, 128);
+        if (sc.nodes_oct && gs.oct) { if (nb == 1) k_generate_trace<1, true><<<g, 128, 0, stream>>>(sc, fp, bufs); else k_generate_trace<2, true><<<g, 128, 0, stream>>>(sc, fp, bufs); }
+        else if (nb == 1) k_generate_trace<1, false><<<g, 128, 0, stream>>>(sc, fp, bufs);
+        else k_generate_trace<2, false><<<g, 128, 0, stream>>>(sc, fp, bufs);
+        nl++;
+    } else {
+        tm.begin(0, stream); k_generate<<<cdiv(n, 256), 256, 0, stream>>>(fp, bufs); tm.end(stream); nl++;
+        tm.cur_bounce = -1;
+        tm.begin(1, stream);
+        launch_trace(gs, g_trace, sc, fp, bufs, -1, stream);
+        tm.end(stream); nl++;
+    }
     for (int bnc = 0; bnc < b_tail; bnc++) {
         tm.cur_bounce = bnc;
         tm.begin(2, stream);

@@ -296,6 +296,7 @@ def test_million_triangle_bvh(orc, pkg, gpu, scenes):
     {'LYS_TRACE_NB': '1'},             # one box stage per loop iteration
     {'LYS_SHADE_THREADS': '512'}, {'LYS_SHADE_THREADS': '128'}, {'LYS_SHADE_BARS': '3'},
     {'LYS_SHADE_ORDER': '0'},          # k_shade walks the queue in slot order instead of hits first
+    {'LYS_FUSE_GENERATE': '0'},        # k_generate and k_trace(-1) as two launches
     {'LYS_TAIL_MAX': '0'},             # no fused tail kernel: one launch per stage and bounce
     {'LYS_TAIL_MAX': '100000000'},     # fused tail from bounce 1 on (every queue is 'short')
     {'LYS_TAIL_MAX': '100000000', 'LYS_TRACE_OCT': '0'},
