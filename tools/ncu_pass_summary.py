@@ -32,7 +32,7 @@ def table(last):
         us = m.get('gpu__time_duration.sum', 0.0) / 1000.0
         mb = (m.get('dram__bytes_read.sum', 0.0) + m.get('dram__bytes_write.sum', 0.0)) / 1e6
         tot_us += us
-        if n.startswith('k_trace'):
+        if n.startswith('k_trace') or n.startswith('k_generate_trace'):      # the camera-ray launch carries trace(-1)
             tr.append((us, mb * 1e6))
         lines.append(f"| {i} | {n} | {us:.1f} | {mb:.1f} | {m.get('smsp__inst_executed.sum', 0.0) / 1e6:.1f} | {m.get('smsp__thread_inst_executed_per_inst_executed.ratio', 0.0):.1f} |")
     share = sum(u for u, _ in tr) / tot_us
