@@ -2,17 +2,18 @@
  *
  * Replaces the per-pixel megakernel the Futhark compiler generates for `sample_pixels`
  * (reference src/integrator.fut:103-116, one thread running `path_trace` :27-76 to completion) by
- * queue-driven stages, one launch per stage and bounce:
- *   k_generate   camera.fut:68-110, integrator.fut:78-93,109-115   wavelength + primary ray per pixel
- *   k_trace      bvh.fut:123-145 (closest_hit), bvh.fut:149-167 (any_hit): extend of bounce b+1 and connect of
- *                bounce b in ONE persistent launch (grid = SMs x resident CTAs, grid-stride over device-side counts)
- *   k_shade      integrator.fut:46-76, direct.fut:32-122, material.fut   vertex shading; emits <= 2
- *                                                                   shadow rays, the continuation ray,
- *                                                                   and compacts live paths (warp ballot)
- *   connect_item direct.fut:7-15 + bvh.fut:149-167 (any_hit)        shadow rays, radiance accumulation (inside k_trace)
- *   k_accumulate integrator.fut:133-192                             channel resolve + running average
- *   k_render     lib.fut:187-196                                    upscale + ARGB pack
- * Per-path arithmetic is the reference's, operation for operation; only the scheduling differs.
+ * queue-driven stages:
+ *   k_generate_trace  camera.fut:68-110, integrator.fut:78-93,109-115   wavelength + camera ray per pixel, and its closest hit
+ *   k_shade(b)        integrator.fut:46-76, direct.fut:32-122, material.fut   vertex shading; emits <= 2 shadow rays and the
+ *                                                                   continuation ray, compacts live paths (warp ballot)
+ *   k_trace(b)        bvh.fut:123-145 (closest_hit) of bounce b+1 and direct.fut:7-15 + bvh.fut:149-167 (any_hit) of the
+ *                     shadow rays of bounce b, with the radiance accumulation, in ONE persistent launch
+ *                     (grid = SMs x resident CTAs, warp-uniform grid-stride over device-side counts)
+ *   k_tail(b0)        all bounces from the first sparse one on in one launch (CTA-local wavefront)
+ *   k_accumulate      integrator.fut:133-192                             channel resolve + running average
+ *   k_render          lib.fut:187-196                                    upscale + ARGB pack
+ * Per-path arithmetic is the reference's, operation for operation; only the scheduling differs.  Kept selectable and
+ * parity-tested, slower: k_generate + k_trace(-1) as two launches, k_trace_refill, the phase-split shading kernels.
  */
 #include "lys_wavefront.h"
 #include <cstdio>
@@ -201,11 +202,10 @@ LYS_D float incident_radiance(const LightD &l, V3 hitp, V3 lightp) {
 LYS_D float balance1(float pf, float pg) { return 1.0f * pf / (1.0f * pf + 1.0f * pg); }   /* direct.fut:56-58, nf = ng = 1 */
 
 /* ------------------------------------------------------------------ shade
- * One vertex = prologue (re-intersection, material, frame) + light sample + BSDF-MIS sample + continuation.
- * The monolithic kernel k_shade runs all of it; its executed code (~43 KB of SASS) does not fit the instruction
- * cache and it stalls on instruction fetch (profiles/README.md 4.2).  For the populated early bounces the work is
- * therefore also available as three phase kernels (k_shade_light / k_shade_bsdf / k_shade_cont) that each redo the
- * small prologue and exchange their partial results through per-slot scratch; arithmetic is identical. */
+ * One vertex = prologue (t of the winning leaf, material, frame) + light sample + BSDF-MIS sample + continuation.
+ * k_shade runs all of it (see its header for the CTA-level arrangements).  Three phase kernels (k_shade_light /
+ * k_shade_bsdf / k_shade_cont, LYS_SHADE_SPLIT) that each redo the small prologue and exchange partial results through
+ * per-slot scratch date from when the monolithic kernel was instruction-fetch bound; arithmetic is identical. */
 struct VertexCtx {
     int pid, leaf;
     V3 o, d, pos, n, wo, wo_l;
@@ -342,15 +342,16 @@ LYS_D void shade_compact(const PassBuffers &b, int bounce, bool alive, int pid, 
     if (lane == 0 && (vsum | ssum)) { atomicAdd(&b.stats[0], (unsigned long long)vsum); atomicAdd(&b.stats[2], (unsigned long long)ssum); }
 }
 
-/* monolithic: everything for one vertex in one thread, with two CTA-level arrangements (profiles/README.md 4.2, 4.5):
- *  - the kernel's code is larger than the instruction cache, so the warps of a CTA are kept in lockstep with block
- *    barriers between the phases (block-uniform loop) and fetch the same code lines together;
+/* monolithic: everything for one vertex in one thread, with these arrangements (profiles/README.md 4.2, 4.5):
  *  - the reflection branch of uber_sample_dir (material.fut:365-370) is taken by a few percent of the vertices of a
  *    dielectric scene, i.e. by one or two lanes of almost every warp, and costs ~560 instructions (sample_wh,
  *    Torrance-Sparrow terms).  Both sample_dir calls of a vertex therefore only DECIDE their branch in place
  *    (bsdf_choose); refraction samples are drawn in place, reflection samples are queued in shared memory and drawn
  *    after a barrier by the first threads of the CTA, one queue entry per thread (dense warps).  Same inputs, same
- *    arithmetic, another thread.  The rng state after a reflection sample is its two draws further (:283-286). */
+ *    arithmetic, another thread.  The rng state after a reflection sample is its two draws further (:283-286);
+ *  - for bounces >= 1 the slots are walked in the order k_trace left (hits first): warps are all-hit or all-miss;
+ *  - optional block barriers between the phases (bars bits 0, 1) kept the warps of a CTA fetching the same code while the
+ *    kernel was larger than the instruction cache with the reflection path inline in every warp; off by default now. */
 template <int T>
 struct ShadeShared {
     float res[6][2 * T];      /* slot k * T + tid: sample k of the thread (in: wo_l, roughness, rng; out: DirSample local) */
@@ -646,9 +647,10 @@ __global__ void __launch_bounds__(128) k_trace_refill(SceneDev sc, const __grid_
     }
 }
 
-/* The default variant: one item per thread and grid-stride iteration, plain traverse<> loops.  Measured on B200
- * (CornellBox 1080p) it beats the refill variant above, whose every refill stalls the warp on dependent
- * queue -> ray loads; the refill kernel is kept selectable (LYS_TRACE_MODE=1) and is parity-tested too. */
+/* The default variant: a warp owns 32 consecutive items per grid-stride step and runs the vote-synchronised traverse<>
+ * loops on them.  Measured on B200 (CornellBox 1080p) it beats the refill variant above, whose every refill stalls the
+ * warp on dependent queue -> ray loads; the refill kernel is kept selectable (LYS_TRACE_MODE=1) and is parity-tested too.
+ * `ordered` bit 0: append the slots of bounce + 1 to the hits-first order list and walk this bounce's vertices in theirs. */
 #ifndef LYS_TRACE_MINB
 #define LYS_TRACE_MINB 10     /* <= 51 registers: 10 CTAs of 128 threads per SM */
 #endif
