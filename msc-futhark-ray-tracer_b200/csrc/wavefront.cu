@@ -84,6 +84,9 @@ LYS_D bool leaf_test(const RayInv &r, const float4 *__restrict__ leaf_tri, int l
  * stack[0] holds the end marker: popping needs no empty check.  Visits, their order and every comparison are those
  * of the reference's walk (see above), only the interleaving between lanes differs. */
 #define TRAV_DONE ((int)0x80000000)
+#ifdef LYS_SMEM_STACK
+static __device__ __noinline__ int *trav_smem_stack() { __shared__ int s[LYS_SMEM_STACK * 128]; return s; }
+#endif
 template <bool ANY, int NB, bool OCT>
 LYS_D int traverse(const float4 *__restrict__ nodes, const float4 *__restrict__ leaf_tri, int n_nodes, bool active,
                    V3 o, V3 d, float tmax, float &t_hit) {
@@ -93,7 +96,16 @@ LYS_D int traverse(const float4 *__restrict__ nodes, const float4 *__restrict__ 
     asm volatile("" : "+l"(nbase));      /* keep the sum in a register pair: one IMAD.WIDE per node address */
     int stack[TRAV_STACK + 1];
     int closest = -1;
+#ifdef LYS_SMEM_STACK      /* experiment: the first LYS_SMEM_STACK levels of the stack in shared memory (128-thread CTAs), the rest local */
+    int *const ss = trav_smem_stack() + threadIdx.x;
+#define TRAV_PUSH(v) do { if (sp < LYS_SMEM_STACK) ss[sp * 128] = (v); else stack[sp - LYS_SMEM_STACK] = (v); sp++; } while (0)
+#define TRAV_POP() (--sp, (sp < LYS_SMEM_STACK) ? ss[sp * 128] : stack[sp - LYS_SMEM_STACK])
+    ss[0] = TRAV_DONE;
+#else
+#define TRAV_PUSH(v) (stack[sp++] = (v))
+#define TRAV_POP() (stack[--sp])
     stack[0] = TRAV_DONE;
+#endif
     int sp = 1;
     int cur = (active && n_nodes > 0) ? 0 : TRAV_DONE;   /* internal node to enter (>= 0), leaf pointer (~leaf) or TRAV_DONE */
     do {
@@ -103,15 +115,15 @@ LYS_D int traverse(const float4 *__restrict__ nodes, const float4 *__restrict__ 
                 const float4 *q = reinterpret_cast<const float4 *>(nbase + 32ull * (unsigned)cur);
                 float4 lo = __ldg(q), hi = __ldg(q + 1);
                 if (OCT ? slab_test_oct(r, lo, hi, tmax) : slab_test(r, lo, hi, tmax)) {
-                    stack[sp++] = __float_as_int(hi.w);       /* right child waits */
+                    TRAV_PUSH(__float_as_int(hi.w));          /* right child waits */
                     cur = __float_as_int(lo.w);               /* left child first */
-                } else cur = stack[--sp];
+                } else cur = TRAV_POP();
             }
         }
         if ((unsigned)cur > (unsigned)TRAV_DONE) {            /* a leaf pointer */
             float t;
             if (leaf_test(r, leaf_tri, ~cur, tmax, t)) { closest = ~cur; tmax = t; }
-            cur = (ANY && closest >= 0) ? TRAV_DONE : stack[--sp];      /* any_hit stops at the first hit (bvh.fut:152) */
+            cur = (ANY && closest >= 0) ? TRAV_DONE : TRAV_POP();       /* any_hit stops at the first hit (bvh.fut:152) */
         }
     } while (__any_sync(0xffffffffu, cur != TRAV_DONE));
     t_hit = tmax;
