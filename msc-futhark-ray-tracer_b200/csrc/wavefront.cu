@@ -975,7 +975,7 @@ __global__ void k_material_probe(const float *mat28, float wavelen, V3 wo, V3 wi
 static inline int cdiv(long long a, int b) { return (int)((a + b - 1) / b); }
 
 /* persistent grids: SM count x resident CTAs per SM of each kernel (queried once per device) */
-struct GridSizes { int trace = 0, shade = 0, refill = 0, sl = 0, sb = 0, sc = 0; int mode = 0, split_bounces = 0, nb = 0, bars = 0, shade_threads = 256, oct = 1, adaptive = 1, sms = 148, tail_max = 8192, tail_items = 128, profile_tail = 0, order = 1, tail_min = 148, fuse_gen = 1; };
+struct GridSizes { int trace = 0, shade = 0, refill = 0, sl = 0, sb = 0, sc = 0; int mode = 0, split_bounces = 0, nb = 0, bars = 0, shade_threads = 256, oct = 1, adaptive = 1, sms = 148, tail_max = 8192, tail_items = 128, profile_tail = 0, order = 1, tail_min = 148, fuse_gen = 1, dyn_grids = 0; };
 static GridSizes grid_sizes() {
     static GridSizes g[64];
     int dev = 0; cudaGetDevice(&dev);
@@ -998,6 +998,7 @@ static GridSizes grid_sizes() {
         const char *ord = getenv("LYS_SHADE_ORDER"); if (ord) g[dev].order = atoi(ord) ? 1 : 0;      /* 0: k_shade walks the slots in queue order */
         g[dev].tail_min = sms;
         const char *tmn = getenv("LYS_TAIL_MIN_CTAS"); if (tmn && atoi(tmn) > 0) g[dev].tail_min = atoi(tmn);
+        const char *dg = getenv("LYS_DYN_GRIDS"); if (dg) g[dev].dyn_grids = atoi(dg) & 3;      /* bit 0: k_trace, bit 1: k_shade launched with one item per thread when the queue length is known */
         const char *fg = getenv("LYS_FUSE_GENERATE"); if (fg) g[dev].fuse_gen = atoi(fg) ? 1 : 0;    /* 0: k_generate and k_trace(-1) as two launches */
         const char *tit = getenv("LYS_TAIL_ITEMS"); if (tit && atoi(tit) > 0) g[dev].tail_items = atoi(tit);
         const char *ptl = getenv("LYS_PROFILE_TAIL"); if (ptl) g[dev].profile_tail = atoi(ptl) ? 1 : 0;
@@ -1046,6 +1047,8 @@ cudaError_t run_sample_pass(const SceneDev &sc, const FrameParams &fp, PassBuffe
     const int g_min = max(1, gs.sms);                    /* never below one CTA per SM: a stale estimate costs at most ~10x on one pass */
     auto sized = [&](long long items, int threads, int g_full) {
         if (!have_est) return g_full;
+        const long long per_item = (items + items / 16 + 2048 + threads - 1) / threads;      /* one item per thread (+6 %): the hardware balances the CTAs */
+        if (gs.dyn_grids & ((threads == 128) ? 1 : 2)) return (int)max((long long)g_min, min(per_item, 1ll << 22));
         return (int)max((long long)g_min, min((long long)g_full, (2 * items + 4096 + threads - 1) / threads));
     };
     /* first bounce whose queue was short enough in the earlier pass: from there on one k_tail launch */
