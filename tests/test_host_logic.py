@@ -98,3 +98,23 @@ def test_path_len_knob(orc, scenes):
     finally:
         orc.set_path_len(16)
     assert bits_equal(short[..., :4], full[..., :4]) and not short[..., 5:].any()
+
+
+def test_roofline_traffic_matches_the_committed_ncu_list(tmp_path):
+    """bench.py's roofline.traffic comes from profiles/r1_k_trace_dram.json; that file must be what tools/ncu_pass_summary.py
+    derives from the committed ncu launch list (17 trace launches per pass, per-launch mean of DRAM read + write bytes)."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    md, js = tmp_path / 'x.md', tmp_path / 'x.json'
+    subprocess.check_call([sys.executable, os.path.join(root, 'tools', 'ncu_pass_summary.py'),
+                           os.path.join(root, 'profiles', 'r1_pass_launches_final.csv'), str(md), str(js)], stdout=subprocess.DEVNULL)
+    new, old = json.load(open(js)), json.load(open(os.path.join(root, 'profiles', 'r1_k_trace_dram.json')))
+    for seq in ('per_bounce_sequence', 'steady_state_sequence'):
+        assert new[seq]['launches_per_pass'] == old[seq]['launches_per_pass']
+        assert abs(new[seq]['dram_bytes_per_launch'] - old[seq]['dram_bytes_per_launch']) < 1.0
+    assert old['per_bounce_sequence']['launches_per_pass'] == 17
+    # algorithmic bytes per launch (bench.py) are an order of magnitude above the DRAM traffic: the BVH is cache resident
+    assert old['per_bounce_sequence']['dram_bytes_per_launch'] < 0.2 * 211e6
