@@ -107,3 +107,27 @@ def test_divergence_probes_are_consistent(orc, scenes):
     leaf, _ = s.closest_hits(r1)
     assert np.array_equal((pat == 3).any(axis=1), leaf >= 0)
     assert np.all(pat[:, 0] <= 1)                                       # every walk starts with the root's box
+
+
+def test_simt_model_tool_runs_and_orders_the_loop_shapes():
+    """tools/simt_model.py (the lock-step cost model behind the traversal loop shape) on a small frame: a loop that lets a lane
+    do a box visit and a triangle visit per iteration never needs more iterations than one visit per iteration, and the
+    while-while shape needs the fewest iterations of all (it is the instruction count that makes it the worst)."""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location('simt_model', os.path.join(root, 'tools', 'simt_model.py'))
+    sm = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(sm)
+    costs = {'B': 45, 'T': 60, 'loop': 6}
+    seen = 0
+    for b, r, pat, ln in sm.bounce_rays('cornell', 48, 64):
+        if len(r) < 64:
+            continue
+        base = np.arange(len(r))
+        it = {s: sm.schedule_cost(pat, ln, base, s, costs)[1] for s in ('X', 'BT', 'BBT', 'B*T')}
+        assert it['BT'] <= it['X'] and it['BBT'] <= it['BT'] and it['B*T'] <= it['BBT'], it
+        c_x, _ = sm.schedule_cost(pat, ln, base, 'X', costs)
+        assert c_x > 0
+        seen += 1
+    assert seen >= 2
