@@ -136,3 +136,198 @@ def test_spectrum_lookup(orc):
     assert L.orc_spectrum_lookup(1550.0, u) == np.float32(5.0)
     z = np.array([-1, 0] * 6, np.float32)
     assert L.orc_spectrum_lookup(500.0, z) == 0.0
+
+
+def test_hit_triangle_against_an_independent_restatement(orc, scenes):
+    """The oracle's closest hit over all triangles (orc_brute_force_hits: hit_triangle on every leaf, strictly smaller t wins)
+    against hit_triangle written here from reference src/shapes.fut:66-86 and src/common.fut:35 in numpy f32 (operand order of
+    athas/vector: dot = x*x' + y*y' + z*z' left to right; scale (1/a) v = (1/a) * each component):
+    hit / miss, the winning source triangle and the bits of t."""
+    F = np.float32
+    t9, tm, m = scenes['spectrumsphere']
+    tri = np.ascontiguousarray(t9, F).reshape(-1, 3, 3)
+    s = orc.State.init(t9, tm, m, 48, 64)
+    order = s.bvh()['src_index']                              # brute force walks the leaves in sorted order
+    rays = s.probe_primary(want_rays=True)['rays'].reshape(-1, 6)
+    rng = np.random.default_rng(3)
+    extra = np.concatenate([rng.uniform(-1, 1, (2000, 3)) + (0, 0.8, 0), rng.normal(0, 1, (2000, 3))], axis=1).astype(F)
+    extra[:, 3:] /= np.sqrt((extra[:, 3:].astype(np.float64) ** 2).sum(axis=1, keepdims=True)).astype(F)
+    rays = np.ascontiguousarray(np.concatenate([rays, extra]), F)
+    src_o, t_o = s.brute_force_hits(rays)
+
+    def dot(a, b):
+        return (a[..., 0] * b[..., 0] + a[..., 1] * b[..., 1]) + a[..., 2] * b[..., 2]
+
+    def cross(a, b):
+        return np.stack([a[..., 1] * b[..., 2] - a[..., 2] * b[..., 1], a[..., 2] * b[..., 0] - a[..., 0] * b[..., 2],
+                         a[..., 0] * b[..., 1] - a[..., 1] * b[..., 0]], axis=-1)
+
+    A, B, Cc = tri[order, 0], tri[order, 1], tri[order, 2]
+    e1, e2 = (B - A).astype(F), (Cc - A).astype(F)
+    n = cross(e1, e2).astype(F)
+    best_t = np.full(len(rays), np.inf, F)
+    best = np.full(len(rays), -1, np.int64)
+    o, d = rays[:, None, :3], rays[:, None, 3:]
+    with np.errstate(divide='ignore', invalid='ignore', over='ignore'):
+        a = -(dot(n[None], d))                                     # [rays][tris]
+        sv = (o - A[None]).astype(F)
+        mv = cross(sv, np.broadcast_to(d, sv.shape)).astype(F)
+        inv = (F(1) / a).astype(F)
+        t = inv * dot(n[None], sv)
+        u = inv * dot(mv, e2[None])
+        v = inv * (-(dot(mv, e1[None])))
+        ok = ~((a > F(-0.00001)) & (a < F(0.00001))) & (u >= 0) & (v >= 0) & (u + v <= 1) & (t < np.finfo(F).max) & (t > 0)
+    for k in range(len(order)):                                   # strictly smaller t wins, earlier leaf kept on ties
+        better = ok[:, k] & ((best < 0) | (t[:, k] < best_t))
+        best_t = np.where(better, t[:, k], best_t)
+        best = np.where(better, k, best)
+    src = np.where(best >= 0, order[np.maximum(best, 0)], -1)
+    assert np.array_equal(src, src_o)
+    hit = best >= 0
+    assert 0.2 < hit.mean() < 0.98
+    assert np.array_equal(best_t[hit].view(np.uint32), t_o[hit].view(np.uint32))
+
+
+def test_stackless_walk_against_an_independent_restatement(orc, scenes):
+    """closest_hit (reference src/bvh.fut:123-145: stackless, parent pointers, left first, strict t < tmax) and hit_aabb
+    (src/shapes.fut:114-135) written here in scalar numpy f32 straight from the .fut text, run on the oracle's own tree and boxes
+    (truncated refit included), against the oracle's walk: same leaf, same bits of t.  SpectrumSphere is the scene whose
+    truncated boxes do not enclose all their triangles, so the order of the decisions matters."""
+    F = np.float32
+    t9, tm, m = scenes['spectrumsphere']
+    tri = np.ascontiguousarray(t9, F).reshape(-1, 3, 3)
+    s = orc.State.init(t9, tm, m, 16, 20)
+    bv = s.bvh()
+    left, right, parent, box, order = bv['left'], bv['right'], bv['parent'], bv['node_aabb'], bv['src_index']
+    rays = s.probe_primary(want_rays=True)['rays'].reshape(-1, 6)
+    rng = np.random.default_rng(5)
+    extra = np.concatenate([rng.uniform(-0.8, 0.8, (120, 3)) + (0, 0.8, 0), rng.normal(0, 1, (120, 3))], axis=1).astype(F)
+    rays = np.ascontiguousarray(np.concatenate([rays, extra]), F)
+    leaf_o, t_o = s.closest_hits(rays)
+    HIGHEST = np.finfo(F).max
+    one, eps_far = F(1), F(0.001)
+
+    def hit_aabb(tmax, o, d, c, h):
+        mn, mx = c - h, c + h
+        tmin = F(0)
+        for a in range(3):
+            with np.errstate(divide='ignore', invalid='ignore', over='ignore'):
+                inv = one / d[a]
+                t0, t1 = (mn[a] - o[a]) * inv, (mx[a] - o[a]) * inv
+                if inv < 0:
+                    t0, t1 = t1, t0
+                t1 = t1 * (one + eps_far)
+            tmin, tmax = np.fmax(t0, tmin), np.fmin(t1, tmax)
+            if tmax <= tmin:
+                return False
+        return True
+
+    def dot(a, b):
+        return (a[0] * b[0] + a[1] * b[1]) + a[2] * b[2]
+
+    def cross(a, b):
+        return np.array([a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]], F)
+
+    def hit_triangle(tmax, o, d, k):
+        A, B, Cc = tri[order[k]]
+        e1, e2 = B - A, Cc - A
+        n = cross(e1, e2)
+        a = -(dot(n, d))
+        if a > F(-0.00001) and a < F(0.00001):
+            return None
+        sv = o - A
+        mv = cross(sv, d)
+        with np.errstate(divide='ignore', invalid='ignore', over='ignore'):
+            inv = one / a
+            t, u, v = inv * dot(n, sv), inv * dot(mv, e2), inv * (-(dot(mv, e1)))
+        if u >= 0 and v >= 0 and u + v <= 1 and t < tmax and t > 0:
+            return t
+        return None
+
+    for r, lo, to in zip(rays, leaf_o, t_o):
+        o, d = r[:3], r[3:]
+        closest, tmax, current, prev = -1, HIGHEST, 0, -1                  # prev: a child pointer (internal i, leaf ~i); the root's "prev" is internal -1
+        prev_is_root_marker = True
+        steps = 0
+        while current != -1:
+            steps += 1
+            assert steps < 10000
+            l, rr = int(left[current]), int(right[current])
+            came = None if prev_is_root_marker else prev
+            if came is not None and came == l:
+                child = rr
+            elif (came is None or came != rr) and hit_aabb(tmax, o, d, box[current, :3], box[current, 3:]):
+                child = l
+            else:
+                child = None
+            prev_is_root_marker = False
+            if child is None:
+                prev, current = current, int(parent[current])
+            elif child >= 0:
+                prev, current = current, child
+            else:
+                t = hit_triangle(tmax, o, d, ~child)
+                if t is not None:
+                    closest, tmax = ~child, t
+                prev = child
+        assert closest == lo
+        if closest >= 0:
+            t = hit_triangle(HIGHEST, o, d, closest)                        # the final re-intersection with the outer tmax
+            assert t is not None and np.float32(t).view(np.uint32) == to.view(np.uint32)
+    assert (leaf_o >= 0).mean() > 0.2
+
+
+@pytest.mark.parametrize('name', ['cornell', 'spectrumsphere', 'spectrumspherehigh'])
+def test_build_against_an_independent_restatement(orc, scenes, name):
+    """The whole BVH build of reference src/bvh.fut:86-121 restated here in numpy f32 from the .fut text -- triangle boxes
+    (shapes.fut:96-110), the left fold of containing_aabb from the {0, -inf} neutral, Morton codes of the normalised centres, a
+    stable sort by key, and `i32(log2 n) + 2` literal Jacobi sweeps from zero boxes over the oracle's tree topology -- against
+    the oracle's bounds, sorted keys, permutation and (truncated) node boxes, bit for bit."""
+    F = np.float32
+    t9, tm, m = scenes[name]
+    tri = np.ascontiguousarray(t9, F).reshape(-1, 3, 3)
+    n = len(tri)
+    bv = orc.State.init(t9, tm, m, 8, 8).bvh()
+
+    def contain(c1, h1, c2, h2):
+        mn = np.fmin(c1 - h1, c2 - h2)
+        mx = np.fmax(c1 + h1, c2 + h2)
+        c = F(0.5) * (mn + mx)
+        return c.astype(F), (mx - c).astype(F)
+
+    z = np.zeros((n, 3), F)
+    cb, hb = contain(tri[:, 1], z, tri[:, 2], z)                     # containing_aabb b c
+    c, h = contain(tri[:, 0], z, cb, hb)                             # containing_aabb a (...)
+    bc, bh = np.zeros(3, F), np.full(3, -np.inf, F)
+    for k in range(n):                                                # reduce on the c backend = sequential left fold
+        bc, bh = contain(bc, bh, c[k], h[k])
+    assert np.array_equal(np.concatenate([bc, bh]).view(np.uint32), bv['bounds'].view(np.uint32))
+    with np.errstate(divide='ignore', invalid='ignore'):
+        v = ((c - (bc - bh)) / (F(2) * bh)).astype(F)                 # normalise_position
+    s = np.fmin(v * F(1024), F(1023))
+    q = np.where(s > 0, s, 0).astype(np.uint32)                       # u32.f32 truncation
+
+    def expand(x):
+        x = (x * np.uint32(0x00010001)) & np.uint32(0xFF0000FF)
+        x = (x * np.uint32(0x00000101)) & np.uint32(0x0F00F00F)
+        x = (x * np.uint32(0x00000011)) & np.uint32(0xC30C30C3)
+        x = (x * np.uint32(0x00000005)) & np.uint32(0x49249249)
+        return x
+    with np.errstate(over='ignore'):
+        mort = expand(q[:, 0]) * np.uint32(4) + expand(q[:, 1]) * np.uint32(2) + expand(q[:, 2])
+    perm = np.argsort(mort, kind='stable')
+    assert np.array_equal(perm, bv['src_index'])
+    assert np.array_equal(mort[perm], bv['morton'])
+    # Jacobi refit on the oracle's topology (the topology itself is pinned by the Karras tests above)
+    left, right = bv['left'], bv['right']
+    lc, lh = c[perm], h[perm]
+    assert np.array_equal(np.concatenate([lc, lh], axis=1).view(np.uint32), bv['leaf_aabb'].view(np.uint32))
+    nc, nh = np.zeros((n - 1, 3), F), np.zeros((n - 1, 3), F)
+    li, ri = np.where(left >= 0, left, 0), np.where(right >= 0, right, 0)
+    ll, rl = np.where(left < 0, ~left, 0), np.where(right < 0, ~right, 0)
+    depth = int(np.float32(np.log2(np.float32(n)))) + 2
+    for _ in range(depth):
+        c1 = np.where((left >= 0)[:, None], nc[li], lc[ll]); h1 = np.where((left >= 0)[:, None], nh[li], lh[ll])
+        c2 = np.where((right >= 0)[:, None], nc[ri], lc[rl]); h2 = np.where((right >= 0)[:, None], nh[ri], lh[rl])
+        nc, nh = contain(c1, h1, c2, h2)
+    assert np.array_equal(np.concatenate([nc, nh], axis=1).view(np.uint32), bv['node_aabb'].view(np.uint32))
