@@ -331,3 +331,217 @@ def test_build_against_an_independent_restatement(orc, scenes, name):
         c2 = np.where((right >= 0)[:, None], nc[ri], lc[rl]); h2 = np.where((right >= 0)[:, None], nh[ri], lh[rl])
         nc, nh = contain(c1, h1, c2, h2)
     assert np.array_equal(np.concatenate([nc, nh], axis=1).view(np.uint32), bv['node_aabb'].view(np.uint32))
+
+
+def test_material_against_an_independent_restatement(orc):
+    """bsdf_f, bsdf_pdf and sample_dir (reference src/material.fut:60-410, rand.fut) written here in scalar numpy f32 straight
+    from the .fut text, sharing with the oracle only what the reference does not define: the transcendental contract
+    (include/lys_detmath.h through orc_eval_math), the LCG and spectrum_lookup (pinned by the tests above).  Bit-exact on
+    dielectric, metallic, transparent and mixed materials, both hemispheres, all three pdf kinds."""
+    import ctypes
+    F = np.float32
+    L = orc.lib()
+    PI = F(np.pi)
+    INV_PI = F(1.0) / PI
+    fmax, fmin = np.fmax, np.fmin
+
+    def m1(fn, x):
+        return orc.eval_math(fn, np.array([x], F))[0]
+
+    def dot(a, b):
+        return (a[0] * b[0] + a[1] * b[1]) + a[2] * b[2]
+
+    def norm(v):
+        return np.sqrt(dot(v, v))
+
+    def normalise(v):
+        return (F(1) / norm(v)) * v
+
+    def cross(a, b):
+        return np.array([a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]], F)
+
+    def lerp(a, b, t):
+        return a + (b - a) * t
+
+    class Rng:
+        def __init__(self, s):
+            self.s = s
+
+        def unit(self, lo=F(0), hi=F(0.9999)):
+            out = ctypes.c_uint32()
+            v = L.orc_rng_uniform(self.s, lo, hi, ctypes.byref(out))
+            self.s = out.value
+            return F(v)
+
+    def same_hemisphere(w, u):
+        return w[2] * u[2] > 0
+
+    def sin2_theta(w):
+        return fmax(F(0), F(1) - w[2] * w[2])
+
+    def alpha_of(r):
+        return F(1.62142) * fmax(F(0.004), r)
+
+    def D(alpha, wh):
+        with np.errstate(divide='ignore', invalid='ignore', over='ignore'):
+            t2 = sin2_theta(wh) / (wh[2] * wh[2])
+            if np.isinf(t2):
+                return F(0)
+            return m1('exp', -t2 / (alpha * alpha)) / (PI * alpha * alpha * (wh[2] * wh[2]) * (wh[2] * wh[2]))
+
+    def G(alpha, wo, wi):
+        def lam(w):
+            with np.errstate(divide='ignore', invalid='ignore', over='ignore'):
+                at = np.abs(np.sqrt(sin2_theta(w)) / w[2])
+                if np.isinf(at):
+                    return F(0)
+                a = F(1) / (alpha * at)
+            if a >= F(1.6):
+                return F(0)
+            return (F(1) - F(1.259) * a + F(0.396) * a * a) / (F(3.535) * a + F(2.181) * a * a)
+        return F(1) / (F(1) + lam(wo) + lam(wi))
+
+    def refl_bsdf(wo, wi, m):
+        with np.errstate(divide='ignore', invalid='ignore', over='ignore'):
+            wh = normalise(wi + wo)
+            a = alpha_of(m['roughness'])
+            return (D(a, wh) * G(a, wo, wi)) / (F(4) * wo[2] * wi[2])
+
+    def refl_pdf(wo, wi, m):
+        if not same_hemisphere(wo, wi):
+            return F(0)
+        with np.errstate(divide='ignore', invalid='ignore', over='ignore'):
+            wh = normalise(wo + wi)
+            return (D(alpha_of(m['roughness']), wh) * np.abs(wh[2])) / (F(4) * dot(wo, wh))
+
+    def fresnel(wo, m):
+        x = (F(1) - m['ref_ix']) / (F(1) + m['ref_ix'])
+        r0 = x * x
+        return r0 + (F(1) - r0) * m1('pow5', F(1) - wo[2])
+
+    def diffuse_pdf(wo, wi):
+        return wi[2] * INV_PI if same_hemisphere(wo, wi) else F(0)
+
+    def refr_bsdf(m):
+        return lerp(F(0), m['color'] * INV_PI, m['opacity'])
+
+    def refr_pdf(wo, wi, m):
+        return lerp(F(0), diffuse_pdf(wo, wi), m['opacity'])
+
+    def uber_bsdf(wo, wi, m):
+        refl = F(0) if wo[2] <= 0 else fresnel(wo, m)
+        diel = lerp(refr_bsdf(m), refl_bsdf(wo, wi, m), refl)
+        return lerp(diel, m['color'] * refl_bsdf(wo, wi, m), m['metalness'])
+
+    def uber_pdf(wo, wi, m):
+        if wo[2] <= 0:
+            diel = refr_pdf(wo, wi, m)
+        else:
+            diel = lerp(refr_pdf(wo, wi, m), refl_pdf(wo, wi, m), fresnel(wo, m))
+        return lerp(refl_pdf(wo, wi, m), diel, m['metalness'])            # operands as written in the reference (:360-361)
+
+    def reflect(w, n):
+        return F(-1) * w + (F(2) * dot(w, n)) * n
+
+    def sample_reflection(wo, m, rng):
+        u0, u1 = rng.unit(), rng.unit()
+        ls = m1('log', F(1) - u0)
+        if np.isinf(ls):
+            wh, pdf_wh = np.zeros(3, F), F(0)
+        else:
+            a = alpha_of(m['roughness'])
+            tan2 = -a * a * ls
+            phi = u1 * F(2) * PI
+            ct = F(1) / np.sqrt(F(1) + tan2)
+            st = np.sqrt(fmax(F(0), F(1) - ct * ct))
+            wh = np.array([st * m1('cos', phi), st * m1('sin', phi), ct], F)
+            if not same_hemisphere(wo, wh):
+                wh = -wh
+            pdf_wh = D(a, wh) * np.abs(ct)
+        wi = reflect(wo, wh)
+        if not same_hemisphere(wo, wi):
+            return np.zeros(3, F), F(0), 1, F(0)                          # null_sample: #impossible
+        with np.errstate(divide='ignore', invalid='ignore'):
+            kind, pdf = (2, pdf_wh / (F(4) * dot(wo, wh))) if pdf_wh > 0 else (1, F(0))
+        return wi, refl_bsdf(wo, wi, m), kind, pdf
+
+    def sample_refraction(wo, m, rng):
+        p = rng.unit()
+        if p < m['opacity']:
+            theta = rng.unit(F(0), F(2) * PI)
+            u = rng.unit()
+            r = np.sqrt(u)
+            d = r * np.array([m1('cos', theta), m1('sin', theta), F(0)], F)
+            z = np.sqrt(fmax(F(0), F(1) - (d[0] * d[0] + d[1] * d[1])))
+            return np.array([d[0], d[1], z], F), m['color'] * INV_PI, 2, z * INV_PI
+        entering = wo[2] > 0
+        n = np.array([0, 0, 1], F) if entering else np.array([-0.0, -0.0, -1.0], F)
+        eta = F(1.0) / m['ref_ix'] if entering else m['ref_ix'] / F(1.0)
+        ci = dot(n, wo)
+        s2i = fmax(F(0), F(1) - ci * ci)
+        s2t = eta * eta * s2i
+        if s2t >= 1:
+            wi = reflect(wo, n)
+        else:
+            wi = (-eta) * wo + (eta * ci - np.sqrt(F(1) - s2t)) * n
+        with np.errstate(divide='ignore'):
+            return wi, F(1) / np.abs(wi[2]), 0, F(0)
+
+    def uber_sample(wo, m, rng):
+        p = rng.unit()
+        if p < m['metalness']:
+            wi, b, k, pdf = sample_reflection(wo, m, rng)
+            return wi, m['color'] * b, k, pdf
+        if wo[2] <= 0:
+            return sample_refraction(wo, m, rng)
+        r = fresnel(wo, m)
+        q = rng.unit()
+        return sample_reflection(wo, m, rng) if q < r else sample_refraction(wo, m, rng)
+
+    def onb(nrm):
+        with np.errstate(divide='ignore', invalid='ignore'):
+            if np.abs(nrm[0]) > np.abs(nrm[2]):
+                b = normalise(np.array([-nrm[1], nrm[0], 0], F))
+            else:
+                b = normalise(np.array([0, -nrm[2], nrm[1]], F))
+        return cross(b, nrm), b, nrm
+
+    def to_local(o, w):
+        return np.array([dot(w, o[0]), dot(w, o[1]), dot(w, o[2])], F)
+
+    rs = np.random.default_rng(11)
+    checked, kinds = 0, set()
+    for trial in range(400):
+        mat = np.zeros(28, F)
+        mat[0:12:2] = -1
+        mat[16:28:2] = -1
+        mat[0:4] = (400, rs.uniform(0, 1), 700, rs.uniform(0, 1))          # two colour knots
+        mat[12] = rs.choice([0.0, 0.001, 0.05, 0.3, 1.0])                  # roughness
+        mat[13] = rs.choice([0.0, 0.0, 1.0, 0.4])                          # metalness
+        mat[14] = rs.choice([1.0, 1.33, 1.5, 2.4])                         # ref_ix
+        mat[15] = rs.choice([1.0, 1.0, 0.0, 0.5])                          # opacity
+        wl = F(rs.uniform(380, 750))
+        nrm = rs.normal(0, 1, 3).astype(F)
+        nrm = (nrm / np.sqrt((nrm.astype(np.float64) ** 2).sum())).astype(F)
+        wo = rs.normal(0, 1, 3).astype(F)
+        wo = (wo / np.sqrt((wo.astype(np.float64) ** 2).sum())).astype(F)
+        wi = rs.normal(0, 1, 3).astype(F)
+        wi = (wi / np.sqrt((wi.astype(np.float64) ** 2).sum())).astype(F)
+        seed = int(rs.integers(1, 2 ** 31 - 2))
+        out = np.zeros(9, F)
+        L.orc_material_probe(mat, wl, wo, wi, nrm, seed, out)
+        m = dict(color=F(L.orc_spectrum_lookup(wl, np.ascontiguousarray(mat[:12]))), roughness=mat[12], metalness=mat[13],
+                 ref_ix=mat[14] - (wl - F(589)) / F(10000), opacity=mat[15])
+        o = onb(nrm)
+        wo_l, wi_l = to_local(o, wo), to_local(o, wi)
+        with np.errstate(divide='ignore', invalid='ignore', over='ignore'):
+            f, pdf = uber_bsdf(wo_l, wi_l, m), uber_pdf(wo_l, wi_l, m)
+            rng = Rng(seed)
+            swi, sb, sk, spdf = uber_sample(wo_l, m, rng)
+            swi_w = (swi[0] * o[0] + swi[1] * o[1]) + swi[2] * o[2]
+        got = np.array([f, pdf, swi_w[0], swi_w[1], swi_w[2], sb, F(sk), spdf], F)
+        assert np.array_equal(got.view(np.uint32), out[:8].view(np.uint32)), (trial, mat[12:16], got, out[:8])
+        assert rng.s == int(out[8:9].view(np.uint32)[0])
+        kinds.add(sk)
+        checked += 1
+    assert checked == 400 and kinds == {0, 1, 2}
