@@ -378,3 +378,54 @@ def test_path_tracer_against_an_independent_restatement(orc, scenes, name, h, w,
             assert np.array_equal(dist.view(np.uint32), want['distance'].reshape(-1, 16)[ix].view(np.uint32)), ix
             vertices += int(np.isfinite(dist).sum())
     assert vertices > h * w // 2                                          # the sample really exercises shading, not just misses
+
+
+@pytest.mark.parametrize('pitch,yaw', [(0.0, 0.0), (0.1, 0.3), (-0.4, 2.5)])
+def test_camera_against_an_independent_restatement(orc, scenes, pitch, yaw):
+    """sample_camera_wavelength and sample_camera_ray (reference src/camera.fut:46-55,68-110, visual_conf of src/lib.fut:18-27)
+    restated from the .fut text: channel pick, probit wavelength, pixel jitter and lens sample from PEEKED draws, pinhole ray.
+    Per-frame scalars (sin / cos of yaw and pitch, tan of the half field of view) come from the C library like in the c backend."""
+    libm = ctypes.CDLL('libm.so.6')
+    for fn in ('sinf', 'cosf', 'tanf'):
+        getattr(libm, fn).restype = ctypes.c_float
+        getattr(libm, fn).argtypes = [ctypes.c_float]
+    t9, tm, m = scenes['cornell']
+    h, w = 24, 40
+    origin = np.array([0.1, 0.7, 1.9], F)
+    st = orc.State.init(t9, tm, m, h, w, pitch=pitch, yaw=yaw, origin=tuple(float(x) for x in origin))
+    fut = Fut(orc, t9, tm, m, st.bvh())
+    prim = st.probe_primary(want_rays=True)
+    rng0 = st.scalars()['rng']
+    L = orc.lib()
+    sensor = [(F(455), F(22)), (F(535), F(32)), (F(610), F(26))]
+    fov = F(80) * PI / F(180)                                             # from_deg (linalg.fut:52)
+    cam_dir = normalise(np.array([libm.sinf(F(yaw)), libm.sinf(F(pitch)), -libm.cosf(F(yaw))], F))
+    right = normalise(cross(cam_dir, np.array([0, 1, 0], F)))
+    up = normalise(cross(right, cam_dir))
+    ratio = F(w) / F(h)
+    half_h = F(libm.tanf(fov / F(2.0)))
+    half_w = ratio * half_h
+    wv, focus = F(-1) * cam_dir, F(1)
+    llc = ((origin - (half_w * focus) * right) - (half_h * focus) * up) - focus * wv
+    horizontal, vertical = (F(2) * half_w * focus) * right, (F(2) * half_h * focus) * up
+    for i in range(h):
+        for j in range(w):
+            ix = i * w + j
+            s = rng0 ^ int(L.orc_hash(ix))
+            s = fut.lcg(s)
+            mu, sigma = sensor[s % 3]
+            s, p = fut.uniform(s)
+            wl = mu + sigma * fut.m1('probit', p)
+            s1, ox = fut.uniform(s)                                        # peeked: the caller keeps s
+            _, oy = fut.uniform(s1)
+            x = (F(j) + F(1) * ox) / F(w)
+            y = ((F(h) - F(i) - F(1.0)) + F(1) * oy) / F(h)
+            s2, theta = fut.uniform(s, F(0), F(2) * PI)                    # the same draws again for the lens sample
+            _, u = fut.uniform(s2)
+            r = np.sqrt(u)
+            lens = F(0) * (r * np.array([fut.m1('cos', theta), fut.m1('sin', theta), F(0)], F))
+            o = origin + (lens[0] * right + lens[1] * up)
+            d = normalise(((llc + x * horizontal) + y * vertical) - o)
+            got = np.concatenate([o, d]).astype(F)
+            assert np.array_equal(got.view(np.uint32), prim['rays'][i, j].view(np.uint32)), (i, j, got, prim['rays'][i, j])
+            assert np.float32(wl).view(np.uint32) == prim['wavelen'][i, j].view(np.uint32), (i, j)
