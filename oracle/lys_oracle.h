@@ -11,7 +11,9 @@
  * environment, so this restatement cannot be checked against outputs of the
  * reference itself.  It is auditable line-by-line against the .fut sources cited
  * in lys_oracle.cpp, and is pinned only by self-authored known-answer vectors
- * (tests/golden/).
+ * (tests/golden/) and by a second, independently written reading of the .fut text
+ * (tests/test_oracle_kat.py, tests/test_oracle_pathtrace_kat.py: build, walks, BSDF,
+ * camera and a complete scalar path tracer, all bit for bit).
  */
 #ifndef LYS_ORACLE_H
 #define LYS_ORACLE_H
