@@ -429,3 +429,43 @@ def test_camera_against_an_independent_restatement(orc, scenes, pitch, yaw):
             got = np.concatenate([o, d]).astype(F)
             assert np.array_equal(got.view(np.uint32), prim['rays'][i, j].view(np.uint32)), (i, j, got, prim['rays'][i, j])
             assert np.float32(wl).view(np.uint32) == prim['wavelen'][i, j].view(np.uint32), (i, j)
+
+
+def test_accumulation_and_render_against_an_independent_restatement(orc, scenes):
+    """visualize_pixels (#render_color, reference src/integrator.fut:133-170: sequential sum of intensity * channel vector over
+    the 16 path entries, times the channel count), sample_n_frames / sample_frame_accum (src/lib.fut:67-74, integrator.fut:180-192:
+    running average weighted with the OLD frame count, so the first frame is discarded) and render (src/lib.fut:187-196 with
+    matte's argb.from_rgba: clamp, * 255, truncate), from the per-vertex radiance of three consecutive passes."""
+    t9, tm, m = scenes['spectrumsphere']
+    h, w = 20, 28
+    st = orc.State.init(t9, tm, m, h, w)
+    vis = [np.array([0, 0, 1], F), np.array([0, 1, 0], F), np.array([1, 0, 0], F)]     # visual_conf sensor (lib.fut:24-26)
+    frames = []
+    for k in range(3):
+        pp = st.advance_rng(k).probe_pass()
+        img = np.zeros((h, w, 3), F)
+        for i in range(h):
+            for j in range(w):
+                acc = np.zeros(3, F)
+                for v in range(16):
+                    acc = acc + pp['radiance'][i, j, v] * vis[pp['channel'][i, j]]
+                img[i, j] = F(3) * acc
+        frames.append(img)
+    img, nf = frames[0], 1
+    while nf < 3:
+        n = F(nf)
+        img = (((n - F(1)) / n) * img + (F(1) / n) * frames[nf]).astype(F)
+        nf += 1
+    got = st.sample_n_frames(3)
+    assert np.array_equal(img.view(np.uint32), got.view(np.uint32))
+    # the interactive path: accumulate on (key m), three steps, then render
+    s = st.key(0x6D)
+    for _ in range(3):
+        s = s.step()
+    px = s.render()
+    im = s.image()
+    c = np.clip(im, 0, 1)
+    c = np.where(np.isnan(im), 0, c)
+    ch = (c * F(255)).astype(np.uint32)
+    argb = ((np.uint32(255) << 24) | (ch[..., 0] << 16) | (ch[..., 1] << 8) | ch[..., 2]).astype(np.uint32)
+    assert np.array_equal(argb.view(np.int32), px[:im.shape[0], :im.shape[1]])
