@@ -57,7 +57,9 @@ class Fut:
         # get_lights: emissive triangles in input order
         def emissive(row):
             return any(row[16 + 2 * k] >= 0 and row[17 + 2 * k] > 0 for k in range(6))
-        self.lights = [i for i in range(len(self.tri)) if emissive(self.mats[self.tri_mats[i]])]
+        self.light_ix = [i for i in range(len(self.tri)) if emissive(self.mats[self.tri_mats[i]])]
+        self.lights = [dict(kind='diffuse', tri=self.tri[i], em=self.mats[self.tri_mats[i]][16:28], theta=F(0)) for i in self.light_ix]
+        self.extra = []                                                  # the transmitter lights of the current pixel (camera.fut:112-122)
 
     # ---- shared primitives
     def m1(self, fn, x):
@@ -267,12 +269,15 @@ class Fut:
 
     # ---- light.fut / direct.fut
     def incident(self, light, hitp, lightp, wl):
-        A, B, Cc = self.tri[light]
+        A, B, Cc = light['tri']
         v = lightp - hitp
         wi, d2 = normalise(v), dot(v, v)
         ln = normalise(cross(B - A, Cc - A))
         cl = dot(-wi, ln)
-        return fmax(F(0), self.lookup(wl, self.mats[self.tri_mats[light]][16:28]) * cl / d2)
+        E = self.lookup(wl, light['em'])
+        if light['kind'] == 'diffuse':
+            return fmax(F(0), E * cl / d2)
+        return E / d2 if self.m1('acos', cl) <= light['theta'] else F(0)   # frustumlight_incident_radiance (light.fut:32-44)
 
     def occluded(self, pos, n, lightp):
         v = lightp - pos
@@ -283,11 +288,12 @@ class Fut:
         return self.walk(norm(v) - F(0.01), o, d, True)
 
     def direct_radiance(self, s, wo, pos, n, m, wl):
-        if not self.lights:
+        lights = self.lights + self.extra
+        if not lights:
             return s, F(0)
         s = self.lcg(s)                                                  # random_select: one raw draw
-        light = self.lights[s % len(self.lights)]
-        A, B, Cc = self.tri[light]
+        light = lights[s % len(lights)]
+        A, B, Cc = light['tri']
         e1, e2 = B - A, Cc - A
         area = norm(cross(e1, e2)) / F(2)
         # sample_arealight peeks two draws (the advanced rng is dropped, direct.fut:38,42)
@@ -321,8 +327,25 @@ class Fut:
                 lp = F(1) / area
                 weight = F(1) * bpdf / (F(1) * bpdf + F(1) * lp)
                 Bv = f * in_rad * weight / bpdf
-        light_pdf = F(1) / F(len(self.lights))
+        light_pdf = F(1) / F(len(lights))
         return s, (L + Bv) / light_pdf
+
+    def disk(self, p, normal, radius, libm):
+        """shapes.fut:17-35: 8 sector triangles around p; per-frame trigonometry from the C library like the c backend"""
+        a = F(2) * PI / F(8)
+        c = cross(normal, np.array([0, 1, 0], F))
+        right = np.array([1, 0, 0], F) if norm(c) == 0 else normalise(c)
+        up = normalise(cross(right, normal))
+
+        def vec(b):
+            x = F(1) * F(libm.cosf(b)) - F(0) * F(libm.sinf(b))           # vec3.rot_z b (1, 0, 0)
+            y = F(1) * F(libm.sinf(b)) + F(0) * F(libm.cosf(b))
+            return x * right + y * up
+        out = []
+        for i in range(8):
+            v0, v1 = vec(a * F(i)), vec(a * (F(i) + F(1)))
+            out.append(np.stack([p, p + radius * v1, p + radius * v0]).astype(F))
+        return out
 
     # ---- integrator.fut
     def path_trace(self, o, d, wl, s, ambience12, path_len=16):
@@ -365,7 +388,7 @@ def test_path_tracer_against_an_independent_restatement(orc, scenes, name, h, w,
     prim = st.probe_primary(want_rays=True)
     want = st.probe_pass()
     rays, wls = prim['rays'].reshape(-1, 6), prim['wavelen'].reshape(-1)
-    assert sorted(fut.lights) == sorted(st.light_indices().tolist()) and fut.lights == st.light_indices().tolist()
+    assert fut.light_ix == st.light_indices().tolist()
     L = orc.lib()
     vertices = 0
     with np.errstate(divide='ignore', invalid='ignore', over='ignore'):
@@ -469,3 +492,61 @@ def test_accumulation_and_render_against_an_independent_restatement(orc, scenes)
     ch = (c * F(255)).astype(np.uint32)
     argb = ((np.uint32(255) << 24) | (ch[..., 0] << 16) | (ch[..., 1] << 8) | ch[..., 2]).astype(np.uint32)
     assert np.array_equal(argb.view(np.int32), px[:im.shape[0], :im.shape[1]])
+
+
+def _libm():
+    libm = ctypes.CDLL('libm.so.6')
+    for fn in ('sinf', 'cosf', 'tanf', 'expf'):
+        getattr(libm, fn).restype = ctypes.c_float
+        getattr(libm, fn).argtypes = [ctypes.c_float]
+    libm.powf.restype = ctypes.c_float
+    libm.powf.argtypes = [ctypes.c_float, ctypes.c_float]
+    return libm
+
+
+@pytest.mark.parametrize('conf', [2, 1])
+def test_transmitter_lights_against_an_independent_restatement(orc, scenes, conf):
+    """The LIDAR (scanning frustum lights around every pixel's own ray, src/camera.fut:112-122, light.fut:32-44, lidar_conf of
+    lib.fut:10-16) and flash (a disk of diffuse lights at the camera, visual_flash_conf lib.fut:29-33 with the normalised
+    black-body spectrum of spectrum.fut:60-79) configurations: per-vertex radiance and distance of one pass."""
+    libm = _libm()
+    t9, tm, m = scenes['cornell']
+    h, w = 14, 18
+    st = orc.State.init(t9, tm, m, h, w, cam_conf_id=conf)
+    fut = Fut(orc, t9, tm, m, st.bvh())
+    sc = st.scalars()
+    prim = st.probe_primary(want_rays=True)
+    want = st.probe_pass()
+    rays, wls = prim['rays'].reshape(-1, 6), prim['wavelen'].reshape(-1)
+    origin = np.array([0.0, 0.8, 1.8], F)
+    if conf == 2:
+        em = np.array([0, 1500] + [-1, 0] * 5, F)                         # uniform_spectrum 1500
+        theta = F(3) * PI / F(180.0)
+    else:
+        cc, hh, kb, T = F(299792458), F(6.62606957e-34), F(1.3806488e-23), F(5500)
+        nm = [F(150), F(460), F(550), F(610), F(1000), F(2000)]           # blue / green / red_wavelen (spectrum.fut:8-10)
+        ls = [x * F(1e-9) for x in nm]
+        planck = [(F(2) * hh * cc * cc) / (F(libm.powf(l, F(5))) * (F(libm.expf((hh * cc) / (l * kb * T))) - F(1))) for l in ls]
+        knots = np.array([v for l, pl in zip(ls, planck) for v in (l * F(1e9), pl)], F)
+        lam_max = (F(2.8977721e-3) / T) * F(1e9)
+        mx = fut.lookup(lam_max, knots)
+        em = knots.copy()
+        em[1::2] = (knots[1::2] / mx) * F(1000)
+        cam_dir = normalise(np.array([libm.sinf(F(0)), libm.sinf(F(0)), -libm.cosf(F(0))], F))
+        flash = [dict(kind='diffuse', tri=t, em=em, theta=F(0)) for t in fut.disk(origin, cam_dir, F(0.05), libm)]
+    L = orc.lib()
+    lit = 0
+    with np.errstate(divide='ignore', invalid='ignore', over='ignore'):
+        for ix in range(h * w):
+            s = sc['rng'] ^ int(L.orc_hash(ix))
+            s = fut.lcg(s)
+            s = fut.lcg(s)
+            if conf == 2:
+                fut.extra = [dict(kind='frustum', tri=t, em=em, theta=theta) for t in fut.disk(origin, rays[ix, 3:], F(0.01), libm)]
+            else:
+                fut.extra = flash
+            rad, dist = fut.path_trace(rays[ix, :3], rays[ix, 3:], wls[ix], s, sc['ambience'])
+            assert np.array_equal(rad.view(np.uint32), want['radiance'].reshape(-1, 16)[ix].view(np.uint32)), (ix, rad, want['radiance'].reshape(-1, 16)[ix])
+            assert np.array_equal(dist.view(np.uint32), want['distance'].reshape(-1, 16)[ix].view(np.uint32)), ix
+            lit += int((rad > 0).any())
+    assert lit > h * w // 8
