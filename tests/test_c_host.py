@@ -1,5 +1,6 @@
-"""The headless C host (host/lys_headless.c): the reference's liblys.c call sequence, linked against the STATIC
-libtracer.a + libljus exactly as the reference links main-interactive (Makefile:48-49)."""
+"""The C hosts: host/lys_headless.c (the reference's liblys.c call sequence) and host/lys_save.c (the reference's Rust
+demo-save host: LIDAR point cloud -> .pcd, image capture), linked against the STATIC libtracer.a + libljus exactly as the
+reference links main-interactive (Makefile:48-49) and demo-save (ffi.rs:1)."""
 import os
 import subprocess
 import numpy as np
@@ -7,22 +8,80 @@ import pytest
 from conftest import ROOT, bits_equal
 
 HOST = os.path.join(ROOT, 'host', 'lys_headless')
+SAVE = os.path.join(ROOT, 'host', 'lys_save')
+SELFTEST = os.path.join(ROOT, 'host', 'pcd_selftest')
 
 
 def build_host(pkg):
     pkg.build()
     subprocess.check_call(['make', '-C', os.path.join(ROOT, 'host')], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
-    assert os.path.exists(HOST)
+    assert os.path.exists(HOST) and os.path.exists(SAVE) and os.path.exists(SELFTEST)
 
 
 def test_c_host_links_statically_and_fails_loudly_without_gpu(pkg):
     build_host(pkg)
-    undefined = subprocess.check_output(['nm', '-u', HOST]).decode()
-    assert 'futhark_' not in undefined                      # every futhark_* symbol was resolved from libtracer.a
     import torch
-    if not torch.cuda.is_available():
-        r = subprocess.run([HOST, '-o', 'missing.obj'], capture_output=True, text=True)
-        assert r.returncode != 0 and 'no CUDA device' in r.stderr
+    for exe in (HOST, SAVE):
+        undefined = subprocess.check_output(['nm', '-u', exe]).decode()
+        assert 'futhark_' not in undefined                  # every futhark_* symbol was resolved from libtracer.a
+        if not torch.cuda.is_available():
+            r = subprocess.run([exe, '-o', 'missing.obj'], capture_output=True, text=True)
+            assert r.returncode != 0 and 'no CUDA device' in r.stderr
+
+
+def read_pcd(path):
+    lines = open(path).read().split('\n')
+    hdr = {l.split(' ', 1)[0]: l.split(' ', 1)[1] for l in lines[1:11]}
+    body = [l for l in lines[11:] if l]
+    return lines[0], hdr, body
+
+
+def rust_display_f32(v):
+    """What Rust's `{}` prints for an f32: shortest round-trip digits, positional notation."""
+    if np.isnan(v):
+        return 'NaN'
+    if np.isinf(v):
+        return '-inf' if v < 0 else 'inf'
+    return np.format_float_positional(np.float32(v), unique=True, trim='-')
+
+
+def test_pcd_writer_format_and_roundtrip(pkg, tmp_path):
+    """demo-save/src/main.rs:23-31: one ASCII x y z record per pixel, WIDTH = number of points, HEIGHT = 1."""
+    build_host(pkg)
+    rng = np.random.default_rng(5)
+    pts = rng.integers(0, 2 ** 32, (5000, 4), dtype=np.uint64).astype(np.uint32).view(np.float32)     # every kind of f32
+    pts[:8, 0] = [0.0, -0.0, 1.0, 0.1, 1e-7, 1e10, np.inf, -np.inf]
+    pts[8, 1] = np.nan
+    raw, out = str(tmp_path / 'p.f32'), str(tmp_path / 'p.pcd')
+    pts.tofile(raw)
+    subprocess.check_call([SELFTEST, 'pcd', raw, str(len(pts)), out])
+    first, hdr, body = read_pcd(out)
+    assert first.startswith('# .PCD v')
+    assert hdr['FIELDS'] == 'x y z' and hdr['SIZE'] == '4 4 4' and hdr['TYPE'] == 'F F F' and hdr['COUNT'] == '1 1 1'
+    assert hdr['WIDTH'] == str(len(pts)) and hdr['HEIGHT'] == '1' and hdr['POINTS'] == str(len(pts)) and hdr['DATA'] == 'ascii'
+    assert hdr['VIEWPOINT'] == '0 0 0 1 0 0 0'
+    assert len(body) == len(pts)
+    for row, line in zip(pts, body):
+        assert line == ' '.join(rust_display_f32(v) for v in row[:3])
+    back = np.array([[np.float32(t) for t in line.split(' ')] for line in body], np.float32)
+    ok = (back.view(np.uint32) == pts[:, :3].view(np.uint32)) | (np.isnan(back) & np.isnan(pts[:, :3]))
+    assert ok.all()                                          # the text parses back to the same bits (NaN payloads aside)
+
+
+def test_ppm_writer_quantisation(pkg, tmp_path):
+    """main.rs:43-46: (x.clamp(0, 1) * 255.99) as u8."""
+    build_host(pkg)
+    img = np.linspace(-0.25, 1.25, 7 * 5 * 3, dtype=np.float32).reshape(5, 7, 3)
+    img[0, 0] = [np.nan, np.inf, -np.inf]
+    raw, out = str(tmp_path / 'i.f32'), str(tmp_path / 'i.ppm')
+    img.tofile(raw)
+    subprocess.check_call([SELFTEST, 'ppm', raw, '7', '5', out])
+    data = open(out, 'rb').read()
+    hdr = b'P6\n7 5\n255\n'
+    assert data.startswith(hdr)
+    got = np.frombuffer(data[len(hdr):], np.uint8).reshape(5, 7, 3)
+    want = (np.clip(np.nan_to_num(img, nan=0.0, posinf=1.0, neginf=0.0), 0, 1) * np.float32(255.99)).astype(np.uint8)
+    assert np.array_equal(got, want) and got.max() == 255 and got.min() == 0
 
 
 def test_obj_writer_roundtrip(pkg, scenes, tmp_path):
@@ -54,3 +113,41 @@ def test_c_host_matches_python_host(pkg, gpu, scenes, tmp_path):
     px = s.render().view(np.uint32)
     want = np.stack([(px >> 16) & 255, (px >> 8) & 255, px & 255], axis=2).astype(np.uint8)
     assert np.array_equal(img, want) and img.max() > 0
+
+
+@pytest.mark.gpu
+def test_c_save_host_point_cloud_matches_oracle(pkg, orc, gpu, scenes, tmp_path):
+    """host/lys_save = demo-save (wrapper.rs:34-101, main.rs:11-32): LIDAR preset, sample_points_n, x y z of every pixel in
+    dump.pcd -- bit-identical (through the shortest round-trip text) to the oracle's sample_points_n."""
+    from lysref import objwriter
+    build_host(pkg)
+    t, tm, m = scenes['spectrumsphere']
+    obj, pcd = str(tmp_path / 's.obj'), str(tmp_path / 'dump.pcd')
+    objwriter.write_obj(obj, t, tm, m)
+    w, h, spp = 64, 48, 5
+    out = subprocess.check_output([SAVE, '-o', obj, '-w', str(w), '-h', str(h), '-s', str(spp), '-p', pcd]).decode()
+    assert 'points %d' % (w * h) in out
+    _, hdr, body = read_pcd(pcd)
+    assert hdr['WIDTH'] == str(w * h) and hdr['HEIGHT'] == '1'
+    got = np.array([[np.float32(x) for x in line.split(' ')] for line in body], np.float32).reshape(h, w, 3)
+    want = orc.State.init(t, tm, m, h, w, cam_conf_id=2).sample_points_n(spp)[1]
+    assert bits_equal(got, np.ascontiguousarray(want[..., :3]))
+    assert np.isfinite(got).any()
+
+
+@pytest.mark.gpu
+def test_c_save_host_image_matches_python_host(pkg, gpu, scenes, tmp_path):
+    """The image capture path of demo-save (main.rs:34-49): sample_n_frames -> clamp * 255.99 -> u8."""
+    from lysref import objwriter
+    build_host(pkg)
+    t, tm, m = scenes['cornell']
+    obj, ppm = str(tmp_path / 'c.obj'), str(tmp_path / 'c.ppm')
+    objwriter.write_obj(obj, t, tm, m)
+    w, h, n = 96, 64, 6
+    subprocess.check_call([SAVE, '-o', obj, '-w', str(w), '-h', str(h), '-s', str(n), '-i', ppm], stdout=subprocess.DEVNULL)
+    raw = open(ppm, 'rb').read()
+    hdr = ('P6\n%d %d\n255\n' % (w, h)).encode()
+    got = np.frombuffer(raw[len(hdr):], np.uint8).reshape(h, w, 3)
+    img = pkg.State.init(gpu, t, tm, m, h, w).sample_n_frames(n)
+    want = (np.clip(np.nan_to_num(img, nan=0.0, posinf=1.0, neginf=0.0), 0, 1) * np.float32(255.99)).astype(np.uint8)
+    assert np.array_equal(got, want) and got.max() > 0
