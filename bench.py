@@ -113,11 +113,18 @@ def ncu_traffic():
         return None, None
 
 
-def cpu_baseline(oracle, scene, passes, threads=None):
-    """Oracle Mpaths/s on the host cores + work counters for the algorithmic-bytes figure (bounded sample)."""
+def cpu_baseline(oracle, scene, passes, threads=None, target_s=15.0):
+    """Oracle Mpaths/s on the host cores + work counters for the algorithmic-bytes figure, on a bounded sample:
+    `passes` sample passes of the bench workload, or (passes = 0) as many as fit in about `target_s` seconds of CPU work,
+    sized from one warm calibration pass (2..64)."""
     t, tm, m = scene
     oracle.set_threads(threads or host_threads())      # explicit: torchrun exports OMP_NUM_THREADS=1
     s = oracle.State.init(t, tm, m, H, W)
+    if passes <= 0:
+        s.sample_n_frames(1)                           # thread pool / page-fault warm-up
+        t0 = time.perf_counter()
+        s.sample_n_frames(1)
+        passes = int(min(64, max(2, round(target_s / max(time.perf_counter() - t0, 1e-3)))))
     oracle.counters_reset()
     t0 = time.perf_counter()
     s.sample_n_frames(passes)
@@ -160,7 +167,7 @@ def main():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200')
-    ap.add_argument('--cpu-passes', type=int, default=2, help='passes of the CPU baseline sample')
+    ap.add_argument('--cpu-passes', type=int, default=0, help='passes of the CPU baseline sample (0 = about 15 s of CPU work)')
     ap.add_argument('--no-cpu', action='store_true')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != 'reference' else args.warmup
