@@ -120,6 +120,30 @@ def test_pass_radiance_bit_exact(orc, pkg, gpu, scenes, name, conf):
     assert qo['radiance'].max() > 0
 
 
+@pytest.mark.parametrize('seed', [1, 2, 3])
+def test_random_soup_scenes_bit_exact(orc, pkg, gpu, seed):
+    """Fuzzed scenes (lysref.objwriter.random_soup): the whole uber-BSDF parameter space, ten light triangles (one of zero
+    area), duplicated and degenerate triangles, in all three camera presets -- LBVH, first hits, per-vertex radiance /
+    distance / channel of one pass, three accumulated passes and the LIDAR point cloud."""
+    from lysref import objwriter
+    scene = objwriter.random_soup(seed)
+    for conf in (0, 1, 2):
+        so, sg = both(orc, pkg, gpu, scene, 60, 84, cam_conf_id=conf, origin=(0.0, 1.0, 0.9))
+        if conf == 0:
+            bo, bg = so.bvh(), sg.bvh()
+            for key in ('bounds', 'morton', 'src_index', 'left', 'right', 'parent', 'node_aabb', 'leaf_aabb'):
+                assert bits_equal(bo[key], bg[key]), (seed, key)
+            assert bits_equal(so.light_indices(), sg.light_indices()) and len(sg.light_indices()) == 10
+            po, pg = so.probe_primary(), sg.probe_primary()
+            assert bits_equal(po['leaf'], pg['leaf']) and bits_equal(po['t'], pg['t'])
+        qo, qg = so.probe_pass(), sg.probe_pass()
+        for key in ('radiance', 'distance', 'channel'):
+            assert bits_equal(qo[key], qg[key]), (seed, conf, key)
+        assert (qo['radiance'] > 0).any()
+        assert bits_equal(so.sample_n_frames(3), sg.sample_n_frames(3)), (seed, conf)
+    assert bits_equal(so.sample_points_n(3)[1], sg.sample_points_n(3)[1]), seed
+
+
 def test_random_rays(orc, pkg, gpu, scenes):
     from test_oracle_scene import random_rays
     for name in ('cornell', 'spectrumspherehigh'):

@@ -550,3 +550,34 @@ def test_transmitter_lights_against_an_independent_restatement(orc, scenes, conf
             assert np.array_equal(dist.view(np.uint32), want['distance'].reshape(-1, 16)[ix].view(np.uint32)), ix
             lit += int((rad > 0).any())
     assert lit > h * w // 8
+
+
+@pytest.mark.parametrize('seed', [1, 2])
+def test_path_tracer_on_random_soup_against_an_independent_restatement(orc, seed):
+    """The same comparison on a fuzzed scene (lysref.objwriter.random_soup): rough and smooth metals, dispersive dielectrics,
+    partial opacity, unused spectrum knots, ten light triangles (one of zero area), duplicated and degenerate triangles --
+    the parts of material.fut / direct.fut the four bundled assets hardly reach."""
+    from lysref import objwriter
+    t9, tm, m = objwriter.random_soup(seed)
+    h, w, origin = 16, 20, (0.0, 1.0, 0.9)
+    st = orc.State.init(t9, tm, m, h, w, origin=origin)
+    fut = Fut(orc, t9, tm, m, st.bvh())
+    sc = st.scalars()
+    prim = st.probe_primary(want_rays=True)
+    want = st.probe_pass()
+    rays, wls = prim['rays'].reshape(-1, 6), prim['wavelen'].reshape(-1)
+    assert fut.light_ix == st.light_indices().tolist() and len(fut.light_ix) == 10
+    L = orc.lib()
+    vertices = lit = 0
+    with np.errstate(divide='ignore', invalid='ignore', over='ignore'):
+        for ix in range(h * w):
+            s = sc['rng'] ^ int(L.orc_hash(ix))
+            s = fut.lcg(s)
+            s = fut.lcg(s)
+            rad, dist = fut.path_trace(rays[ix, :3], rays[ix, 3:], wls[ix], s, sc['ambience'])
+            wr, wd = want['radiance'].reshape(-1, 16)[ix], want['distance'].reshape(-1, 16)[ix]
+            assert np.array_equal(rad.view(np.uint32), wr.view(np.uint32)), (ix, rad, wr)
+            assert np.array_equal(dist.view(np.uint32), wd.view(np.uint32)), ix
+            vertices += int(np.isfinite(dist).sum())
+            lit += int((rad > 0).any())
+    assert vertices > h * w and lit > h * w // 10
