@@ -58,7 +58,9 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    hnd, _ = frame(min(a.passes, 4 * world))                                      # warm-up (buffers, queue-length estimates)
+    # warm-up: at least LYS_PIPELINE (8) passes on EVERY rank, so that all pipeline buffer sets exist before the timed frame
+    # (a 4-pass warm-up left 4 of the 8 sets to be cudaMalloc'ed inside the first timed frame: ~0.1 s at 4K)
+    hnd, _ = frame(min(a.passes, 16 * world) if a.mode == 'passes' else min(a.passes, 16))
     state.free_f32_3d(hnd)
     best = None
     for _ in range(a.reps):
