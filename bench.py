@@ -16,8 +16,9 @@ accumulated on the device.  A path = one pixel sample (one `sample_pixel`, integ
   cpu_baseline  the CPU restatement of the reference (oracle/, OpenMP over pixel rows) on a bounded sample.
 
 N > 1 (torchrun): one process per GPU, scene replicated, each rank renders its own PASSES passes of the full
-frame (disjoint pass ranges of one N*PASSES-pass render), one NCCL sum-reduce of the framebuffer to rank 0 per
-step inside the timed region; per-GPU work is fixed, so "scaling" is "weak".
+frame (disjoint pass ranges of one N*PASSES-pass render); the per-rank running averages are weighted and combined by
+one NCCL sum-reduce of the framebuffer to rank 0 per step (parallel.merge_pass_split) inside the timed region; per-GPU
+work is fixed, so "scaling" is "weak".
 
 --impl reference: times the oracle (the reference itself cannot be built here: no futhark compiler, Futhark
 packages not vendored) on the host cores for the same metric/config, one pass per step.
@@ -205,8 +206,8 @@ def main():
     def step_resident():
         h, ptr, shape, _ = state.sample_n_frames_device(PASSES, want_stats=False)
         if world > 1:
-            with torch.cuda.stream(stream):
-                par.reduce_framebuffer(par.as_torch(ptr, shape, dev), dst=0)
+            with torch.cuda.stream(stream):     # weights + ONE sum-reduce: rank 0 ends up with the mean over all ranks' passes
+                par.merge_pass_split(par.as_torch(ptr, shape, dev), PASSES, [PASSES] * world, dst=0)
         return h
 
     # ---- value: state resident in HBM, result left on the device ------------------------------------------
@@ -250,7 +251,7 @@ def main():
         hnd, ptr, shape, _ = s.sample_n_frames_device(PASSES, want_stats=False)
         if world > 1:
             with torch.cuda.stream(stream):
-                par.reduce_framebuffer(par.as_torch(ptr, shape, dev), dst=0)
+                par.merge_pass_split(par.as_torch(ptr, shape, dev), PASSES, [PASSES] * world, dst=0)
         if rank == 0:
             ctx.check(ctx._L.futhark_values_f32_3d(ctx._ctx, hnd, out_pin.data_ptr()), 'futhark_values_f32_3d')   # blocking D2H
         else:

@@ -108,6 +108,47 @@ int futhark_entry_sample_points_n(struct futhark_context *ctx, struct futhark_op
                                   struct futhark_f32_3d **out1,
                                   const struct futhark_opaque_state *s, const uint32_t samples_per_pixel);
 
+/* ---- the rest of the surface a `futhark cuda --library` header carries ----------------------
+ * None of this is called by the reference's hosts (liblys.c, ffi.rs); it is what the Futhark compiler emits next to the
+ * declarations above for every CUDA-backend library, restated from the compiler's conventions so that a host written
+ * against the generated tracer.h (tuning flags, profiling report, zero-copy device access) still links and behaves
+ * sensibly.  There is no run-time compilation and no tunable "size" in this library: the program / PTX / nvrtc / size
+ * setters are accepted and ignored, futhark_get_num_sizes() is 0 and futhark_context_config_set_size() reports failure. */
+void futhark_context_config_set_profiling(struct futhark_context_config *cfg, int flag);    /* kernel-class timing from the start */
+void futhark_context_config_add_nvrtc_option(struct futhark_context_config *cfg, const char *opt);
+void futhark_context_config_dump_program_to(struct futhark_context_config *cfg, const char *path);
+void futhark_context_config_load_program_from(struct futhark_context_config *cfg, const char *path);
+void futhark_context_config_dump_ptx_to(struct futhark_context_config *cfg, const char *path);
+void futhark_context_config_load_ptx_from(struct futhark_context_config *cfg, const char *path);
+void futhark_context_config_set_default_group_size(struct futhark_context_config *cfg, int size);
+void futhark_context_config_set_default_num_groups(struct futhark_context_config *cfg, int num);
+void futhark_context_config_set_default_tile_size(struct futhark_context_config *cfg, int num);
+void futhark_context_config_set_default_threshold(struct futhark_context_config *cfg, int num);
+int futhark_context_config_set_size(struct futhark_context_config *cfg, const char *size_name, size_t size_value);   /* 1: no such size */
+int futhark_get_num_sizes(void);
+const char *futhark_get_size_name(int i);
+const char *futhark_get_size_class(int i);
+void futhark_context_pause_profiling(struct futhark_context *ctx);
+void futhark_context_unpause_profiling(struct futhark_context *ctx);
+/* malloc'ed text (caller frees): kernel launches, device time per kernel class when profiling is on, pooled device memory */
+char *futhark_context_report(struct futhark_context *ctx);
+
+/* Zero-copy device access.  The generated CUDA header spells the pointer type CUdeviceptr (<cuda.h>); this typedef is
+ * ABI-identical, so tracer.h does not need the CUDA headers.  futhark_new_raw_* COPIES dim0*... elements from device memory
+ * at `data + offset` (offset in bytes) into a new array on the context's stream; futhark_values_raw_* returns the array's own
+ * device memory, valid until the array is freed (work queued by the library is complete after futhark_context_sync). */
+typedef unsigned long long futhark_deviceptr;
+struct futhark_f32_1d *futhark_new_raw_f32_1d(struct futhark_context *ctx, const futhark_deviceptr data, int offset, int64_t dim0);
+struct futhark_f32_2d *futhark_new_raw_f32_2d(struct futhark_context *ctx, const futhark_deviceptr data, int offset, int64_t dim0, int64_t dim1);
+struct futhark_f32_3d *futhark_new_raw_f32_3d(struct futhark_context *ctx, const futhark_deviceptr data, int offset, int64_t dim0, int64_t dim1, int64_t dim2);
+struct futhark_u32_1d *futhark_new_raw_u32_1d(struct futhark_context *ctx, const futhark_deviceptr data, int offset, int64_t dim0);
+struct futhark_i32_2d *futhark_new_raw_i32_2d(struct futhark_context *ctx, const futhark_deviceptr data, int offset, int64_t dim0, int64_t dim1);
+futhark_deviceptr futhark_values_raw_f32_1d(struct futhark_context *ctx, struct futhark_f32_1d *arr);
+futhark_deviceptr futhark_values_raw_f32_2d(struct futhark_context *ctx, struct futhark_f32_2d *arr);
+futhark_deviceptr futhark_values_raw_f32_3d(struct futhark_context *ctx, struct futhark_f32_3d *arr);
+futhark_deviceptr futhark_values_raw_u32_1d(struct futhark_context *ctx, struct futhark_u32_1d *arr);
+futhark_deviceptr futhark_values_raw_i32_2d(struct futhark_context *ctx, struct futhark_i32_2d *arr);
+
 #ifdef __cplusplus
 }
 #endif

@@ -23,7 +23,7 @@
 using namespace lys;
 
 /* ------------------------------------------------------------------ objects */
-struct futhark_context_config { int device = 0; std::string device_name; int debugging = 0; int logging = 0; };
+struct futhark_context_config { int device = 0; std::string device_name; int debugging = 0; int logging = 0; int profiling = 0; };
 
 struct futhark_context {
     int device = 0;
@@ -413,6 +413,7 @@ struct futhark_context *futhark_context_new(struct futhark_context_config *cfg) 
     }
     futhark_context *ctx = new futhark_context();
     ctx->device = dev; ctx->logging = cfg ? cfg->logging : 0;
+    ctx->timer.on = cfg && cfg->profiling;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return nullptr; }
     cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1); cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
     { const char *pe = getenv("LYS_PIPELINE"); if (pe) { int v = atoi(pe); if (v >= 1 && v <= 16) ctx->pipeline = v; } }
@@ -456,6 +457,40 @@ int futhark_context_clear_caches(struct futhark_context *ctx) {
     ctx->pool.clear();
     return 0;
 }
+/* the rest of the generated cuda-backend surface (tracer.h): no run-time compilation, no tunable sizes */
+void futhark_context_config_set_profiling(struct futhark_context_config *cfg, int flag) { if (cfg) cfg->profiling = flag; }
+void futhark_context_config_add_nvrtc_option(struct futhark_context_config *cfg, const char *opt) { (void)cfg; (void)opt; }
+void futhark_context_config_dump_program_to(struct futhark_context_config *cfg, const char *path) { (void)cfg; (void)path; }
+void futhark_context_config_load_program_from(struct futhark_context_config *cfg, const char *path) { (void)cfg; (void)path; }
+void futhark_context_config_dump_ptx_to(struct futhark_context_config *cfg, const char *path) { (void)cfg; (void)path; }
+void futhark_context_config_load_ptx_from(struct futhark_context_config *cfg, const char *path) { (void)cfg; (void)path; }
+void futhark_context_config_set_default_group_size(struct futhark_context_config *cfg, int size) { (void)cfg; (void)size; }
+void futhark_context_config_set_default_num_groups(struct futhark_context_config *cfg, int num) { (void)cfg; (void)num; }
+void futhark_context_config_set_default_tile_size(struct futhark_context_config *cfg, int num) { (void)cfg; (void)num; }
+void futhark_context_config_set_default_threshold(struct futhark_context_config *cfg, int num) { (void)cfg; (void)num; }
+int futhark_context_config_set_size(struct futhark_context_config *cfg, const char *size_name, size_t size_value) { (void)cfg; (void)size_name; (void)size_value; return 1; }
+int futhark_get_num_sizes(void) { return 0; }
+const char *futhark_get_size_name(int i) { (void)i; return nullptr; }
+const char *futhark_get_size_class(int i) { (void)i; return nullptr; }
+void futhark_context_pause_profiling(struct futhark_context *ctx) { if (ctx) { ctx->timer.resolve(ctx->stream); ctx->timer.on = false; } }
+void futhark_context_unpause_profiling(struct futhark_context *ctx) { if (ctx) ctx->timer.on = true; }
+char *futhark_context_report(struct futhark_context *ctx) {
+    if (!ctx) return nullptr;
+    ctx->timer.resolve(ctx->stream);
+    static const char *const cls[LYS_PROFILE_CLASSES] = {"generate", "trace", "shade", "tail", "accumulate"};
+    size_t pooled = 0;
+    for (auto &kv : ctx->pool) pooled += kv.first;
+    std::string r = "libtracer (sm_100a): " + std::to_string((unsigned long long)ctx->launches) + " kernel launches, " +
+                    std::to_string((unsigned long long)pooled) + " bytes of device memory pooled for reuse\n";
+    char line[160];
+    for (int i = 0; i < LYS_PROFILE_CLASSES; i++) {
+        if (!ctx->timer.n[i]) continue;
+        snprintf(line, sizeof line, "%-10s ran %8llu times; avg: %8.1fus; total: %10.1fus\n", cls[i], (unsigned long long)ctx->timer.n[i],
+                 1e3 * ctx->timer.ms[i] / (double)ctx->timer.n[i], 1e3 * ctx->timer.ms[i]);
+        r += line;
+    }
+    return strdup(r.c_str());
+}
 char *futhark_context_get_error(struct futhark_context *ctx) {
     if (!ctx) return nullptr;
     char *r = strdup(ctx->error.c_str());
@@ -471,7 +506,12 @@ char *futhark_context_get_error(struct futhark_context *ctx) {
     }                                                                                                                 \
     int futhark_free_##NAME(struct futhark_context *ctx, struct futhark_##NAME *arr) { (void)ctx; delete arr; return 0; } \
     int futhark_values_##NAME(struct futhark_context *ctx, struct futhark_##NAME *arr, T *data) { return array_values(ctx, arr, data); } \
-    const int64_t *futhark_shape_##NAME(struct futhark_context *ctx, struct futhark_##NAME *arr) { (void)ctx; return arr ? arr->shape : nullptr; }
+    const int64_t *futhark_shape_##NAME(struct futhark_context *ctx, struct futhark_##NAME *arr) { (void)ctx; return arr ? arr->shape : nullptr; } \
+    struct futhark_##NAME *futhark_new_raw_##NAME(struct futhark_context *ctx, const futhark_deviceptr data, int offset, DIMS_DECL) { \
+        int64_t shape[RANK] = DIMS_INIT;                                                                              \
+        return new_array<futhark_##NAME, T>(ctx, (const T *)(uintptr_t)(data + (unsigned long long)(long long)offset), shape, RANK, cudaMemcpyDeviceToDevice); \
+    }                                                                                                                 \
+    futhark_deviceptr futhark_values_raw_##NAME(struct futhark_context *ctx, struct futhark_##NAME *arr) { (void)ctx; return arr ? (futhark_deviceptr)(uintptr_t)arr->mem->p : 0; }
 #define LYS_D1 int64_t dim0
 #define LYS_D2 int64_t dim0, int64_t dim1
 #define LYS_D3 int64_t dim0, int64_t dim1, int64_t dim2

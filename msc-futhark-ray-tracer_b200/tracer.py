@@ -80,6 +80,18 @@ def _load():
         g = getattr(L, 'futhark_shape_' + nm)
         g.restype = C.POINTER(C.c_int64)
         g.argtypes = [vp, vp]
+        r = getattr(L, 'futhark_new_raw_' + nm)                 # device-to-device copy from (CUdeviceptr, byte offset)
+        r.restype = vp
+        r.argtypes = [vp, C.c_uint64, C.c_int] + [C.c_int64] * rank
+        v = getattr(L, 'futhark_values_raw_' + nm)              # the array's own device memory (CUdeviceptr)
+        v.restype = C.c_uint64
+        v.argtypes = [vp, vp]
+    L.futhark_context_config_set_profiling.argtypes = [vp, C.c_int]
+    L.futhark_context_pause_profiling.argtypes = [vp]
+    L.futhark_context_unpause_profiling.argtypes = [vp]
+    L.futhark_context_report.restype = vp
+    L.futhark_context_report.argtypes = [vp]
+    L.futhark_context_clear_caches.argtypes = [vp]
     L.futhark_free_opaque_state.argtypes = [vp, vp]
     L.futhark_entry_init.argtypes = [vp, C.POINTER(vp), C.c_int32, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp, vp, C.c_float, C.c_float, vp]
     L.futhark_entry_resize.argtypes = [vp, C.POINTER(vp), C.c_uint32, C.c_uint32, vp]
@@ -160,12 +172,14 @@ def load_obj(path):
 class Context:
     """futhark_context_config_new + futhark_context_new (liblys.c:166-209)."""
 
-    def __init__(self, device=None):
+    def __init__(self, device=None, profiling=False):
         L = _load()
         self._L = L
         cfg = L.futhark_context_config_new()
         if device is not None:
             L.futhark_context_config_set_device(cfg, str(device).encode())
+        if profiling:
+            L.futhark_context_config_set_profiling(cfg, 1)
         self._ctx = L.futhark_context_new(cfg)
         L.futhark_context_config_free(cfg)
         if not self._ctx:
@@ -192,6 +206,14 @@ class Context:
 
     def sync(self):
         self.check(self._L.futhark_context_sync(self._ctx), 'futhark_context_sync')
+
+    def report(self):
+        """futhark_context_report: launches, device time per kernel class (when profiling), pooled device memory."""
+        p = self._L.futhark_context_report(self._ctx)
+        txt = C.string_at(p).decode() if p else ''
+        if p:
+            _libc.free(p)
+        return txt
 
     # knobs (lys_ext.h)
     def set_path_len(self, n):

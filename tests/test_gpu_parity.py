@@ -266,6 +266,44 @@ def test_row_partition_sums_to_full_image(pkg, gpu, scenes):
     assert bits_equal(acc, full)
 
 
+def test_generated_surface_extras(pkg, gpu, scenes):
+    """The rest of a `futhark cuda --library` header (tracer.h, last section): raw device access, profiling report."""
+    L, c = gpu._L, gpu._ctx
+    a = np.arange(2 * 3 * 5, dtype=np.float32).reshape(2, 3, 5)
+    arr = L.futhark_new_f32_3d(c, a.ctypes.data, 2, 3, 5)
+    dptr = L.futhark_values_raw_f32_3d(c, arr)
+    assert dptr != 0
+    cp = L.futhark_new_raw_f32_3d(c, dptr, 5 * 4, 1, 5, 5)               # 25 elements starting one row (20 bytes) in
+    out = np.empty((1, 5, 5), np.float32)
+    gpu.check(L.futhark_values_f32_3d(c, cp, out.ctypes.data), 'values')
+    assert np.array_equal(out.reshape(-1), a.reshape(-1)[5:30])
+    assert L.futhark_values_raw_f32_3d(c, cp) != dptr                      # new_raw copies, it does not alias
+    L.futhark_free_f32_3d(c, cp); L.futhark_free_f32_3d(c, arr)
+    u = np.arange(7, dtype=np.uint32)
+    ua = L.futhark_new_u32_1d(c, u.ctypes.data, 7)
+    ub = L.futhark_new_raw_u32_1d(c, L.futhark_values_raw_u32_1d(c, ua), 0, 7)
+    back = np.empty(7, np.uint32)
+    gpu.check(L.futhark_values_u32_1d(c, ub, back.ctypes.data), 'values')
+    assert np.array_equal(back, u)
+    L.futhark_free_u32_1d(c, ua); L.futhark_free_u32_1d(c, ub)
+    assert L.futhark_get_num_sizes() == 0 and L.futhark_context_config_set_size(None, b'x', 1) == 1
+    t, tm, m = scenes['cornell']
+    with pkg.Context(profiling=True) as pc:                                # futhark_context_config_set_profiling
+        s = pkg.State.init(pc, t, tm, m, 48, 64)
+        img = s.sample_n_frames(3)
+        rep = pc.report()
+        assert 'kernel launches' in rep and 'trace' in rep and 'shade' in rep and 'accumulate' in rep
+        L.futhark_context_pause_profiling(pc._ctx)
+        n0 = pc.profile(reset=False)['trace'][1]
+        s.sample_n_frames(2)
+        assert pc.profile(reset=False)['trace'][1] == n0                   # paused: nothing recorded
+        L.futhark_context_unpause_profiling(pc._ctx)
+        s.sample_n_frames(1)
+        assert pc.profile(reset=False)['trace'][1] > n0
+        s.free()
+    assert bits_equal(img, pkg.State.init(gpu, t, tm, m, 48, 64).sample_n_frames(3))   # profiling does not change results
+
+
 def test_error_behaviour(pkg, gpu, scenes):
     t, tm, m = scenes['cornell']
     with pytest.raises(pkg.TracerError, match='at least 2 triangles'):
