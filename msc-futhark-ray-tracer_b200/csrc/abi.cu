@@ -183,6 +183,7 @@ namespace {
 
 template <class A, class T> A *new_array(futhark_context *ctx, const T *data, const int64_t *shape, int rank, cudaMemcpyKind kind) {
     if (!ctx) return nullptr;
+    cudaSetDevice(ctx->device);          /* a host may hold contexts on several devices */
     A *a = new A();
     int64_t c = 1;
     for (int i = 0; i < rank; i++) { a->shape[i] = shape[i]; c *= shape[i]; }
@@ -197,6 +198,7 @@ template <class A, class T> A *new_array(futhark_context *ctx, const T *data, co
 }
 template <class A, class T> int array_values(futhark_context *ctx, A *a, T *out) {
     if (!ctx || !a || !out) { if (ctx) set_error(ctx, "null argument"); return 1; }
+    cudaSetDevice(ctx->device);
     CU(ctx, cudaMemcpyAsync(out, a->mem->p, sizeof(T) * (size_t)a->count(), cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     return 0;
@@ -452,6 +454,7 @@ int futhark_context_sync(struct futhark_context *ctx) {
 }
 int futhark_context_clear_caches(struct futhark_context *ctx) {
     if (!ctx) return 1;
+    cudaSetDevice(ctx->device);
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     for (auto &kv : ctx->pool) cudaFree(kv.second);
     ctx->pool.clear();
