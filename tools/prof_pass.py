@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""A few 1080p CornellBox sample passes (profiling target for ncu)."""
+"""A few sample passes (profiling target for ncu): tools/prof_pass.py [scene] [passes]; scene = a bundled scene name or
+`synthetic` (BASELINE config 5: 1 003 244 triangles); LYS_H / LYS_W set the frame (default 1080 x 1920)."""
 import importlib, os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -7,7 +8,9 @@ sys.path.insert(0, ROOT)
 pkg = importlib.import_module('msc-futhark-ray-tracer_b200')
 name = sys.argv[1] if len(sys.argv) > 1 else 'cornell'
 passes = int(sys.argv[2]) if len(sys.argv) > 2 else 2
-d = np.load(os.path.join(ROOT, 'tests', 'golden', 'scenes', name + '.npz'))
+d = dict(np.load(os.path.join(ROOT, 'tests', 'golden', 'scenes', ('cornell' if name == 'synthetic' else name) + '.npz')))
+if name == 'synthetic':
+    d['tris'], d['tri_mats'] = pkg.scenes.synthetic_cornell(d['tris'], d['tri_mats'], int(os.environ.get('LYS_K', 151)))
 ctx = pkg.Context()
 kw = {'origin': (0.0, 0.8, 0.6)} if name == 'mirrorbox' else {}
 H, W = (int(os.environ.get('LYS_H', 1080)), int(os.environ.get('LYS_W', 1920)))
