@@ -8,6 +8,7 @@ candidate slot order and counts what a lock-step warp issues for a candidate loo
 
   python tools/simt_model.py orders    [scene] [h w]   ray orderings (pixel order, octant sorts, walk-length bound)
   python tools/simt_model.py schedules [scene] [h w]   loop shapes: stages per iteration ('B' box, 'T' triangle)
+  scene: a bundled scene or `synthetic[:k]` (BASELINE config 5); LYS_MODEL_MAX_STEPS bounds the modelled walk length (400)
 
 Loop shapes: 'X' = one visit per lane and iteration (the first k_trace); 'BT', 'BBT', ... = every iteration runs the
 listed stages in order and a lane takes part in a stage if its next visit has that type (k_trace today: 'BBT');
@@ -28,18 +29,46 @@ from lysref import oracle as orc  # noqa: E402
 BOX, TRI, LOOP = 45, 60, 6
 
 
+MAX_STEPS = 400
+
+
+def load_scene(scene):
+    """a bundled scene name, or `synthetic` / `synthetic:k` = BASELINE config 5 (every Cornell quad as a k x k grid, k = 151)"""
+    name, _, k = scene.partition(':')
+    d = dict(np.load(os.path.join(ROOT, 'tests', 'golden', 'scenes', ('cornell' if name == 'synthetic' else name) + '.npz')))
+    if name == 'synthetic':
+        sys.path.insert(0, ROOT)
+        import importlib
+        scenes = importlib.import_module('msc-futhark-ray-tracer_b200.scenes')
+        d['tris'], d['tri_mats'] = scenes.synthetic_cornell(d['tris'], d['tri_mats'], int(k or 151))
+    return d
+
+
 def bounce_rays(scene, h, w):
-    d = np.load(os.path.join(ROOT, 'tests', 'golden', 'scenes', scene + '.npz'))
+    d = load_scene(scene)
     st = orc.State.init(d['tris'], d['tri_mats'], d['mats'], h, w)
     rays, nr = st.probe_path_rays()
     rays, nr = rays.reshape(-1, 16, 6), nr.reshape(-1)
-    print(f'{scene} {w}x{h}: closest-hit rays per path {nr.mean():.3f}')
+    print(f'{scene} {w}x{h}: {len(d["tris"])} triangles, closest-hit rays per path {nr.mean():.3f}')
     for b in (0, 1, 2):
         live = np.nonzero(nr > b)[0]                       # pixel order == the compacted slot order k_shade produces
         r = rays[live, b]
-        pat, ln = st.closest_hits_pattern(r, 400)
-        assert ln.max() <= 400
+        pat, ln = st.closest_hits_pattern(r, MAX_STEPS)
+        if ln.max() > MAX_STEPS:
+            print(f'   (bounce {b}: {int((ln > MAX_STEPS).sum())} walks longer than {MAX_STEPS} visits are truncated in the model)')
+            ln = np.minimum(ln, MAX_STEPS)
         yield b, r, pat, ln
+
+
+def morton_cells(p, bits):
+    """Morton index of points on a 2^bits grid over their bounding box"""
+    lo, hi = p.min(axis=0), p.max(axis=0)
+    q = np.minimum(((p - lo) / np.maximum(hi - lo, 1e-20) * (1 << bits)).astype(np.int64), (1 << bits) - 1)
+    code = np.zeros(len(p), np.int64)
+    for bit in range(bits):
+        for ax in range(3):
+            code |= ((q[:, ax] >> bit) & 1) << (3 * bit + (2 - ax))
+    return code
 
 
 def schedule_cost(pat, ln, order, stages, costs):
@@ -85,6 +114,49 @@ def schedule_cost(pat, ln, order, stages, costs):
     return total / n, iters / (len(p) // 32)
 
 
+def refill_cost(pat, ln, order, slice_len, keep, costs, refill=30):
+    """k_trace_refill (LYS_TRACE_MODE=1): a warp owns a contiguous slice of `slice_len` rays; every lane does ONE visit per
+    step; when fewer than `keep` lanes are busy (or the warp is empty) the idle lanes pull the next rays of the slice
+    (`refill` warp instructions per refill round).  Returns warp instructions per ray and steps per warp."""
+    p = pat[order]
+    l = ln[order].astype(np.int64)
+    n = len(p)
+    kind = np.where(p <= 1, 0, np.where(p <= 3, 1, 2)).astype(np.int8)
+    n_warps = (n + slice_len - 1) // slice_len
+    cursor = np.arange(n_warps, dtype=np.int64) * slice_len
+    end = np.minimum(cursor + slice_len, n)
+    ray = np.full((n_warps, 32), -1, np.int64)               # ray of each lane, -1 = idle
+    ptr = np.zeros((n_warps, 32), np.int64)
+    total = steps = 0
+    while True:
+        busy = ray >= 0
+        nb = busy.sum(axis=1)
+        want = ((nb < keep) | (nb == 0)) & (cursor < end)    # refill round
+        if want.any():
+            for wi in np.nonzero(want)[0]:
+                idle = np.nonzero(ray[wi] < 0)[0]
+                take = min(len(idle), int(end[wi] - cursor[wi]))
+                ray[wi, idle[:take]] = cursor[wi] + np.arange(take)
+                ptr[wi, idle[:take]] = 0
+                cursor[wi] += take
+            total += refill * int(want.sum())
+            busy = ray >= 0
+        # lanes whose ray has no visits at all finish at once
+        if not busy.any():
+            break
+        rr = np.where(busy, ray, 0)
+        k = np.where(busy, kind[rr, np.minimum(ptr, kind.shape[1] - 1)], 2)
+        done0 = busy & (ptr >= l[rr])
+        k = np.where(done0, 2, k)
+        aw = busy.any(axis=1)
+        steps += int(aw.sum())
+        total += costs['loop'] * int(aw.sum()) + costs['B'] * int((k == 0).any(axis=1).sum()) + costs['T'] * int((k == 1).any(axis=1).sum())
+        ptr = ptr + busy
+        fin = busy & (ptr >= l[rr])
+        ray = np.where(fin, -1, ray)
+    return total / n, steps / n_warps
+
+
 def lane_stats(pat, order):
     p = pat[order]
     pad = (-len(p)) % 32
@@ -107,6 +179,10 @@ def study_orders(scene, h, w):
             orders[f'octant sort within blocks of {blk} live rays'] = np.argsort((base // blk) * 8 + octant, kind='stable')
         orders['global octant sort'] = np.argsort(octant, kind='stable')
         orders['global octant + dominant axis'] = np.argsort(octant * 3 + dom, kind='stable')
+        for bits in (2, 4):                                 # spatial sorts: rays that start in the same cell and head into the same octant
+            cell = morton_cells(r[:, :3].astype(np.float64), bits)
+            orders[f'origin cell ({1 << bits}^3) then octant'] = np.argsort(cell * 8 + octant, kind='stable')
+            orders[f'octant then origin cell ({1 << bits}^3)'] = np.argsort(octant * (1 << (3 * bits)) + cell, kind='stable')
         orders['sorted by walk length (bound)'] = np.argsort(ln, kind='stable')
         print(f'bounce {b}: {n} rays, visits per ray mean {ln.mean():.1f} max {ln.max()}')
         for k, o in orders.items():
@@ -124,10 +200,15 @@ def study_schedules(scene, h, w):
             for stages in ('X', 'BT', 'BBT', 'BBBT', 'BTT', 'BBTT', 'B*T'):
                 c, it = schedule_cost(pat, ln, base, stages, costs)
                 print(f'   box {box} tri {tri}  {stages:5s} {c:7.1f} warp-instr/ray  {it:5.1f} iters/warp')
+            for slice_len in (128, 1024):
+                for keep in (20, 28):
+                    c, it = refill_cost(pat, ln, base, slice_len, keep, costs)
+                    print(f'   box {box} tri {tri}  refill: slices of {slice_len}, refill below {keep} busy lanes {c:7.1f} warp-instr/ray  {it:7.1f} steps/warp')
 
 
 if __name__ == '__main__':
     what = sys.argv[1] if len(sys.argv) > 1 else 'orders'
     scene = sys.argv[2] if len(sys.argv) > 2 else 'cornell'
     h, w = (int(sys.argv[3]), int(sys.argv[4])) if len(sys.argv) > 4 else (270, 480)
+    MAX_STEPS = int(os.environ.get('LYS_MODEL_MAX_STEPS', MAX_STEPS))
     (study_schedules if what == 'schedules' else study_orders)(scene, h, w)
