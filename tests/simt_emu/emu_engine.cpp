@@ -1,0 +1,206 @@
+/* emu_engine.cpp -- the CPU SIMT engine and the stand-in CUDA runtime of the emulator build (TEST INFRASTRUCTURE, see
+ * tests/simt_emu/README.md and cuda_runtime.h in this directory).
+ *
+ * Execution model: a launch runs its CTAs one after another (in blockIdx order).  Inside a CTA every GPU thread is a
+ * fiber (ucontext) with its own stack; the scheduler runs the lanes of a warp one at a time until each has finished or
+ * parked at a collective.  When every live lane of a warp is parked at a warp collective the results are computed and
+ * the lanes continue; when every live lane of the CTA is parked at __syncthreads the barrier opens.  Lanes that have
+ * returned from the kernel do not take part (as on the hardware).  Because a lane only stops at collectives, code between
+ * two collectives is atomic with respect to the other lanes, which makes plain read-modify-write a correct atomicAdd, and
+ * spinning on a flag is only safe if the flag was set by an EARLIER CTA (true for the ticketed onesweep look-back).
+ * The arithmetic is the host compiler's IEEE f32 with -ffp-contract=off, i.e. the contract of include/lys_detmath.h.
+ */
+#include "cuda_runtime.h"
+#include <ucontext.h>
+#include <sys/mman.h>
+#include <chrono>
+#include <cstdio>
+#include <vector>
+
+namespace emu {
+
+uint3 g_block_idx = {0, 0, 0}, g_block_dim = {1, 1, 1}, g_grid_dim = {1, 1, 1};
+
+namespace {
+enum St { ST_RUN = 0, ST_WARP, ST_CTA, ST_DONE };
+struct Lane {
+    ucontext_t ctx;
+    uint3 tid;
+    int st, op;
+    uint32_t a, b, out;
+};
+const int MAX_LANES = 1024;
+const size_t STACK_BYTES = 512 * 1024;
+Lane *g_lanes = nullptr;
+char *g_stacks = nullptr;
+Lane *g_cur = nullptr;
+ucontext_t g_sched;
+const std::function<void()> *g_body = nullptr;
+std::vector<char> g_smem;
+Stats g_stats = {0, 0, 0, 0, 0};
+uint3 g_no_tid = {0, 0, 0};
+
+[[noreturn]] void fatal(const char *msg) {
+    fprintf(stderr, "simt_emu: %s (block %u, lane %d)\n", msg, g_block_idx.x, g_cur ? (int)(g_cur - g_lanes) : -1);
+    abort();
+}
+void trampoline() {
+    (*g_body)();
+    g_cur->st = ST_DONE;            /* returning resumes uc_link = the scheduler */
+}
+void park(int st) {
+    Lane *me = g_cur;
+    if (!me) fatal("collective called outside a kernel");
+    me->st = st;
+    swapcontext(&me->ctx, &g_sched);
+}
+void resolve_warp(Lane *w, int n) {
+    int op = 0;
+    for (int l = 0; l < n; l++) if (w[l].st == ST_WARP) { if (!op) op = w[l].op; else if (op != w[l].op) fatal("lanes of one warp wait at different collectives"); }
+    g_stats.warp_collectives++;
+    switch (op) {
+        case OP_BALLOT: {
+            uint32_t m = 0;
+            for (int l = 0; l < n; l++) if (w[l].st == ST_WARP && (w[l].a & 1u)) m |= 1u << l;
+            for (int l = 0; l < n; l++) w[l].out = m;
+            break;
+        }
+        case OP_SHFL: case OP_SHFL_XOR:
+            for (int l = 0; l < n; l++) {
+                if (w[l].st != ST_WARP) continue;
+                int src = (op == OP_SHFL) ? (int)(w[l].b & 31u) : (l ^ (int)(w[l].b & 31u));
+                w[l].out = (src < n && w[src].st == ST_WARP) ? w[src].a : w[l].a;
+            }
+            break;
+        case OP_REDUCE_ADD: {
+            uint32_t s = 0;
+            for (int l = 0; l < n; l++) if (w[l].st == ST_WARP) s += w[l].a;
+            for (int l = 0; l < n; l++) w[l].out = s;
+            break;
+        }
+        case OP_MATCH_ANY:
+            for (int l = 0; l < n; l++) {
+                if (w[l].st != ST_WARP) continue;
+                uint32_t m = 0;
+                for (int k = 0; k < n; k++) if (w[k].st == ST_WARP && w[k].a == w[l].a) m |= 1u << k;
+                w[l].out = m;
+            }
+            break;
+        case OP_SYNCWARP: break;
+        default: fatal("unknown collective");
+    }
+    for (int l = 0; l < n; l++) if (w[l].st == ST_WARP) w[l].st = ST_RUN;
+}
+void run_cta(int n) {
+    if (n > MAX_LANES) fatal("CTA larger than 1024 threads");
+    if (!g_lanes) {
+        g_lanes = new Lane[MAX_LANES];
+        g_stacks = (char *)mmap(nullptr, STACK_BYTES * MAX_LANES, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+        if (g_stacks == (char *)MAP_FAILED) fatal("mmap of the lane stacks failed");
+    }
+    const unsigned bx = g_block_dim.x, by = g_block_dim.y;
+    for (int t = 0; t < n; t++) {
+        Lane &L = g_lanes[t];
+        getcontext(&L.ctx);
+        L.ctx.uc_stack.ss_sp = g_stacks + (size_t)t * STACK_BYTES;
+        L.ctx.uc_stack.ss_size = STACK_BYTES;
+        L.ctx.uc_link = &g_sched;
+        makecontext(&L.ctx, trampoline, 0);
+        L.tid.x = (unsigned)t % bx; L.tid.y = ((unsigned)t / bx) % by; L.tid.z = (unsigned)t / (bx * by);
+        L.st = ST_RUN; L.op = 0; L.a = L.b = L.out = 0;
+    }
+    g_stats.ctas++; g_stats.lanes += (uint64_t)n;
+    const int nw = (n + 31) / 32;
+    while (true) {
+        bool progress = false;
+        int done = 0, at_cta = 0;
+        for (int w = 0; w < nw; w++) {
+            Lane *W = g_lanes + 32 * w;
+            const int wn = (n - 32 * w < 32) ? n - 32 * w : 32;
+            while (true) {
+                for (int l = 0; l < wn; l++)
+                    if (W[l].st == ST_RUN) { g_cur = &W[l]; swapcontext(&g_sched, &W[l].ctx); g_cur = nullptr; progress = true; }
+                int nW = 0, nC = 0, nD = 0;
+                for (int l = 0; l < wn; l++) { nW += W[l].st == ST_WARP; nC += W[l].st == ST_CTA; nD += W[l].st == ST_DONE; }
+                if (nW == 0) { done += nD; at_cta += nC; break; }
+                if (nC) fatal("a warp has lanes at a warp collective and lanes at __syncthreads");
+                resolve_warp(W, wn);
+            }
+        }
+        if (done == n) break;
+        if (at_cta + done == n) {
+            for (int t = 0; t < n; t++) if (g_lanes[t].st == ST_CTA) g_lanes[t].st = ST_RUN;
+            g_stats.cta_barriers++;
+            progress = true;
+        }
+        if (!progress) fatal("deadlock: no lane can run");
+    }
+}
+}  // namespace
+
+const uint3 &cur_tid() { return g_cur ? g_cur->tid : g_no_tid; }
+uint32_t warp_collective(Op op, uint32_t a, uint32_t b) {
+    Lane *me = g_cur;
+    if (!me) fatal("warp collective called outside a kernel");
+    me->op = op; me->a = a; me->b = b;
+    park(ST_WARP);
+    return me->out;
+}
+void cta_barrier() { park(ST_CTA); }
+void *dyn_smem() { return g_smem.data(); }
+Stats stats() { return g_stats; }
+
+void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()> &body) {
+    if (g_cur) fatal("nested launch");
+    const int n = (int)(block.x * block.y * block.z);
+    if (n <= 0 || grid.x == 0 || grid.y == 0 || grid.z == 0) return;
+    g_smem.assign(smem + 16, 0);
+    g_body = &body;
+    g_grid_dim = {grid.x, grid.y, grid.z};
+    g_block_dim = {block.x, block.y, block.z};
+    g_stats.launches++;
+    for (unsigned z = 0; z < grid.z; z++)
+        for (unsigned y = 0; y < grid.y; y++)
+            for (unsigned x = 0; x < grid.x; x++) { g_block_idx = {x, y, z}; run_cta(n); }
+    g_body = nullptr;
+}
+
+}  // namespace emu
+
+/* ------------------------------------------------------------------ stand-in runtime */
+struct emu_stream { int id; };
+struct emu_event { double ms; };
+static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+static int env_int(const char *name, int dflt) { const char *e = getenv(name); return (e && *e) ? atoi(e) : dflt; }
+
+const char *cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : (e == cudaErrorMemoryAllocation ? "out of memory" : "invalid value"); }
+cudaError_t cudaGetLastError() { return cudaSuccess; }
+cudaError_t cudaGetDeviceCount(int *n) { *n = env_int("LYS_EMU_DEVICES", 1); return cudaSuccess; }
+cudaError_t cudaGetDevice(int *d) { *d = 0; return cudaSuccess; }
+cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+cudaError_t cudaGetDeviceFlags(unsigned int *f) { *f = 0; return cudaSuccess; }
+cudaError_t cudaSetDeviceFlags(unsigned int) { return cudaSuccess; }
+cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int) { memset(p, 0, sizeof *p); strcpy(p->name, "lys SIMT emulator (CPU)"); p->multiProcessorCount = env_int("LYS_EMU_SMS", 4); return cudaSuccess; }
+cudaError_t cudaDeviceGetAttribute(int *v, cudaDeviceAttr, int) { *v = env_int("LYS_EMU_SMS", 4); return cudaSuccess; }
+cudaError_t cudaMalloc(void **p, size_t n) { void *q = nullptr; if (posix_memalign(&q, 256, n ? n : 1)) { *p = nullptr; return cudaErrorMemoryAllocation; } *p = q; return cudaSuccess; }
+cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }
+cudaError_t cudaHostAlloc(void **p, size_t n, unsigned int) { return cudaMalloc(p, n); }
+cudaError_t cudaFreeHost(void *p) { free(p); return cudaSuccess; }
+cudaError_t cudaMemcpy(void *dst, const void *src, size_t n, cudaMemcpyKind) { if (n) memmove(dst, src, n); return cudaSuccess; }
+cudaError_t cudaMemcpyAsync(void *dst, const void *src, size_t n, cudaMemcpyKind, cudaStream_t) { if (n) memmove(dst, src, n); return cudaSuccess; }
+cudaError_t cudaMemsetAsync(void *p, int v, size_t n, cudaStream_t) { if (n) memset(p, v, n); return cudaSuccess; }
+cudaError_t cudaStreamCreate(cudaStream_t *s) { *s = new emu_stream{0}; return cudaSuccess; }
+cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned int) { return cudaStreamCreate(s); }
+cudaError_t cudaStreamDestroy(cudaStream_t s) { delete s; return cudaSuccess; }
+cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned int) { return cudaSuccess; }
+cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = new emu_event{0.0}; return cudaSuccess; }
+cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned int) { return cudaEventCreate(e); }
+cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
+cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t) { if (e) e->ms = now_ms(); return cudaSuccess; }
+cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b) { *ms = (float)(b->ms - a->ms); return cudaSuccess; }
+
+extern "C" void lys_emu_stats(uint64_t *out5) {
+    emu::Stats s = emu::stats();
+    out5[0] = s.launches; out5[1] = s.ctas; out5[2] = s.lanes; out5[3] = s.warp_collectives; out5[4] = s.cta_barriers;
+}
