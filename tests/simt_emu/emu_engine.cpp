@@ -2,7 +2,7 @@
  * tests/simt_emu/README.md and cuda_runtime.h in this directory).
  *
  * Execution model: a launch runs its CTAs one after another (in blockIdx order).  Inside a CTA every GPU thread is a
- * fiber (ucontext) with its own stack; the scheduler runs the lanes of a warp one at a time until each has finished or
+ * fiber with its own stack (a six-register context switch on x86-64, ucontext elsewhere); the scheduler runs the lanes of a warp one at a time until each has finished or
  * parked at a collective.  When every live lane of a warp is parked at a warp collective the results are computed and
  * the lanes continue; when every live lane of the CTA is parked at __syncthreads the barrier opens.  Lanes that have
  * returned from the kernel do not take part (as on the hardware).  Because a lane only stops at collectives, code between
@@ -11,8 +11,22 @@
  * The arithmetic is the host compiler's IEEE f32 with -ffp-contract=off, i.e. the contract of include/lys_detmath.h.
  */
 #include "cuda_runtime.h"
-#include <ucontext.h>
 #include <sys/mman.h>
+#if defined(__x86_64__) && !defined(LYS_EMU_UCONTEXT)
+/* a context switch is six callee-saved registers and the stack pointer (System V x86-64); glibc's swapcontext would add a
+ * sigprocmask system call per switch, and a pass makes millions of switches */
+#define LYS_EMU_ASM_SWITCH 1
+struct emu_ctx { void *sp; };
+extern "C" void lys_emu_switch(emu_ctx *from, emu_ctx *to);
+asm(".text\n.globl lys_emu_switch\n.type lys_emu_switch,@function\nlys_emu_switch:\n"
+    "    pushq %rbp\n    pushq %rbx\n    pushq %r12\n    pushq %r13\n    pushq %r14\n    pushq %r15\n"
+    "    movq %rsp, (%rdi)\n    movq (%rsi), %rsp\n"
+    "    popq %r15\n    popq %r14\n    popq %r13\n    popq %r12\n    popq %rbx\n    popq %rbp\n    ret\n"
+    ".size lys_emu_switch, .-lys_emu_switch\n");
+#else
+#include <ucontext.h>
+typedef ucontext_t emu_ctx;
+#endif
 #include <chrono>
 #include <cstdio>
 #include <vector>
@@ -24,7 +38,7 @@ uint3 g_block_idx = {0, 0, 0}, g_block_dim = {1, 1, 1}, g_grid_dim = {1, 1, 1};
 namespace {
 enum St { ST_RUN = 0, ST_WARP, ST_CTA, ST_DONE };
 struct Lane {
-    ucontext_t ctx;
+    emu_ctx ctx;
     uint3 tid;
     int st, op;
     uint32_t a, b, out;
@@ -34,7 +48,7 @@ const size_t STACK_BYTES = 512 * 1024;
 Lane *g_lanes = nullptr;
 char *g_stacks = nullptr;
 Lane *g_cur = nullptr;
-ucontext_t g_sched;
+emu_ctx g_sched;
 const std::function<void()> *g_body = nullptr;
 std::vector<char> g_smem;
 Stats g_stats = {0, 0, 0, 0, 0};
@@ -44,15 +58,43 @@ uint3 g_no_tid = {0, 0, 0};
     fprintf(stderr, "simt_emu: %s (block %u, lane %d)\n", msg, g_block_idx.x, g_cur ? (int)(g_cur - g_lanes) : -1);
     abort();
 }
+#ifdef LYS_EMU_ASM_SWITCH
+void to_sched(Lane *me) { lys_emu_switch(&me->ctx, &g_sched); }
+void to_lane(Lane *l) { lys_emu_switch(&g_sched, &l->ctx); }
+void trampoline() {
+    (*g_body)();
+    g_cur->st = ST_DONE;
+    to_sched(g_cur);
+    abort();                        /* a finished lane is never resumed */
+}
+void init_lane(Lane &L, char *stack) {
+    /* first switch-in pops six registers and returns into trampoline() with the stack 8 mod 16, as after a call */
+    void **top = (void **)(((uintptr_t)stack + STACK_BYTES) & ~(uintptr_t)15);
+    *--top = nullptr;               /* trampoline's (unused) return address */
+    *--top = (void *)trampoline;
+    for (int k = 0; k < 6; k++) *--top = nullptr;
+    L.ctx.sp = top;
+}
+#else
+void to_sched(Lane *me) { swapcontext(&me->ctx, &g_sched); }
+void to_lane(Lane *l) { swapcontext(&g_sched, &l->ctx); }
 void trampoline() {
     (*g_body)();
     g_cur->st = ST_DONE;            /* returning resumes uc_link = the scheduler */
 }
+void init_lane(Lane &L, char *stack) {
+    getcontext(&L.ctx);
+    L.ctx.uc_stack.ss_sp = stack;
+    L.ctx.uc_stack.ss_size = STACK_BYTES;
+    L.ctx.uc_link = &g_sched;
+    makecontext(&L.ctx, trampoline, 0);
+}
+#endif
 void park(int st) {
     Lane *me = g_cur;
     if (!me) fatal("collective called outside a kernel");
     me->st = st;
-    swapcontext(&me->ctx, &g_sched);
+    to_sched(me);
 }
 void resolve_warp(Lane *w, int n) {
     int op = 0;
@@ -101,11 +143,7 @@ void run_cta(int n) {
     const unsigned bx = g_block_dim.x, by = g_block_dim.y;
     for (int t = 0; t < n; t++) {
         Lane &L = g_lanes[t];
-        getcontext(&L.ctx);
-        L.ctx.uc_stack.ss_sp = g_stacks + (size_t)t * STACK_BYTES;
-        L.ctx.uc_stack.ss_size = STACK_BYTES;
-        L.ctx.uc_link = &g_sched;
-        makecontext(&L.ctx, trampoline, 0);
+        init_lane(L, g_stacks + (size_t)t * STACK_BYTES);
         L.tid.x = (unsigned)t % bx; L.tid.y = ((unsigned)t / bx) % by; L.tid.z = (unsigned)t / (bx * by);
         L.st = ST_RUN; L.op = 0; L.a = L.b = L.out = 0;
     }
@@ -119,7 +157,7 @@ void run_cta(int n) {
             const int wn = (n - 32 * w < 32) ? n - 32 * w : 32;
             while (true) {
                 for (int l = 0; l < wn; l++)
-                    if (W[l].st == ST_RUN) { g_cur = &W[l]; swapcontext(&g_sched, &W[l].ctx); g_cur = nullptr; progress = true; }
+                    if (W[l].st == ST_RUN) { g_cur = &W[l]; to_lane(&W[l]); g_cur = nullptr; progress = true; }
                 int nW = 0, nC = 0, nD = 0;
                 for (int l = 0; l < wn; l++) { nW += W[l].st == ST_WARP; nC += W[l].st == ST_CTA; nD += W[l].st == ST_DONE; }
                 if (nW == 0) { done += nD; at_cta += nC; break; }
