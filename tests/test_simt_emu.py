@@ -53,3 +53,16 @@ def test_emulated_kernel_variants(emu_lib, env):
     e = dict(env)
     e['LYS_EMU_FAST_MATH_SWEEP'] = '1'
     check(sweep(emu_lib, ['cornell'], e))
+
+
+def test_gpu_parity_suite_on_the_emulator(emu_lib):
+    """tests/test_gpu_parity.py itself (the `-m gpu` parity tests: LBVH edge cases, fuzzed soup scenes, all camera presets,
+    entry points, LIDAR points, row partition, error behaviour, raw device access ...) run in a subprocess against the
+    emulated library.  Left out: the 1080p / 1 M-triangle cases (minutes of fibers) and the variant sweep (covered above)."""
+    e = dict(os.environ)
+    e['LYS_LIBTRACER'] = emu_lib
+    r = subprocess.run([sys.executable, '-m', 'pytest', os.path.join(ROOT, 'tests', 'test_gpu_parity.py'), '-m', 'gpu', '-q', '-x', '-p', 'no:cacheprovider',
+                        '-k', 'not full_size and not million and not kernel_variants'], env=e, text=True, capture_output=True, timeout=1500, cwd=ROOT)
+    tail = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else r.stderr[-400:]
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
+    assert ' passed' in tail and 'failed' not in tail and int(tail.split(' passed')[0].split()[-1]) >= 40, tail
