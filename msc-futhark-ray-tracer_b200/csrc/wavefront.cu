@@ -723,6 +723,171 @@ __global__ void __launch_bounds__(128, LYS_TRACE_MINB) k_trace(SceneDev sc, cons
     }
 }
 
+/* ------------------------------------------------------------------ staged traversal with lane refill (LYS_TRACE_MODE=2)
+ * EXPERIMENTAL, off by default.  Written after the GPU budget of round 1 was spent: validated bit for bit on the CPU SIMT
+ * emulator (tests/simt_emu, tests/test_simt_emu.py), NOT yet run or timed on a GPU.
+ *
+ * Why: on large scenes the walks of one warp's rays differ wildly in length (1 M triangles: mean 83 visits, max 781 on
+ * bounce 1), so the vote-synchronised loop of traverse<> runs every warp as long as its longest ray: 12.8 of 32 threads
+ * active.  k_trace_refill keeps lanes busy but pays with a one-visit-per-step state machine (measured slower on every scene).
+ * This kernel keeps traverse<>'s staged iteration (NB box stages, one triangle stage, one vote) and adds a refill round
+ * between iterations: when fewer than `keep` lanes are busy and the warp's slice of the queue is not exhausted, finished
+ * lanes store their hit (and append to the hits-first order list) and pull the next rays of the slice.  tools/simt_model.py
+ * (`refill_cost`) puts the saving at ~40 % of the issued instructions of the incoherent bounces on the 1 M-triangle scene.
+ * Per-lane visits, their order and every comparison are those of traverse<>; only which lane walks which ray changes.
+ * The shadow rays of the bounce go through the same scheme (second loop). */
+template <int NB, bool OCT>
+__global__ void __launch_bounds__(128, LYS_TRACE_MINB) k_trace_sr(SceneDev sc, const __grid_constant__ FrameParams fp, PassBuffers b, int bounce, int ordered, int keep) {
+    const int n_ext = (bounce + 1 < fp.path_len) ? b.counts[bounce + 1] : 0;
+    const int n_con = (bounce >= 0) ? b.counts[bounce] : 0;
+    const int stride = gridDim.x * blockDim.x;
+    const int n_nodes = (int)sc.n_tris - 1;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    const float4 *__restrict__ nodes = OCT ? sc.nodes_oct : sc.nodes;
+    const float4 *__restrict__ leaf_tri = sc.leaf_tri;
+    /* ---- closest hits of bounce + 1: every warp owns one contiguous slice of the queue */
+    {
+        const int n_warps = gridDim.x * (blockDim.x >> 5);
+        const int gwarp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+        const long long per = max(32ll, (((long long)n_ext + n_warps - 1) / n_warps + 31) & ~31ll);
+        int cursor = (int)min((long long)n_ext, (long long)gwarp * per);
+        const int end = (int)min((long long)n_ext, (long long)gwarp * per + per);
+        int stack[TRAV_STACK + 1];
+        stack[0] = TRAV_DONE;
+        int sp = 1, cur = TRAV_DONE, item = -1, closest = -1;
+        float tmax = FLT_MAX;
+        RayInv r; r.o = v3(0.0f, 0.0f, 0.0f); r.d = v3(1.0f, 1.0f, 1.0f); r.inv = r.d;
+        unsigned long long nbase = reinterpret_cast<unsigned long long>(nodes);
+        while (true) {
+            const unsigned busy = __ballot_sync(0xffffffffu, cur != TRAV_DONE);
+            if (busy == 0u || (cursor < end && __popc(busy) < keep)) {
+                /* refill round: retire the finished lanes, then hand the idle lanes the next rays of the slice */
+                const bool fin = item >= 0 && cur == TRAV_DONE;
+                if (fin) b.hit[item] = closest;
+                if (ordered) {                  /* processing order of shade(bounce + 1): hits from the front, misses from the back */
+                    const bool isH = fin && closest >= 0, isM = fin && closest < 0;
+                    const unsigned mh = __ballot_sync(0xffffffffu, isH), mm = __ballot_sync(0xffffffffu, isM);
+                    int bh = 0, bm = 0;
+                    if (lane == 0) { if (mh) bh = atomicAdd(&b.split[2 * (bounce + 1)], __popc(mh)); if (mm) bm = atomicAdd(&b.split[2 * (bounce + 1) + 1], __popc(mm)); }
+                    bh = __shfl_sync(0xffffffffu, bh, 0); bm = __shfl_sync(0xffffffffu, bm, 0);
+                    if (isH) b.order[(bounce + 1) & 1][bh + __popc(mh & lt)] = item;
+                    if (isM) b.order[(bounce + 1) & 1][n_ext - 1 - (bm + __popc(mm & lt))] = item;
+                }
+                if (fin) item = -1;
+                const unsigned idle = __ballot_sync(0xffffffffu, item < 0);
+                if (cursor < end) {
+                    const int mine = cursor + __popc(idle & lt);
+                    if (item < 0 && mine < end) {
+                        const float4 ro = b.ray_o[(bounce + 1) & 1][mine], rd = b.ray_d[(bounce + 1) & 1][mine];
+                        r.o = v3(ro.x, ro.y, ro.z); r.d = v3(rd.x, rd.y, rd.z);
+                        r.inv = v3(1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z);
+                        nbase = reinterpret_cast<unsigned long long>(nodes);
+                        if (OCT) nbase += 32ull * (unsigned)n_nodes * (unsigned)(((r.inv.x < 0.0f) ? 4 : 0) | ((r.inv.y < 0.0f) ? 2 : 0) | ((r.inv.z < 0.0f) ? 1 : 0));
+                        item = mine; cur = (n_nodes > 0) ? 0 : TRAV_DONE; sp = 1; closest = -1; tmax = FLT_MAX;
+                    }
+                    cursor = min(end, cursor + __popc(idle));
+                }
+                if (!__any_sync(0xffffffffu, cur != TRAV_DONE)) { if (cursor >= end) break; else continue; }
+            }
+            /* one staged iteration of traverse<false, NB, OCT> */
+#pragma unroll
+            for (int k = 0; k < NB; k++) {
+                if (cur >= 0) {
+                    const float4 *q = reinterpret_cast<const float4 *>(nbase + 32ull * (unsigned)cur);
+                    float4 lo = __ldg(q), hi = __ldg(q + 1);
+                    if (OCT ? slab_test_oct(r, lo, hi, tmax) : slab_test(r, lo, hi, tmax)) {
+                        stack[sp++] = __float_as_int(hi.w);
+                        cur = __float_as_int(lo.w);
+                    } else cur = stack[--sp];
+                }
+            }
+            if ((unsigned)cur > (unsigned)TRAV_DONE) {
+                float t;
+                if (leaf_test(r, leaf_tri, ~cur, tmax, t)) { closest = ~cur; tmax = t; }
+                cur = stack[--sp];
+            }
+        }
+    }
+    /* ---- shadow rays of this bounce with the same refill scheme.  An item is a vertex (walked in the order shade(bounce)
+     * took them: hits first); it carries up to two shadow rays, traced one after the other by the lane that owns the vertex
+     * (the second one starts at a refill round), then the vertex radiance is accumulated (connect_finish).  Vertices without
+     * shadow rays are finished on the spot by the lane that pulls them. */
+    {
+        const int n_warps = gridDim.x * (blockDim.x >> 5);
+        const int gwarp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+        const long long per = max(32ll, (((long long)n_con + n_warps - 1) / n_warps + 31) & ~31ll);
+        int cursor = (int)min((long long)n_con, (long long)gwarp * per);
+        const int end = (int)min((long long)n_con, (long long)gwarp * per + per);
+        int stack[TRAV_STACK + 1];
+        stack[0] = TRAV_DONE;
+        int sp = 1, cur = TRAV_DONE, slot = -1, flags = 0, phase = 0, hit = 0;
+        float tmax = 0.0f, L = 0.0f;
+        RayInv r; r.o = v3(0.0f, 0.0f, 0.0f); r.d = v3(1.0f, 1.0f, 1.0f); r.inv = r.d;
+        unsigned long long nbase = reinterpret_cast<unsigned long long>(nodes);
+        while (true) {
+            const unsigned busy = __ballot_sync(0xffffffffu, cur != TRAV_DONE);
+            if (busy == 0u || (cursor < end && __popc(busy) < keep)) {
+                float4 dn = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                bool start = false;
+                if (slot >= 0 && cur == TRAV_DONE) {                    /* a shadow ray of this lane's vertex has ended */
+                    const float4 rc = b.sh_c[slot];
+                    if (phase == 1) {
+                        L = hit ? 0.0f : rc.x;
+                        if (flags & 2) { dn = b.sh_d2[slot]; phase = 2; start = true; }
+                        else { connect_finish(fp, b, bounce, slot, flags, L, 0.0f, rc.z, rc.w, rc.z); slot = -1; }
+                    } else {
+                        connect_finish(fp, b, bounce, slot, flags, L, hit ? 0.0f : rc.y, rc.z, rc.w, rc.z);
+                        slot = -1;
+                    }
+                }
+                const unsigned idle = __ballot_sync(0xffffffffu, slot < 0);
+                if (cursor < end) {
+                    const int mine = cursor + __popc(idle & lt);
+                    if (slot < 0 && mine < end) {
+                        const int s = (ordered && bounce >= 1) ? b.order[bounce & 1][mine] : mine;
+                        const float4 ro = b.sh_o[s];
+                        const int fl = __float_as_int(ro.w);
+                        if ((fl & 4) || !(fl & 3)) { const float4 rc = b.sh_c[s]; connect_finish(fp, b, bounce, s, fl, 0.0f, 0.0f, rc.z, rc.w, rc.z); }
+                        else {
+                            slot = s; flags = fl; L = 0.0f;
+                            r.o = v3(ro.x, ro.y, ro.z);
+                            if (fl & 1) { dn = b.sh_d1[s]; phase = 1; } else { dn = b.sh_d2[s]; phase = 2; }
+                            start = true;
+                        }
+                    }
+                    cursor = min(end, cursor + __popc(idle));
+                }
+                if (start) {
+                    r.d = v3(dn.x, dn.y, dn.z);
+                    r.inv = v3(1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z);
+                    nbase = reinterpret_cast<unsigned long long>(nodes);
+                    if (OCT) nbase += 32ull * (unsigned)n_nodes * (unsigned)(((r.inv.x < 0.0f) ? 4 : 0) | ((r.inv.y < 0.0f) ? 2 : 0) | ((r.inv.z < 0.0f) ? 1 : 0));
+                    tmax = dn.w; hit = 0; sp = 1; cur = (n_nodes > 0) ? 0 : TRAV_DONE;
+                }
+                if (!__any_sync(0xffffffffu, cur != TRAV_DONE)) { if (cursor >= end) break; else continue; }
+            }
+            /* one staged iteration of traverse<true, NB, OCT> */
+#pragma unroll
+            for (int k = 0; k < NB; k++) {
+                if (cur >= 0) {
+                    const float4 *q = reinterpret_cast<const float4 *>(nbase + 32ull * (unsigned)cur);
+                    float4 lo = __ldg(q), hi = __ldg(q + 1);
+                    if (OCT ? slab_test_oct(r, lo, hi, tmax) : slab_test(r, lo, hi, tmax)) {
+                        stack[sp++] = __float_as_int(hi.w);
+                        cur = __float_as_int(lo.w);
+                    } else cur = stack[--sp];
+                }
+            }
+            if ((unsigned)cur > (unsigned)TRAV_DONE) {
+                float t;
+                if (leaf_test(r, leaf_tri, ~cur, tmax, t)) { hit = 1; cur = TRAV_DONE; }     /* any_hit stops at the first hit (bvh.fut:152) */
+                else cur = stack[--sp];
+            }
+        }
+    }
+}
+
 /* ------------------------------------------------------------------ generate + trace(-1) in one launch
  * The camera ray of a pixel goes straight from the registers into the traversal loop: one launch less per pass and no
  * read-back of the 32-byte ray records just written (k_shade(0) still needs them, so they are written once). */
@@ -975,7 +1140,7 @@ __global__ void k_material_probe(const float *mat28, float wavelen, V3 wo, V3 wi
 static inline int cdiv(long long a, int b) { return (int)((a + b - 1) / b); }
 
 /* persistent grids: SM count x resident CTAs per SM of each kernel (queried once per device) */
-struct GridSizes { int trace = 0, shade = 0, refill = 0, sl = 0, sb = 0, sc = 0; int mode = 0, split_bounces = 0, nb = 0, bars = 0, shade_threads = 256, oct = 1, adaptive = 1, sms = 148, tail_max = 8192, tail_items = 128, profile_tail = 0, order = 1, tail_min = 148, fuse_gen = 1, dyn_grids = 0; };
+struct GridSizes { int trace = 0, shade = 0, refill = 0, sl = 0, sb = 0, sc = 0; int sr = 0, sr_keep = 24; int mode = 0, split_bounces = 0, nb = 0, bars = 0, shade_threads = 256, oct = 1, adaptive = 1, sms = 148, tail_max = 8192, tail_items = 128, profile_tail = 0, order = 1, tail_min = 148, fuse_gen = 1, dyn_grids = 0; };
 static GridSizes grid_sizes() {
     static GridSizes g[64];
     int dev = 0; cudaGetDevice(&dev);
@@ -993,7 +1158,9 @@ static GridSizes grid_sizes() {
         /* experiment knobs: persistent grids as a fraction of the resident maximum (co-residency of kernels of different streams) */
         const char *gt = getenv("LYS_TRACE_GRID_PCT"); if (gt && atoi(gt) > 0) g[dev].trace = max(sms, g[dev].trace * atoi(gt) / 100);
         const char *gsh = getenv("LYS_SHADE_GRID_PCT"); if (gsh && atoi(gsh) > 0) g[dev].shade = max(sms, g[dev].shade * atoi(gsh) / 100);
-        const char *e = getenv("LYS_TRACE_MODE"); g[dev].mode = (e && atoi(e) == 1) ? 1 : 0;
+        const char *e = getenv("LYS_TRACE_MODE"); g[dev].mode = (e && atoi(e) == 1) ? 1 : 0;      /* 1: k_trace_refill instead of k_trace */
+        g[dev].sr = (e && atoi(e) == 2) ? 1 : 0;                                               /* 2: k_trace_sr (staged loop + lane refill) for the bounce launches */
+        const char *kp = getenv("LYS_TRACE_SR_KEEP"); if (kp && atoi(kp) >= 1 && atoi(kp) <= 32) g[dev].sr_keep = atoi(kp);
         g[dev].sms = sms;
         const char *ord = getenv("LYS_SHADE_ORDER"); if (ord) g[dev].order = atoi(ord) ? 1 : 0;      /* 0: k_shade walks the slots in queue order */
         g[dev].tail_min = sms;
@@ -1022,6 +1189,12 @@ static void launch_trace(const GridSizes &gs0, int grid, const SceneDev &sc, con
     if (gs.nb == 0) gs.nb = (sc.n_tris <= 4096) ? 2 : 1;
     if (gs.mode) { k_trace_refill<<<grid, 128, 0, stream>>>(sc, fp, bufs, bounce); return; }
     const int ordered = (gs.order && bounce >= 0) ? 1 : 0;      /* write the hits-first order of bounce + 1, walk the one of bounce */
+    if (gs.sr && bounce >= 0) {                                /* experimental: staged loop with lane refill (camera rays keep k_trace) */
+        if (sc.nodes_oct && gs.oct) { if (gs.nb == 1) k_trace_sr<1, true><<<grid, 128, 0, stream>>>(sc, fp, bufs, bounce, ordered, gs.sr_keep); else k_trace_sr<2, true><<<grid, 128, 0, stream>>>(sc, fp, bufs, bounce, ordered, gs.sr_keep); }
+        else if (gs.nb == 1) k_trace_sr<1, false><<<grid, 128, 0, stream>>>(sc, fp, bufs, bounce, ordered, gs.sr_keep);
+        else k_trace_sr<2, false><<<grid, 128, 0, stream>>>(sc, fp, bufs, bounce, ordered, gs.sr_keep);
+        return;
+    }
     if (sc.nodes_oct && gs.oct) { if (gs.nb == 1) k_trace<1, true><<<grid, 128, 0, stream>>>(sc, fp, bufs, bounce, ordered); else k_trace<2, true><<<grid, 128, 0, stream>>>(sc, fp, bufs, bounce, ordered); }
     else if (gs.nb == 1) k_trace<1, false><<<grid, 128, 0, stream>>>(sc, fp, bufs, bounce, ordered);
     else k_trace<2, false><<<grid, 128, 0, stream>>>(sc, fp, bufs, bounce, ordered);

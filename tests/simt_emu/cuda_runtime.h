@@ -52,7 +52,7 @@ const uint3 &cur_tid();
 uint32_t warp_collective(Op op, uint32_t a, uint32_t b);     /* parks the lane; returns its result */
 void cta_barrier();
 void *dyn_smem();
-void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()> &body);
+void launch(const char *name, dim3 grid, dim3 block, size_t smem, const std::function<void()> &body);
 struct Stats { uint64_t launches, ctas, lanes, warp_collectives, cta_barriers; };
 Stats stats();
 }

@@ -188,7 +188,11 @@ void cta_barrier() { park(ST_CTA); }
 void *dyn_smem() { return g_smem.data(); }
 Stats stats() { return g_stats; }
 
-void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()> &body) {
+/* LYS_EMU_TRACE=1: one line per launch on stderr (kernel, grid, block, warp collectives, CTA barriers) -- the number of
+ * collectives of a traversal kernel is its number of lock-step loop iterations, a proxy for issued warp instructions */
+void launch(const char *name, dim3 grid, dim3 block, size_t smem, const std::function<void()> &body) {
+    static const bool trace = getenv("LYS_EMU_TRACE") && atoi(getenv("LYS_EMU_TRACE")) > 0;
+    const Stats s0 = g_stats;
     if (g_cur) fatal("nested launch");
     const int n = (int)(block.x * block.y * block.z);
     if (n <= 0 || grid.x == 0 || grid.y == 0 || grid.z == 0) return;
@@ -201,6 +205,8 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()> &bod
         for (unsigned y = 0; y < grid.y; y++)
             for (unsigned x = 0; x < grid.x; x++) { g_block_idx = {x, y, z}; run_cta(n); }
     g_body = nullptr;
+    if (trace) fprintf(stderr, "emu launch %-28s grid %6u block %4d  warp collectives %10llu  cta barriers %8llu\n", name, grid.x * grid.y * grid.z, n,
+                       (unsigned long long)(g_stats.warp_collectives - s0.warp_collectives), (unsigned long long)(g_stats.cta_barriers - s0.cta_barriers));
 }
 
 }  // namespace emu

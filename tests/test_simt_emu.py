@@ -48,11 +48,29 @@ def test_emulated_library_equals_the_oracle(emu_lib):
     {'LYS_TAIL_MAX': '100000000'},                     # fused tail kernel from bounce 1 on
     {'LYS_TRACE_MODE': '1'},                           # refill variant of the trace kernel
     {'LYS_SHADE_SPLIT': '2', 'LYS_FUSE_GENERATE': '0'},
+    {'LYS_TRACE_MODE': '2'},                           # k_trace_sr: staged loop + lane refill (experimental, emulator-validated only)
+    {'LYS_TRACE_MODE': '2', 'LYS_TRACE_SR_KEEP': '32', 'LYS_TRACE_OCT': '0', 'LYS_TRACE_NB': '1', 'LYS_EMU_SMS': '2'},   # refill at every idle lane, long slices
+    {'LYS_TRACE_MODE': '2', 'LYS_TRACE_SR_KEEP': '1', 'LYS_TAIL_MAX': '0', 'LYS_SHADE_ORDER': '0', 'LYS_EMU_SMS': '32'},  # refill only when the warp is empty, short slices
 ], ids=lambda e: ','.join(f'{k}={v}' for k, v in e.items()))
 def test_emulated_kernel_variants(emu_lib, env):
     e = dict(env)
     e['LYS_EMU_FAST_MATH_SWEEP'] = '1'
     check(sweep(emu_lib, ['cornell'], e))
+
+
+def test_staged_refill_kernel_on_the_parity_suite(emu_lib):
+    """k_trace_sr (LYS_TRACE_MODE=2) has not run on a GPU yet (it was written after the GPU budget of round 1 was spent), so
+    it is NOT in the `-m gpu` variant list; here it goes through the fuzzed scenes, all camera presets, the edge
+    configurations and the entry points on the emulator.  Move it into tests/test_gpu_parity.py::test_kernel_variants_bit_exact
+    after its first B200 run."""
+    e = dict(os.environ)
+    e.update({'LYS_LIBTRACER': emu_lib, 'LYS_TRACE_MODE': '2'})
+    r = subprocess.run([sys.executable, '-m', 'pytest', os.path.join(ROOT, 'tests', 'test_gpu_parity.py'), '-m', 'gpu', '-q', '-x', '-p', 'no:cacheprovider',
+                        '-k', 'soup or edge_configurations or entry_points or sample_points or pass_radiance or path_len or row_partition'],
+                       env=e, text=True, capture_output=True, timeout=1500, cwd=ROOT)
+    tail = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else r.stderr[-400:]
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
+    assert ' passed' in tail and 'failed' not in tail and int(tail.split(' passed')[0].split()[-1]) >= 20, tail
 
 
 def test_gpu_parity_suite_on_the_emulator(emu_lib):
