@@ -1,0 +1,22 @@
+#!/bin/bash
+# What the first GPU call of the next round should measure (everything here was prepared without GPU time at the end of round 1).
+#   /usr/local/graft/bin/gpurun --timeout 600 -- 'bash tools/next_round_first_call.sh'
+# 1. k_trace_sr (LYS_TRACE_MODE=2: staged traversal loop with lane refill) has only run on the CPU SIMT emulator: parity on the GPU,
+#    then its throughput next to the default kernels on the scenes where the emulator predicts a gain (3, 4, 5) and a loss (metric).
+# 2. Pipeline depth on the large scene (its late-bounce launches are 0.3-0.7 ms latency tails, profiles/README.md section 7).
+# 3. BASELINE config 5 on one GPU with the fixed warm-up (2 / 4 / 8 GPUs: torchrun tools/bench_synthetic_multi.py, separate calls).
+set -x
+O=gpurun_out
+mkdir -p $O
+LYS_TRACE_MODE=2 python tools/gpu_parity_quick.py > $O/n_parity_mode2.log 2>&1; tail -3 $O/n_parity_mode2.log | cut -c1-300
+for m in 0 2; do
+  LYS_TRACE_MODE=$m python tools/bench_configs.py metric 3 4 5 > $O/n_configs_mode$m.jsonl 2> $O/n_configs_mode$m.err
+  cut -c1-160 $O/n_configs_mode$m.jsonl
+done
+for k in 16 28; do
+  LYS_TRACE_MODE=2 LYS_TRACE_SR_KEEP=$k python tools/bench_configs.py 4 5 > $O/n_configs_mode2_keep$k.jsonl 2>/dev/null; cut -c1-160 $O/n_configs_mode2_keep$k.jsonl
+done
+for p in 12 16; do
+  LYS_PIPELINE=$p python tools/bench_configs.py 5 > $O/n_configs_pipeline$p.jsonl 2>/dev/null; cut -c1-160 $O/n_configs_pipeline$p.jsonl
+done
+python tools/bench_synthetic_multi.py --passes 256 > $O/n_synth_n1.json 2> $O/n_synth_n1.err; cat $O/n_synth_n1.json
