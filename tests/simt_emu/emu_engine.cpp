@@ -52,6 +52,7 @@ emu_ctx g_sched;
 const std::function<void()> *g_body = nullptr;
 std::vector<char> g_smem;
 Stats g_stats = {0, 0, 0, 0, 0};
+uint64_t g_ballots = 0, g_ballot_bits = 0;      /* votes / ballots and the lanes that voted true (LYS_EMU_TRACE) */
 uint3 g_no_tid = {0, 0, 0};
 
 [[noreturn]] void fatal(const char *msg) {
@@ -105,6 +106,7 @@ void resolve_warp(Lane *w, int n) {
             uint32_t m = 0;
             for (int l = 0; l < n; l++) if (w[l].st == ST_WARP && (w[l].a & 1u)) m |= 1u << l;
             for (int l = 0; l < n; l++) w[l].out = m;
+            g_ballots++; g_ballot_bits += (uint64_t)__builtin_popcount(m);
             break;
         }
         case OP_SHFL: case OP_SHFL_XOR:
@@ -188,11 +190,13 @@ void cta_barrier() { park(ST_CTA); }
 void *dyn_smem() { return g_smem.data(); }
 Stats stats() { return g_stats; }
 
-/* LYS_EMU_TRACE=1: one line per launch on stderr (kernel, grid, block, warp collectives, CTA barriers) -- the number of
- * collectives of a traversal kernel is its number of lock-step loop iterations, a proxy for issued warp instructions */
+/* LYS_EMU_TRACE=1: one line per launch on stderr (kernel, grid, block, warp collectives, CTA barriers, mean number of lanes
+ * that voted true) -- the number of collectives of a traversal kernel is its number of lock-step loop iterations, a proxy
+ * for issued warp instructions, and its votes ask "is this lane still walking", so the last figure is its SIMT occupancy */
 void launch(const char *name, dim3 grid, dim3 block, size_t smem, const std::function<void()> &body) {
     static const bool trace = getenv("LYS_EMU_TRACE") && atoi(getenv("LYS_EMU_TRACE")) > 0;
     const Stats s0 = g_stats;
+    const uint64_t b0 = g_ballots, bb0 = g_ballot_bits;
     if (g_cur) fatal("nested launch");
     const int n = (int)(block.x * block.y * block.z);
     if (n <= 0 || grid.x == 0 || grid.y == 0 || grid.z == 0) return;
@@ -205,8 +209,9 @@ void launch(const char *name, dim3 grid, dim3 block, size_t smem, const std::fun
         for (unsigned y = 0; y < grid.y; y++)
             for (unsigned x = 0; x < grid.x; x++) { g_block_idx = {x, y, z}; run_cta(n); }
     g_body = nullptr;
-    if (trace) fprintf(stderr, "emu launch %-28s grid %6u block %4d  warp collectives %10llu  cta barriers %8llu\n", name, grid.x * grid.y * grid.z, n,
-                       (unsigned long long)(g_stats.warp_collectives - s0.warp_collectives), (unsigned long long)(g_stats.cta_barriers - s0.cta_barriers));
+    if (trace) fprintf(stderr, "emu launch %-28s grid %6u block %4d  warp collectives %10llu  cta barriers %8llu  true lanes per vote %5.1f\n", name,
+                       grid.x * grid.y * grid.z, n, (unsigned long long)(g_stats.warp_collectives - s0.warp_collectives),
+                       (unsigned long long)(g_stats.cta_barriers - s0.cta_barriers), g_ballots > b0 ? (double)(g_ballot_bits - bb0) / (double)(g_ballots - b0) : 0.0);
 }
 
 }  // namespace emu
