@@ -19,4 +19,9 @@ done
 for p in 12 16; do
   LYS_PIPELINE=$p python tools/bench_configs.py 5 > $O/n_configs_pipeline$p.jsonl 2>/dev/null; cut -c1-160 $O/n_configs_pipeline$p.jsonl
 done
+# 2b. the fused tail kernel earlier on the large scene: its CTAs wavefront their own chunk through all remaining bounces, so the
+#     per-bounce "launch lasts as long as its longest ray" barrier disappears (k_trace(3..8) are 21 % of the serialised pass there)
+for t in 65536 262144 1048576; do
+  LYS_TAIL_MAX=$t python tools/bench_configs.py 5 > $O/n_configs_tailmax$t.jsonl 2>/dev/null; cut -c1-160 $O/n_configs_tailmax$t.jsonl
+done
 python tools/bench_synthetic_multi.py --passes 256 > $O/n_synth_n1.json 2> $O/n_synth_n1.err; cat $O/n_synth_n1.json
