@@ -135,6 +135,16 @@ void resolve_warp(Lane *w, int n) {
     }
     for (int l = 0; l < n; l++) if (w[l].st == ST_WARP) w[l].st = ST_RUN;
 }
+/* LYS_EMU_SCHEDULE: 0 = CTAs, warps and lanes in index order (default); 1 = all three reversed; s >= 2 = pseudo-random orders
+ * from seed s, redrawn for every CTA.  Results must not depend on it: a kernel whose output changes with the schedule has a
+ * race (a missing barrier, an unordered read-modify-write) or an order-dependent result. */
+int g_schedule = -1;
+uint64_t g_rng = 0;
+uint32_t next_rand() { g_rng ^= g_rng << 13; g_rng ^= g_rng >> 7; g_rng ^= g_rng << 17; return (uint32_t)(g_rng >> 11); }
+void make_order(int *ord, int n) {
+    for (int i = 0; i < n; i++) ord[i] = (g_schedule == 1) ? n - 1 - i : i;
+    if (g_schedule >= 2) for (int i = n - 1; i > 0; i--) { int j = (int)(next_rand() % (uint32_t)(i + 1)); int t = ord[i]; ord[i] = ord[j]; ord[j] = t; }
+}
 void run_cta(int n) {
     if (n > MAX_LANES) fatal("CTA larger than 1024 threads");
     if (!g_lanes) {
@@ -151,15 +161,20 @@ void run_cta(int n) {
     }
     g_stats.ctas++; g_stats.lanes += (uint64_t)n;
     const int nw = (n + 31) / 32;
+    int worder[32], lorder[32];
+    make_order(worder, nw); make_order(lorder, 32);
     while (true) {
         bool progress = false;
         int done = 0, at_cta = 0;
-        for (int w = 0; w < nw; w++) {
+        for (int wi = 0; wi < nw; wi++) {
+            const int w = worder[wi];
             Lane *W = g_lanes + 32 * w;
             const int wn = (n - 32 * w < 32) ? n - 32 * w : 32;
             while (true) {
-                for (int l = 0; l < wn; l++)
-                    if (W[l].st == ST_RUN) { g_cur = &W[l]; to_lane(&W[l]); g_cur = nullptr; progress = true; }
+                for (int li = 0; li < 32; li++) {
+                    const int l = lorder[li];
+                    if (l < wn && W[l].st == ST_RUN) { g_cur = &W[l]; to_lane(&W[l]); g_cur = nullptr; progress = true; }
+                }
                 int nW = 0, nC = 0, nD = 0;
                 for (int l = 0; l < wn; l++) { nW += W[l].st == ST_WARP; nC += W[l].st == ST_CTA; nD += W[l].st == ST_DONE; }
                 if (nW == 0) { done += nD; at_cta += nC; break; }
@@ -205,9 +220,15 @@ void launch(const char *name, dim3 grid, dim3 block, size_t smem, const std::fun
     g_grid_dim = {grid.x, grid.y, grid.z};
     g_block_dim = {block.x, block.y, block.z};
     g_stats.launches++;
-    for (unsigned z = 0; z < grid.z; z++)
-        for (unsigned y = 0; y < grid.y; y++)
-            for (unsigned x = 0; x < grid.x; x++) { g_block_idx = {x, y, z}; run_cta(n); }
+    if (g_schedule < 0) { const char *e = getenv("LYS_EMU_SCHEDULE"); g_schedule = (e && atoi(e) > 0) ? atoi(e) : 0; g_rng = 0x9E3779B97F4A7C15ull ^ (uint64_t)g_schedule; }
+    const unsigned total = grid.x * grid.y * grid.z;
+    std::vector<int> corder(total);
+    if (total <= (1u << 24)) make_order(corder.data(), (int)total);
+    for (unsigned c = 0; c < total; c++) {
+        const unsigned k = (unsigned)corder[c];
+        g_block_idx = {k % grid.x, (k / grid.x) % grid.y, k / (grid.x * grid.y)};
+        run_cta(n);
+    }
     g_body = nullptr;
     if (trace) fprintf(stderr, "emu launch %-28s grid %6u block %4d  warp collectives %10llu  cta barriers %8llu  true lanes per vote %5.1f\n", name,
                        grid.x * grid.y * grid.z, n, (unsigned long long)(g_stats.warp_collectives - s0.warp_collectives),
