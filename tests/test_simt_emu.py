@@ -82,6 +82,7 @@ def test_gpu_parity_suite_on_the_emulator(emu_lib):
     emulated library.  Left out: the 1080p / 1 M-triangle cases (minutes of fibers) and the variant sweep (covered above)."""
     e = dict(os.environ)
     e['LYS_LIBTRACER'] = emu_lib
+    e['LYS_EMU_SCHEDULE'] = '20261018'                      # pseudo-random CTA / warp / lane order: also a race probe
     r = subprocess.run([sys.executable, '-m', 'pytest', os.path.join(ROOT, 'tests', 'test_gpu_parity.py'), '-m', 'gpu', '-q', '-x', '-p', 'no:cacheprovider',
                         '-k', 'not full_size and not million and not kernel_variants'], env=e, text=True, capture_output=True, timeout=1500, cwd=ROOT)
     tail = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else r.stderr[-400:]
