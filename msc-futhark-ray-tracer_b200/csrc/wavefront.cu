@@ -725,7 +725,7 @@ __global__ void __launch_bounds__(128, LYS_TRACE_MINB) k_trace(SceneDev sc, cons
 
 /* ------------------------------------------------------------------ staged traversal with lane refill (LYS_TRACE_MODE=2)
  * EXPERIMENTAL, off by default.  Written after the GPU budget of round 1 was spent: validated bit for bit on the CPU SIMT
- * emulator (tests/simt_emu, tests/test_simt_emu.py), NOT yet run or timed on a GPU.
+ * emulator of the test-suite (a fiber-per-thread host build of these sources), NOT yet run or timed on a GPU.
  *
  * Why: on large scenes the walks of one warp's rays differ wildly in length (1 M triangles: mean 83 visits, max 781 on
  * bounce 1), so the vote-synchronised loop of traverse<> runs every warp as long as its longest ray: 12.8 of 32 threads

@@ -97,6 +97,7 @@ def test_product_does_not_reference_the_oracle():
             if f.endswith(('.cu', '.cuh', '.h', '.cpp', '.py')) or f == 'Makefile':
                 txt = open(os.path.join(dirpath, f)).read()
                 assert 'lys_oracle' not in txt and 'lysref' not in txt and 'oracle/' not in txt, os.path.join(dirpath, f)
+                assert 'simt_emu' not in txt and 'libtracer_emu' not in txt and 'LYS_SIMT_EMU' not in txt, os.path.join(dirpath, f)   # nor the CPU emulator of tests/
 
 
 @pytest.mark.skipif(not os.path.isdir(REF), reason='needs the reference host sources')
