@@ -1,6 +1,6 @@
 #!/bin/bash
 # What the first GPU call of the next round should measure (everything here was prepared without GPU time at the end of round 1).
-#   /usr/local/graft/bin/gpurun --timeout 600 -- 'bash tools/next_round_first_call.sh'
+#   /usr/local/graft/bin/gpurun --timeout 900 -- 'bash tools/next_round_first_call.sh'      (about 5-6 minutes of box time)
 # 1. k_trace_sr (LYS_TRACE_MODE=2: staged traversal loop with lane refill) has only run on the CPU SIMT emulator: parity on the GPU,
 #    then its throughput next to the default kernels on the scenes where the emulator predicts a gain (3, 4, 5) and a loss (metric).
 # 2. Pipeline depth on the large scene (its late-bounce launches are 0.3-0.7 ms latency tails, profiles/README.md section 7).
