@@ -62,6 +62,9 @@ def _load():
     if not os.path.exists(_SO):
         raise TracerError('libtracer.so is not built (run __graft_entry__.build() or make -C %s); there is no CPU fallback' % _HERE)
     L = C.CDLL(_SO)
+    if hasattr(L, 'lys_emu_stats') and os.environ.get('LYS_ALLOW_EMULATOR') != '1':
+        # LYS_LIBTRACER points at the test-suite's host build of the kernels: never a fallback, only loaded when a test says so
+        raise TracerError('%s is the CPU emulator build of the test-suite, not libtracer; set LYS_ALLOW_EMULATOR=1 only inside tests' % _SO)
     L.futhark_context_config_new.restype = vp
     L.futhark_context_config_free.argtypes = [vp]
     L.futhark_context_config_set_device.argtypes = [vp, C.c_char_p]

@@ -22,6 +22,7 @@ def sweep(emu_lib, scenes, env=None):
     e = dict(os.environ)
     e.update(env or {})
     e['LYS_LIBTRACER'] = emu_lib
+    e['LYS_ALLOW_EMULATOR'] = '1'
     out = subprocess.check_output([sys.executable, os.path.join(ROOT, 'tools', 'gpu_parity_quick.py')] + scenes, env=e, text=True, timeout=1500)
     res = {}
     for line in out.splitlines():
@@ -67,7 +68,7 @@ def test_staged_refill_kernel_on_the_parity_suite(emu_lib):
     configurations and the entry points on the emulator.  Move it into tests/test_gpu_parity.py::test_kernel_variants_bit_exact
     after its first B200 run."""
     e = dict(os.environ)
-    e.update({'LYS_LIBTRACER': emu_lib, 'LYS_TRACE_MODE': '2'})
+    e.update({'LYS_LIBTRACER': emu_lib, 'LYS_ALLOW_EMULATOR': '1', 'LYS_TRACE_MODE': '2'})
     r = subprocess.run([sys.executable, '-m', 'pytest', os.path.join(ROOT, 'tests', 'test_gpu_parity.py'), '-m', 'gpu', '-q', '-x', '-p', 'no:cacheprovider',
                         '-k', 'soup or edge_configurations or entry_points or sample_points or pass_radiance or path_len or row_partition'],
                        env=e, text=True, capture_output=True, timeout=1500, cwd=ROOT)
@@ -83,9 +84,20 @@ def test_gpu_parity_suite_on_the_emulator(emu_lib):
     minute) and the variant sweep (covered above)."""
     e = dict(os.environ)
     e['LYS_LIBTRACER'] = emu_lib
+    e['LYS_ALLOW_EMULATOR'] = '1'
     e['LYS_EMU_SCHEDULE'] = '20261018'                      # pseudo-random CTA / warp / lane order: also a race probe
     r = subprocess.run([sys.executable, '-m', 'pytest', os.path.join(ROOT, 'tests', 'test_gpu_parity.py'), '-m', 'gpu', '-q', '-x', '-p', 'no:cacheprovider',
                         '-k', 'not full_size and not kernel_variants'], env=e, text=True, capture_output=True, timeout=1500, cwd=ROOT)
     tail = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else r.stderr[-400:]
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
     assert ' passed' in tail and 'failed' not in tail and int(tail.split(' passed')[0].split()[-1]) >= 40, tail
+
+
+def test_product_binding_refuses_the_emulator_unless_a_test_allows_it(emu_lib):
+    """No silent CPU path: the Python binding only loads the emulated library when LYS_ALLOW_EMULATOR=1 is set (by tests)."""
+    e = dict(os.environ)
+    e['LYS_LIBTRACER'] = emu_lib
+    e.pop('LYS_ALLOW_EMULATOR', None)
+    code = "import importlib; p = importlib.import_module('msc-futhark-ray-tracer_b200'); p.Context()"
+    r = subprocess.run([sys.executable, '-c', code], env=e, text=True, capture_output=True, cwd=ROOT)
+    assert r.returncode != 0 and 'CPU emulator build' in r.stderr
