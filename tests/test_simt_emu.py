@@ -101,3 +101,17 @@ def test_product_binding_refuses_the_emulator_unless_a_test_allows_it(emu_lib):
     code = "import importlib; p = importlib.import_module('msc-futhark-ray-tracer_b200'); p.Context()"
     r = subprocess.run([sys.executable, '-c', code], env=e, text=True, capture_output=True, cwd=ROOT)
     assert r.returncode != 0 and 'CPU emulator build' in r.stderr
+
+
+@pytest.mark.parametrize('what,seed,count,env', [
+    ('lbvh', 1, 40, {'LYS_EMU_SCHEDULE': '3'}),        # hostile geometry: inf / NaN / denormals / duplicates / identical triangles
+    ('soup', 2, 10, {}),                               # random scenes, materials, camera presets, poses, frame sizes, seeds
+    ('soup', 3, 8, {'LYS_TRACE_MODE': '2', 'LYS_EMU_SCHEDULE': '7'}),
+], ids=lambda v: str(v) if not isinstance(v, dict) else ','.join(f'{k}={x}' for k, x in v.items()) or 'default')
+def test_fuzzed_parity_on_the_emulator(emu_lib, what, seed, count, env):
+    """tools/fuzz_parity.py (usable on the GPU as well) against the emulated library: zero mismatching scenes."""
+    e = dict(os.environ)
+    e.update(env)
+    e.update({'LYS_LIBTRACER': emu_lib, 'LYS_ALLOW_EMULATOR': '1'})
+    r = subprocess.run([sys.executable, os.path.join(ROOT, 'tools', 'fuzz_parity.py'), what, str(seed), str(count)], env=e, text=True, capture_output=True, timeout=1500)
+    assert r.returncode == 0 and '%d scenes, 0 mismatching' % count in r.stdout, r.stdout[-2000:] + r.stderr[-1000:]

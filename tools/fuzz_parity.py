@@ -1,0 +1,103 @@
+#!/usr/bin/env python
+"""Randomised parity of the library against the oracle (development / test tool; exit status 1 on any mismatch).
+
+    python tools/fuzz_parity.py lbvh [seed] [scenes]    hostile geometry: inf / NaN / denormal / 1e30 / 1e-30 coordinates, exact
+                                                        duplicates, flat and identical triangles, sizes around the warp, tile and
+                                                        chunk boundaries -> every LBVH array, bit for bit (NaN payloads included)
+    python tools/fuzz_parity.py soup [seed] [scenes]    lysref.objwriter.random_soup scenes (whole uber-BSDF parameter space, ten
+                                                        lights) in a random camera preset and frame size -> per-vertex radiance,
+                                                        distance, channel and two accumulated passes, bit for bit
+Runs on the GPU by default; with LYS_LIBTRACER / LYS_ALLOW_EMULATOR=1 set by tests/test_simt_emu.py it runs the same CUDA sources
+on the CPU SIMT emulator."""
+import importlib
+import os
+import sys
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+pkg = importlib.import_module('msc-futhark-ray-tracer_b200')
+from lysref import oracle, objwriter  # noqa: E402
+
+
+def same_bits(a, b):
+    a, b = np.ascontiguousarray(a), np.ascontiguousarray(b)
+    return a.shape == b.shape and (np.array_equal(a.view(np.uint32), b.view(np.uint32)) if a.dtype == np.float32 else np.array_equal(a, b))
+
+
+def hostile_triangles(rng, it):
+    n = int(rng.choice([2, 3, 5, 31, 32, 33, 100, 257, 600, 1500]))
+    kind = it % 10
+    t = rng.random((n, 3, 3))
+    if kind == 1:
+        t = t * 1e-30
+    elif kind == 2:
+        t = t * 1e30
+    elif kind == 3:
+        t[rng.integers(0, n, max(1, n // 10))] = np.inf
+    elif kind == 4:
+        t[rng.integers(0, n, max(1, n // 10)), rng.integers(0, 3), rng.integers(0, 3)] = np.nan
+    elif kind == 5:
+        t = np.round(t * 4) / 4                                  # many exact duplicates, coplanar
+    elif kind == 6:
+        t[:, :, 0] = 0.5                                         # zero extent on x
+    elif kind == 7:
+        t = np.repeat(t[:1], n, axis=0)                          # all identical: the index tie-break decides the whole tree
+    elif kind == 8:
+        t = t - 0.5
+        t[::2] *= -1e-3                                          # mixed signs and scales
+    elif kind == 9:
+        t = t * 1e-40                                            # denormals
+    with np.errstate(all='ignore'):
+        return np.ascontiguousarray(t, np.float32), kind
+
+
+def fuzz_lbvh(ctx, rng, count):
+    mats = np.load(os.path.join(ROOT, 'tests', 'golden', 'scenes', 'cornell.npz'))['mats']
+    bad = 0
+    for it in range(count):
+        t, kind = hostile_triangles(rng, it)
+        tm = np.zeros(len(t), np.uint32)
+        so, sg = oracle.State.init(t, tm, mats, 4, 4), pkg.State.init(ctx, t, tm, mats, 4, 4)
+        bo, bg = so.bvh(), sg.bvh()
+        for key in ('bounds', 'morton', 'src_index', 'left', 'right', 'parent', 'node_aabb', 'leaf_aabb'):
+            if not same_bits(bo[key], bg[key]):
+                print('MISMATCH lbvh scene', it, 'kind', kind, 'n', len(t), key, flush=True)
+                bad += 1
+                break
+        sg.free()
+    return bad
+
+
+def fuzz_soup(ctx, rng, count):
+    bad = 0
+    for it in range(count):
+        seed = int(rng.integers(100, 1 << 30))
+        scene = objwriter.random_soup(seed, n_tris=int(rng.integers(40, 400)))
+        conf = int(rng.integers(0, 3))
+        h, w = int(rng.integers(8, 48)), int(rng.integers(8, 64))
+        origin = tuple(float(x) for x in rng.uniform([-0.6, 0.4, -0.6], [0.6, 1.6, 0.9]))
+        kw = dict(cam_conf_id=conf, origin=origin, pitch=float(rng.uniform(-0.5, 0.5)), yaw=float(rng.uniform(-3, 3)), seed=int(rng.integers(0, 1000)))
+        so, sg = oracle.State.init(*scene, h, w, **kw), pkg.State.init(ctx, *scene, h, w, **kw)
+        qo, qg = so.probe_pass(), sg.probe_pass()
+        ok = all(same_bits(qo[k], qg[k]) for k in ('radiance', 'distance', 'channel')) and same_bits(so.sample_n_frames(2), sg.sample_n_frames(2))
+        if not ok:
+            print('MISMATCH soup scene', it, 'seed', seed, 'conf', conf, 'frame', (h, w), flush=True)
+            bad += 1
+        sg.free()
+    return bad
+
+
+def main():
+    what = sys.argv[1] if len(sys.argv) > 1 else 'lbvh'
+    rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
+    count = int(sys.argv[3]) if len(sys.argv) > 3 else 50
+    with pkg.Context() as ctx, np.errstate(all='ignore'):
+        bad = fuzz_lbvh(ctx, rng, count) if what == 'lbvh' else fuzz_soup(ctx, rng, count)
+    print('%s: %d scenes, %d mismatching' % (what, count, bad), flush=True)
+    sys.exit(1 if bad else 0)
+
+
+if __name__ == '__main__':
+    main()
