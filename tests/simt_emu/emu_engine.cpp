@@ -222,10 +222,10 @@ void launch(const char *name, dim3 grid, dim3 block, size_t smem, const std::fun
     g_stats.launches++;
     if (g_schedule < 0) { const char *e = getenv("LYS_EMU_SCHEDULE"); g_schedule = (e && atoi(e) > 0) ? atoi(e) : 0; g_rng = 0x9E3779B97F4A7C15ull ^ (uint64_t)g_schedule; }
     const unsigned total = grid.x * grid.y * grid.z;
-    std::vector<int> corder(total);
-    if (total <= (1u << 24)) make_order(corder.data(), (int)total);
+    std::vector<int> corder;
+    if (g_schedule > 0 && total <= (1u << 24)) { corder.resize(total); make_order(corder.data(), (int)total); }
     for (unsigned c = 0; c < total; c++) {
-        const unsigned k = (unsigned)corder[c];
+        const unsigned k = corder.empty() ? c : (unsigned)corder[c];
         g_block_idx = {k % grid.x, (k / grid.x) % grid.y, k / (grid.x * grid.y)};
         run_cta(n);
     }

@@ -107,6 +107,7 @@ def test_product_binding_refuses_the_emulator_unless_a_test_allows_it(emu_lib):
     ('lbvh', 1, 40, {'LYS_EMU_SCHEDULE': '3'}),        # hostile geometry: inf / NaN / denormals / duplicates / identical triangles
     ('soup', 2, 10, {}),                               # random scenes, materials, camera presets, poses, frame sizes, seeds
     ('soup', 3, 8, {'LYS_TRACE_MODE': '2', 'LYS_EMU_SCHEDULE': '7'}),
+    ('keys', 4, 12, {}),                               # random host sessions: key events, resizes, steps -> scalars, image, ARGB frame
 ], ids=lambda v: str(v) if not isinstance(v, dict) else ','.join(f'{k}={x}' for k, x in v.items()) or 'default')
 def test_fuzzed_parity_on_the_emulator(emu_lib, what, seed, count, env):
     """tools/fuzz_parity.py (usable on the GPU as well) against the emulated library: zero mismatching scenes."""

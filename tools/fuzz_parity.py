@@ -7,6 +7,7 @@
     python tools/fuzz_parity.py soup [seed] [scenes]    lysref.objwriter.random_soup scenes (whole uber-BSDF parameter space, ten
                                                         lights) in a random camera preset and frame size -> per-vertex radiance,
                                                         distance, channel and two accumulated passes, bit for bit
+    python tools/fuzz_parity.py keys [seed] [sessions]  random host sessions (key events, resizes, steps) -> state scalars, image, ARGB frame
 Runs on the GPU by default; with LYS_LIBTRACER / LYS_ALLOW_EMULATOR=1 set by tests/test_simt_emu.py it runs the same CUDA sources
 on the CPU SIMT emulator."""
 import importlib
@@ -89,12 +90,77 @@ def fuzz_soup(ctx, rng, count):
     return bad
 
 
+KEYS = [0x20, 0x31, 0x32, 0x61, 0x64, 0x69, 0x6B, 0x6C, 0x6D, 0x6E, 0x6F, 0x70, 0x73, 0x74, 0x77, 0x78, 0x7A,
+        0x4000004F, 0x40000050, 0x40000051, 0x40000052, 0x71, 0x0]        # every key of lib.fut:120-185 plus two unbound ones
+
+
+def fuzz_keys(ctx, rng, count):
+    """random host sessions: key-down / key-up events, resizes and steps in any order (the state machine of lib.fut:108-185 and
+    state.fut), then the state scalars, the accumulated image and the ARGB frame"""
+    d = np.load(os.path.join(ROOT, 'tests', 'golden', 'scenes', 'cornell.npz'))
+    scene = (d['tris'], d['tri_mats'], d['mats'])
+    bad = 0
+    for it in range(count):
+        h, w = int(rng.integers(4, 24)), int(rng.integers(4, 32))
+        kw = dict(cam_conf_id=int(rng.integers(0, 3)), seed=int(rng.integers(0, 100)))
+        so, sg = oracle.State.init(*scene, h, w, **kw), pkg.State.init(ctx, *scene, h, w, **kw)
+        trace = []
+        errored = [False]
+
+        def step_both():
+            """one step on both sides; accumulating onto an image of another shape is a run-time size error in the reference
+            (`img_new :> [m][n]vec3`, integrator.fut:184): the library must report it, the oracle (which aborts) is not asked"""
+            nonlocal so, sg
+            sc = so.scalars()
+            _, _, gw, gh = so.dims()
+            if sc['mode'] and sc['n_frames'] > 0 and so.image().shape[:2] != (gh, gw):
+                try:
+                    sg.step()
+                    raise SystemExit('the library accepted an accumulate step onto an image of another shape: %r' % (trace,))
+                except pkg.TracerError:
+                    errored[0] = True
+                    return False
+            so, sg = so.step(), sg.step()
+            return True
+        for _ in range(int(rng.integers(5, 40))):
+            r = rng.random()
+            if r < 0.55:
+                key, e = int(rng.choice(KEYS)), int(rng.random() < 0.15)
+                if key == 0x32 and so.scalars()['subsampling'] >= 6:
+                    continue
+                so, sg = so.key(key, e), sg.key(key, e)
+                trace.append(('key', hex(key), e))
+            elif r < 0.65:
+                h, w = int(rng.integers(4, 24)), int(rng.integers(4, 32))
+                so, sg = so.resize(h, w), sg.resize(h, w)
+                trace.append(('resize', h, w))
+            else:
+                if not step_both():
+                    break
+                trace.append(('step',))
+        else:
+            step_both()
+        if errored[0]:
+            sg.free()
+            continue
+        a, b = so.scalars(), sg.info()
+        cam_g = np.array([b['cam_pitch'], b['cam_yaw'], *b['cam_origin'], b['aperture'], b['focal_dist']], np.float32)
+        ok = all(a[k] == b[k] for k in ('rng', 'n_frames', 'subsampling', 'render_mode', 'cam_conf_id')) and int(a['mode']) == int(b['mode'])
+        ok = ok and same_bits(a['cam'], cam_g) and same_bits(a['ambience'], b['ambience'])
+        ok = ok and same_bits(so.image(), sg.image()) and same_bits(so.render(), sg.render())
+        if not ok:
+            print('MISMATCH session', it, trace, flush=True)
+            bad += 1
+        sg.free()
+    return bad
+
+
 def main():
     what = sys.argv[1] if len(sys.argv) > 1 else 'lbvh'
     rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
     count = int(sys.argv[3]) if len(sys.argv) > 3 else 50
     with pkg.Context() as ctx, np.errstate(all='ignore'):
-        bad = fuzz_lbvh(ctx, rng, count) if what == 'lbvh' else fuzz_soup(ctx, rng, count)
+        bad = {'lbvh': fuzz_lbvh, 'soup': fuzz_soup, 'keys': fuzz_keys}[what](ctx, rng, count)
     print('%s: %d scenes, %d mismatching' % (what, count, bad), flush=True)
     sys.exit(1 if bad else 0)
 
