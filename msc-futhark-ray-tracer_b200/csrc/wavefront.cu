@@ -1140,7 +1140,7 @@ __global__ void k_material_probe(const float *mat28, float wavelen, V3 wo, V3 wi
 static inline int cdiv(long long a, int b) { return (int)((a + b - 1) / b); }
 
 /* persistent grids: SM count x resident CTAs per SM of each kernel (queried once per device) */
-struct GridSizes { int trace = 0, shade = 0, refill = 0, sl = 0, sb = 0, sc = 0; int sr = 0, sr_keep = 24; int mode = 0, split_bounces = 0, nb = 0, bars = 0, shade_threads = 256, oct = 1, adaptive = 1, sms = 148, tail_max = 8192, tail_items = 128, profile_tail = 0, order = 1, tail_min = 148, fuse_gen = 1, dyn_grids = 0; };
+struct GridSizes { int trace = 0, shade = 0, refill = 0, sl = 0, sb = 0, sc = 0; int sr = 0, sr_keep = 24, sr_cam = 0; int mode = 0, split_bounces = 0, nb = 0, bars = 0, shade_threads = 256, oct = 1, adaptive = 1, sms = 148, tail_max = 8192, tail_items = 128, profile_tail = 0, order = 1, tail_min = 148, fuse_gen = 1, dyn_grids = 0; };
 static GridSizes grid_sizes() {
     static GridSizes g[64];
     int dev = 0; cudaGetDevice(&dev);
@@ -1161,6 +1161,7 @@ static GridSizes grid_sizes() {
         const char *e = getenv("LYS_TRACE_MODE"); g[dev].mode = (e && atoi(e) == 1) ? 1 : 0;      /* 1: k_trace_refill instead of k_trace */
         g[dev].sr = (e && atoi(e) == 2) ? 1 : 0;                                               /* 2: k_trace_sr (staged loop + lane refill) for the bounce launches */
         const char *kp = getenv("LYS_TRACE_SR_KEEP"); if (kp && atoi(kp) >= 1 && atoi(kp) <= 32) g[dev].sr_keep = atoi(kp);
+        const char *kc = getenv("LYS_TRACE_SR_CAMERA"); g[dev].sr_cam = (g[dev].sr && kc && atoi(kc) == 1) ? 1 : 0;    /* camera rays through k_trace_sr too (k_generate + k_trace_sr(-1)) */
         g[dev].sms = sms;
         const char *ord = getenv("LYS_SHADE_ORDER"); if (ord) g[dev].order = atoi(ord) ? 1 : 0;      /* 0: k_shade walks the slots in queue order */
         g[dev].tail_min = sms;
@@ -1189,7 +1190,7 @@ static void launch_trace(const GridSizes &gs0, int grid, const SceneDev &sc, con
     if (gs.nb == 0) gs.nb = (sc.n_tris <= 4096) ? 2 : 1;
     if (gs.mode) { k_trace_refill<<<grid, 128, 0, stream>>>(sc, fp, bufs, bounce); return; }
     const int ordered = (gs.order && bounce >= 0) ? 1 : 0;      /* write the hits-first order of bounce + 1, walk the one of bounce */
-    if (gs.sr && bounce >= 0) {                                /* experimental: staged loop with lane refill (camera rays keep k_trace) */
+    if (gs.sr && (bounce >= 0 || gs.sr_cam)) {                 /* experimental: staged loop with lane refill (camera rays keep k_trace unless LYS_TRACE_SR_CAMERA=1) */
         if (sc.nodes_oct && gs.oct) { if (gs.nb == 1) k_trace_sr<1, true><<<grid, 128, 0, stream>>>(sc, fp, bufs, bounce, ordered, gs.sr_keep); else k_trace_sr<2, true><<<grid, 128, 0, stream>>>(sc, fp, bufs, bounce, ordered, gs.sr_keep); }
         else if (gs.nb == 1) k_trace_sr<1, false><<<grid, 128, 0, stream>>>(sc, fp, bufs, bounce, ordered, gs.sr_keep);
         else k_trace_sr<2, false><<<grid, 128, 0, stream>>>(sc, fp, bufs, bounce, ordered, gs.sr_keep);
@@ -1228,7 +1229,7 @@ cudaError_t run_sample_pass(const SceneDev &sc, const FrameParams &fp, PassBuffe
     int b_tail = fp.path_len;
     if (have_est && gs.tail_max > 0 && !gs.mode && !(tm.on && !gs.profile_tail))      /* per-class timing wants every ray in the trace class */
         for (int k = 1; k < fp.path_len; k++) if (est[k] <= gs.tail_max) { b_tail = k; break; }
-    if (gs.fuse_gen && !gs.mode && !tm.on) {                /* per-class timing keeps the two launches apart */
+    if (gs.fuse_gen && !gs.mode && !gs.sr_cam && !tm.on) {  /* per-class timing keeps the two launches apart */
         const int nb = gs.nb ? gs.nb : ((sc.n_tris <= 4096) ? 2 : 1);
         const int g = cdiv(n, 128);
         if (sc.nodes_oct && gs.oct) { if (nb == 1) k_generate_trace<1, true><<<g, 128, 0, stream>>>(sc, fp, bufs); else k_generate_trace<2, true><<<g, 128, 0, stream>>>(sc, fp, bufs); }

@@ -52,6 +52,7 @@ def test_emulated_library_equals_the_oracle(emu_lib):
     {'LYS_TRACE_MODE': '2'},                           # k_trace_sr: staged loop + lane refill (experimental, emulator-validated only)
     {'LYS_TRACE_MODE': '2', 'LYS_TRACE_SR_KEEP': '32', 'LYS_TRACE_OCT': '0', 'LYS_TRACE_NB': '1', 'LYS_EMU_SMS': '2'},   # refill at every idle lane, long slices
     {'LYS_TRACE_MODE': '2', 'LYS_TRACE_SR_KEEP': '1', 'LYS_TAIL_MAX': '0', 'LYS_SHADE_ORDER': '0', 'LYS_EMU_SMS': '32'},  # refill only when the warp is empty, short slices
+    {'LYS_TRACE_MODE': '2', 'LYS_TRACE_SR_CAMERA': '1'},   # camera rays through k_trace_sr as well (k_generate + k_trace_sr(-1))
     {'LYS_EMU_SCHEDULE': '1'},                         # CTAs, warps and lanes run in reverse order: results must not depend on the schedule
     {'LYS_EMU_SCHEDULE': '4242', 'LYS_TAIL_MAX': '100000000'},       # pseudo-random orders, redrawn per CTA (race / order-dependence probe)
     {'LYS_EMU_SCHEDULE': '977', 'LYS_TRACE_MODE': '2', 'LYS_EMU_SMS': '8'},

@@ -13,6 +13,7 @@ for m in 0 2; do
   LYS_TRACE_MODE=$m python tools/bench_configs.py metric 3 4 5 > $O/n_configs_mode$m.jsonl 2> $O/n_configs_mode$m.err
   cut -c1-160 $O/n_configs_mode$m.jsonl
 done
+LYS_TRACE_MODE=2 LYS_TRACE_SR_CAMERA=1 python tools/bench_configs.py 4 5 > $O/n_configs_mode2_camera.jsonl 2>/dev/null; cut -c1-160 $O/n_configs_mode2_camera.jsonl
 for k in 16 28; do
   LYS_TRACE_MODE=2 LYS_TRACE_SR_KEEP=$k python tools/bench_configs.py 4 5 > $O/n_configs_mode2_keep$k.jsonl 2>/dev/null; cut -c1-160 $O/n_configs_mode2_keep$k.jsonl
 done
