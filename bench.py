@@ -50,8 +50,12 @@ def load_scene(name=SCENE):
 
 def peaks():
     p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
-    if os.path.exists(p):
-        return float(json.load(open(p))['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    try:
+        v = float(json.load(open(p))['hbm_gbs'])
+        if v > 0:
+            return v, 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    except (OSError, ValueError, KeyError, TypeError):
+        pass
     return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
 
 
