@@ -25,4 +25,6 @@ done
 for t in 65536 262144 1048576; do
   LYS_TAIL_MAX=$t python tools/bench_configs.py 5 > $O/n_configs_tailmax$t.jsonl 2>/dev/null; cut -c1-160 $O/n_configs_tailmax$t.jsonl
 done
+# 2c. the interactive loop is latency bound (one pass at a time): an earlier fused tail shortens its chain of small launches
+for t in 8192 32768 131072; do LYS_TAIL_MAX=$t python tools/bench_interactive.py > $O/n_interactive_tailmax$t.json 2>/dev/null; cut -c1-200 $O/n_interactive_tailmax$t.json; done
 python tools/bench_synthetic_multi.py --passes 256 > $O/n_synth_n1.json 2> $O/n_synth_n1.err; cat $O/n_synth_n1.json
