@@ -8,6 +8,9 @@
 set -x
 O=gpurun_out
 mkdir -p $O
+# 0. the randomised parity runs that so far only ran on the CPU emulator, on the real device (about a minute)
+for f in "soup 21 200" "lbvh 22 300" "keys 23 60"; do python tools/fuzz_parity.py $f > $O/n_fuzz_$(echo $f | cut -d' ' -f1).log 2>&1; tail -1 $O/n_fuzz_$(echo $f | cut -d' ' -f1).log; done
+LYS_TRACE_MODE=2 python tools/fuzz_parity.py soup 24 100 > $O/n_fuzz_soup_mode2.log 2>&1; tail -1 $O/n_fuzz_soup_mode2.log
 LYS_TRACE_MODE=2 python tools/gpu_parity_quick.py > $O/n_parity_mode2.log 2>&1; tail -3 $O/n_parity_mode2.log | cut -c1-300
 for m in 0 2; do
   LYS_TRACE_MODE=$m python tools/bench_configs.py metric 3 4 5 > $O/n_configs_mode$m.jsonl 2> $O/n_configs_mode$m.err
