@@ -14,7 +14,7 @@ sys.path.insert(0, os.path.join(ROOT, 'tests', 'simt_emu'))
 
 @pytest.fixture(scope='module')
 def emu_lib():
-    import build as emu_build
+    import emu_build
     return emu_build.build()
 
 
