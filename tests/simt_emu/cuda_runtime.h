@@ -2,7 +2,7 @@
  * (tests/simt_emu/README.md).  TEST INFRASTRUCTURE: it is found instead of the real header because tests/simt_emu comes
  * first on the include path of that one build; the product (msc-futhark-ray-tracer_b200/Makefile, nvcc) never sees it.
  *
- * What it provides, so that the UNMODIFIED csrc/*.cu sources compile with g++ and run on the host:
+ * What it provides, so that the UNMODIFIED product sources (the .cu files under csrc) compile with g++ and run on the host:
  *   - the CUDA qualifiers as no-ops, vector types, the device intrinsics the sources use;
  *   - threadIdx / blockIdx / blockDim / gridDim of the lane that is running;
  *   - warp collectives (__ballot_sync, __any_sync, __shfl_sync, __shfl_xor_sync, __reduce_add_sync, __match_any_sync,
