@@ -117,3 +117,36 @@ def test_fuzzed_parity_on_the_emulator(emu_lib, what, seed, count, env):
     e.update({'LYS_LIBTRACER': emu_lib, 'LYS_ALLOW_EMULATOR': '1'})
     r = subprocess.run([sys.executable, os.path.join(ROOT, 'tools', 'fuzz_parity.py'), what, str(seed), str(count)], env=e, text=True, capture_output=True, timeout=1500)
     assert r.returncode == 0 and '%d scenes, 0 mismatching' % count in r.stdout, r.stdout[-2000:] + r.stderr[-1000:]
+
+
+def test_c_hosts_on_the_emulator(emu_lib, orc, scenes, tmp_path):
+    """The C hosts (host/lys_save.c = the reference's demo-save, host/lys_headless.c = liblys.c's loop) linked against the
+    emulated library: their whole flow -- OBJ/MTL loader, futhark_new_*, init, sample_points_n / step + render, file writers --
+    on the CPU, against the oracle.  (The GPU versions of these checks are in tests/test_c_host.py.)"""
+    import numpy as np
+    import emu_build
+    from conftest import bits_equal
+    from lysref import objwriter
+    exe = emu_build.build_hosts()
+    t, tm, m = scenes['spectrumsphere']
+    obj, pcd, ppm = str(tmp_path / 's.obj'), str(tmp_path / 'dump.pcd'), str(tmp_path / 'f.ppm')
+    objwriter.write_obj(obj, t, tm, m)
+    w, h, spp = 40, 30, 3
+    out = subprocess.check_output([exe['lys_save'], '-o', obj, '-w', str(w), '-h', str(h), '-s', str(spp), '-p', pcd], text=True, timeout=600)
+    assert 'points %d' % (w * h) in out
+    lines = open(pcd).read().split('\n')
+    assert lines[6] == 'WIDTH %d' % (w * h) and lines[10] == 'DATA ascii'
+    got = np.array([[np.float32(x) for x in line.split(' ')] for line in lines[11:] if line], np.float32).reshape(h, w, 3)
+    want = orc.State.init(t, tm, m, h, w, cam_conf_id=2).sample_points_n(spp)[1]
+    assert bits_equal(got, np.ascontiguousarray(want[..., :3]))
+    frames = 3
+    out = subprocess.check_output([exe['lys_headless'], '-o', obj, '-w', str(w), '-h', str(h), '-n', str(frames), '-k', '109', '-p', ppm], text=True, timeout=600)
+    assert 'frames %d' % frames in out
+    raw = open(ppm, 'rb').read()
+    hdr = ('P6\n%d %d\n255\n' % (w, h)).encode()
+    img = np.frombuffer(raw[len(hdr):], np.uint8).reshape(h, w, 3)
+    so = orc.State.init(t, tm, m, h, w).resize(h, w).key(109)
+    for _ in range(frames):
+        so = so.step()
+    px = so.render().view(np.uint32)
+    assert np.array_equal(img, np.stack([(px >> 16) & 255, (px >> 8) & 255, px & 255], axis=2).astype(np.uint8)) and img.max() > 0
