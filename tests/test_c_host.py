@@ -151,3 +151,33 @@ def test_c_save_host_image_matches_python_host(pkg, gpu, scenes, tmp_path):
     img = pkg.State.init(gpu, t, tm, m, h, w).sample_n_frames(n)
     want = (np.clip(np.nan_to_num(img, nan=0.0, posinf=1.0, neginf=0.0), 0, 1) * np.float32(255.99)).astype(np.uint8)
     assert np.array_equal(got, want) and got.max() > 0
+
+
+REF_HOST = os.path.join(ROOT, 'host', 'liblys_ref_headless')
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(REF_HOST), reason='host/liblys_ref_headless is built in the container that holds the reference checkout (tests/simt_emu/emu_build.py)')
+def test_unmodified_reference_host_on_the_gpu(pkg, gpu, scenes, tmp_path):
+    """The reference's demo-interactive/liblys.c, compiled unmodified and linked against the static libtracer.a and the headless
+    SDL stand-in (tests/sdl_stub), on the B200: a scripted session (800x600 window, resize, SPACE, five frames); the last window
+    contents equal the Python host's frame for the same session."""
+    from lysref import objwriter
+    t, tm, m = scenes['spectrumsphere']
+    obj, ppm = str(tmp_path / 's.obj'), str(tmp_path / 'w.ppm')
+    objwriter.write_obj(obj, t, tm, m)
+    e = dict(os.environ)
+    e.update({'LYS_SDL_SCRIPT': '0:resize:320x200 1:key:32 5:quit', 'LYS_SDL_DUMP': ppm})
+    r = subprocess.run([REF_HOST, '-o', obj], env=e, text=True, capture_output=True, timeout=300)
+    if r.returncode != 0:                                  # a prebuilt binary that travelled here: do not let a loader problem mask the suite
+        pytest.skip('host/liblys_ref_headless did not run on this box: ' + (r.stderr or r.stdout)[-300:])
+    assert 'sdl_stub: 5 frames, 3 events, window 320x200' in r.stdout
+    s = pkg.State.init(gpu, t, tm, m, 600, 800).resize(600, 800).step().resize(200, 320).key(32)
+    for _ in range(4):
+        s = s.step()
+    px = s.render().view(np.uint32)
+    want = np.stack([(px >> 16) & 255, (px >> 8) & 255, px & 255], axis=2).astype(np.uint8)
+    raw = open(ppm, 'rb').read()
+    hdr = b'P6\n320 200\n255\n'
+    assert raw.startswith(hdr)
+    assert np.array_equal(np.frombuffer(raw[len(hdr):], np.uint8).reshape(200, 320, 3), want) and want.max() > 0

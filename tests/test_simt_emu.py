@@ -150,3 +150,35 @@ def test_c_hosts_on_the_emulator(emu_lib, orc, scenes, tmp_path):
         so = so.step()
     px = so.render().view(np.uint32)
     assert np.array_equal(img, np.stack([(px >> 16) & 255, (px >> 8) & 255, px & 255], axis=2).astype(np.uint8)) and img.max() > 0
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/demo-interactive'), reason='the reference checkout only exists in the build container')
+def test_unmodified_reference_host_runs_against_the_library(emu_lib, orc, scenes, tmp_path):
+    """demo-interactive/liblys.c, compiled UNMODIFIED from the reference checkout, linked against the (emulated) library and a
+    headless SDL stand-in (tests/sdl_stub), runs a scripted session -- its own init with an 800x600 window, a resize event, a
+    key event, five frames -- and the last window contents equal the oracle's ARGB frame for the same session."""
+    import numpy as np
+    import emu_build
+    from lysref import objwriter
+    exe = emu_build.build_reference_host()
+    assert 'emu' in exe
+    t, tm, m = scenes['cornell']
+    obj, ppm = str(tmp_path / 'c.obj'), str(tmp_path / 'w.ppm')
+    objwriter.write_obj(obj, t, tm, m)
+    e = dict(os.environ)
+    e.update({'LYS_SDL_SCRIPT': '0:resize:64x48 1:key:32 5:quit', 'LYS_SDL_DUMP': ppm})
+    out = subprocess.check_output([exe['emu'], '-o', obj], env=e, text=True, timeout=900)
+    assert 'sdl_stub: 5 frames, 3 events, window 64x48' in out
+    s = orc.State.init(t, tm, m, 600, 800).resize(600, 800).step().resize(48, 64).key(32)      # liblys.c:133-152, then the script
+    for _ in range(4):
+        s = s.step()
+    px = s.render().view(np.uint32)
+    want = np.stack([(px >> 16) & 255, (px >> 8) & 255, px & 255], axis=2).astype(np.uint8)
+    raw = open(ppm, 'rb').read()
+    hdr = b'P6\n64 48\n255\n'
+    assert raw.startswith(hdr)
+    assert np.array_equal(np.frombuffer(raw[len(hdr):], np.uint8).reshape(48, 64, 3), want) and want.max() > 0
+    # the reference's own error path: accumulating (key m) onto an image of another size is a Futhark size error (integrator.fut:184)
+    e['LYS_SDL_SCRIPT'] = '0:resize:32x24 0:key:109 3:quit'
+    r = subprocess.run([exe['emu'], '-o', obj], env=e, text=True, capture_output=True, timeout=900)
+    assert r.returncode != 0 and 'Futhark error' in r.stderr and 'shape does not match' in r.stderr
