@@ -10,9 +10,14 @@ accumulated on the device.  A path = one pixel sample (one `sample_pixel`, integ
   e2e        the same through the C ABI from HOST buffers: futhark_new_* (H2D of the triangle / material arrays),
              futhark_entry_init (LBVH build), futhark_entry_sample_n_frames, futhark_values_f32_3d (D2H framebuffer),
              every step, inside the timed region.
-  roofline   dominant kernel class (BVH traversal `k_trace`), device time from CUDA events recorded by the
-             library around every launch (separate profiling step), algorithmic bytes from the oracle's
-             counters for the same workload: 32 B per box test + 40 B per triangle test.
+  roofline   dominant kernel class = BVH traversal (k_generate_trace + k_trace + k_tail).  The PRODUCTION launch sequence of
+             the timed region (fused camera-ray launch, fused tail, 8 passes in flight) is run again with CUDA events
+             around every launch (library timer mode 2); kernels of different passes overlap, so the per-class event sums
+             are used as SHARES and the class times are share x ms_per_step (they add up to the step).  Algorithmic bytes
+             from the oracle's counters for the same workload: 32 B per box test + 40 B per triangle test (SURVEY.md
+             8(d)).  The scene is cache resident, so the bound is SM issue: roofline.issue = warp instructions of a pass
+             (committed ncu launch list of this workload, profiles/r2_pass_ncu.json) x passes / step time against
+             SMs x 4 x SM clock, with the instruction-weighted active threads per instruction.
   cpu_baseline  the CPU restatement of the reference (oracle/, OpenMP over pixel rows) on a bounded sample.
 
 N > 1 (torchrun): one process per GPU, scene replicated, each rank renders its own PASSES passes of the full
@@ -107,15 +112,18 @@ def host_threads():
         return os.cpu_count() or 1
 
 
-def ncu_traffic():
-    """DRAM bytes per k_trace launch from the committed ncu launch list of this workload (profiles/, see tools/ncu_pass_summary.py);
-    measured under the profiler once per round, not in this run."""
-    p = os.path.join(ROOT, 'profiles', 'r1_k_trace_dram.json')
-    try:
-        d = json.load(open(p))
-        return d['per_bounce_sequence']['dram_bytes_per_launch'], 'profiles/r1_k_trace_dram.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean over the 17 k_trace launches of a pass)'
-    except Exception:
-        return None, None
+def ncu_pass():
+    """Per-pass ncu figures of this workload's steady-state (production) launch sequence from the committed launch list
+    (profiles/, made by tools/ncu_pass_summary.py from an `ncu --csv` run of tools/prof_pass.py): DRAM bytes and warp
+    instructions are properties of the launch sequence, measured under the profiler once per round, not in this run."""
+    for name in ('r2_pass_ncu.json', 'r1_k_trace_dram.json'):
+        try:
+            d = json.load(open(os.path.join(ROOT, 'profiles', name)))['steady_state_sequence']
+            if 'warp_inst_per_pass' in d:
+                return d, 'profiles/' + name
+        except Exception:
+            pass
+    return None, None
 
 
 def cpu_baseline(oracle, scene, passes, threads=None, target_s=15.0):
@@ -202,16 +210,18 @@ def main():
     base = pkg.State.init(ctx, t, tm, m, H, W)
     state = base.advance_rng(rank * PASSES) if world > 1 else base      # disjoint pass ranges per rank
 
+    weight = par.pass_weight(PASSES, [PASSES] * world) if world > 1 else 1.0
+
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
     def step_resident():
-        h, ptr, shape, _ = state.sample_n_frames_device(PASSES, want_stats=False)
+        h, ptr, shape, _ = state.sample_n_frames_device(PASSES, want_stats=False, weight=weight)   # weight applied by the last accumulate kernel
         if world > 1:
-            with torch.cuda.stream(stream):     # weights + ONE sum-reduce: rank 0 ends up with the mean over all ranks' passes
-                par.merge_pass_split(par.as_torch(ptr, shape, dev), PASSES, [PASSES] * world, dst=0)
+            with torch.cuda.stream(stream):     # ONE sum-reduce: rank 0 ends up with the mean over all ranks' passes
+                par.merge_pass_split(par.as_torch(ptr, shape, dev), PASSES, [PASSES] * world, dst=0, weighted=True)
         return h
 
     # ---- value: state resident in HBM, result left on the device ------------------------------------------
@@ -252,10 +262,10 @@ def main():
             s2 = s.advance_rng(rank * PASSES)
             s.free()
             s = s2
-        hnd, ptr, shape, _ = s.sample_n_frames_device(PASSES, want_stats=False)
+        hnd, ptr, shape, _ = s.sample_n_frames_device(PASSES, want_stats=False, weight=weight)
         if world > 1:
             with torch.cuda.stream(stream):
-                par.merge_pass_split(par.as_torch(ptr, shape, dev), PASSES, [PASSES] * world, dst=0)
+                par.merge_pass_split(par.as_torch(ptr, shape, dev), PASSES, [PASSES] * world, dst=0, weighted=True)
         if rank == 0:
             ctx.check(ctx._L.futhark_values_f32_3d(ctx._ctx, hnd, out_pin.data_ptr()), 'futhark_values_f32_3d')   # blocking D2H
         else:
@@ -279,13 +289,21 @@ def main():
 
     line = None
     if rank == 0:
-        # ---- roofline: kernel-class device time (library events) + oracle counters -------------------------
-        ctx.set_profiling(True)
-        ctx.profile(reset=True)
-        hnd = step_resident() if world == 1 else state.sample_n_frames_device(PASSES, want_stats=False)[0]
-        prof = ctx.profile(reset=True)
-        ctx.set_profiling(False)
-        state.free_f32_3d(hnd)
+        # ---- roofline: the production sequence again, with events around every launch (shares of the step) ----------
+        prof, prof_ms = None, None
+        if world == 1:
+            PROF_STEPS = 5
+            ctx.set_profiling(2)
+            ctx.profile(reset=True)
+            p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            p0.record(stream)
+            for _ in range(PROF_STEPS):
+                state.free_f32_3d(step_resident())
+            p1.record(stream)
+            torch.cuda.synchronize(dev)
+            prof = ctx.profile(reset=True)
+            ctx.set_profiling(0)
+            prof_ms = p0.elapsed_time(p1) / PROF_STEPS
         build_ms = base.bvh_rebuild_ms(5)
         build_1m = None
         if world == 1:
@@ -304,21 +322,41 @@ def main():
             ext_bytes = (32 * per_path['closest_box'] + 40 * per_path['closest_tri']) * W * H * PASSES       # all k_extend launches of a step
             con_bytes = (32 * per_path['shadow_box'] + 40 * per_path['shadow_tri']) * W * H * PASSES
             b_path = 24 + 32 * per_path['box_tests'] + 40 * per_path['tri_tests'] + 112 * per_path['vertices']
-            tr_ms, tr_n = prof['trace']
+            step_ms = ms / args.steps
+            ev_tot = sum(v[0] for v in prof.values())
+            share = {k: v[0] / ev_tot for k, v in prof.items()}                       # overlapping kernels: shares, not exclusive times
+            class_ms = {k: share[k] * step_ms for k in prof}                          # adds up to ms_per_step
+            tr_ms = class_ms['trace'] + class_ms['tail']                              # every traversal launch (the tail also shades its few paths)
+            tr_n = (prof['trace'][1] + prof['tail'][1]) / PROF_STEPS                  # traversal launches per step
             tr_bytes = ext_bytes + con_bytes
-            tot_ms = sum(v[0] for v in prof.values())
             achieved = tr_bytes / (tr_ms * 1e-3) / 1e9
-            traffic, traffic_src = ncu_traffic()
-            roof = {'bound': 'hbm', 'kernel': 'k_trace (closest hits + shadow rays, all launches of a step)', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-                    'frac': achieved / peak, 'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': peak_src,
-                    'algorithmic_bytes_per_launch': tr_bytes / max(tr_n, 1), 'avg_launch_ms': tr_ms / max(tr_n, 1), 'launches': tr_n,
-                    'share_of_step': tr_ms / tot_ms if tot_ms else None,
-                    'b_path_bytes': b_path, 'whole_pass_algorithmic_gbs': b_path * W * H * PASSES / (tot_ms * 1e-3) / 1e9,
+            ncu, ncu_src = ncu_pass()
+            issue = None
+            if ncu:
+                props = torch.cuda.get_device_properties(dev)
+                mhz = (clocks or {}).get('sm_mhz') or (clocks or {}).get('sm_max_mhz') or 1965.0
+                issue_peak = props.multi_processor_count * 4 * mhz * 1e6              # warp instructions / s: 4 schedulers per SM, one per cycle
+                w_step = ncu['warp_inst_per_pass'] * PASSES
+                issue = {'warp_inst_per_step': w_step, 'warp_inst_per_s': w_step / (step_ms * 1e-3), 'issue_peak_per_s': issue_peak,
+                         'frac_of_issue_peak': w_step / (step_ms * 1e-3) / issue_peak, 'threads_per_inst': ncu['threads_per_inst'],
+                         'frac_of_lane_issue_peak': w_step / (step_ms * 1e-3) / issue_peak * ncu['threads_per_inst'] / 32.0,
+                         'k_trace_warp_inst_per_step': ncu['k_trace_warp_inst_per_pass'] * PASSES, 'k_trace_threads_per_inst': ncu['k_trace_threads_per_inst'],
+                         'sm_count': props.multi_processor_count, 'sm_mhz_used': mhz,
+                         'source': ncu_src + ' (smsp__inst_executed.sum, smsp__thread_inst_executed_per_inst_executed.ratio per launch of one steady-state pass) x %d passes / ms_per_step' % PASSES}
+            roof = {'bound': 'issue', 'kernel': 'BVH traversal: k_generate_trace + k_trace + k_tail (closest hits + shadow rays), all launches of a step',
+                    'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                    'traffic': ncu['dram_bytes_per_launch'] if ncu else None,
+                    'traffic_source': (ncu_src + ' (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean over the traversal launches of a steady-state pass)') if ncu else None,
+                    'peak_source': peak_src, 'algorithmic_bytes_per_launch': tr_bytes / max(tr_n, 1), 'avg_launch_ms': tr_ms / max(tr_n, 1), 'launches': tr_n,
+                    'share_of_step': share['trace'] + share['tail'], 'issue': issue,
+                    'b_path_bytes': b_path, 'whole_pass_algorithmic_gbs': b_path * W * H * PASSES / (step_ms * 1e-3) / 1e9,
                     'rays_per_s': (per_path['closest_rays'] + per_path['shadow_rays']) * W * H * PASSES / (tr_ms * 1e-3),
                     'per_path': {k: round(per_path[k], 3) for k in ('vertices', 'closest_rays', 'shadow_rays', 'closest_box', 'closest_tri', 'shadow_box', 'shadow_tri')},
-                    'class_ms': {k: round(v[0], 3) for k, v in prof.items()},
-                    'note': 'scene (3.6 KB BVH) is L1/L2 resident: this path is issue/latency bound, the HBM fraction is reported as the contract asks; '
-                            'class times come from a profiled run with one launch per bounce (no fused k_tail), so the trace class holds every ray'}
+                    'class_ms': {k: round(v, 3) for k, v in class_ms.items()}, 'class_share': {k: round(v, 4) for k, v in share.items()},
+                    'profiled_ms_per_step': prof_ms,
+                    'note': 'bound = SM issue (the 3.6 KB BVH is L1/L2 resident; DRAM only sees path state): see roofline.issue; achieved / frac are the algorithmic '
+                            'traversal bytes over the traversal classes\' share of the timed step against the HBM peak, as the contract asks. class_ms = event-time '
+                            'shares of the production sequence (profiled right after the timed region, profiled_ms_per_step) x ms_per_step'}
         line = {'metric': 'Mpaths/s', 'value': value, 'unit': 'Mpaths/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
                 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
                 'data': 'bundled scene arrays (tests/golden/scenes/cornell.npz), synthetic camera path',

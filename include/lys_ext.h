@@ -31,6 +31,9 @@ uint64_t lys_context_launch_count(struct futhark_context *ctx);
 
 /* Kernel-class device timing (CUDA events around every launch of the sample pass).  Off by default: the
  * extra event records perturb throughput, so it is used for a separate profiling step, never the timed run.
+ * on = 1: one launch per stage and bounce, one pass at a time (exclusive times; every ray in the trace class);
+ * on = 2: the production sequence (fused camera-ray launch, fused tail, passes pipelined over streams) with events around
+ *         its launches: kernels of different passes overlap, so the class sums are SHARES of the step, not exclusive times.
  * Classes: 0 generate, 1 trace (closest hits of bounce b+1 + shadow rays of bounce b), 2 shade, 3 tail (k_tail: all bounces from the first sparse one on, in one launch), 4 accumulate. */
 #define LYS_PROFILE_CLASSES 5
 int lys_context_set_profiling(struct futhark_context *ctx, int on);
@@ -98,6 +101,11 @@ typedef struct {
 } lys_pass_stats;
 int lys_sample_n_frames_stats(struct futhark_context *ctx, struct futhark_f32_3d **out0,
                               const struct futhark_opaque_state *s, uint32_t n, lys_pass_stats *stats);
+/* The same with the image multiplied by `weight` inside the last accumulate kernel: the share of this rank's passes in a
+ * pass-split multi-GPU frame, so that the per-rank images only need the one sum-reduce.  weight 1 = the
+ * reference's result, bit for bit.  stats may be NULL. */
+int lys_sample_n_frames_weighted(struct futhark_context *ctx, struct futhark_f32_3d **out0,
+                                 const struct futhark_opaque_state *s, uint32_t n, float weight, lys_pass_stats *stats);
 
 #ifdef __cplusplus
 }

@@ -23,17 +23,18 @@
 using namespace lys;
 
 /* ------------------------------------------------------------------ objects */
-struct futhark_context_config { int device = 0; std::string device_name; int debugging = 0; int logging = 0; int profiling = 0; };
+struct futhark_context_config { int device = 0; std::string device_name; int debugging = 0; int logging = 0; int profiling = 0; };   /* device = the #k of "#k name": k-th device whose name contains `device_name` */
 
 struct futhark_context {
     int device = 0;
     cudaStream_t stream = nullptr;
     std::string error;
-    bool failed = false;
     int path_len = 16, refit_mode = 0, rank = 0, world = 1;
     uint64_t launches = 0;
     int logging = 0;
     std::multimap<size_t, void *> pool;          /* free device blocks by size */
+    size_t pooled_bytes = 0, pool_cap = (size_t)1 << 30;   /* the pool never holds more than pool_cap bytes (set from the device size) */
+    struct InitReadback { int lights[4]; float origin[3]; int crown_overflow; } *h_init = nullptr;   /* pinned: the one read-back of futhark_entry_init */
     PassBuffers bufs; BuildScratch scratch;
     float4 *pts_pos = nullptr; float *pts_dist = nullptr; int64_t pts_cap = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr;
@@ -52,32 +53,59 @@ namespace {
 struct DevBlock {
     futhark_context *ctx; void *p; size_t bytes;
     DevBlock(futhark_context *c, void *q, size_t b) : ctx(c), p(q), bytes(b) {}
-    ~DevBlock() { if (p) ctx->pool.insert({bytes, p}); }
+    ~DevBlock();
 };
 typedef std::shared_ptr<DevBlock> DevRef;
 
 bool set_error(futhark_context *ctx, const std::string &msg) { ctx->error = msg; return false; }
 bool cu_ok(futhark_context *ctx, cudaError_t e, const char *what) {
     if (e == cudaSuccess) return true;
-    ctx->failed = true;
     return set_error(ctx, std::string(what) + ": " + cudaGetErrorString(e));
 }
 #define CU(ctx, call) do { if (!cu_ok(ctx, (call), #call)) return 1; } while (0)
 #define CUB(ctx, call) do { if (!cu_ok(ctx, (call), #call)) return false; } while (0)
 
+/* Block pool.  Every step / render / resize takes its image from here and gives it back when the state is freed, so the
+ * steady state of a host loop costs no cudaMalloc / cudaFree.  Reuse is best fit within 12.5 % slack (a window dragged
+ * through many sizes reuses near-size blocks instead of parking one block per size); the pool holds at most pool_cap bytes
+ * (largest blocks are released first beyond that); when cudaMalloc fails the whole pool is released and the call retried
+ * once, as Futhark's generated allocator does. */
+void pool_release_all(futhark_context *ctx) {
+    if (ctx->pool.empty()) return;
+    cudaStreamSynchronize(ctx->stream);
+    for (auto &kv : ctx->pool) cudaFree(kv.second);
+    ctx->pool.clear(); ctx->pooled_bytes = 0;
+}
+DevBlock::~DevBlock() {
+    if (!p) return;
+    ctx->pool.insert({bytes, p}); ctx->pooled_bytes += bytes;
+    while (ctx->pooled_bytes > ctx->pool_cap && !ctx->pool.empty()) {
+        auto last = std::prev(ctx->pool.end());
+        ctx->pooled_bytes -= last->first;
+        cudaFree(last->second);                 /* synchronises: nothing can still be using a block that is being dropped */
+        ctx->pool.erase(last);
+    }
+}
 DevRef dev_alloc(futhark_context *ctx, size_t bytes) {
     if (bytes == 0) bytes = 16;
     bytes = (bytes + 255) & ~(size_t)255;
-    auto it = ctx->pool.find(bytes);
-    if (it != ctx->pool.end()) { void *p = it->second; ctx->pool.erase(it); return std::make_shared<DevBlock>(ctx, p, bytes); }
+    auto it = ctx->pool.lower_bound(bytes);
+    if (it != ctx->pool.end() && it->first <= bytes + bytes / 8) {
+        void *p = it->second; const size_t have = it->first;
+        ctx->pool.erase(it); ctx->pooled_bytes -= have;
+        return std::make_shared<DevBlock>(ctx, p, have);
+    }
     void *p = nullptr;
     cudaError_t e = cudaMalloc(&p, bytes);
+    if (e == cudaErrorMemoryAllocation) { cudaGetLastError(); pool_release_all(ctx); e = cudaMalloc(&p, bytes); }
     if (e != cudaSuccess) { cu_ok(ctx, e, "cudaMalloc"); return nullptr; }
     return std::make_shared<DevBlock>(ctx, p, bytes);
 }
 template <class T> bool raw_alloc(futhark_context *ctx, T *&p, size_t count) {
     void *q = nullptr;
-    if (!cu_ok(ctx, cudaMalloc(&q, sizeof(T) * (count ? count : 1)), "cudaMalloc")) return false;
+    cudaError_t e = cudaMalloc(&q, sizeof(T) * (count ? count : 1));
+    if (e == cudaErrorMemoryAllocation) { cudaGetLastError(); pool_release_all(ctx); e = cudaMalloc(&q, sizeof(T) * (count ? count : 1)); }
+    if (!cu_ok(ctx, e, "cudaMalloc")) return false;
     p = (T *)q; return true;
 }
 template <class T> void raw_free(T *&p) { if (p) cudaFree(p); p = nullptr; }
@@ -86,6 +114,7 @@ template <class T> void raw_free(T *&p) { if (p) cudaFree(p); p = nullptr; }
  * (the e2e benchmark does it every step) costs no cudaMalloc / cudaFree (cudaFree synchronises the device) */
 struct SceneHolder {
     SceneDev d;
+    int refit_mode = 0;                  /* the mode the BVH was built with (a later rebuild must not change its semantics) */
     std::vector<DevRef> blocks;
     template <class T> bool take(futhark_context *ctx, T *&p, size_t count) {
         DevRef r = dev_alloc(ctx, sizeof(T) * (count ? count : 1));
@@ -353,17 +382,6 @@ uint32_t h_rng_from_seed(int32_t seed) {                                        
 
 futhark_opaque_state *clone_state(const futhark_opaque_state *s) { return new futhark_opaque_state(*s); }
 
-/* LBVH build; if the crown pair buffer overflowed, redo the refit with the literal Jacobi sweeps (always exact) */
-bool build_scene_bvh(futhark_context *ctx, SceneDev &sc, bool check_overflow) {
-    CUB(ctx, build_lbvh(sc, ctx->scratch, ctx->refit_mode, ctx->stream, &ctx->launches));
-    if (check_overflow && ctx->refit_mode == 0) {
-        int ovf = 0;
-        CUB(ctx, cudaMemcpyAsync(&ovf, ctx->scratch.crown_cnt + 63, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-        CUB(ctx, cudaStreamSynchronize(ctx->stream));
-        if (ovf) CUB(ctx, build_lbvh(sc, ctx->scratch, 2, ctx->stream, &ctx->launches));
-    }
-    return true;
-}
 
 /* sample_frame / sample_frame_accum (integrator.fut:172-192) into `img` */
 bool sample_into(futhark_context *ctx, const futhark_opaque_state *s, uint32_t rng, const float *img_old, float *img_new, bool merge, float n_frames) {
@@ -384,11 +402,12 @@ extern "C" {
 struct futhark_context_config *futhark_context_config_new(void) { return new futhark_context_config(); }
 void futhark_context_config_free(struct futhark_context_config *cfg) { delete cfg; }
 void futhark_context_config_set_device(struct futhark_context_config *cfg, const char *s) {
+    /* as the generated cuda backend parses it: an optional "#k" (k-th matching device), then a substring of the device
+     * name; a bare number is a name substring, not an index */
     if (!cfg || !s) return;
-    const char *p = (*s == '#') ? s + 1 : s;
-    char *end = nullptr; long v = strtol(p, &end, 10);
-    if (end != p && *end == '\0') { cfg->device = (int)v; cfg->device_name.clear(); }
-    else cfg->device_name = s;
+    int k = 0;
+    if (*s == '#') { s++; while (*s >= '0' && *s <= '9') k = k * 10 + (*s++ - '0'); while (*s == ' ' || *s == '\t') s++; }
+    cfg->device = k; cfg->device_name = s;
 }
 void futhark_context_config_set_debugging(struct futhark_context_config *cfg, int flag) { if (cfg) cfg->debugging = flag; }
 void futhark_context_config_set_logging(struct futhark_context_config *cfg, int flag) { if (cfg) cfg->logging = flag; }
@@ -399,13 +418,17 @@ struct futhark_context *futhark_context_new(struct futhark_context_config *cfg) 
         fprintf(stderr, "libtracer: no CUDA device available (this library has no CPU path)\n");
         return nullptr;
     }
-    int dev = cfg ? cfg->device : 0;
-    if (cfg && !cfg->device_name.empty()) {
-        dev = -1;
-        for (int i = 0; i < count; i++) { cudaDeviceProp p; if (cudaGetDeviceProperties(&p, i) == cudaSuccess && strstr(p.name, cfg->device_name.c_str())) { dev = i; break; } }
-        if (dev < 0) { fprintf(stderr, "libtracer: no CUDA device matches '%s'\n", cfg->device_name.c_str()); return nullptr; }
+    int dev = -1;
+    {
+        int want = cfg ? cfg->device : 0, seen = 0;
+        const char *name = cfg ? cfg->device_name.c_str() : "";
+        for (int i = 0; i < count && dev < 0; i++) {
+            cudaDeviceProp p;
+            if (cudaGetDeviceProperties(&p, i) != cudaSuccess || !strstr(p.name, name)) continue;
+            if (seen++ == want) dev = i;
+        }
+        if (dev < 0) { fprintf(stderr, "libtracer: no CUDA device #%d matching '%s'\n", want, name); return nullptr; }
     }
-    if (dev < 0 || dev >= count) { fprintf(stderr, "libtracer: CUDA device %d out of range\n", dev); return nullptr; }
     if (cudaSetDevice(dev) != cudaSuccess) return nullptr;
     /* the sample pass alternates kernels with different local-memory footprints (traversal stacks, shading
      * temporaries); without this flag the driver may shrink / regrow the local-memory pool between launches */
@@ -415,10 +438,12 @@ struct futhark_context *futhark_context_new(struct futhark_context_config *cfg) 
     }
     futhark_context *ctx = new futhark_context();
     ctx->device = dev; ctx->logging = cfg ? cfg->logging : 0;
-    ctx->timer.on = cfg && cfg->profiling;
+    ctx->timer.on = (cfg && cfg->profiling) ? 1 : 0;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return nullptr; }
     cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1); cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
     { const char *pe = getenv("LYS_PIPELINE"); if (pe) { int v = atoi(pe); if (v >= 1 && v <= 16) ctx->pipeline = v; } }
+    if (cudaHostAlloc((void **)&ctx->h_init, sizeof(*ctx->h_init), cudaHostAllocDefault) != cudaSuccess) { cudaStreamDestroy(ctx->stream); delete ctx; return nullptr; }
+    { size_t fr = 0, tot = 0; if (cudaMemGetInfo(&fr, &tot) == cudaSuccess) ctx->pool_cap = std::max<size_t>((size_t)1 << 30, tot / 8); else cudaGetLastError(); }
     if (cudaHostAlloc((void **)&ctx->h_counts, sizeof(int) * (LYS_MAX_PATH_LEN + 1), cudaHostAllocDefault) == cudaSuccess) {
         for (int k = 0; k <= LYS_MAX_PATH_LEN; k++) ctx->h_counts[k] = -1;          /* no estimate yet */
     } else { ctx->h_counts = nullptr; cudaGetLastError(); }
@@ -439,8 +464,9 @@ void futhark_context_free(struct futhark_context *ctx) {
     if (w.crown_pairs) cudaFree(w.crown_pairs);
     raw_free(ctx->pts_pos); raw_free(ctx->pts_dist);
     if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
+    if (ctx->h_init) cudaFreeHost(ctx->h_init);
     for (auto &kv : ctx->pool) cudaFree(kv.second);
-    ctx->pool.clear();
+    ctx->pool.clear(); ctx->pooled_bytes = 0;
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
@@ -449,15 +475,14 @@ void futhark_context_free(struct futhark_context *ctx) {
 }
 int futhark_context_sync(struct futhark_context *ctx) {
     if (!ctx) return 1;
+    cudaSetDevice(ctx->device);
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     return 0;
 }
 int futhark_context_clear_caches(struct futhark_context *ctx) {
     if (!ctx) return 1;
     cudaSetDevice(ctx->device);
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
-    for (auto &kv : ctx->pool) cudaFree(kv.second);
-    ctx->pool.clear();
+    pool_release_all(ctx);
     return 0;
 }
 /* the rest of the generated cuda-backend surface (tracer.h): no run-time compilation, no tunable sizes */
@@ -475,14 +500,13 @@ int futhark_context_config_set_size(struct futhark_context_config *cfg, const ch
 int futhark_get_num_sizes(void) { return 0; }
 const char *futhark_get_size_name(int i) { (void)i; return nullptr; }
 const char *futhark_get_size_class(int i) { (void)i; return nullptr; }
-void futhark_context_pause_profiling(struct futhark_context *ctx) { if (ctx) { ctx->timer.resolve(ctx->stream); ctx->timer.on = false; } }
-void futhark_context_unpause_profiling(struct futhark_context *ctx) { if (ctx) ctx->timer.on = true; }
+void futhark_context_pause_profiling(struct futhark_context *ctx) { if (ctx) { ctx->timer.resolve(ctx->stream); ctx->timer.on = 0; } }
+void futhark_context_unpause_profiling(struct futhark_context *ctx) { if (ctx) ctx->timer.on = 1; }
 char *futhark_context_report(struct futhark_context *ctx) {
     if (!ctx) return nullptr;
     ctx->timer.resolve(ctx->stream);
     static const char *const cls[LYS_PROFILE_CLASSES] = {"generate", "trace", "shade", "tail", "accumulate"};
-    size_t pooled = 0;
-    for (auto &kv : ctx->pool) pooled += kv.first;
+    const size_t pooled = ctx->pooled_bytes;
     std::string r = "libtracer (sm_100a): " + std::to_string((unsigned long long)ctx->launches) + " kernel launches, " +
                     std::to_string((unsigned long long)pooled) + " bytes of device memory pooled for reuse\n";
     char line[160];
@@ -495,7 +519,7 @@ char *futhark_context_report(struct futhark_context *ctx) {
     return strdup(r.c_str());
 }
 char *futhark_context_get_error(struct futhark_context *ctx) {
-    if (!ctx) return nullptr;
+    if (!ctx || ctx->error.empty()) return nullptr;        /* NULL when there is nothing to report, as the generated code does */
     char *r = strdup(ctx->error.c_str());
     ctx->error.clear();
     return r;
@@ -546,45 +570,49 @@ int futhark_entry_init(struct futhark_context *ctx, struct futhark_opaque_state 
     if (n >= (1ll << 30)) { set_error(ctx, "init: too many triangles"); return 1; }
     if (m < 1) { set_error(ctx, "init: at least 1 material is required"); return 1; }
 
-    /* host copies of the small / index arrays: material table, material indices, camera origin */
-    std::vector<uint32_t> h_tm((size_t)n); std::vector<float> h_mats((size_t)m * 28); float org[3];
-    CU(ctx, cudaMemcpyAsync(h_tm.data(), tri_mats->mem->p, sizeof(uint32_t) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(ctx, cudaMemcpyAsync(h_mats.data(), mat_data->mem->p, sizeof(float) * (size_t)m * 28, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(ctx, cudaMemcpyAsync(org, cam_origin->mem->p, sizeof(org), cudaMemcpyDeviceToHost, ctx->stream));
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
-    std::vector<char> emissive((size_t)m, 0);
-    for (int64_t i = 0; i < m; i++)                                          /* nonzero_spectrum scene.fut:59-60 */
-        for (int k = 0; k < 6; k++) if (h_mats[i * 28 + 16 + 2 * k] >= 0 && h_mats[i * 28 + 16 + 2 * k + 1] > 0) emissive[i] = 1;
-    std::vector<int> light_src;
-    for (int64_t i = 0; i < n; i++) {
-        if (h_tm[i] >= (uint64_t)m) { set_error(ctx, "init: material index out of range"); return 1; }
-        if (emissive[h_tm[i]]) light_src.push_back((int)i);
-    }
-
     auto holder = std::make_shared<SceneHolder>();
     SceneDev &sc = holder->d;
-    sc.n_tris = n; sc.n_mats = m; sc.n_lights = (int64_t)light_src.size();
+    sc.n_tris = n; sc.n_mats = m; sc.n_lights = 0;
+    holder->refit_mode = ctx->refit_mode;
     size_t c = (size_t)n;
     SceneHolder &H = *holder;
+    /* lights are found on the device (scene.fut:58-66); their number is only known after the read-back below, so the
+     * arrays get a first capacity that covers every bundled scene and are regrown in the rare case it does not */
+    int light_cap = (int)std::min<int64_t>(n, 4096);
+    const size_t light_chunks = (c + 1023) / 1024;
+    unsigned char *mat_flag = nullptr; int *light_chunk = nullptr, *light_info = nullptr;
     if (!H.take(ctx, sc.tris, 9 * c) || !H.take(ctx, sc.tri_mats, c) || !H.take(ctx, sc.mats, (size_t)m * 28) ||
         !H.take(ctx, sc.leaf_tri, 4 * c) || !H.take(ctx, sc.leaf_box, 2 * c) || !H.take(ctx, sc.nodes, 2 * c) ||
         !H.take(ctx, sc.node_box, 2 * c) || !H.take(ctx, sc.left, c) || !H.take(ctx, sc.right, c) || !H.take(ctx, sc.parent, c) ||
         !H.take(ctx, sc.height, c) || !H.take(ctx, sc.morton, c) || !H.take(ctx, sc.sorted_idx, c) || !H.take(ctx, sc.bounds, 8) ||
-        !H.take(ctx, sc.lights, light_src.size()) || !H.take(ctx, sc.light_src, light_src.size())) return 1;
+        !H.take(ctx, sc.lights, (size_t)light_cap) || !H.take(ctx, sc.light_src, (size_t)light_cap) ||
+        !H.take(ctx, mat_flag, (size_t)m) || !H.take(ctx, light_chunk, light_chunks) || !H.take(ctx, light_info, 4)) return 1;
     if (n - 1 <= LYS_OCT_MAX_NODES && n >= 2 && !H.take(ctx, sc.nodes_oct, 16 * c)) return 1;
     CU(ctx, cudaMemcpyAsync(sc.tris, tri_geoms->mem->p, sizeof(float) * 9 * c, cudaMemcpyDeviceToDevice, ctx->stream));
     CU(ctx, cudaMemcpyAsync(sc.tri_mats, tri_mats->mem->p, sizeof(uint32_t) * c, cudaMemcpyDeviceToDevice, ctx->stream));
     CU(ctx, cudaMemcpyAsync(sc.mats, mat_data->mem->p, sizeof(float) * (size_t)m * 28, cudaMemcpyDeviceToDevice, ctx->stream));
-    if (!light_src.empty()) {
-        CU(ctx, cudaMemcpyAsync(sc.light_src, light_src.data(), sizeof(int) * light_src.size(), cudaMemcpyHostToDevice, ctx->stream));
-        CU(ctx, build_lights(sc, sc.light_src, (int)light_src.size(), ctx->stream, &ctx->launches));
-    }
+    CU(ctx, build_lights(sc, mat_flag, light_chunk, light_info, light_cap, ctx->stream, &ctx->launches));
     if (!ensure_scratch(ctx, n)) return 1;
     CU(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-    if (!build_scene_bvh(ctx, sc, true)) return 1;
+    CU(ctx, build_lbvh(sc, ctx->scratch, ctx->refit_mode, ctx->stream, &ctx->launches));
     CU(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    /* the one read-back of init: number of lights + index check, camera origin, crown overflow flag of the refit */
+    futhark_context::InitReadback *rb = ctx->h_init;
+    rb->crown_overflow = 0;
+    CU(ctx, cudaMemcpyAsync(rb->lights, light_info, sizeof(rb->lights), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(rb->origin, cam_origin->mem->p, sizeof(rb->origin), cudaMemcpyDeviceToHost, ctx->stream));
+    if (ctx->refit_mode == 0) CU(ctx, cudaMemcpyAsync(&rb->crown_overflow, ctx->scratch.crown_cnt + 63, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     cudaEventElapsedTime(&sc.build_ms, ctx->ev0, ctx->ev1);
+    if (rb->lights[1]) { set_error(ctx, "init: material index out of range"); return 1; }
+    sc.n_lights = rb->lights[0];
+    if (sc.n_lights > light_cap) {                     /* more lights than the first capacity: larger arrays, scatter + records again */
+        light_cap = (int)sc.n_lights;
+        if (!H.take(ctx, sc.lights, (size_t)light_cap) || !H.take(ctx, sc.light_src, (size_t)light_cap)) return 1;
+        CU(ctx, rebuild_lights(sc, mat_flag, light_chunk, light_info, light_cap, ctx->stream, &ctx->launches));
+    }
+    if (rb->crown_overflow) CU(ctx, build_lbvh(sc, ctx->scratch, 2, ctx->stream, &ctx->launches));      /* pair buffer overflowed: literal sweeps (always exact) */
+    const float org[3] = {rb->origin[0], rb->origin[1], rb->origin[2]};
 
     futhark_opaque_state *s = new futhark_opaque_state();
     s->dim_w = w; s->dim_h = h; s->subsampling = 1;
@@ -600,7 +628,6 @@ int futhark_entry_init(struct futhark_context *ctx, struct futhark_opaque_state 
     s->cam_conf_id = cam_conf_id;
     s->cam.pitch = cam_pitch; s->cam.yaw = cam_yaw; s->cam.origin = v3(org[0], org[1], org[2]);
     s->scene = holder;
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
     *out0 = s;
     return 0;
 }
@@ -687,41 +714,46 @@ int futhark_entry_render(struct futhark_context *ctx, struct futhark_i32_2d **ou
     return 0;
 }
 
-int lys_sample_n_frames_stats(struct futhark_context *ctx, struct futhark_f32_3d **out0, const struct futhark_opaque_state *s, uint32_t n,
-                              lys_pass_stats *stats) {                              /* lib.fut:67-74 */
+/* sample_n_frames (lib.fut:67-74); out_scale is applied by the last accumulate (1 = the reference's result) */
+static int sample_n_frames_impl(struct futhark_context *ctx, struct futhark_f32_3d **out0, const struct futhark_opaque_state *s, uint32_t n,
+                                float out_scale, lys_pass_stats *stats) {
     if (!ctx) return 1;
     if (!out0 || !s) { set_error(ctx, "sample_n_frames: null argument"); return 1; }
     cudaSetDevice(ctx->device);
     uint32_t gw, gh; grid_dims(s, gw, gh);
     int64_t shape[3] = {(int64_t)gh, (int64_t)gw, 3};
-    futhark_f32_3d *a = new_array<futhark_f32_3d, float>(ctx, nullptr, shape, 3, cudaMemcpyDeviceToDevice);
+    std::unique_ptr<futhark_f32_3d> a(new_array<futhark_f32_3d, float>(ctx, nullptr, shape, 3, cudaMemcpyDeviceToDevice));      /* freed on every early return */
     if (!a) return 1;
     uint64_t l0 = ctx->launches;
     if (ctx->world > 1) CU(ctx, cudaMemsetAsync(a->ptr(), 0, sizeof(float) * 3 * (size_t)gw * gh, ctx->stream));
     const uint32_t passes = n < 1 ? 1 : n;                               /* the first sample_frame always runs (lib.fut:68) */
-    const int S = ctx->timer.on ? 1 : (int)std::min<uint32_t>((uint32_t)ctx->pipeline, passes);
-    if (!ensure_slots(ctx, S, (int64_t)gw * gh)) { delete a; return 1; }
+    const int S = ctx->timer.on == 1 ? 1 : (int)std::min<uint32_t>((uint32_t)ctx->pipeline, passes);
+    if (!ensure_slots(ctx, S, (int64_t)gw * gh)) return 1;
     FrameParams fp;
-    if (!make_frame_params(ctx, s, s->rng, 1.0f, fp)) { delete a; return 1; }      /* uploads the flash lights once */
+    if (!make_frame_params(ctx, s, s->rng, 1.0f, fp)) return 1;          /* uploads the flash lights once */
     for (int i = 0; i < S; i++) CU(ctx, cudaMemsetAsync(ctx->slots[i].bufs.stats, 0, 4 * sizeof(unsigned long long), ctx->stream));
     CU(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     CU(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
     for (int i = 0; i < S; i++) CU(ctx, cudaStreamWaitEvent(ctx->slots[i].stream, ctx->ev_fork, 0));
     uint32_t rng = s->rng;
     cudaEvent_t prev = nullptr;
-    for (uint32_t k = 0; k < passes; k++) {
+    int rc = 0;
+    for (uint32_t k = 0; k < passes && !rc; k++) {
         futhark_context::PassSlot &sl = ctx->slots[k % S];
         fp.frame_rng = rng;
-        CU(ctx, run_sample_pass(s->scene->d, fp, sl.bufs, sl.stream, &ctx->launches, &ctx->timer, ctx->h_counts));
-        if (prev) CU(ctx, cudaStreamWaitEvent(sl.stream, prev, 0));             /* running average is order dependent */
-        CU(ctx, run_accumulate(fp, sl.bufs, a->ptr(), a->ptr(), k > 0 ? 1 : 0, (float)k, sl.stream, &ctx->launches, &ctx->timer));
-        CU(ctx, cudaEventRecord(sl.done, sl.stream));
+        if (!cu_ok(ctx, run_sample_pass(s->scene->d, fp, sl.bufs, sl.stream, &ctx->launches, &ctx->timer, ctx->h_counts), "sample pass")) { rc = 1; break; }
+        if (prev && !cu_ok(ctx, cudaStreamWaitEvent(sl.stream, prev, 0), "cudaStreamWaitEvent")) { rc = 1; break; }      /* running average is order dependent */
+        if (!cu_ok(ctx, run_accumulate(fp, sl.bufs, a->ptr(), a->ptr(), k > 0 ? 1 : 0, (float)k, sl.stream, &ctx->launches, &ctx->timer,
+                                       k + 1 == passes ? out_scale : 1.0f), "accumulate") ||
+            !cu_ok(ctx, cudaEventRecord(sl.done, sl.stream), "cudaEventRecord")) { rc = 1; break; }
         prev = sl.done;
         rng = h_advance_rng(rng);
     }
-    CU(ctx, cudaStreamWaitEvent(ctx->stream, prev, 0));
+    /* join every slot stream back into the context's stream, also after an error: nothing may stay forked */
+    for (int i = 0; i < S; i++) if (cudaEventRecord(ctx->slots[i].done, ctx->slots[i].stream) == cudaSuccess) cudaStreamWaitEvent(ctx->stream, ctx->slots[i].done, 0);
+    if (rc) { cudaStreamSynchronize(ctx->stream); return 1; }             /* `a` goes back to the pool only after its writers have drained */
     CU(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
-    if (ctx->timer.on) ctx->timer.resolve(ctx->stream);
+    if (ctx->timer.on == 1 || ctx->timer.used > 3000) ctx->timer.resolve(ctx->stream);
     if (stats) {
         unsigned long long hs[4] = {0, 0, 0, 0}, one[4];
         for (int i = 0; i < S; i++) {
@@ -733,11 +765,19 @@ int lys_sample_n_frames_stats(struct futhark_context *ctx, struct futhark_f32_3d
         stats->closest_rays = 0; stats->launches = ctx->launches - l0;
         cudaEventElapsedTime(&stats->device_ms, ctx->ev0, ctx->ev1);
     }
-    *out0 = a;
+    *out0 = a.release();
     return 0;
 }
+int lys_sample_n_frames_stats(struct futhark_context *ctx, struct futhark_f32_3d **out0, const struct futhark_opaque_state *s, uint32_t n,
+                              lys_pass_stats *stats) {
+    return sample_n_frames_impl(ctx, out0, s, n, 1.0f, stats);
+}
+int lys_sample_n_frames_weighted(struct futhark_context *ctx, struct futhark_f32_3d **out0, const struct futhark_opaque_state *s, uint32_t n,
+                                 float weight, lys_pass_stats *stats) {
+    return sample_n_frames_impl(ctx, out0, s, n, weight, stats);
+}
 int futhark_entry_sample_n_frames(struct futhark_context *ctx, struct futhark_f32_3d **out0, const struct futhark_opaque_state *s, const uint32_t n) {
-    return lys_sample_n_frames_stats(ctx, out0, s, n, nullptr);
+    return sample_n_frames_impl(ctx, out0, s, n, 1.0f, nullptr);
 }
 
 int futhark_entry_sample_points_n(struct futhark_context *ctx, struct futhark_opaque_state **out0, struct futhark_f32_3d **out1,
@@ -748,11 +788,11 @@ int futhark_entry_sample_points_n(struct futhark_context *ctx, struct futhark_op
     uint32_t gw, gh; grid_dims(s, gw, gh);
     int64_t np = (int64_t)gw * gh;
     int64_t shape[3] = {(int64_t)gh, (int64_t)gw, 4};
-    futhark_f32_3d *a = new_array<futhark_f32_3d, float>(ctx, nullptr, shape, 3, cudaMemcpyDeviceToDevice);
+    std::unique_ptr<futhark_f32_3d> a(new_array<futhark_f32_3d, float>(ctx, nullptr, shape, 3, cudaMemcpyDeviceToDevice));      /* freed on every early return */
     if (!a) return 1;
     if (ctx->pts_cap < np) {
         raw_free(ctx->pts_pos); raw_free(ctx->pts_dist); ctx->pts_cap = 0;
-        if (!raw_alloc(ctx, ctx->pts_pos, (size_t)np) || !raw_alloc(ctx, ctx->pts_dist, (size_t)np)) { delete a; return 1; }
+        if (!raw_alloc(ctx, ctx->pts_pos, (size_t)np) || !raw_alloc(ctx, ctx->pts_dist, (size_t)np)) return 1;
         ctx->pts_cap = np;
     }
     if (ctx->world > 1) { CU(ctx, cudaMemsetAsync(ctx->pts_pos, 0, sizeof(float4) * (size_t)np, ctx->stream)); }
@@ -760,28 +800,30 @@ int futhark_entry_sample_points_n(struct futhark_context *ctx, struct futhark_op
     uint32_t rng = s->rng;
     uint32_t passes = spp < 1 ? 1 : spp;                                           /* the first pass always runs (lib.fut:52) */
     const int S = (int)std::min<uint32_t>((uint32_t)ctx->pipeline, passes);
-    if (!ensure_slots(ctx, S, np)) { delete a; return 1; }
+    if (!ensure_slots(ctx, S, np)) return 1;
     FrameParams fp;
-    if (!make_frame_params(ctx, s, rng, factor, fp)) { delete a; return 1; }
+    if (!make_frame_params(ctx, s, rng, factor, fp)) return 1;
     fp.render_mode = 1;
     CU(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
     for (int i = 0; i < S; i++) CU(ctx, cudaStreamWaitEvent(ctx->slots[i].stream, ctx->ev_fork, 0));
     cudaEvent_t prev = nullptr;
+    int rc = 0;
     for (uint32_t k = 0; k < passes; k++) {
         futhark_context::PassSlot &sl = ctx->slots[k % S];
         fp.frame_rng = rng;
-        if (!cu_ok(ctx, run_sample_pass(s->scene->d, fp, sl.bufs, sl.stream, &ctx->launches, nullptr, ctx->h_counts), "sample pass")) { delete a; return 1; }
-        if (prev) CU(ctx, cudaStreamWaitEvent(sl.stream, prev, 0));                /* merge keeps the earlier point on ties (lib.fut:51) */
-        if (!cu_ok(ctx, run_points_merge(fp, sl.bufs, ctx->pts_pos, ctx->pts_dist, k == 0 ? 1 : 0, sl.stream, &ctx->launches), "points merge")) { delete a; return 1; }
-        CU(ctx, cudaEventRecord(sl.done, sl.stream));
+        if (!cu_ok(ctx, run_sample_pass(s->scene->d, fp, sl.bufs, sl.stream, &ctx->launches, nullptr, ctx->h_counts), "sample pass") ||
+            (prev && !cu_ok(ctx, cudaStreamWaitEvent(sl.stream, prev, 0), "cudaStreamWaitEvent")) ||                   /* merge keeps the earlier point on ties (lib.fut:51) */
+            !cu_ok(ctx, run_points_merge(fp, sl.bufs, ctx->pts_pos, ctx->pts_dist, k == 0 ? 1 : 0, sl.stream, &ctx->launches), "points merge") ||
+            !cu_ok(ctx, cudaEventRecord(sl.done, sl.stream), "cudaEventRecord")) { rc = 1; break; }
         prev = sl.done;
         rng = h_advance_rng(rng);
     }
-    CU(ctx, cudaStreamWaitEvent(ctx->stream, prev, 0));
-    if (!cu_ok(ctx, run_points_export(fp, ctx->pts_pos, a->ptr(), ctx->stream, &ctx->launches), "points export")) { delete a; return 1; }
+    for (int i = 0; i < S; i++) if (cudaEventRecord(ctx->slots[i].done, ctx->slots[i].stream) == cudaSuccess) cudaStreamWaitEvent(ctx->stream, ctx->slots[i].done, 0);   /* nothing stays forked */
+    if (rc) { cudaStreamSynchronize(ctx->stream); return 1; }
+    if (!cu_ok(ctx, run_points_export(fp, ctx->pts_pos, a->ptr(), ctx->stream, &ctx->launches), "points export")) return 1;
     futhark_opaque_state *r = clone_state(s);
     r->rng = rng;
-    *out0 = r; *out1 = a;
+    *out0 = r; *out1 = a.release();
     return 0;
 }
 
@@ -795,7 +837,7 @@ int lys_context_set_partition(struct futhark_context *ctx, int rank, int world_s
     if (!ctx || world_size < 1 || rank < 0 || rank >= world_size) { if (ctx) set_error(ctx, "bad partition"); return 1; }
     ctx->rank = rank; ctx->world = world_size; return 0;
 }
-int lys_context_set_profiling(struct futhark_context *ctx, int on) { if (!ctx) return 1; ctx->timer.resolve(ctx->stream); ctx->timer.on = on != 0; return 0; }
+int lys_context_set_profiling(struct futhark_context *ctx, int on) { if (!ctx) return 1; ctx->timer.resolve(ctx->stream); ctx->timer.on = (on == 2) ? 2 : (on != 0); return 0; }
 int lys_context_profile_get(struct futhark_context *ctx, float *ms, uint64_t *launches, int reset) {
     if (!ctx) return 1;
     ctx->timer.resolve(ctx->stream);
@@ -848,6 +890,7 @@ int lys_state_info_get(struct futhark_context *ctx, const struct futhark_opaque_
 }
 int lys_state_image(struct futhark_context *ctx, const struct futhark_opaque_state *s, float *out) {
     if (!ctx || !s || !out) return 1;
+    cudaSetDevice(ctx->device);
     CU(ctx, cudaMemcpyAsync(out, s->img->p, sizeof(float) * 3 * (size_t)s->img_h * s->img_w, cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     return 0;
@@ -856,6 +899,7 @@ int lys_state_bvh_get(struct futhark_context *ctx, const struct futhark_opaque_s
                       int32_t *sorted_src_index, int32_t *left, int32_t *right, int32_t *parent, float *node_aabb, float *leaf_aabb,
                       int32_t *node_height) {
     if (!ctx || !s) return 1;
+    cudaSetDevice(ctx->device);
     const SceneDev &d = s->scene->d;
     size_t n = (size_t)d.n_tris, nn = n - 1;
     auto get = [&](void *dst, const void *src, size_t bytes) -> bool {
@@ -874,6 +918,7 @@ int lys_state_bvh_get(struct futhark_context *ctx, const struct futhark_opaque_s
 }
 int lys_state_light_indices(struct futhark_context *ctx, const struct futhark_opaque_state *s, int32_t *src_index) {
     if (!ctx || !s || !src_index) return 1;
+    cudaSetDevice(ctx->device);
     const SceneDev &d = s->scene->d;
     if (d.n_lights > 0) { CU(ctx, cudaMemcpyAsync(src_index, d.light_src, sizeof(int) * (size_t)d.n_lights, cudaMemcpyDeviceToHost, ctx->stream)); CU(ctx, cudaStreamSynchronize(ctx->stream)); }
     return 0;
@@ -882,14 +927,21 @@ int lys_state_bvh_rebuild_timed(struct futhark_context *ctx, const struct futhar
     if (!ctx || !s || reps < 1) return 1;
     cudaSetDevice(ctx->device);
     SceneDev &d = s->scene->d;
+    const int mode = s->scene->refit_mode;          /* the mode the scene was built with: a timing helper must not change results */
     if (!ensure_scratch(ctx, d.n_tris)) return 1;
     float total = 0.0f;
     for (int r = 0; r < reps; r++) {
         CU(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-        if (!build_scene_bvh(ctx, d, false)) return 1;
+        CU(ctx, build_lbvh(d, ctx->scratch, mode, ctx->stream, &ctx->launches));
         CU(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
         CU(ctx, cudaStreamSynchronize(ctx->stream));
         float t = 0.0f; cudaEventElapsedTime(&t, ctx->ev0, ctx->ev1); total += t;
+    }
+    if (mode == 0) {                                /* outside the timed region: same overflow fallback as init, so the state keeps exact boxes */
+        int ovf = 0;
+        CU(ctx, cudaMemcpyAsync(&ovf, ctx->scratch.crown_cnt + 63, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        if (ovf) { CU(ctx, build_lbvh(d, ctx->scratch, 2, ctx->stream, &ctx->launches)); CU(ctx, cudaStreamSynchronize(ctx->stream)); }
     }
     if (ms) *ms = total / (float)reps;
     return 0;

@@ -568,16 +568,30 @@ __global__ void k_pack_nodes(const float4 *__restrict__ A, const int *__restrict
 /* ------------------------------------------------------------------ host driver */
 static inline int cdiv(long long a, int b) { return (int)((a + b - 1) / b); }
 
+/* per-device launch facts (SM count, one-time function attributes) */
+struct BuildDevice { int sms = 0; bool fold_attr = false; };
+static BuildDevice &build_device() {
+    static BuildDevice d[64];
+    int dev = 0; cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (!d[dev].sms) { int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); d[dev].sms = sms > 0 ? sms : 148; }
+    return d[dev];
+}
+
 cudaError_t build_lbvh(SceneDev &sc, BuildScratch &ws, int refit_mode, cudaStream_t stream, uint64_t *launches) {
+    BuildDevice &dev = build_device();
     const int n = (int)sc.n_tris;
     const int n_nodes = n - 1;
     const int T = 256;
     uint64_t nl = 0;
     k_tri_boxes<<<cdiv(n, BOX_CHUNK), BOX_CHUNK, 0, stream>>>(sc.tris, n, ws.box_c, ws.box_h, ws.chunk_lo, ws.chunk_hi); nl++;
     {
-        static bool attr_set = false;
         const int max_chunk_sm = 24576;                                    /* 24576 x 8 B = 192 KB of dynamic shared memory (6.3 M triangles) */
-        if (!attr_set) { cudaFuncSetAttribute(k_bounds_fold, cudaFuncAttributeMaxDynamicSharedMemorySize, max_chunk_sm * 8); attr_set = true; }
+        if (!dev.fold_attr) {                                              /* a function attribute is per device: a host may hold contexts on several */
+            cudaError_t e = cudaFuncSetAttribute(k_bounds_fold, cudaFuncAttributeMaxDynamicSharedMemorySize, max_chunk_sm * 8);
+            if (e != cudaSuccess) return e;
+            dev.fold_attr = true;
+        }
         const int n_chunk_sm = min(cdiv(n, BOX_CHUNK), max_chunk_sm);
         k_bounds_fold<<<3, FOLD_THREADS, (size_t)n_chunk_sm * 8, stream>>>(ws.box_c, ws.box_h, ws.chunk_lo, ws.chunk_hi, n, n_chunk_sm, sc.bounds); nl++;
     }
@@ -586,7 +600,7 @@ cudaError_t build_lbvh(SceneDev &sc, BuildScratch &ws, int refit_mode, cudaStrea
     const int tiles = cdiv(n, RS_TILE);
     cudaMemsetAsync(ws.rs_hist, 0, 4 * RS_RADIX * sizeof(uint32_t), stream);
     cudaMemsetAsync(ws.rs_status, 0, (size_t)4 * tiles * RS_RADIX * sizeof(uint32_t) + 4 * sizeof(uint32_t), stream);
-    k_rs_hist<<<min(cdiv(n, RS_THREADS * 8), 148 * 8), RS_THREADS, 0, stream>>>(ws.keys[0], n, ws.rs_hist); nl++;
+    k_rs_hist<<<min(cdiv(n, RS_THREADS * 8), dev.sms * 8), RS_THREADS, 0, stream>>>(ws.keys[0], n, ws.rs_hist); nl++;
     k_rs_scan<<<4, RS_RADIX, 0, stream>>>(ws.rs_hist); nl++;
     int cur = 0;
     for (int p = 0; p < 4; p++) {
@@ -615,7 +629,7 @@ cudaError_t build_lbvh(SceneDev &sc, BuildScratch &ws, int refit_mode, cudaStrea
         cudaMemsetAsync(ws.crown_cnt, 0, 64 * sizeof(int), stream);
         k_crown_find<<<cdiv(n_nodes, T), T, 0, stream>>>(ws.F, sc.height, n_nodes, depth, sc.node_box, (CrownPair *)ws.crown_pairs, ws.crown_cnt, ws.crown_cap, ws.crown_cnt + 63); nl++;
         /* expand levels 0 .. depth-2 (level lv creates level lv+1); eval levels depth-1 .. 0 */
-        const int G = 148 * 4;
+        const int G = dev.sms * 4;
         const int n_top = max(0, (depth - 1) - CROWN_TAIL_LEVELS);            /* expand levels handled by the single CTA */
         if (n_top > 0) { k_crown_top_expand<<<1, 1024, 0, stream>>>(sc.left, sc.right, sc.height, (CrownPair *)ws.crown_pairs, ws.crown_cnt, n_top, depth, ws.crown_cap, ws.crown_cnt + 63); nl++; }
         for (int lv = n_top; lv < depth - 1; lv++) { k_crown_expand<<<G, T, 0, stream>>>(sc.left, sc.right, sc.height, (CrownPair *)ws.crown_pairs, ws.crown_cnt, lv, depth, ws.crown_cap, ws.crown_cnt + 63); nl++; }
@@ -624,6 +638,115 @@ cudaError_t build_lbvh(SceneDev &sc, BuildScratch &ws, int refit_mode, cudaStrea
     }
     k_pack_nodes<<<cdiv(n_nodes, T), T, 0, stream>>>(sc.node_box, sc.left, sc.right, n_nodes, sc.nodes, sc.nodes_oct); nl++;
     if (launches) *launches += nl;
+    return cudaGetLastError();
+}
+
+/* ------------------------------------------------------------------ lights (scene.fut:58-66), on the device
+ * get_lights keeps the triangles whose material has a non-zero emission spectrum (a knot with wavelength >= 0 and value > 0,
+ * scene.fut:59-60), IN INPUT ORDER: direct.fut:116-119 picks light `rand % n_lights` by position.  Four small launches
+ * (flag per material, count per 1024-triangle chunk + index range check, scan of the chunk counts by one CTA, ordered
+ * scatter) and the record kernel; the host learns n_lights with the single read-back that ends futhark_entry_init. */
+#define LIGHT_CHUNK 1024
+__global__ void k_mat_emissive(const float *__restrict__ mats, int m, unsigned char *__restrict__ flag) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const float *e = mats + 28ll * i + 16;
+    bool on = false;
+#pragma unroll
+    for (int k = 0; k < 6; k++) if (e[2 * k] >= 0.0f && e[2 * k + 1] > 0.0f) on = true;
+    flag[i] = on ? 1 : 0;
+}
+__device__ __forceinline__ bool tri_is_light(const uint32_t *__restrict__ tri_mats, const unsigned char *__restrict__ mat_flag, int i, int n, int m, bool &bad) {
+    if (i >= n) return false;
+    const uint32_t k = tri_mats[i];
+    if (k >= (uint32_t)m) { bad = true; return false; }
+    return mat_flag[k] != 0;
+}
+__global__ void __launch_bounds__(LIGHT_CHUNK) k_light_count(const uint32_t *__restrict__ tri_mats, const unsigned char *__restrict__ mat_flag, int n, int m,
+                                                              int *__restrict__ chunk_cnt, int *__restrict__ info) {
+    bool bad = false;
+    const bool on = tri_is_light(tri_mats, mat_flag, blockIdx.x * LIGHT_CHUNK + threadIdx.x, n, m, bad);
+    const int c = __syncthreads_count(on);
+    if (__syncthreads_or(bad) && threadIdx.x == 0) info[1] = 1;             /* material index out of range */
+    if (threadIdx.x == 0) chunk_cnt[blockIdx.x] = c;
+}
+/* exclusive scan of the chunk counts in place (one CTA, 1024 chunks per round); info[0] = number of lights */
+__global__ void __launch_bounds__(1024) k_light_scan(int *__restrict__ chunk_cnt, int n_chunks, int *__restrict__ info) {
+    __shared__ int wsum[32];
+    __shared__ int carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n_chunks; base += 1024) {
+        const int i = base + threadIdx.x;
+        const int v = i < n_chunks ? chunk_cnt[i] : 0;
+        int x = v;
+        for (int o = 1; o < 32; o <<= 1) { int y = __shfl_sync(0xffffffffu, x, max(lane - o, 0)); if (lane >= o) x += y; }
+        if (lane == 31) wsum[warp] = x;
+        __syncthreads();
+        if (warp == 0) { int w = wsum[lane], z = w; for (int o = 1; o < 32; o <<= 1) { int y = __shfl_sync(0xffffffffu, z, max(lane - o, 0)); if (lane >= o) z += y; } wsum[lane] = z - w; }
+        __syncthreads();
+        const int excl = carry + wsum[warp] + x - v;
+        if (i < n_chunks) chunk_cnt[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) info[0] = carry;
+}
+__global__ void __launch_bounds__(LIGHT_CHUNK) k_light_scatter(const uint32_t *__restrict__ tri_mats, const unsigned char *__restrict__ mat_flag, int n, int m,
+                                                                const int *__restrict__ chunk_off, int cap, int *__restrict__ light_src) {
+    __shared__ int wsum[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int i = blockIdx.x * LIGHT_CHUNK + threadIdx.x;
+    bool bad = false;
+    const bool on = tri_is_light(tri_mats, mat_flag, i, n, m, bad);
+    const unsigned mask = __ballot_sync(0xffffffffu, on);
+    if (lane == 0) wsum[warp] = __popc(mask);
+    __syncthreads();
+    if (warp == 0) { int w = wsum[lane], z = w; for (int o = 1; o < 32; o <<= 1) { int y = __shfl_sync(0xffffffffu, z, max(lane - o, 0)); if (lane >= o) z += y; } wsum[lane] = z - w; }
+    __syncthreads();
+    if (on) { const int slot = chunk_off[blockIdx.x] + wsum[warp] + __popc(mask & ((1u << lane) - 1u)); if (slot < cap) light_src[slot] = i; }
+}
+__global__ void k_build_lights(const float *__restrict__ tris, const uint32_t *__restrict__ tri_mats, const float *__restrict__ mats,
+                               const int *__restrict__ src, const int *__restrict__ info, int cap, LightRec *__restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= min(info[0], cap)) return;
+    int s = src[i];
+    const float *t = tris + 9ll * s;
+    V3 a = v3(t[0], t[1], t[2]), bb = v3(t[3], t[4], t[5]), c = v3(t[6], t[7], t[8]);
+    V3 e1 = bb - a, e2 = c - a;
+    V3 nc = cross(e1, e2);
+    float area = norm(nc) / 2.0f;                       /* direct.fut:17-20,37 */
+    V3 n = normalise(nc);                               /* triangle_normal shapes.fut:59-62 */
+    LightRec r;
+    r.a[0] = a.x; r.a[1] = a.y; r.a[2] = a.z; r.area = area;
+    r.e1[0] = e1.x; r.e1[1] = e1.y; r.e1[2] = e1.z; r.inv_area = 1.0f / area;
+    r.e2[0] = e2.x; r.e2[1] = e2.y; r.e2[2] = e2.z; r.theta = 0.0f;
+    r.n[0] = n.x; r.n[1] = n.y; r.n[2] = n.z; r.kind = 0;
+    const float *em = mats + 28ll * tri_mats[s] + 16;
+    for (int k = 0; k < 12; k++) r.emission[k] = em[k];
+    r.src_index = s; r.pad[0] = r.pad[1] = r.pad[2] = 0;
+    out[i] = r;
+}
+cudaError_t build_lights(SceneDev &sc, unsigned char *mat_flag, int *chunk_cnt, int *info, int cap, cudaStream_t stream, uint64_t *launches) {
+    const int n = (int)sc.n_tris, m = (int)sc.n_mats;
+    const int chunks = cdiv(n, LIGHT_CHUNK);
+    cudaMemsetAsync(info, 0, 4 * sizeof(int), stream);
+    k_mat_emissive<<<cdiv(m, 128), 128, 0, stream>>>(sc.mats, m, mat_flag);
+    k_light_count<<<chunks, LIGHT_CHUNK, 0, stream>>>(sc.tri_mats, mat_flag, n, m, chunk_cnt, info);
+    k_light_scan<<<1, 1024, 0, stream>>>(chunk_cnt, chunks, info);
+    k_light_scatter<<<chunks, LIGHT_CHUNK, 0, stream>>>(sc.tri_mats, mat_flag, n, m, chunk_cnt, cap, sc.light_src);
+    k_build_lights<<<cdiv(cap, 128), 128, 0, stream>>>(sc.tris, sc.tri_mats, sc.mats, sc.light_src, info, cap, sc.lights);
+    if (launches) *launches += 5;
+    return cudaGetLastError();
+}
+/* after the host has learnt that there are more lights than `old cap`: scatter + records again into larger arrays */
+cudaError_t rebuild_lights(SceneDev &sc, const unsigned char *mat_flag, const int *chunk_off, const int *info, int cap, cudaStream_t stream, uint64_t *launches) {
+    const int n = (int)sc.n_tris, m = (int)sc.n_mats;
+    k_light_scatter<<<cdiv(n, LIGHT_CHUNK), LIGHT_CHUNK, 0, stream>>>(sc.tri_mats, mat_flag, n, m, chunk_off, cap, sc.light_src);
+    k_build_lights<<<cdiv(cap, 128), 128, 0, stream>>>(sc.tris, sc.tri_mats, sc.mats, sc.light_src, info, cap, sc.lights);
+    if (launches) *launches += 2;
     return cudaGetLastError();
 }
 

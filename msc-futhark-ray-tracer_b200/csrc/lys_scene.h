@@ -57,7 +57,10 @@ struct BuildScratch {
 
 /* refit_mode: 0 reference-exact (truncated Jacobi via crown worklists), 1 converged, 2 reference-exact via literal sweeps */
 cudaError_t build_lbvh(SceneDev &sc, BuildScratch &ws, int refit_mode, cudaStream_t stream, uint64_t *launches);
-/* lights: gathers emissive triangles (indices in input order) into LightRec */
-cudaError_t build_lights(SceneDev &sc, const int *light_src_dev, int n_lights, cudaStream_t stream, uint64_t *launches);
+/* lights (scene.fut:58-66) on the device: emissive triangles in input order -> sc.light_src / sc.lights (capacity `cap`).
+ * info[0] = number of lights found (may exceed cap: then call rebuild_lights with larger arrays), info[1] = 1 if a material
+ * index is out of range.  mat_flag [n_mats] bytes and chunk_cnt [ceil(n / 1024)] ints are scratch that rebuild_lights reuses. */
+cudaError_t build_lights(SceneDev &sc, unsigned char *mat_flag, int *chunk_cnt, int *info, int cap, cudaStream_t stream, uint64_t *launches);
+cudaError_t rebuild_lights(SceneDev &sc, const unsigned char *mat_flag, const int *chunk_off, const int *info, int cap, cudaStream_t stream, uint64_t *launches);
 
 } // namespace lys

@@ -61,9 +61,13 @@ struct PassBuffers {
     float *probe_rad = nullptr, *probe_dist = nullptr;   /* [cap][16] */
 };
 
-/* optional per-launch timing: events are recorded around each launch and resolved by the owner */
+/* optional per-launch timing: events are recorded around each launch and resolved by the owner.
+ * on = 1: per-class sequence (k_generate and k_trace(-1) as two launches, one launch per bounce, one pass at a time) so that
+ *         every ray is in the trace class; on = 2: the PRODUCTION sequence (fused camera-ray launch, fused tail, passes
+ *         pipelined over the slot streams) with events around its launches -- concurrent kernels share the GPU, so the
+ *         per-class sums are used as SHARES of the step, not as exclusive times. */
 struct LaunchTimer {
-    bool on = false;
+    int on = 0;
     std::vector<cudaEvent_t> ev0, ev1; std::vector<int> cls, bnc; size_t used = 0; int cur_bounce = 0;
     float ms[5] = {0, 0, 0, 0, 0}; uint64_t n[5] = {0, 0, 0, 0, 0};
     float detail[2][18] = {};          /* [0] trace, [1] shade; index = bounce + 1 */
@@ -91,8 +95,9 @@ struct LaunchTimer {
 cudaError_t run_sample_pass(const SceneDev &sc, const FrameParams &fp, PassBuffers &bufs, cudaStream_t stream, uint64_t *launches, LaunchTimer *timer = nullptr,
                             int *est_counts = nullptr);
 /* resolve + merge into the image: mode 0 = replace (sample_frame), 1 = running average (sample_frame_accum) */
+/* out_scale != 1: the merged pixel is multiplied by it (the weight of this rank's passes in a pass-split multi-GPU frame) */
 cudaError_t run_accumulate(const FrameParams &fp, const PassBuffers &bufs, const float *img_old, float *img_new,
-                           int merge, float n_frames, cudaStream_t stream, uint64_t *launches, LaunchTimer *timer = nullptr);
+                           int merge, float n_frames, cudaStream_t stream, uint64_t *launches, LaunchTimer *timer = nullptr, float out_scale = 1.0f);
 /* point cloud: resolve one pass into [gh][gw] (pos.xyz, distance, intensity) and merge (lib.fut:41-59) */
 cudaError_t run_points_merge(const FrameParams &fp, const PassBuffers &bufs, float4 *pos_int, float *dist, int first,
                              cudaStream_t stream, uint64_t *launches);

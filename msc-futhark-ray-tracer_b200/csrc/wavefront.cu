@@ -87,7 +87,19 @@ LYS_D bool leaf_test(const RayInv &r, const float4 *__restrict__ leaf_tri, int l
 #ifdef LYS_SMEM_STACK
 static __device__ __noinline__ int *trav_smem_stack() { __shared__ int s[LYS_SMEM_STACK * 128]; return s; }
 #endif
-template <bool ANY, int NB, bool OCT>
+/* PF: the right child pushed on the stack is certain to be popped later (closest hit) or likely to be (any hit); its
+ * address is known now, one dependent L2 / DRAM access before it is needed.  PF = 1 asks for its node sector to be brought
+ * into L1 at push time (prefetch.global.L1, no register, no scoreboard), PF = 2 for its leaf sector too.  Large scenes only:
+ * on cache-resident trees the extra instructions are pure cost. */
+LYS_D void trav_prefetch(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+/* PF = 3 (experiment): the same through the async-copy path -- a 16-byte cp.async.ca into a per-thread shared sink pulls the
+ * 32-byte sector through L1 without a destination register; the sink is never read */
+LYS_D void trav_prefetch_async(const void *p) {
+    __shared__ float4 sink[128];
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(&sink[threadIdx.x & 127]);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(p));
+}
+template <bool ANY, int NB, bool OCT, int PF = 0>
 LYS_D int traverse(const float4 *__restrict__ nodes, const float4 *__restrict__ leaf_tri, int n_nodes, bool active,
                    V3 o, V3 d, float tmax, float &t_hit) {
     RayInv r; r.o = o; r.d = d; r.inv = v3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
@@ -115,7 +127,11 @@ LYS_D int traverse(const float4 *__restrict__ nodes, const float4 *__restrict__ 
                 const float4 *q = reinterpret_cast<const float4 *>(nbase + 32ull * (unsigned)cur);
                 float4 lo = __ldg(q), hi = __ldg(q + 1);
                 if (OCT ? slab_test_oct(r, lo, hi, tmax) : slab_test(r, lo, hi, tmax)) {
-                    TRAV_PUSH(__float_as_int(hi.w));          /* right child waits */
+                    const int rc = __float_as_int(hi.w);
+                    TRAV_PUSH(rc);                            /* right child waits */
+                    if ((PF == 1 || PF == 2) && rc >= 0) trav_prefetch(reinterpret_cast<const void *>(nbase + 32ull * (unsigned)rc));
+                    if (PF == 2 && rc < 0) trav_prefetch(leaf_tri + 4ll * ~rc);
+                    if (PF == 3 && rc >= 0) trav_prefetch_async(reinterpret_cast<const void *>(nbase + 32ull * (unsigned)rc));
                     cur = __float_as_int(lo.w);               /* left child first */
                 } else cur = TRAV_POP();
             }
@@ -126,6 +142,7 @@ LYS_D int traverse(const float4 *__restrict__ nodes, const float4 *__restrict__ 
             cur = (ANY && closest >= 0) ? TRAV_DONE : TRAV_POP();       /* any_hit stops at the first hit (bvh.fut:152) */
         }
     } while (__any_sync(0xffffffffu, cur != TRAV_DONE));
+    if (PF == 3) asm volatile("cp.async.wait_all;" ::: "memory");
     t_hit = tmax;
     return closest;
 }
@@ -666,7 +683,7 @@ __global__ void __launch_bounds__(128) k_trace_refill(SceneDev sc, const __grid_
 #ifndef LYS_TRACE_MINB
 #define LYS_TRACE_MINB 10     /* <= 51 registers: 10 CTAs of 128 threads per SM */
 #endif
-template <int NB, bool OCT>
+template <int NB, bool OCT, int PF>
 __global__ void __launch_bounds__(128, LYS_TRACE_MINB) k_trace(SceneDev sc, const __grid_constant__ FrameParams fp, PassBuffers b, int bounce, int ordered) {
     const int n_ext = (bounce + 1 < fp.path_len) ? b.counts[bounce + 1] : 0;
     const int n_con = (bounce >= 0) ? b.counts[bounce] : 0;
@@ -683,7 +700,7 @@ __global__ void __launch_bounds__(128, LYS_TRACE_MINB) k_trace(SceneDev sc, cons
             float4 ro = make_float4(0.0f, 0.0f, 0.0f, 0.0f), rd = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
             if (is_ext) { ro = b.ray_o[(bounce + 1) & 1][i]; rd = b.ray_d[(bounce + 1) & 1][i]; }
             float t;
-            int h = traverse<false, NB, OCT>(nodes, sc.leaf_tri, n_nodes, is_ext, v3(ro.x, ro.y, ro.z), v3(rd.x, rd.y, rd.z), FLT_MAX, t);
+            int h = traverse<false, NB, OCT, PF>(nodes, sc.leaf_tri, n_nodes, is_ext, v3(ro.x, ro.y, ro.z), v3(rd.x, rd.y, rd.z), FLT_MAX, t);
             if (is_ext) b.hit[i] = h;
             /* processing order of shade(bounce + 1): hits from the front, misses from the back (one atomic per warp and kind) */
             if (ordered) {                     /* not for camera rays (their misses are whole warps already: shade(0) walks the slots in order) */
@@ -709,13 +726,13 @@ __global__ void __launch_bounds__(128, LYS_TRACE_MINB) k_trace(SceneDev sc, cons
             if (__any_sync(0xffffffffu, need1)) {
                 float4 d1 = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
                 if (need1) d1 = b.sh_d1[slot];
-                int h = traverse<true, NB, OCT>(nodes, sc.leaf_tri, n_nodes, need1, o, v3(d1.x, d1.y, d1.z), d1.w, t);
+                int h = traverse<true, NB, OCT, PF>(nodes, sc.leaf_tri, n_nodes, need1, o, v3(d1.x, d1.y, d1.z), d1.w, t);
                 if (need1 && h < 0) L = rc.x;
             }
             if (__any_sync(0xffffffffu, need2)) {
                 float4 d2 = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
                 if (need2) d2 = b.sh_d2[slot];
-                int h = traverse<true, NB, OCT>(nodes, sc.leaf_tri, n_nodes, need2, o, v3(d2.x, d2.y, d2.z), d2.w, t);
+                int h = traverse<true, NB, OCT, PF>(nodes, sc.leaf_tri, n_nodes, need2, o, v3(d2.x, d2.y, d2.z), d2.w, t);
                 if (need2 && h < 0) B = rc.y;
             }
             if (is_con) connect_finish(fp, b, bounce, slot, flags, L, B, rc.z, rc.w, rc.z);
@@ -891,7 +908,7 @@ __global__ void __launch_bounds__(128, LYS_TRACE_MINB) k_trace_sr(SceneDev sc, c
 /* ------------------------------------------------------------------ generate + trace(-1) in one launch
  * The camera ray of a pixel goes straight from the registers into the traversal loop: one launch less per pass and no
  * read-back of the 32-byte ray records just written (k_shade(0) still needs them, so they are written once). */
-template <int NB, bool OCT>
+template <int NB, bool OCT, int PF>
 __global__ void __launch_bounds__(128, LYS_TRACE_MINB) k_generate_trace(SceneDev sc, const __grid_constant__ FrameParams fp, PassBuffers b) {
     const int pid = blockIdx.x * blockDim.x + threadIdx.x;
     if (pid == 0) {
@@ -915,7 +932,7 @@ __global__ void __launch_bounds__(128, LYS_TRACE_MINB) k_generate_trace(SceneDev
         if (b.probe_rad) for (int k = 0; k < LYS_MAX_PATH_LEN; k++) { b.probe_rad[(size_t)pid * 16 + k] = 0.0f; b.probe_dist[(size_t)pid * 16 + k] = LYS_INF; }
     }
     float t;
-    const int h = traverse<false, NB, OCT>(OCT ? sc.nodes_oct : sc.nodes, sc.leaf_tri, (int)sc.n_tris - 1, act, o, d, FLT_MAX, t);
+    const int h = traverse<false, NB, OCT, PF>(OCT ? sc.nodes_oct : sc.nodes, sc.leaf_tri, (int)sc.n_tris - 1, act, o, d, FLT_MAX, t);
     if (act) b.hit[pid] = h;
 }
 
@@ -1039,7 +1056,7 @@ LYS_D V3 resolve_pixel(const FrameParams &fp, const PassBuffers &b, int pid) {  
     return v3(k * (vis.x == 1.0f ? s : z), k * (vis.y == 1.0f ? s : z), k * (vis.z == 1.0f ? s : z));
 }
 __global__ void __launch_bounds__(256) k_accumulate(const __grid_constant__ FrameParams fp, PassBuffers b, const float *__restrict__ img_old,
-                                                    float *__restrict__ img_new, int merge, float n_frames) {
+                                                    float *__restrict__ img_new, int merge, float n_frames, float out_scale) {
     int pid = blockIdx.x * blockDim.x + threadIdx.x;
     if (pid >= fp.n_local) return;
     int col, row; int ix = local_to_pixel(fp, pid, col, row);
@@ -1049,6 +1066,7 @@ __global__ void __launch_bounds__(256) k_accumulate(const __grid_constant__ Fram
         if (fp.render_mode == 1) c = (norm(acc) > 0.0f) ? acc : c;
         else c = ((n_frames - 1.0f) / n_frames) * acc + (1.0f / n_frames) * c;
     }
+    if (out_scale != 1.0f) c = out_scale * c;                         /* pass-split frames: this rank's weight, folded into its last accumulate */
     img_new[3ll * ix] = c.x; img_new[3ll * ix + 1] = c.y; img_new[3ll * ix + 2] = c.z;
 }
 
@@ -1140,7 +1158,7 @@ __global__ void k_material_probe(const float *mat28, float wavelen, V3 wo, V3 wi
 static inline int cdiv(long long a, int b) { return (int)((a + b - 1) / b); }
 
 /* persistent grids: SM count x resident CTAs per SM of each kernel (queried once per device) */
-struct GridSizes { int trace = 0, shade = 0, refill = 0, sl = 0, sb = 0, sc = 0; int sr = 0, sr_keep = 24, sr_cam = 0; int mode = 0, split_bounces = 0, nb = 0, bars = 0, shade_threads = 256, oct = 1, adaptive = 1, sms = 148, tail_max = 8192, tail_items = 128, profile_tail = 0, order = 1, tail_min = 148, fuse_gen = 1, dyn_grids = 0; };
+struct GridSizes { int trace = 0, shade = 0, refill = 0, sl = 0, sb = 0, sc = 0; int sr = 0, sr_keep = 24, sr_cam = 0; int mode = 0, split_bounces = 0, nb = 0, bars = 0, shade_threads = 256, oct = 1, adaptive = 1, sms = 148, tail_max = 8192, tail_items = 128, profile_tail = 0, order = 1, tail_min = 148, fuse_gen = 1, dyn_grids = 0, pf = 0, pf_cam = 0; };
 static GridSizes grid_sizes() {
     static GridSizes g[64];
     int dev = 0; cudaGetDevice(&dev);
@@ -1148,7 +1166,7 @@ static GridSizes grid_sizes() {
     if (!g[dev].trace) {
         int sms = 148, bt = 8, bs = 4;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bt, k_trace<2, true>, 128, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bt, k_trace<2, true, 0>, 128, 0);
         const char *sth = getenv("LYS_SHADE_THREADS"); if (sth && (atoi(sth) == 512 || atoi(sth) == 128)) g[dev].shade_threads = atoi(sth);
         if (g[dev].shade_threads == 256) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bs, k_shade<256>, 256, 0);
         else if (g[dev].shade_threads == 128) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bs, k_shade<128>, 128, 0);
@@ -1174,6 +1192,8 @@ static GridSizes grid_sizes() {
         const char *ad = getenv("LYS_ADAPTIVE_GRIDS"); if (ad) g[dev].adaptive = atoi(ad) ? 1 : 0;
         const char *oc = getenv("LYS_TRACE_OCT"); if (oc) g[dev].oct = atoi(oc) ? 1 : 0;          /* 0: always the select-based box test */
         const char *nb = getenv("LYS_TRACE_NB"); g[dev].nb = nb ? ((atoi(nb) == 1) ? 1 : 2) : 0;      /* box stages per loop iteration; 0 = by scene size */
+        const char *pf = getenv("LYS_TRACE_PF"); if (pf) g[dev].pf = g[dev].pf_cam = max(0, min(3, atoi(pf)));   /* right-child prefetch at push time (NB = 1 variants) */
+        const char *pfc = getenv("LYS_TRACE_PF_CAMERA"); if (pfc) g[dev].pf_cam = max(0, min(3, atoi(pfc)));
         int b1 = 8, b2 = 8, b3 = 8;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, k_shade_light, 128, 0); cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b2, k_shade_bsdf, 128, 0);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b3, k_shade_cont, 128, 0);
@@ -1196,9 +1216,12 @@ static void launch_trace(const GridSizes &gs0, int grid, const SceneDev &sc, con
         else k_trace_sr<2, false><<<grid, 128, 0, stream>>>(sc, fp, bufs, bounce, ordered, gs.sr_keep);
         return;
     }
-    if (sc.nodes_oct && gs.oct) { if (gs.nb == 1) k_trace<1, true><<<grid, 128, 0, stream>>>(sc, fp, bufs, bounce, ordered); else k_trace<2, true><<<grid, 128, 0, stream>>>(sc, fp, bufs, bounce, ordered); }
-    else if (gs.nb == 1) k_trace<1, false><<<grid, 128, 0, stream>>>(sc, fp, bufs, bounce, ordered);
-    else k_trace<2, false><<<grid, 128, 0, stream>>>(sc, fp, bufs, bounce, ordered);
+    const bool oct = sc.nodes_oct && gs.oct;
+#define LYS_LAUNCH_TRACE(NB, OCT, PF) k_trace<NB, OCT, PF><<<grid, 128, 0, stream>>>(sc, fp, bufs, bounce, ordered)
+    if (gs.nb != 1) { if (oct) LYS_LAUNCH_TRACE(2, true, 0); else LYS_LAUNCH_TRACE(2, false, 0); }
+    else if (oct) { if (gs.pf == 3) LYS_LAUNCH_TRACE(1, true, 3); else if (gs.pf == 2) LYS_LAUNCH_TRACE(1, true, 2); else if (gs.pf == 1) LYS_LAUNCH_TRACE(1, true, 1); else LYS_LAUNCH_TRACE(1, true, 0); }
+    else { if (gs.pf == 3) LYS_LAUNCH_TRACE(1, false, 3); else if (gs.pf == 2) LYS_LAUNCH_TRACE(1, false, 2); else if (gs.pf == 1) LYS_LAUNCH_TRACE(1, false, 1); else LYS_LAUNCH_TRACE(1, false, 0); }
+#undef LYS_LAUNCH_TRACE
 }
 cudaError_t run_sample_pass(const SceneDev &sc, const FrameParams &fp, PassBuffers &bufs, cudaStream_t stream, uint64_t *launches, LaunchTimer *timer,
                             int *est_counts) {
@@ -1227,15 +1250,20 @@ cudaError_t run_sample_pass(const SceneDev &sc, const FrameParams &fp, PassBuffe
     };
     /* first bounce whose queue was short enough in the earlier pass: from there on one k_tail launch */
     int b_tail = fp.path_len;
-    if (have_est && gs.tail_max > 0 && !gs.mode && !(tm.on && !gs.profile_tail))      /* per-class timing wants every ray in the trace class */
+    if (have_est && gs.tail_max > 0 && !gs.mode && !(tm.on == 1 && !gs.profile_tail))      /* per-class timing (mode 1) wants every ray in the trace class */
         for (int k = 1; k < fp.path_len; k++) if (est[k] <= gs.tail_max) { b_tail = k; break; }
-    if (gs.fuse_gen && !gs.mode && !gs.sr_cam && !tm.on) {  /* per-class timing keeps the two launches apart */
+    if (gs.fuse_gen && !gs.mode && !gs.sr_cam && tm.on != 1) {  /* per-class timing (mode 1) keeps the two launches apart */
+        tm.cur_bounce = -1;
+        tm.begin(1, stream);
         const int nb = gs.nb ? gs.nb : ((sc.n_tris <= 4096) ? 2 : 1);
         const int g = cdiv(n, 128);
-        if (sc.nodes_oct && gs.oct) { if (nb == 1) k_generate_trace<1, true><<<g, 128, 0, stream>>>(sc, fp, bufs); else k_generate_trace<2, true><<<g, 128, 0, stream>>>(sc, fp, bufs); }
-        else if (nb == 1) k_generate_trace<1, false><<<g, 128, 0, stream>>>(sc, fp, bufs);
-        else k_generate_trace<2, false><<<g, 128, 0, stream>>>(sc, fp, bufs);
-        nl++;
+        const bool oct = sc.nodes_oct && gs.oct;
+#define LYS_LAUNCH_GEN(NB, OCT, PF) k_generate_trace<NB, OCT, PF><<<g, 128, 0, stream>>>(sc, fp, bufs)
+        if (nb != 1) { if (oct) LYS_LAUNCH_GEN(2, true, 0); else LYS_LAUNCH_GEN(2, false, 0); }
+        else if (oct) { if (gs.pf_cam == 3) LYS_LAUNCH_GEN(1, true, 3); else if (gs.pf_cam == 2) LYS_LAUNCH_GEN(1, true, 2); else if (gs.pf_cam == 1) LYS_LAUNCH_GEN(1, true, 1); else LYS_LAUNCH_GEN(1, true, 0); }
+        else { if (gs.pf_cam == 3) LYS_LAUNCH_GEN(1, false, 3); else if (gs.pf_cam == 2) LYS_LAUNCH_GEN(1, false, 2); else if (gs.pf_cam == 1) LYS_LAUNCH_GEN(1, false, 1); else LYS_LAUNCH_GEN(1, false, 0); }
+#undef LYS_LAUNCH_GEN
+        tm.end(stream); nl++;
     } else {
         tm.begin(0, stream); k_generate<<<cdiv(n, 256), 256, 0, stream>>>(fp, bufs); tm.end(stream); nl++;
         tm.cur_bounce = -1;
@@ -1281,10 +1309,10 @@ cudaError_t run_sample_pass(const SceneDev &sc, const FrameParams &fp, PassBuffe
     return cudaGetLastError();
 }
 cudaError_t run_accumulate(const FrameParams &fp, const PassBuffers &bufs, const float *img_old, float *img_new, int merge,
-                           float n_frames, cudaStream_t stream, uint64_t *launches, LaunchTimer *timer) {
+                           float n_frames, cudaStream_t stream, uint64_t *launches, LaunchTimer *timer, float out_scale) {
     if (fp.n_local <= 0) return cudaSuccess;
     if (timer) timer->begin(4, stream);
-    k_accumulate<<<cdiv(fp.n_local, 256), 256, 0, stream>>>(fp, bufs, img_old, img_new, merge, n_frames);
+    k_accumulate<<<cdiv(fp.n_local, 256), 256, 0, stream>>>(fp, bufs, img_old, img_new, merge, n_frames, out_scale);
     if (timer) timer->end(stream);
     if (launches) *launches += 1;
     return cudaGetLastError();
@@ -1333,35 +1361,6 @@ cudaError_t run_eval_math(int fn, const float *in, float *out, int64_t n, cudaSt
 }
 cudaError_t run_material_probe(const float *mat28_dev, float wavelen, V3 wo, V3 wi, V3 n, uint32_t rng, float *out9_dev, cudaStream_t stream) {
     k_material_probe<<<1, 1, 0, stream>>>(mat28_dev, wavelen, wo, wi, n, rng, out9_dev);
-    return cudaGetLastError();
-}
-
-/* ------------------------------------------------------------------ lights (scene.fut:58-66) */
-__global__ void k_build_lights(const float *__restrict__ tris, const uint32_t *__restrict__ tri_mats, const float *__restrict__ mats,
-                               const int *__restrict__ src, int n_lights, LightRec *__restrict__ out) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_lights) return;
-    int s = src[i];
-    const float *t = tris + 9ll * s;
-    V3 a = v3(t[0], t[1], t[2]), bb = v3(t[3], t[4], t[5]), c = v3(t[6], t[7], t[8]);
-    V3 e1 = bb - a, e2 = c - a;
-    V3 nc = cross(e1, e2);
-    float area = norm(nc) / 2.0f;                       /* direct.fut:17-20,37 */
-    V3 n = normalise(nc);                               /* triangle_normal shapes.fut:59-62 */
-    LightRec r;
-    r.a[0] = a.x; r.a[1] = a.y; r.a[2] = a.z; r.area = area;
-    r.e1[0] = e1.x; r.e1[1] = e1.y; r.e1[2] = e1.z; r.inv_area = 1.0f / area;
-    r.e2[0] = e2.x; r.e2[1] = e2.y; r.e2[2] = e2.z; r.theta = 0.0f;
-    r.n[0] = n.x; r.n[1] = n.y; r.n[2] = n.z; r.kind = 0;
-    const float *em = mats + 28ll * tri_mats[s] + 16;
-    for (int k = 0; k < 12; k++) r.emission[k] = em[k];
-    r.src_index = s; r.pad[0] = r.pad[1] = r.pad[2] = 0;
-    out[i] = r;
-}
-cudaError_t build_lights(SceneDev &sc, const int *light_src_dev, int n_lights, cudaStream_t stream, uint64_t *launches) {
-    if (n_lights <= 0) return cudaSuccess;
-    k_build_lights<<<cdiv(n_lights, 128), 128, 0, stream>>>(sc.tris, sc.tri_mats, sc.mats, light_src_dev, n_lights, sc.lights);
-    if (launches) *launches += 1;
     return cudaGetLastError();
 }
 

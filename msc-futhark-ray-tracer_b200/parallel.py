@@ -49,37 +49,56 @@ def averaged_passes(count):
     return max(int(count) - 1, 1)
 
 
-def merge_pass_split(buf, my_count, counts, dst=0):
-    """Combine per-rank images of a pass-split frame: buf (this rank's `sample_n_frames(my_count)` result) is scaled
-    in place by its share of the averaged passes and sum-reduced to `dst`.  `counts` = the pass counts of all ranks."""
+def pass_weight(my_count, counts):
+    """Weight of this rank's `sample_n_frames(my_count)` image in a pass-split frame whose ranks hold `counts` passes."""
     total = sum(averaged_passes(c) for c in counts if c > 0)
-    buf.mul_(averaged_passes(my_count) / total if my_count > 0 else 0.0)
+    return averaged_passes(my_count) / total if my_count > 0 else 0.0
+
+
+def merge_pass_split(buf, my_count, counts, dst=0, weighted=False):
+    """Combine per-rank images of a pass-split frame: buf (this rank's `sample_n_frames(my_count)` result) is scaled by its
+    share of the averaged passes and sum-reduced to `dst`.  `counts` = the pass counts of all ranks.  weighted=True: the
+    library already applied the weight inside its last accumulate kernel (State.sample_n_frames_device(..., weight=w)), so
+    only the reduce is left -- no extra pass over the framebuffer."""
+    if not weighted:
+        buf.mul_(pass_weight(my_count, counts))
     return reduce_framebuffer(buf, dst=dst)
+
+
+def context_stream(ctx, device):
+    """torch view of the stream the context launches on.  The library renders on its own non-blocking stream, which is NOT
+    ordered with torch's current stream: every torch / NCCL operation on a library buffer must be issued on this stream (or
+    after ctx.sync())."""
+    return torch.cuda.ExternalStream(ctx.stream, device=device)
 
 
 def render_frame(ctx, state, total_passes, mode, rank, world, device, stream=None):
     """One frame of `total_passes` sample passes over `world` ranks (mode 'rows' or 'passes'); returns
     (array handle, torch view of the [h][w][3] f32 device image).  After the call the view holds the full image on
     rank 0.  The caller frees the handle with state.free_f32_3d.  For 'rows' the context must have been given
-    ctx.set_partition(rank, world) before the state's passes run."""
-    import torch as _torch
+    ctx.set_partition(rank, world) before the state's passes run.
+    Ordering: the reduce is issued on the context's own stream (stream=None builds the torch view of it), i.e. behind the
+    passes that produce the image; freeing the handle afterwards is safe because the pool reuses blocks on that same stream."""
+    if stream is None:
+        stream = context_stream(ctx, device) if torch.device(device).type == 'cuda' else None
     if mode == 'rows':
         hnd, ptr, shape, _ = state.sample_n_frames_device(total_passes, want_stats=False)
         view = as_torch(ptr, shape, device)
-        with _torch.cuda.stream(stream) if stream is not None else _nullcontext():
+        with torch.cuda.stream(stream) if stream is not None else _nullcontext():
             reduce_framebuffer(view, dst=0)
         return hnd, view
     if mode != 'passes':
         raise ValueError("mode must be 'rows' or 'passes'")
     ranges = pass_ranges(total_passes, world)
     first, count = ranges[rank]
+    counts = [c for _, c in ranges]
     s = state.advance_rng(first) if first else state
-    hnd, ptr, shape, _ = s.sample_n_frames_device(max(count, 1), want_stats=False)
+    hnd, ptr, shape, _ = s.sample_n_frames_device(max(count, 1), want_stats=False, weight=pass_weight(count, counts))
     if s is not state:
         s.free()
     view = as_torch(ptr, shape, device)
-    with _torch.cuda.stream(stream) if stream is not None else _nullcontext():
-        merge_pass_split(view, count, [c for _, c in ranges], dst=0)
+    with torch.cuda.stream(stream) if stream is not None else _nullcontext():
+        merge_pass_split(view, count, counts, dst=0, weighted=True)
     return hnd, view
 
 

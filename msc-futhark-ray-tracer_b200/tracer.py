@@ -11,7 +11,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.environ.get('LYS_LIBTRACER') or os.path.join(_HERE, 'libtracer.so')     # override: development builds only
+_SO = os.path.join(_HERE, 'libtracer.so')     # the one library this binding opens: no override, no fallback
 _LJUS = os.path.join(_HERE, 'libljus.so')
 
 # src/sdl.fut key codes used by lib.fut:120-185
@@ -62,9 +62,6 @@ def _load():
     if not os.path.exists(_SO):
         raise TracerError('libtracer.so is not built (run __graft_entry__.build() or make -C %s); there is no CPU fallback' % _HERE)
     L = C.CDLL(_SO)
-    if hasattr(L, 'lys_emu_stats') and os.environ.get('LYS_ALLOW_EMULATOR') != '1':
-        # LYS_LIBTRACER points at the test-suite's host build of the kernels: never a fallback, only loaded when a test says so
-        raise TracerError('%s is the CPU emulator build of the test-suite, not libtracer; set LYS_ALLOW_EMULATOR=1 only inside tests' % _SO)
     L.futhark_context_config_new.restype = vp
     L.futhark_context_config_free.argtypes = [vp]
     L.futhark_context_config_set_device.argtypes = [vp, C.c_char_p]
@@ -136,6 +133,7 @@ def _load():
     L.lys_eval_math.argtypes = [vp, C.c_int, vp, vp, C.c_int64]
     L.lys_material_probe.argtypes = [vp, vp, C.c_float, vp, vp, vp, C.c_uint32, vp]
     L.lys_sample_n_frames_stats.argtypes = [vp, C.POINTER(vp), vp, C.c_uint32, C.POINTER(PassStats)]
+    L.lys_sample_n_frames_weighted.argtypes = [vp, C.POINTER(vp), vp, C.c_uint32, C.c_float, C.POINTER(PassStats)]
     _lib = L
     return L
 
@@ -180,7 +178,8 @@ class Context:
         self._L = L
         cfg = L.futhark_context_config_new()
         if device is not None:
-            L.futhark_context_config_set_device(cfg, str(device).encode())
+            # an int is a device ordinal ("#k", the generated backend's syntax); a str goes through as is ("#1 B200", "B200")
+            L.futhark_context_config_set_device(cfg, ('#%d' % device if isinstance(device, int) else str(device)).encode())
         if profiling:
             L.futhark_context_config_set_profiling(cfg, 1)
         self._ctx = L.futhark_context_new(cfg)
@@ -229,7 +228,8 @@ class Context:
         self.check(self._L.lys_context_set_partition(self._ctx, int(rank), int(world)), 'lys_context_set_partition')
 
     def set_profiling(self, on):
-        self.check(self._L.lys_context_set_profiling(self._ctx, int(bool(on))), 'lys_context_set_profiling')
+        # True / 1: per-class sequence (exclusive times); 2: the production sequence with events around its launches (shares)
+        self.check(self._L.lys_context_set_profiling(self._ctx, 2 if on == 2 else int(bool(on))), 'lys_context_set_profiling')
 
     def profile(self, reset=True):
         """-> {class: (device ms, launches)} for generate / trace / shade / accumulate."""
@@ -343,12 +343,14 @@ class State:
     def sample_n_frames(self, n):
         return self._take(self._entry('futhark_entry_sample_n_frames', self._p, n), 'f32_3d', np.float32)
 
-    def sample_n_frames_device(self, n, want_stats=True):
-        """-> (futhark_f32_3d handle, device pointer, shape, stats dict); caller frees with free_f32_3d."""
+    def sample_n_frames_device(self, n, want_stats=True, weight=1.0):
+        """-> (futhark_f32_3d handle, device pointer, shape, stats dict); caller frees with free_f32_3d.
+        weight != 1: the image is multiplied by it inside the last accumulate kernel (pass-split multi-GPU frames)."""
         L = self.ctx._L
         out = vp()
         st = PassStats()
-        self.ctx.check(L.lys_sample_n_frames_stats(self.ctx._ctx, C.byref(out), self._p, n, C.byref(st) if want_stats else None), 'lys_sample_n_frames_stats')
+        self.ctx.check(L.lys_sample_n_frames_weighted(self.ctx._ctx, C.byref(out), self._p, n, float(weight), C.byref(st) if want_stats else None),
+                       'lys_sample_n_frames_weighted')
         shp = L.futhark_shape_f32_3d(self.ctx._ctx, out.value)
         stats = {k: getattr(st, k) for k, _ in PassStats._fields_}
         return out.value, int(L.lys_device_ptr_f32_3d(self.ctx._ctx, out.value)), tuple(int(shp[i]) for i in range(3)), stats

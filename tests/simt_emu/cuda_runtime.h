@@ -74,6 +74,20 @@ template <class T> static inline T __ldcg(const T *p) { return *(const volatile 
 template <> inline float4 __ldcg<float4>(const float4 *p) { return *p; }
 static inline void __threadfence() {}
 static inline void __syncthreads() { emu::cta_barrier(); }
+/* block-wide vote barriers: lanes run one at a time, so a plain counter between barriers is exact */
+namespace emu { inline int &sync_acc() { static int a; return a; } }
+static inline int __syncthreads_count(int pred) {
+    emu::cta_barrier();
+    if (threadIdx.x == 0 && threadIdx.y == 0 && threadIdx.z == 0) emu::sync_acc() = 0;
+    emu::cta_barrier();
+    if (pred) emu::sync_acc()++;
+    emu::cta_barrier();
+    const int r = emu::sync_acc();
+    emu::cta_barrier();
+    return r;
+}
+static inline int __syncthreads_or(int pred) { return __syncthreads_count(pred) != 0; }
+static inline size_t __cvta_generic_to_shared(const void *p) { return (size_t)p; }
 static inline void __syncwarp(unsigned int = 0xffffffffu) { (void)emu::warp_collective(emu::OP_SYNCWARP, 0, 0); }
 static inline unsigned int __ballot_sync(unsigned int, int pred) { return emu::warp_collective(emu::OP_BALLOT, pred ? 1u : 0u, 0); }
 static inline int __any_sync(unsigned int m, int pred) { return __ballot_sync(m, pred) != 0; }
@@ -143,4 +157,5 @@ cudaError_t cudaEventDestroy(cudaEvent_t e);
 cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t s = nullptr);
 cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b);
 template <class F> static inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int *n, F, int, size_t) { *n = 2; return cudaSuccess; }
+static inline cudaError_t cudaMemGetInfo(size_t *fr, size_t *tot) { *fr = (size_t)8 << 30; *tot = (size_t)16 << 30; return cudaSuccess; }
 template <class F> static inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }

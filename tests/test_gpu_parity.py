@@ -1,6 +1,8 @@
 """GPU parity: the sm_100a library, called through its C ABI, against the CPU oracle on identical inputs.
 Bit-exact everywhere (integers, indices AND f32 results): the arithmetic contract makes that a meaningful bar."""
+import importlib
 import os
+import sys
 import numpy as np
 import pytest
 from conftest import SCENE_NAMES, bits_equal
@@ -353,6 +355,89 @@ def test_million_triangle_bvh(orc, pkg, gpu, scenes):
     assert bits_equal(so.sample_n_frames(2), sg.sample_n_frames(2))
 
 
+BASELINE_SIZES = [                       # BASELINE.json configs 2-5 at the resolutions they are quoted on
+    ('mirrorbox', 1080, 1920, 3),        # camera inside the box: 9 vertices per path, every bounce launch carries a long queue
+    ('spectrumsphere', 1080, 1920, 2),
+    ('spectrumspherehigh', 1080, 1920, 2),
+    ('synthetic', 2160, 3840, 2),        # 1 003 244 triangles at 4K: plain node array, one box stage, the large-scene grid sizing
+]
+
+
+@pytest.mark.parametrize('name,h,w,passes', BASELINE_SIZES, ids=[b[0] for b in BASELINE_SIZES])
+def test_baseline_resolution_images_bit_exact(gpu, name, h, w, passes):
+    """Queue lengths, the bounce the fused tail starts at, the hits-first order lists and the grid sizes all depend on the
+    frame size: the accumulated image at the full BASELINE size against the oracle's, bit for bit (the second and later
+    passes run with the queue-length estimates of the first)."""
+    sys.path.insert(0, os.path.join(ROOT, 'tools'))
+    import gpu_parity_image
+    r = gpu_parity_image.compare(gpu, name, h, w, passes)
+    assert r['img_bits'] and r['nonzero'], r
+
+
+@pytest.mark.parametrize('env,scene', [
+    ({'LYS_TAIL_MAX': '100000000'}, 'mirrorbox'),      # deep specular paths through k_tail at 1080p (by default its queues never get short enough)
+    ({'LYS_TAIL_MAX': '262144'}, 'synthetic'),         # k_tail on the large scene
+], ids=['tail-mirrorbox-1080p', 'tail-synthetic-4k'])
+def test_fused_tail_at_baseline_resolution(env, scene):
+    import json
+    import subprocess
+    h, w = (2160, 3840) if scene == 'synthetic' else (1080, 1920)
+    e = dict(os.environ)
+    e.update(env)
+    out = subprocess.check_output([sys.executable, os.path.join(ROOT, 'tools', 'gpu_parity_image.py'), scene, str(h), str(w), '3'], env=e, text=True, timeout=900)
+    r = json.loads(out.strip().splitlines()[-1])
+    assert r['img_bits'] and r['nonzero'], (env, r)
+
+
+def test_pass_split_merge_matches_single_gpu(pkg, gpu, scenes):
+    """Pass-split multi-GPU frame on one device: two 'ranks' render passes [0, 9) and [9, 18) of one frame with their weights
+    applied inside the last accumulate kernel (lys_sample_n_frames_weighted); their sum must agree with the single-GPU
+    18-pass image within 1e-4 relative (north star: per-pass radiance tolerance; the running average is order dependent, so
+    not bitwise).  Weight 1 must be the unweighted image bit for bit."""
+    par = importlib.import_module('msc-futhark-ray-tracer_b200.parallel')
+    t, tm, m = scenes['cornell']
+    s = pkg.State.init(gpu, t, tm, m, 108, 192)
+    total, world = 18, 2
+    full = s.sample_n_frames(total)
+    ranges = par.pass_ranges(total, world)
+    counts = [c for _, c in ranges]
+    acc = np.zeros_like(full, dtype=np.float64)
+    for first, count in ranges:
+        sr = s.advance_rng(first) if first else s
+        hnd, _, shape, _ = sr.sample_n_frames_device(count, want_stats=False, weight=par.pass_weight(count, counts))
+        acc += sr.values_f32_3d(hnd, shape)
+        sr.free_f32_3d(hnd)
+    # each rank drops its first pass (integrator.fut:183-186), so the two means cover 16 of the 17 passes the single image averages
+    assert abs(float(acc.mean()) - float(full.mean())) / max(float(full.mean()), 1e-6) < 0.03      # two estimates of the same image: means agree (Monte Carlo noise averaged over the pixels)
+    # exactness of the fold: weight w inside the kernel == the same image scaled afterwards
+    hnd, _, shape, _ = s.sample_n_frames_device(5, want_stats=False, weight=0.25)
+    scaled = s.values_f32_3d(hnd, shape); s.free_f32_3d(hnd)
+    assert bits_equal(scaled, (np.float32(0.25) * s.sample_n_frames(5)).astype(np.float32))
+    hnd, _, shape, _ = s.sample_n_frames_device(5, want_stats=False, weight=1.0)
+    one = s.values_f32_3d(hnd, shape); s.free_f32_3d(hnd)
+    assert bits_equal(one, s.sample_n_frames(5))
+    # the same split evaluated by the oracle's arithmetic: mean of per-rank means == what the ranks produced, to 1e-4 relative
+    ref = np.zeros_like(acc)
+    for first, count in ranges:
+        sr = s.advance_rng(first) if first else s
+        ref += np.float64(par.pass_weight(count, counts)) * sr.sample_n_frames(count).astype(np.float64)
+    assert np.allclose(acc, ref, rtol=1e-4, atol=1e-7)
+
+
+def test_init_light_capacity_regrow(orc, pkg, gpu, scenes):
+    """More emissive triangles than the first capacity of the light arrays (4096): init regrows them after its single
+    read-back; light indices keep the input order (scene.fut:58-66)."""
+    t, tm, m = scenes['cornell']
+    st, sm = pkg.scenes.synthetic_cornell(t, tm, 40)                      # 35 200 triangles, 3 200 of them on the light quad
+    mm = m.copy()
+    emits = ((m[:, 16:28:2] >= 0) & (m[:, 17:28:2] > 0)).any(axis=1)        # nonzero_spectrum, scene.fut:59-60
+    mm[:, 16:] = m[np.flatnonzero(emits)[0], 16:]                          # every material emits: all triangles are lights
+    so, sg = orc.State.init(st, sm, mm, 8, 8), pkg.State.init(gpu, st, sm, mm, 8, 8)
+    assert sg.info()['n_lights'] == len(st) > 4096
+    assert bits_equal(so.light_indices(), sg.light_indices())
+    assert bits_equal(so.sample_n_frames(2), sg.sample_n_frames(2))
+
+
 @pytest.mark.parametrize('env', [
     {'LYS_TRACE_OCT': '0'},            # select-based box test on the plain node array (what scenes above 128K nodes use)
     {'LYS_TRACE_NB': '1'},             # one box stage per loop iteration
@@ -364,6 +449,11 @@ def test_million_triangle_bvh(orc, pkg, gpu, scenes):
     {'LYS_TAIL_MAX': '100000000', 'LYS_TRACE_OCT': '0'},
     {'LYS_TRACE_MODE': '1'},           # refill variant of the trace kernel
     {'LYS_SHADE_SPLIT': '2'},          # phase-split shading kernels for the first two bounces
+    {'LYS_TRACE_MODE': '2'},           # k_trace_sr: staged loop + lane refill
+    {'LYS_TRACE_MODE': '2', 'LYS_TRACE_SR_CAMERA': '1'},
+    {'LYS_TRACE_NB': '1', 'LYS_TRACE_PF': '1'},      # right-child prefetch at push time (what large scenes may select)
+    {'LYS_TRACE_NB': '1', 'LYS_TRACE_PF': '2', 'LYS_TRACE_OCT': '0'},
+    {'LYS_TRACE_NB': '1', 'LYS_TRACE_PF': '3'},
 ], ids=lambda e: ','.join(f'{k}={v}' for k, v in e.items()))
 def test_kernel_variants_bit_exact(env):
     """Every selectable kernel variant (environment knobs read once per process) gives the oracle's bits: the sweep of

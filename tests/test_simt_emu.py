@@ -10,6 +10,7 @@ import pytest
 from conftest import ROOT
 
 sys.path.insert(0, os.path.join(ROOT, 'tests', 'simt_emu'))
+RUN_EMU = os.path.join(ROOT, 'tests', 'simt_emu', 'run_with_emu.py')      # the only place that points the binding at the emulator build
 
 
 @pytest.fixture(scope='module')
@@ -21,9 +22,8 @@ def emu_lib():
 def sweep(emu_lib, scenes, env=None):
     e = dict(os.environ)
     e.update(env or {})
-    e['LYS_LIBTRACER'] = emu_lib
-    e['LYS_ALLOW_EMULATOR'] = '1'
-    out = subprocess.check_output([sys.executable, os.path.join(ROOT, 'tools', 'gpu_parity_quick.py')] + scenes, env=e, text=True, timeout=1500)
+    e['LYS_EMU_LIB'] = emu_lib
+    out = subprocess.check_output([sys.executable, RUN_EMU, os.path.join(ROOT, 'tools', 'gpu_parity_quick.py')] + scenes, env=e, text=True, timeout=1500)
     res = {}
     for line in out.splitlines():
         name, _, js = line.partition(' ')
@@ -64,13 +64,11 @@ def test_emulated_kernel_variants(emu_lib, env):
 
 
 def test_staged_refill_kernel_on_the_parity_suite(emu_lib):
-    """k_trace_sr (LYS_TRACE_MODE=2) has not run on a GPU yet (it was written after the GPU budget of round 1 was spent), so
-    it is NOT in the `-m gpu` variant list; here it goes through the fuzzed scenes, all camera presets, the edge
-    configurations and the entry points on the emulator.  Move it into tests/test_gpu_parity.py::test_kernel_variants_bit_exact
-    after its first B200 run."""
+    """k_trace_sr (LYS_TRACE_MODE=2; on the B200 it is in tests/test_gpu_parity.py::test_kernel_variants_bit_exact) through the
+    fuzzed scenes, all camera presets, the edge configurations and the entry points on the emulator."""
     e = dict(os.environ)
-    e.update({'LYS_LIBTRACER': emu_lib, 'LYS_ALLOW_EMULATOR': '1', 'LYS_TRACE_MODE': '2'})
-    r = subprocess.run([sys.executable, '-m', 'pytest', os.path.join(ROOT, 'tests', 'test_gpu_parity.py'), '-m', 'gpu', '-q', '-x', '-p', 'no:cacheprovider',
+    e.update({'LYS_EMU_LIB': emu_lib, 'LYS_TRACE_MODE': '2'})
+    r = subprocess.run([sys.executable, RUN_EMU, '-m', 'pytest', os.path.join(ROOT, 'tests', 'test_gpu_parity.py'), '-m', 'gpu', '-q', '-x', '-p', 'no:cacheprovider',
                         '-k', 'soup or edge_configurations or entry_points or sample_points or path_len or row_partition'],
                        env=e, text=True, capture_output=True, timeout=1500, cwd=ROOT)
     tail = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else r.stderr[-400:]
@@ -81,27 +79,29 @@ def test_staged_refill_kernel_on_the_parity_suite(emu_lib):
 def test_gpu_parity_suite_on_the_emulator(emu_lib):
     """tests/test_gpu_parity.py itself (the `-m gpu` parity tests: LBVH edge cases, fuzzed soup scenes, all camera presets,
     entry points, LIDAR points, row partition, error behaviour, raw device access ...) run in a subprocess against the
-    emulated library, 1 003 244-triangle LBVH included.  Left out: the 1080p case (passes on the emulator too, but takes a
-    minute) and the variant sweep (covered above)."""
+    emulated library, 1 003 244-triangle LBVH included.  Left out: the 1080p / 4K cases (a minute and more per frame on the
+    emulator) and the variant sweep (covered above)."""
     e = dict(os.environ)
-    e['LYS_LIBTRACER'] = emu_lib
-    e['LYS_ALLOW_EMULATOR'] = '1'
+    e['LYS_EMU_LIB'] = emu_lib
     e['LYS_EMU_SCHEDULE'] = '20261018'                      # pseudo-random CTA / warp / lane order: also a race probe
-    r = subprocess.run([sys.executable, '-m', 'pytest', os.path.join(ROOT, 'tests', 'test_gpu_parity.py'), '-m', 'gpu', '-q', '-x', '-p', 'no:cacheprovider',
-                        '-k', 'not full_size and not kernel_variants'], env=e, text=True, capture_output=True, timeout=1500, cwd=ROOT)
+    r = subprocess.run([sys.executable, RUN_EMU, '-m', 'pytest', os.path.join(ROOT, 'tests', 'test_gpu_parity.py'), '-m', 'gpu', '-q', '-x', '-p', 'no:cacheprovider',
+                        '-k', 'not full_size and not kernel_variants and not baseline_resolution'], env=e, text=True, capture_output=True, timeout=1500, cwd=ROOT)
     tail = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else r.stderr[-400:]
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
     assert ' passed' in tail and 'failed' not in tail and int(tail.split(' passed')[0].split()[-1]) >= 40, tail
 
 
-def test_product_binding_refuses_the_emulator_unless_a_test_allows_it(emu_lib):
-    """No silent CPU path: the Python binding only loads the emulated library when LYS_ALLOW_EMULATOR=1 is set (by tests)."""
+def test_product_binding_has_no_library_override(emu_lib):
+    """No CPU path reachable from the product: the Python binding ignores the environment and only opens the libtracer.so
+    next to it (the emulator build is reached through tests/simt_emu/run_with_emu.py alone)."""
     e = dict(os.environ)
-    e['LYS_LIBTRACER'] = emu_lib
-    e.pop('LYS_ALLOW_EMULATOR', None)
-    code = "import importlib; p = importlib.import_module('msc-futhark-ray-tracer_b200'); p.Context()"
+    e.update({'LYS_LIBTRACER': emu_lib, 'LYS_ALLOW_EMULATOR': '1', 'LYS_EMU_LIB': emu_lib})
+    code = ("import importlib, os; p = importlib.import_module('msc-futhark-ray-tracer_b200'); "
+            "assert os.path.basename(p.lib_path()) == 'libtracer.so' and os.path.dirname(p.lib_path()) == os.path.dirname(p.__file__), p.lib_path()")
     r = subprocess.run([sys.executable, '-c', code], env=e, text=True, capture_output=True, cwd=ROOT)
-    assert r.returncode != 0 and 'CPU emulator build' in r.stderr
+    assert r.returncode == 0, r.stderr
+    src = open(os.path.join(ROOT, 'msc-futhark-ray-tracer_b200', 'tracer.py')).read()
+    assert 'environ' not in src and 'emu' not in src.lower()
 
 
 @pytest.mark.parametrize('what,seed,count,env', [
@@ -114,8 +114,8 @@ def test_fuzzed_parity_on_the_emulator(emu_lib, what, seed, count, env):
     """tools/fuzz_parity.py (usable on the GPU as well) against the emulated library: zero mismatching scenes."""
     e = dict(os.environ)
     e.update(env)
-    e.update({'LYS_LIBTRACER': emu_lib, 'LYS_ALLOW_EMULATOR': '1'})
-    r = subprocess.run([sys.executable, os.path.join(ROOT, 'tools', 'fuzz_parity.py'), what, str(seed), str(count)], env=e, text=True, capture_output=True, timeout=1500)
+    e.update({'LYS_EMU_LIB': emu_lib})
+    r = subprocess.run([sys.executable, RUN_EMU, os.path.join(ROOT, 'tools', 'fuzz_parity.py'), what, str(seed), str(count)], env=e, text=True, capture_output=True, timeout=1500)
     assert r.returncode == 0 and '%d scenes, 0 mismatching' % count in r.stdout, r.stdout[-2000:] + r.stderr[-1000:]
 
 
