@@ -373,11 +373,9 @@ bool make_frame_params(futhark_context *ctx, const futhark_opaque_state *s, uint
     return true;
 }
 
-uint32_t h_advance_rng(uint32_t s) { return (48271u * s) % 2147483647u; }           /* rand.fut:11-12 */
+uint32_t h_advance_rng(uint32_t s) { return lys_pin_lcg(s); }                      /* rand.fut:11-12 */
 uint32_t h_rng_from_seed(int32_t seed) {                                            /* cpprandom rng_from_seed [seed] */
-    uint32_t sp = 1;
-    sp = ((sp >> 16) ^ sp) ^ ((uint32_t)seed ^ 0x1555u);
-    return h_advance_rng(sp);
+    return lys_pin_rng_from_seed(seed);
 }
 
 futhark_opaque_state *clone_state(const futhark_opaque_state *s) { return new futhark_opaque_state(*s); }

@@ -10,6 +10,7 @@
 #include <stdint.h>
 #include <float.h>
 #include "../../include/lys_detmath.h"
+#include "../../include/lys_pins.h"      /* third-party package semantics: one shared definition each (oracle + device) */
 
 #define LYS_D __device__ __forceinline__
 /* The big shading routines.  They were out of line while k_shade was instruction-fetch bound (6000 SASS instructions with
@@ -49,7 +50,7 @@ LYS_HDI float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 LYS_HDI V3 cross(V3 a, V3 b) { return v3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
 LYS_HDI float quadrance(V3 v) { return dot(v, v); }
 LYS_HDI float norm(V3 v) { return sqrtf(quadrance(v)); }
-LYS_HDI V3 normalise(V3 v) { float l = norm(v); return (1.0f / l) * v; }
+LYS_HDI V3 normalise(V3 v) { V3 r; lys_pin_normalise(v.x, v.y, v.z, norm(v), &r.x, &r.y, &r.z); return r; }    /* vector `normalise` (lys_pins.h) */
 LYS_HDI V3 same_side(V3 dominant, V3 w) { return lys_sgnf(dot(dominant, w)) * w; }     /* linalg.fut:30-31 */
 LYS_HDI V3 vmin3(V3 a, V3 b) { return v3(lys_fminf(a.x, b.x), lys_fminf(a.y, b.y), lys_fminf(a.z, b.z)); }
 LYS_HDI V3 vmax3(V3 a, V3 b) { return v3(lys_fmaxf(a.x, b.x), lys_fmaxf(a.y, b.y), lys_fmaxf(a.z, b.z)); }
@@ -85,19 +86,13 @@ LYS_HDI uint32_t morton30(V3 v) {
 }
 
 /* ---- RNG: rand.fut + cpprandom minstd_rand (wrapping-u32 LCG) -------------------------- */
-LYS_HDI uint32_t lcg_next(uint32_t &s) { s = (48271u * s) % 2147483647u; return s; }
+LYS_HDI uint32_t lcg_next(uint32_t &s) { s = lys_pin_lcg(s); return s; }
 LYS_HDI float lcg_uniform(uint32_t &s, float lo, float hi) {
-    uint32_t x = lcg_next(s);
-    float xp = ((float)x - 0.0f) / (2147483648.0f - 0.0f);      /* f32(2^31-1) == 2^31 */
-    return lo + xp * (hi - lo);
+    return lys_pin_uniform(lcg_next(s), lo, hi);                 /* uniform_real_distribution (lys_pins.h) */
 }
 LYS_HDI void rng_advance(uint32_t &s) { (void)lcg_next(s); }                               /* rand.fut:11-12 */
 LYS_HDI float rng_unit(uint32_t &s) { return lcg_uniform(s, 0.0f, 0.9999f); }              /* rand.fut:15-16 */
-LYS_HDI uint32_t rng_split_hash(uint32_t x) {
-    x = ((x >> 16) ^ x) * 0x45d9f3bu;
-    x = ((x >> 16) ^ x) * 0x45d9f3bu;
-    return (x >> 16) ^ x;
-}
+LYS_HDI uint32_t rng_split_hash(uint32_t x) { return lys_pin_split_hash(x); }              /* cpprandom hash of split_rng (lys_pins.h) */
 LYS_HDI V3 rng_unit_disk(uint32_t &s) {                                                    /* rand.fut:21-25 */
     float theta = lcg_uniform(s, 0.0f, 2.0f * LYS_PI);
     float u = rng_unit(s);

@@ -1094,7 +1094,7 @@ __global__ void k_points_export(int n, const float4 *__restrict__ pos_int, float
 }
 
 /* ------------------------------------------------------------------ render (lib.fut:187-196, matte argb.from_rgba) */
-LYS_D uint32_t chan8(float x) { float c = (x < 0.0f) ? 0.0f : ((x > 1.0f) ? 1.0f : x); return trunc_u32(c * 255.0f); }
+LYS_D uint32_t chan8(float x) { return lys_pin_argb_channel(x); }          /* matte argb.from_rgba (lys_pins.h) */
 __global__ void __launch_bounds__(256) k_render(const float *__restrict__ img, int img_h, int img_w, int full_h, int full_w, int sub,
                                                 int32_t *__restrict__ out) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;

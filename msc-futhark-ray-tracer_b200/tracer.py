@@ -30,7 +30,7 @@ def lib_path():
 def build(force=False):
     """Compile libtracer.so / libtracer.a / libljus.so in-tree with nvcc for sm_100a (no GPU needed)."""
     srcs = [os.path.join(_HERE, 'csrc', f) for f in os.listdir(os.path.join(_HERE, 'csrc'))]
-    srcs += [os.path.join(_HERE, '..', 'include', f) for f in ('tracer.h', 'lys_ext.h', 'lys_detmath.h')]
+    srcs += [os.path.join(_HERE, '..', 'include', f) for f in ('tracer.h', 'lys_ext.h', 'lys_detmath.h', 'lys_pins.h')]
     newest = max(os.path.getmtime(s) for s in srcs)
     stale = force or not all(os.path.exists(p) and os.path.getmtime(p) >= newest for p in (_SO, _LJUS, os.path.join(_HERE, 'libtracer.a')))
     if stale:

@@ -13,6 +13,7 @@
  */
 #include "lys_oracle.h"
 #include "../include/lys_detmath.h"
+#include "../include/lys_pins.h"       /* third-party package semantics: the ONE definition shared with the device code */
 
 #include <cfloat>
 #include <cmath>
@@ -85,7 +86,7 @@ inline vec3 vcross(vec3 a, vec3 b) {
 inline vec3 vscale(float s, vec3 v) { return {s * v.x, s * v.y, s * v.z}; }
 inline float vquadrance(vec3 v) { return vdot(v, v); }
 inline float vnorm(vec3 v) { return sqrtf(vquadrance(v)); }
-inline vec3 vnormalise(vec3 v) { float l = vnorm(v); return vscale(1.0f / l, v); }
+inline vec3 vnormalise(vec3 v) { vec3 r; lys_pin_normalise(v.x, v.y, v.z, vnorm(v), &r.x, &r.y, &r.z); return r; }
 inline vec3 vneg(vec3 v) { return {-v.x, -v.y, -v.z}; }                       /* linalg.fut:19 */
 inline vec3 same_side(vec3 dominant, vec3 w) { return vscale(lys_sgnf(vdot(dominant, w)), w); } /* linalg.fut:30-31 */
 inline vec3 vmax(vec3 u, vec3 v) { return {f_max(u.x, v.x), f_max(u.y, v.y), f_max(u.z, v.z)}; } /* linalg.fut:35 */
@@ -98,14 +99,10 @@ inline bool approx_zero(float a, float eps) { return a > -eps && a < eps; }   /*
 /* ------------------------------------------------------------------ rand.fut + cpprandom minstd_rand
  * linear_congruential_engine u32 {a=48271, c=0, m=2147483647}: rand x = (a*x + c) %% m in wrapping u32. */
 typedef uint32_t rnge;
-inline uint32_t rng_rand(rnge &s) { s = (uint32_t)(48271u * s) % 2147483647u; return s; }
+inline uint32_t rng_rand(rnge &s) { s = lys_pin_lcg(s); return s; }
 /* uniform_real_distribution f32: x' = (f32 x - f32 min) / (f32 max - f32 min); lo + x' * (hi - lo) */
 inline float dist_rand(rnge &s, float lo, float hi) {
-    uint32_t x = rng_rand(s);
-    float xf = (float)(uint64_t)x;
-    float mx = (float)(uint64_t)2147483647u;
-    float xp = (xf - 0.0f) / (mx - 0.0f);
-    return lo + xp * (hi - lo);
+    return lys_pin_uniform(rng_rand(s), lo, hi);
 }
 inline void advance_rng(rnge &s) { (void)dist_rand(s, 0.0f, 1.0f); }            /* rand.fut:11-12 */
 inline float random_unit_exclusive(rnge &s) { return dist_rand(s, 0.0f, 0.9999f); } /* rand.fut:15-16 */
@@ -123,19 +120,11 @@ inline void random_in_triangle(rnge &s, float &u, float &v) {                  /
     float su = sqrtf(a);
     u = 1.0f - su; v = b * su;
 }
-/* cpprandom hash (stackoverflow 12996028), u32 arithmetic */
-inline uint32_t rng_hash(int32_t xi) {
-    uint32_t x = (uint32_t)xi;
-    x = ((x >> 16) ^ x) * 0x45d9f3bu;
-    x = ((x >> 16) ^ x) * 0x45d9f3bu;
-    x = (x >> 16) ^ x;
-    return x;
-}
+/* cpprandom hash (stackoverflow 12996028) as split_rng uses it: lys_pins.h (LYS_PIN_HASH_SHIFT_ARITHMETIC) */
+inline uint32_t rng_hash(int32_t xi) { return lys_pin_split_hash((uint32_t)xi); }
 /* rng_from_seed [seed]: seed' = fold ((s'>>16)^s') ^ (seed ^ 0b1010101010101) from 1; then one rand */
 inline rnge rng_from_seed1(int32_t seed) {
-    uint32_t sp = 1;
-    sp = ((sp >> 16) ^ sp) ^ ((uint32_t)seed ^ 0x1555u);
-    rnge s = sp; rng_rand(s); return s;
+    return lys_pin_rng_from_seed(seed);
 }
 
 /* ------------------------------------------------------------------ spectrum.fut */
@@ -944,7 +933,8 @@ rnge sample_frame_accum(const orc_state &s, std::vector<vec3> &out, uint32_t &gw
 int32_t argb_from_rgba(float r, float g, float b, float a) {                   /* matte colour.fut argb.from_rgba */
     auto ch = [](float x) -> uint32_t {
         float c = (x < 0.0f) ? 0.0f : ((x > 1.0f) ? 1.0f : x);
-        return u32_of_f32(c * 255.0f);
+        (void)c;
+        return lys_pin_argb_channel(x);
     };
     return (int32_t)((ch(a) << 24) | (ch(r) << 16) | (ch(g) << 8) | ch(b));
 }
@@ -1134,6 +1124,21 @@ uint32_t orc_rng_next(uint32_t s) { rng_rand(s); return s; }
 float orc_rng_uniform(uint32_t s, float lo, float hi, uint32_t *s_out) { float v = dist_rand(s, lo, hi); if (s_out) *s_out = s; return v; }
 void orc_radix_tree(const uint32_t *keys, int64_t n, int32_t *left, int32_t *right, int32_t *parent) { radix_tree_mk(keys, n, left, right, parent); }
 float orc_spectrum_lookup(float v, const float *spectrum12) { return spectrum_lookup(v, spectrum_from12(spectrum12)); }
+int32_t orc_hit_aabb(float tmax, const float *ray6, const float *box6) {          /* box6 = center xyz, half_dims xyz */
+    ray r = {{ray6[0], ray6[1], ray6[2]}, {ray6[3], ray6[4], ray6[5]}};
+    aabb b = {{box6[0], box6[1], box6[2]}, {box6[3], box6[4], box6[5]}};
+    return hit_aabb(tmax, r, b) ? 1 : 0;
+}
+int32_t orc_hit_triangle(float tmax, const float *ray6, const float *tri9, float *t_pos_normal7) {
+    ray r = {{ray6[0], ray6[1], ray6[2]}, {ray6[3], ray6[4], ray6[5]}};
+    triangle tr = {{tri9[0], tri9[1], tri9[2]}, {tri9[3], tri9[4], tri9[5]}, {tri9[6], tri9[7], tri9[8]}};
+    hit h;
+    if (!hit_triangle(tmax, r, tr, h)) return 0;
+    if (t_pos_normal7) { float o[7] = {h.t, h.pos.x, h.pos.y, h.pos.z, h.normal.x, h.normal.y, h.normal.z}; memcpy(t_pos_normal7, o, sizeof o); }
+    return 1;
+}
+void orc_normalise(const float *v3, float *out3) { vec3 r = vnormalise({v3[0], v3[1], v3[2]}); out3[0] = r.x; out3[1] = r.y; out3[2] = r.z; }
+int32_t orc_argb_from_rgba(float r, float g, float b, float a) { return argb_from_rgba(r, g, b, a); }
 void orc_eval_math(int fn, const float *in, float *out, int64_t n) {
     for (int64_t i = 0; i < n; i++) {
         float x = in[i], y;

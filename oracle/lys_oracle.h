@@ -71,6 +71,10 @@ uint32_t orc_rng_next(uint32_t s);
 float    orc_rng_uniform(uint32_t s, float lo, float hi, uint32_t *s_out);
 void orc_radix_tree(const uint32_t *keys, int64_t n, int32_t *left, int32_t *right, int32_t *parent);
 float orc_spectrum_lookup(float v, const float *spectrum12);
+int32_t orc_hit_aabb(float tmax, const float *ray6, const float *box6 /* center, half_dims */);             /* shapes.fut:114-135 */
+int32_t orc_hit_triangle(float tmax, const float *ray6, const float *tri9, float *t_pos_normal7 /* or NULL */); /* shapes.fut:66-86 */
+void orc_normalise(const float *v3, float *out3);                                                          /* vector `normalise` (lys_pins.h) */
+int32_t orc_argb_from_rgba(float r, float g, float b, float a);                                           /* matte argb.from_rgba (lys_pins.h) */
 void orc_eval_math(int fn, const float *in, float *out, int64_t n);
 void orc_material_probe(const float *mat28, float wavelen, const float *wo, const float *wi, const float *normal,
                         uint32_t rng, float *out /* bsdf_f, bsdf_pdf, sample wi xyz, sample bsdf, pdf kind, pdf, rng_out */);

@@ -39,10 +39,15 @@ def py_lcg(s):
 
 
 def py_hash(x):
-    x &= 0xFFFFFFFF
-    x = (((x >> 16) ^ x) * 0x45d9f3b) & 0xFFFFFFFF
-    x = (((x >> 16) ^ x) * 0x45d9f3b) & 0xFFFFFFFF
-    return (x >> 16) ^ x
+    """cpprandom `hash (x: i32): i32` with Futhark's `>>` on i32 = ARITHMETIC shift (include/lys_pins.h,
+    LYS_PIN_HASH_SHIFT_ARITHMETIC = 1), written on Python's unbounded signed integers."""
+    def i32(v):
+        v &= 0xFFFFFFFF
+        return v - (1 << 32) if v & 0x80000000 else v
+    x = i32(x)
+    x = i32(((x >> 16) ^ x) * 0x45d9f3b)
+    x = i32(((x >> 16) ^ x) * 0x45d9f3b)
+    return ((x >> 16) ^ x) & 0xFFFFFFFF
 
 
 def test_rng(orc):
