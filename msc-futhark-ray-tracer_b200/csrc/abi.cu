@@ -242,13 +242,13 @@ bool ensure_bufs(futhark_context *ctx, PassBuffers &b, int64_t n, bool probes) {
     if (b.cap < n) {
         raw_free(b.ray_o[0]); raw_free(b.ray_o[1]); raw_free(b.ray_d[0]); raw_free(b.ray_d[1]); raw_free(b.dist[0]); raw_free(b.dist[1]); raw_free(b.acc);
         raw_free(b.chan); raw_free(b.queue[0]); raw_free(b.queue[1]); raw_free(b.hit); raw_free(b.order[0]); raw_free(b.order[1]); raw_free(b.sh_o); raw_free(b.sh_d1); raw_free(b.sh_d2);
-        raw_free(b.sh_c); raw_free(b.tmp_a); raw_free(b.tmp_b); raw_free(b.probe_rad); raw_free(b.probe_dist);
+        raw_free(b.sh_c); raw_free(b.probe_rad); raw_free(b.probe_dist);
         b.cap = 0;
         size_t c = (size_t)n;
         if (!raw_alloc(ctx, b.ray_o[0], c) || !raw_alloc(ctx, b.ray_o[1], c) || !raw_alloc(ctx, b.ray_d[0], c) || !raw_alloc(ctx, b.ray_d[1], c) ||
             !raw_alloc(ctx, b.dist[0], c) || !raw_alloc(ctx, b.dist[1], c) || !raw_alloc(ctx, b.acc, c) || !raw_alloc(ctx, b.chan, c) ||
             !raw_alloc(ctx, b.queue[0], c) || !raw_alloc(ctx, b.queue[1], c) || !raw_alloc(ctx, b.hit, c) || !raw_alloc(ctx, b.order[0], c) || !raw_alloc(ctx, b.order[1], c) || !raw_alloc(ctx, b.sh_o, c) ||
-            !raw_alloc(ctx, b.sh_d1, c) || !raw_alloc(ctx, b.sh_d2, c) || !raw_alloc(ctx, b.sh_c, c) || !raw_alloc(ctx, b.tmp_a, c) || !raw_alloc(ctx, b.tmp_b, c)) return false;
+            !raw_alloc(ctx, b.sh_d1, c) || !raw_alloc(ctx, b.sh_d2, c) || !raw_alloc(ctx, b.sh_c, c)) return false;
         b.cap = n;
     }
     if (!b.counts) {
@@ -266,7 +266,7 @@ bool ensure_pass_buffers(futhark_context *ctx, int64_t n, bool probes) { return 
 void free_bufs(PassBuffers &b, bool owns_tx) {
     raw_free(b.ray_o[0]); raw_free(b.ray_o[1]); raw_free(b.ray_d[0]); raw_free(b.ray_d[1]); raw_free(b.dist[0]); raw_free(b.dist[1]); raw_free(b.acc);
     raw_free(b.chan); raw_free(b.queue[0]); raw_free(b.queue[1]); raw_free(b.hit); raw_free(b.order[0]); raw_free(b.order[1]); raw_free(b.sh_o); raw_free(b.sh_d1); raw_free(b.sh_d2);
-    raw_free(b.sh_c); raw_free(b.tmp_a); raw_free(b.tmp_b); raw_free(b.counts); raw_free(b.stats); raw_free(b.split); raw_free(b.probe_rad); raw_free(b.probe_dist);
+    raw_free(b.sh_c); raw_free(b.counts); raw_free(b.stats); raw_free(b.split); raw_free(b.probe_rad); raw_free(b.probe_dist);
     if (owns_tx) raw_free(b.tx_lights);
     b.cap = 0;
 }
@@ -580,12 +580,12 @@ int futhark_entry_init(struct futhark_context *ctx, struct futhark_opaque_state 
     const size_t light_chunks = (c + 1023) / 1024;
     unsigned char *mat_flag = nullptr; int *light_chunk = nullptr, *light_info = nullptr;
     if (!H.take(ctx, sc.tris, 9 * c) || !H.take(ctx, sc.tri_mats, c) || !H.take(ctx, sc.mats, (size_t)m * 28) ||
-        !H.take(ctx, sc.leaf_tri, 4 * c) || !H.take(ctx, sc.leaf_box, 2 * c) || !H.take(ctx, sc.nodes, 2 * c) ||
+        !H.take(ctx, sc.leaf_tri, 4 * c) || !H.take(ctx, sc.leaf_box, 2 * c) || !H.take(ctx, sc.nodes, 4 * c) ||
         !H.take(ctx, sc.node_box, 2 * c) || !H.take(ctx, sc.left, c) || !H.take(ctx, sc.right, c) || !H.take(ctx, sc.parent, c) ||
         !H.take(ctx, sc.height, c) || !H.take(ctx, sc.morton, c) || !H.take(ctx, sc.sorted_idx, c) || !H.take(ctx, sc.bounds, 8) ||
         !H.take(ctx, sc.lights, (size_t)light_cap) || !H.take(ctx, sc.light_src, (size_t)light_cap) ||
         !H.take(ctx, mat_flag, (size_t)m) || !H.take(ctx, light_chunk, light_chunks) || !H.take(ctx, light_info, 4)) return 1;
-    if (n - 1 <= LYS_OCT_MAX_NODES && n >= 2 && !H.take(ctx, sc.nodes_oct, 16 * c)) return 1;
+    if (n - 1 <= LYS_OCT_MAX_NODES && n >= 2 && !H.take(ctx, sc.nodes_oct, 32 * c)) return 1;
     CU(ctx, cudaMemcpyAsync(sc.tris, tri_geoms->mem->p, sizeof(float) * 9 * c, cudaMemcpyDeviceToDevice, ctx->stream));
     CU(ctx, cudaMemcpyAsync(sc.tri_mats, tri_mats->mem->p, sizeof(uint32_t) * c, cudaMemcpyDeviceToDevice, ctx->stream));
     CU(ctx, cudaMemcpyAsync(sc.mats, mat_data->mem->p, sizeof(float) * (size_t)m * 28, cudaMemcpyDeviceToDevice, ctx->stream));

@@ -14,7 +14,7 @@
  *   k_crown_*        bvh.fut:109,118-120 the reference stops after floor(log2 n)+2 Jacobi sweeps from
  *                                        zero boxes; nodes higher than that keep truncated boxes,
  *                                        recomputed here exactly through level-synchronous worklists
- *   k_pack_nodes                         traversal layout: 2 x float4 per node (min|left, max|right)
+ *   k_pack_nodes                         traversal layout: 4 x float4 per node (both children's boxes + child pointers)
  */
 #include "lys_scene.h"
 #include "lys_device.cuh"
@@ -545,22 +545,49 @@ __global__ void k_copy_f4(const float4 *__restrict__ in, float4 *__restrict__ ou
 }
 
 /* traversal layout: node i -> (min.xyz | left), (max.xyz | right); min/max as hit_aabb derives them (shapes.fut:120) */
+/* record i: the boxes of both children of node i with the child pointers (lys_scene.h); record n_nodes: the super-root */
 __global__ void k_pack_nodes(const float4 *__restrict__ A, const int *__restrict__ left, const int *__restrict__ right,
-                             int n_nodes, float4 *__restrict__ nodes, float4 *__restrict__ nodes_oct) {
+                             int n_nodes, float4 *__restrict__ nodes, float4 *__restrict__ nodes_oct, int single) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_nodes) return;
-    float4 c = A[2ll * i], h = A[2ll * i + 1];
-    V3 mn = v3(c.x, c.y, c.z) - v3(h.x, h.y, h.z), mx = v3(c.x, c.y, c.z) + v3(h.x, h.y, h.z);
-    const float l = __int_as_float(left[i]), r = __int_as_float(right[i]);
-    nodes[2ll * i + 0] = make_float4(mn.x, mn.y, mn.z, l);
-    nodes[2ll * i + 1] = make_float4(mx.x, mx.y, mx.z, r);
-    if (nodes_oct) {
-        /* octant o: axis with 1/dir < 0 enters through max and leaves through min (the swap of shapes.fut:124-126) */
+    if (i > n_nodes) return;
+    if (single && i < n_nodes) {            /* small scenes: octant copies of the node's own box (LAY_SINGLE) */
+        float4 c = A[2ll * i], h = A[2ll * i + 1];
+        V3 mn = v3(c.x, c.y, c.z) - v3(h.x, h.y, h.z), mx = v3(c.x, c.y, c.z) + v3(h.x, h.y, h.z);
+        const float l = __int_as_float(left[i]), r = __int_as_float(right[i]);
 #pragma unroll
         for (int o = 0; o < 8; o++) {
             float4 *q = nodes_oct + 2ll * ((long long)o * n_nodes + i);
             q[0] = make_float4((o & 4) ? mx.x : mn.x, (o & 2) ? mx.y : mn.y, (o & 1) ? mx.z : mn.z, l);
             q[1] = make_float4((o & 4) ? mn.x : mx.x, (o & 2) ? mn.y : mx.y, (o & 1) ? mn.z : mx.z, r);
+        }
+    }
+    const int lc = (i == n_nodes) ? 0 : left[i], rc = (i == n_nodes) ? (int)0x80000000 : right[i];
+    V3 mn[2], mx[2];
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const int c = k ? rc : lc;
+        mn[k] = mx[k] = v3(0.0f, 0.0f, 0.0f);
+        if (c >= 0) {
+            float4 cc = A[2ll * c], h = A[2ll * c + 1];
+            mn[k] = v3(cc.x, cc.y, cc.z) - v3(h.x, h.y, h.z); mx[k] = v3(cc.x, cc.y, cc.z) + v3(h.x, h.y, h.z);
+        }
+    }
+    const float l = __int_as_float(lc), r = __int_as_float(rc);
+    float4 *q = nodes + 4ll * i;
+    q[0] = make_float4(mn[0].x, mn[0].y, mn[0].z, l);
+    q[1] = make_float4(mx[0].x, mx[0].y, mx[0].z, r);
+    q[2] = make_float4(mn[1].x, mn[1].y, mn[1].z, 0.0f);
+    q[3] = make_float4(mx[1].x, mx[1].y, mx[1].z, 0.0f);
+    if (nodes_oct && !single) {
+        /* octant o: axis with 1/dir < 0 enters through max and leaves through min (the swap of shapes.fut:124-126) */
+#pragma unroll
+        for (int o = 0; o < 8; o++) {
+            float4 *qo = nodes_oct + 4ll * ((long long)o * (n_nodes + 1) + i);
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                qo[2 * k + 0] = make_float4((o & 4) ? mx[k].x : mn[k].x, (o & 2) ? mx[k].y : mn[k].y, (o & 1) ? mx[k].z : mn[k].z, k ? 0.0f : l);
+                qo[2 * k + 1] = make_float4((o & 4) ? mn[k].x : mx[k].x, (o & 2) ? mn[k].y : mx[k].y, (o & 1) ? mn[k].z : mx[k].z, k ? 0.0f : r);
+            }
         }
     }
 }
@@ -636,7 +663,11 @@ cudaError_t build_lbvh(SceneDev &sc, BuildScratch &ws, int refit_mode, cudaStrea
         for (int lv = depth - 1; lv > n_top; lv--) { k_crown_eval<<<G, T, 0, stream>>>(sc.left, sc.right, sc.leaf_box, ws.F, (const CrownPair *)ws.crown_pairs, ws.crown_box, ws.crown_cnt, lv, depth, ws.crown_cap, sc.node_box); nl++; }
         k_crown_top_eval<<<1, 1024, 0, stream>>>(sc.left, sc.right, sc.leaf_box, ws.F, (const CrownPair *)ws.crown_pairs, ws.crown_box, ws.crown_cnt, min(n_top, depth - 1), depth, ws.crown_cap, sc.node_box); nl++;
     }
-    k_pack_nodes<<<cdiv(n_nodes, T), T, 0, stream>>>(sc.node_box, sc.left, sc.right, n_nodes, sc.nodes, sc.nodes_oct); nl++;
+    {
+        static const int force_pair = []() { const char *e = getenv("LYS_TRACE_PAIR"); return (e && atoi(e)) ? 1 : 0; }();   /* 1: pair records on small scenes too (tests) */
+        sc.single_nodes = (sc.nodes_oct && n <= LYS_SINGLE_MAX_TRIS && !force_pair) ? 1 : 0;
+        k_pack_nodes<<<cdiv(n_nodes + 1, T), T, 0, stream>>>(sc.node_box, sc.left, sc.right, n_nodes, sc.nodes, sc.nodes_oct, sc.single_nodes); nl++;
+    }
     if (launches) *launches += nl;
     return cudaGetLastError();
 }

@@ -7,10 +7,16 @@
  *   leaf_tri  [n][4]  float4  sorted leaves, 64 B: (a.xyz | mat_ix), (e1 x e2 | source index) = the plane test's sector,
  *                             then (e1.xyz | 0), (e2.xyz | 0) for the barycentric test
  *   leaf_box  [n][2]  float4  sorted leaf boxes (center | half_dims)
- *   nodes     [n-1][2] float4 traversal nodes: (min.xyz | left), (max.xyz | right); one 32-byte sector
- *   nodes_oct [8][n-1][2] float4 (scenes up to LYS_OCT_MAX_NODES nodes) the same nodes once per ray-direction octant:
- *                             (near.xyz | left), (far.xyz | right) with near/far already picked per axis as hit_aabb's
- *                             swap would (octant bit 2/1/0 = 1/dir.x, .y, .z < 0), so the box test needs no select
+ *   nodes     [n][4]  float4  traversal records, 64 B = two sectors: record i < n-1 holds the boxes of BOTH children of node i,
+ *                             (Lmin.xyz | left) (Lmax.xyz | right) (Rmin.xyz | 0) (Rmax.xyz | 0); the box slot of a leaf child
+ *                             is zero (leaves are never box-tested, bvh.fut:133).  Record n-1 is the super-root: left = node 0
+ *                             with the root's own box, right = the end marker 0x80000000.  Corners are derived from
+ *                             (center, half) with the subtraction / addition hit_aabb does per visit (shapes.fut:120)
+ *   nodes_oct [8][n][4] float4 (scenes up to LYS_OCT_MAX_NODES nodes) the same records once per ray-direction octant:
+ *                             (near | left) (far | right) (near | 0) (far | 0) with near/far already picked per axis as hit_aabb's
+ *                             swap would (octant bit 2/1/0 = 1/dir.x, .y, .z < 0), so the box test needs no select.
+ *                             Scenes up to LYS_SINGLE_MAX_TRIS triangles (single_nodes = 1): [8][n-1][2] float4, one box per
+ *                             record, (near.xyz | left) (far.xyz | right) of node i itself
  *   node_box  [n-1][2] float4 node boxes as the reference stores them (center | half_dims)
  *   left/right/parent/height [n-1] i32; child encoding: internal i -> i, leaf i -> ~i
  *   morton, sorted_idx [n] u32; bounds [6] f32 (center, half_dims)
@@ -22,7 +28,8 @@
 
 namespace lys {
 
-#define LYS_OCT_MAX_NODES (1 << 17)      /* 8 x 4 MB of octant nodes at most: stays L2 resident */
+#define LYS_SINGLE_MAX_TRIS 1024         /* up to here the octant copies hold one box per record (wavefront.cu: LAY_SINGLE) */
+#define LYS_OCT_MAX_NODES (1 << 16)      /* 8 x 4 MB of octant records at most: stays L2 resident */
 
 struct LightRec {            /* 32 floats = 128 B, float4-aligned */
     float a[3]; float area;                /* vertex a, triangle area (direct.fut:17-20) */
@@ -38,6 +45,7 @@ struct SceneDev {
     float *tris = nullptr; uint32_t *tri_mats = nullptr; float *mats = nullptr;
     float4 *leaf_tri = nullptr, *leaf_box = nullptr, *nodes = nullptr, *node_box = nullptr;
     float4 *nodes_oct = nullptr;           /* null for scenes above LYS_OCT_MAX_NODES */
+    int single_nodes = 0;                  /* nodes_oct holds single-box records (scenes up to LYS_SINGLE_MAX_TRIS triangles) */
     int *left = nullptr, *right = nullptr, *parent = nullptr, *height = nullptr;
     uint32_t *morton = nullptr, *sorted_idx = nullptr;
     float *bounds = nullptr;

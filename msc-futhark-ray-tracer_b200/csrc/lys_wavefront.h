@@ -52,8 +52,6 @@ struct PassBuffers {
     float4 *sh_d1 = nullptr;    /* dir1.xyz | tmax1 */
     float4 *sh_d2 = nullptr;    /* dir2.xyz | tmax2 */
     float4 *sh_c = nullptr;     /* cL, cB, emission (vertex 0), vertex distance */
-    float2 *tmp_a = nullptr;    /* phase kernels: cL | flags of the light sample */
-    float4 *tmp_b = nullptr;    /* phase kernels: cB | flags | rng after the BSDF-MIS sample | - */
     int *counts = nullptr;      /* [LYS_MAX_PATH_LEN + 1] active paths per bounce */
     unsigned long long *stats = nullptr;   /* [4] vertices, closest rays, shadow rays, paths */
     LightRec *tx_lights = nullptr;         /* [8] flash transmitter lights */

@@ -12,8 +12,7 @@
  *   k_tail(b0)        all bounces from the first sparse one on in one launch (CTA-local wavefront)
  *   k_accumulate      integrator.fut:133-192                             channel resolve + running average
  *   k_render          lib.fut:187-196                                    upscale + ARGB pack
- * Per-path arithmetic is the reference's, operation for operation; only the scheduling differs.  Kept selectable and
- * parity-tested, slower: k_generate + k_trace(-1) as two launches, k_trace_refill, the phase-split shading kernels.
+ * Per-path arithmetic is the reference's, operation for operation; only the scheduling differs.
  */
 #include "lys_wavefront.h"
 #include <cstdio>
@@ -31,8 +30,9 @@ namespace lys {
 struct RayInv { V3 o, d, inv; };
 /* hit_aabb (shapes.fut:114-135).  The reference leaves after the first axis with tmax <= tmin; tmin only grows and
  * tmax only shrinks from axis to axis (fmaxf/fminf drop NaN operands), so an axis that fails keeps failing and the
- * single test after the third axis gives the same boolean.  No per-axis branch: the lanes of a warp stay together. */
-LYS_D bool slab_test(const RayInv &r, float4 lo, float4 hi, float tmax) {
+ * single test after the third axis gives the same boolean.  No per-axis branch: the lanes of a warp stay together.
+ * `tn` = tmin after the third axis = max(0, the three entry distances): it does not depend on the ray's tmax. */
+LYS_D bool slab_test(const RayInv &r, float4 lo, float4 hi, float tmax, float &tn) {
     float tmin = 0.0f;
     {
         float t0 = (lo.x - r.o.x) * r.inv.x, t1 = (hi.x - r.o.x) * r.inv.x;
@@ -52,14 +52,16 @@ LYS_D bool slab_test(const RayInv &r, float4 lo, float4 hi, float tmax) {
         t1 = t1 * (1.0f + 0.001f);
         tmin = fmaxf(t0, tmin); tmax = fminf(t1, tmax);
     }
+    tn = tmin;
     return !(tmax <= tmin);
 }
-/* the same test on an octant node (lys_scene.h: near/far picked at build time as the swap above would) */
-LYS_D bool slab_test_oct(const RayInv &r, float4 nr, float4 fr, float tmax) {
+/* the same test on an octant box (lys_scene.h: near/far picked at build time as the swap above would) */
+LYS_D bool slab_test_oct(const RayInv &r, float4 nr, float4 fr, float tmax, float &tn) {
     float tmin = 0.0f;
     tmin = fmaxf((nr.x - r.o.x) * r.inv.x, tmin); tmax = fminf(((fr.x - r.o.x) * r.inv.x) * (1.0f + 0.001f), tmax);
     tmin = fmaxf((nr.y - r.o.y) * r.inv.y, tmin); tmax = fminf(((fr.y - r.o.y) * r.inv.y) * (1.0f + 0.001f), tmax);
     tmin = fmaxf((nr.z - r.o.z) * r.inv.z, tmin); tmax = fminf(((fr.z - r.o.z) * r.inv.z) * (1.0f + 0.001f), tmax);
+    tn = tmin;
     return !(tmax <= tmin);
 }
 /* hit_triangle (shapes.fut:66-86) against sorted leaf `leaf`: the plane part needs only (a, n = e1 x e2), one 32-byte
@@ -74,75 +76,123 @@ LYS_D bool leaf_test_at(const RayInv &r, const float4 *__restrict__ q, float tma
 LYS_D bool leaf_test(const RayInv &r, const float4 *__restrict__ leaf_tri, int leaf, float tmax, float &t) {
     return leaf_test_at(r, leaf_tri + 4ll * leaf, tmax, t);
 }
-/* One loop iteration = NB box stages, then one triangle stage, then a warp vote.  A lane takes part in a stage if its
- * next visit has that type, so a node whose left child is a leaf is box-tested and the leaf triangle-tested in the
- * same iteration, and the lanes of a warp meet in few, well filled stages (model: tools/simt_model.py; a loop in which
- * each lane does ONE visit per iteration issues the triangle block for 4-5 lanes in every second iteration, a
- * while-while loop makes the lanes at leaves wait for the slowest descent).  The vote keeps the warp converged at the
- * loop head -- without it the compiler threads "still at an internal node" back into the box stage, i.e. builds
- * while-while.  ALL 32 LANES OF A WARP MUST CALL THIS TOGETHER; lanes without a ray pass active = false.
- * stack[0] holds the end marker: popping needs no empty check.  Visits, their order and every comparison are those
- * of the reference's walk (see above), only the interleaving between lanes differs. */
+/* ---- the walk.  Reference order (bvh.fut:126-142): enter a node = test ITS box against the CURRENT tmax; if it passes go
+ * left, and come back for the right child when the left subtree is done; leaves are never box-tested.
+ *
+ * Pair nodes: record i holds the boxes of BOTH children of node i (lys_scene.h), so one 64-byte visit decides two of the
+ * reference's box tests and a failing child costs no visit of its own (no dependent load, no loop iteration):
+ *   - the left child is entered right after its parent passes, with the same tmax: its test here IS the reference's test;
+ *   - the right child's test belongs after the left subtree, with a tmax that can only have shrunk since.  The test is
+ *     !(fminf(T1, tmax) <= tn) with tn (entry distance, NaN-free) and T1 (scaled exit distance, NaN dropped by fminf)
+ *     independent of tmax, hence monotone in tmax: a right child that fails now fails then (it is dropped now), and one
+ *     that passes now passes then iff !(tmax_then <= tn).  So it is pushed WITH tn and re-checked against the current tmax
+ *     when popped (a compare, no memory access).  For any_hit tmax never changes: plain pop.
+ * Decisions, their order and every comparison are the reference's; hits, ties (strict t < tmax, shapes.fut:64) and the
+ * culling by the non-conservative truncated boxes (bvh.fut:105-120) are identical (parity tests, tests/test_traversal_algebra.py).
+ * Record n_nodes is a super-root: left child = node 0 (the root's own box test, bvh.fut:127), right child = the end marker,
+ * which like a leaf pointer always "passes" and is pushed: the stack needs no other sentinel.
+ *
+ * One loop iteration = TRAV_NB node stages, then one triangle stage, then a warp vote.  A lane takes part in a stage if its
+ * next visit has that type, so a node whose left child is a leaf is entered and the leaf triangle-tested in the same
+ * iteration, and the lanes of a warp meet in few, well filled stages (model: tools/simt_model.py).  The vote keeps the warp
+ * converged at the loop head -- without it the compiler threads "still at an internal node" back into the node stage, i.e.
+ * builds a while-while loop.  ALL 32 LANES OF A WARP MUST CALL THIS TOGETHER; lanes without a ray pass active = false. */
 #define TRAV_DONE ((int)0x80000000)
-#ifdef LYS_SMEM_STACK
-static __device__ __noinline__ int *trav_smem_stack() { __shared__ int s[LYS_SMEM_STACK * 128]; return s; }
-#endif
-/* PF: the right child pushed on the stack is certain to be popped later (closest hit) or likely to be (any hit); its
- * address is known now, one dependent L2 / DRAM access before it is needed.  PF = 1 asks for its node sector to be brought
- * into L1 at push time (prefetch.global.L1, no register, no scoreboard), PF = 2 for its leaf sector too.  Large scenes only:
- * on cache-resident trees the extra instructions are pure cost. */
-LYS_D void trav_prefetch(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
-/* PF = 3 (experiment): the same through the async-copy path -- a 16-byte cp.async.ca into a per-thread shared sink pulls the
- * 32-byte sector through L1 without a destination register; the sink is never read */
-LYS_D void trav_prefetch_async(const void *p) {
-    __shared__ float4 sink[128];
-    const unsigned sa = (unsigned)__cvta_generic_to_shared(&sink[threadIdx.x & 127]);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(p));
+template <bool ANY> struct TravStack;
+template <> struct TravStack<true> {          /* any_hit: node pointers only */
+    int e[TRAV_STACK + 1];
+    LYS_D void push(int &sp, int node, float) { e[sp++] = node; }
+    LYS_D int pop(int &sp, float) { return e[--sp]; }
+};
+template <> struct TravStack<false> {         /* closest_hit: (node, entry distance) */
+    int2 e[TRAV_STACK + 1];
+    LYS_D void push(int &sp, int node, float tn) { e[sp++] = make_int2(node, __float_as_int(tn)); }
+    LYS_D int pop(int &sp, float tmax) {      /* entries the shrunken tmax has cut off are skipped */
+        int2 x;
+        do { x = e[--sp]; } while (tmax <= __int_as_float(x.y));
+        return x.x;
+    }
+};
+template <bool OCT>
+LYS_D unsigned long long trav_base(const float4 *nodes, int n_nodes, const RayInv &r) {
+    unsigned long long nbase = reinterpret_cast<unsigned long long>(nodes);            /* per-lane base: record i at nbase + 64 i */
+    if (OCT) nbase += 64ull * (unsigned)(n_nodes + 1) * (unsigned)(((r.inv.x < 0.0f) ? 4 : 0) | ((r.inv.y < 0.0f) ? 2 : 0) | ((r.inv.z < 0.0f) ? 1 : 0));   /* `nodes` = nodes_oct */
+    asm volatile("" : "+l"(nbase));      /* keep the sum in a register pair: one IMAD.WIDE per node address */
+    return nbase;
 }
-template <bool ANY, int NB, bool OCT, int PF = 0>
+/* one node stage: cur >= 0 on entry */
+template <bool ANY, bool OCT>
+LYS_D void trav_node_stage(const RayInv &r, unsigned long long nbase, float tmax, int &cur, int &sp, TravStack<ANY> &st) {
+    const float4 *q = reinterpret_cast<const float4 *>(nbase + 64ull * (unsigned)cur);
+    const float4 l0 = __ldg(q), l1 = __ldg(q + 1), r0 = __ldg(q + 2), r1 = __ldg(q + 3);
+    const int lc = __float_as_int(l0.w), rc = __float_as_int(l1.w);
+    float tl, tr;
+    bool pl = OCT ? slab_test_oct(r, l0, l1, tmax, tl) : slab_test(r, l0, l1, tmax, tl);
+    bool pr = OCT ? slab_test_oct(r, r0, r1, tmax, tr) : slab_test(r, r0, r1, tmax, tr);
+    if (lc < 0) pl = true;                                   /* leaves (and the end marker) are not box-tested */
+    if (rc < 0) { pr = true; tr = -LYS_INF; }
+    if (pl) { cur = lc; if (pr) st.push(sp, rc, tr); }       /* left child first, right child waits */
+    else if (pr) cur = rc;
+    else cur = st.pop(sp, tmax);
+}
+/* Record layouts (lys_scene.h), picked per scene by the build:
+ *   LAY_SINGLE    one box per record, octant copies: small trees (issue bound, half the child slots are leaves whose box
+ *                 slot a pair record would test for nothing: measured 5-9 % faster than pair records on CornellBox / MirrorBox)
+ *   LAY_PAIR_OCT  pair records, octant copies
+ *   LAY_PAIR      pair records, one copy, box test with selects (scenes whose octant copies would not stay in L2) */
+enum { LAY_SINGLE = 0, LAY_PAIR_OCT = 1, LAY_PAIR = 2 };
+#define TRAV_NB 2          /* node stages per loop iteration: 2 measured best on every layout and scene size (profiles/README.md 8.2) */
+template <bool ANY, int LAY>
 LYS_D int traverse(const float4 *__restrict__ nodes, const float4 *__restrict__ leaf_tri, int n_nodes, bool active,
                    V3 o, V3 d, float tmax, float &t_hit) {
     RayInv r; r.o = o; r.d = d; r.inv = v3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
-    unsigned long long nbase = reinterpret_cast<unsigned long long>(nodes);            /* per-lane base: node i at nbase + 32 i */
-    if (OCT) nbase += 32ull * (unsigned)n_nodes * (unsigned)(((r.inv.x < 0.0f) ? 4 : 0) | ((r.inv.y < 0.0f) ? 2 : 0) | ((r.inv.z < 0.0f) ? 1 : 0));   /* `nodes` = nodes_oct */
-    asm volatile("" : "+l"(nbase));      /* keep the sum in a register pair: one IMAD.WIDE per node address */
-    int stack[TRAV_STACK + 1];
     int closest = -1;
-#ifdef LYS_SMEM_STACK      /* experiment: the first LYS_SMEM_STACK levels of the stack in shared memory (128-thread CTAs), the rest local */
-    int *const ss = trav_smem_stack() + threadIdx.x;
-#define TRAV_PUSH(v) do { if (sp < LYS_SMEM_STACK) ss[sp * 128] = (v); else stack[sp - LYS_SMEM_STACK] = (v); sp++; } while (0)
-#define TRAV_POP() (--sp, (sp < LYS_SMEM_STACK) ? ss[sp * 128] : stack[sp - LYS_SMEM_STACK])
-    ss[0] = TRAV_DONE;
-#else
-#define TRAV_PUSH(v) (stack[sp++] = (v))
-#define TRAV_POP() (stack[--sp])
-    stack[0] = TRAV_DONE;
-#endif
-    int sp = 1;
-    int cur = (active && n_nodes > 0) ? 0 : TRAV_DONE;   /* internal node to enter (>= 0), leaf pointer (~leaf) or TRAV_DONE */
-    do {
+    if (LAY == LAY_SINGLE) {
+        /* one box per visit, the reference's walk with a stack instead of parent pointers: pushing the right child while
+         * descending left takes the same decisions in the same order.  stack[0] holds the end marker. */
+        unsigned long long nbase = reinterpret_cast<unsigned long long>(nodes);        /* per-lane base: node i at nbase + 32 i */
+        nbase += 32ull * (unsigned)n_nodes * (unsigned)(((r.inv.x < 0.0f) ? 4 : 0) | ((r.inv.y < 0.0f) ? 2 : 0) | ((r.inv.z < 0.0f) ? 1 : 0));
+        asm volatile("" : "+l"(nbase));
+        int stack[TRAV_STACK + 1];
+        stack[0] = TRAV_DONE;
+        int sp = 1;
+        int cur = (active && n_nodes > 0) ? 0 : TRAV_DONE;
+        do {
 #pragma unroll
-        for (int k = 0; k < NB; k++) {
-            if (cur >= 0) {
-                const float4 *q = reinterpret_cast<const float4 *>(nbase + 32ull * (unsigned)cur);
-                float4 lo = __ldg(q), hi = __ldg(q + 1);
-                if (OCT ? slab_test_oct(r, lo, hi, tmax) : slab_test(r, lo, hi, tmax)) {
-                    const int rc = __float_as_int(hi.w);
-                    TRAV_PUSH(rc);                            /* right child waits */
-                    if ((PF == 1 || PF == 2) && rc >= 0) trav_prefetch(reinterpret_cast<const void *>(nbase + 32ull * (unsigned)rc));
-                    if (PF == 2 && rc < 0) trav_prefetch(leaf_tri + 4ll * ~rc);
-                    if (PF == 3 && rc >= 0) trav_prefetch_async(reinterpret_cast<const void *>(nbase + 32ull * (unsigned)rc));
-                    cur = __float_as_int(lo.w);               /* left child first */
-                } else cur = TRAV_POP();
+            for (int k = 0; k < TRAV_NB; k++) {
+                if (cur >= 0) {
+                    const float4 *q = reinterpret_cast<const float4 *>(nbase + 32ull * (unsigned)cur);
+                    float4 lo = __ldg(q), hi = __ldg(q + 1);
+                    float tn;
+                    if (slab_test_oct(r, lo, hi, tmax, tn)) {
+                        stack[sp++] = __float_as_int(hi.w);       /* right child waits */
+                        cur = __float_as_int(lo.w);               /* left child first */
+                    } else cur = stack[--sp];
+                }
             }
-        }
-        if ((unsigned)cur > (unsigned)TRAV_DONE) {            /* a leaf pointer */
-            float t;
-            if (leaf_test(r, leaf_tri, ~cur, tmax, t)) { closest = ~cur; tmax = t; }
-            cur = (ANY && closest >= 0) ? TRAV_DONE : TRAV_POP();       /* any_hit stops at the first hit (bvh.fut:152) */
-        }
-    } while (__any_sync(0xffffffffu, cur != TRAV_DONE));
-    if (PF == 3) asm volatile("cp.async.wait_all;" ::: "memory");
+            if ((unsigned)cur > (unsigned)TRAV_DONE) {            /* a leaf pointer */
+                float t;
+                if (leaf_test(r, leaf_tri, ~cur, tmax, t)) { closest = ~cur; tmax = t; }
+                cur = (ANY && closest >= 0) ? TRAV_DONE : stack[--sp];      /* any_hit stops at the first hit (bvh.fut:152) */
+            }
+        } while (__any_sync(0xffffffffu, cur != TRAV_DONE));
+    } else {
+        constexpr bool OCT = LAY == LAY_PAIR_OCT;
+        const unsigned long long nbase = trav_base<OCT>(nodes, n_nodes, r);
+        TravStack<ANY> st;
+        int sp = 0;
+        int cur = (active && n_nodes > 0) ? n_nodes : TRAV_DONE;   /* internal node to enter (>= 0; n_nodes = the super-root), leaf pointer (~leaf) or TRAV_DONE */
+        do {
+#pragma unroll
+            for (int k = 0; k < TRAV_NB; k++)
+                if (cur >= 0) trav_node_stage<ANY, OCT>(r, nbase, tmax, cur, sp, st);
+            if ((unsigned)cur > (unsigned)TRAV_DONE) {            /* a leaf pointer */
+                float t;
+                if (leaf_test(r, leaf_tri, ~cur, tmax, t)) { closest = ~cur; tmax = t; }
+                cur = (ANY && closest >= 0) ? TRAV_DONE : st.pop(sp, tmax);       /* any_hit stops at the first hit (bvh.fut:152) */
+            }
+        } while (__any_sync(0xffffffffu, cur != TRAV_DONE));
+    }
     t_hit = tmax;
     return closest;
 }
@@ -165,11 +215,26 @@ LYS_DN void camera_sample(const FrameParams &fp, int col, int row, uint32_t &rng
     o = fp.cam_origin + lens_offset;
     d = normalise(((fp.llc + px * fp.horizontal) + py * fp.vertical) - o);
 }
+/* Path id -> pixel.  Path ids are an implementation detail (everything a pixel's value depends on is keyed by the PIXEL index:
+ * rng stream integrator.fut:109-114, framebuffer position), so they are laid out for the hardware: a warp's 32 consecutive
+ * ids cover an 8 x 4 pixel tile instead of a 32 x 1 strip -- camera rays of a warp walk the same nodes, and the paths they
+ * start stay close.  The local rows (this rank's rows of the interleaved partition) are cut into bands of 4; a band is
+ * gw / 8 full tiles, then the gw % 8 leftover columns; an incomplete last band is walked row by row.  A bijection for any size. */
+LYS_HDI void path_tile(int gw, int lrows, int pid, int &col, int &rl) {
+    const int band_sz = 4 * gw;
+    const int band = pid / band_sz, q = pid - band * band_sz;
+    if (band * 4 + 4 > lrows) { const int r = q / gw; rl = band * 4 + r; col = q - r * gw; return; }
+    const int full = gw >> 3;
+    if (q < 32 * full) { const int t = q >> 5, k = q & 31; col = t * 8 + (k & 7); rl = band * 4 + (k >> 3); return; }
+    const int rem = gw & 7, q2 = q - 32 * full, r = q2 / rem;
+    rl = band * 4 + r; col = full * 8 + (q2 - r * rem);
+}
 LYS_D int local_to_pixel(const FrameParams &fp, int pid, int &col, int &row) {
-    int rl = pid / fp.gw; col = pid - rl * fp.gw; row = rl * fp.world + fp.rank;
+    int rl; path_tile(fp.gw, fp.n_local / fp.gw, pid, col, rl);
+    row = rl * fp.world + fp.rank;
     return row * fp.gw + col;
 }
-
+LYS_D size_t probe_index(const FrameParams &fp, int pid) { int c, r; return (size_t)local_to_pixel(fp, pid, c, r); }   /* probes are exported in pixel order */
 __global__ void __launch_bounds__(256) k_generate(const __grid_constant__ FrameParams fp, PassBuffers b) {
     int pid = blockIdx.x * blockDim.x + threadIdx.x;
     if (pid == 0) {
@@ -188,7 +253,7 @@ __global__ void __launch_bounds__(256) k_generate(const __grid_constant__ FrameP
     b.acc[pid] = make_float4(0.0f, 0.0f, LYS_INF, 0.0f);
     b.chan[pid] = (uint8_t)ch;
     b.queue[0][pid] = pid;
-    if (b.probe_rad) for (int k = 0; k < LYS_MAX_PATH_LEN; k++) { b.probe_rad[(size_t)pid * 16 + k] = 0.0f; b.probe_dist[(size_t)pid * 16 + k] = LYS_INF; }
+    if (b.probe_rad) for (int k = 0; k < LYS_MAX_PATH_LEN; k++) { b.probe_rad[(size_t)ix * 16 + k] = 0.0f; b.probe_dist[(size_t)ix * 16 + k] = LYS_INF; }
 }
 
 /* ------------------------------------------------------------------ lights */
@@ -232,9 +297,7 @@ LYS_D float balance1(float pf, float pg) { return 1.0f * pf / (1.0f * pf + 1.0f 
 
 /* ------------------------------------------------------------------ shade
  * One vertex = prologue (t of the winning leaf, material, frame) + light sample + BSDF-MIS sample + continuation.
- * k_shade runs all of it (see its header for the CTA-level arrangements).  Three phase kernels (k_shade_light /
- * k_shade_bsdf / k_shade_cont, LYS_SHADE_SPLIT) that each redo the small prologue and exchange partial results through
- * per-slot scratch date from when the monolithic kernel was instruction-fetch bound; arithmetic is identical. */
+ * k_shade runs all of it (see its header for the CTA-level arrangements). */
 struct VertexCtx {
     int pid, leaf;
     V3 o, d, pos, n, wo, wo_l;
@@ -378,9 +441,7 @@ LYS_D void shade_compact(const PassBuffers &b, int bounce, bool alive, int pid, 
  *    (bsdf_choose); refraction samples are drawn in place, reflection samples are queued in shared memory and drawn
  *    after a barrier by the first threads of the CTA, one queue entry per thread (dense warps).  Same inputs, same
  *    arithmetic, another thread.  The rng state after a reflection sample is its two draws further (:283-286);
- *  - for bounces >= 1 the slots are walked in the order k_trace left (hits first): warps are all-hit or all-miss;
- *  - optional block barriers between the phases (bars bits 0, 1) kept the warps of a CTA fetching the same code while the
- *    kernel was larger than the instruction cache with the reflection path inline in every warp; off by default now. */
+ *  - for bounces >= 1 the slots are walked in the order k_trace left (hits first): warps are all-hit or all-miss. */
 template <int T>
 struct ShadeShared {
     float res[6][2 * T];      /* slot k * T + tid: sample k of the thread (in: wo_l, roughness, rng; out: DirSample local) */
@@ -421,10 +482,10 @@ LYS_D void shade_draw_or_queue(SH &sh, bool want, int slot, const VertexCtx &v, 
     }
 }
 #ifndef LYS_SHADE_MINB
-#define LYS_SHADE_MINB(T) ((T) == 256 ? 3 : 2048 / (T) / 2)      /* 256 threads: 3 CTAs / 80 registers (no spills) measured best; else 64 registers */
+#define LYS_SHADE_MINB(T) 3      /* 256 threads: 3 CTAs per SM / 80 registers measured best */
 #endif
 template <int SHADE_THREADS>
-__global__ void __launch_bounds__(SHADE_THREADS, LYS_SHADE_MINB(SHADE_THREADS)) k_shade(SceneDev sc, const __grid_constant__ FrameParams fp, PassBuffers b, int bounce, int bars) {
+__global__ void __launch_bounds__(SHADE_THREADS, LYS_SHADE_MINB(SHADE_THREADS)) k_shade(SceneDev sc, const __grid_constant__ FrameParams fp, PassBuffers b, int bounce, int ordered) {
     __shared__ ShadeShared<SHADE_THREADS> sh;
     const int count = b.counts[bounce];
     const int stride = gridDim.x * blockDim.x;
@@ -433,7 +494,7 @@ __global__ void __launch_bounds__(SHADE_THREADS, LYS_SHADE_MINB(SHADE_THREADS)) 
     __syncthreads();
     for (int b0 = blockIdx.x * blockDim.x; b0 < count; b0 += stride) {
         const bool valid = b0 + (int)threadIdx.x < count;
-        const int i = !valid ? 0 : (bars & 4) ? b.order[bounce & 1][b0 + threadIdx.x] : b0 + (int)threadIdx.x;      /* hits first: warps are all-hit or all-miss */
+        const int i = !valid ? 0 : ordered ? b.order[bounce & 1][b0 + threadIdx.x] : b0 + (int)threadIdx.x;      /* hits first: warps are all-hit or all-miss */
         bool alive = false, hit = false; int pid = -1; unsigned n_vert = 0, n_shadow = 0;
         float4 next_o = make_float4(0.0f, 0.0f, 0.0f, 0.0f), next_d = next_o; float next_dist = 0.0f;
         VertexCtx v;
@@ -442,11 +503,9 @@ __global__ void __launch_bounds__(SHADE_THREADS, LYS_SHADE_MINB(SHADE_THREADS)) 
         LightD l;
         if (valid) hit = shade_prologue(sc, b, bounce, i, v);
         const bool lit = hit && nl > 0;
-        if (bars & 1) __syncthreads();                                    /* lockstep only (instruction cache) */
         if (lit) shade_pick_light(sc, fp, b, v, nl, l);
         if (lit) shade_light_sample(v, l, cL, rec_d1, flags);
         if (hit) b.sh_d1[i] = rec_d1;                                     /* records leave the registers as soon as they are complete */
-        if (bars & 2) __syncthreads();                                    /* lockstep only */
         /* both sample_dir calls of the vertex: the MIS sample (direct.fut:83) and the continuation (integrator.fut:56) */
         bool metal1, metal2;
         shade_draw_or_queue(sh, lit, threadIdx.x, v, v.rng, metal1);
@@ -481,92 +540,11 @@ __global__ void __launch_bounds__(SHADE_THREADS, LYS_SHADE_MINB(SHADE_THREADS)) 
         __syncthreads();                                                  /* sh is reused by the next iteration */
     }
 }
-/* phase kernels: light sample */
-__global__ void __launch_bounds__(128, 8) k_shade_light(SceneDev sc, const __grid_constant__ FrameParams fp, PassBuffers b, int bounce) {
-    const int count = b.counts[bounce];
-    const int stride = gridDim.x * blockDim.x;
-    const int nl = fp.n_scene_lights + ((fp.tx_kind == 0) ? 0 : 8);
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
-        VertexCtx v;
-        float cL = 0.0f; int flags = 0;
-        float4 rec_d1 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        if (shade_prologue(sc, b, bounce, i, v)) {
-            LightD l;
-            shade_pick_light(sc, fp, b, v, nl, l);
-            shade_light_sample(v, l, cL, rec_d1, flags);
-        }
-        b.sh_d1[i] = rec_d1;
-        b.tmp_a[i] = make_float2(cL, __int_as_float(flags));
-    }
-}
-/* phase kernels: BSDF-MIS sample (advances the rng; the new state travels in tmp_b.z) */
-__global__ void __launch_bounds__(128, 8) k_shade_bsdf(SceneDev sc, const __grid_constant__ FrameParams fp, PassBuffers b, int bounce) {
-    const int count = b.counts[bounce];
-    const int stride = gridDim.x * blockDim.x;
-    const int nl = fp.n_scene_lights + ((fp.tx_kind == 0) ? 0 : 8);
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
-        VertexCtx v;
-        float cB = 0.0f; int flags = 0;
-        float4 rec_d2 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        if (shade_prologue(sc, b, bounce, i, v)) {
-            LightD l;
-            shade_pick_light(sc, fp, b, v, nl, l);
-            shade_bsdf_light_sample(v, l, cB, rec_d2, flags);
-        }
-        b.sh_d2[i] = rec_d2;
-        b.tmp_b[i] = make_float4(cB, __int_as_float(flags), __uint_as_float(v.rng), 0.0f);
-    }
-}
-/* phase kernels: records + continuation + compaction; `split` = the two kernels above ran for this bounce */
-__global__ void __launch_bounds__(128, 8) k_shade_cont(SceneDev sc, const __grid_constant__ FrameParams fp, PassBuffers b, int bounce, int split) {
-    const int count = b.counts[bounce];
-    const int lane = threadIdx.x & 31;
-    const int stride = gridDim.x * blockDim.x;
-    for (int i0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31); i0 < count; i0 += stride) {
-        const int i = i0 + lane;
-        bool alive = false; int pid = -1; unsigned n_vert = 0, n_shadow = 0;
-        float4 next_o = make_float4(0.0f, 0.0f, 0.0f, 0.0f), next_d = next_o; float next_dist = 0.0f;
-        if (i < count) {
-            VertexCtx v;
-            if (shade_prologue(sc, b, bounce, i, v)) {
-                float cL = 0.0f, cB = 0.0f; int flags = 0;
-                if (split) {
-                    float2 ta = b.tmp_a[i]; float4 tb = b.tmp_b[i];
-                    cL = ta.x; cB = tb.x; flags = __float_as_int(ta.y) | __float_as_int(tb.y);
-                    v.rng = __float_as_uint(tb.z);
-                } else { b.sh_d1[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f); b.sh_d2[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f); }
-                alive = shade_finish(fp, b, bounce, i, v, cL, cB, flags, next_o, next_d, next_dist);
-                n_vert = 1; n_shadow = (flags & 1) + ((flags >> 1) & 1);
-            } else shade_miss(fp, b, i, v);
-            pid = v.pid;
-        }
-        shade_compact(b, bounce, alive, pid, next_o, next_d, next_dist, n_vert, n_shadow);
-    }
-}
-
 /* ------------------------------------------------------------------ trace: all BVH traversal of one bounce boundary
  * One persistent launch resolves the shadow rays of bounce `bounce` (connect) and the closest hits of bounce
  * `bounce + 1` (extend); both only read the scene and touch disjoint path state.  bounce = -1: primary rays only.
- *
- * Every lane runs a small state machine: one BVH node visit (box test or triangle test) per step, with the same
- * left-first order as traverse<>.  Rays need very different numbers of steps, so a lane that finishes its item
- * does not wait for the warp: when fewer than TRACE_REFILL lanes are busy the idle lanes pull the next items of
- * the warp's own contiguous slice of the work list (ballot + prefix popcount; no atomics, no shared memory).
- * A connect item carries up to two shadow rays; they are traced back to back by the same lane, then the vertex
- * radiance is accumulated (direct.fut:121-122, integrator.fut:51-55). */
-#define TRACE_REFILL 20
-struct LaneState {
-    int item;            /* work index, -1 = idle */
-    int phase;           /* 0 extend ray, 1 first shadow ray, 2 second shadow ray */
-    int cur, sp, closest;
-    float tmax;
-    V3 o, d, inv;
-    int flags; float cL, cB, em, dist, L;      /* connect item */
-};
-LYS_D void lane_start_ray(LaneState &st, V3 o, V3 d, float tmax) {
-    st.o = o; st.d = d; st.inv = v3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
-    st.tmax = tmax; st.cur = 0; st.sp = 0; st.closest = -1;
-}
+ * A connect item carries up to two shadow rays; after them the vertex radiance is accumulated (direct.fut:121-122,
+ * integrator.fut:51-55). */
 LYS_D void connect_finish(const FrameParams &fp, const PassBuffers &b, int bounce, int slot, int flags, float L, float B, float em, float dist, float miss_r) {
     int pid = b.queue[bounce & 1][slot];
     float r;
@@ -583,115 +561,29 @@ LYS_D void connect_finish(const FrameParams &fp, const PassBuffers &b, int bounc
     float inten = r * fp.intensity_factor;
     if (inten > 0.0f && dist > 0.5f && dist < 10.0f && dist < a.z) { a.z = dist; a.w = inten; }
     b.acc[pid] = a;
-    if (b.probe_rad) { b.probe_rad[(size_t)pid * 16 + bounce] = r; b.probe_dist[(size_t)pid * 16 + bounce] = dist; }
+    if (b.probe_rad) { const size_t ix = probe_index(fp, pid); b.probe_rad[ix * 16 + bounce] = r; b.probe_dist[ix * 16 + bounce] = dist; }
 }
-__global__ void __launch_bounds__(128) k_trace_refill(SceneDev sc, const __grid_constant__ FrameParams fp, PassBuffers b, int bounce) {
-    const int n_ext = (bounce + 1 < fp.path_len) ? b.counts[bounce + 1] : 0;
-    const int n_con = (bounce >= 0) ? b.counts[bounce] : 0;
-    const int total = n_ext + n_con;
-    const int lane = threadIdx.x & 31;
-    const unsigned lt_mask = (1u << lane) - 1u;
-    const int n_warps = gridDim.x * (blockDim.x >> 5);
-    const int gwarp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    int per = (total + n_warps - 1) / n_warps;
-    per = max(32, (per + 31) & ~31);
-    long long beg = (long long)gwarp * per;
-    if (beg >= total) return;
-    int cursor = (int)beg;
-    const int range_end = (int)min((long long)total, beg + per);
-    const float4 *__restrict__ nodes = sc.nodes;
-    const float4 *__restrict__ leaf_tri = sc.leaf_tri;
-    int stack[TRAV_STACK];
-    LaneState st; st.item = -1; st.phase = 0; st.cur = 0; st.sp = 0; st.closest = -1; st.tmax = 0.0f;
-    st.o = v3(0, 0, 0); st.d = st.o; st.inv = st.o; st.flags = 0; st.cL = st.cB = st.em = st.dist = st.L = 0.0f;
-    while (true) {
-        /* ---- refill idle lanes from the warp's slice */
-        for (int round = 0; round < 4; round++) {
-            unsigned idle = __ballot_sync(0xffffffffu, st.item < 0);
-            if (!idle || cursor >= range_end) break;
-            int mine = cursor + __popc(idle & lt_mask);
-            cursor = min(range_end, cursor + __popc(idle));
-            if (st.item < 0 && mine < range_end) {
-                if (mine < n_ext) {                                        /* extend item of bounce + 1 */
-                    float4 ro = b.ray_o[(bounce + 1) & 1][mine], rd = b.ray_d[(bounce + 1) & 1][mine];
-                    st.item = mine; st.phase = 0;
-                    lane_start_ray(st, v3(ro.x, ro.y, ro.z), v3(rd.x, rd.y, rd.z), FLT_MAX);
-                } else {                                                   /* connect item of bounce */
-                    int slot = mine - n_ext;
-                    float4 ro = b.sh_o[slot], rc = b.sh_c[slot];
-                    int flags = __float_as_int(ro.w);
-                    if ((flags & 4) || !(flags & 3)) connect_finish(fp, b, bounce, slot, flags, 0.0f, 0.0f, rc.z, rc.w, rc.z);
-                    else {
-                        st.item = mine; st.flags = flags; st.cL = rc.x; st.cB = rc.y; st.em = rc.z; st.dist = rc.w; st.L = 0.0f;
-                        float4 dd = (flags & 1) ? b.sh_d1[slot] : b.sh_d2[slot];
-                        st.phase = (flags & 1) ? 1 : 2;
-                        lane_start_ray(st, v3(ro.x, ro.y, ro.z), v3(dd.x, dd.y, dd.z), dd.w);
-                    }
-                }
-            }
-        }
-        unsigned busy = __ballot_sync(0xffffffffu, st.item >= 0);
-        if (!busy) { if (cursor >= range_end) break; else continue; }
-        /* ---- traversal steps until too many lanes have gone idle (or to completion once the slice is empty) */
-        const int keep = (cursor >= range_end) ? 1 : TRACE_REFILL;
-        do {
-            if (st.item >= 0) {
-                bool done = false;
-                if (st.cur >= 0) {
-                    float4 lo = __ldg(nodes + 2ll * st.cur), hi = __ldg(nodes + 2ll * st.cur + 1);
-                    RayInv r; r.o = st.o; r.d = st.d; r.inv = st.inv;
-                    if (slab_test(r, lo, hi, st.tmax)) { stack[st.sp++] = __float_as_int(hi.w); st.cur = __float_as_int(lo.w); }
-                    else if (st.sp == 0) done = true;
-                    else st.cur = stack[--st.sp];
-                } else {
-                    RayInv r; r.o = st.o; r.d = st.d; r.inv = st.inv;
-                    float t;
-                    bool hit = leaf_test(r, leaf_tri, ~st.cur, st.tmax, t);
-                    if (hit) { st.closest = ~st.cur; st.tmax = t; }
-                    if (hit && st.phase != 0) done = true;                 /* any_hit stops at the first hit (bvh.fut:152) */
-                    else if (st.sp == 0) done = true;
-                    else st.cur = stack[--st.sp];
-                }
-                if (done) {
-                    if (st.phase == 0) { b.hit[st.item] = st.closest; st.item = -1; }
-                    else {
-                        const int slot = st.item - n_ext;
-                        const bool visible = st.closest < 0;
-                        if (st.phase == 1) {
-                            st.L = visible ? st.cL : 0.0f;
-                            if (st.flags & 2) {
-                                float4 d2 = b.sh_d2[slot];
-                                st.phase = 2;
-                                lane_start_ray(st, st.o, v3(d2.x, d2.y, d2.z), d2.w);
-                            } else { connect_finish(fp, b, bounce, slot, st.flags, st.L, 0.0f, st.em, st.dist, 0.0f); st.item = -1; }
-                        } else {
-                            connect_finish(fp, b, bounce, slot, st.flags, st.L, visible ? st.cB : 0.0f, st.em, st.dist, 0.0f);
-                            st.item = -1;
-                        }
-                    }
-                }
-            }
-            busy = __ballot_sync(0xffffffffu, st.item >= 0);
-        } while (__popc(busy) >= keep);
-    }
-}
-
-/* The default variant: a warp owns 32 consecutive items per grid-stride step and runs the vote-synchronised traverse<>
- * loops on them.  Measured on B200 (CornellBox 1080p) it beats the refill variant above, whose every refill stalls the
- * warp on dependent queue -> ray loads; the refill kernel is kept selectable (LYS_TRACE_MODE=1) and is parity-tested too.
+/* A warp owns 32 consecutive items per grid-stride step and runs the vote-synchronised traverse<> loops on them.  Two
+ * lane-refill variants (a one-visit-per-step state machine, and this staged loop with a refill round between iterations)
+ * were built, parity-tested and measured: -38 % and +3 % on the 1 M-triangle scene, slower on every bundled scene
+ * (profiles/README.md 7.2, 8.1); they are no longer part of the build.
  * `ordered` bit 0: append the slots of bounce + 1 to the hits-first order list and walk this bounce's vertices in theirs. */
+/* resident CTAs of 128 threads per SM the traversal kernels are compiled for.  Small scenes are issue bound: 10 CTAs / 48
+ * registers, no spills.  Pair layouts are latency bound (dependent L2 / DRAM record loads): more warps in flight win even
+ * with a few registers spilled to L1 -- 12 CTAs (40 registers) with octant copies, 16 (32 registers) on the large scenes
+ * (measured: profiles/README.md 8.2). */
 #ifndef LYS_TRACE_MINB
-#define LYS_TRACE_MINB 10     /* <= 51 registers: 10 CTAs of 128 threads per SM */
+#define LYS_TRACE_MINB(LAY) ((LAY) == LAY_PAIR ? 16 : (LAY) == LAY_PAIR_OCT ? 12 : 10)
 #endif
-template <int NB, bool OCT, int PF>
-__global__ void __launch_bounds__(128, LYS_TRACE_MINB) k_trace(SceneDev sc, const __grid_constant__ FrameParams fp, PassBuffers b, int bounce, int ordered) {
+template <int LAY>
+__global__ void __launch_bounds__(128, LYS_TRACE_MINB(LAY)) k_trace(SceneDev sc, const __grid_constant__ FrameParams fp, PassBuffers b, int bounce, int ordered) {
     const int n_ext = (bounce + 1 < fp.path_len) ? b.counts[bounce + 1] : 0;
     const int n_con = (bounce >= 0) ? b.counts[bounce] : 0;
     const int total = n_ext + n_con;
     const int stride = gridDim.x * blockDim.x;
     const int n_nodes = (int)sc.n_tris - 1;
     const int lane = threadIdx.x & 31;
-    const float4 *__restrict__ nodes = OCT ? sc.nodes_oct : sc.nodes;
+    const float4 *__restrict__ nodes = (LAY == LAY_PAIR) ? sc.nodes : sc.nodes_oct;
     /* warp-uniform loop (traverse<> votes): a warp owns 32 consecutive items; only the warp that straddles n_ext mixes kinds */
     for (int i0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31); i0 < total; i0 += stride) {
         const int i = i0 + lane;
@@ -700,7 +592,7 @@ __global__ void __launch_bounds__(128, LYS_TRACE_MINB) k_trace(SceneDev sc, cons
             float4 ro = make_float4(0.0f, 0.0f, 0.0f, 0.0f), rd = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
             if (is_ext) { ro = b.ray_o[(bounce + 1) & 1][i]; rd = b.ray_d[(bounce + 1) & 1][i]; }
             float t;
-            int h = traverse<false, NB, OCT, PF>(nodes, sc.leaf_tri, n_nodes, is_ext, v3(ro.x, ro.y, ro.z), v3(rd.x, rd.y, rd.z), FLT_MAX, t);
+            int h = traverse<false, LAY>(nodes, sc.leaf_tri, n_nodes, is_ext, v3(ro.x, ro.y, ro.z), v3(rd.x, rd.y, rd.z), FLT_MAX, t);
             if (is_ext) b.hit[i] = h;
             /* processing order of shade(bounce + 1): hits from the front, misses from the back (one atomic per warp and kind) */
             if (ordered) {                     /* not for camera rays (their misses are whole warps already: shade(0) walks the slots in order) */
@@ -726,13 +618,13 @@ __global__ void __launch_bounds__(128, LYS_TRACE_MINB) k_trace(SceneDev sc, cons
             if (__any_sync(0xffffffffu, need1)) {
                 float4 d1 = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
                 if (need1) d1 = b.sh_d1[slot];
-                int h = traverse<true, NB, OCT, PF>(nodes, sc.leaf_tri, n_nodes, need1, o, v3(d1.x, d1.y, d1.z), d1.w, t);
+                int h = traverse<true, LAY>(nodes, sc.leaf_tri, n_nodes, need1, o, v3(d1.x, d1.y, d1.z), d1.w, t);
                 if (need1 && h < 0) L = rc.x;
             }
             if (__any_sync(0xffffffffu, need2)) {
                 float4 d2 = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
                 if (need2) d2 = b.sh_d2[slot];
-                int h = traverse<true, NB, OCT, PF>(nodes, sc.leaf_tri, n_nodes, need2, o, v3(d2.x, d2.y, d2.z), d2.w, t);
+                int h = traverse<true, LAY>(nodes, sc.leaf_tri, n_nodes, need2, o, v3(d2.x, d2.y, d2.z), d2.w, t);
                 if (need2 && h < 0) B = rc.y;
             }
             if (is_con) connect_finish(fp, b, bounce, slot, flags, L, B, rc.z, rc.w, rc.z);
@@ -740,176 +632,11 @@ __global__ void __launch_bounds__(128, LYS_TRACE_MINB) k_trace(SceneDev sc, cons
     }
 }
 
-/* ------------------------------------------------------------------ staged traversal with lane refill (LYS_TRACE_MODE=2)
- * EXPERIMENTAL, off by default.  Written after the GPU budget of round 1 was spent: validated bit for bit on the CPU SIMT
- * emulator of the test-suite (a fiber-per-thread host build of these sources), NOT yet run or timed on a GPU.
- *
- * Why: on large scenes the walks of one warp's rays differ wildly in length (1 M triangles: mean 83 visits, max 781 on
- * bounce 1), so the vote-synchronised loop of traverse<> runs every warp as long as its longest ray: 12.8 of 32 threads
- * active.  k_trace_refill keeps lanes busy but pays with a one-visit-per-step state machine (measured slower on every scene).
- * This kernel keeps traverse<>'s staged iteration (NB box stages, one triangle stage, one vote) and adds a refill round
- * between iterations: when fewer than `keep` lanes are busy and the warp's slice of the queue is not exhausted, finished
- * lanes store their hit (and append to the hits-first order list) and pull the next rays of the slice.  tools/simt_model.py
- * (`refill_cost`) puts the saving at ~40 % of the issued instructions of the incoherent bounces on the 1 M-triangle scene.
- * Per-lane visits, their order and every comparison are those of traverse<>; only which lane walks which ray changes.
- * The shadow rays of the bounce go through the same scheme (second loop). */
-template <int NB, bool OCT>
-__global__ void __launch_bounds__(128, LYS_TRACE_MINB) k_trace_sr(SceneDev sc, const __grid_constant__ FrameParams fp, PassBuffers b, int bounce, int ordered, int keep) {
-    const int n_ext = (bounce + 1 < fp.path_len) ? b.counts[bounce + 1] : 0;
-    const int n_con = (bounce >= 0) ? b.counts[bounce] : 0;
-    const int stride = gridDim.x * blockDim.x;
-    const int n_nodes = (int)sc.n_tris - 1;
-    const int lane = threadIdx.x & 31;
-    const unsigned lt = (1u << lane) - 1u;
-    const float4 *__restrict__ nodes = OCT ? sc.nodes_oct : sc.nodes;
-    const float4 *__restrict__ leaf_tri = sc.leaf_tri;
-    /* ---- closest hits of bounce + 1: every warp owns one contiguous slice of the queue */
-    {
-        const int n_warps = gridDim.x * (blockDim.x >> 5);
-        const int gwarp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-        const long long per = max(32ll, (((long long)n_ext + n_warps - 1) / n_warps + 31) & ~31ll);
-        int cursor = (int)min((long long)n_ext, (long long)gwarp * per);
-        const int end = (int)min((long long)n_ext, (long long)gwarp * per + per);
-        int stack[TRAV_STACK + 1];
-        stack[0] = TRAV_DONE;
-        int sp = 1, cur = TRAV_DONE, item = -1, closest = -1;
-        float tmax = FLT_MAX;
-        RayInv r; r.o = v3(0.0f, 0.0f, 0.0f); r.d = v3(1.0f, 1.0f, 1.0f); r.inv = r.d;
-        unsigned long long nbase = reinterpret_cast<unsigned long long>(nodes);
-        while (true) {
-            const unsigned busy = __ballot_sync(0xffffffffu, cur != TRAV_DONE);
-            if (busy == 0u || (cursor < end && __popc(busy) < keep)) {
-                /* refill round: retire the finished lanes, then hand the idle lanes the next rays of the slice */
-                const bool fin = item >= 0 && cur == TRAV_DONE;
-                if (fin) b.hit[item] = closest;
-                if (ordered) {                  /* processing order of shade(bounce + 1): hits from the front, misses from the back */
-                    const bool isH = fin && closest >= 0, isM = fin && closest < 0;
-                    const unsigned mh = __ballot_sync(0xffffffffu, isH), mm = __ballot_sync(0xffffffffu, isM);
-                    int bh = 0, bm = 0;
-                    if (lane == 0) { if (mh) bh = atomicAdd(&b.split[2 * (bounce + 1)], __popc(mh)); if (mm) bm = atomicAdd(&b.split[2 * (bounce + 1) + 1], __popc(mm)); }
-                    bh = __shfl_sync(0xffffffffu, bh, 0); bm = __shfl_sync(0xffffffffu, bm, 0);
-                    if (isH) b.order[(bounce + 1) & 1][bh + __popc(mh & lt)] = item;
-                    if (isM) b.order[(bounce + 1) & 1][n_ext - 1 - (bm + __popc(mm & lt))] = item;
-                }
-                if (fin) item = -1;
-                const unsigned idle = __ballot_sync(0xffffffffu, item < 0);
-                if (cursor < end) {
-                    const int mine = cursor + __popc(idle & lt);
-                    if (item < 0 && mine < end) {
-                        const float4 ro = b.ray_o[(bounce + 1) & 1][mine], rd = b.ray_d[(bounce + 1) & 1][mine];
-                        r.o = v3(ro.x, ro.y, ro.z); r.d = v3(rd.x, rd.y, rd.z);
-                        r.inv = v3(1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z);
-                        nbase = reinterpret_cast<unsigned long long>(nodes);
-                        if (OCT) nbase += 32ull * (unsigned)n_nodes * (unsigned)(((r.inv.x < 0.0f) ? 4 : 0) | ((r.inv.y < 0.0f) ? 2 : 0) | ((r.inv.z < 0.0f) ? 1 : 0));
-                        item = mine; cur = (n_nodes > 0) ? 0 : TRAV_DONE; sp = 1; closest = -1; tmax = FLT_MAX;
-                    }
-                    cursor = min(end, cursor + __popc(idle));
-                }
-                if (!__any_sync(0xffffffffu, cur != TRAV_DONE)) { if (cursor >= end) break; else continue; }
-            }
-            /* one staged iteration of traverse<false, NB, OCT> */
-#pragma unroll
-            for (int k = 0; k < NB; k++) {
-                if (cur >= 0) {
-                    const float4 *q = reinterpret_cast<const float4 *>(nbase + 32ull * (unsigned)cur);
-                    float4 lo = __ldg(q), hi = __ldg(q + 1);
-                    if (OCT ? slab_test_oct(r, lo, hi, tmax) : slab_test(r, lo, hi, tmax)) {
-                        stack[sp++] = __float_as_int(hi.w);
-                        cur = __float_as_int(lo.w);
-                    } else cur = stack[--sp];
-                }
-            }
-            if ((unsigned)cur > (unsigned)TRAV_DONE) {
-                float t;
-                if (leaf_test(r, leaf_tri, ~cur, tmax, t)) { closest = ~cur; tmax = t; }
-                cur = stack[--sp];
-            }
-        }
-    }
-    /* ---- shadow rays of this bounce with the same refill scheme.  An item is a vertex (walked in the order shade(bounce)
-     * took them: hits first); it carries up to two shadow rays, traced one after the other by the lane that owns the vertex
-     * (the second one starts at a refill round), then the vertex radiance is accumulated (connect_finish).  Vertices without
-     * shadow rays are finished on the spot by the lane that pulls them. */
-    {
-        const int n_warps = gridDim.x * (blockDim.x >> 5);
-        const int gwarp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-        const long long per = max(32ll, (((long long)n_con + n_warps - 1) / n_warps + 31) & ~31ll);
-        int cursor = (int)min((long long)n_con, (long long)gwarp * per);
-        const int end = (int)min((long long)n_con, (long long)gwarp * per + per);
-        int stack[TRAV_STACK + 1];
-        stack[0] = TRAV_DONE;
-        int sp = 1, cur = TRAV_DONE, slot = -1, flags = 0, phase = 0, hit = 0;
-        float tmax = 0.0f, L = 0.0f;
-        RayInv r; r.o = v3(0.0f, 0.0f, 0.0f); r.d = v3(1.0f, 1.0f, 1.0f); r.inv = r.d;
-        unsigned long long nbase = reinterpret_cast<unsigned long long>(nodes);
-        while (true) {
-            const unsigned busy = __ballot_sync(0xffffffffu, cur != TRAV_DONE);
-            if (busy == 0u || (cursor < end && __popc(busy) < keep)) {
-                float4 dn = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                bool start = false;
-                if (slot >= 0 && cur == TRAV_DONE) {                    /* a shadow ray of this lane's vertex has ended */
-                    const float4 rc = b.sh_c[slot];
-                    if (phase == 1) {
-                        L = hit ? 0.0f : rc.x;
-                        if (flags & 2) { dn = b.sh_d2[slot]; phase = 2; start = true; }
-                        else { connect_finish(fp, b, bounce, slot, flags, L, 0.0f, rc.z, rc.w, rc.z); slot = -1; }
-                    } else {
-                        connect_finish(fp, b, bounce, slot, flags, L, hit ? 0.0f : rc.y, rc.z, rc.w, rc.z);
-                        slot = -1;
-                    }
-                }
-                const unsigned idle = __ballot_sync(0xffffffffu, slot < 0);
-                if (cursor < end) {
-                    const int mine = cursor + __popc(idle & lt);
-                    if (slot < 0 && mine < end) {
-                        const int s = (ordered && bounce >= 1) ? b.order[bounce & 1][mine] : mine;
-                        const float4 ro = b.sh_o[s];
-                        const int fl = __float_as_int(ro.w);
-                        if ((fl & 4) || !(fl & 3)) { const float4 rc = b.sh_c[s]; connect_finish(fp, b, bounce, s, fl, 0.0f, 0.0f, rc.z, rc.w, rc.z); }
-                        else {
-                            slot = s; flags = fl; L = 0.0f;
-                            r.o = v3(ro.x, ro.y, ro.z);
-                            if (fl & 1) { dn = b.sh_d1[s]; phase = 1; } else { dn = b.sh_d2[s]; phase = 2; }
-                            start = true;
-                        }
-                    }
-                    cursor = min(end, cursor + __popc(idle));
-                }
-                if (start) {
-                    r.d = v3(dn.x, dn.y, dn.z);
-                    r.inv = v3(1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z);
-                    nbase = reinterpret_cast<unsigned long long>(nodes);
-                    if (OCT) nbase += 32ull * (unsigned)n_nodes * (unsigned)(((r.inv.x < 0.0f) ? 4 : 0) | ((r.inv.y < 0.0f) ? 2 : 0) | ((r.inv.z < 0.0f) ? 1 : 0));
-                    tmax = dn.w; hit = 0; sp = 1; cur = (n_nodes > 0) ? 0 : TRAV_DONE;
-                }
-                if (!__any_sync(0xffffffffu, cur != TRAV_DONE)) { if (cursor >= end) break; else continue; }
-            }
-            /* one staged iteration of traverse<true, NB, OCT> */
-#pragma unroll
-            for (int k = 0; k < NB; k++) {
-                if (cur >= 0) {
-                    const float4 *q = reinterpret_cast<const float4 *>(nbase + 32ull * (unsigned)cur);
-                    float4 lo = __ldg(q), hi = __ldg(q + 1);
-                    if (OCT ? slab_test_oct(r, lo, hi, tmax) : slab_test(r, lo, hi, tmax)) {
-                        stack[sp++] = __float_as_int(hi.w);
-                        cur = __float_as_int(lo.w);
-                    } else cur = stack[--sp];
-                }
-            }
-            if ((unsigned)cur > (unsigned)TRAV_DONE) {
-                float t;
-                if (leaf_test(r, leaf_tri, ~cur, tmax, t)) { hit = 1; cur = TRAV_DONE; }     /* any_hit stops at the first hit (bvh.fut:152) */
-                else cur = stack[--sp];
-            }
-        }
-    }
-}
-
 /* ------------------------------------------------------------------ generate + trace(-1) in one launch
  * The camera ray of a pixel goes straight from the registers into the traversal loop: one launch less per pass and no
  * read-back of the 32-byte ray records just written (k_shade(0) still needs them, so they are written once). */
-template <int NB, bool OCT, int PF>
-__global__ void __launch_bounds__(128, LYS_TRACE_MINB) k_generate_trace(SceneDev sc, const __grid_constant__ FrameParams fp, PassBuffers b) {
+template <int LAY>
+__global__ void __launch_bounds__(128, LYS_TRACE_MINB(LAY)) k_generate_trace(SceneDev sc, const __grid_constant__ FrameParams fp, PassBuffers b) {
     const int pid = blockIdx.x * blockDim.x + threadIdx.x;
     if (pid == 0) {
         b.counts[0] = fp.n_local;
@@ -929,10 +656,10 @@ __global__ void __launch_bounds__(128, LYS_TRACE_MINB) k_generate_trace(SceneDev
         b.acc[pid] = make_float4(0.0f, 0.0f, LYS_INF, 0.0f);
         b.chan[pid] = (uint8_t)ch;
         b.queue[0][pid] = pid;
-        if (b.probe_rad) for (int k = 0; k < LYS_MAX_PATH_LEN; k++) { b.probe_rad[(size_t)pid * 16 + k] = 0.0f; b.probe_dist[(size_t)pid * 16 + k] = LYS_INF; }
+        if (b.probe_rad) for (int k = 0; k < LYS_MAX_PATH_LEN; k++) { b.probe_rad[(size_t)ix * 16 + k] = 0.0f; b.probe_dist[(size_t)ix * 16 + k] = LYS_INF; }
     }
     float t;
-    const int h = traverse<false, NB, OCT, PF>(OCT ? sc.nodes_oct : sc.nodes, sc.leaf_tri, (int)sc.n_tris - 1, act, o, d, FLT_MAX, t);
+    const int h = traverse<false, LAY>((LAY == LAY_PAIR) ? sc.nodes : sc.nodes_oct, sc.leaf_tri, (int)sc.n_tris - 1, act, o, d, FLT_MAX, t);
     if (act) b.hit[pid] = h;
 }
 
@@ -944,7 +671,7 @@ __global__ void __launch_bounds__(128, LYS_TRACE_MINB) k_generate_trace(SceneDev
  * compaction (live paths stay inside the chunk's slot range of the ping-pong buffers, so the very same per-slot device
  * routines are used).  Per-path arithmetic is unchanged; the host picks bounce0 from an earlier pass's queue lengths
  * and any choice is correct. */
-template <bool OCT>
+template <int LAY>
 __global__ void __launch_bounds__(128) k_tail(SceneDev sc, const __grid_constant__ FrameParams fp, PassBuffers b, int bounce0) {
     __shared__ int s_next;
     const int count0 = b.counts[bounce0];
@@ -954,7 +681,7 @@ __global__ void __launch_bounds__(128) k_tail(SceneDev sc, const __grid_constant
     const int nl = fp.n_scene_lights + ((fp.tx_kind == 0) ? 0 : 8);
     const int n_nodes = (int)sc.n_tris - 1;
     const int lane = threadIdx.x & 31;
-    const float4 *__restrict__ nodes = OCT ? sc.nodes_oct : sc.nodes;
+    const float4 *__restrict__ nodes = (LAY == LAY_PAIR) ? sc.nodes : sc.nodes_oct;
     for (int bounce = bounce0; bounce < fp.path_len && n_cur > 0; bounce++) {
         if (threadIdx.x == 0) s_next = 0;
         __syncthreads();
@@ -1003,7 +730,7 @@ __global__ void __launch_bounds__(128) k_tail(SceneDev sc, const __grid_constant
             float4 ro = make_float4(0.0f, 0.0f, 0.0f, 0.0f), rd = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
             if (act) { ro = b.ray_o[(bounce + 1) & 1][i]; rd = b.ray_d[(bounce + 1) & 1][i]; }
             float t;
-            int h = traverse<false, 2, OCT>(nodes, sc.leaf_tri, n_nodes, act, v3(ro.x, ro.y, ro.z), v3(rd.x, rd.y, rd.z), FLT_MAX, t);
+            int h = traverse<false, LAY>(nodes, sc.leaf_tri, n_nodes, act, v3(ro.x, ro.y, ro.z), v3(rd.x, rd.y, rd.z), FLT_MAX, t);
             if (act) b.hit[i] = h;
         }
         for (int j0 = threadIdx.x & ~31; j0 < n_cur; j0 += blockDim.x) {
@@ -1018,13 +745,13 @@ __global__ void __launch_bounds__(128) k_tail(SceneDev sc, const __grid_constant
             if (__any_sync(0xffffffffu, need1)) {
                 float4 d1 = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
                 if (need1) d1 = b.sh_d1[slot];
-                int h = traverse<true, 2, OCT>(nodes, sc.leaf_tri, n_nodes, need1, o, v3(d1.x, d1.y, d1.z), d1.w, t);
+                int h = traverse<true, LAY>(nodes, sc.leaf_tri, n_nodes, need1, o, v3(d1.x, d1.y, d1.z), d1.w, t);
                 if (need1 && h < 0) L = rc.x;
             }
             if (__any_sync(0xffffffffu, need2)) {
                 float4 d2 = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
                 if (need2) d2 = b.sh_d2[slot];
-                int h = traverse<true, 2, OCT>(nodes, sc.leaf_tri, n_nodes, need2, o, v3(d2.x, d2.y, d2.z), d2.w, t);
+                int h = traverse<true, LAY>(nodes, sc.leaf_tri, n_nodes, need2, o, v3(d2.x, d2.y, d2.z), d2.w, t);
                 if (need2 && h < 0) B = rc.y;
             }
             if (act) connect_finish(fp, b, bounce, slot, flags, L, B, rc.z, rc.w, rc.z);
@@ -1107,17 +834,18 @@ __global__ void __launch_bounds__(256) k_render(const float *__restrict__ img, i
 }
 
 /* ------------------------------------------------------------------ probes / tools */
-__global__ void k_primary_probe(SceneDev sc, PassBuffers b, int n, int *leaf, int *src, float *t) {
+__global__ void k_primary_probe(SceneDev sc, const __grid_constant__ FrameParams fp, PassBuffers b, int n, int *leaf, int *src, float *t) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     const bool act = i < n;                                          /* no early return: traverse<> votes per warp */
     float4 ro = make_float4(0.0f, 0.0f, 0.0f, 0.0f), rd = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
     if (act) { ro = b.ray_o[0][i]; rd = b.ray_d[0][i]; }
     float th;
-    int l = traverse<false, 1, false>(sc.nodes, sc.leaf_tri, (int)sc.n_tris - 1, act, v3(ro.x, ro.y, ro.z), v3(rd.x, rd.y, rd.z), FLT_MAX, th);
+    int l = traverse<false, LAY_PAIR>(sc.nodes, sc.leaf_tri, (int)sc.n_tris - 1, act, v3(ro.x, ro.y, ro.z), v3(rd.x, rd.y, rd.z), FLT_MAX, th);
     if (!act) return;
-    leaf[i] = l;
-    if (src) src[i] = (l < 0) ? -1 : (int)__float_as_uint(sc.leaf_tri[4ll * l + 1].w);
-    if (t) t[i] = (l < 0) ? LYS_INF : th;
+    const size_t ix = probe_index(fp, i);
+    leaf[ix] = l;
+    if (src) src[ix] = (l < 0) ? -1 : (int)__float_as_uint(sc.leaf_tri[4ll * l + 1].w);
+    if (t) t[ix] = (l < 0) ? LYS_INF : th;
 }
 __global__ void k_trace_rays(SceneDev sc, const float *__restrict__ rays, const float *__restrict__ tmax, long long n,
                              int *out_leaf, float *out_t, int any) {
@@ -1126,8 +854,8 @@ __global__ void k_trace_rays(SceneDev sc, const float *__restrict__ rays, const 
     V3 o = v3(0.0f, 0.0f, 0.0f), d = v3(1.0f, 1.0f, 1.0f);
     if (act) { const float *r = rays + 6 * i; o = v3(r[0], r[1], r[2]); d = v3(r[3], r[4], r[5]); }
     float th; int l;
-    if (any) l = traverse<true, 1, false>(sc.nodes, sc.leaf_tri, (int)sc.n_tris - 1, act, o, d, act ? tmax[i] : 0.0f, th);
-    else l = traverse<false, 1, false>(sc.nodes, sc.leaf_tri, (int)sc.n_tris - 1, act, o, d, FLT_MAX, th);
+    if (any) l = traverse<true, LAY_PAIR>(sc.nodes, sc.leaf_tri, (int)sc.n_tris - 1, act, o, d, act ? tmax[i] : 0.0f, th);
+    else l = traverse<false, LAY_PAIR>(sc.nodes, sc.leaf_tri, (int)sc.n_tris - 1, act, o, d, FLT_MAX, th);
     if (!act) return;
     out_leaf[i] = any ? (l >= 0 ? 1 : 0) : l;
     if (out_t) out_t[i] = (l < 0) ? LYS_INF : th;
@@ -1157,71 +885,45 @@ __global__ void k_material_probe(const float *mat28, float wavelen, V3 wo, V3 wi
 /* ------------------------------------------------------------------ host launchers */
 static inline int cdiv(long long a, int b) { return (int)((a + b - 1) / b); }
 
-/* persistent grids: SM count x resident CTAs per SM of each kernel (queried once per device) */
-struct GridSizes { int trace = 0, shade = 0, refill = 0, sl = 0, sb = 0, sc = 0; int sr = 0, sr_keep = 24, sr_cam = 0; int mode = 0, split_bounces = 0, nb = 0, bars = 0, shade_threads = 256, oct = 1, adaptive = 1, sms = 148, tail_max = 8192, tail_items = 128, profile_tail = 0, order = 1, tail_min = 148, fuse_gen = 1, dyn_grids = 0, pf = 0, pf_cam = 0; };
+/* persistent grids: SM count x resident CTAs per SM of each kernel (queried once per device).  The environment knobs
+ * force what is otherwise chosen by scene size or by the previous pass (tests/test_gpu_parity.py::test_kernel_variants_bit_exact
+ * runs each setting against the oracle): LYS_TRACE_PAIR (lbvh.cu), LYS_TRACE_OCT, LYS_TAIL_MAX, LYS_ADAPTIVE_GRIDS, LYS_SHADE_ORDER,
+ * LYS_FUSE_GENERATE; LYS_PROFILE_TAIL keeps the fused tail under per-class timing. */
+struct GridSizes { int trace[3] = {0, 0, 0}, shade = 0, oct = 1, adaptive = 1, sms = 148, tail_max = 8192, tail_items = 128, profile_tail = 0, order = 1, fuse_gen = 1; };
 static GridSizes grid_sizes() {
     static GridSizes g[64];
     int dev = 0; cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64) dev = 0;
-    if (!g[dev].trace) {
-        int sms = 148, bt = 8, bs = 4;
+    if (!g[dev].shade) {
+        int sms = 148, bt[3] = {10, 12, 16}, bs = 3;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bt, k_trace<2, true, 0>, 128, 0);
-        const char *sth = getenv("LYS_SHADE_THREADS"); if (sth && (atoi(sth) == 512 || atoi(sth) == 128)) g[dev].shade_threads = atoi(sth);
-        if (g[dev].shade_threads == 256) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bs, k_shade<256>, 256, 0);
-        else if (g[dev].shade_threads == 128) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bs, k_shade<128>, 128, 0);
-        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bs, k_shade<512>, 512, 0);
-        int br = 8; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&br, k_trace_refill, 128, 0);
-        g[dev].trace = sms * (bt > 0 ? bt : 1); g[dev].shade = sms * (bs > 0 ? bs : 1); g[dev].refill = sms * (br > 0 ? br : 1);
-        /* experiment knobs: persistent grids as a fraction of the resident maximum (co-residency of kernels of different streams) */
-        const char *gt = getenv("LYS_TRACE_GRID_PCT"); if (gt && atoi(gt) > 0) g[dev].trace = max(sms, g[dev].trace * atoi(gt) / 100);
-        const char *gsh = getenv("LYS_SHADE_GRID_PCT"); if (gsh && atoi(gsh) > 0) g[dev].shade = max(sms, g[dev].shade * atoi(gsh) / 100);
-        const char *e = getenv("LYS_TRACE_MODE"); g[dev].mode = (e && atoi(e) == 1) ? 1 : 0;      /* 1: k_trace_refill instead of k_trace */
-        g[dev].sr = (e && atoi(e) == 2) ? 1 : 0;                                               /* 2: k_trace_sr (staged loop + lane refill) for the bounce launches */
-        const char *kp = getenv("LYS_TRACE_SR_KEEP"); if (kp && atoi(kp) >= 1 && atoi(kp) <= 32) g[dev].sr_keep = atoi(kp);
-        const char *kc = getenv("LYS_TRACE_SR_CAMERA"); g[dev].sr_cam = (g[dev].sr && kc && atoi(kc) == 1) ? 1 : 0;    /* camera rays through k_trace_sr too (k_generate + k_trace_sr(-1)) */
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bt[LAY_SINGLE], k_trace<LAY_SINGLE>, 128, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bt[LAY_PAIR_OCT], k_trace<LAY_PAIR_OCT>, 128, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bt[LAY_PAIR], k_trace<LAY_PAIR>, 128, 0);
+        for (int k = 0; k < 3; k++) g[dev].trace[k] = sms * (bt[k] > 0 ? bt[k] : 1);
+        g[dev].shade = sms * (bs > 0 ? bs : 1);
         g[dev].sms = sms;
         const char *ord = getenv("LYS_SHADE_ORDER"); if (ord) g[dev].order = atoi(ord) ? 1 : 0;      /* 0: k_shade walks the slots in queue order */
-        g[dev].tail_min = sms;
-        const char *tmn = getenv("LYS_TAIL_MIN_CTAS"); if (tmn && atoi(tmn) > 0) g[dev].tail_min = atoi(tmn);
-        const char *dg = getenv("LYS_DYN_GRIDS"); if (dg) g[dev].dyn_grids = atoi(dg) & 3;      /* bit 0: k_trace, bit 1: k_shade launched with one item per thread when the queue length is known */
         const char *fg = getenv("LYS_FUSE_GENERATE"); if (fg) g[dev].fuse_gen = atoi(fg) ? 1 : 0;    /* 0: k_generate and k_trace(-1) as two launches */
-        const char *tit = getenv("LYS_TAIL_ITEMS"); if (tit && atoi(tit) > 0) g[dev].tail_items = atoi(tit);
         const char *ptl = getenv("LYS_PROFILE_TAIL"); if (ptl) g[dev].profile_tail = atoi(ptl) ? 1 : 0;
         const char *tmx = getenv("LYS_TAIL_MAX"); if (tmx) g[dev].tail_max = atoi(tmx);          /* 0: no fused tail */
         const char *ad = getenv("LYS_ADAPTIVE_GRIDS"); if (ad) g[dev].adaptive = atoi(ad) ? 1 : 0;
         const char *oc = getenv("LYS_TRACE_OCT"); if (oc) g[dev].oct = atoi(oc) ? 1 : 0;          /* 0: always the select-based box test */
-        const char *nb = getenv("LYS_TRACE_NB"); g[dev].nb = nb ? ((atoi(nb) == 1) ? 1 : 2) : 0;      /* box stages per loop iteration; 0 = by scene size */
-        const char *pf = getenv("LYS_TRACE_PF"); if (pf) g[dev].pf = g[dev].pf_cam = max(0, min(3, atoi(pf)));   /* right-child prefetch at push time (NB = 1 variants) */
-        const char *pfc = getenv("LYS_TRACE_PF_CAMERA"); if (pfc) g[dev].pf_cam = max(0, min(3, atoi(pfc)));
-        int b1 = 8, b2 = 8, b3 = 8;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, k_shade_light, 128, 0); cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b2, k_shade_bsdf, 128, 0);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b3, k_shade_cont, 128, 0);
-        g[dev].sl = sms * (b1 > 0 ? b1 : 1); g[dev].sb = sms * (b2 > 0 ? b2 : 1); g[dev].sc = sms * (b3 > 0 ? b3 : 1);
-        const char *sbar = getenv("LYS_SHADE_BARS"); if (sbar) g[dev].bars = atoi(sbar) & 3;     /* optional lockstep barriers of k_shade */
-        const char *sp = getenv("LYS_SHADE_SPLIT"); if (sp) g[dev].split_bounces = atoi(sp);     /* phase kernels for bounces < this */
     }
     return g[dev];
 }
-static void launch_trace(const GridSizes &gs0, int grid, const SceneDev &sc, const FrameParams &fp, PassBuffers &bufs, int bounce, cudaStream_t stream) {
-    GridSizes gs = gs0;
-    /* box stages per loop iteration: 2 for small, cache-resident trees (issue bound: fewer, fuller iterations), 1 for large
-     * ones (two dependent node loads per lock-step iteration cost more than they save); measured in profiles/README.md 4.5 */
-    if (gs.nb == 0) gs.nb = (sc.n_tris <= 4096) ? 2 : 1;
-    if (gs.mode) { k_trace_refill<<<grid, 128, 0, stream>>>(sc, fp, bufs, bounce); return; }
+static int trace_layout(const GridSizes &gs, const SceneDev &sc) {
+    if (sc.single_nodes) return LAY_SINGLE;
+    return (sc.nodes_oct && gs.oct) ? LAY_PAIR_OCT : LAY_PAIR;
+}
+/* the three traversal variants a scene can select */
+#define LYS_TRAV_DISPATCH(lay, CALL) do { \
+        if ((lay) == LAY_SINGLE) { CALL(LAY_SINGLE); } else if ((lay) == LAY_PAIR_OCT) { CALL(LAY_PAIR_OCT); } else { CALL(LAY_PAIR); } } while (0)
+static void launch_trace(const GridSizes &gs, int grid, const SceneDev &sc, const FrameParams &fp, PassBuffers &bufs, int bounce, cudaStream_t stream) {
     const int ordered = (gs.order && bounce >= 0) ? 1 : 0;      /* write the hits-first order of bounce + 1, walk the one of bounce */
-    if (gs.sr && (bounce >= 0 || gs.sr_cam)) {                 /* experimental: staged loop with lane refill (camera rays keep k_trace unless LYS_TRACE_SR_CAMERA=1) */
-        if (sc.nodes_oct && gs.oct) { if (gs.nb == 1) k_trace_sr<1, true><<<grid, 128, 0, stream>>>(sc, fp, bufs, bounce, ordered, gs.sr_keep); else k_trace_sr<2, true><<<grid, 128, 0, stream>>>(sc, fp, bufs, bounce, ordered, gs.sr_keep); }
-        else if (gs.nb == 1) k_trace_sr<1, false><<<grid, 128, 0, stream>>>(sc, fp, bufs, bounce, ordered, gs.sr_keep);
-        else k_trace_sr<2, false><<<grid, 128, 0, stream>>>(sc, fp, bufs, bounce, ordered, gs.sr_keep);
-        return;
-    }
-    const bool oct = sc.nodes_oct && gs.oct;
-#define LYS_LAUNCH_TRACE(NB, OCT, PF) k_trace<NB, OCT, PF><<<grid, 128, 0, stream>>>(sc, fp, bufs, bounce, ordered)
-    if (gs.nb != 1) { if (oct) LYS_LAUNCH_TRACE(2, true, 0); else LYS_LAUNCH_TRACE(2, false, 0); }
-    else if (oct) { if (gs.pf == 3) LYS_LAUNCH_TRACE(1, true, 3); else if (gs.pf == 2) LYS_LAUNCH_TRACE(1, true, 2); else if (gs.pf == 1) LYS_LAUNCH_TRACE(1, true, 1); else LYS_LAUNCH_TRACE(1, true, 0); }
-    else { if (gs.pf == 3) LYS_LAUNCH_TRACE(1, false, 3); else if (gs.pf == 2) LYS_LAUNCH_TRACE(1, false, 2); else if (gs.pf == 1) LYS_LAUNCH_TRACE(1, false, 1); else LYS_LAUNCH_TRACE(1, false, 0); }
-#undef LYS_LAUNCH_TRACE
+#define LYS_CALL(LAY) k_trace<LAY><<<grid, 128, 0, stream>>>(sc, fp, bufs, bounce, ordered)
+    LYS_TRAV_DISPATCH(trace_layout(gs, sc), LYS_CALL);
+#undef LYS_CALL
 }
 cudaError_t run_sample_pass(const SceneDev &sc, const FrameParams &fp, PassBuffers &bufs, cudaStream_t stream, uint64_t *launches, LaunchTimer *timer,
                             int *est_counts) {
@@ -1230,7 +932,7 @@ cudaError_t run_sample_pass(const SceneDev &sc, const FrameParams &fp, PassBuffe
     uint64_t nl = 0;
     LaunchTimer none; LaunchTimer &tm = timer ? *timer : none;
     const GridSizes gs = grid_sizes();
-    const int g_trace = min(gs.mode ? gs.refill : gs.trace, cdiv(2ll * n, 128)), g_shade = min(gs.shade, cdiv(n, gs.shade_threads));
+    const int g_trace = min(gs.trace[trace_layout(gs, sc)], cdiv(2ll * n, 128)), g_shade = min(gs.shade, cdiv(n, 256));
     /* queue-length estimates: a snapshot of what an earlier pass left (the copy below may be updating it: harmless, the
      * numbers only size grids); valid if it is about the same sample grid */
     int est[LYS_MAX_PATH_LEN + 2];
@@ -1244,25 +946,19 @@ cudaError_t run_sample_pass(const SceneDev &sc, const FrameParams &fp, PassBuffe
     const int g_min = max(1, gs.sms);                    /* never below one CTA per SM: a stale estimate costs at most ~10x on one pass */
     auto sized = [&](long long items, int threads, int g_full) {
         if (!have_est) return g_full;
-        const long long per_item = (items + items / 16 + 2048 + threads - 1) / threads;      /* one item per thread (+6 %): the hardware balances the CTAs */
-        if (gs.dyn_grids & ((threads == 128) ? 1 : 2)) return (int)max((long long)g_min, min(per_item, 1ll << 22));
         return (int)max((long long)g_min, min((long long)g_full, (2 * items + 4096 + threads - 1) / threads));
     };
     /* first bounce whose queue was short enough in the earlier pass: from there on one k_tail launch */
     int b_tail = fp.path_len;
-    if (have_est && gs.tail_max > 0 && !gs.mode && !(tm.on == 1 && !gs.profile_tail))      /* per-class timing (mode 1) wants every ray in the trace class */
+    if (have_est && gs.tail_max > 0 && !(tm.on == 1 && !gs.profile_tail))      /* per-class timing (mode 1) wants every ray in the trace class */
         for (int k = 1; k < fp.path_len; k++) if (est[k] <= gs.tail_max) { b_tail = k; break; }
-    if (gs.fuse_gen && !gs.mode && !gs.sr_cam && tm.on != 1) {  /* per-class timing (mode 1) keeps the two launches apart */
+    if (gs.fuse_gen && tm.on != 1) {                     /* per-class timing (mode 1) keeps the two launches apart */
         tm.cur_bounce = -1;
         tm.begin(1, stream);
-        const int nb = gs.nb ? gs.nb : ((sc.n_tris <= 4096) ? 2 : 1);
         const int g = cdiv(n, 128);
-        const bool oct = sc.nodes_oct && gs.oct;
-#define LYS_LAUNCH_GEN(NB, OCT, PF) k_generate_trace<NB, OCT, PF><<<g, 128, 0, stream>>>(sc, fp, bufs)
-        if (nb != 1) { if (oct) LYS_LAUNCH_GEN(2, true, 0); else LYS_LAUNCH_GEN(2, false, 0); }
-        else if (oct) { if (gs.pf_cam == 3) LYS_LAUNCH_GEN(1, true, 3); else if (gs.pf_cam == 2) LYS_LAUNCH_GEN(1, true, 2); else if (gs.pf_cam == 1) LYS_LAUNCH_GEN(1, true, 1); else LYS_LAUNCH_GEN(1, true, 0); }
-        else { if (gs.pf_cam == 3) LYS_LAUNCH_GEN(1, false, 3); else if (gs.pf_cam == 2) LYS_LAUNCH_GEN(1, false, 2); else if (gs.pf_cam == 1) LYS_LAUNCH_GEN(1, false, 1); else LYS_LAUNCH_GEN(1, false, 0); }
-#undef LYS_LAUNCH_GEN
+#define LYS_CALL(LAY) k_generate_trace<LAY><<<g, 128, 0, stream>>>(sc, fp, bufs)
+        LYS_TRAV_DISPATCH(trace_layout(gs, sc), LYS_CALL);
+#undef LYS_CALL
         tm.end(stream); nl++;
     } else {
         tm.begin(0, stream); k_generate<<<cdiv(n, 256), 256, 0, stream>>>(fp, bufs); tm.end(stream); nl++;
@@ -1274,31 +970,20 @@ cudaError_t run_sample_pass(const SceneDev &sc, const FrameParams &fp, PassBuffe
     for (int bnc = 0; bnc < b_tail; bnc++) {
         tm.cur_bounce = bnc;
         tm.begin(2, stream);
-        if (bnc < gs.split_bounces) {
-            const int nlights = fp.n_scene_lights + ((fp.tx_kind == 0) ? 0 : 8);
-            if (nlights > 0) {
-                k_shade_light<<<min(gs.sl, cdiv(n, 128)), 128, 0, stream>>>(sc, fp, bufs, bnc);
-                k_shade_bsdf<<<min(gs.sb, cdiv(n, 128)), 128, 0, stream>>>(sc, fp, bufs, bnc); nl += 2;
-            }
-            k_shade_cont<<<min(gs.sc, cdiv(n, 128)), 128, 0, stream>>>(sc, fp, bufs, bnc, nlights > 0 ? 1 : 0);
-        } else {
-            const int g = sized(have_est ? est[bnc] : 0, gs.shade_threads, g_shade);
-            const int fl = gs.bars | ((gs.order && !gs.mode && bnc > 0) ? 4 : 0);       /* bit 2: follow b.order (written by k_trace, not by the refill variant) */
-            if (gs.shade_threads == 512) k_shade<512><<<g, 512, 0, stream>>>(sc, fp, bufs, bnc, fl);
-            else if (gs.shade_threads == 128) k_shade<128><<<g, 128, 0, stream>>>(sc, fp, bufs, bnc, fl);
-            else k_shade<256><<<g, 256, 0, stream>>>(sc, fp, bufs, bnc, fl);
-        }
+        k_shade<256><<<sized(have_est ? est[bnc] : 0, 256, g_shade), 256, 0, stream>>>(sc, fp, bufs, bnc, (gs.order && bnc > 0) ? 1 : 0);   /* follow b.order (written by k_trace) */
         tm.end(stream); nl++;
         tm.begin(1, stream);
         launch_trace(gs, sized(have_est ? (long long)est[bnc] + est[bnc + 1] : 0, 128, g_trace), sc, fp, bufs, bnc, stream);
         tm.end(stream); nl++;
     }
     if (b_tail < fp.path_len) {
-        const int g = (int)max((long long)gs.tail_min, min((long long)gs.sms * 4, (long long)((est[b_tail] + est[b_tail] / 4 + gs.tail_items - 1) / gs.tail_items)));   /* few, well filled CTAs (they stay resident for all the remaining bounces), never fewer than one per SM: a stale estimate must not serialise a long queue */
+        const int g = (int)max((long long)gs.sms, min((long long)gs.sms * 4, (long long)((est[b_tail] + est[b_tail] / 4 + gs.tail_items - 1) / gs.tail_items)));   /* few, well filled CTAs (they stay resident for all the remaining bounces), never fewer than one per SM: a stale estimate must not serialise a long queue */
         tm.cur_bounce = b_tail;
         tm.begin(3, stream);
-        if (sc.nodes_oct && gs.oct) k_tail<true><<<g, 128, 0, stream>>>(sc, fp, bufs, b_tail);
-        else k_tail<false><<<g, 128, 0, stream>>>(sc, fp, bufs, b_tail);
+        const int lay = trace_layout(gs, sc);
+        if (lay == LAY_SINGLE) k_tail<LAY_SINGLE><<<g, 128, 0, stream>>>(sc, fp, bufs, b_tail);
+        else if (lay == LAY_PAIR_OCT) k_tail<LAY_PAIR_OCT><<<g, 128, 0, stream>>>(sc, fp, bufs, b_tail);
+        else k_tail<LAY_PAIR><<<g, 128, 0, stream>>>(sc, fp, bufs, b_tail);
         tm.end(stream); nl++;
     }
     if (est_counts && gs.adaptive) {
@@ -1343,7 +1028,7 @@ cudaError_t run_primary_probe(const SceneDev &sc, const FrameParams &fp, PassBuf
     const int n = fp.n_local;
     if (n <= 0) return cudaSuccess;
     k_generate<<<cdiv(n, 256), 256, 0, stream>>>(fp, bufs);
-    k_primary_probe<<<cdiv(n, 128), 128, 0, stream>>>(sc, bufs, n, leaf, src, t);
+    k_primary_probe<<<cdiv(n, 128), 128, 0, stream>>>(sc, fp, bufs, n, leaf, src, t);
     if (launches) *launches += 2;
     return cudaGetLastError();
 }

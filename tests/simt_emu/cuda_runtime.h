@@ -34,6 +34,7 @@
 
 /* ---- vector types -------------------------------------------------------------------- */
 struct alignas(8) float2 { float x, y; };
+struct alignas(8) int2 { int x, y; };
 struct alignas(16) float4 { float x, y, z, w; };
 struct uint3 { unsigned int x, y, z; };
 struct dim3 {
@@ -41,6 +42,7 @@ struct dim3 {
     dim3(unsigned int x_ = 1, unsigned int y_ = 1, unsigned int z_ = 1) : x(x_), y(y_), z(z_) {}
 };
 static inline float2 make_float2(float x, float y) { float2 r; r.x = x; r.y = y; return r; }
+static inline int2 make_int2(int x, int y) { int2 r; r.x = x; r.y = y; return r; }
 static inline float4 make_float4(float x, float y, float z, float w) { float4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
 
 /* ---- the SIMT engine (emu_engine.cpp) ------------------------------------------------ */

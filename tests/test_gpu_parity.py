@@ -439,24 +439,19 @@ def test_init_light_capacity_regrow(orc, pkg, gpu, scenes):
 
 
 @pytest.mark.parametrize('env', [
-    {'LYS_TRACE_OCT': '0'},            # select-based box test on the plain node array (what scenes above 128K nodes use)
-    {'LYS_TRACE_NB': '1'},             # one box stage per loop iteration
-    {'LYS_SHADE_THREADS': '512'}, {'LYS_SHADE_THREADS': '128'}, {'LYS_SHADE_BARS': '3'},
+    {'LYS_TRACE_PAIR': '1'},           # pair records on the small scene too (what scenes above 1024 triangles use)
+    {'LYS_TRACE_PAIR': '1', 'LYS_TRACE_OCT': '0'},            # select-based box test on the plain record array (scenes above 64K nodes)
+    {'LYS_TRACE_OCT': '0'},            # small scene: single-box records stay (they exist as octant copies only); spectrumsphere: plain pair records
     {'LYS_SHADE_ORDER': '0'},          # k_shade walks the queue in slot order instead of hits first
-    {'LYS_FUSE_GENERATE': '0'},        # k_generate and k_trace(-1) as two launches
+    {'LYS_FUSE_GENERATE': '0'},        # k_generate and k_trace(-1) as two launches (the per-class timing sequence)
     {'LYS_TAIL_MAX': '0'},             # no fused tail kernel: one launch per stage and bounce
     {'LYS_TAIL_MAX': '100000000'},     # fused tail from bounce 1 on (every queue is 'short')
     {'LYS_TAIL_MAX': '100000000', 'LYS_TRACE_OCT': '0'},
-    {'LYS_TRACE_MODE': '1'},           # refill variant of the trace kernel
-    {'LYS_SHADE_SPLIT': '2'},          # phase-split shading kernels for the first two bounces
-    {'LYS_TRACE_MODE': '2'},           # k_trace_sr: staged loop + lane refill
-    {'LYS_TRACE_MODE': '2', 'LYS_TRACE_SR_CAMERA': '1'},
-    {'LYS_TRACE_NB': '1', 'LYS_TRACE_PF': '1'},      # right-child prefetch at push time (what large scenes may select)
-    {'LYS_TRACE_NB': '1', 'LYS_TRACE_PF': '2', 'LYS_TRACE_OCT': '0'},
-    {'LYS_TRACE_NB': '1', 'LYS_TRACE_PF': '3'},
+    {'LYS_TAIL_MAX': '100000000', 'LYS_TRACE_PAIR': '1'},
+    {'LYS_ADAPTIVE_GRIDS': '0'},       # every pass runs like the first pass of a frame (full grids, no tail)
 ], ids=lambda e: ','.join(f'{k}={v}' for k, v in e.items()))
 def test_kernel_variants_bit_exact(env):
-    """Every selectable kernel variant (environment knobs read once per process) gives the oracle's bits: the sweep of
+    """Every kernel variant the library selects by scene size or from the previous pass, forced by its environment knob (read once per process), gives the oracle's bits: the sweep of
     tools/gpu_parity_quick.py (BVH, first hits, per-vertex radiance, 4 accumulated passes, step/render) in a subprocess."""
     import json
     import subprocess

@@ -45,35 +45,18 @@ def test_emulated_library_equals_the_oracle(emu_lib):
 
 
 @pytest.mark.parametrize('env', [
-    {'LYS_TRACE_OCT': '0', 'LYS_TRACE_NB': '1'},       # what scenes above 128K nodes run: select-based box test, one box stage
+    {'LYS_TRACE_PAIR': '1', 'LYS_TRACE_OCT': '0'},       # what scenes above 64K nodes run: pair records, select-based box test
+    {'LYS_TRACE_PAIR': '1'},                             # 1K .. 64K nodes: pair records, octant copies
     {'LYS_TAIL_MAX': '100000000'},                     # fused tail kernel from bounce 1 on
-    {'LYS_TRACE_MODE': '1'},                           # refill variant of the trace kernel
-    {'LYS_SHADE_SPLIT': '2', 'LYS_FUSE_GENERATE': '0'},
-    {'LYS_TRACE_MODE': '2'},                           # k_trace_sr: staged loop + lane refill (experimental, emulator-validated only)
-    {'LYS_TRACE_MODE': '2', 'LYS_TRACE_SR_KEEP': '32', 'LYS_TRACE_OCT': '0', 'LYS_TRACE_NB': '1', 'LYS_EMU_SMS': '2'},   # refill at every idle lane, long slices
-    {'LYS_TRACE_MODE': '2', 'LYS_TRACE_SR_KEEP': '1', 'LYS_TAIL_MAX': '0', 'LYS_SHADE_ORDER': '0', 'LYS_EMU_SMS': '32'},  # refill only when the warp is empty, short slices
-    {'LYS_TRACE_MODE': '2', 'LYS_TRACE_SR_CAMERA': '1'},   # camera rays through k_trace_sr as well (k_generate + k_trace_sr(-1))
+    {'LYS_TAIL_MAX': '0', 'LYS_SHADE_ORDER': '0', 'LYS_FUSE_GENERATE': '0', 'LYS_EMU_SMS': '32'},
     {'LYS_EMU_SCHEDULE': '1'},                         # CTAs, warps and lanes run in reverse order: results must not depend on the schedule
     {'LYS_EMU_SCHEDULE': '4242', 'LYS_TAIL_MAX': '100000000'},       # pseudo-random orders, redrawn per CTA (race / order-dependence probe)
-    {'LYS_EMU_SCHEDULE': '977', 'LYS_TRACE_MODE': '2', 'LYS_EMU_SMS': '8'},
-], ids=lambda e: ','.join(f'{k}={v}' for k, v in e.items()))
+    {'LYS_EMU_SCHEDULE': '977', 'LYS_TRACE_PAIR': '1', 'LYS_TRACE_OCT': '0', 'LYS_EMU_SMS': '8'},
+])
 def test_emulated_kernel_variants(emu_lib, env):
     e = dict(env)
     e['LYS_EMU_FAST_MATH_SWEEP'] = '1'
     check(sweep(emu_lib, ['cornell'], e))
-
-
-def test_staged_refill_kernel_on_the_parity_suite(emu_lib):
-    """k_trace_sr (LYS_TRACE_MODE=2; on the B200 it is in tests/test_gpu_parity.py::test_kernel_variants_bit_exact) through the
-    fuzzed scenes, all camera presets, the edge configurations and the entry points on the emulator."""
-    e = dict(os.environ)
-    e.update({'LYS_EMU_LIB': emu_lib, 'LYS_TRACE_MODE': '2'})
-    r = subprocess.run([sys.executable, RUN_EMU, '-m', 'pytest', os.path.join(ROOT, 'tests', 'test_gpu_parity.py'), '-m', 'gpu', '-q', '-x', '-p', 'no:cacheprovider',
-                        '-k', 'soup or edge_configurations or entry_points or sample_points or path_len or row_partition'],
-                       env=e, text=True, capture_output=True, timeout=1500, cwd=ROOT)
-    tail = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else r.stderr[-400:]
-    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
-    assert ' passed' in tail and 'failed' not in tail and int(tail.split(' passed')[0].split()[-1]) >= 10, tail
 
 
 def test_gpu_parity_suite_on_the_emulator(emu_lib):
@@ -107,7 +90,7 @@ def test_product_binding_has_no_library_override(emu_lib):
 @pytest.mark.parametrize('what,seed,count,env', [
     ('lbvh', 1, 40, {'LYS_EMU_SCHEDULE': '3'}),        # hostile geometry: inf / NaN / denormals / duplicates / identical triangles
     ('soup', 2, 10, {}),                               # random scenes, materials, camera presets, poses, frame sizes, seeds
-    ('soup', 3, 8, {'LYS_TRACE_MODE': '2', 'LYS_EMU_SCHEDULE': '7'}),
+    ('soup', 3, 8, {'LYS_TRACE_PAIR': '1', 'LYS_TRACE_OCT': '0', 'LYS_EMU_SCHEDULE': '7'}),
     ('keys', 4, 12, {}),                               # random host sessions: key events, resizes, steps -> scalars, image, ARGB frame
 ], ids=lambda v: str(v) if not isinstance(v, dict) else ','.join(f'{k}={x}' for k, x in v.items()) or 'default')
 def test_fuzzed_parity_on_the_emulator(emu_lib, what, seed, count, env):

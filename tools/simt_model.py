@@ -206,9 +206,79 @@ def study_schedules(scene, h, w):
                     print(f'   box {box} tri {tri}  refill: slices of {slice_len}, refill below {keep} busy lanes {c:7.1f} warp-instr/ray  {it:7.1f} steps/warp')
 
 
+def pair_cost(pat, ln, order, policy, costs, thr=8, nb=2):
+    """Pair records (wavefront.cu: LAY_PAIR*): a failing box test costs no visit of its own, so a ray's stage sequence is its
+    reference pattern without the 'box fail' events ('N' = enter a node: both children tested, 'T' = triangle test).
+    policy 'static': every iteration runs nb N stages then one T stage (k_trace today);
+    policy 'vote':   every iteration runs ONE stage chosen by a warp vote: T if at least `thr` lanes wait at a leaf or no lane
+                     is at a node, else N (lanes at leaves wait).  Returns warp instructions per ray, iterations per warp,
+                     mean active lanes per N stage and per T stage."""
+    p = pat[order]
+    n = len(p)
+    pad = (-n) % 32
+    if pad:
+        p = np.concatenate([p, np.full((pad, p.shape[1]), 255, np.uint8)])
+    # compress: drop box-fail events (code 0); 1 -> N, 2/3 -> T
+    keep = (p == 1) | (p == 2) | (p == 3)
+    L = keep.sum(axis=1)
+    width = int(L.max()) + 1
+    kind = np.full((len(p), width), 2, np.int8)
+    idx = np.cumsum(keep, axis=1) - 1
+    r, c = np.nonzero(keep)
+    kind[r, idx[r, c]] = np.where(p[r, c] == 1, 0, 1)
+    ptr = np.zeros(len(p), np.int64)
+    rows = np.arange(len(p))
+    total = iters = 0
+    laneN = stageN = laneT = stageT = 0
+    while True:
+        k = kind[rows, ptr]
+        isN, isT = (k == 0).reshape(-1, 32), (k == 1).reshape(-1, 32)
+        alive = isN.any(axis=1) | isT.any(axis=1)
+        if not alive.any():
+            break
+        iters += int(alive.sum())
+        total += costs['loop'] * int(alive.sum())
+        if policy == 'static':
+            for _ in range(nb):
+                k = kind[rows, ptr]
+                take = (k == 0)
+                tw = take.reshape(-1, 32)
+                total += costs['N'] * int(tw.any(axis=1).sum()); laneN += int(take.sum()); stageN += int(tw.any(axis=1).sum())
+                ptr = ptr + take
+            k = kind[rows, ptr]
+            take = (k == 1)
+            tw = take.reshape(-1, 32)
+            total += costs['T'] * int(tw.any(axis=1).sum()); laneT += int(take.sum()); stageT += int(tw.any(axis=1).sum())
+            ptr = ptr + take
+        else:
+            nN, nT = isN.sum(axis=1), isT.sum(axis=1)
+            runT = (nT >= thr) | (nN == 0)
+            takeT = (isT & runT[:, None]).reshape(-1)
+            takeN = (isN & ~runT[:, None]).reshape(-1)
+            total += costs['T'] * int((runT & alive).sum()) + costs['N'] * int((~runT & alive).sum())
+            laneT += int(takeT.sum()); stageT += int((runT & alive).sum()); laneN += int(takeN.sum()); stageN += int((~runT & alive).sum())
+            ptr = ptr + takeT + takeN
+    return total / n, iters / (len(p) // 32), laneN / max(stageN, 1), laneT / max(stageT, 1)
+
+
+def study_pair(scene, h, w):
+    for b, r, pat, ln in bounce_rays(scene, h, w):
+        base = np.arange(len(r))
+        costs = {'N': 70, 'T': 75, 'loop': 8}
+        print(f'bounce {b}: {len(r)} rays, reference visits per ray mean {ln.mean():.1f}')
+        c, it = schedule_cost(pat, ln, base, 'BBT', {'B': 33, 'T': 75, 'loop': 6})
+        print(f'   single-box records BBT            {c:7.1f} warp-instr/ray  {it:6.1f} iters/warp')
+        for nb in (1, 2, 3):
+            c, it, ln_, lt_ = pair_cost(pat, ln, base, 'static', costs, nb=nb)
+            print(f'   pair static {"N" * nb}T               {c:7.1f} warp-instr/ray  {it:6.1f} iters/warp  lanes per N stage {ln_:4.1f}, per T stage {lt_:4.1f}')
+        for thr in (1, 2, 4, 6, 8, 12, 16, 33):
+            c, it, ln_, lt_ = pair_cost(pat, ln, base, 'vote', costs, thr=thr)
+            print(f'   pair vote, T when >= {thr:2d} at leaves  {c:7.1f} warp-instr/ray  {it:6.1f} iters/warp  lanes per N stage {ln_:4.1f}, per T stage {lt_:4.1f}')
+
+
 if __name__ == '__main__':
     what = sys.argv[1] if len(sys.argv) > 1 else 'orders'
     scene = sys.argv[2] if len(sys.argv) > 2 else 'cornell'
     h, w = (int(sys.argv[3]), int(sys.argv[4])) if len(sys.argv) > 4 else (270, 480)
     MAX_STEPS = int(os.environ.get('LYS_MODEL_MAX_STEPS', MAX_STEPS))
-    (study_schedules if what == 'schedules' else study_orders)(scene, h, w)
+    {'schedules': study_schedules, 'pair': study_pair}.get(what, study_orders)(scene, h, w)
