@@ -977,7 +977,7 @@ int lys_probe_pass(struct futhark_context *ctx, const struct futhark_opaque_stat
     std::vector<uint8_t> ch;
     if (channel) { ch.resize(np); CU(ctx, cudaMemcpyAsync(ch.data(), b.chan, np, cudaMemcpyDeviceToHost, ctx->stream)); }
     CU(ctx, cudaStreamSynchronize(ctx->stream));
-    if (channel) for (size_t i = 0; i < np; i++) channel[i] = ch[i];
+    if (channel) for (size_t i = 0; i < np; i++) { int col, rl; path_tile((int)gw, (int)gh, (int)i, col, rl); channel[(size_t)rl * gw + col] = ch[i]; }   /* path order -> pixel order */
     /* probes off again for the timed paths */
     raw_free(ctx->bufs.probe_rad); raw_free(ctx->bufs.probe_dist);
     return 0;

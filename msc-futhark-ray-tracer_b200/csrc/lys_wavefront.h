@@ -30,6 +30,21 @@ struct FrameParams {
     float intensity_factor;     /* 1, or 1/spp for sample_points_n (lib.fut:39,42) */
 };
 
+/* Path id -> pixel.  Path ids are an implementation detail (everything a pixel's value depends on is keyed by the PIXEL index:
+ * rng stream integrator.fut:109-114, framebuffer position), so they are laid out for the hardware: a warp's 32 consecutive
+ * ids cover an 8 x 4 pixel tile instead of a 32 x 1 strip -- camera rays of a warp walk the same nodes, and the paths they
+ * start stay close.  The local rows (this rank's rows of the interleaved partition) are cut into bands of 4; a band is
+ * gw / 8 full tiles, then the gw % 8 leftover columns; an incomplete last band is walked row by row.  A bijection for any size. */
+LYS_HDI void path_tile(int gw, int lrows, int pid, int &col, int &rl) {
+    const int band_sz = 4 * gw;
+    const int band = pid / band_sz, q = pid - band * band_sz;
+    if (band * 4 + 4 > lrows) { const int r = q / gw; rl = band * 4 + r; col = q - r * gw; return; }
+    const int full = gw >> 3;
+    if (q < 32 * full) { const int t = q >> 5, k = q & 31; col = t * 8 + (k & 7); rl = band * 4 + (k >> 3); return; }
+    const int rem = gw & 7, q2 = q - 32 * full, r = q2 / rem;
+    rl = band * 4 + r; col = full * 8 + (q2 - r * rem);
+}
+
 /* Work buffers, sized for `cap` paths.  Path state is indexed by path id (= local pixel index),
  * queues and shadow records by queue slot. */
 struct PassBuffers {

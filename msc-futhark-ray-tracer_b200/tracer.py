@@ -325,20 +325,26 @@ class State:
     def advance_rng(self, k):
         return State(self.ctx, self._entry('lys_state_advance_rng', self._p, k))
 
-    def _take(self, arr, nm, dtype):
+    def _take(self, arr, nm, dtype, out=None):
         L = self.ctx._L
         rank = int(nm[-2])
         shp = getattr(L, 'futhark_shape_' + nm)(self.ctx._ctx, arr)
         shape = tuple(int(shp[i]) for i in range(rank))
-        out = np.empty(shape, dtype)
+        if out is None:
+            out = np.empty(shape, dtype)
+        elif out.shape != shape or out.dtype != dtype or not out.flags['C_CONTIGUOUS']:
+            getattr(L, 'futhark_free_' + nm)(self.ctx._ctx, arr)
+            raise ValueError('out must be a C-contiguous %s array of shape %s' % (np.dtype(dtype).name, shape))
         try:
             self.ctx.check(getattr(L, 'futhark_values_' + nm)(self.ctx._ctx, arr, _ptr(out)), 'futhark_values_' + nm)
         finally:
             getattr(L, 'futhark_free_' + nm)(self.ctx._ctx, arr)
         return out
 
-    def render(self):
-        return self._take(self._entry('futhark_entry_render', self._p), 'i32_2d', np.int32)
+    def render(self, out=None):
+        """futhark_entry_render + futhark_values_i32_2d + futhark_free_i32_2d (liblys.c:113-115).  `out`: a frame buffer to
+        fill (the reference host reads every frame into the same SDL surface); default: a new array."""
+        return self._take(self._entry('futhark_entry_render', self._p), 'i32_2d', np.int32, out)
 
     def sample_n_frames(self, n):
         return self._take(self._entry('futhark_entry_sample_n_frames', self._p, n), 'f32_3d', np.float32)

@@ -29,14 +29,14 @@ def main():
     d = np.load(os.path.join(ROOT, 'tests', 'golden', 'scenes', name + '.npz'))
     with pkg.Context() as ctx:
         s = pkg.State.init(ctx, d['tris'], d['tri_mats'], d['mats'], h, w).resize(h, w).key(pkg.KEY['m'])   # accumulate on
-        out = None
+        out = np.empty((h, w), np.int32)                        # the host's frame buffer (liblys.c:66 allocates it once per window size)
         for phase, n in (('warm-up', 20), ('timed', frames)):
             t0 = time.perf_counter()
             for _ in range(n):
                 nxt = s.step()
                 s.free()
                 s = nxt
-                out = s.render()                                 # render + values_i32_2d + free_i32_2d
+                s.render(out)                                    # render + values_i32_2d + free_i32_2d
             dt = time.perf_counter() - t0
         info = s.info()
         print(json.dumps({'loop': 'step + render + values_i32_2d per frame (liblys.c:104-123)', 'scene': name, 'res': '%dx%d' % (w, h),
