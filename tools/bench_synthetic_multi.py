@@ -33,6 +33,7 @@ def main():
     ap.add_argument('--width', type=int, default=3840)
     ap.add_argument('--height', type=int, default=2160)
     ap.add_argument('--reps', type=int, default=2)
+    ap.add_argument('--check-passes', type=int, default=0, help='rows mode: compare a frame of this many passes bit for bit with the unpartitioned render on rank 0')
     a = ap.parse_args()
     rank, world, local = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1)), int(os.environ.get('LOCAL_RANK', 0))
     torch.cuda.set_device(local)
@@ -77,13 +78,43 @@ def main():
         state.free_f32_3d(hnd)
         if best is None or ms.item() < best[0]:
             best = (float(ms.item()), mean)
+    # the one collective on its own: sum-reduce of a framebuffer-sized device buffer to rank 0
+    reduce_ms = None
+    if world > 1:
+        buf = torch.zeros((a.height, a.width, 3), dtype=torch.float32, device=dev)
+        with torch.cuda.stream(stream):
+            par.reduce_framebuffer(buf, dst=0)
+        sync()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            r0.record(stream)
+            for _ in range(5):
+                par.reduce_framebuffer(buf, dst=0)
+            r1.record(stream)
+        sync()
+        t = torch.tensor([r0.elapsed_time(r1) / 5], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        reduce_ms = float(t.item())
+    bit_exact = None
+    if a.mode == 'rows' and a.check_passes > 0:
+        hnd, view = frame(a.check_passes)
+        sync()
+        if rank == 0:
+            got = view.cpu().numpy().copy()
+        state.free_f32_3d(hnd)
+        if rank == 0:
+            full = pkg.Context(device=local)
+            want = pkg.State.init(full, tris, tri_mats, d['mats'], a.height, a.width).sample_n_frames(a.check_passes)
+            bit_exact = bool(np.array_equal(got.view(np.uint32), want.view(np.uint32)))
+            full.close()
     if rank == 0:
         ms, mean = best
         print(json.dumps({'config': '5 synthetic cornell k=%d' % a.k, 'tris': int(len(tris)), 'res': '%dx%d' % (a.width, a.height),
                           'passes': a.passes, 'mode': a.mode, 'n_gpus': world, 'frame_ms': round(ms, 2),
                           'mpaths_s': round(a.width * a.height * a.passes / (ms * 1e-3) / 1e6, 1), 'scaling': 'strong',
                           'lbvh_build_ms': round(build_ms, 3), 'image_mean': mean,
-                          'reduce_bytes': a.width * a.height * 12}), flush=True)
+                          'reduce_bytes': a.width * a.height * 12, 'reduce_ms': None if reduce_ms is None else round(reduce_ms, 3),
+                          'rows_image_bit_exact_vs_single_gpu': bit_exact, 'check_passes': a.check_passes or None}), flush=True)
     sync()
     state.free()
     ctx.close()
