@@ -16,6 +16,8 @@
 #include <cstring>
 #include <algorithm>
 #include <map>
+#include <deque>
+#include <atomic>
 #include <memory>
 #include <string>
 #include <vector>
@@ -46,6 +48,14 @@ struct futhark_context {
     int pipeline = 8;
     int *h_counts = nullptr;             /* pinned: queue lengths of a recent pass (grid sizing only, see run_sample_pass) */
     uint64_t est_tag = 0;                /* what the estimates are about: scene, camera, path length */
+    /* stepping loop of an interactive host (liblys.c:104-123: step, render, values, repeat): once the host steps the state
+     * the previous step returned, the following steps are started AHEAD on the pass-slot streams (see futhark_entry_step),
+     * so frame k's render + read-back overlap the passes of frames k+1 ..; states are immutable values, so a step computed
+     * ahead is the step the host asks for next, bit for bit -- or it is dropped. */
+    struct Ahead { uint64_t in_serial; struct futhark_opaque_state *out; };
+    std::deque<Ahead> ahead;
+    uint64_t last_step_out = 0;          /* serial of the state the latest futhark_entry_step returned */
+    int ahead_depth = 3; uint64_t ahead_slot = 0;
 };
 
 namespace {
@@ -199,6 +209,13 @@ struct futhark_opaque_state {                          /* state.fut:8-19 */
     uint32_t cam_conf_id;
     Camera cam;
     std::shared_ptr<SceneHolder> scene;
+    /* a state produced on a pass-slot stream (futhark_entry_step in a stepping loop): `ready` is recorded behind the kernels
+     * that write its image.  The context's stream is made to wait for it when the state is handed to the host (or dropped),
+     * so every other entry point, all of which work on the context's stream, sees a finished image; the input image stays
+     * referenced until then. */
+    struct Sync { cudaEvent_t ready = nullptr; DevRef prev_img; ~Sync() { if (ready) cudaEventDestroy(ready); } };
+    std::shared_ptr<Sync> sync;
+    uint64_t serial = 0;                 /* identity of this value (pointers are reused by the allocator) */
 };
 
 template <class T, int R> struct fut_array { DevRef mem; int64_t shape[R]; int64_t count() const { int64_t c = 1; for (int i = 0; i < R; i++) c *= shape[i]; return c; } T *ptr() const { return (T *)mem->p; } };
@@ -378,7 +395,8 @@ uint32_t h_rng_from_seed(int32_t seed) {                                        
     return lys_pin_rng_from_seed(seed);
 }
 
-futhark_opaque_state *clone_state(const futhark_opaque_state *s) { return new futhark_opaque_state(*s); }
+std::atomic<uint64_t> g_state_serial{1};
+futhark_opaque_state *clone_state(const futhark_opaque_state *s) { futhark_opaque_state *r = new futhark_opaque_state(*s); r->serial = g_state_serial++; return r; }
 
 
 /* sample_frame / sample_frame_accum (integrator.fut:172-192) into `img` */
@@ -390,6 +408,15 @@ bool sample_into(futhark_context *ctx, const futhark_opaque_state *s, uint32_t r
     CUB(ctx, run_accumulate(fp, ctx->bufs, img_old, img_new, merge ? 1 : 0, n_frames, ctx->stream, &ctx->launches, &ctx->timer));
     if (ctx->timer.on && ctx->timer.used > 3000) ctx->timer.resolve(ctx->stream);
     return true;
+}
+
+/* drop the steps computed ahead; the context's stream waits for their kernels before their images return to the pool */
+void drop_ahead(futhark_context *ctx) {
+    for (auto &a : ctx->ahead) {
+        if (a.out->sync && a.out->sync->ready) cudaStreamWaitEvent(ctx->stream, a.out->sync->ready, 0);
+        delete a.out;
+    }
+    ctx->ahead.clear();
 }
 
 } // namespace
@@ -440,6 +467,7 @@ struct futhark_context *futhark_context_new(struct futhark_context_config *cfg) 
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return nullptr; }
     cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1); cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
     { const char *pe = getenv("LYS_PIPELINE"); if (pe) { int v = atoi(pe); if (v >= 1 && v <= 16) ctx->pipeline = v; } }
+    { const char *ae = getenv("LYS_STEP_AHEAD"); if (ae) { int v = atoi(ae); if (v >= 0 && v <= 4) ctx->ahead_depth = v; } }   /* steps started ahead in a stepping loop (0: none) */
     if (cudaHostAlloc((void **)&ctx->h_init, sizeof(*ctx->h_init), cudaHostAllocDefault) != cudaSuccess) { cudaStreamDestroy(ctx->stream); delete ctx; return nullptr; }
     { size_t fr = 0, tot = 0; if (cudaMemGetInfo(&fr, &tot) == cudaSuccess) ctx->pool_cap = std::max<size_t>((size_t)1 << 30, tot / 8); else cudaGetLastError(); }
     if (cudaHostAlloc((void **)&ctx->h_counts, sizeof(int) * (LYS_MAX_PATH_LEN + 1), cudaHostAllocDefault) == cudaSuccess) {
@@ -452,6 +480,7 @@ struct futhark_context *futhark_context_new(struct futhark_context_config *cfg) 
 void futhark_context_free(struct futhark_context *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    drop_ahead(ctx);
     cudaStreamSynchronize(ctx->stream);
     for (auto &sl : ctx->slots) { cudaStreamSynchronize(sl.stream); free_bufs(sl.bufs, false); cudaStreamDestroy(sl.stream); cudaEventDestroy(sl.done); }
     ctx->slots.clear();
@@ -549,7 +578,11 @@ LYS_ARRAY_API(f32_3d, float, 3, LYS_D3, LYS_I3)
 LYS_ARRAY_API(u32_1d, uint32_t, 1, LYS_D1, LYS_I1)
 LYS_ARRAY_API(i32_2d, int32_t, 2, LYS_D2, LYS_I2)
 
-int futhark_free_opaque_state(struct futhark_context *ctx, struct futhark_opaque_state *obj) { (void)ctx; delete obj; return 0; }
+int futhark_free_opaque_state(struct futhark_context *ctx, struct futhark_opaque_state *obj) {
+    if (ctx && obj && !ctx->ahead.empty() && ctx->ahead.front().in_serial == obj->serial) { cudaSetDevice(ctx->device); drop_ahead(ctx); }   /* nobody can ask for them any more */
+    delete obj;
+    return 0;
+}
 
 /* ---- init (lib.fut:76-106) ---- */
 int futhark_entry_init(struct futhark_context *ctx, struct futhark_opaque_state **out0, const int32_t seed, const uint32_t h,
@@ -580,7 +613,7 @@ int futhark_entry_init(struct futhark_context *ctx, struct futhark_opaque_state 
     const size_t light_chunks = (c + 1023) / 1024;
     unsigned char *mat_flag = nullptr; int *light_chunk = nullptr, *light_info = nullptr;
     if (!H.take(ctx, sc.tris, 9 * c) || !H.take(ctx, sc.tri_mats, c) || !H.take(ctx, sc.mats, (size_t)m * 28) ||
-        !H.take(ctx, sc.leaf_tri, 4 * c) || !H.take(ctx, sc.leaf_box, 2 * c) || !H.take(ctx, sc.nodes, 4 * c) ||
+        !H.take(ctx, sc.leaf_tri, 4 * c) || !H.take(ctx, sc.leaf_box, 2 * c) || !H.take(ctx, sc.leaf_frame, 3 * c) || !H.take(ctx, sc.nodes, 4 * c) ||
         !H.take(ctx, sc.node_box, 2 * c) || !H.take(ctx, sc.left, c) || !H.take(ctx, sc.right, c) || !H.take(ctx, sc.parent, c) ||
         !H.take(ctx, sc.height, c) || !H.take(ctx, sc.morton, c) || !H.take(ctx, sc.sorted_idx, c) || !H.take(ctx, sc.bounds, 8) ||
         !H.take(ctx, sc.lights, (size_t)light_cap) || !H.take(ctx, sc.light_src, (size_t)light_cap) ||
@@ -613,6 +646,7 @@ int futhark_entry_init(struct futhark_context *ctx, struct futhark_opaque_state 
     const float org[3] = {rb->origin[0], rb->origin[1], rb->origin[2]};
 
     futhark_opaque_state *s = new futhark_opaque_state();
+    s->serial = g_state_serial++;
     s->dim_w = w; s->dim_h = h; s->subsampling = 1;
     s->rng = h_rng_from_seed(seed);
     s->img_h = h; s->img_w = w;
@@ -679,6 +713,41 @@ int futhark_entry_key(struct futhark_context *ctx, struct futhark_opaque_state *
     return 0;
 }
 
+/* ---- step (lib.fut:111-118) ----
+ * step_on_slot: one step computed on a pass-slot stream instead of the context's stream.  The slot stream first waits for
+ * everything issued on the context's stream so far (the block pool is ordered on that stream), and its accumulate kernel for
+ * the input state's own `ready` event. */
+static futhark_opaque_state *step_on_slot(struct futhark_context *ctx, const struct futhark_opaque_state *s) {
+    uint32_t gw, gh; grid_dims(s, gw, gh);
+    const bool accum = s->mode && s->n_frames > 0;
+    if (accum && (s->img_w != gw || s->img_h != gh)) return nullptr;
+    const int S = ctx->ahead_depth + 1;
+    if (!ensure_slots(ctx, S, (int64_t)gw * gh)) return nullptr;
+    futhark_context::PassSlot &sl = ctx->slots[ctx->ahead_slot++ % (uint64_t)S];
+    std::unique_ptr<futhark_opaque_state> r(clone_state(s));
+    r->img = dev_alloc(ctx, sizeof(float) * 3 * (size_t)gw * gh);
+    if (!r->img) return nullptr;
+    r->img_w = gw; r->img_h = gh;
+    r->sync = std::make_shared<futhark_opaque_state::Sync>();
+    r->sync->prev_img = s->img;
+    FrameParams fp;
+    if (!make_frame_params(ctx, s, s->rng, 1.0f, fp)) return nullptr;
+    if (!cu_ok(ctx, cudaEventCreateWithFlags(&r->sync->ready, cudaEventDisableTiming), "cudaEventCreate") ||
+        !cu_ok(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream), "cudaEventRecord") ||
+        !cu_ok(ctx, cudaStreamWaitEvent(sl.stream, ctx->ev_fork, 0), "cudaStreamWaitEvent")) return nullptr;
+    /* the pass reads the scene and the state's scalars only; the input IMAGE is needed by the accumulate kernel, so the wait
+     * for the state that produces it goes between the two: the passes of consecutive steps overlap, as in sample_n_frames */
+    const bool ok = cu_ok(ctx, run_sample_pass(s->scene->d, fp, sl.bufs, sl.stream, &ctx->launches, nullptr, ctx->h_counts), "sample pass") &&
+                    (!s->sync || cu_ok(ctx, cudaStreamWaitEvent(sl.stream, s->sync->ready, 0), "cudaStreamWaitEvent")) &&
+                    cu_ok(ctx, run_accumulate(fp, sl.bufs, (const float *)s->img->p, (float *)r->img->p, accum ? 1 : 0, (float)s->n_frames, sl.stream, &ctx->launches), "accumulate");
+    /* whatever was launched writes r->img: the event goes behind it in any case, and the caller orders the context's stream
+     * after it before the image can go back to the pool */
+    cudaEventRecord(r->sync->ready, sl.stream);
+    if (!ok) { cudaStreamWaitEvent(ctx->stream, r->sync->ready, 0); return nullptr; }
+    r->rng = h_advance_rng(s->rng);                                                /* integrator.fut:116 */
+    r->n_frames = accum ? s->n_frames + 1 : 1;
+    return r.release();
+}
 int futhark_entry_step(struct futhark_context *ctx, struct futhark_opaque_state **out0, const struct futhark_opaque_state *s) { /* lib.fut:111-118 */
     if (!ctx) return 1;
     if (!out0 || !s) { set_error(ctx, "step: null argument"); return 1; }
@@ -686,15 +755,39 @@ int futhark_entry_step(struct futhark_context *ctx, struct futhark_opaque_state 
     uint32_t gw, gh; grid_dims(s, gw, gh);
     bool accum = s->mode && s->n_frames > 0;
     if (accum && (s->img_w != gw || s->img_h != gh)) { set_error(ctx, "step: accumulated image shape does not match the sample grid"); return 1; }
-    futhark_opaque_state *r = clone_state(s);
-    size_t bytes = sizeof(float) * 3 * (size_t)gw * gh;
-    r->img = dev_alloc(ctx, bytes);
-    if (!r->img) { delete r; return 1; }
-    if (ctx->world > 1 && cudaMemsetAsync(r->img->p, 0, bytes, ctx->stream) != cudaSuccess) { delete r; set_error(ctx, "memset failed"); return 1; }
-    r->img_w = gw; r->img_h = gh;
-    if (!sample_into(ctx, s, s->rng, (const float *)s->img->p, (float *)r->img->p, accum, (float)s->n_frames)) { delete r; return 1; }
-    r->rng = h_advance_rng(s->rng);                                                /* integrator.fut:116 */
-    r->n_frames = accum ? s->n_frames + 1 : 1;
+    /* the host steps the state the previous step returned: a stepping loop.  Not with a row partition (the caller reduces
+     * the image itself), per-launch timing, or the flash preset (its light records are re-uploaded per pass). */
+    const bool loop = ctx->ahead_depth > 0 && s->serial == ctx->last_step_out && ctx->world == 1 && !ctx->timer.on && s->cam.conf.tx_kind != 1;
+    futhark_opaque_state *r = nullptr;
+    if (!ctx->ahead.empty() && ctx->ahead.front().in_serial == s->serial) {         /* computed ahead */
+        r = ctx->ahead.front().out;
+        ctx->ahead.pop_front();
+    } else {
+        drop_ahead(ctx);
+        if (loop) r = step_on_slot(ctx, s);
+        if (!r) {                                                                   /* on the context's stream */
+            r = clone_state(s);
+            size_t bytes = sizeof(float) * 3 * (size_t)gw * gh;
+            r->img = dev_alloc(ctx, bytes);
+            if (!r->img) { delete r; return 1; }
+            if (ctx->world > 1 && cudaMemsetAsync(r->img->p, 0, bytes, ctx->stream) != cudaSuccess) { delete r; set_error(ctx, "memset failed"); return 1; }
+            r->img_w = gw; r->img_h = gh;
+            r->sync.reset();
+            if (!sample_into(ctx, s, s->rng, (const float *)s->img->p, (float *)r->img->p, accum, (float)s->n_frames)) { delete r; return 1; }
+            r->rng = h_advance_rng(s->rng);                                         /* integrator.fut:116 */
+            r->n_frames = accum ? s->n_frames + 1 : 1;
+        }
+    }
+    if (r->sync && r->sync->ready) CU(ctx, cudaStreamWaitEvent(ctx->stream, r->sync->ready, 0));   /* every later call sees the finished image */
+    ctx->last_step_out = r->serial;
+    if (loop) {                                                                     /* start the next steps now */
+        while ((int)ctx->ahead.size() < ctx->ahead_depth) {
+            const futhark_opaque_state *base = ctx->ahead.empty() ? r : ctx->ahead.back().out;
+            futhark_opaque_state *nx = step_on_slot(ctx, base);
+            if (!nx) { ctx->error.clear(); break; }                                  /* a step that cannot run ahead is reported when the host asks for it */
+            ctx->ahead.push_back({base->serial, nx});
+        }
+    }
     *out0 = r;
     return 0;
 }

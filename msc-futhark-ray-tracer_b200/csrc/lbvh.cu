@@ -342,7 +342,7 @@ k_rs_onesweep(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__
 __global__ void k_gather_leaves(const float *__restrict__ tris, const uint32_t *__restrict__ tri_mats,
                                 const float4 *__restrict__ box_c, const float4 *__restrict__ box_h,
                                 const uint32_t *__restrict__ sorted_idx, int n,
-                                float4 *__restrict__ leaf_tri /* [n][4] */, float4 *__restrict__ leaf_box /* [n][2] */) {
+                                float4 *__restrict__ leaf_tri /* [n][4] */, float4 *__restrict__ leaf_box /* [n][2] */, float4 *__restrict__ leaf_frame /* [n][3] */) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t s = sorted_idx[i];
@@ -356,6 +356,13 @@ __global__ void k_gather_leaves(const float *__restrict__ tris, const uint32_t *
     leaf_tri[4ll * i + 3] = make_float4(e2.x, e2.y, e2.z, 0.0f);
     leaf_box[2ll * i + 0] = box_c[s];
     leaf_box[2ll * i + 1] = box_h[s];
+    /* the shading frame of a hit on this triangle depends on the triangle only: unit normal (shapes.fut:84, never flipped) and
+     * mk_orthonormal_basis of it (material.fut:374-379), computed here once with the operations k_shade would repeat per vertex */
+    const V3 nn = normalise(nc);
+    const Onb f = make_onb(nn);
+    leaf_frame[3ll * i + 0] = make_float4(nn.x, nn.y, nn.z, 0.0f);
+    leaf_frame[3ll * i + 1] = make_float4(f.b.x, f.b.y, f.b.z, 0.0f);
+    leaf_frame[3ll * i + 2] = make_float4(f.t.x, f.t.y, f.t.z, 0.0f);
 }
 
 /* ------------------------------------------------------------------ Karras radix tree */
@@ -640,7 +647,7 @@ cudaError_t build_lbvh(SceneDev &sc, BuildScratch &ws, int refit_mode, cudaStrea
     /* 4 passes -> result back in buffer 0 */
     cudaMemcpyAsync(sc.morton, ws.keys[cur], (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, stream);
     cudaMemcpyAsync(sc.sorted_idx, ws.vals[cur], (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, stream);
-    k_gather_leaves<<<cdiv(n, T), T, 0, stream>>>(sc.tris, sc.tri_mats, ws.box_c, ws.box_h, sc.sorted_idx, n, sc.leaf_tri, sc.leaf_box); nl++;
+    k_gather_leaves<<<cdiv(n, T), T, 0, stream>>>(sc.tris, sc.tri_mats, ws.box_c, ws.box_h, sc.sorted_idx, n, sc.leaf_tri, sc.leaf_box, sc.leaf_frame); nl++;
     k_karras<<<cdiv(n_nodes, T), T, 0, stream>>>(sc.morton, n, sc.left, sc.right, sc.parent, ws.leaf_parent); nl++;
     cudaMemsetAsync(ws.visits, 0, (size_t)n_nodes * sizeof(unsigned int), stream);
     k_refit<<<cdiv(n, T), T, 0, stream>>>(sc.left, sc.right, sc.parent, ws.leaf_parent, sc.leaf_box, ws.F, sc.height, ws.visits, n); nl++;

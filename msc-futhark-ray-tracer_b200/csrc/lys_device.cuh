@@ -223,14 +223,15 @@ LYS_DN_RTERMS void reflection_terms(V3 wo, V3 wi, const Mat1 &m, float &bsdf, fl
     pdf = same_hemi(wo, wi) ? (D * lys_fabsf(wh.z)) / (4.0f * dot(wo, wh)) : 0.0f;
 }
 /* uber_bsdf (:357-358) and uber_pdf (:360-361, operands as written in the reference) in local space */
-LYS_DN_UBER void uber_eval(V3 wo, V3 wi, const Mat1 &m, float &f, float &pdf) {
+/* have_F: F_pre = schlick(wo, m) computed by the caller (it depends on the vertex only and is needed up to three times) */
+LYS_DN_UBER void uber_eval(V3 wo, V3 wi, const Mat1 &m, float &f, float &pdf, bool have_F = false, float F_pre = 0.0f) {
     float refl_f, refl_pdf;
     reflection_terms(wo, wi, m, refl_f, refl_pdf);
     float refr_f = lerpf(0.0f, m.color * LYS_INV_PI, m.opacity);                              /* :187-188 */
     float diff_pdf = same_hemi(wo, wi) ? wi.z * LYS_INV_PI : 0.0f;                             /* :117-120 */
     float refr_pdf = lerpf(0.0f, diff_pdf, m.opacity);                                         /* :190-193 */
     bool inside = wo.z <= 0.0f;
-    float F = inside ? 0.0f : schlick(wo, m);
+    float F = inside ? 0.0f : (have_F ? F_pre : schlick(wo, m));
     float diel_f = lerpf(refr_f, refl_f, F);                                                   /* :317-323 */
     float diel_pdf = inside ? refr_pdf : lerpf(refr_pdf, refl_pdf, F);                         /* :325-330 */
     f = lerpf(diel_f, m.color * refl_f, m.metalness);
@@ -285,12 +286,12 @@ LYS_DN_REFR DirSample sample_refraction(V3 wo, const Mat1 &m, uint32_t &rng) {
 }
 /* The draws of uber_sample_dir (:365-370) that come before its branch: metal (:352-355), else Fresnel coin (:338-344).
  * Returns true for the reflection branch; rng is left where the chosen sampler starts. */
-LYS_D bool bsdf_choose(V3 wo, const Mat1 &m, uint32_t &rng, bool &metal) {
+LYS_D bool bsdf_choose(V3 wo, const Mat1 &m, uint32_t &rng, bool &metal, bool have_F = false, float F_pre = 0.0f) {
     float p = rng_unit(rng);
     metal = p < m.metalness;
     if (metal) return true;
     if (wo.z <= 0.0f) return false;
-    float r = schlick(wo, m); float q = rng_unit(rng);
+    float r = have_F ? F_pre : schlick(wo, m); float q = rng_unit(rng);
     return q < r;
 }
 /* sample_dir (:406-410) = uber_sample_dir (:365-370) in the local frame */

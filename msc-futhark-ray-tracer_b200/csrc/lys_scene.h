@@ -7,6 +7,7 @@
  *   leaf_tri  [n][4]  float4  sorted leaves, 64 B: (a.xyz | mat_ix), (e1 x e2 | source index) = the plane test's sector,
  *                             then (e1.xyz | 0), (e2.xyz | 0) for the barycentric test
  *   leaf_box  [n][2]  float4  sorted leaf boxes (center | half_dims)
+ *   leaf_frame [n][3] float4  shading frame of a hit on the leaf: unit normal, then b and t of mk_orthonormal_basis (material.fut:374-379)
  *   nodes     [n][4]  float4  traversal records, 64 B = two sectors: record i < n-1 holds the boxes of BOTH children of node i,
  *                             (Lmin.xyz | left) (Lmax.xyz | right) (Rmin.xyz | 0) (Rmax.xyz | 0); the box slot of a leaf child
  *                             is zero (leaves are never box-tested, bvh.fut:133).  Record n-1 is the super-root: left = node 0
@@ -43,7 +44,7 @@ struct LightRec {            /* 32 floats = 128 B, float4-aligned */
 struct SceneDev {
     int64_t n_tris = 0, n_mats = 0, n_lights = 0;
     float *tris = nullptr; uint32_t *tri_mats = nullptr; float *mats = nullptr;
-    float4 *leaf_tri = nullptr, *leaf_box = nullptr, *nodes = nullptr, *node_box = nullptr;
+    float4 *leaf_tri = nullptr, *leaf_box = nullptr, *leaf_frame = nullptr, *nodes = nullptr, *node_box = nullptr;
     float4 *nodes_oct = nullptr;           /* null for scenes above LYS_OCT_MAX_NODES */
     int single_nodes = 0;                  /* nodes_oct holds single-box records (scenes up to LYS_SINGLE_MAX_TRIS triangles) */
     int *left = nullptr, *right = nullptr, *parent = nullptr, *height = nullptr;

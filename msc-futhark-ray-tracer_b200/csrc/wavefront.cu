@@ -290,6 +290,7 @@ struct VertexCtx {
     float wavelen, t;
     uint32_t rng;                 /* state after the per-vertex advance_rng (integrator.fut:48) */
     Onb onb; Mat1 m; const float *mrow;
+    float F;                      /* schlick(wo_l, m) (material.fut:207-211) when wo_l.z > 0: used by the light sample's bsdf_f and by both sample_dir calls */
 };
 LYS_D bool shade_prologue(const SceneDev &sc, const PassBuffers &b, int bounce, int i, VertexCtx &v) {
     v.pid = b.queue[bounce & 1][i];
@@ -305,12 +306,15 @@ LYS_D bool shade_prologue(const SceneDev &sc, const PassBuffers &b, int bounce, 
     V3 nc = v3(q1.x, q1.y, q1.z);                                          /* e1 x e2, stored by the build */
     { float inv; V3 s; (void)tri_plane_test(v.o, v.d, v3(q0.x, q0.y, q0.z), nc, FLT_MAX, v.t, inv, s); }   /* bvh.fut:143-145: t of the winner */
     v.pos = v.o + v.t * v.d;
-    v.n = normalise(nc);
+    const float4 *fq = sc.leaf_frame + 3ll * v.leaf;                       /* normalise(nc) and mk_orthonormal_basis of it, stored by the build */
+    float4 f0 = __ldg(fq), f1 = __ldg(fq + 1), f2 = __ldg(fq + 2);
+    v.n = v3(f0.x, f0.y, f0.z);
+    v.onb.n = v.n; v.onb.b = v3(f1.x, f1.y, f1.z); v.onb.t = v3(f2.x, f2.y, f2.z);
     rng_advance(v.rng);                                                   /* integrator.fut:48 */
     v.wo = -v.d;
-    v.onb = make_onb(v.n);
     v.m = material_at(v.mrow, v.wavelen);
     v.wo_l = to_local(v.onb, v.wo);
+    v.F = (v.wo_l.z <= 0.0f) ? 0.0f : schlick(v.wo_l, v.m);
     return true;
 }
 /* direct.fut:116-119: one raw draw picks the light (scene lights, then the 8 transmitter lights of this ray) */
@@ -340,7 +344,7 @@ LYS_D void shade_light_sample(const VertexCtx &v, const LightD &l, float &cL, fl
     bool facing = !(dot(wi, v.n) <= 0.0f);                                 /* direct.fut:12 */
     if (facing && !(pdf == 0.0f || in_rad == 0.0f)) {                      /* direct.fut:51-53,73-74 */
         float f, spdf;
-        uber_eval(v.wo_l, to_local(v.onb, wi), v.m, f, spdf);
+        uber_eval(v.wo_l, to_local(v.onb, wi), v.m, f, spdf, true, v.F);
         f = f * lys_fabsf(dot(wi, v.n));
         float weight = balance1(pdf, spdf);
         cL = f * weight * in_rad / pdf;
@@ -451,7 +455,7 @@ template <class SH>
 LYS_D void shade_draw_or_queue(SH &sh, bool want, int slot, const VertexCtx &v, uint32_t &rng, bool &metal) {
     bool reflect = false; metal = false;
     if (want) {
-        reflect = bsdf_choose(v.wo_l, v.m, rng, metal);
+        reflect = bsdf_choose(v.wo_l, v.m, rng, metal, true, v.F);
         if (reflect) {
             sh.res[0][slot] = v.wo_l.x; sh.res[1][slot] = v.wo_l.y; sh.res[2][slot] = v.wo_l.z;
             sh.res[3][slot] = v.m.roughness; sh.res[4][slot] = __uint_as_float(rng);

@@ -128,6 +128,8 @@ def fuzz_keys(ctx, rng, count):
         so, sg = oracle.State.init(*scene, h, w, **kw), pkg.State.init(ctx, *scene, h, w, **kw)
         trace = []
         errored = [False]
+        free_old = [False]
+        saved = None                        # an older pair of states, stepped again later (the library may have run ahead of it)
 
         def step_both():
             """one step on both sides; accumulating onto an image of another shape is a run-time size error in the reference
@@ -142,7 +144,10 @@ def fuzz_keys(ctx, rng, count):
                 except pkg.TracerError:
                     errored[0] = True
                     return False
-            so, sg = so.step(), sg.step()
+            so = so.step()
+            old, sg = sg, sg.step()
+            if free_old[0]:
+                old.free()                  # the interactive host's pattern (liblys.c:110): the stepped state is freed at once
             return True
         for _ in range(int(rng.integers(5, 40))):
             r = rng.random()
@@ -156,10 +161,28 @@ def fuzz_keys(ctx, rng, count):
                 h, w = int(rng.integers(4, 24)), int(rng.integers(4, 32))
                 so, sg = so.resize(h, w), sg.resize(h, w)
                 trace.append(('resize', h, w))
-            else:
+            elif r < 0.80:
                 if not step_both():
                     break
                 trace.append(('step',))
+            elif r < 0.93:                  # a stepping loop as the interactive host runs it: the library starts steps ahead
+                free_old[0] = bool(rng.random() < 0.7)
+                n = int(rng.integers(2, 7))
+                ok = True
+                for k in range(n):
+                    ok = ok and step_both()
+                    if ok and k == 1 and saved is None and not free_old[0] and rng.random() < 0.5:
+                        saved = (so, sg)
+                    if ok and rng.random() < 0.3:
+                        sg.render()         # render + read-back between the steps
+                free_old[0] = False
+                trace.append(('steps', n))
+                if not ok:
+                    break
+            elif saved is not None:         # back to an older state: what was computed ahead of the newer one is dropped
+                so, sg = saved
+                saved = None
+                trace.append(('back',))
         else:
             step_both()
         if errored[0]:

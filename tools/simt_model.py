@@ -261,6 +261,59 @@ def pair_cost(pat, ln, order, policy, costs, thr=8, nb=2):
     return total / n, iters / (len(p) // 32), laneN / max(stageN, 1), laneT / max(stageT, 1)
 
 
+def pair_phased_cost(pat, ln, order, caps, costs, nb=2, requeue=120):
+    """Pair records, static N..NT iterations, in PHASES: a warp stops after caps[k] iterations; rays that are not finished
+    save their walk (stack, current node, tmax), are compacted, and the next phase resumes them in dense warps.
+    `requeue` = warp instructions per warp of 32 resumed rays (save + restore).  Returns warp instructions per ray and the
+    fraction of rays entering each phase."""
+    p = pat[order]
+    n = len(p)
+    keep = (p == 1) | (p == 2) | (p == 3)
+    L = keep.sum(axis=1)
+    width = int(L.max()) + 1
+    kind = np.full((n, width), 2, np.int8)
+    idx = np.cumsum(keep, axis=1) - 1
+    r, c = np.nonzero(keep)
+    kind[r, idx[r, c]] = np.where(p[r, c] == 1, 0, 1)
+    ptr = np.zeros(n, np.int64)
+    live = np.arange(n)
+    total = 0
+    fracs = []
+    for cap in list(caps) + [1 << 30]:
+        if len(live) == 0:
+            break
+        fracs.append(len(live) / n)
+        m = len(live)
+        pad = (-m) % 32
+        rows = np.concatenate([live, np.full(pad, -1, np.int64)])
+        valid = rows >= 0
+        rr = np.where(valid, rows, 0)
+        pp = np.where(valid, ptr[rr], width - 1)
+        if len(fracs) > 1:
+            total += requeue * (len(rows) // 32)
+        it = 0
+        while it < cap:
+            k = np.where(valid, kind[rr, pp], 2)
+            alive = (k != 2).reshape(-1, 32).any(axis=1)
+            if not alive.any():
+                break
+            total += costs['loop'] * int(alive.sum())
+            for _ in range(nb):
+                k = np.where(valid, kind[rr, pp], 2)
+                take = k == 0
+                total += costs['N'] * int(take.reshape(-1, 32).any(axis=1).sum())
+                pp = pp + take
+            k = np.where(valid, kind[rr, pp], 2)
+            take = k == 1
+            total += costs['T'] * int(take.reshape(-1, 32).any(axis=1).sum())
+            pp = pp + take
+            it += 1
+        ptr[rows[valid]] = pp[valid]
+        unfinished = valid & (np.where(valid, kind[rr, pp], 2) != 2)
+        live = rows[unfinished]
+    return total / n, fracs
+
+
 def study_pair(scene, h, w):
     for b, r, pat, ln in bounce_rays(scene, h, w):
         base = np.arange(len(r))
@@ -271,7 +324,10 @@ def study_pair(scene, h, w):
         for nb in (1, 2, 3):
             c, it, ln_, lt_ = pair_cost(pat, ln, base, 'static', costs, nb=nb)
             print(f'   pair static {"N" * nb}T               {c:7.1f} warp-instr/ray  {it:6.1f} iters/warp  lanes per N stage {ln_:4.1f}, per T stage {lt_:4.1f}')
-        for thr in (1, 2, 4, 6, 8, 12, 16, 33):
+        for caps in ((8,), (12,), (16,), (24,), (8, 16), (8, 24), (12, 24), (12, 32), (8, 16, 32), (8, 16, 32, 64)):
+            c, fr = pair_phased_cost(pat, ln, base, caps, costs)
+            print(f'   pair NNT in phases, caps {str(caps):18s} {c:7.1f} warp-instr/ray  rays entering the phases: ' + ' '.join(f'{x:.2f}' for x in fr))
+        for thr in (2, 33):
             c, it, ln_, lt_ = pair_cost(pat, ln, base, 'vote', costs, thr=thr)
             print(f'   pair vote, T when >= {thr:2d} at leaves  {c:7.1f} warp-instr/ray  {it:6.1f} iters/warp  lanes per N stage {ln_:4.1f}, per T stage {lt_:4.1f}')
 
