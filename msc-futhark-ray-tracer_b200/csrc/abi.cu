@@ -56,7 +56,6 @@ struct futhark_context {
     std::deque<Ahead> ahead;
     uint64_t last_step_out = 0;          /* serial of the state the latest futhark_entry_step returned */
     int ahead_depth = 3; uint64_t ahead_slot = 0;
-    bool want_tq = false;                /* the scene about to be sampled uses the phased traversal: its buffer sets carry park queues */
 };
 
 namespace {
@@ -273,15 +272,6 @@ bool ensure_bufs(futhark_context *ctx, PassBuffers &b, int64_t n, bool probes) {
         if (!raw_alloc(ctx, b.counts, LYS_MAX_PATH_LEN + 1) || !raw_alloc(ctx, b.stats, 4) || !raw_alloc(ctx, b.split, 2 * (LYS_MAX_PATH_LEN + 1))) return false;
         CUB(ctx, cudaMemsetAsync(b.stats, 0, 4 * sizeof(unsigned long long), ctx->stream));
     }
-    if (ctx->want_tq && b.tq_cap < (int)std::min<int64_t>(b.cap / 2 + 32, 1 << 30)) {      /* park queues of the phased traversal (pair-layout scenes) */
-        for (int k = 0; k < 2; k++) { raw_free(b.tq_hdr[k]); raw_free(b.tq_tmax[k]); raw_free(b.tq_stack[k]); }
-        b.tq_cap = 0;
-        const size_t qc = (size_t)std::min<int64_t>(b.cap / 2 + 32, 1 << 30);
-        for (int k = 0; k < 2; k++)
-            if (!raw_alloc(ctx, b.tq_hdr[k], qc) || !raw_alloc(ctx, b.tq_tmax[k], qc) || !raw_alloc(ctx, b.tq_stack[k], qc * LYS_TRACE_SAVE_DEPTH)) return false;
-        if (!b.tq_count && !raw_alloc(ctx, b.tq_count, LYS_TRACE_MAX_PHASES * (LYS_MAX_PATH_LEN + 1))) return false;
-        b.tq_cap = (int)qc;
-    }
     if (!ctx->bufs.tx_lights && !raw_alloc(ctx, ctx->bufs.tx_lights, 8)) return false;
     b.tx_lights = ctx->bufs.tx_lights;          /* one copy shared by all buffer sets */
     if (probes && !b.probe_rad) {
@@ -294,8 +284,6 @@ void free_bufs(PassBuffers &b, bool owns_tx) {
     raw_free(b.ray_o[0]); raw_free(b.ray_o[1]); raw_free(b.ray_d[0]); raw_free(b.ray_d[1]); raw_free(b.dist[0]); raw_free(b.dist[1]); raw_free(b.acc);
     raw_free(b.chan); raw_free(b.queue[0]); raw_free(b.queue[1]); raw_free(b.hit); raw_free(b.order[0]); raw_free(b.order[1]); raw_free(b.sh_o); raw_free(b.sh_d1); raw_free(b.sh_d2);
     raw_free(b.sh_c); raw_free(b.counts); raw_free(b.stats); raw_free(b.split); raw_free(b.probe_rad); raw_free(b.probe_dist);
-    for (int k = 0; k < 2; k++) { raw_free(b.tq_hdr[k]); raw_free(b.tq_tmax[k]); raw_free(b.tq_stack[k]); }
-    raw_free(b.tq_count); b.tq_cap = 0;
     if (owns_tx) raw_free(b.tx_lights);
     b.cap = 0;
 }
@@ -414,7 +402,6 @@ futhark_opaque_state *clone_state(const futhark_opaque_state *s) { futhark_opaqu
 /* sample_frame / sample_frame_accum (integrator.fut:172-192) into `img` */
 bool sample_into(futhark_context *ctx, const futhark_opaque_state *s, uint32_t rng, const float *img_old, float *img_new, bool merge, float n_frames) {
     FrameParams fp;
-    ctx->want_tq = trace_phase_count() > 0 && !s->scene->d.single_nodes;
     if (!ensure_pass_buffers(ctx, (int64_t)((s->dim_w + s->subsampling - 1) / s->subsampling) * ((s->dim_h + s->subsampling - 1) / s->subsampling), false)) return false;
     if (!make_frame_params(ctx, s, rng, 1.0f, fp)) return false;
     CUB(ctx, run_sample_pass(s->scene->d, fp, ctx->bufs, ctx->stream, &ctx->launches, &ctx->timer, ctx->h_counts));
@@ -735,7 +722,6 @@ static futhark_opaque_state *step_on_slot(struct futhark_context *ctx, const str
     const bool accum = s->mode && s->n_frames > 0;
     if (accum && (s->img_w != gw || s->img_h != gh)) return nullptr;
     const int S = ctx->ahead_depth + 1;
-    ctx->want_tq = trace_phase_count() > 0 && !s->scene->d.single_nodes;
     if (!ensure_slots(ctx, S, (int64_t)gw * gh)) return nullptr;
     futhark_context::PassSlot &sl = ctx->slots[ctx->ahead_slot++ % (uint64_t)S];
     std::unique_ptr<futhark_opaque_state> r(clone_state(s));
@@ -833,7 +819,6 @@ static int sample_n_frames_impl(struct futhark_context *ctx, struct futhark_f32_
     if (ctx->world > 1) CU(ctx, cudaMemsetAsync(a->ptr(), 0, sizeof(float) * 3 * (size_t)gw * gh, ctx->stream));
     const uint32_t passes = n < 1 ? 1 : n;                               /* the first sample_frame always runs (lib.fut:68) */
     const int S = ctx->timer.on == 1 ? 1 : (int)std::min<uint32_t>((uint32_t)ctx->pipeline, passes);
-    ctx->want_tq = trace_phase_count() > 0 && !s->scene->d.single_nodes;
     if (!ensure_slots(ctx, S, (int64_t)gw * gh)) return 1;
     FrameParams fp;
     if (!make_frame_params(ctx, s, s->rng, 1.0f, fp)) return 1;          /* uploads the flash lights once */
@@ -906,7 +891,6 @@ int futhark_entry_sample_points_n(struct futhark_context *ctx, struct futhark_op
     uint32_t rng = s->rng;
     uint32_t passes = spp < 1 ? 1 : spp;                                           /* the first pass always runs (lib.fut:52) */
     const int S = (int)std::min<uint32_t>((uint32_t)ctx->pipeline, passes);
-    ctx->want_tq = trace_phase_count() > 0 && !s->scene->d.single_nodes;
     if (!ensure_slots(ctx, S, np)) return 1;
     FrameParams fp;
     if (!make_frame_params(ctx, s, rng, factor, fp)) return 1;
@@ -1059,7 +1043,6 @@ int lys_probe_primary(struct futhark_context *ctx, const struct futhark_opaque_s
     cudaSetDevice(ctx->device);
     uint32_t gw, gh; grid_dims(s, gw, gh);
     size_t np = (size_t)gw * gh;
-    ctx->want_tq = trace_phase_count() > 0 && !s->scene->d.single_nodes;
     if (!ensure_pass_buffers(ctx, (int64_t)np, false)) return 1;
     FrameParams fp; if (!make_frame_params(ctx, s, s->rng, 1.0f, fp)) return 1;
     if (ctx->world != 1) { set_error(ctx, "probe requires world_size 1"); return 1; }
@@ -1078,7 +1061,6 @@ int lys_probe_pass(struct futhark_context *ctx, const struct futhark_opaque_stat
     uint32_t gw, gh; grid_dims(s, gw, gh);
     size_t np = (size_t)gw * gh;
     if (ctx->world != 1) { set_error(ctx, "probe requires world_size 1"); return 1; }
-    ctx->want_tq = trace_phase_count() > 0 && !s->scene->d.single_nodes;
     if (!ensure_pass_buffers(ctx, (int64_t)np, true)) return 1;
     FrameParams fp; if (!make_frame_params(ctx, s, s->rng, 1.0f, fp)) return 1;
     PassBuffers b = ctx->bufs;

@@ -45,9 +45,6 @@ LYS_HDI void path_tile(int gw, int lrows, int pid, int &col, int &rl) {
     rl = band * 4 + r; col = full * 8 + (q2 - r * rem);
 }
 
-#define LYS_TRACE_MAX_PHASES 4
-#define LYS_TRACE_SAVE_DEPTH 40     /* stack levels a parked walk can carry */
-
 /* Work buffers, sized for `cap` paths.  Path state is indexed by path id (= local pixel index),
  * queues and shadow records by queue slot. */
 struct PassBuffers {
@@ -70,12 +67,6 @@ struct PassBuffers {
     float4 *sh_d1 = nullptr;    /* dir1.xyz | tmax1 */
     float4 *sh_d2 = nullptr;    /* dir2.xyz | tmax2 */
     float4 *sh_c = nullptr;     /* cL, cB, emission (vertex 0), vertex distance */
-    /* phased traversal (wavefront.cu: k_trace<LAY, true>, k_trace_resume): closest-hit walks that outlive a phase's iteration
-     * budget are parked here -- header (item, cur, sp, closest), tmax, and the walk's stack level-major [level][queue slot] --
-     * and resumed in dense warps by the next phase; two queues, ping-pong between phases; null = no phases */
-    int4 *tq_hdr[2] = {nullptr, nullptr}; float *tq_tmax[2] = {nullptr, nullptr}; int2 *tq_stack[2] = {nullptr, nullptr};
-    int *tq_count = nullptr;    /* [LYS_MAX_PATH_LEN + 1][LYS_TRACE_MAX_PHASES] walks parked per bounce and phase */
-    int tq_cap = 0;             /* queue slots; a walk that finds the queue full (or is deeper than LYS_TRACE_SAVE_DEPTH) goes on in place */
     int *counts = nullptr;      /* [LYS_MAX_PATH_LEN + 1] active paths per bounce */
     unsigned long long *stats = nullptr;   /* [4] vertices, closest rays, shadow rays, paths */
     LightRec *tx_lights = nullptr;         /* [8] flash transmitter lights */
@@ -110,8 +101,6 @@ struct LaunchTimer {
     ~LaunchTimer() { for (auto e : ev0) cudaEventDestroy(e); for (auto e : ev1) cudaEventDestroy(e); }
 };
 
-/* number of budgeted traversal phases configured (0: none): the pass buffers of pair-layout scenes then carry the park queues */
-int trace_phase_count();
 /* one sample pass: generate, (extend, shade, connect) x path_len.  Results stay in bufs.acc. */
 /* est_counts (host, pinned, may be null): queue lengths per bounce of an earlier pass of the same frame; they only size the
  * persistent grids of the sparse late bounces (any grid size is correct: all kernels are grid-stride over device-side counts),

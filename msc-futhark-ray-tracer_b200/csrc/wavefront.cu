@@ -98,7 +98,6 @@ LYS_D bool leaf_test(const RayInv &r, const float4 *__restrict__ leaf_tri, int l
  * converged at the loop head -- without it the compiler threads "still at an internal node" back into the node stage, i.e.
  * builds a while-while loop.  ALL 32 LANES OF A WARP MUST CALL THIS TOGETHER; lanes without a ray pass active = false. */
 #define TRAV_DONE ((int)0x80000000)
-#define TRAV_NB 2          /* node stages per loop iteration: 2 measured best on every layout and scene size (profiles/README.md 8.2) */
 template <bool ANY> struct TravStack;
 template <> struct TravStack<true> {          /* any_hit: node pointers only */
     int e[TRAV_STACK + 1];
@@ -136,28 +135,13 @@ LYS_D void trav_node_stage(const RayInv &r, unsigned long long nbase, float tmax
     else if (pr) cur = rc;
     else cur = st.pop(sp, tmax);
 }
-/* the pair-record walk as a resumable loop over (cur, sp, closest, tmax, stack): runs until every lane of the warp is done or,
- * with BUDGET, for at most `budget` iterations (the count is warp uniform) */
-template <bool ANY, bool OCT, bool BUDGET>
-LYS_D void trav_loop(const RayInv &r, unsigned long long nbase, const float4 *__restrict__ leaf_tri, int &cur, int &sp, int &closest, float &tmax,
-                     TravStack<ANY> &st, int budget) {
-    do {
-#pragma unroll
-        for (int k = 0; k < TRAV_NB; k++)
-            if (cur >= 0) trav_node_stage<ANY, OCT>(r, nbase, tmax, cur, sp, st);
-        if ((unsigned)cur > (unsigned)TRAV_DONE) {            /* a leaf pointer */
-            float t;
-            if (leaf_test(r, leaf_tri, ~cur, tmax, t)) { closest = ~cur; tmax = t; }
-            cur = (ANY && closest >= 0) ? TRAV_DONE : st.pop(sp, tmax);       /* any_hit stops at the first hit (bvh.fut:152) */
-        }
-    } while (__any_sync(0xffffffffu, cur != TRAV_DONE) && (!BUDGET || --budget > 0));
-}
 /* Record layouts (lys_scene.h), picked per scene by the build:
  *   LAY_SINGLE    one box per record, octant copies: small trees (issue bound, half the child slots are leaves whose box
  *                 slot a pair record would test for nothing: measured 5-9 % faster than pair records on CornellBox / MirrorBox)
  *   LAY_PAIR_OCT  pair records, octant copies
  *   LAY_PAIR      pair records, one copy, box test with selects (scenes whose octant copies would not stay in L2) */
 enum { LAY_SINGLE = 0, LAY_PAIR_OCT = 1, LAY_PAIR = 2 };
+#define TRAV_NB 2          /* node stages per loop iteration: 2 measured best on every layout and scene size (profiles/README.md 8.2) */
 template <bool ANY, int LAY>
 LYS_D int traverse(const float4 *__restrict__ nodes, const float4 *__restrict__ leaf_tri, int n_nodes, bool active,
                    V3 o, V3 d, float tmax, float &t_hit) {
@@ -198,7 +182,16 @@ LYS_D int traverse(const float4 *__restrict__ nodes, const float4 *__restrict__ 
         TravStack<ANY> st;
         int sp = 0;
         int cur = (active && n_nodes > 0) ? n_nodes : TRAV_DONE;   /* internal node to enter (>= 0; n_nodes = the super-root), leaf pointer (~leaf) or TRAV_DONE */
-        trav_loop<ANY, OCT, false>(r, nbase, leaf_tri, cur, sp, closest, tmax, st, 0);
+        do {
+#pragma unroll
+            for (int k = 0; k < TRAV_NB; k++)
+                if (cur >= 0) trav_node_stage<ANY, OCT>(r, nbase, tmax, cur, sp, st);
+            if ((unsigned)cur > (unsigned)TRAV_DONE) {            /* a leaf pointer */
+                float t;
+                if (leaf_test(r, leaf_tri, ~cur, tmax, t)) { closest = ~cur; tmax = t; }
+                cur = (ANY && closest >= 0) ? TRAV_DONE : st.pop(sp, tmax);       /* any_hit stops at the first hit (bvh.fut:152) */
+            }
+        } while (__any_sync(0xffffffffu, cur != TRAV_DONE));
     }
     t_hit = tmax;
     return closest;
@@ -234,7 +227,6 @@ __global__ void __launch_bounds__(256) k_generate(const __grid_constant__ FrameP
         b.counts[0] = fp.n_local;
         for (int k = 1; k <= LYS_MAX_PATH_LEN; k++) b.counts[k] = 0;
         for (int k = 0; k < 2 * (LYS_MAX_PATH_LEN + 1); k++) b.split[k] = 0;
-        if (b.tq_count) for (int k = 0; k < LYS_TRACE_MAX_PHASES * (LYS_MAX_PATH_LEN + 1); k++) b.tq_count[k] = 0;
     }
     if (pid >= fp.n_local) return;
     int col, row; int ix = local_to_pixel(fp, pid, col, row);
@@ -573,54 +565,8 @@ LYS_D void connect_finish(const FrameParams &fp, const PassBuffers &b, int bounc
 #ifndef LYS_TRACE_MINB
 #define LYS_TRACE_MINB(LAY) ((LAY) == LAY_PAIR ? 16 : (LAY) == LAY_PAIR_OCT ? 12 : 10)
 #endif
-/* closest hit of slot `item` of bounce + 1 is known: store it and append the slot to the processing order of shade(bounce + 1),
- * hits from the front, misses from the back (one atomic per warp and kind).  Warp-collective. */
-LYS_D void publish_hit(const PassBuffers &b, int bounce, int ordered, int n_ext, bool valid, int item, int h) {
-    const int lane = threadIdx.x & 31;
-    if (valid) b.hit[item] = h;
-    if (ordered) {                     /* not for camera rays (their misses are whole warps already: shade(0) walks the slots in order) */
-        const bool isH = valid && h >= 0, isM = valid && h < 0;
-        const unsigned mh = __ballot_sync(0xffffffffu, isH), mm = __ballot_sync(0xffffffffu, isM);
-        int bh = 0, bm = 0;
-        if (lane == 0) { if (mh) bh = atomicAdd(&b.split[2 * (bounce + 1)], __popc(mh)); if (mm) bm = atomicAdd(&b.split[2 * (bounce + 1) + 1], __popc(mm)); }
-        bh = __shfl_sync(0xffffffffu, bh, 0); bm = __shfl_sync(0xffffffffu, bm, 0);
-        const unsigned lt = (1u << lane) - 1u;
-        if (isH) b.order[(bounce + 1) & 1][bh + __popc(mh & lt)] = item;
-        if (isM) b.order[(bounce + 1) & 1][n_ext - 1 - (bm + __popc(mm & lt))] = item;
-    }
-}
-/* ---- phased traversal.  The closest-hit walks of a warp differ wildly in length (1 M triangles, bounce 1: mean 41 record
- * visits, max > 500), and a lock-step warp runs as long as its longest ray: 10 of 32 lanes busy.  So a launch gives every warp
- * an iteration BUDGET; walks that are not finished by then are parked in a queue (PassBuffers::tq_*: header, tmax, stack) and
- * the next phase (k_trace_resume) picks them up 32 to a warp -- dense warps of long walks.  Per-ray visits, their order and every
- * comparison are untouched: only which lane of which launch continues a walk changes.  Model: tools/simt_model.py `pair`
- * (-35 .. -45 % issued instructions on incoherent bounces); measured: profiles/README.md 8.3.
- * trav_park: after a budgeted run, lanes still walking (`cur != TRAV_DONE`) park in queue `qi` and become TRAV_DONE; a lane whose
- * stack is deeper than LYS_TRACE_SAVE_DEPTH, or that finds the queue full, finishes its walk here.  Returns true for parked lanes
- * (no result to publish yet).  Warp-collective. */
-template <bool OCT>
-LYS_D bool trav_park(const PassBuffers &b, int count_ix, int qi, int item, const RayInv &r, unsigned long long nbase, const float4 *__restrict__ leaf_tri,
-                     int &cur, int &sp, int &closest, float &tmax, TravStack<false> &st) {
-    const int lane = threadIdx.x & 31;
-    bool park = cur != TRAV_DONE && sp <= LYS_TRACE_SAVE_DEPTH;
-    const unsigned m = __ballot_sync(0xffffffffu, park);
-    if (m) {
-        int base = 0;
-        if (lane == 0) base = atomicAdd(&b.tq_count[count_ix], __popc(m));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        const int q = base + __popc(m & ((1u << lane) - 1u));
-        if (park && q >= b.tq_cap) park = false;               /* queue full: the consumer clamps the count */
-        if (park) { b.tq_hdr[qi][q] = make_int4(item, cur, sp, closest); b.tq_tmax[qi][q] = tmax; }
-        const int maxsp = __reduce_max_sync(0xffffffffu, park ? sp : 0);
-        for (int l = 0; l < maxsp; l++) if (park && l < sp) b.tq_stack[qi][(size_t)l * b.tq_cap + q] = st.e[l];      /* coalesced: consecutive lanes, consecutive slots */
-        if (park) cur = TRAV_DONE;
-    }
-    if (__any_sync(0xffffffffu, cur != TRAV_DONE)) trav_loop<false, OCT, false>(r, nbase, leaf_tri, cur, sp, closest, tmax, st, 0);
-    return park;
-}
-/* `budget` > 0 (PHASED kernels only): iteration budget of the closest-hit walks of this launch (phase 0) */
-template <int LAY, bool PHASED>
-__global__ void __launch_bounds__(128, LYS_TRACE_MINB(LAY)) k_trace(SceneDev sc, const __grid_constant__ FrameParams fp, PassBuffers b, int bounce, int ordered, int budget) {
+template <int LAY>
+__global__ void __launch_bounds__(128, LYS_TRACE_MINB(LAY)) k_trace(SceneDev sc, const __grid_constant__ FrameParams fp, PassBuffers b, int bounce, int ordered) {
     const int n_ext = (bounce + 1 < fp.path_len) ? b.counts[bounce + 1] : 0;
     const int n_con = (bounce >= 0) ? b.counts[bounce] : 0;
     const int total = n_ext + n_con;
@@ -635,20 +581,19 @@ __global__ void __launch_bounds__(128, LYS_TRACE_MINB(LAY)) k_trace(SceneDev sc,
         if (i0 < n_ext) {
             float4 ro = make_float4(0.0f, 0.0f, 0.0f, 0.0f), rd = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
             if (is_ext) { ro = b.ray_o[(bounce + 1) & 1][i]; rd = b.ray_d[(bounce + 1) & 1][i]; }
-            if (PHASED && LAY != LAY_SINGLE) {
-                constexpr bool OCT = LAY == LAY_PAIR_OCT;
-                RayInv r; r.o = v3(ro.x, ro.y, ro.z); r.d = v3(rd.x, rd.y, rd.z); r.inv = v3(1.0f / rd.x, 1.0f / rd.y, 1.0f / rd.z);
-                const unsigned long long nbase = trav_base<OCT>(nodes, n_nodes, r);
-                TravStack<false> st;
-                int sp = 0, closest = -1, cur = (is_ext && n_nodes > 0) ? n_nodes : TRAV_DONE;
-                float tmax = FLT_MAX;
-                trav_loop<false, OCT, true>(r, nbase, sc.leaf_tri, cur, sp, closest, tmax, st, budget);
-                const bool parked = trav_park<OCT>(b, (bounce + 1) * LYS_TRACE_MAX_PHASES, 0, i, r, nbase, sc.leaf_tri, cur, sp, closest, tmax, st);
-                publish_hit(b, bounce, ordered, n_ext, is_ext && !parked, i, closest);
-            } else {
-                float t;
-                int h = traverse<false, LAY>(nodes, sc.leaf_tri, n_nodes, is_ext, v3(ro.x, ro.y, ro.z), v3(rd.x, rd.y, rd.z), FLT_MAX, t);
-                publish_hit(b, bounce, ordered, n_ext, is_ext, i, h);
+            float t;
+            int h = traverse<false, LAY>(nodes, sc.leaf_tri, n_nodes, is_ext, v3(ro.x, ro.y, ro.z), v3(rd.x, rd.y, rd.z), FLT_MAX, t);
+            if (is_ext) b.hit[i] = h;
+            /* processing order of shade(bounce + 1): hits from the front, misses from the back (one atomic per warp and kind) */
+            if (ordered) {                     /* not for camera rays (their misses are whole warps already: shade(0) walks the slots in order) */
+                const bool isH = is_ext && h >= 0, isM = is_ext && h < 0;
+                const unsigned mh = __ballot_sync(0xffffffffu, isH), mm = __ballot_sync(0xffffffffu, isM);
+                int bh = 0, bm = 0;
+                if (lane == 0) { if (mh) bh = atomicAdd(&b.split[2 * (bounce + 1)], __popc(mh)); if (mm) bm = atomicAdd(&b.split[2 * (bounce + 1) + 1], __popc(mm)); }
+                bh = __shfl_sync(0xffffffffu, bh, 0); bm = __shfl_sync(0xffffffffu, bm, 0);
+                const unsigned lt = (1u << lane) - 1u;
+                if (isH) b.order[(bounce + 1) & 1][bh + __popc(mh & lt)] = i;
+                if (isM) b.order[(bounce + 1) & 1][n_ext - 1 - (bm + __popc(mm & lt))] = i;
             }
         }
         if (i0 + 31 >= n_ext) {
@@ -677,39 +622,6 @@ __global__ void __launch_bounds__(128, LYS_TRACE_MINB(LAY)) k_trace(SceneDev sc,
     }
 }
 
-/* phase >= 1 of the closest hits of bounce + 1: the walks parked by phase - 1, 32 to a warp; budget 0 = run to the end */
-template <int LAY>
-__global__ void __launch_bounds__(128, LYS_TRACE_MINB(LAY)) k_trace_resume(SceneDev sc, PassBuffers b, int bounce, int ordered, int phase, int budget) {
-    constexpr bool OCT = LAY == LAY_PAIR_OCT;
-    const int n_ext = b.counts[bounce + 1];
-    const int n_in = min(b.tq_count[(bounce + 1) * LYS_TRACE_MAX_PHASES + phase - 1], b.tq_cap);
-    const int qin = (phase - 1) & 1, qout = phase & 1;
-    const int stride = gridDim.x * blockDim.x;
-    const int n_nodes = (int)sc.n_tris - 1;
-    const int lane = threadIdx.x & 31;
-    const float4 *__restrict__ nodes = (LAY == LAY_PAIR) ? sc.nodes : sc.nodes_oct;
-    for (int q0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31); q0 < n_in; q0 += stride) {
-        const int q = q0 + lane;
-        const bool act = q < n_in;
-        int4 hd = make_int4(0, TRAV_DONE, 0, -1);
-        float tmax = FLT_MAX;
-        float4 ro = make_float4(0.0f, 0.0f, 0.0f, 0.0f), rd = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
-        if (act) { hd = b.tq_hdr[qin][q]; tmax = b.tq_tmax[qin][q]; ro = b.ray_o[(bounce + 1) & 1][hd.x]; rd = b.ray_d[(bounce + 1) & 1][hd.x]; }
-        RayInv r; r.o = v3(ro.x, ro.y, ro.z); r.d = v3(rd.x, rd.y, rd.z); r.inv = v3(1.0f / rd.x, 1.0f / rd.y, 1.0f / rd.z);
-        const unsigned long long nbase = trav_base<OCT>(nodes, n_nodes, r);
-        TravStack<false> st;
-        int cur = hd.y, sp = hd.z, closest = hd.w;
-        const int maxsp = __reduce_max_sync(0xffffffffu, act ? sp : 0);
-        for (int l = 0; l < maxsp; l++) if (act && l < sp) st.e[l] = b.tq_stack[qin][(size_t)l * b.tq_cap + q];
-        bool parked = false;
-        if (budget > 0) {
-            trav_loop<false, OCT, true>(r, nbase, sc.leaf_tri, cur, sp, closest, tmax, st, budget);
-            parked = trav_park<OCT>(b, (bounce + 1) * LYS_TRACE_MAX_PHASES + phase, qout, hd.x, r, nbase, sc.leaf_tri, cur, sp, closest, tmax, st);
-        } else trav_loop<false, OCT, false>(r, nbase, sc.leaf_tri, cur, sp, closest, tmax, st, 0);
-        publish_hit(b, bounce, ordered, n_ext, act && !parked, hd.x, closest);
-    }
-}
-
 /* ------------------------------------------------------------------ generate + trace(-1) in one launch
  * The camera ray of a pixel goes straight from the registers into the traversal loop: one launch less per pass and no
  * read-back of the 32-byte ray records just written (k_shade(0) still needs them, so they are written once). */
@@ -720,7 +632,6 @@ __global__ void __launch_bounds__(128, LYS_TRACE_MINB(LAY)) k_generate_trace(Sce
         b.counts[0] = fp.n_local;
         for (int k = 1; k <= LYS_MAX_PATH_LEN; k++) b.counts[k] = 0;
         for (int k = 0; k < 2 * (LYS_MAX_PATH_LEN + 1); k++) b.split[k] = 0;
-        if (b.tq_count) for (int k = 0; k < LYS_TRACE_MAX_PHASES * (LYS_MAX_PATH_LEN + 1); k++) b.tq_count[k] = 0;
     }
     const bool act = pid < fp.n_local;                     /* no early return: traverse<> votes per warp */
     V3 o = v3(0.0f, 0.0f, 0.0f), d = v3(1.0f, 1.0f, 1.0f);
@@ -968,7 +879,7 @@ static inline int cdiv(long long a, int b) { return (int)((a + b - 1) / b); }
  * force what is otherwise chosen by scene size or by the previous pass (tests/test_gpu_parity.py::test_kernel_variants_bit_exact
  * runs each setting against the oracle): LYS_TRACE_PAIR (lbvh.cu), LYS_TRACE_OCT, LYS_TAIL_MAX, LYS_ADAPTIVE_GRIDS, LYS_SHADE_ORDER,
  * LYS_FUSE_GENERATE; LYS_PROFILE_TAIL keeps the fused tail under per-class timing. */
-struct GridSizes { int n_budgets = 0, budget[LYS_TRACE_MAX_PHASES] = {0, 0, 0, 0}; int trace[3] = {0, 0, 0}, shade = 0, oct = 1, adaptive = 1, sms = 148, tail_max = 8192, tail_items = 128, profile_tail = 0, order = 1, fuse_gen = 1; };
+struct GridSizes { int trace[3] = {0, 0, 0}, shade = 0, oct = 1, adaptive = 1, sms = 148, tail_max = 8192, tail_items = 128, profile_tail = 0, order = 1, fuse_gen = 1; };
 static GridSizes grid_sizes() {
     static GridSizes g[64];
     int dev = 0; cudaGetDevice(&dev);
@@ -976,9 +887,9 @@ static GridSizes grid_sizes() {
     if (!g[dev].shade) {
         int sms = 148, bt[3] = {10, 12, 16}, bs = 3;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bt[LAY_SINGLE], k_trace<LAY_SINGLE, false>, 128, 0);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bt[LAY_PAIR_OCT], k_trace<LAY_PAIR_OCT, false>, 128, 0);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bt[LAY_PAIR], k_trace<LAY_PAIR, false>, 128, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bt[LAY_SINGLE], k_trace<LAY_SINGLE>, 128, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bt[LAY_PAIR_OCT], k_trace<LAY_PAIR_OCT>, 128, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bt[LAY_PAIR], k_trace<LAY_PAIR>, 128, 0);
         for (int k = 0; k < 3; k++) g[dev].trace[k] = sms * (bt[k] > 0 ? bt[k] : 1);
         g[dev].shade = sms * (bs > 0 ? bs : 1);
         g[dev].sms = sms;
@@ -988,9 +899,6 @@ static GridSizes grid_sizes() {
         const char *tmx = getenv("LYS_TAIL_MAX"); if (tmx) g[dev].tail_max = atoi(tmx);          /* 0: no fused tail */
         const char *ad = getenv("LYS_ADAPTIVE_GRIDS"); if (ad) g[dev].adaptive = atoi(ad) ? 1 : 0;
         const char *oc = getenv("LYS_TRACE_OCT"); if (oc) g[dev].oct = atoi(oc) ? 1 : 0;          /* 0: always the select-based box test */
-        /* phased traversal on the pair layouts: iteration budgets of the phases, e.g. "16,32" = 16 iterations, then 32, then to the end; "0" = off */
-        const char *ph = getenv("LYS_TRACE_PHASES");
-        if (ph) { for (const char *c = ph; *c && g[dev].n_budgets < LYS_TRACE_MAX_PHASES; ) { int v = atoi(c); if (v > 0) g[dev].budget[g[dev].n_budgets++] = v; while (*c && *c != ',') c++; if (*c == ',') c++; } }
     }
     return g[dev];
 }
@@ -1001,25 +909,12 @@ static int trace_layout(const GridSizes &gs, const SceneDev &sc) {
 /* the three traversal variants a scene can select */
 #define LYS_TRAV_DISPATCH(lay, CALL) do { \
         if ((lay) == LAY_SINGLE) { CALL(LAY_SINGLE); } else if ((lay) == LAY_PAIR_OCT) { CALL(LAY_PAIR_OCT); } else { CALL(LAY_PAIR); } } while (0)
-static void launch_trace(const GridSizes &gs, int grid, const SceneDev &sc, const FrameParams &fp, PassBuffers &bufs, int bounce, cudaStream_t stream, uint64_t *launches = nullptr) {
+static void launch_trace(const GridSizes &gs, int grid, const SceneDev &sc, const FrameParams &fp, PassBuffers &bufs, int bounce, cudaStream_t stream) {
     const int ordered = (gs.order && bounce >= 0) ? 1 : 0;      /* write the hits-first order of bounce + 1, walk the one of bounce */
-    const int lay = trace_layout(gs, sc);
-    if (lay != LAY_SINGLE && gs.n_budgets > 0 && bufs.tq_hdr[0] && bounce >= 0 && bounce + 1 < fp.path_len) {      /* phased closest hits (incoherent bounces only) */
-        if (lay == LAY_PAIR_OCT) k_trace<LAY_PAIR_OCT, true><<<grid, 128, 0, stream>>>(sc, fp, bufs, bounce, ordered, gs.budget[0]);
-        else k_trace<LAY_PAIR, true><<<grid, 128, 0, stream>>>(sc, fp, bufs, bounce, ordered, gs.budget[0]);
-        for (int p = 1; p <= gs.n_budgets; p++) {
-            const int bud = p < gs.n_budgets ? gs.budget[p] : 0;
-            if (lay == LAY_PAIR_OCT) k_trace_resume<LAY_PAIR_OCT><<<grid, 128, 0, stream>>>(sc, bufs, bounce, ordered, p, bud);
-            else k_trace_resume<LAY_PAIR><<<grid, 128, 0, stream>>>(sc, bufs, bounce, ordered, p, bud);
-            if (launches) (*launches)++;
-        }
-        return;
-    }
-#define LYS_CALL(LAY) k_trace<LAY, false><<<grid, 128, 0, stream>>>(sc, fp, bufs, bounce, ordered, 0)
-    LYS_TRAV_DISPATCH(lay, LYS_CALL);
+#define LYS_CALL(LAY) k_trace<LAY><<<grid, 128, 0, stream>>>(sc, fp, bufs, bounce, ordered)
+    LYS_TRAV_DISPATCH(trace_layout(gs, sc), LYS_CALL);
 #undef LYS_CALL
 }
-int trace_phase_count() { return grid_sizes().n_budgets; }
 cudaError_t run_sample_pass(const SceneDev &sc, const FrameParams &fp, PassBuffers &bufs, cudaStream_t stream, uint64_t *launches, LaunchTimer *timer,
                             int *est_counts) {
     const int n = fp.n_local;
@@ -1068,7 +963,7 @@ cudaError_t run_sample_pass(const SceneDev &sc, const FrameParams &fp, PassBuffe
         k_shade<256><<<sized(have_est ? est[bnc] : 0, 256, g_shade), 256, 0, stream>>>(sc, fp, bufs, bnc, (gs.order && bnc > 0) ? 1 : 0);   /* follow b.order (written by k_trace) */
         tm.end(stream); nl++;
         tm.begin(1, stream);
-        launch_trace(gs, sized(have_est ? (long long)est[bnc] + est[bnc + 1] : 0, 128, g_trace), sc, fp, bufs, bnc, stream, &nl);
+        launch_trace(gs, sized(have_est ? (long long)est[bnc] + est[bnc + 1] : 0, 128, g_trace), sc, fp, bufs, bnc, stream);
         tm.end(stream); nl++;
     }
     if (b_tail < fp.path_len) {

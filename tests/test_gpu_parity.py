@@ -442,9 +442,6 @@ def test_init_light_capacity_regrow(orc, pkg, gpu, scenes):
     {'LYS_TRACE_PAIR': '1'},           # pair records on the small scene too (what scenes above 1024 triangles use)
     {'LYS_TRACE_PAIR': '1', 'LYS_TRACE_OCT': '0'},            # select-based box test on the plain record array (scenes above 64K nodes)
     {'LYS_TRACE_OCT': '0'},            # small scene: single-box records stay (they exist as octant copies only); spectrumsphere: plain pair records
-    {'LYS_TRACE_PAIR': '1', 'LYS_TRACE_PHASES': '2,3'},       # phased traversal: walks parked after 2 iterations, again after 3 more, then run to the end
-    {'LYS_TRACE_PAIR': '1', 'LYS_TRACE_PHASES': '1,1,1,1', 'LYS_TRACE_OCT': '0', 'LYS_TAIL_MAX': '0'},
-    {'LYS_TRACE_PHASES': '8,16'},
     {'LYS_SHADE_ORDER': '0'},          # k_shade walks the queue in slot order instead of hits first
     {'LYS_FUSE_GENERATE': '0'},        # k_generate and k_trace(-1) as two launches (the per-class timing sequence)
     {'LYS_TAIL_MAX': '0'},             # no fused tail kernel: one launch per stage and bounce

@@ -47,8 +47,6 @@ def test_emulated_library_equals_the_oracle(emu_lib):
 @pytest.mark.parametrize('env', [
     {'LYS_TRACE_PAIR': '1', 'LYS_TRACE_OCT': '0'},       # what scenes above 64K nodes run: pair records, select-based box test
     {'LYS_TRACE_PAIR': '1'},                             # 1K .. 64K nodes: pair records, octant copies
-    {'LYS_TRACE_PAIR': '1', 'LYS_TRACE_PHASES': '2,3'},                      # phased traversal: walks parked after 2 iterations, again after 3 more, then run to the end
-    {'LYS_TRACE_PAIR': '1', 'LYS_TRACE_PHASES': '1,1,1,1', 'LYS_TRACE_OCT': '0', 'LYS_EMU_SCHEDULE': '31', 'LYS_TAIL_MAX': '0'},   # four budgeted phases, every bounce phased
     {'LYS_TAIL_MAX': '100000000'},                     # fused tail kernel from bounce 1 on
     {'LYS_TAIL_MAX': '0', 'LYS_SHADE_ORDER': '0', 'LYS_FUSE_GENERATE': '0', 'LYS_EMU_SMS': '32'},
     {'LYS_EMU_SCHEDULE': '1'},                         # CTAs, warps and lanes run in reverse order: results must not depend on the schedule
