@@ -35,6 +35,7 @@
 /* ---- vector types -------------------------------------------------------------------- */
 struct alignas(8) float2 { float x, y; };
 struct alignas(8) int2 { int x, y; };
+struct alignas(16) int4 { int x, y, z, w; };
 struct alignas(16) float4 { float x, y, z, w; };
 struct uint3 { unsigned int x, y, z; };
 struct dim3 {
@@ -43,11 +44,12 @@ struct dim3 {
 };
 static inline float2 make_float2(float x, float y) { float2 r; r.x = x; r.y = y; return r; }
 static inline int2 make_int2(int x, int y) { int2 r; r.x = x; r.y = y; return r; }
+static inline int4 make_int4(int x, int y, int z, int w) { int4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
 static inline float4 make_float4(float x, float y, float z, float w) { float4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
 
 /* ---- the SIMT engine (emu_engine.cpp) ------------------------------------------------ */
 namespace emu {
-enum Op { OP_BALLOT = 1, OP_SHFL, OP_SHFL_XOR, OP_REDUCE_ADD, OP_MATCH_ANY, OP_SYNCWARP };
+enum Op { OP_BALLOT = 1, OP_SHFL, OP_SHFL_XOR, OP_REDUCE_ADD, OP_MATCH_ANY, OP_SYNCWARP, OP_REDUCE_MAX };
 struct LaneIds { uint3 tid; };
 extern uint3 g_block_idx, g_block_dim, g_grid_dim;
 const uint3 &cur_tid();
@@ -100,6 +102,7 @@ static inline int __shfl_xor_sync(unsigned int, int v, int m) { return (int)emu:
 static inline unsigned int __shfl_xor_sync(unsigned int, unsigned int v, int m) { return emu::warp_collective(emu::OP_SHFL_XOR, v, (uint32_t)m); }
 static inline float __shfl_xor_sync(unsigned int, float v, int m) { return __uint_as_float(emu::warp_collective(emu::OP_SHFL_XOR, __float_as_uint(v), (uint32_t)m)); }
 static inline unsigned int __reduce_add_sync(unsigned int, unsigned int v) { return emu::warp_collective(emu::OP_REDUCE_ADD, v, 0); }
+static inline int __reduce_max_sync(unsigned int, int v) { return (int)emu::warp_collective(emu::OP_REDUCE_MAX, (unsigned int)v, 0); }
 static inline unsigned int __match_any_sync(unsigned int, unsigned int v) { return emu::warp_collective(emu::OP_MATCH_ANY, v, 0); }
 /* atomics: lanes run one at a time, so plain read-modify-write is atomic */
 template <class T, class U> static inline T atomicAdd(T *p, U v) { T old = *p; *p = (T)(old + (T)v); return old; }

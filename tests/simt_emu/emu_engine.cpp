@@ -122,6 +122,12 @@ void resolve_warp(Lane *w, int n) {
             for (int l = 0; l < n; l++) w[l].out = s;
             break;
         }
+        case OP_REDUCE_MAX: {           /* signed maximum (__reduce_max_sync on int) */
+            int32_t s = INT32_MIN;
+            for (int l = 0; l < n; l++) if (w[l].st == ST_WARP && (int32_t)w[l].a > s) s = (int32_t)w[l].a;
+            for (int l = 0; l < n; l++) w[l].out = (uint32_t)s;
+            break;
+        }
         case OP_MATCH_ANY:
             for (int l = 0; l < n; l++) {
                 if (w[l].st != ST_WARP) continue;
