@@ -689,16 +689,22 @@ __global__ void k_mat_emissive(const float *__restrict__ mats, int m, unsigned c
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m) return;
     const float *e = mats + 28ll * i + 16;
-    bool on = false;
+    bool on = false, dark = true;
 #pragma unroll
-    for (int k = 0; k < 6; k++) if (e[2 * k] >= 0.0f && e[2 * k + 1] > 0.0f) on = true;
-    flag[i] = on ? 1 : 0;
+    for (int k = 0; k < 6; k++) {
+        if (e[2 * k] >= 0.0f && e[2 * k + 1] > 0.0f) on = true;
+        if (__float_as_uint(e[2 * k + 1]) != 0u) dark = false;
+    }
+    /* bit 0: emissive (scene.fut:59-60).  bit 1: every emission VALUE is +0.0 -- whatever the knots' wavelengths, spectrum_lookup
+     * (spectrum.fut:30-49) then returns +0.0 for any wavelength (0, a knot value, or +0 + (+0 - +0) * t), so k_shade skips the
+     * lookup of the vertex-0 emission term (integrator.fut:51-53) for such materials */
+    flag[i] = (on ? 1 : 0) | (dark ? 2 : 0);
 }
 __device__ __forceinline__ bool tri_is_light(const uint32_t *__restrict__ tri_mats, const unsigned char *__restrict__ mat_flag, int i, int n, int m, bool &bad) {
     if (i >= n) return false;
     const uint32_t k = tri_mats[i];
     if (k >= (uint32_t)m) { bad = true; return false; }
-    return mat_flag[k] != 0;
+    return (mat_flag[k] & 1) != 0;
 }
 __global__ void __launch_bounds__(LIGHT_CHUNK) k_light_count(const uint32_t *__restrict__ tri_mats, const unsigned char *__restrict__ mat_flag, int n, int m,
                                                               int *__restrict__ chunk_cnt, int *__restrict__ info) {
@@ -772,6 +778,7 @@ cudaError_t build_lights(SceneDev &sc, unsigned char *mat_flag, int *chunk_cnt, 
     const int chunks = cdiv(n, LIGHT_CHUNK);
     cudaMemsetAsync(info, 0, 4 * sizeof(int), stream);
     k_mat_emissive<<<cdiv(m, 128), 128, 0, stream>>>(sc.mats, m, mat_flag);
+    sc.mat_flag = mat_flag;
     k_light_count<<<chunks, LIGHT_CHUNK, 0, stream>>>(sc.tri_mats, mat_flag, n, m, chunk_cnt, info);
     k_light_scan<<<1, 1024, 0, stream>>>(chunk_cnt, chunks, info);
     k_light_scatter<<<chunks, LIGHT_CHUNK, 0, stream>>>(sc.tri_mats, mat_flag, n, m, chunk_cnt, cap, sc.light_src);

@@ -34,6 +34,22 @@
 #define LYS_DN_RTERMS LYS_DN
 #endif
 
+/* evict-first cache operators (ld.global.cs / st.global.cs) for path-state records, used by the traversal kernels of LARGE
+ * scenes only: there the records of a bounce (read once, written once) would otherwise displace the traversal records from L2
+ * (+2 % on the 1 M-triangle scene; -0.5 % on CornellBox when used everywhere, hence the template switch; a persisting
+ * access-policy window on the records changed nothing: profiles/README.md 8.4) */
+template <bool CS, class T> LYS_D T ld_state(const T *p) {
+#ifdef __CUDACC__
+    if (CS) return __ldcs(p);
+#endif
+    return *p;
+}
+template <bool CS, class T> LYS_D void st_state(T *p, T v) {
+#ifdef __CUDACC__
+    if (CS) { __stcs(p, v); return; }
+#endif
+    *p = v;
+}
 #define LYS_PI 3.14159265358979323846f
 #define LYS_INV_PI (1.0f / LYS_PI)          /* linalg.fut:55 */
 #define LYS_INF (lys_u2f(0x7f800000u))

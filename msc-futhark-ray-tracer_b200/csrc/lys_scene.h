@@ -52,6 +52,7 @@ struct SceneDev {
     float *bounds = nullptr;
     LightRec *lights = nullptr;
     int *light_src = nullptr;
+    const unsigned char *mat_flag = nullptr;   /* [m] bit 0: emissive material, bit 1: all emission values are +0.0 (lbvh.cu: k_mat_emissive) */
     float build_ms = 0.0f;
 };
 

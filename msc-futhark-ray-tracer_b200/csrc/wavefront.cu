@@ -290,6 +290,7 @@ struct VertexCtx {
     float wavelen, t;
     uint32_t rng;                 /* state after the per-vertex advance_rng (integrator.fut:48) */
     Onb onb; Mat1 m; const float *mrow;
+    bool dark;                    /* the material's emission spectrum is +0.0 everywhere (SceneDev::mat_flag bit 1) */
     float F;                      /* schlick(wo_l, m) (material.fut:207-211) when wo_l.z > 0: used by the light sample's bsdf_f and by both sample_dir calls */
 };
 LYS_D bool shade_prologue(const SceneDev &sc, const PassBuffers &b, int bounce, int i, VertexCtx &v) {
@@ -303,6 +304,7 @@ LYS_D bool shade_prologue(const SceneDev &sc, const PassBuffers &b, int bounce, 
     const float4 *lq = sc.leaf_tri + 4ll * v.leaf;
     float4 q0 = __ldg(lq), q1 = __ldg(lq + 1);
     v.mrow = sc.mats + 28ll * (int)__float_as_uint(q0.w);
+    v.dark = (__ldg(sc.mat_flag + (int)__float_as_uint(q0.w)) & 2) != 0;
     V3 nc = v3(q1.x, q1.y, q1.z);                                          /* e1 x e2, stored by the build */
     { float inv; V3 s; (void)tri_plane_test(v.o, v.d, v3(q0.x, q0.y, q0.z), nc, FLT_MAX, v.t, inv, s); }   /* bvh.fut:143-145: t of the winner */
     v.pos = v.o + v.t * v.d;
@@ -380,7 +382,7 @@ LYS_D void shade_bsdf_light_sample(VertexCtx &v, const LightD &l, float &cB, flo
 /* emission, distance, shadow record, continuation + roulette (integrator.fut:51-75); returns true if the path lives on */
 LYS_D bool shade_finish_use(const FrameParams &fp, const PassBuffers &b, int bounce, int i, VertexCtx &v, const DirSample &s, float cL, float cB, int flags,
                             float4 &next_o, float4 &next_d, float &next_dist) {
-    float em = (bounce == 0) ? spectrum_lookup12(v.wavelen, v.mrow + 16) : 0.0f;      /* integrator.fut:51-53 */
+    float em = (bounce == 0 && !v.dark) ? spectrum_lookup12(v.wavelen, v.mrow + 16) : 0.0f;      /* integrator.fut:51-53 */
     const float dist = b.dist[bounce & 1][i] + v.t;                                     /* :54 */
     next_dist = dist;
     V3 so = v.pos + 0.001f * v.n;       /* mkray_adjust_acne with dot(w, n) > 0: same_side = 1 * n */
@@ -408,8 +410,8 @@ LYS_D void shade_miss(const FrameParams &fp, const PassBuffers &b, int i, const 
     b.sh_o[i] = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(4));          /* bit 2: miss vertex, radiance = sh_c.z */
     b.sh_c[i] = make_float4(0.0f, 0.0f, amb, LYS_INF);
 }
-/* compaction of live paths (warp ballot + prefix popcount, one atomic per warp) and statistics */
-LYS_D void shade_compact(const PassBuffers &b, int bounce, bool alive, int pid, float4 next_o, float4 next_d, float next_dist, unsigned n_vert, unsigned n_shadow) {
+/* compaction of live paths (warp ballot + prefix popcount, one atomic per warp) */
+LYS_D void shade_compact(const PassBuffers &b, int bounce, bool alive, int pid, float4 next_o, float4 next_d, float next_dist) {
     const int lane = threadIdx.x & 31;
     unsigned mask = __ballot_sync(0xffffffffu, alive);
     int base = 0;
@@ -420,8 +422,11 @@ LYS_D void shade_compact(const PassBuffers &b, int bounce, bool alive, int pid, 
         b.queue[(bounce + 1) & 1][slot] = pid;
         b.ray_o[(bounce + 1) & 1][slot] = next_o; b.ray_d[(bounce + 1) & 1][slot] = next_d; b.dist[(bounce + 1) & 1][slot] = next_dist;       /* coalesced: consecutive lanes, consecutive slots */
     }
+}
+/* statistics (vertices, shadow rays) of a thread's whole grid-stride loop: one pair of atomics per warp and launch */
+LYS_D void shade_stats(const PassBuffers &b, unsigned n_vert, unsigned n_shadow) {
     unsigned vsum = __reduce_add_sync(0xffffffffu, n_vert), ssum = __reduce_add_sync(0xffffffffu, n_shadow);
-    if (lane == 0 && (vsum | ssum)) { atomicAdd(&b.stats[0], (unsigned long long)vsum); atomicAdd(&b.stats[2], (unsigned long long)ssum); }
+    if ((threadIdx.x & 31) == 0 && (vsum | ssum)) { atomicAdd(&b.stats[0], (unsigned long long)vsum); atomicAdd(&b.stats[2], (unsigned long long)ssum); }
 }
 
 /* monolithic: everything for one vertex in one thread, with these arrangements (profiles/README.md 4.2, 4.5):
@@ -431,7 +436,8 @@ LYS_D void shade_compact(const PassBuffers &b, int bounce, bool alive, int pid, 
  *    (bsdf_choose); refraction samples are drawn in place, reflection samples are queued in shared memory and drawn
  *    after a barrier by the first threads of the CTA, one queue entry per thread (dense warps).  Same inputs, same
  *    arithmetic, another thread.  The rng state after a reflection sample is its two draws further (:283-286);
- *  - for bounces >= 1 the slots are walked in the order k_trace left (hits first): warps are all-hit or all-miss. */
+ *  - for bounces >= 1 the slots are walked in the order k_trace left (hits first): warps are all-hit or all-miss.
+ * (A double-buffered exchange area saves the third barrier of an iteration but costs 13 KB of L1 per CTA: measured 1.4 % slower.) */
 template <int T>
 struct ShadeShared {
     float res[6][2 * T];      /* slot k * T + tid: sample k of the thread (in: wo_l, roughness, rng; out: DirSample local) */
@@ -482,10 +488,11 @@ __global__ void __launch_bounds__(SHADE_THREADS, LYS_SHADE_MINB(SHADE_THREADS)) 
     const int nl = fp.n_scene_lights + ((fp.tx_kind == 0) ? 0 : 8);
     if (threadIdx.x == 0) sh.qn = 0;
     __syncthreads();
+    unsigned tot_vert = 0, tot_shadow = 0;
     for (int b0 = blockIdx.x * blockDim.x; b0 < count; b0 += stride) {
         const bool valid = b0 + (int)threadIdx.x < count;
         const int i = !valid ? 0 : ordered ? b.order[bounce & 1][b0 + threadIdx.x] : b0 + (int)threadIdx.x;      /* hits first: warps are all-hit or all-miss */
-        bool alive = false, hit = false; int pid = -1; unsigned n_vert = 0, n_shadow = 0;
+        bool alive = false, hit = false; int pid = -1;
         float4 next_o = make_float4(0.0f, 0.0f, 0.0f, 0.0f), next_d = next_o; float next_dist = 0.0f;
         VertexCtx v;
         float cL = 0.0f, cB = 0.0f; int flags = 0;
@@ -522,13 +529,14 @@ __global__ void __launch_bounds__(SHADE_THREADS, LYS_SHADE_MINB(SHADE_THREADS)) 
                 if (metal2) s.bsdf = v.m.color * s.bsdf;
                 s.wi = to_world(v.onb, s.wi);
                 alive = shade_finish_use(fp, b, bounce, i, v, s, cL, cB, flags, next_o, next_d, next_dist);
-                n_vert = 1; n_shadow = (flags & 1) + ((flags >> 1) & 1);
+                tot_vert += 1; tot_shadow += (flags & 1) + ((flags >> 1) & 1);
             } else shade_miss(fp, b, i, v);
             pid = v.pid;
         }
-        shade_compact(b, bounce, alive, pid, next_o, next_d, next_dist, n_vert, n_shadow);
+        shade_compact(b, bounce, alive, pid, next_o, next_d, next_dist);
         __syncthreads();                                                  /* sh is reused by the next iteration */
     }
+    shade_stats(b, tot_vert, tot_shadow);
 }
 /* ------------------------------------------------------------------ trace: all BVH traversal of one bounce boundary
  * One persistent launch resolves the shadow rays of bounce `bounce` (connect) and the closest hits of bounce
@@ -574,16 +582,17 @@ __global__ void __launch_bounds__(128, LYS_TRACE_MINB(LAY)) k_trace(SceneDev sc,
     const int n_nodes = (int)sc.n_tris - 1;
     const int lane = threadIdx.x & 31;
     const float4 *__restrict__ nodes = (LAY == LAY_PAIR) ? sc.nodes : sc.nodes_oct;
+    constexpr bool CS = LAY == LAY_PAIR;      /* large scenes: path-state records bypass L2 residency (lys_device.cuh: ld_state) */
     /* warp-uniform loop (traverse<> votes): a warp owns 32 consecutive items; only the warp that straddles n_ext mixes kinds */
     for (int i0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31); i0 < total; i0 += stride) {
         const int i = i0 + lane;
         const bool is_ext = i < n_ext, is_con = !is_ext && i < total;
         if (i0 < n_ext) {
             float4 ro = make_float4(0.0f, 0.0f, 0.0f, 0.0f), rd = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
-            if (is_ext) { ro = b.ray_o[(bounce + 1) & 1][i]; rd = b.ray_d[(bounce + 1) & 1][i]; }
+            if (is_ext) { ro = ld_state<CS>(&b.ray_o[(bounce + 1) & 1][i]); rd = ld_state<CS>(&b.ray_d[(bounce + 1) & 1][i]); }
             float t;
             int h = traverse<false, LAY>(nodes, sc.leaf_tri, n_nodes, is_ext, v3(ro.x, ro.y, ro.z), v3(rd.x, rd.y, rd.z), FLT_MAX, t);
-            if (is_ext) b.hit[i] = h;
+            if (is_ext) st_state<CS>(&b.hit[i], h);
             /* processing order of shade(bounce + 1): hits from the front, misses from the back (one atomic per warp and kind) */
             if (ordered) {                     /* not for camera rays (their misses are whole warps already: shade(0) walks the slots in order) */
                 const bool isH = is_ext && h >= 0, isM = is_ext && h < 0;
@@ -592,28 +601,28 @@ __global__ void __launch_bounds__(128, LYS_TRACE_MINB(LAY)) k_trace(SceneDev sc,
                 if (lane == 0) { if (mh) bh = atomicAdd(&b.split[2 * (bounce + 1)], __popc(mh)); if (mm) bm = atomicAdd(&b.split[2 * (bounce + 1) + 1], __popc(mm)); }
                 bh = __shfl_sync(0xffffffffu, bh, 0); bm = __shfl_sync(0xffffffffu, bm, 0);
                 const unsigned lt = (1u << lane) - 1u;
-                if (isH) b.order[(bounce + 1) & 1][bh + __popc(mh & lt)] = i;
-                if (isM) b.order[(bounce + 1) & 1][n_ext - 1 - (bm + __popc(mm & lt))] = i;
+                if (isH) st_state<CS>(&b.order[(bounce + 1) & 1][bh + __popc(mh & lt)], i);
+                if (isM) st_state<CS>(&b.order[(bounce + 1) & 1][n_ext - 1 - (bm + __popc(mm & lt))], i);
             }
         }
         if (i0 + 31 >= n_ext) {
             /* vertices of this bounce in the order shade(bounce) took them: hit vertices (shadow rays) first, miss vertices last */
-            const int slot = !is_con ? 0 : (ordered && bounce >= 1) ? b.order[bounce & 1][i - n_ext] : i - n_ext;
+            const int slot = !is_con ? 0 : (ordered && bounce >= 1) ? ld_state<CS>(&b.order[bounce & 1][i - n_ext]) : i - n_ext;
             float4 ro = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(4)), rc = ro;
-            if (is_con) { ro = b.sh_o[slot]; rc = b.sh_c[slot]; }
+            if (is_con) { ro = ld_state<CS>(&b.sh_o[slot]); rc = ld_state<CS>(&b.sh_c[slot]); }
             const int flags = __float_as_int(ro.w);
             float L = 0.0f, B = 0.0f, t;
             V3 o = v3(ro.x, ro.y, ro.z);
             const bool need1 = is_con && !(flags & 4) && (flags & 1), need2 = is_con && !(flags & 4) && (flags & 2);
             if (__any_sync(0xffffffffu, need1)) {
                 float4 d1 = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
-                if (need1) d1 = b.sh_d1[slot];
+                if (need1) d1 = ld_state<CS>(&b.sh_d1[slot]);
                 int h = traverse<true, LAY>(nodes, sc.leaf_tri, n_nodes, need1, o, v3(d1.x, d1.y, d1.z), d1.w, t);
                 if (need1 && h < 0) L = rc.x;
             }
             if (__any_sync(0xffffffffu, need2)) {
                 float4 d2 = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
-                if (need2) d2 = b.sh_d2[slot];
+                if (need2) d2 = ld_state<CS>(&b.sh_d2[slot]);
                 int h = traverse<true, LAY>(nodes, sc.leaf_tri, n_nodes, need2, o, v3(d2.x, d2.y, d2.z), d2.w, t);
                 if (need2 && h < 0) B = rc.y;
             }
@@ -640,8 +649,9 @@ __global__ void __launch_bounds__(128, LYS_TRACE_MINB(LAY)) k_generate_trace(Sce
         uint32_t rng = fp.frame_rng ^ rng_split_hash((uint32_t)ix);   /* split_rng integrator.fut:109-114 */
         float wl; int ch;
         camera_sample(fp, col, row, rng, o, d, wl, ch);
-        b.ray_o[0][pid] = make_float4(o.x, o.y, o.z, wl);          /* bounce 0: slot == path id */
-        b.ray_d[0][pid] = make_float4(d.x, d.y, d.z, __uint_as_float(rng));
+        constexpr bool CS = LAY == LAY_PAIR;
+        st_state<CS>(&b.ray_o[0][pid], make_float4(o.x, o.y, o.z, wl));          /* bounce 0: slot == path id */
+        st_state<CS>(&b.ray_d[0][pid], make_float4(d.x, d.y, d.z, __uint_as_float(rng)));
         b.dist[0][pid] = 0.0f;
         b.acc[pid] = make_float4(0.0f, 0.0f, LYS_INF, 0.0f);
         b.chan[pid] = (uint8_t)ch;
@@ -650,7 +660,7 @@ __global__ void __launch_bounds__(128, LYS_TRACE_MINB(LAY)) k_generate_trace(Sce
     }
     float t;
     const int h = traverse<false, LAY>((LAY == LAY_PAIR) ? sc.nodes : sc.nodes_oct, sc.leaf_tri, (int)sc.n_tris - 1, act, o, d, FLT_MAX, t);
-    if (act) b.hit[pid] = h;
+    if (act) st_state<LAY == LAY_PAIR>(&b.hit[pid], h);
 }
 
 /* ------------------------------------------------------------------ tail: all remaining bounces in one launch
