@@ -28,6 +28,16 @@ namespace lys {
  * walk that pushes the right child while descending left takes exactly the same decisions in the same
  * order, so hits, ties (strict t < tmax, shapes.fut:64) and culling are identical. */
 struct RayInv { V3 o, d, inv; };
+/* one 32-byte sector of a traversal record in ONE request: sm_100 has 256-bit global loads (LDG.E.256), half the LSU
+ * instructions and L1 tag look-ups of two 128-bit loads (the large scene runs the L1 data stage at 72 % of its peak) */
+LYS_D void ld_sector(const float4 *__restrict__ p, float4 &a, float4 &b) {
+#ifdef __CUDACC__
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
+#else
+    a = p[0]; b = p[1];
+#endif
+}
 /* hit_aabb (shapes.fut:114-135).  The reference leaves after the first axis with tmax <= tmin; tmin only grows and
  * tmax only shrinks from axis to axis (fmaxf/fminf drop NaN operands), so an axis that fails keeps failing and the
  * single test after the third axis gives the same boolean.  No per-axis branch: the lanes of a warp stay together.
@@ -67,10 +77,10 @@ LYS_D bool slab_test_oct(const RayInv &r, float4 nr, float4 fr, float tmax, floa
 /* hit_triangle (shapes.fut:66-86) against sorted leaf `leaf`: the plane part needs only (a, n = e1 x e2), one 32-byte
  * sector; the edges are fetched only by the lanes whose t lies in (0, tmax). */
 LYS_D bool leaf_test_at(const RayInv &r, const float4 *__restrict__ q, float tmax, float &t) {
-    float4 q0 = __ldg(q), q1 = __ldg(q + 1);
+    float4 q0, q1; ld_sector(q, q0, q1);
     float inv; V3 s;
     if (!tri_plane_test(r.o, r.d, v3(q0.x, q0.y, q0.z), v3(q1.x, q1.y, q1.z), tmax, t, inv, s)) return false;
-    float4 q2 = __ldg(q + 2), q3 = __ldg(q + 3);
+    float4 q2, q3; ld_sector(q + 2, q2, q3);
     return tri_uv_test(r.d, s, inv, v3(q2.x, q2.y, q2.z), v3(q3.x, q3.y, q3.z));
 }
 LYS_D bool leaf_test(const RayInv &r, const float4 *__restrict__ leaf_tri, int leaf, float tmax, float &t) {
@@ -124,7 +134,8 @@ LYS_D unsigned long long trav_base(const float4 *nodes, int n_nodes, const RayIn
 template <bool ANY, bool OCT>
 LYS_D void trav_node_stage(const RayInv &r, unsigned long long nbase, float tmax, int &cur, int &sp, TravStack<ANY> &st) {
     const float4 *q = reinterpret_cast<const float4 *>(nbase + 64ull * (unsigned)cur);
-    const float4 l0 = __ldg(q), l1 = __ldg(q + 1), r0 = __ldg(q + 2), r1 = __ldg(q + 3);
+    float4 l0, l1, r0, r1;
+    ld_sector(q, l0, l1); ld_sector(q + 2, r0, r1);
     const int lc = __float_as_int(l0.w), rc = __float_as_int(l1.w);
     float tl, tr;
     bool pl = OCT ? slab_test_oct(r, l0, l1, tmax, tl) : slab_test(r, l0, l1, tmax, tl);
@@ -162,7 +173,7 @@ LYS_D int traverse(const float4 *__restrict__ nodes, const float4 *__restrict__ 
             for (int k = 0; k < TRAV_NB; k++) {
                 if (cur >= 0) {
                     const float4 *q = reinterpret_cast<const float4 *>(nbase + 32ull * (unsigned)cur);
-                    float4 lo = __ldg(q), hi = __ldg(q + 1);
+                    float4 lo, hi; ld_sector(q, lo, hi);
                     float tn;
                     if (slab_test_oct(r, lo, hi, tmax, tn)) {
                         stack[sp++] = __float_as_int(hi.w);       /* right child waits */
