@@ -152,7 +152,9 @@ LYS_D void trav_node_stage(const RayInv &r, unsigned long long nbase, float tmax
  *   LAY_PAIR_OCT  pair records, octant copies
  *   LAY_PAIR      pair records, one copy, box test with selects (scenes whose octant copies would not stay in L2) */
 enum { LAY_SINGLE = 0, LAY_PAIR_OCT = 1, LAY_PAIR = 2 };
+#ifndef TRAV_NB
 #define TRAV_NB 2          /* node stages per loop iteration: 2 measured best on every layout and scene size (profiles/README.md 8.2) */
+#endif
 template <bool ANY, int LAY>
 LYS_D int traverse(const float4 *__restrict__ nodes, const float4 *__restrict__ leaf_tri, int n_nodes, bool active,
                    V3 o, V3 d, float tmax, float &t_hit) {

@@ -199,6 +199,38 @@ def test_entry_points_bit_exact(orc, pkg, gpu, scenes, name):
     assert bits_equal(a.image(), b.image()) and a.image().shape == (33, 47, 3)
 
 
+def test_stepping_loop_runs_ahead_bit_exact(orc, pkg, gpu, scenes):
+    """The interactive host's loop (liblys.c:104-123: step, free the stepped state, render + read back, repeat).  Once the host
+    steps the state the previous step returned, the library computes steps AHEAD on its pass-slot streams
+    (futhark_entry_step); what the host sees must not depend on that: every frame equals the oracle's, also when the loop is
+    interrupted by a key event (steps computed ahead are dropped), resumed, and when an older state is stepped again."""
+    so, sg = both(orc, pkg, gpu, scenes['cornell'], 90, 120)
+    so, sg = so.key(K['m']), sg.key(K['m'])
+    frame = np.empty((90, 120), np.int32)
+    keep = None
+    for k in range(14):
+        so_old, so = so, so.step()
+        old, sg = sg, sg.step()
+        if k == 5:
+            keep = (so_old, old)                              # an older state the library has already run ahead of
+        else:
+            old.free()
+        sg.render(frame)
+        if k in (2, 9, 13):
+            assert bits_equal(so.render(), frame), k
+    assert bits_equal(so.image(), sg.image()) and so.scalars()['n_frames'] == sg.info()['n_frames'] == 14
+    so, sg = so.key(K['w']), sg.key(K['w'])                   # camera moves: n_frames back to 0, ahead steps dropped
+    for k in range(5):
+        so = so.step()
+        old, sg = sg, sg.step()
+        old.free()
+    assert bits_equal(so.image(), sg.image()) and bits_equal(so.render(), sg.render())
+    so, sg = keep                                             # back to the state saved in the first loop
+    for k in range(3):
+        so, sg = so.step(), sg.step()
+    assert bits_equal(so.image(), sg.image()) and so.scalars()['rng'] == sg.info()['rng']
+
+
 def test_sample_points_bit_exact(orc, pkg, gpu, scenes):
     for name in ('cornell', 'spectrumsphere'):
         so, sg = both(orc, pkg, gpu, scenes[name], 48, 64, cam_conf_id=2)     # demo-save uses cam_conf_id 2 (wrapper.rs:50)

@@ -118,3 +118,41 @@ def test_roofline_traffic_matches_the_committed_ncu_list(tmp_path):
     assert old['per_bounce_sequence']['launches_per_pass'] == 17
     # algorithmic bytes per launch (bench.py) are an order of magnitude above the DRAM traffic: the BVH is cache resident
     assert old['per_bounce_sequence']['dram_bytes_per_launch'] < 0.2 * 211e6
+
+
+def test_path_tile_is_a_bijection(tmp_path):
+    """path_tile (csrc/lys_wavefront.h): path id -> (column, local row) with 8x4 pixel tiles per warp.  Compiled for the host
+    (the header is plain C++ next to the emulator's cuda_runtime.h stand-in) and checked for every id of grids with ragged
+    edges, incomplete last bands, single rows / columns: every pixel exactly once, and a full band's first ids are 8x4 tiles."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / 'tile.cpp'
+    src.write_text(r"""
+#include "lys_wavefront.h"
+#include <cstdio>
+#include <vector>
+int main() {
+    const int sizes[][2] = {{1, 1}, {7, 3}, {8, 4}, {9, 5}, {16, 8}, {17, 9}, {31, 2}, {33, 7}, {128, 96}, {5, 100}, {100, 5}, {1920, 1080}, {3, 4}, {8, 1}};
+    for (auto &sz : sizes) {
+        const int gw = sz[0], rows = sz[1];
+        std::vector<int> seen((size_t)gw * rows, 0);
+        for (int pid = 0; pid < gw * rows; pid++) {
+            int col = -1, rl = -1;
+            lys::path_tile(gw, rows, pid, col, rl);
+            if (col < 0 || col >= gw || rl < 0 || rl >= rows) { printf("out of range %d %d pid %d -> %d %d\n", gw, rows, pid, col, rl); return 1; }
+            if (seen[(size_t)rl * gw + col]++) { printf("twice %d %d pid %d\n", gw, rows, pid); return 1; }
+            const int band = pid / (4 * gw), q = pid % (4 * gw);
+            if (band * 4 + 4 <= rows && q < 32 * (gw / 8)) {       /* a full tile: 32 consecutive ids = 8 columns x 4 rows */
+                if (col / 8 != q / 32 || rl / 4 != band) { printf("tile %d %d pid %d -> %d %d\n", gw, rows, pid, col, rl); return 1; }
+            }
+        }
+    }
+    printf("ok\n");
+    return 0;
+}
+""")
+    exe = tmp_path / 'tile'
+    subprocess.check_call(['g++', '-std=c++17', '-O1', '-I', os.path.join(root, 'tests', 'simt_emu'), '-I', os.path.join(root, 'msc-futhark-ray-tracer_b200', 'csrc'),
+                           '-DLYS_EMU_HOST_ONLY', str(src), '-o', str(exe)])
+    assert subprocess.check_output([str(exe)], text=True).strip() == 'ok'

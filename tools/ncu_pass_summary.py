@@ -28,6 +28,7 @@ def table(last):
     lines = ['| # | kernel | us | DRAM MB (read + write) | warp instr (M) | threads / instr |', '|---|---|---|---|---|---|']
     tot_us = 0.0
     tr = []
+    tail_us = 0.0
     winst = tinst = tr_winst = tr_tinst = 0.0
     for i, (n, m) in enumerate(last):
         us = m.get('gpu__time_duration.sum', 0.0) / 1000.0
@@ -39,13 +40,15 @@ def table(last):
         if n.startswith('k_trace') or n.startswith('k_generate_trace'):      # the camera-ray launch carries trace(-1)
             tr.append((us, mb * 1e6))
             tr_winst += wi; tr_tinst += ti
+        if n.startswith('k_tail'):
+            tail_us += us
         lines.append(f"| {i} | {n} | {us:.1f} | {mb:.1f} | {m.get('smsp__inst_executed.sum', 0.0) / 1e6:.1f} | {m.get('smsp__thread_inst_executed_per_inst_executed.ratio', 0.0):.1f} |")
     share = sum(u for u, _ in tr) / tot_us
     lines.append('')
     lines.append(f'{len(last)} launches, {tot_us:.0f} us of serialised kernel time; k_trace: {len(tr)} launches, {sum(u for u, _ in tr):.0f} us '
                  f'({share * 100:.0f} % of the pass), {sum(b for _, b in tr) / 1e6:.0f} MB of DRAM traffic = {sum(b for _, b in tr) / len(tr) / 1e6:.1f} MB per launch.')
     return lines, {'launches_per_pass': len(tr), 'dram_bytes_per_pass': sum(b for _, b in tr), 'dram_bytes_per_launch': sum(b for _, b in tr) / len(tr),
-                   'k_trace_us': sum(u for u, _ in tr), 'pass_us': tot_us, 'k_trace_share_of_pass_ncu': share,
+                   'k_trace_us': sum(u for u, _ in tr), 'k_tail_us': tail_us, 'traversal_us': sum(u for u, _ in tr) + tail_us, 'pass_us': tot_us, 'k_trace_share_of_pass_ncu': share,
                    # issue roofline inputs (what bench.py's roofline.issue is computed from): warp-level instructions of one pass and
                    # the instruction-weighted number of active threads per issued instruction
                    'warp_inst_per_pass': winst, 'threads_per_inst': tinst / winst if winst else None,
