@@ -146,7 +146,7 @@ def fuzz_keys(ctx, rng, count):
                     return False
             so = so.step()
             old, sg = sg, sg.step()
-            if free_old[0]:
+            if free_old[0] and not (saved is not None and old is saved[1]):
                 old.free()                  # the interactive host's pattern (liblys.c:110): the stepped state is freed at once
             return True
         for _ in range(int(rng.integers(5, 40))):
