@@ -165,3 +165,24 @@ def test_unmodified_reference_host_runs_against_the_library(emu_lib, orc, scenes
     e['LYS_SDL_SCRIPT'] = '0:resize:32x24 0:key:109 3:quit'
     r = subprocess.run([exe['emu'], '-o', obj], env=e, text=True, capture_output=True, timeout=900)
     assert r.returncode != 0 and 'Futhark error' in r.stderr and 'shape does not match' in r.stderr
+
+
+def test_partitioned_rendering_world2_gloo_runs_the_library_kernels(emu_lib, tmp_path):
+    """SURVEY 8(e) with world_size 2 over gloo, THROUGH the library: each rank runs the product's kernels (this emulator build)
+    on its interleaved rows (lys_context_set_partition) resp. its pass range (lys_state_advance_rng + the weighted last
+    accumulate), one sum-reduce of the framebuffer, and rank 0 compares with the oracle: rows bit for bit, passes within 1e-4."""
+    import json
+    import socket
+    sk = socket.socket(); sk.bind(('127.0.0.1', 0)); port = sk.getsockname()[1]; sk.close()
+    out = str(tmp_path / 'res.json')
+    procs = []
+    for rank in range(2):
+        e = dict(os.environ)
+        e.update({'LYS_EMU_LIB': emu_lib, 'RANK': str(rank), 'WORLD_SIZE': '2', 'MASTER_ADDR': '127.0.0.1', 'MASTER_PORT': str(port), 'OUT': out,
+                  'OMP_NUM_THREADS': '2'})
+        procs.append(subprocess.Popen([sys.executable, RUN_EMU, os.path.join(ROOT, 'tests', 'simt_emu', 'partition_worker.py')], env=e,
+                                      stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    logs = [p.communicate(timeout=900)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), '\n'.join(l[-1500:] for l in logs)
+    res = json.load(open(out))
+    assert res == {'rows_zero_elsewhere': True, 'rows_bit_exact': True, 'passes_close': True}, res
