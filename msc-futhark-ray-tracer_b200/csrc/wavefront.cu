@@ -450,12 +450,14 @@ LYS_D void shade_stats(const PassBuffers &b, unsigned n_vert, unsigned n_shadow)
  *    after a barrier by the first threads of the CTA, one queue entry per thread (dense warps).  Same inputs, same
  *    arithmetic, another thread.  The rng state after a reflection sample is its two draws further (:283-286);
  *  - for bounces >= 1 the slots are walked in the order k_trace left (hits first): warps are all-hit or all-miss.
- * (A double-buffered exchange area saves the third barrier of an iteration but costs 13 KB of L1 per CTA: measured 1.4 % slower.) */
+ * Two block barriers per iteration (queue filled / queue drained).  What a third one at the end would protect is the queue and its
+ * counter only (sample slots are private to their thread outside the drain phase), so those two alternate between iterations
+ * (+1 KB of shared memory; double-buffering the whole 13 KB exchange area was measured 1.4 % slower: it costs L1). */
 template <int T>
 struct ShadeShared {
     float res[6][2 * T];      /* slot k * T + tid: sample k of the thread (in: wo_l, roughness, rng; out: DirSample local) */
-    unsigned short q[2 * T];  /* slots waiting for a reflection sample */
-    int qn;
+    unsigned short q[2][2 * T];  /* slots waiting for a reflection sample; two queues, alternating between iterations */
+    int qn[2];
 };
 template <class SH>
 LYS_D void shade_put_sample(SH &sh, int slot, const DirSample &s) {
@@ -471,7 +473,7 @@ LYS_D DirSample shade_get_sample(const SH &sh, int slot) {
 }
 /* one sample_dir call up to its branch: refraction sample drawn here, reflection sample queued.  Warp-collective. */
 template <class SH>
-LYS_D void shade_draw_or_queue(SH &sh, bool want, int slot, const VertexCtx &v, uint32_t &rng, bool &metal) {
+LYS_D void shade_draw_or_queue(SH &sh, int par, bool want, int slot, const VertexCtx &v, uint32_t &rng, bool &metal) {
     bool reflect = false; metal = false;
     if (want) {
         reflect = bsdf_choose(v.wo_l, v.m, rng, metal, true, v.F);
@@ -485,9 +487,9 @@ LYS_D void shade_draw_or_queue(SH &sh, bool want, int slot, const VertexCtx &v, 
     if (mask) {
         const int lane = threadIdx.x & 31;
         int base = 0;
-        if (lane == __ffs(mask) - 1) base = atomicAdd(&sh.qn, __popc(mask));
+        if (lane == __ffs(mask) - 1) base = atomicAdd(&sh.qn[par], __popc(mask));
         base = __shfl_sync(0xffffffffu, base, __ffs(mask) - 1);
-        if (reflect) sh.q[base + __popc(mask & ((1u << lane) - 1u))] = (unsigned short)slot;
+        if (reflect) sh.q[par][base + __popc(mask & ((1u << lane) - 1u))] = (unsigned short)slot;
     }
 }
 #ifndef LYS_SHADE_MINB
@@ -499,10 +501,11 @@ __global__ void __launch_bounds__(SHADE_THREADS, LYS_SHADE_MINB(SHADE_THREADS)) 
     const int count = b.counts[bounce];
     const int stride = gridDim.x * blockDim.x;
     const int nl = fp.n_scene_lights + ((fp.tx_kind == 0) ? 0 : 8);
-    if (threadIdx.x == 0) sh.qn = 0;
+    if (threadIdx.x == 0) { sh.qn[0] = 0; sh.qn[1] = 0; }
     __syncthreads();
     unsigned tot_vert = 0, tot_shadow = 0;
-    for (int b0 = blockIdx.x * blockDim.x; b0 < count; b0 += stride) {
+    int par = 0;
+    for (int b0 = blockIdx.x * blockDim.x; b0 < count; b0 += stride, par ^= 1) {
         const bool valid = b0 + (int)threadIdx.x < count;
         const int i = !valid ? 0 : ordered ? b.order[bounce & 1][b0 + threadIdx.x] : b0 + (int)threadIdx.x;      /* hits first: warps are all-hit or all-miss */
         bool alive = false, hit = false; int pid = -1;
@@ -518,17 +521,17 @@ __global__ void __launch_bounds__(SHADE_THREADS, LYS_SHADE_MINB(SHADE_THREADS)) 
         if (hit) b.sh_d1[i] = rec_d1;                                     /* records leave the registers as soon as they are complete */
         /* both sample_dir calls of the vertex: the MIS sample (direct.fut:83) and the continuation (integrator.fut:56) */
         bool metal1, metal2;
-        shade_draw_or_queue(sh, lit, threadIdx.x, v, v.rng, metal1);
-        shade_draw_or_queue(sh, hit, SHADE_THREADS + threadIdx.x, v, v.rng, metal2);
+        shade_draw_or_queue(sh, par, lit, threadIdx.x, v, v.rng, metal1);
+        shade_draw_or_queue(sh, par, hit, SHADE_THREADS + threadIdx.x, v, v.rng, metal2);
         __syncthreads();
-        for (int j = threadIdx.x; j < sh.qn; j += SHADE_THREADS) {
-            const int slot = sh.q[j];
+        for (int j = threadIdx.x; j < sh.qn[par]; j += SHADE_THREADS) {
+            const int slot = sh.q[par][j];
             Mat1 m; m.color = 0.0f; m.roughness = sh.res[3][slot]; m.metalness = 0.0f; m.ref_ix = 0.0f; m.opacity = 0.0f;
             uint32_t rng = __float_as_uint(sh.res[4][slot]);
             shade_put_sample(sh, slot, sample_reflection(v3(sh.res[0][slot], sh.res[1][slot], sh.res[2][slot]), m, rng));
         }
         __syncthreads();
-        if (threadIdx.x == 0) sh.qn = 0;        /* queue drained: empty it for the next iteration (ordered by the barrier that ends this one) */
+        if (threadIdx.x == 0) sh.qn[par] = 0;   /* queue drained: empty for the iteration after the next (the next one uses the other queue) */
         if (lit) {
             DirSample s = shade_get_sample(sh, threadIdx.x);
             if (metal1) s.bsdf = v.m.color * s.bsdf;                      /* metal :352-355 */
@@ -547,7 +550,8 @@ __global__ void __launch_bounds__(SHADE_THREADS, LYS_SHADE_MINB(SHADE_THREADS)) 
             pid = v.pid;
         }
         shade_compact(b, bounce, alive, pid, next_o, next_d, next_dist);
-        __syncthreads();                                                  /* sh is reused by the next iteration */
+        /* no barrier here: after the second barrier a thread only reads its OWN two sample slots, and the next iteration
+         * writes its own slots and the OTHER queue; this iteration's queue is touched again two barriers later */
     }
     shade_stats(b, tot_vert, tot_shadow);
 }
