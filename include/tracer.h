@@ -108,26 +108,12 @@ int futhark_entry_sample_points_n(struct futhark_context *ctx, struct futhark_op
                                   struct futhark_f32_3d **out1,
                                   const struct futhark_opaque_state *s, const uint32_t samples_per_pixel);
 
-/* ---- the rest of the surface a `futhark cuda --library` header carries ----------------------
- * None of this is called by the reference's hosts (liblys.c, ffi.rs); it is what the Futhark compiler emits next to the
- * declarations above for every CUDA-backend library, restated from the compiler's conventions so that a host written
- * against the generated tracer.h (tuning flags, profiling report, zero-copy device access) still links and behaves
- * sensibly.  There is no run-time compilation and no tunable "size" in this library: the program / PTX / nvrtc / size
- * setters are accepted and ignored, futhark_get_num_sizes() is 0 and futhark_context_config_set_size() reports failure. */
+/* ---- what else a `futhark cuda --library` header carries and a host can use ------------------
+ * Not called by the reference's hosts (liblys.c, ffi.rs): the profiling report and zero-copy device access, with the
+ * generated header's signatures.  The run-time-compilation and tuning setters of a generated header (nvrtc options, program /
+ * PTX dumps, default group / tile sizes, named sizes) have no counterpart here -- nothing is compiled at run time and no grid
+ * size is user-tunable -- and are not declared. */
 void futhark_context_config_set_profiling(struct futhark_context_config *cfg, int flag);    /* kernel-class timing from the start */
-void futhark_context_config_add_nvrtc_option(struct futhark_context_config *cfg, const char *opt);
-void futhark_context_config_dump_program_to(struct futhark_context_config *cfg, const char *path);
-void futhark_context_config_load_program_from(struct futhark_context_config *cfg, const char *path);
-void futhark_context_config_dump_ptx_to(struct futhark_context_config *cfg, const char *path);
-void futhark_context_config_load_ptx_from(struct futhark_context_config *cfg, const char *path);
-void futhark_context_config_set_default_group_size(struct futhark_context_config *cfg, int size);
-void futhark_context_config_set_default_num_groups(struct futhark_context_config *cfg, int num);
-void futhark_context_config_set_default_tile_size(struct futhark_context_config *cfg, int num);
-void futhark_context_config_set_default_threshold(struct futhark_context_config *cfg, int num);
-int futhark_context_config_set_size(struct futhark_context_config *cfg, const char *size_name, size_t size_value);   /* 1: no such size */
-int futhark_get_num_sizes(void);
-const char *futhark_get_size_name(int i);
-const char *futhark_get_size_class(int i);
 void futhark_context_pause_profiling(struct futhark_context *ctx);
 void futhark_context_unpause_profiling(struct futhark_context *ctx);
 /* malloc'ed text (caller frees): kernel launches, device time per kernel class when profiling is on, pooled device memory */

@@ -512,21 +512,8 @@ int futhark_context_clear_caches(struct futhark_context *ctx) {
     pool_release_all(ctx);
     return 0;
 }
-/* the rest of the generated cuda-backend surface (tracer.h): no run-time compilation, no tunable sizes */
+/* profiling surface of a generated cuda-backend header (tracer.h) */
 void futhark_context_config_set_profiling(struct futhark_context_config *cfg, int flag) { if (cfg) cfg->profiling = flag; }
-void futhark_context_config_add_nvrtc_option(struct futhark_context_config *cfg, const char *opt) { (void)cfg; (void)opt; }
-void futhark_context_config_dump_program_to(struct futhark_context_config *cfg, const char *path) { (void)cfg; (void)path; }
-void futhark_context_config_load_program_from(struct futhark_context_config *cfg, const char *path) { (void)cfg; (void)path; }
-void futhark_context_config_dump_ptx_to(struct futhark_context_config *cfg, const char *path) { (void)cfg; (void)path; }
-void futhark_context_config_load_ptx_from(struct futhark_context_config *cfg, const char *path) { (void)cfg; (void)path; }
-void futhark_context_config_set_default_group_size(struct futhark_context_config *cfg, int size) { (void)cfg; (void)size; }
-void futhark_context_config_set_default_num_groups(struct futhark_context_config *cfg, int num) { (void)cfg; (void)num; }
-void futhark_context_config_set_default_tile_size(struct futhark_context_config *cfg, int num) { (void)cfg; (void)num; }
-void futhark_context_config_set_default_threshold(struct futhark_context_config *cfg, int num) { (void)cfg; (void)num; }
-int futhark_context_config_set_size(struct futhark_context_config *cfg, const char *size_name, size_t size_value) { (void)cfg; (void)size_name; (void)size_value; return 1; }
-int futhark_get_num_sizes(void) { return 0; }
-const char *futhark_get_size_name(int i) { (void)i; return nullptr; }
-const char *futhark_get_size_class(int i) { (void)i; return nullptr; }
 void futhark_context_pause_profiling(struct futhark_context *ctx) { if (ctx) { ctx->timer.resolve(ctx->stream); ctx->timer.on = 0; } }
 void futhark_context_unpause_profiling(struct futhark_context *ctx) { if (ctx) ctx->timer.on = 1; }
 char *futhark_context_report(struct futhark_context *ctx) {

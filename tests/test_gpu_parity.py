@@ -320,7 +320,6 @@ def test_generated_surface_extras(pkg, gpu, scenes):
     gpu.check(L.futhark_values_u32_1d(c, ub, back.ctypes.data), 'values')
     assert np.array_equal(back, u)
     L.futhark_free_u32_1d(c, ua); L.futhark_free_u32_1d(c, ub)
-    assert L.futhark_get_num_sizes() == 0 and L.futhark_context_config_set_size(None, b'x', 1) == 1
     t, tm, m = scenes['cornell']
     with pkg.Context(profiling=True) as pc:                                # futhark_context_config_set_profiling
         s = pkg.State.init(pc, t, tm, m, 48, 64)
