@@ -351,8 +351,8 @@ __global__ void k_gather_leaves(const float *__restrict__ tris, const uint32_t *
     V3 e1 = b - a, e2 = c - a;                                          /* shapes.fut:69-70 */
     V3 nc = cross(e1, e2);                                              /* shapes.fut:71: ray independent, stored once */
     leaf_tri[4ll * i + 0] = make_float4(a.x, a.y, a.z, __uint_as_float(tri_mats[s]));
-    leaf_tri[4ll * i + 1] = make_float4(nc.x, nc.y, nc.z, __uint_as_float(s));
-    leaf_tri[4ll * i + 2] = make_float4(e1.x, e1.y, e1.z, 0.0f);
+    leaf_tri[4ll * i + 1] = make_float4(nc.x, nc.y, nc.z, __int_as_float((int)0x80000000));   /* .w: escape link (k_thread_links) */
+    leaf_tri[4ll * i + 2] = make_float4(e1.x, e1.y, e1.z, __uint_as_float(s));
     leaf_tri[4ll * i + 3] = make_float4(e2.x, e2.y, e2.z, 0.0f);
     leaf_box[2ll * i + 0] = box_c[s];
     leaf_box[2ll * i + 1] = box_h[s];
@@ -599,6 +599,27 @@ __global__ void k_pack_nodes(const float4 *__restrict__ A, const int *__restrict
     }
 }
 
+/* Escape links for the single-box layout (LAY_SINGLE, wavefront.cu).  The reference's walk always goes left first
+ * (bvh.fut:126-142), whatever the ray: the node visited after a failed box test or a finished leaf is therefore a property of
+ * the TREE -- the right child of the nearest ancestor-or-self that is a left child, or the end marker on the right spine --
+ * and can be stored instead of being kept on a per-ray stack (a threaded tree).  Thread x < n: leaf x (link in leaf_tri[4x+1].w);
+ * thread n + i: internal node i (link replaces the right-child slot of its eight octant records: the right child itself is the
+ * escape link of the left child, nobody else needs it). */
+__global__ void k_thread_links(const int *__restrict__ right, const int *__restrict__ parent, const int *__restrict__ leaf_parent,
+                               int n, float4 *__restrict__ leaf_tri, float4 *__restrict__ nodes_oct) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n_nodes = n - 1;
+    if (x >= n + n_nodes) return;
+    const bool leaf = x < n;
+    int self = leaf ? ~x : x - n;                       /* child encoding: internal i -> i, leaf i -> ~i */
+    int p = leaf ? leaf_parent[x] : parent[x - n];
+    while (p >= 0 && right[p] == self) { self = p; p = parent[p]; }      /* climb while we are a right child */
+    const int link = (p < 0) ? (int)0x80000000 : right[p];
+    if (leaf) leaf_tri[4ll * x + 1].w = __int_as_float(link);
+    else for (int o = 0; o < 8; o++) nodes_oct[2ll * ((long long)o * n_nodes + (x - n)) + 1].w = __int_as_float(link);
+}
+
+
 /* ------------------------------------------------------------------ host driver */
 static inline int cdiv(long long a, int b) { return (int)((a + b - 1) / b); }
 
@@ -672,8 +693,10 @@ cudaError_t build_lbvh(SceneDev &sc, BuildScratch &ws, int refit_mode, cudaStrea
     }
     {
         static const int force_pair = []() { const char *e = getenv("LYS_TRACE_PAIR"); return (e && atoi(e)) ? 1 : 0; }();   /* 1: pair records on small scenes too (tests) */
-        sc.single_nodes = (sc.nodes_oct && n <= LYS_SINGLE_MAX_TRIS && !force_pair) ? 1 : 0;
+        static const int single_max = []() { const char *e = getenv("LYS_SINGLE_MAX"); return (e && atoi(e) > 0) ? atoi(e) : LYS_SINGLE_MAX_TRIS; }();   /* layout threshold (tests, measurements) */
+        sc.single_nodes = (sc.nodes_oct && n <= single_max && !force_pair) ? 1 : 0;
         k_pack_nodes<<<cdiv(n_nodes + 1, T), T, 0, stream>>>(sc.node_box, sc.left, sc.right, n_nodes, sc.nodes, sc.nodes_oct, sc.single_nodes); nl++;
+        if (sc.single_nodes) { k_thread_links<<<cdiv(n + n_nodes, T), T, 0, stream>>>(sc.right, sc.parent, ws.leaf_parent, n, sc.leaf_tri, sc.nodes_oct); nl++; }
     }
     if (launches) *launches += nl;
     return cudaGetLastError();

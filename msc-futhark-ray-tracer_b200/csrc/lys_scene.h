@@ -4,8 +4,9 @@
  *   tris      [n][9]  f32   input triangles as uploaded (src/scene.fut:26-35)
  *   tri_mats  [n]     u32
  *   mats      [m][28] f32   material rows (src/scene.fut:37-53)
- *   leaf_tri  [n][4]  float4  sorted leaves, 64 B: (a.xyz | mat_ix), (e1 x e2 | source index) = the plane test's sector,
- *                             then (e1.xyz | 0), (e2.xyz | 0) for the barycentric test
+ *   leaf_tri  [n][4]  float4  sorted leaves, 64 B: (a.xyz | mat_ix), (e1 x e2 | escape link) = the plane test's sector,
+ *                             then (e1.xyz | source index), (e2.xyz | 0) for the barycentric test.  Escape link (single-box
+ *                             scenes only): the node the left-first walk visits after this leaf (lbvh.cu: k_thread_links)
  *   leaf_box  [n][2]  float4  sorted leaf boxes (center | half_dims)
  *   leaf_frame [n][3] float4  shading frame of a hit on the leaf: unit normal, then b and t of mk_orthonormal_basis (material.fut:374-379)
  *   nodes     [n][4]  float4  traversal records, 64 B = two sectors: record i < n-1 holds the boxes of BOTH children of node i,
@@ -17,7 +18,8 @@
  *                             (near | left) (far | right) (near | 0) (far | 0) with near/far already picked per axis as hit_aabb's
  *                             swap would (octant bit 2/1/0 = 1/dir.x, .y, .z < 0), so the box test needs no select.
  *                             Scenes up to LYS_SINGLE_MAX_TRIS triangles (single_nodes = 1): [8][n-1][2] float4, one box per
- *                             record, (near.xyz | left) (far.xyz | right) of node i itself
+ *                             record, (near.xyz | left) (far.xyz | escape link) of node i itself: a threaded tree, the walk
+ *                             needs no stack (where it goes when the box fails is a property of the tree, not of the ray)
  *   node_box  [n-1][2] float4 node boxes as the reference stores them (center | half_dims)
  *   left/right/parent/height [n-1] i32; child encoding: internal i -> i, leaf i -> ~i
  *   morton, sorted_idx [n] u32; bounds [6] f32 (center, half_dims)
@@ -29,7 +31,7 @@
 
 namespace lys {
 
-#define LYS_SINGLE_MAX_TRIS 1024         /* up to here the octant copies hold one box per record (wavefront.cu: LAY_SINGLE) */
+#define LYS_SINGLE_MAX_TRIS 16384        /* up to here the octant copies hold one box per record (wavefront.cu: LAY_SINGLE, stackless; measured: profiles/README.md 8.10) */
 #define LYS_OCT_MAX_NODES (1 << 16)      /* 8 x 4 MB of octant records at most: stays L2 resident */
 
 struct LightRec {            /* 32 floats = 128 B, float4-aligned */

@@ -76,15 +76,16 @@ LYS_D bool slab_test_oct(const RayInv &r, float4 nr, float4 fr, float tmax, floa
 }
 /* hit_triangle (shapes.fut:66-86) against sorted leaf `leaf`: the plane part needs only (a, n = e1 x e2), one 32-byte
  * sector; the edges are fetched only by the lanes whose t lies in (0, tmax). */
-LYS_D bool leaf_test_at(const RayInv &r, const float4 *__restrict__ q, float tmax, float &t) {
+LYS_D bool leaf_test_at(const RayInv &r, const float4 *__restrict__ q, float tmax, float &t, int *escape = nullptr) {
     float4 q0, q1; ld_sector(q, q0, q1);
+    if (escape) *escape = __float_as_int(q1.w);          /* single-box scenes: where the walk goes after this leaf */
     float inv; V3 s;
     if (!tri_plane_test(r.o, r.d, v3(q0.x, q0.y, q0.z), v3(q1.x, q1.y, q1.z), tmax, t, inv, s)) return false;
     float4 q2, q3; ld_sector(q + 2, q2, q3);
     return tri_uv_test(r.d, s, inv, v3(q2.x, q2.y, q2.z), v3(q3.x, q3.y, q3.z));
 }
-LYS_D bool leaf_test(const RayInv &r, const float4 *__restrict__ leaf_tri, int leaf, float tmax, float &t) {
-    return leaf_test_at(r, leaf_tri + 4ll * leaf, tmax, t);
+LYS_D bool leaf_test(const RayInv &r, const float4 *__restrict__ leaf_tri, int leaf, float tmax, float &t, int *escape = nullptr) {
+    return leaf_test_at(r, leaf_tri + 4ll * leaf, tmax, t, escape);
 }
 /* ---- the walk.  Reference order (bvh.fut:126-142): enter a node = test ITS box against the CURRENT tmax; if it passes go
  * left, and come back for the right child when the left subtree is done; leaves are never box-tested.
@@ -161,14 +162,12 @@ LYS_D int traverse(const float4 *__restrict__ nodes, const float4 *__restrict__ 
     RayInv r; r.o = o; r.d = d; r.inv = v3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
     int closest = -1;
     if (LAY == LAY_SINGLE) {
-        /* one box per visit, the reference's walk with a stack instead of parent pointers: pushing the right child while
-         * descending left takes the same decisions in the same order.  stack[0] holds the end marker. */
+        /* one box per visit, the reference's walk with escape links instead of parent pointers: the walk is left-first whatever
+         * the ray (bvh.fut:126-142), so the node that follows a failed box test or a finished leaf is stored in the record
+         * (lbvh.cu: k_thread_links) -- same decisions in the same order, no stack, no local memory */
         unsigned long long nbase = reinterpret_cast<unsigned long long>(nodes);        /* per-lane base: node i at nbase + 32 i */
         nbase += 32ull * (unsigned)n_nodes * (unsigned)(((r.inv.x < 0.0f) ? 4 : 0) | ((r.inv.y < 0.0f) ? 2 : 0) | ((r.inv.z < 0.0f) ? 1 : 0));
         asm volatile("" : "+l"(nbase));
-        int stack[TRAV_STACK + 1];
-        stack[0] = TRAV_DONE;
-        int sp = 1;
         int cur = (active && n_nodes > 0) ? 0 : TRAV_DONE;
         do {
 #pragma unroll
@@ -177,16 +176,13 @@ LYS_D int traverse(const float4 *__restrict__ nodes, const float4 *__restrict__ 
                     const float4 *q = reinterpret_cast<const float4 *>(nbase + 32ull * (unsigned)cur);
                     float4 lo, hi; ld_sector(q, lo, hi);
                     float tn;
-                    if (slab_test_oct(r, lo, hi, tmax, tn)) {
-                        stack[sp++] = __float_as_int(hi.w);       /* right child waits */
-                        cur = __float_as_int(lo.w);               /* left child first */
-                    } else cur = stack[--sp];
+                    cur = __float_as_int(slab_test_oct(r, lo, hi, tmax, tn) ? lo.w : hi.w);      /* left child, or the escape link */
                 }
             }
             if ((unsigned)cur > (unsigned)TRAV_DONE) {            /* a leaf pointer */
-                float t;
-                if (leaf_test(r, leaf_tri, ~cur, tmax, t)) { closest = ~cur; tmax = t; }
-                cur = (ANY && closest >= 0) ? TRAV_DONE : stack[--sp];      /* any_hit stops at the first hit (bvh.fut:152) */
+                float t; int next;
+                if (leaf_test(r, leaf_tri, ~cur, tmax, t, &next)) { closest = ~cur; tmax = t; }
+                cur = (ANY && closest >= 0) ? TRAV_DONE : next;             /* any_hit stops at the first hit (bvh.fut:152) */
             }
         } while (__any_sync(0xffffffffu, cur != TRAV_DONE));
     } else {
@@ -494,6 +490,9 @@ LYS_D void shade_draw_or_queue(SH &sh, int par, bool want, int slot, const Verte
 }
 #ifndef LYS_SHADE_MINB
 #define LYS_SHADE_MINB(T) 3      /* 256 threads: 3 CTAs per SM / 80 registers measured best */
+#endif
+#ifndef LYS_SHADE_T
+#define LYS_SHADE_T 256          /* CTA size of k_shade (128 / 256 / 512 measured: profiles/README.md 4.4, 4.5, 8.10) */
 #endif
 template <int SHADE_THREADS>
 __global__ void __launch_bounds__(SHADE_THREADS, LYS_SHADE_MINB(SHADE_THREADS)) k_shade(SceneDev sc, const __grid_constant__ FrameParams fp, PassBuffers b, int bounce, int ordered) {
@@ -861,7 +860,7 @@ __global__ void k_primary_probe(SceneDev sc, const __grid_constant__ FrameParams
     if (!act) return;
     const size_t ix = probe_index(fp, i);
     leaf[ix] = l;
-    if (src) src[ix] = (l < 0) ? -1 : (int)__float_as_uint(sc.leaf_tri[4ll * l + 1].w);
+    if (src) src[ix] = (l < 0) ? -1 : (int)__float_as_uint(sc.leaf_tri[4ll * l + 2].w);
     if (t) t[ix] = (l < 0) ? LYS_INF : th;
 }
 __global__ void k_trace_rays(SceneDev sc, const float *__restrict__ rays, const float *__restrict__ tmax, long long n,
@@ -914,6 +913,7 @@ static GridSizes grid_sizes() {
     if (!g[dev].shade) {
         int sms = 148, bt[3] = {10, 12, 16}, bs = 3;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bs, k_shade<LYS_SHADE_T>, LYS_SHADE_T, 0);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bt[LAY_SINGLE], k_trace<LAY_SINGLE>, 128, 0);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bt[LAY_PAIR_OCT], k_trace<LAY_PAIR_OCT>, 128, 0);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bt[LAY_PAIR], k_trace<LAY_PAIR>, 128, 0);
@@ -949,7 +949,7 @@ cudaError_t run_sample_pass(const SceneDev &sc, const FrameParams &fp, PassBuffe
     uint64_t nl = 0;
     LaunchTimer none; LaunchTimer &tm = timer ? *timer : none;
     const GridSizes gs = grid_sizes();
-    const int g_trace = min(gs.trace[trace_layout(gs, sc)], cdiv(2ll * n, 128)), g_shade = min(gs.shade, cdiv(n, 256));
+    const int g_trace = min(gs.trace[trace_layout(gs, sc)], cdiv(2ll * n, 128)), g_shade = min(gs.shade, cdiv(n, LYS_SHADE_T));
     /* queue-length estimates: a snapshot of what an earlier pass left (the copy below may be updating it: harmless, the
      * numbers only size grids); valid if it is about the same sample grid */
     int est[LYS_MAX_PATH_LEN + 2];
@@ -987,7 +987,7 @@ cudaError_t run_sample_pass(const SceneDev &sc, const FrameParams &fp, PassBuffe
     for (int bnc = 0; bnc < b_tail; bnc++) {
         tm.cur_bounce = bnc;
         tm.begin(2, stream);
-        k_shade<256><<<sized(have_est ? est[bnc] : 0, 256, g_shade), 256, 0, stream>>>(sc, fp, bufs, bnc, (gs.order && bnc > 0) ? 1 : 0);   /* follow b.order (written by k_trace) */
+        k_shade<LYS_SHADE_T><<<sized(have_est ? est[bnc] : 0, LYS_SHADE_T, g_shade), LYS_SHADE_T, 0, stream>>>(sc, fp, bufs, bnc, (gs.order && bnc > 0) ? 1 : 0);   /* follow b.order (written by k_trace) */
         tm.end(stream); nl++;
         tm.begin(1, stream);
         launch_trace(gs, sized(have_est ? (long long)est[bnc] + est[bnc + 1] : 0, 128, g_trace), sc, fp, bufs, bnc, stream);

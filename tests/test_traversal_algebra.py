@@ -6,7 +6,10 @@
     reference's swap;
  3. the deferred right-child test of the pair-node walk: a box tested early against tmax_a and re-checked later against a
     smaller tmax_b with ONE comparison, !(tmax_b <= tn), tn = the entry distance of the early test, gives the boolean the
-    reference's full test gives at the later time.
+    reference's full test gives at the later time;
+ 4. the escape links of the single-box layout (csrc/lbvh.cu: k_thread_links): the reference's parent-pointer walk
+    (bvh.fut:126-142), a left-first walk with a stack and a walk that follows stored escape links visit the same nodes in
+    the same order whatever the box tests and triangle tests answer.
 
 Inputs include the cases that make the difference between a careful and a careless rewrite: zero and negative-zero direction
 components (1/dir = +-inf, 0 * inf = NaN), origins exactly on slab planes, flat boxes, NaN directions, infinite tmax."""
@@ -183,3 +186,92 @@ def test_early_rejections_of_the_triangle_test_do_not_change_it():
     assert np.array_equal(ref, ok), int((ref != ok).sum())
     assert np.array_equal(t[ref].view(np.uint32), t2[ref].view(np.uint32))
     assert 0.1 < ref.mean() < 0.9
+
+
+# ---- 4. escape links ------------------------------------------------------------------------------------------------
+DONE = -(1 << 31)
+
+
+def random_tree(rng, n_leaves):
+    """random binary tree in the child encoding of the build: internal i -> i, leaf j -> ~j; node 0 is the root"""
+    left, right, parent = [0] * (n_leaves - 1), [0] * (n_leaves - 1), [-1] * (n_leaves - 1)
+    leaf_parent = [0] * n_leaves
+    next_node, next_leaf = [1], [0]
+
+    def build(i, k):                                   # node i covers k >= 2 leaves
+        kl = int(rng.integers(1, k))
+        for side, kk in ((0, kl), (1, k - kl)):
+            if kk == 1:
+                c = ~next_leaf[0]; leaf_parent[next_leaf[0]] = i; next_leaf[0] += 1
+            else:
+                c = next_node[0]; next_node[0] += 1; parent[c] = i
+            (left if side == 0 else right)[i] = c
+            if kk > 1:
+                build(c, kk)
+    build(0, n_leaves)
+    return left, right, parent, leaf_parent
+
+
+def thread_links(left, right, parent, leaf_parent):
+    """k_thread_links: the right child of the nearest ancestor-or-self that is a left child, DONE on the right spine"""
+    def link(self, p):
+        while p >= 0 and right[p] == self:
+            self, p = p, parent[p]
+        return DONE if p < 0 else right[p]
+    return [link(i, parent[i]) for i in range(len(left))], [link(~j, leaf_parent[j]) for j in range(len(leaf_parent))]
+
+
+def walk_parent_pointers(left, right, parent, box_pass):
+    """bvh.fut:126-142 as written: (current, prev); the box of `current` is tested when it is entered from above, the right
+    child follows the left one, leaves are triangle-tested without a box test.  Returns the sequence of tests."""
+    seq, current, prev = [], 0, None                    # prev: child pointer we came back from, or None = from above
+    while current != -1:
+        if prev is not None and prev == left[current]:
+            ptr = right[current]
+        elif not (prev is not None and prev == right[current]):
+            seq.append(current)                         # hit_aabb of this node
+            ptr = left[current] if box_pass[current] else None
+        else:
+            ptr = None
+        if ptr is None:
+            current, prev = parent[current], current
+        elif ptr >= 0:
+            current, prev = ptr, None
+        else:
+            seq.append(ptr)                             # hit_triangle of the leaf
+            prev = ptr
+    return seq
+
+
+def walk_stack(left, right, box_pass):
+    seq, stack, cur = [], [DONE], 0
+    while cur != DONE:
+        seq.append(cur)
+        if cur >= 0 and box_pass[cur]:
+            stack.append(right[cur]); cur = left[cur]
+        else:
+            cur = stack.pop()
+    return seq
+
+
+def walk_threaded(left, node_link, leaf_link, box_pass):
+    seq, cur = [], 0
+    while cur != DONE:
+        seq.append(cur)
+        cur = (left[cur] if box_pass[cur] else node_link[cur]) if cur >= 0 else leaf_link[~cur]
+    return seq
+
+
+def test_escape_links_visit_what_the_stack_and_the_parent_pointers_visit():
+    rng = np.random.default_rng(77)
+    for trial in range(300):
+        n = int(rng.integers(2, 200))
+        left, right, parent, leaf_parent = random_tree(rng, n)
+        node_link, leaf_link = thread_links(left, right, parent, leaf_parent)
+        for p in (0.0, 0.3, 0.7, 1.0):
+            box_pass = (rng.random(n - 1) < p) if 0.0 < p < 1.0 else np.full(n - 1, p == 1.0)
+            a = walk_stack(left, right, box_pass)
+            assert a == walk_threaded(left, node_link, leaf_link, box_pass)
+            assert a == walk_parent_pointers(left, right, parent, box_pass)
+        if trial == 0:
+            assert len(walk_threaded(left, node_link, leaf_link, np.ones(n - 1, bool))) == 2 * n - 1     # every node and leaf once
