@@ -554,15 +554,15 @@ __global__ void k_copy_f4(const float4 *__restrict__ in, float4 *__restrict__ ou
 /* traversal layout: node i -> (min.xyz | left), (max.xyz | right); min/max as hit_aabb derives them (shapes.fut:120) */
 /* record i: the boxes of both children of node i with the child pointers (lys_scene.h); record n_nodes: the super-root */
 __global__ void k_pack_nodes(const float4 *__restrict__ A, const int *__restrict__ left, const int *__restrict__ right,
-                             int n_nodes, float4 *__restrict__ nodes, float4 *__restrict__ nodes_oct, int single) {
+                             int n_nodes, float4 *__restrict__ nodes, float4 *__restrict__ nodes_oct, int single, int copies) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i > n_nodes) return;
-    if (single && i < n_nodes) {            /* small scenes: octant copies of the node's own box (LAY_SINGLE) */
+    if (single && i < n_nodes) {            /* the node's own box (LAY_SINGLE: octant copies; LAY_SINGLE_SEL: one copy, min | max) */
         float4 c = A[2ll * i], h = A[2ll * i + 1];
         V3 mn = v3(c.x, c.y, c.z) - v3(h.x, h.y, h.z), mx = v3(c.x, c.y, c.z) + v3(h.x, h.y, h.z);
         const float l = __int_as_float(left[i]), r = __int_as_float(right[i]);
 #pragma unroll
-        for (int o = 0; o < 8; o++) {
+        for (int o = 0; o < copies; o++) {
             float4 *q = nodes_oct + 2ll * ((long long)o * n_nodes + i);
             q[0] = make_float4((o & 4) ? mx.x : mn.x, (o & 2) ? mx.y : mn.y, (o & 1) ? mx.z : mn.z, l);
             q[1] = make_float4((o & 4) ? mn.x : mx.x, (o & 2) ? mn.y : mx.y, (o & 1) ? mn.z : mx.z, r);
@@ -585,7 +585,7 @@ __global__ void k_pack_nodes(const float4 *__restrict__ A, const int *__restrict
     q[1] = make_float4(mx[0].x, mx[0].y, mx[0].z, r);
     q[2] = make_float4(mn[1].x, mn[1].y, mn[1].z, 0.0f);
     q[3] = make_float4(mx[1].x, mx[1].y, mx[1].z, 0.0f);
-    if (nodes_oct && !single) {
+    if (nodes_oct && !single && copies == 8) {
         /* octant o: axis with 1/dir < 0 enters through max and leaves through min (the swap of shapes.fut:124-126) */
 #pragma unroll
         for (int o = 0; o < 8; o++) {
@@ -606,7 +606,7 @@ __global__ void k_pack_nodes(const float4 *__restrict__ A, const int *__restrict
  * thread n + i: internal node i (link replaces the right-child slot of its eight octant records: the right child itself is the
  * escape link of the left child, nobody else needs it). */
 __global__ void k_thread_links(const int *__restrict__ right, const int *__restrict__ parent, const int *__restrict__ leaf_parent,
-                               int n, float4 *__restrict__ leaf_tri, float4 *__restrict__ nodes_oct) {
+                               int n, float4 *__restrict__ leaf_tri, float4 *__restrict__ nodes_oct, int copies) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int n_nodes = n - 1;
     if (x >= n + n_nodes) return;
@@ -616,7 +616,7 @@ __global__ void k_thread_links(const int *__restrict__ right, const int *__restr
     while (p >= 0 && right[p] == self) { self = p; p = parent[p]; }      /* climb while we are a right child */
     const int link = (p < 0) ? (int)0x80000000 : right[p];
     if (leaf) leaf_tri[4ll * x + 1].w = __int_as_float(link);
-    else for (int o = 0; o < 8; o++) nodes_oct[2ll * ((long long)o * n_nodes + (x - n)) + 1].w = __int_as_float(link);
+    else for (int o = 0; o < copies; o++) nodes_oct[2ll * ((long long)o * n_nodes + (x - n)) + 1].w = __int_as_float(link);
 }
 
 
@@ -694,9 +694,10 @@ cudaError_t build_lbvh(SceneDev &sc, BuildScratch &ws, int refit_mode, cudaStrea
     {
         static const int force_pair = []() { const char *e = getenv("LYS_TRACE_PAIR"); return (e && atoi(e)) ? 1 : 0; }();   /* 1: pair records on small scenes too (tests) */
         static const int single_max = []() { const char *e = getenv("LYS_SINGLE_MAX"); return (e && atoi(e) > 0) ? atoi(e) : LYS_SINGLE_MAX_TRIS; }();   /* layout threshold (tests, measurements) */
-        sc.single_nodes = (sc.nodes_oct && n <= single_max && !force_pair) ? 1 : 0;
-        k_pack_nodes<<<cdiv(n_nodes + 1, T), T, 0, stream>>>(sc.node_box, sc.left, sc.right, n_nodes, sc.nodes, sc.nodes_oct, sc.single_nodes); nl++;
-        if (sc.single_nodes) { k_thread_links<<<cdiv(n + n_nodes, T), T, 0, stream>>>(sc.right, sc.parent, ws.leaf_parent, n, sc.leaf_tri, sc.nodes_oct); nl++; }
+        static const int big_single = []() { const char *e = getenv("LYS_BIG_SINGLE"); return (e && atoi(e)) ? 1 : 0; }();       /* 1: single-box records above the octant-copy limit too */
+        sc.single_nodes = (sc.nodes_oct && !force_pair && (sc.oct_copies == 8 ? n <= single_max : big_single)) ? 1 : 0;
+        k_pack_nodes<<<cdiv(n_nodes + 1, T), T, 0, stream>>>(sc.node_box, sc.left, sc.right, n_nodes, sc.nodes, sc.nodes_oct, sc.single_nodes, sc.oct_copies); nl++;
+        if (sc.single_nodes) { k_thread_links<<<cdiv(n + n_nodes, T), T, 0, stream>>>(sc.right, sc.parent, ws.leaf_parent, n, sc.leaf_tri, sc.nodes_oct, sc.oct_copies); nl++; }
     }
     if (launches) *launches += nl;
     return cudaGetLastError();

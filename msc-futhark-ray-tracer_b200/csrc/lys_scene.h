@@ -49,6 +49,7 @@ struct SceneDev {
     float4 *leaf_tri = nullptr, *leaf_box = nullptr, *leaf_frame = nullptr, *nodes = nullptr, *node_box = nullptr;
     float4 *nodes_oct = nullptr;           /* null for scenes above LYS_OCT_MAX_NODES */
     int single_nodes = 0;                  /* nodes_oct holds single-box records (scenes up to LYS_SINGLE_MAX_TRIS triangles) */
+    int oct_copies = 8;                    /* copies in nodes_oct: 8 (one per ray-direction octant) or 1 (scenes above LYS_OCT_MAX_NODES: single-box records only, box test with selects) */
     int *left = nullptr, *right = nullptr, *parent = nullptr, *height = nullptr;
     uint32_t *morton = nullptr, *sorted_idx = nullptr;
     float *bounds = nullptr;

@@ -152,7 +152,7 @@ LYS_D void trav_node_stage(const RayInv &r, unsigned long long nbase, float tmax
  *                 slot a pair record would test for nothing: measured 5-9 % faster than pair records on CornellBox / MirrorBox)
  *   LAY_PAIR_OCT  pair records, octant copies
  *   LAY_PAIR      pair records, one copy, box test with selects (scenes whose octant copies would not stay in L2) */
-enum { LAY_SINGLE = 0, LAY_PAIR_OCT = 1, LAY_PAIR = 2 };
+enum { LAY_SINGLE = 0, LAY_PAIR_OCT = 1, LAY_PAIR = 2, LAY_SINGLE_SEL = 3 };
 #ifndef TRAV_NB
 #define TRAV_NB 2          /* node stages per loop iteration: 2 measured best on every layout and scene size (profiles/README.md 8.2) */
 #endif
@@ -161,12 +161,12 @@ LYS_D int traverse(const float4 *__restrict__ nodes, const float4 *__restrict__ 
                    V3 o, V3 d, float tmax, float &t_hit) {
     RayInv r; r.o = o; r.d = d; r.inv = v3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
     int closest = -1;
-    if (LAY == LAY_SINGLE) {
+    if (LAY == LAY_SINGLE || LAY == LAY_SINGLE_SEL) {
         /* one box per visit, the reference's walk with escape links instead of parent pointers: the walk is left-first whatever
          * the ray (bvh.fut:126-142), so the node that follows a failed box test or a finished leaf is stored in the record
          * (lbvh.cu: k_thread_links) -- same decisions in the same order, no stack, no local memory */
         unsigned long long nbase = reinterpret_cast<unsigned long long>(nodes);        /* per-lane base: node i at nbase + 32 i */
-        nbase += 32ull * (unsigned)n_nodes * (unsigned)(((r.inv.x < 0.0f) ? 4 : 0) | ((r.inv.y < 0.0f) ? 2 : 0) | ((r.inv.z < 0.0f) ? 1 : 0));
+        if (LAY == LAY_SINGLE) nbase += 32ull * (unsigned)n_nodes * (unsigned)(((r.inv.x < 0.0f) ? 4 : 0) | ((r.inv.y < 0.0f) ? 2 : 0) | ((r.inv.z < 0.0f) ? 1 : 0));
         asm volatile("" : "+l"(nbase));
         int cur = (active && n_nodes > 0) ? 0 : TRAV_DONE;
         do {
@@ -176,7 +176,7 @@ LYS_D int traverse(const float4 *__restrict__ nodes, const float4 *__restrict__ 
                     const float4 *q = reinterpret_cast<const float4 *>(nbase + 32ull * (unsigned)cur);
                     float4 lo, hi; ld_sector(q, lo, hi);
                     float tn;
-                    cur = __float_as_int(slab_test_oct(r, lo, hi, tmax, tn) ? lo.w : hi.w);      /* left child, or the escape link */
+                    cur = __float_as_int(((LAY == LAY_SINGLE) ? slab_test_oct(r, lo, hi, tmax, tn) : slab_test(r, lo, hi, tmax, tn)) ? lo.w : hi.w);      /* left child, or the escape link */
                 }
             }
             if ((unsigned)cur > (unsigned)TRAV_DONE) {            /* a leaf pointer */
@@ -587,7 +587,7 @@ LYS_D void connect_finish(const FrameParams &fp, const PassBuffers &b, int bounc
  * with a few registers spilled to L1 -- 12 CTAs (40 registers) with octant copies, 16 (32 registers) on the large scenes
  * (measured: profiles/README.md 8.2). */
 #ifndef LYS_TRACE_MINB
-#define LYS_TRACE_MINB(LAY) ((LAY) == LAY_PAIR ? 16 : (LAY) == LAY_PAIR_OCT ? 12 : 10)
+#define LYS_TRACE_MINB(LAY) (((LAY) == LAY_PAIR || (LAY) == LAY_SINGLE_SEL) ? 16 : (LAY) == LAY_PAIR_OCT ? 12 : 10)
 #endif
 template <int LAY>
 __global__ void __launch_bounds__(128, LYS_TRACE_MINB(LAY)) k_trace(SceneDev sc, const __grid_constant__ FrameParams fp, PassBuffers b, int bounce, int ordered) {
@@ -598,7 +598,7 @@ __global__ void __launch_bounds__(128, LYS_TRACE_MINB(LAY)) k_trace(SceneDev sc,
     const int n_nodes = (int)sc.n_tris - 1;
     const int lane = threadIdx.x & 31;
     const float4 *__restrict__ nodes = (LAY == LAY_PAIR) ? sc.nodes : sc.nodes_oct;
-    constexpr bool CS = LAY == LAY_PAIR;      /* large scenes: path-state records bypass L2 residency (lys_device.cuh: ld_state) */
+    constexpr bool CS = LAY == LAY_PAIR || LAY == LAY_SINGLE_SEL;      /* large scenes: path-state records bypass L2 residency (lys_device.cuh: ld_state) */
     /* warp-uniform loop (traverse<> votes): a warp owns 32 consecutive items; only the warp that straddles n_ext mixes kinds */
     for (int i0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31); i0 < total; i0 += stride) {
         const int i = i0 + lane;
@@ -665,7 +665,7 @@ __global__ void __launch_bounds__(128, LYS_TRACE_MINB(LAY)) k_generate_trace(Sce
         uint32_t rng = fp.frame_rng ^ rng_split_hash((uint32_t)ix);   /* split_rng integrator.fut:109-114 */
         float wl; int ch;
         camera_sample(fp, col, row, rng, o, d, wl, ch);
-        constexpr bool CS = LAY == LAY_PAIR;
+        constexpr bool CS = LAY == LAY_PAIR || LAY == LAY_SINGLE_SEL;
         st_state<CS>(&b.ray_o[0][pid], make_float4(o.x, o.y, o.z, wl));          /* bounce 0: slot == path id */
         st_state<CS>(&b.ray_d[0][pid], make_float4(d.x, d.y, d.z, __uint_as_float(rng)));
         b.dist[0][pid] = 0.0f;
@@ -676,7 +676,7 @@ __global__ void __launch_bounds__(128, LYS_TRACE_MINB(LAY)) k_generate_trace(Sce
     }
     float t;
     const int h = traverse<false, LAY>((LAY == LAY_PAIR) ? sc.nodes : sc.nodes_oct, sc.leaf_tri, (int)sc.n_tris - 1, act, o, d, FLT_MAX, t);
-    if (act) st_state<LAY == LAY_PAIR>(&b.hit[pid], h);
+    if (act) st_state<LAY == LAY_PAIR || LAY == LAY_SINGLE_SEL>(&b.hit[pid], h);
 }
 
 /* ------------------------------------------------------------------ tail: all remaining bounces in one launch
@@ -905,19 +905,20 @@ static inline int cdiv(long long a, int b) { return (int)((a + b - 1) / b); }
  * force what is otherwise chosen by scene size or by the previous pass (tests/test_gpu_parity.py::test_kernel_variants_bit_exact
  * runs each setting against the oracle): LYS_TRACE_PAIR (lbvh.cu), LYS_TRACE_OCT, LYS_TAIL_MAX, LYS_ADAPTIVE_GRIDS, LYS_SHADE_ORDER,
  * LYS_FUSE_GENERATE; LYS_PROFILE_TAIL keeps the fused tail under per-class timing. */
-struct GridSizes { int trace[3] = {0, 0, 0}, shade = 0, oct = 1, adaptive = 1, sms = 148, tail_max = 8192, tail_items = 128, profile_tail = 0, order = 1, fuse_gen = 1; };
+struct GridSizes { int trace[4] = {0, 0, 0, 0}, shade = 0, oct = 1, adaptive = 1, sms = 148, tail_max = 8192, tail_items = 128, profile_tail = 0, order = 1, fuse_gen = 1; };
 static GridSizes grid_sizes() {
     static GridSizes g[64];
     int dev = 0; cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64) dev = 0;
     if (!g[dev].shade) {
-        int sms = 148, bt[3] = {10, 12, 16}, bs = 3;
+        int sms = 148, bt[4] = {10, 12, 16, 16}, bs = 3;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bs, k_shade<LYS_SHADE_T>, LYS_SHADE_T, 0);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bt[LAY_SINGLE], k_trace<LAY_SINGLE>, 128, 0);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bt[LAY_PAIR_OCT], k_trace<LAY_PAIR_OCT>, 128, 0);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bt[LAY_PAIR], k_trace<LAY_PAIR>, 128, 0);
-        for (int k = 0; k < 3; k++) g[dev].trace[k] = sms * (bt[k] > 0 ? bt[k] : 1);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bt[LAY_SINGLE_SEL], k_trace<LAY_SINGLE_SEL>, 128, 0);
+        for (int k = 0; k < 4; k++) g[dev].trace[k] = sms * (bt[k] > 0 ? bt[k] : 1);
         g[dev].shade = sms * (bs > 0 ? bs : 1);
         g[dev].sms = sms;
         const char *ord = getenv("LYS_SHADE_ORDER"); if (ord) g[dev].order = atoi(ord) ? 1 : 0;      /* 0: k_shade walks the slots in queue order */
@@ -930,12 +931,12 @@ static GridSizes grid_sizes() {
     return g[dev];
 }
 static int trace_layout(const GridSizes &gs, const SceneDev &sc) {
-    if (sc.single_nodes) return LAY_SINGLE;
-    return (sc.nodes_oct && gs.oct) ? LAY_PAIR_OCT : LAY_PAIR;
+    if (sc.single_nodes) return sc.oct_copies == 8 ? LAY_SINGLE : LAY_SINGLE_SEL;
+    return (sc.nodes_oct && sc.oct_copies == 8 && gs.oct) ? LAY_PAIR_OCT : LAY_PAIR;
 }
 /* the three traversal variants a scene can select */
 #define LYS_TRAV_DISPATCH(lay, CALL) do { \
-        if ((lay) == LAY_SINGLE) { CALL(LAY_SINGLE); } else if ((lay) == LAY_PAIR_OCT) { CALL(LAY_PAIR_OCT); } else { CALL(LAY_PAIR); } } while (0)
+        if ((lay) == LAY_SINGLE) { CALL(LAY_SINGLE); } else if ((lay) == LAY_PAIR_OCT) { CALL(LAY_PAIR_OCT); } else if ((lay) == LAY_SINGLE_SEL) { CALL(LAY_SINGLE_SEL); } else { CALL(LAY_PAIR); } } while (0)
 static void launch_trace(const GridSizes &gs, int grid, const SceneDev &sc, const FrameParams &fp, PassBuffers &bufs, int bounce, cudaStream_t stream) {
     const int ordered = (gs.order && bounce >= 0) ? 1 : 0;      /* write the hits-first order of bounce + 1, walk the one of bounce */
 #define LYS_CALL(LAY) k_trace<LAY><<<grid, 128, 0, stream>>>(sc, fp, bufs, bounce, ordered)
@@ -1000,6 +1001,7 @@ cudaError_t run_sample_pass(const SceneDev &sc, const FrameParams &fp, PassBuffe
         const int lay = trace_layout(gs, sc);
         if (lay == LAY_SINGLE) k_tail<LAY_SINGLE><<<g, 128, 0, stream>>>(sc, fp, bufs, b_tail);
         else if (lay == LAY_PAIR_OCT) k_tail<LAY_PAIR_OCT><<<g, 128, 0, stream>>>(sc, fp, bufs, b_tail);
+        else if (lay == LAY_SINGLE_SEL) k_tail<LAY_SINGLE_SEL><<<g, 128, 0, stream>>>(sc, fp, bufs, b_tail);
         else k_tail<LAY_PAIR><<<g, 128, 0, stream>>>(sc, fp, bufs, b_tail);
         tm.end(stream); nl++;
     }

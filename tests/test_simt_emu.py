@@ -47,6 +47,7 @@ def test_emulated_library_equals_the_oracle(emu_lib):
 @pytest.mark.parametrize('env', [
     {'LYS_TRACE_PAIR': '1', 'LYS_TRACE_OCT': '0'},       # what scenes above 64K nodes run: pair records, select-based box test
     {'LYS_TRACE_PAIR': '1'},                             # 1K .. 64K nodes: pair records, octant copies
+    {'LYS_OCT_ONE_COPY': '1', 'LYS_BIG_SINGLE': '1'},    # single-box records with escape links, one copy (LAY_SINGLE_SEL)
     {'LYS_TAIL_MAX': '100000000'},                     # fused tail kernel from bounce 1 on
     {'LYS_TAIL_MAX': '0', 'LYS_SHADE_ORDER': '0', 'LYS_FUSE_GENERATE': '0', 'LYS_EMU_SMS': '32'},
     {'LYS_EMU_SCHEDULE': '1'},                         # CTAs, warps and lanes run in reverse order: results must not depend on the schedule

@@ -75,6 +75,10 @@ def main():
     if want('5'):
         st, sm = pkg.scenes.synthetic_cornell(c[0], c[1], 151)
         out.append(run(ctx, '5 synthetic 1003244 tris 4K (16 of 1024 passes)', st, sm, c[2], 2160, 3840, 16, reps=2))
+    for lab in only:                                      # "k38": every Cornell quad as a 38 x 38 grid (44 k^2 triangles) at 1080p: layout crossover measurements
+        if lab[0] == 'k' and lab[1:].isdigit():
+            st, sm = pkg.scenes.synthetic_cornell(c[0], c[1], int(lab[1:]))
+            out.append(run(ctx, '%s synthetic %d tris 1080p' % (lab, len(st)), st, sm, c[2], 1080, 1920, 16))
     os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
     if not only:
         json.dump(out, open(os.path.join(ROOT, 'gpurun_out', 'configs.json'), 'w'), indent=1)
