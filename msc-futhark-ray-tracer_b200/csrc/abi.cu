@@ -600,14 +600,14 @@ int futhark_entry_init(struct futhark_context *ctx, struct futhark_opaque_state 
     const size_t light_chunks = (c + 1023) / 1024;
     unsigned char *mat_flag = nullptr; int *light_chunk = nullptr, *light_info = nullptr;
     if (!H.take(ctx, sc.tris, 9 * c) || !H.take(ctx, sc.tri_mats, c) || !H.take(ctx, sc.mats, (size_t)m * 28) ||
-        !H.take(ctx, sc.leaf_tri, 4 * c) || !H.take(ctx, sc.leaf_box, 2 * c) || !H.take(ctx, sc.leaf_frame, 3 * c) || !H.take(ctx, sc.nodes, 4 * c) ||
+        !H.take(ctx, sc.leaf_tri, 4 * c) || !H.take(ctx, sc.leaf_box, 2 * c) || !H.take(ctx, sc.leaf_frame, 3 * c) ||
         !H.take(ctx, sc.node_box, 2 * c) || !H.take(ctx, sc.left, c) || !H.take(ctx, sc.right, c) || !H.take(ctx, sc.parent, c) ||
         !H.take(ctx, sc.height, c) || !H.take(ctx, sc.morton, c) || !H.take(ctx, sc.sorted_idx, c) || !H.take(ctx, sc.bounds, 8) ||
         !H.take(ctx, sc.lights, (size_t)light_cap) || !H.take(ctx, sc.light_src, (size_t)light_cap) ||
         !H.take(ctx, mat_flag, (size_t)m) || !H.take(ctx, light_chunk, light_chunks) || !H.take(ctx, light_info, 4)) return 1;
     static const int one_copy = []() { const char *e = getenv("LYS_OCT_ONE_COPY"); return (e && atoi(e)) ? 1 : 0; }();   /* tests: the large-scene record arrays on a small scene */
     sc.oct_copies = (n - 1 <= LYS_OCT_MAX_NODES && !one_copy) ? 8 : 1;
-    if (!H.take(ctx, sc.nodes_oct, sc.oct_copies == 8 ? 32 * c : 2 * c)) return 1;
+    if (!H.take(ctx, sc.nodes, (size_t)sc.oct_copies * 2 * c)) return 1;
     CU(ctx, cudaMemcpyAsync(sc.tris, tri_geoms->mem->p, sizeof(float) * 9 * c, cudaMemcpyDeviceToDevice, ctx->stream));
     CU(ctx, cudaMemcpyAsync(sc.tri_mats, tri_mats->mem->p, sizeof(uint32_t) * c, cudaMemcpyDeviceToDevice, ctx->stream));
     CU(ctx, cudaMemcpyAsync(sc.mats, mat_data->mem->p, sizeof(float) * (size_t)m * 28, cudaMemcpyDeviceToDevice, ctx->stream));

@@ -14,7 +14,7 @@
  *   k_crown_*        bvh.fut:109,118-120 the reference stops after floor(log2 n)+2 Jacobi sweeps from
  *                                        zero boxes; nodes higher than that keep truncated boxes,
  *                                        recomputed here exactly through level-synchronous worklists
- *   k_pack_nodes                         traversal layout: 4 x float4 per node (both children's boxes + child pointers)
+ *   k_pack_records                       traversal layout: 2 x float4 per node (its box, left child, escape link), per octant
  */
 #include "lys_scene.h"
 #include "lys_device.cuh"
@@ -551,72 +551,34 @@ __global__ void k_copy_f4(const float4 *__restrict__ in, float4 *__restrict__ ou
     if (i < n) out[i] = in[i];
 }
 
-/* traversal layout: node i -> (min.xyz | left), (max.xyz | right); min/max as hit_aabb derives them (shapes.fut:120) */
-/* record i: the boxes of both children of node i with the child pointers (lys_scene.h); record n_nodes: the super-root */
-__global__ void k_pack_nodes(const float4 *__restrict__ A, const int *__restrict__ left, const int *__restrict__ right,
-                             int n_nodes, float4 *__restrict__ nodes, float4 *__restrict__ nodes_oct, int single, int copies) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i > n_nodes) return;
-    if (single && i < n_nodes) {            /* the node's own box (LAY_SINGLE: octant copies; LAY_SINGLE_SEL: one copy, min | max) */
-        float4 c = A[2ll * i], h = A[2ll * i + 1];
-        V3 mn = v3(c.x, c.y, c.z) - v3(h.x, h.y, h.z), mx = v3(c.x, c.y, c.z) + v3(h.x, h.y, h.z);
-        const float l = __int_as_float(left[i]), r = __int_as_float(right[i]);
-#pragma unroll
-        for (int o = 0; o < copies; o++) {
-            float4 *q = nodes_oct + 2ll * ((long long)o * n_nodes + i);
-            q[0] = make_float4((o & 4) ? mx.x : mn.x, (o & 2) ? mx.y : mn.y, (o & 1) ? mx.z : mn.z, l);
-            q[1] = make_float4((o & 4) ? mn.x : mx.x, (o & 2) ? mn.y : mx.y, (o & 1) ? mn.z : mx.z, r);
-        }
-    }
-    const int lc = (i == n_nodes) ? 0 : left[i], rc = (i == n_nodes) ? (int)0x80000000 : right[i];
-    V3 mn[2], mx[2];
-#pragma unroll
-    for (int k = 0; k < 2; k++) {
-        const int c = k ? rc : lc;
-        mn[k] = mx[k] = v3(0.0f, 0.0f, 0.0f);
-        if (c >= 0) {
-            float4 cc = A[2ll * c], h = A[2ll * c + 1];
-            mn[k] = v3(cc.x, cc.y, cc.z) - v3(h.x, h.y, h.z); mx[k] = v3(cc.x, cc.y, cc.z) + v3(h.x, h.y, h.z);
-        }
-    }
-    const float l = __int_as_float(lc), r = __int_as_float(rc);
-    float4 *q = nodes + 4ll * i;
-    q[0] = make_float4(mn[0].x, mn[0].y, mn[0].z, l);
-    q[1] = make_float4(mx[0].x, mx[0].y, mx[0].z, r);
-    q[2] = make_float4(mn[1].x, mn[1].y, mn[1].z, 0.0f);
-    q[3] = make_float4(mx[1].x, mx[1].y, mx[1].z, 0.0f);
-    if (nodes_oct && !single && copies == 8) {
-        /* octant o: axis with 1/dir < 0 enters through max and leaves through min (the swap of shapes.fut:124-126) */
-#pragma unroll
-        for (int o = 0; o < 8; o++) {
-            float4 *qo = nodes_oct + 4ll * ((long long)o * (n_nodes + 1) + i);
-#pragma unroll
-            for (int k = 0; k < 2; k++) {
-                qo[2 * k + 0] = make_float4((o & 4) ? mx[k].x : mn[k].x, (o & 2) ? mx[k].y : mn[k].y, (o & 1) ? mx[k].z : mn[k].z, k ? 0.0f : l);
-                qo[2 * k + 1] = make_float4((o & 4) ? mn[k].x : mx[k].x, (o & 2) ? mn[k].y : mx[k].y, (o & 1) ? mn[k].z : mx[k].z, k ? 0.0f : r);
-            }
-        }
-    }
-}
-
-/* Escape links for the single-box layout (LAY_SINGLE, wavefront.cu).  The reference's walk always goes left first
- * (bvh.fut:126-142), whatever the ray: the node visited after a failed box test or a finished leaf is therefore a property of
- * the TREE -- the right child of the nearest ancestor-or-self that is a left child, or the end marker on the right spine --
- * and can be stored instead of being kept on a per-ray stack (a threaded tree).  Thread x < n: leaf x (link in leaf_tri[4x+1].w);
- * thread n + i: internal node i (link replaces the right-child slot of its eight octant records: the right child itself is the
- * escape link of the left child, nobody else needs it). */
-__global__ void k_thread_links(const int *__restrict__ right, const int *__restrict__ parent, const int *__restrict__ leaf_parent,
-                               int n, float4 *__restrict__ leaf_tri, float4 *__restrict__ nodes_oct, int copies) {
+/* Traversal records (lys_scene.h): node i -> (near.xyz | left child) (far.xyz | escape link), once per ray-direction octant
+ * (copies = 8: near / far picked per axis as hit_aabb's swap would, shapes.fut:124-126) or once as (min | max) (copies = 1);
+ * min / max = center -+ half as hit_aabb derives them per visit (shapes.fut:120).
+ * Escape links: the reference's walk always goes left first (bvh.fut:126-142), whatever the ray, so the node visited after a
+ * failed box test or a finished leaf is a property of the TREE -- the right child of the nearest ancestor-or-self that is a
+ * left child, or the end marker on the right spine -- and is stored instead of being kept on a per-ray stack (a threaded tree;
+ * the right child itself is the escape link of the left child, nobody else needs it).  Thread x < n_nodes: internal node x;
+ * thread n_nodes + j: leaf j (link in leaf_tri[4j+1].w).  The climb is short: half of all nodes are left children. */
+__global__ void k_pack_records(const float4 *__restrict__ A, const int *__restrict__ left, const int *__restrict__ right,
+                               const int *__restrict__ parent, const int *__restrict__ leaf_parent, int n,
+                               float4 *__restrict__ nodes, int copies, float4 *__restrict__ leaf_tri) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int n_nodes = n - 1;
-    if (x >= n + n_nodes) return;
-    const bool leaf = x < n;
-    int self = leaf ? ~x : x - n;                       /* child encoding: internal i -> i, leaf i -> ~i */
-    int p = leaf ? leaf_parent[x] : parent[x - n];
+    if (x >= n_nodes + n) return;
+    const bool leaf = x >= n_nodes;
+    int self = leaf ? ~(x - n_nodes) : x;               /* child encoding: internal i -> i, leaf j -> ~j */
+    int p = leaf ? leaf_parent[x - n_nodes] : parent[x];
     while (p >= 0 && right[p] == self) { self = p; p = parent[p]; }      /* climb while we are a right child */
-    const int link = (p < 0) ? (int)0x80000000 : right[p];
-    if (leaf) leaf_tri[4ll * x + 1].w = __int_as_float(link);
-    else for (int o = 0; o < copies; o++) nodes_oct[2ll * ((long long)o * n_nodes + (x - n)) + 1].w = __int_as_float(link);
+    const float link = __int_as_float((p < 0) ? (int)0x80000000 : right[p]);
+    if (leaf) { leaf_tri[4ll * (x - n_nodes) + 1].w = link; return; }
+    float4 c = A[2ll * x], h = A[2ll * x + 1];
+    V3 mn = v3(c.x, c.y, c.z) - v3(h.x, h.y, h.z), mx = v3(c.x, c.y, c.z) + v3(h.x, h.y, h.z);
+    const float l = __int_as_float(left[x]);
+    for (int o = 0; o < copies; o++) {                  /* copies == 1: o = 0 = no swap */
+        float4 *q = nodes + 2ll * ((long long)o * n_nodes + x);
+        q[0] = make_float4((o & 4) ? mx.x : mn.x, (o & 2) ? mx.y : mn.y, (o & 1) ? mx.z : mn.z, l);
+        q[1] = make_float4((o & 4) ? mn.x : mx.x, (o & 2) ? mn.y : mx.y, (o & 1) ? mn.z : mx.z, link);
+    }
 }
 
 
@@ -691,14 +653,7 @@ cudaError_t build_lbvh(SceneDev &sc, BuildScratch &ws, int refit_mode, cudaStrea
         for (int lv = depth - 1; lv > n_top; lv--) { k_crown_eval<<<G, T, 0, stream>>>(sc.left, sc.right, sc.leaf_box, ws.F, (const CrownPair *)ws.crown_pairs, ws.crown_box, ws.crown_cnt, lv, depth, ws.crown_cap, sc.node_box); nl++; }
         k_crown_top_eval<<<1, 1024, 0, stream>>>(sc.left, sc.right, sc.leaf_box, ws.F, (const CrownPair *)ws.crown_pairs, ws.crown_box, ws.crown_cnt, min(n_top, depth - 1), depth, ws.crown_cap, sc.node_box); nl++;
     }
-    {
-        static const int force_pair = []() { const char *e = getenv("LYS_TRACE_PAIR"); return (e && atoi(e)) ? 1 : 0; }();   /* 1: pair records on small scenes too (tests) */
-        static const int single_max = []() { const char *e = getenv("LYS_SINGLE_MAX"); return (e && atoi(e) > 0) ? atoi(e) : LYS_SINGLE_MAX_TRIS; }();   /* layout threshold (tests, measurements) */
-        static const int big_single = []() { const char *e = getenv("LYS_BIG_SINGLE"); return (e && atoi(e)) ? 1 : 0; }();       /* 1: single-box records above the octant-copy limit too */
-        sc.single_nodes = (sc.nodes_oct && !force_pair && (sc.oct_copies == 8 ? n <= single_max : big_single)) ? 1 : 0;
-        k_pack_nodes<<<cdiv(n_nodes + 1, T), T, 0, stream>>>(sc.node_box, sc.left, sc.right, n_nodes, sc.nodes, sc.nodes_oct, sc.single_nodes, sc.oct_copies); nl++;
-        if (sc.single_nodes) { k_thread_links<<<cdiv(n + n_nodes, T), T, 0, stream>>>(sc.right, sc.parent, ws.leaf_parent, n, sc.leaf_tri, sc.nodes_oct, sc.oct_copies); nl++; }
-    }
+    k_pack_records<<<cdiv(n_nodes + n, T), T, 0, stream>>>(sc.node_box, sc.left, sc.right, sc.parent, ws.leaf_parent, n, sc.nodes, sc.oct_copies, sc.leaf_tri); nl++;
     if (launches) *launches += nl;
     return cudaGetLastError();
 }

@@ -5,21 +5,18 @@
  *   tri_mats  [n]     u32
  *   mats      [m][28] f32   material rows (src/scene.fut:37-53)
  *   leaf_tri  [n][4]  float4  sorted leaves, 64 B: (a.xyz | mat_ix), (e1 x e2 | escape link) = the plane test's sector,
- *                             then (e1.xyz | source index), (e2.xyz | 0) for the barycentric test.  Escape link (single-box
- *                             scenes only): the node the left-first walk visits after this leaf (lbvh.cu: k_thread_links)
+ *                             then (e1.xyz | source index), (e2.xyz | 0) for the barycentric test.  Escape link: the node the
+ *                             left-first walk visits after this leaf (lbvh.cu: k_pack_records)
  *   leaf_box  [n][2]  float4  sorted leaf boxes (center | half_dims)
  *   leaf_frame [n][3] float4  shading frame of a hit on the leaf: unit normal, then b and t of mk_orthonormal_basis (material.fut:374-379)
- *   nodes     [n][4]  float4  traversal records, 64 B = two sectors: record i < n-1 holds the boxes of BOTH children of node i,
- *                             (Lmin.xyz | left) (Lmax.xyz | right) (Rmin.xyz | 0) (Rmax.xyz | 0); the box slot of a leaf child
- *                             is zero (leaves are never box-tested, bvh.fut:133).  Record n-1 is the super-root: left = node 0
- *                             with the root's own box, right = the end marker 0x80000000.  Corners are derived from
- *                             (center, half) with the subtraction / addition hit_aabb does per visit (shapes.fut:120)
- *   nodes_oct [8][n][4] float4 (scenes up to LYS_OCT_MAX_NODES nodes) the same records once per ray-direction octant:
- *                             (near | left) (far | right) (near | 0) (far | 0) with near/far already picked per axis as hit_aabb's
- *                             swap would (octant bit 2/1/0 = 1/dir.x, .y, .z < 0), so the box test needs no select.
- *                             Scenes up to LYS_SINGLE_MAX_TRIS triangles (single_nodes = 1): [8][n-1][2] float4, one box per
- *                             record, (near.xyz | left) (far.xyz | escape link) of node i itself: a threaded tree, the walk
- *                             needs no stack (where it goes when the box fails is a property of the tree, not of the ray)
+ *   nodes     [copies][n-1][2] float4  traversal records, 32 B = one sector: (near.xyz | left child) (far.xyz | escape link) of
+ *                             node i.  copies = 8 (scenes up to LYS_OCT_MAX_NODES nodes): one copy per ray-direction octant (bit
+ *                             2/1/0 = 1/dir.x, .y, .z < 0) with near / far already picked per axis as hit_aabb's swap would
+ *                             (shapes.fut:124-126), so the box test needs no select; copies = 1: (min | max), box test with
+ *                             selects.  Corners are derived from (center, half) with the subtraction / addition hit_aabb does
+ *                             per visit (shapes.fut:120).  Escape link: the node the left-first walk (bvh.fut:126-142) visits
+ *                             after this node's box fails -- a property of the tree, so the walk needs no stack
+ *                             (lbvh.cu: k_pack_records, wavefront.cu: traverse)
  *   node_box  [n-1][2] float4 node boxes as the reference stores them (center | half_dims)
  *   left/right/parent/height [n-1] i32; child encoding: internal i -> i, leaf i -> ~i
  *   morton, sorted_idx [n] u32; bounds [6] f32 (center, half_dims)
@@ -31,8 +28,7 @@
 
 namespace lys {
 
-#define LYS_SINGLE_MAX_TRIS 16384        /* up to here the octant copies hold one box per record (wavefront.cu: LAY_SINGLE, stackless; measured: profiles/README.md 8.10) */
-#define LYS_OCT_MAX_NODES (1 << 16)      /* 8 x 4 MB of octant records at most: stays L2 resident */
+#define LYS_OCT_MAX_NODES (1 << 16)      /* 8 x 2 MB of octant records at most: stays L2 resident */
 
 struct LightRec {            /* 32 floats = 128 B, float4-aligned */
     float a[3]; float area;                /* vertex a, triangle area (direct.fut:17-20) */
@@ -47,9 +43,7 @@ struct SceneDev {
     int64_t n_tris = 0, n_mats = 0, n_lights = 0;
     float *tris = nullptr; uint32_t *tri_mats = nullptr; float *mats = nullptr;
     float4 *leaf_tri = nullptr, *leaf_box = nullptr, *leaf_frame = nullptr, *nodes = nullptr, *node_box = nullptr;
-    float4 *nodes_oct = nullptr;           /* null for scenes above LYS_OCT_MAX_NODES */
-    int single_nodes = 0;                  /* nodes_oct holds single-box records (scenes up to LYS_SINGLE_MAX_TRIS triangles) */
-    int oct_copies = 8;                    /* copies in nodes_oct: 8 (one per ray-direction octant) or 1 (scenes above LYS_OCT_MAX_NODES: single-box records only, box test with selects) */
+    int oct_copies = 8;                    /* copies in `nodes`: 8 (one per ray-direction octant) or 1 (scenes above LYS_OCT_MAX_NODES: box test with selects) */
     int *left = nullptr, *right = nullptr, *parent = nullptr, *height = nullptr;
     uint32_t *morton = nullptr, *sorted_idx = nullptr;
     float *bounds = nullptr;

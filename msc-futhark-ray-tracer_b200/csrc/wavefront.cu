@@ -20,8 +20,6 @@
 
 namespace lys {
 
-#define TRAV_STACK 64      /* delta() is in [0, 63] and strictly grows downwards -> height <= 64 */
-
 /* ------------------------------------------------------------------ BVH traversal
  * The reference walks the tree without a stack: parent pointers, always left child first, a node's box
  * tested once on entry against the CURRENT tmax, leaves never box-tested (bvh.fut:126-142).  A depth-first
@@ -76,132 +74,70 @@ LYS_D bool slab_test_oct(const RayInv &r, float4 nr, float4 fr, float tmax, floa
 }
 /* hit_triangle (shapes.fut:66-86) against sorted leaf `leaf`: the plane part needs only (a, n = e1 x e2), one 32-byte
  * sector; the edges are fetched only by the lanes whose t lies in (0, tmax). */
-LYS_D bool leaf_test_at(const RayInv &r, const float4 *__restrict__ q, float tmax, float &t, int *escape = nullptr) {
+LYS_D bool leaf_test_at(const RayInv &r, const float4 *__restrict__ q, float tmax, float &t, int &escape) {
     float4 q0, q1; ld_sector(q, q0, q1);
-    if (escape) *escape = __float_as_int(q1.w);          /* single-box scenes: where the walk goes after this leaf */
+    escape = __float_as_int(q1.w);                       /* where the walk goes after this leaf */
     float inv; V3 s;
     if (!tri_plane_test(r.o, r.d, v3(q0.x, q0.y, q0.z), v3(q1.x, q1.y, q1.z), tmax, t, inv, s)) return false;
     float4 q2, q3; ld_sector(q + 2, q2, q3);
     return tri_uv_test(r.d, s, inv, v3(q2.x, q2.y, q2.z), v3(q3.x, q3.y, q3.z));
 }
-LYS_D bool leaf_test(const RayInv &r, const float4 *__restrict__ leaf_tri, int leaf, float tmax, float &t, int *escape = nullptr) {
+LYS_D bool leaf_test(const RayInv &r, const float4 *__restrict__ leaf_tri, int leaf, float tmax, float &t, int &escape) {
     return leaf_test_at(r, leaf_tri + 4ll * leaf, tmax, t, escape);
 }
 /* ---- the walk.  Reference order (bvh.fut:126-142): enter a node = test ITS box against the CURRENT tmax; if it passes go
- * left, and come back for the right child when the left subtree is done; leaves are never box-tested.
- *
- * Pair nodes: record i holds the boxes of BOTH children of node i (lys_scene.h), so one 64-byte visit decides two of the
- * reference's box tests and a failing child costs no visit of its own (no dependent load, no loop iteration):
- *   - the left child is entered right after its parent passes, with the same tmax: its test here IS the reference's test;
- *   - the right child's test belongs after the left subtree, with a tmax that can only have shrunk since.  The test is
- *     !(fminf(T1, tmax) <= tn) with tn (entry distance, NaN-free) and T1 (scaled exit distance, NaN dropped by fminf)
- *     independent of tmax, hence monotone in tmax: a right child that fails now fails then (it is dropped now), and one
- *     that passes now passes then iff !(tmax_then <= tn).  So it is pushed WITH tn and re-checked against the current tmax
- *     when popped (a compare, no memory access).  For any_hit tmax never changes: plain pop.
- * Decisions, their order and every comparison are the reference's; hits, ties (strict t < tmax, shapes.fut:64) and the
- * culling by the non-conservative truncated boxes (bvh.fut:105-120) are identical (parity tests, tests/test_traversal_algebra.py).
- * Record n_nodes is a super-root: left child = node 0 (the root's own box test, bvh.fut:127), right child = the end marker,
- * which like a leaf pointer always "passes" and is pushed: the stack needs no other sentinel.
+ * left, and come back for the right child when the left subtree is done; leaves are never box-tested.  The walk is left-first
+ * WHATEVER THE RAY, so the node that follows a failed box test or a finished leaf is a property of the tree: the right child of
+ * the nearest ancestor-or-self that is a left child, or the end marker on the right spine.  The build stores that escape link in
+ * every record (lbvh.cu: k_thread_links), and the walk needs neither the reference's parent pointers nor a stack:
+ *     internal node:  cur = box passes ? left child : escape link          leaf:  triangle test, then cur = escape link
+ * Same tests against the same tmax in the same order, so hits, ties (strict t < tmax, shapes.fut:64) and the culling by the
+ * non-conservative truncated boxes (bvh.fut:105-120) are identical (tests/test_traversal_algebra.py: escape links vs the
+ * parent-pointer walk; parity tests).  No local memory, 23 instructions per box visit.
  *
  * One loop iteration = TRAV_NB node stages, then one triangle stage, then a warp vote.  A lane takes part in a stage if its
  * next visit has that type, so a node whose left child is a leaf is entered and the leaf triangle-tested in the same
  * iteration, and the lanes of a warp meet in few, well filled stages (model: tools/simt_model.py).  The vote keeps the warp
  * converged at the loop head -- without it the compiler threads "still at an internal node" back into the node stage, i.e.
- * builds a while-while loop.  ALL 32 LANES OF A WARP MUST CALL THIS TOGETHER; lanes without a ray pass active = false. */
+ * builds a while-while loop.  ALL 32 LANES OF A WARP MUST CALL THIS TOGETHER; lanes without a ray pass active = false.
+ *
+ * Record layouts (lys_scene.h), picked by scene size in futhark_entry_init:
+ *   LAY_OCT  one copy of the records per ray-direction octant, near / far picked at build time: box test without selects
+ *            (scenes up to LYS_OCT_MAX_NODES nodes: the copies stay cache resident)
+ *   LAY_SEL  one copy, box test with selects (larger scenes)
+ * Pair records (both children's boxes in one 64-byte record, right child pushed with its entry distance and re-checked at pop
+ * time) were the round-2 layout for scenes above 1024 triangles until the escape links made the stack unnecessary: single-box
+ * records now win on every scene size (profiles/README.md 8.10) and the pair code is gone (history: commit 3c87084). */
 #define TRAV_DONE ((int)0x80000000)
-template <bool ANY> struct TravStack;
-template <> struct TravStack<true> {          /* any_hit: node pointers only */
-    int e[TRAV_STACK + 1];
-    LYS_D void push(int &sp, int node, float) { e[sp++] = node; }
-    LYS_D int pop(int &sp, float) { return e[--sp]; }
-};
-template <> struct TravStack<false> {         /* closest_hit: (node, entry distance) */
-    int2 e[TRAV_STACK + 1];
-    LYS_D void push(int &sp, int node, float tn) { e[sp++] = make_int2(node, __float_as_int(tn)); }
-    LYS_D int pop(int &sp, float tmax) {      /* entries the shrunken tmax has cut off are skipped */
-        int2 x;
-        do { x = e[--sp]; } while (tmax <= __int_as_float(x.y));
-        return x.x;
-    }
-};
-template <bool OCT>
-LYS_D unsigned long long trav_base(const float4 *nodes, int n_nodes, const RayInv &r) {
-    unsigned long long nbase = reinterpret_cast<unsigned long long>(nodes);            /* per-lane base: record i at nbase + 64 i */
-    if (OCT) nbase += 64ull * (unsigned)(n_nodes + 1) * (unsigned)(((r.inv.x < 0.0f) ? 4 : 0) | ((r.inv.y < 0.0f) ? 2 : 0) | ((r.inv.z < 0.0f) ? 1 : 0));   /* `nodes` = nodes_oct */
-    asm volatile("" : "+l"(nbase));      /* keep the sum in a register pair: one IMAD.WIDE per node address */
-    return nbase;
-}
-/* one node stage: cur >= 0 on entry */
-template <bool ANY, bool OCT>
-LYS_D void trav_node_stage(const RayInv &r, unsigned long long nbase, float tmax, int &cur, int &sp, TravStack<ANY> &st) {
-    const float4 *q = reinterpret_cast<const float4 *>(nbase + 64ull * (unsigned)cur);
-    float4 l0, l1, r0, r1;
-    ld_sector(q, l0, l1); ld_sector(q + 2, r0, r1);
-    const int lc = __float_as_int(l0.w), rc = __float_as_int(l1.w);
-    float tl, tr;
-    bool pl = OCT ? slab_test_oct(r, l0, l1, tmax, tl) : slab_test(r, l0, l1, tmax, tl);
-    bool pr = OCT ? slab_test_oct(r, r0, r1, tmax, tr) : slab_test(r, r0, r1, tmax, tr);
-    if (lc < 0) pl = true;                                   /* leaves (and the end marker) are not box-tested */
-    if (rc < 0) { pr = true; tr = -LYS_INF; }
-    if (pl) { cur = lc; if (pr) st.push(sp, rc, tr); }       /* left child first, right child waits */
-    else if (pr) cur = rc;
-    else cur = st.pop(sp, tmax);
-}
-/* Record layouts (lys_scene.h), picked per scene by the build:
- *   LAY_SINGLE    one box per record, octant copies: small trees (issue bound, half the child slots are leaves whose box
- *                 slot a pair record would test for nothing: measured 5-9 % faster than pair records on CornellBox / MirrorBox)
- *   LAY_PAIR_OCT  pair records, octant copies
- *   LAY_PAIR      pair records, one copy, box test with selects (scenes whose octant copies would not stay in L2) */
-enum { LAY_SINGLE = 0, LAY_PAIR_OCT = 1, LAY_PAIR = 2, LAY_SINGLE_SEL = 3 };
+enum { LAY_OCT = 0, LAY_SEL = 1 };
 #ifndef TRAV_NB
-#define TRAV_NB 2          /* node stages per loop iteration: 2 measured best on every layout and scene size (profiles/README.md 8.2) */
+#define TRAV_NB 2          /* node stages per loop iteration: 2 measured best on every layout and scene size (profiles/README.md 8.2, 8.10) */
 #endif
 template <bool ANY, int LAY>
 LYS_D int traverse(const float4 *__restrict__ nodes, const float4 *__restrict__ leaf_tri, int n_nodes, bool active,
                    V3 o, V3 d, float tmax, float &t_hit) {
     RayInv r; r.o = o; r.d = d; r.inv = v3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
     int closest = -1;
-    if (LAY == LAY_SINGLE || LAY == LAY_SINGLE_SEL) {
-        /* one box per visit, the reference's walk with escape links instead of parent pointers: the walk is left-first whatever
-         * the ray (bvh.fut:126-142), so the node that follows a failed box test or a finished leaf is stored in the record
-         * (lbvh.cu: k_thread_links) -- same decisions in the same order, no stack, no local memory */
-        unsigned long long nbase = reinterpret_cast<unsigned long long>(nodes);        /* per-lane base: node i at nbase + 32 i */
-        if (LAY == LAY_SINGLE) nbase += 32ull * (unsigned)n_nodes * (unsigned)(((r.inv.x < 0.0f) ? 4 : 0) | ((r.inv.y < 0.0f) ? 2 : 0) | ((r.inv.z < 0.0f) ? 1 : 0));
-        asm volatile("" : "+l"(nbase));
-        int cur = (active && n_nodes > 0) ? 0 : TRAV_DONE;
-        do {
+    unsigned long long nbase = reinterpret_cast<unsigned long long>(nodes);        /* per-lane base: node i at nbase + 32 i */
+    if (LAY == LAY_OCT) nbase += 32ull * (unsigned)n_nodes * (unsigned)(((r.inv.x < 0.0f) ? 4 : 0) | ((r.inv.y < 0.0f) ? 2 : 0) | ((r.inv.z < 0.0f) ? 1 : 0));
+    asm volatile("" : "+l"(nbase));      /* keep the sum in a register pair: one IMAD.WIDE per node address */
+    int cur = (active && n_nodes > 0) ? 0 : TRAV_DONE;       /* internal node to enter (>= 0), leaf pointer (~leaf) or TRAV_DONE */
+    do {
 #pragma unroll
-            for (int k = 0; k < TRAV_NB; k++) {
-                if (cur >= 0) {
-                    const float4 *q = reinterpret_cast<const float4 *>(nbase + 32ull * (unsigned)cur);
-                    float4 lo, hi; ld_sector(q, lo, hi);
-                    float tn;
-                    cur = __float_as_int(((LAY == LAY_SINGLE) ? slab_test_oct(r, lo, hi, tmax, tn) : slab_test(r, lo, hi, tmax, tn)) ? lo.w : hi.w);      /* left child, or the escape link */
-                }
+        for (int k = 0; k < TRAV_NB; k++) {
+            if (cur >= 0) {
+                const float4 *q = reinterpret_cast<const float4 *>(nbase + 32ull * (unsigned)cur);
+                float4 lo, hi; ld_sector(q, lo, hi);
+                float tn;
+                cur = __float_as_int(((LAY == LAY_OCT) ? slab_test_oct(r, lo, hi, tmax, tn) : slab_test(r, lo, hi, tmax, tn)) ? lo.w : hi.w);      /* left child, or the escape link */
             }
-            if ((unsigned)cur > (unsigned)TRAV_DONE) {            /* a leaf pointer */
-                float t; int next;
-                if (leaf_test(r, leaf_tri, ~cur, tmax, t, &next)) { closest = ~cur; tmax = t; }
-                cur = (ANY && closest >= 0) ? TRAV_DONE : next;             /* any_hit stops at the first hit (bvh.fut:152) */
-            }
-        } while (__any_sync(0xffffffffu, cur != TRAV_DONE));
-    } else {
-        constexpr bool OCT = LAY == LAY_PAIR_OCT;
-        const unsigned long long nbase = trav_base<OCT>(nodes, n_nodes, r);
-        TravStack<ANY> st;
-        int sp = 0;
-        int cur = (active && n_nodes > 0) ? n_nodes : TRAV_DONE;   /* internal node to enter (>= 0; n_nodes = the super-root), leaf pointer (~leaf) or TRAV_DONE */
-        do {
-#pragma unroll
-            for (int k = 0; k < TRAV_NB; k++)
-                if (cur >= 0) trav_node_stage<ANY, OCT>(r, nbase, tmax, cur, sp, st);
-            if ((unsigned)cur > (unsigned)TRAV_DONE) {            /* a leaf pointer */
-                float t;
-                if (leaf_test(r, leaf_tri, ~cur, tmax, t)) { closest = ~cur; tmax = t; }
-                cur = (ANY && closest >= 0) ? TRAV_DONE : st.pop(sp, tmax);       /* any_hit stops at the first hit (bvh.fut:152) */
-            }
-        } while (__any_sync(0xffffffffu, cur != TRAV_DONE));
-    }
+        }
+        if ((unsigned)cur > (unsigned)TRAV_DONE) {            /* a leaf pointer */
+            float t; int next;
+            if (leaf_test(r, leaf_tri, ~cur, tmax, t, next)) { closest = ~cur; tmax = t; }
+            cur = (ANY && closest >= 0) ? TRAV_DONE : next;             /* any_hit stops at the first hit (bvh.fut:152) */
+        }
+    } while (__any_sync(0xffffffffu, cur != TRAV_DONE));
     t_hit = tmax;
     return closest;
 }
@@ -582,12 +518,12 @@ LYS_D void connect_finish(const FrameParams &fp, const PassBuffers &b, int bounc
  * were built, parity-tested and measured: -38 % and +3 % on the 1 M-triangle scene, slower on every bundled scene
  * (profiles/README.md 7.2, 8.1); they are no longer part of the build.
  * `ordered` bit 0: append the slots of bounce + 1 to the hits-first order list and walk this bounce's vertices in theirs. */
-/* resident CTAs of 128 threads per SM the traversal kernels are compiled for.  Small scenes are issue bound: 10 CTAs / 48
- * registers, no spills.  Pair layouts are latency bound (dependent L2 / DRAM record loads): more warps in flight win even
- * with a few registers spilled to L1 -- 12 CTAs (40 registers) with octant copies, 16 (32 registers) on the large scenes
- * (measured: profiles/README.md 8.2). */
+/* resident CTAs of 128 threads per SM the traversal kernels are compiled for.  Scenes with octant copies are issue bound: 10
+ * CTAs / 48 registers, no spills (12 CTAs measured the same).  Large scenes are latency bound (dependent L2 / DRAM record
+ * loads): more warps in flight win even with a few registers spilled to L1 -- 1106 / 1147 / 1176 Mpaths/s at 10 / 12 / 16 CTAs
+ * on the 1 M-triangle scene (profiles/README.md 8.10). */
 #ifndef LYS_TRACE_MINB
-#define LYS_TRACE_MINB(LAY) (((LAY) == LAY_PAIR || (LAY) == LAY_SINGLE_SEL) ? 16 : (LAY) == LAY_PAIR_OCT ? 12 : 10)
+#define LYS_TRACE_MINB(LAY) ((LAY) == LAY_SEL ? 16 : 10)
 #endif
 template <int LAY>
 __global__ void __launch_bounds__(128, LYS_TRACE_MINB(LAY)) k_trace(SceneDev sc, const __grid_constant__ FrameParams fp, PassBuffers b, int bounce, int ordered) {
@@ -597,8 +533,8 @@ __global__ void __launch_bounds__(128, LYS_TRACE_MINB(LAY)) k_trace(SceneDev sc,
     const int stride = gridDim.x * blockDim.x;
     const int n_nodes = (int)sc.n_tris - 1;
     const int lane = threadIdx.x & 31;
-    const float4 *__restrict__ nodes = (LAY == LAY_PAIR) ? sc.nodes : sc.nodes_oct;
-    constexpr bool CS = LAY == LAY_PAIR || LAY == LAY_SINGLE_SEL;      /* large scenes: path-state records bypass L2 residency (lys_device.cuh: ld_state) */
+    const float4 *__restrict__ nodes = sc.nodes;
+    constexpr bool CS = LAY == LAY_SEL;      /* large scenes: path-state records bypass L2 residency (lys_device.cuh: ld_state) */
     /* warp-uniform loop (traverse<> votes): a warp owns 32 consecutive items; only the warp that straddles n_ext mixes kinds */
     for (int i0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31); i0 < total; i0 += stride) {
         const int i = i0 + lane;
@@ -665,7 +601,7 @@ __global__ void __launch_bounds__(128, LYS_TRACE_MINB(LAY)) k_generate_trace(Sce
         uint32_t rng = fp.frame_rng ^ rng_split_hash((uint32_t)ix);   /* split_rng integrator.fut:109-114 */
         float wl; int ch;
         camera_sample(fp, col, row, rng, o, d, wl, ch);
-        constexpr bool CS = LAY == LAY_PAIR || LAY == LAY_SINGLE_SEL;
+        constexpr bool CS = LAY == LAY_SEL;
         st_state<CS>(&b.ray_o[0][pid], make_float4(o.x, o.y, o.z, wl));          /* bounce 0: slot == path id */
         st_state<CS>(&b.ray_d[0][pid], make_float4(d.x, d.y, d.z, __uint_as_float(rng)));
         b.dist[0][pid] = 0.0f;
@@ -675,8 +611,8 @@ __global__ void __launch_bounds__(128, LYS_TRACE_MINB(LAY)) k_generate_trace(Sce
         if (b.probe_rad) for (int k = 0; k < LYS_MAX_PATH_LEN; k++) { b.probe_rad[(size_t)ix * 16 + k] = 0.0f; b.probe_dist[(size_t)ix * 16 + k] = LYS_INF; }
     }
     float t;
-    const int h = traverse<false, LAY>((LAY == LAY_PAIR) ? sc.nodes : sc.nodes_oct, sc.leaf_tri, (int)sc.n_tris - 1, act, o, d, FLT_MAX, t);
-    if (act) st_state<LAY == LAY_PAIR || LAY == LAY_SINGLE_SEL>(&b.hit[pid], h);
+    const int h = traverse<false, LAY>(sc.nodes, sc.leaf_tri, (int)sc.n_tris - 1, act, o, d, FLT_MAX, t);
+    if (act) st_state<LAY == LAY_SEL>(&b.hit[pid], h);
 }
 
 /* ------------------------------------------------------------------ tail: all remaining bounces in one launch
@@ -697,7 +633,7 @@ __global__ void __launch_bounds__(128) k_tail(SceneDev sc, const __grid_constant
     const int nl = fp.n_scene_lights + ((fp.tx_kind == 0) ? 0 : 8);
     const int n_nodes = (int)sc.n_tris - 1;
     const int lane = threadIdx.x & 31;
-    const float4 *__restrict__ nodes = (LAY == LAY_PAIR) ? sc.nodes : sc.nodes_oct;
+    const float4 *__restrict__ nodes = sc.nodes;
     for (int bounce = bounce0; bounce < fp.path_len && n_cur > 0; bounce++) {
         if (threadIdx.x == 0) s_next = 0;
         __syncthreads();
@@ -850,19 +786,21 @@ __global__ void __launch_bounds__(256) k_render(const float *__restrict__ img, i
 }
 
 /* ------------------------------------------------------------------ probes / tools */
+template <int LAY>
 __global__ void k_primary_probe(SceneDev sc, const __grid_constant__ FrameParams fp, PassBuffers b, int n, int *leaf, int *src, float *t) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     const bool act = i < n;                                          /* no early return: traverse<> votes per warp */
     float4 ro = make_float4(0.0f, 0.0f, 0.0f, 0.0f), rd = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
     if (act) { ro = b.ray_o[0][i]; rd = b.ray_d[0][i]; }
     float th;
-    int l = traverse<false, LAY_PAIR>(sc.nodes, sc.leaf_tri, (int)sc.n_tris - 1, act, v3(ro.x, ro.y, ro.z), v3(rd.x, rd.y, rd.z), FLT_MAX, th);
+    int l = traverse<false, LAY>(sc.nodes, sc.leaf_tri, (int)sc.n_tris - 1, act, v3(ro.x, ro.y, ro.z), v3(rd.x, rd.y, rd.z), FLT_MAX, th);
     if (!act) return;
     const size_t ix = probe_index(fp, i);
     leaf[ix] = l;
     if (src) src[ix] = (l < 0) ? -1 : (int)__float_as_uint(sc.leaf_tri[4ll * l + 2].w);
     if (t) t[ix] = (l < 0) ? LYS_INF : th;
 }
+template <int LAY>
 __global__ void k_trace_rays(SceneDev sc, const float *__restrict__ rays, const float *__restrict__ tmax, long long n,
                              int *out_leaf, float *out_t, int any) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -870,8 +808,8 @@ __global__ void k_trace_rays(SceneDev sc, const float *__restrict__ rays, const 
     V3 o = v3(0.0f, 0.0f, 0.0f), d = v3(1.0f, 1.0f, 1.0f);
     if (act) { const float *r = rays + 6 * i; o = v3(r[0], r[1], r[2]); d = v3(r[3], r[4], r[5]); }
     float th; int l;
-    if (any) l = traverse<true, LAY_PAIR>(sc.nodes, sc.leaf_tri, (int)sc.n_tris - 1, act, o, d, act ? tmax[i] : 0.0f, th);
-    else l = traverse<false, LAY_PAIR>(sc.nodes, sc.leaf_tri, (int)sc.n_tris - 1, act, o, d, FLT_MAX, th);
+    if (any) l = traverse<true, LAY>(sc.nodes, sc.leaf_tri, (int)sc.n_tris - 1, act, o, d, act ? tmax[i] : 0.0f, th);
+    else l = traverse<false, LAY>(sc.nodes, sc.leaf_tri, (int)sc.n_tris - 1, act, o, d, FLT_MAX, th);
     if (!act) return;
     out_leaf[i] = any ? (l >= 0 ? 1 : 0) : l;
     if (out_t) out_t[i] = (l < 0) ? LYS_INF : th;
@@ -903,22 +841,20 @@ static inline int cdiv(long long a, int b) { return (int)((a + b - 1) / b); }
 
 /* persistent grids: SM count x resident CTAs per SM of each kernel (queried once per device).  The environment knobs
  * force what is otherwise chosen by scene size or by the previous pass (tests/test_gpu_parity.py::test_kernel_variants_bit_exact
- * runs each setting against the oracle): LYS_TRACE_PAIR (lbvh.cu), LYS_TRACE_OCT, LYS_TAIL_MAX, LYS_ADAPTIVE_GRIDS, LYS_SHADE_ORDER,
+ * runs each setting against the oracle): LYS_OCT_ONE_COPY (abi.cu), LYS_TAIL_MAX, LYS_ADAPTIVE_GRIDS, LYS_SHADE_ORDER,
  * LYS_FUSE_GENERATE; LYS_PROFILE_TAIL keeps the fused tail under per-class timing. */
-struct GridSizes { int trace[4] = {0, 0, 0, 0}, shade = 0, oct = 1, adaptive = 1, sms = 148, tail_max = 8192, tail_items = 128, profile_tail = 0, order = 1, fuse_gen = 1; };
+struct GridSizes { int trace[2] = {0, 0}, shade = 0, adaptive = 1, sms = 148, tail_max = 8192, tail_items = 128, profile_tail = 0, order = 1, fuse_gen = 1; };
 static GridSizes grid_sizes() {
     static GridSizes g[64];
     int dev = 0; cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64) dev = 0;
     if (!g[dev].shade) {
-        int sms = 148, bt[4] = {10, 12, 16, 16}, bs = 3;
+        int sms = 148, bt[2] = {10, 16}, bs = 3;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bs, k_shade<LYS_SHADE_T>, LYS_SHADE_T, 0);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bt[LAY_SINGLE], k_trace<LAY_SINGLE>, 128, 0);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bt[LAY_PAIR_OCT], k_trace<LAY_PAIR_OCT>, 128, 0);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bt[LAY_PAIR], k_trace<LAY_PAIR>, 128, 0);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bt[LAY_SINGLE_SEL], k_trace<LAY_SINGLE_SEL>, 128, 0);
-        for (int k = 0; k < 4; k++) g[dev].trace[k] = sms * (bt[k] > 0 ? bt[k] : 1);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bt[LAY_OCT], k_trace<LAY_OCT>, 128, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bt[LAY_SEL], k_trace<LAY_SEL>, 128, 0);
+        for (int k = 0; k < 2; k++) g[dev].trace[k] = sms * (bt[k] > 0 ? bt[k] : 1);
         g[dev].shade = sms * (bs > 0 ? bs : 1);
         g[dev].sms = sms;
         const char *ord = getenv("LYS_SHADE_ORDER"); if (ord) g[dev].order = atoi(ord) ? 1 : 0;      /* 0: k_shade walks the slots in queue order */
@@ -926,21 +862,16 @@ static GridSizes grid_sizes() {
         const char *ptl = getenv("LYS_PROFILE_TAIL"); if (ptl) g[dev].profile_tail = atoi(ptl) ? 1 : 0;
         const char *tmx = getenv("LYS_TAIL_MAX"); if (tmx) g[dev].tail_max = atoi(tmx);          /* 0: no fused tail */
         const char *ad = getenv("LYS_ADAPTIVE_GRIDS"); if (ad) g[dev].adaptive = atoi(ad) ? 1 : 0;
-        const char *oc = getenv("LYS_TRACE_OCT"); if (oc) g[dev].oct = atoi(oc) ? 1 : 0;          /* 0: always the select-based box test */
     }
     return g[dev];
 }
-static int trace_layout(const GridSizes &gs, const SceneDev &sc) {
-    if (sc.single_nodes) return sc.oct_copies == 8 ? LAY_SINGLE : LAY_SINGLE_SEL;
-    return (sc.nodes_oct && sc.oct_copies == 8 && gs.oct) ? LAY_PAIR_OCT : LAY_PAIR;
-}
-/* the three traversal variants a scene can select */
-#define LYS_TRAV_DISPATCH(lay, CALL) do { \
-        if ((lay) == LAY_SINGLE) { CALL(LAY_SINGLE); } else if ((lay) == LAY_PAIR_OCT) { CALL(LAY_PAIR_OCT); } else if ((lay) == LAY_SINGLE_SEL) { CALL(LAY_SINGLE_SEL); } else { CALL(LAY_PAIR); } } while (0)
+static int trace_layout(const SceneDev &sc) { return sc.oct_copies == 8 ? LAY_OCT : LAY_SEL; }
+/* the two traversal variants a scene can select */
+#define LYS_TRAV_DISPATCH(lay, CALL) do { if ((lay) == LAY_OCT) { CALL(LAY_OCT); } else { CALL(LAY_SEL); } } while (0)
 static void launch_trace(const GridSizes &gs, int grid, const SceneDev &sc, const FrameParams &fp, PassBuffers &bufs, int bounce, cudaStream_t stream) {
     const int ordered = (gs.order && bounce >= 0) ? 1 : 0;      /* write the hits-first order of bounce + 1, walk the one of bounce */
 #define LYS_CALL(LAY) k_trace<LAY><<<grid, 128, 0, stream>>>(sc, fp, bufs, bounce, ordered)
-    LYS_TRAV_DISPATCH(trace_layout(gs, sc), LYS_CALL);
+    LYS_TRAV_DISPATCH(trace_layout(sc), LYS_CALL);
 #undef LYS_CALL
 }
 cudaError_t run_sample_pass(const SceneDev &sc, const FrameParams &fp, PassBuffers &bufs, cudaStream_t stream, uint64_t *launches, LaunchTimer *timer,
@@ -950,7 +881,7 @@ cudaError_t run_sample_pass(const SceneDev &sc, const FrameParams &fp, PassBuffe
     uint64_t nl = 0;
     LaunchTimer none; LaunchTimer &tm = timer ? *timer : none;
     const GridSizes gs = grid_sizes();
-    const int g_trace = min(gs.trace[trace_layout(gs, sc)], cdiv(2ll * n, 128)), g_shade = min(gs.shade, cdiv(n, LYS_SHADE_T));
+    const int g_trace = min(gs.trace[trace_layout(sc)], cdiv(2ll * n, 128)), g_shade = min(gs.shade, cdiv(n, LYS_SHADE_T));
     /* queue-length estimates: a snapshot of what an earlier pass left (the copy below may be updating it: harmless, the
      * numbers only size grids); valid if it is about the same sample grid */
     int est[LYS_MAX_PATH_LEN + 2];
@@ -975,7 +906,7 @@ cudaError_t run_sample_pass(const SceneDev &sc, const FrameParams &fp, PassBuffe
         tm.begin(1, stream);
         const int g = cdiv(n, 128);
 #define LYS_CALL(LAY) k_generate_trace<LAY><<<g, 128, 0, stream>>>(sc, fp, bufs)
-        LYS_TRAV_DISPATCH(trace_layout(gs, sc), LYS_CALL);
+        LYS_TRAV_DISPATCH(trace_layout(sc), LYS_CALL);
 #undef LYS_CALL
         tm.end(stream); nl++;
     } else {
@@ -998,11 +929,9 @@ cudaError_t run_sample_pass(const SceneDev &sc, const FrameParams &fp, PassBuffe
         const int g = (int)max((long long)gs.sms, min((long long)gs.sms * 4, (long long)((est[b_tail] + est[b_tail] / 4 + gs.tail_items - 1) / gs.tail_items)));   /* few, well filled CTAs (they stay resident for all the remaining bounces), never fewer than one per SM: a stale estimate must not serialise a long queue */
         tm.cur_bounce = b_tail;
         tm.begin(3, stream);
-        const int lay = trace_layout(gs, sc);
-        if (lay == LAY_SINGLE) k_tail<LAY_SINGLE><<<g, 128, 0, stream>>>(sc, fp, bufs, b_tail);
-        else if (lay == LAY_PAIR_OCT) k_tail<LAY_PAIR_OCT><<<g, 128, 0, stream>>>(sc, fp, bufs, b_tail);
-        else if (lay == LAY_SINGLE_SEL) k_tail<LAY_SINGLE_SEL><<<g, 128, 0, stream>>>(sc, fp, bufs, b_tail);
-        else k_tail<LAY_PAIR><<<g, 128, 0, stream>>>(sc, fp, bufs, b_tail);
+        const int lay = trace_layout(sc);
+        if (lay == LAY_OCT) k_tail<LAY_OCT><<<g, 128, 0, stream>>>(sc, fp, bufs, b_tail);
+        else k_tail<LAY_SEL><<<g, 128, 0, stream>>>(sc, fp, bufs, b_tail);
         tm.end(stream); nl++;
     }
     if (est_counts && gs.adaptive) {
@@ -1047,14 +976,16 @@ cudaError_t run_primary_probe(const SceneDev &sc, const FrameParams &fp, PassBuf
     const int n = fp.n_local;
     if (n <= 0) return cudaSuccess;
     k_generate<<<cdiv(n, 256), 256, 0, stream>>>(fp, bufs);
-    k_primary_probe<<<cdiv(n, 128), 128, 0, stream>>>(sc, fp, bufs, n, leaf, src, t);
+    if (trace_layout(sc) == LAY_OCT) k_primary_probe<LAY_OCT><<<cdiv(n, 128), 128, 0, stream>>>(sc, fp, bufs, n, leaf, src, t);
+    else k_primary_probe<LAY_SEL><<<cdiv(n, 128), 128, 0, stream>>>(sc, fp, bufs, n, leaf, src, t);
     if (launches) *launches += 2;
     return cudaGetLastError();
 }
 cudaError_t run_trace_rays(const SceneDev &sc, const float *rays, const float *tmax, int64_t n, int *out_leaf, float *out_t,
                            int any_hit, cudaStream_t stream, uint64_t *launches) {
     if (n <= 0) return cudaSuccess;
-    k_trace_rays<<<cdiv(n, 128), 128, 0, stream>>>(sc, rays, tmax, n, out_leaf, out_t, any_hit);
+    if (trace_layout(sc) == LAY_OCT) k_trace_rays<LAY_OCT><<<cdiv(n, 128), 128, 0, stream>>>(sc, rays, tmax, n, out_leaf, out_t, any_hit);
+    else k_trace_rays<LAY_SEL><<<cdiv(n, 128), 128, 0, stream>>>(sc, rays, tmax, n, out_leaf, out_t, any_hit);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }

@@ -470,16 +470,12 @@ def test_init_light_capacity_regrow(orc, pkg, gpu, scenes):
 
 
 @pytest.mark.parametrize('env', [
-    {'LYS_TRACE_PAIR': '1'},           # pair records on the small scene too (what scenes above 1024 triangles use)
-    {'LYS_TRACE_PAIR': '1', 'LYS_TRACE_OCT': '0'},            # select-based box test on the plain record array (scenes above 64K nodes)
-    {'LYS_OCT_ONE_COPY': '1', 'LYS_BIG_SINGLE': '1'},      # single-box records with escape links, one copy, select-based box test (LAY_SINGLE_SEL)
-    {'LYS_TRACE_OCT': '0'},            # small scene: single-box records stay (they exist as octant copies only); spectrumsphere: plain pair records
+    {'LYS_OCT_ONE_COPY': '1'},         # one copy of the traversal records, select-based box test (LAY_SEL: what scenes above 64K nodes run)
     {'LYS_SHADE_ORDER': '0'},          # k_shade walks the queue in slot order instead of hits first
     {'LYS_FUSE_GENERATE': '0'},        # k_generate and k_trace(-1) as two launches (the per-class timing sequence)
     {'LYS_TAIL_MAX': '0'},             # no fused tail kernel: one launch per stage and bounce
     {'LYS_TAIL_MAX': '100000000'},     # fused tail from bounce 1 on (every queue is 'short')
-    {'LYS_TAIL_MAX': '100000000', 'LYS_TRACE_OCT': '0'},
-    {'LYS_TAIL_MAX': '100000000', 'LYS_TRACE_PAIR': '1'},
+    {'LYS_TAIL_MAX': '100000000', 'LYS_OCT_ONE_COPY': '1'},
     {'LYS_ADAPTIVE_GRIDS': '0'},       # every pass runs like the first pass of a frame (full grids, no tail)
 ], ids=lambda e: ','.join(f'{k}={v}' for k, v in e.items()))
 def test_kernel_variants_bit_exact(env):

@@ -45,14 +45,12 @@ def test_emulated_library_equals_the_oracle(emu_lib):
 
 
 @pytest.mark.parametrize('env', [
-    {'LYS_TRACE_PAIR': '1', 'LYS_TRACE_OCT': '0'},       # what scenes above 64K nodes run: pair records, select-based box test
-    {'LYS_TRACE_PAIR': '1'},                             # 1K .. 64K nodes: pair records, octant copies
-    {'LYS_OCT_ONE_COPY': '1', 'LYS_BIG_SINGLE': '1'},    # single-box records with escape links, one copy (LAY_SINGLE_SEL)
+    {'LYS_OCT_ONE_COPY': '1'},                           # what scenes above 64K nodes run: one copy of the records, select-based box test
     {'LYS_TAIL_MAX': '100000000'},                     # fused tail kernel from bounce 1 on
     {'LYS_TAIL_MAX': '0', 'LYS_SHADE_ORDER': '0', 'LYS_FUSE_GENERATE': '0', 'LYS_EMU_SMS': '32'},
     {'LYS_EMU_SCHEDULE': '1'},                         # CTAs, warps and lanes run in reverse order: results must not depend on the schedule
     {'LYS_EMU_SCHEDULE': '4242', 'LYS_TAIL_MAX': '100000000'},       # pseudo-random orders, redrawn per CTA (race / order-dependence probe)
-    {'LYS_EMU_SCHEDULE': '977', 'LYS_TRACE_PAIR': '1', 'LYS_TRACE_OCT': '0', 'LYS_EMU_SMS': '8'},
+    {'LYS_EMU_SCHEDULE': '977', 'LYS_OCT_ONE_COPY': '1', 'LYS_EMU_SMS': '8'},
 ])
 def test_emulated_kernel_variants(emu_lib, env):
     e = dict(env)
@@ -91,7 +89,7 @@ def test_product_binding_has_no_library_override(emu_lib):
 @pytest.mark.parametrize('what,seed,count,env', [
     ('lbvh', 1, 40, {'LYS_EMU_SCHEDULE': '3'}),        # hostile geometry: inf / NaN / denormals / duplicates / identical triangles
     ('soup', 2, 10, {}),                               # random scenes, materials, camera presets, poses, frame sizes, seeds
-    ('soup', 3, 8, {'LYS_TRACE_PAIR': '1', 'LYS_TRACE_OCT': '0', 'LYS_EMU_SCHEDULE': '7'}),
+    ('soup', 3, 8, {'LYS_OCT_ONE_COPY': '1', 'LYS_EMU_SCHEDULE': '7'}),
     ('keys', 4, 12, {}),                               # random host sessions: key events, resizes, steps -> scalars, image, ARGB frame
 ], ids=lambda v: str(v) if not isinstance(v, dict) else ','.join(f'{k}={x}' for k, x in v.items()) or 'default')
 def test_fuzzed_parity_on_the_emulator(emu_lib, what, seed, count, env):

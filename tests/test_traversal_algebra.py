@@ -4,10 +4,7 @@
  1. the reference leaves after the first axis with tmax <= tmin; one test after the third axis gives the same boolean;
  2. picking near / far per axis at build time by the sign of 1/dir (the octant node arrays) gives the same t0 / t1 as the
     reference's swap;
- 3. the deferred right-child test of the pair-node walk: a box tested early against tmax_a and re-checked later against a
-    smaller tmax_b with ONE comparison, !(tmax_b <= tn), tn = the entry distance of the early test, gives the boolean the
-    reference's full test gives at the later time;
- 4. the escape links of the single-box layout (csrc/lbvh.cu: k_thread_links): the reference's parent-pointer walk
+ 3. the escape links of the single-box layout (csrc/lbvh.cu: k_pack_records): the reference's parent-pointer walk
     (bvh.fut:126-142), a left-first walk with a stack and a walk that follows stored escape links visit the same nodes in
     the same order whatever the box tests and triangle tests answer.
 
@@ -103,40 +100,6 @@ def test_octant_nodes_equal_the_swap():
             assert np.array_equal(branch_free(*args), octant(*args))
 
 
-def entry_distance(o, inv, lo, hi):
-    """tmin after the third axis (slab_test's `tn`): it does not involve the ray's tmax"""
-    tmin = np.zeros(len(o), F)
-    for a in range(3):
-        t0 = (lo[:, a] - o[:, a]) * inv[:, a]
-        t1 = (hi[:, a] - o[:, a]) * inv[:, a]
-        t0 = np.where(inv[:, a] < 0, t1, t0)
-        tmin = np.fmax(t0, tmin)
-    return tmin
-
-
-def test_deferred_right_child_test_equals_the_test_at_pop_time():
-    """trav_node_stage tests the right child when its parent is entered (tmax_a) and TravStack<false>::pop re-checks it when it
-    is popped (tmax_b <= tmax_a: closest_hit only ever shrinks tmax, bvh.fut:136-139).  The reference tests it once, at pop
-    time, against tmax_b.  Claim: early fail => late fail; early pass => (late pass <=> !(tmax_b <= tn))."""
-    with np.errstate(invalid='ignore', over='ignore'):
-        for seed in range(4):
-            o, inv, lo, hi, tmax_a = cases(200 + seed, 500_000)
-            rng = np.random.default_rng(300 + seed)
-            shrink = rng.random(len(tmax_a)).astype(F)
-            shrink[rng.random(len(tmax_a)) < 0.2] = F(1.0)                  # tmax unchanged (no hit in the left subtree)
-            tmax_b = np.where(np.isnan(tmax_a), tmax_a, np.fmin(tmax_a, np.abs(tmax_a) * shrink)).astype(F)
-            tmax_b = np.where(np.isinf(tmax_b) | (tmax_a == np.finfo(F).max), np.where(shrink == 1, tmax_a, F(10.0) * shrink), tmax_b).astype(F)
-            early = reference(o, inv, lo, hi, tmax_a)
-            late = reference(o, inv, lo, hi, tmax_b)                      # what the reference computes
-            tn = entry_distance(o, inv, lo, hi)
-            assert not np.isnan(tn).any()
-            ok = ~np.isnan(tmax_a)                                         # a ray's tmax is never NaN (FLT_MAX, a hit's t, or distance - 0.01 of a finite vertex)
-            assert not (late & ~early & ok).any()
-            deferred = early & ~(tmax_b <= tn)
-            assert np.array_equal(deferred[ok], late[ok]), int((deferred != late)[ok].sum())
-            assert 0.05 < late.mean() < 0.9 and (early & ~late).mean() > 0.02       # the re-check does cut boxes off
-
-
 def _dot(a, b):
     return (a[:, 0] * b[:, 0] + a[:, 1] * b[:, 1]) + a[:, 2] * b[:, 2]          # vec3.dot, left to right
 
@@ -188,7 +151,7 @@ def test_early_rejections_of_the_triangle_test_do_not_change_it():
     assert 0.1 < ref.mean() < 0.9
 
 
-# ---- 4. escape links ------------------------------------------------------------------------------------------------
+# ---- 3. escape links ------------------------------------------------------------------------------------------------
 DONE = -(1 << 31)
 
 
@@ -213,7 +176,7 @@ def random_tree(rng, n_leaves):
 
 
 def thread_links(left, right, parent, leaf_parent):
-    """k_thread_links: the right child of the nearest ancestor-or-self that is a left child, DONE on the right spine"""
+    """k_pack_records: the right child of the nearest ancestor-or-self that is a left child, DONE on the right spine"""
     def link(self, p):
         while p >= 0 and right[p] == self:
             self, p = p, parent[p]
