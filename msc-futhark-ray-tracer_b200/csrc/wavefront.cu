@@ -518,12 +518,12 @@ LYS_D void connect_finish(const FrameParams &fp, const PassBuffers &b, int bounc
  * were built, parity-tested and measured: -38 % and +3 % on the 1 M-triangle scene, slower on every bundled scene
  * (profiles/README.md 7.2, 8.1); they are no longer part of the build.
  * `ordered` bit 0: append the slots of bounce + 1 to the hits-first order list and walk this bounce's vertices in theirs. */
-/* resident CTAs of 128 threads per SM the traversal kernels are compiled for.  Scenes with octant copies are issue bound: 10
- * CTAs / 48 registers, no spills (12 CTAs measured the same).  Large scenes are latency bound (dependent L2 / DRAM record
- * loads): more warps in flight win even with a few registers spilled to L1 -- 1106 / 1147 / 1176 Mpaths/s at 10 / 12 / 16 CTAs
- * on the 1 M-triangle scene (profiles/README.md 8.10). */
+/* resident CTAs of 128 threads per SM the traversal kernels are compiled for.  The walk waits on dependent record loads, so
+ * more warps in flight win even with a few registers spilled to L1: with octant copies 12 CTAs (40 registers) against 10 (48, no
+ * spills) give +0.5 % on CornellBox and +3-4 % from 2 K to 64 K triangles (16: no further gain); the large scenes run 1106 /
+ * 1147 / 1176 Mpaths/s at 10 / 12 / 16 CTAs (32 registers) on the 1 M-triangle scene (profiles/README.md 8.10). */
 #ifndef LYS_TRACE_MINB
-#define LYS_TRACE_MINB(LAY) ((LAY) == LAY_SEL ? 16 : 10)
+#define LYS_TRACE_MINB(LAY) ((LAY) == LAY_SEL ? 16 : 12)
 #endif
 template <int LAY>
 __global__ void __launch_bounds__(128, LYS_TRACE_MINB(LAY)) k_trace(SceneDev sc, const __grid_constant__ FrameParams fp, PassBuffers b, int bounce, int ordered) {
@@ -849,7 +849,7 @@ static GridSizes grid_sizes() {
     int dev = 0; cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64) dev = 0;
     if (!g[dev].shade) {
-        int sms = 148, bt[2] = {10, 16}, bs = 3;
+        int sms = 148, bt[2] = {12, 16}, bs = 3;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bs, k_shade<LYS_SHADE_T>, LYS_SHADE_T, 0);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bt[LAY_OCT], k_trace<LAY_OCT>, 128, 0);
