@@ -359,7 +359,7 @@ def main():
                     'class_ms': {k: round(v, 3) for k, v in class_ms.items()}, 'class_share': {k: round(v, 4) for k, v in share.items()},
                     'profiled_ms_per_step': prof_ms,
                     'note': 'bound = SM issue (the 3.6 KB BVH is L1/L2 resident; DRAM only sees path state): see roofline.issue; achieved / frac are the algorithmic '
-                            'traversal bytes over the traversal classes\' share of the timed step against the HBM peak, as the contract asks: passes are pipelined over 8 '
+                            'traversal bytes over the traversal classes\' share of the timed step against the HBM peak, as the contract asks: passes are pipelined over 12 '
                             'streams, so that share is smaller than the serialised kernel time and frac can exceed 1 (cache-resident BVH: DRAM traffic is 6x below the '
                             'algorithmic bytes, see traffic); roofline.exclusive is the same quantity over the ncu launch durations. class_ms = event-time shares of the '
                             'production sequence (profiled right after the timed region, profiled_ms_per_step) x ms_per_step'}

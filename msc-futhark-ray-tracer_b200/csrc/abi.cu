@@ -45,7 +45,7 @@ struct futhark_context {
      * (or point-cloud merge) kernels are ordered, so one pass's latency-bound tail overlaps the next pass's head */
     struct PassSlot { cudaStream_t stream = nullptr; PassBuffers bufs; cudaEvent_t done = nullptr; };
     std::vector<PassSlot> slots;
-    int pipeline = 8;
+    int pipeline = 12;                   /* 6 / 8 / 12 / 16 measured: 3305 / 3348 / 3381 / 3389 Mpaths/s on CornellBox (profiles/README.md 8.10) */
     int *h_counts = nullptr;             /* pinned: queue lengths of a recent pass (grid sizing only, see run_sample_pass) */
     uint64_t est_tag = 0;                /* what the estimates are about: scene, camera, path length */
     /* stepping loop of an interactive host (liblys.c:104-123: step, render, values, repeat): once the host steps the state
