@@ -351,7 +351,7 @@ __global__ void k_gather_leaves(const float *__restrict__ tris, const uint32_t *
     V3 e1 = b - a, e2 = c - a;                                          /* shapes.fut:69-70 */
     V3 nc = cross(e1, e2);                                              /* shapes.fut:71: ray independent, stored once */
     leaf_tri[4ll * i + 0] = make_float4(a.x, a.y, a.z, __uint_as_float(tri_mats[s]));
-    leaf_tri[4ll * i + 1] = make_float4(nc.x, nc.y, nc.z, __int_as_float((int)0x80000000));   /* .w: escape link (k_thread_links) */
+    leaf_tri[4ll * i + 1] = make_float4(nc.x, nc.y, nc.z, __int_as_float((int)0x80000000));   /* .w: escape link (k_pack_records) */
     leaf_tri[4ll * i + 2] = make_float4(e1.x, e1.y, e1.z, __uint_as_float(s));
     leaf_tri[4ll * i + 3] = make_float4(e2.x, e2.y, e2.z, 0.0f);
     leaf_box[2ll * i + 0] = box_c[s];

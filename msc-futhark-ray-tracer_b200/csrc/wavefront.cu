@@ -89,7 +89,7 @@ LYS_D bool leaf_test(const RayInv &r, const float4 *__restrict__ leaf_tri, int l
  * left, and come back for the right child when the left subtree is done; leaves are never box-tested.  The walk is left-first
  * WHATEVER THE RAY, so the node that follows a failed box test or a finished leaf is a property of the tree: the right child of
  * the nearest ancestor-or-self that is a left child, or the end marker on the right spine.  The build stores that escape link in
- * every record (lbvh.cu: k_thread_links), and the walk needs neither the reference's parent pointers nor a stack:
+ * every record (lbvh.cu: k_pack_records), and the walk needs neither the reference's parent pointers nor a stack:
  *     internal node:  cur = box passes ? left child : escape link          leaf:  triangle test, then cur = escape link
  * Same tests against the same tmax in the same order, so hits, ties (strict t < tmax, shapes.fut:64) and the culling by the
  * non-conservative truncated boxes (bvh.fut:105-120) are identical (tests/test_traversal_algebra.py: escape links vs the

@@ -49,7 +49,7 @@ def branch_free(o, inv, lo, hi, tmax):
 
 
 def octant(o, inv, lo, hi, tmax):
-    """near / far chosen per axis by (inv < 0) before the arithmetic, as k_pack_nodes stores them per octant"""
+    """near / far chosen per axis by (inv < 0) before the arithmetic, as k_pack_records stores them per octant"""
     tmin = np.zeros(len(tmax), F)
     tmx = tmax.copy()
     for a in range(3):

@@ -207,7 +207,7 @@ def study_schedules(scene, h, w):
 
 
 def pair_cost(pat, ln, order, policy, costs, thr=8, nb=2):
-    """Pair records (wavefront.cu: LAY_PAIR*): a failing box test costs no visit of its own, so a ray's stage sequence is its
+    """Pair records (the round-2 layout that the stackless walk replaced; commit f572386): a failing box test costs no visit of its own, so a ray's stage sequence is its
     reference pattern without the 'box fail' events ('N' = enter a node: both children tested, 'T' = triangle test).
     policy 'static': every iteration runs nb N stages then one T stage (k_trace today);
     policy 'vote':   every iteration runs ONE stage chosen by a warp vote: T if at least `thr` lanes wait at a leaf or no lane
