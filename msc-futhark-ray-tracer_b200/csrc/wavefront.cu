@@ -525,6 +525,105 @@ LYS_D void connect_finish(const FrameParams &fp, const PassBuffers &b, int bounc
 #ifndef LYS_TRACE_MINB
 #define LYS_TRACE_MINB(LAY) ((LAY) == LAY_SEL ? 16 : 12)
 #endif
+/* Closest hits with LANE REFILL (large scenes, LAY_SEL).  The stackless walk's state is (cur, tmax, closest) plus the ray, so a
+ * lane that has finished its walk can take the warp's next item instead of idling until the longest walk of its batch of 32 ends
+ * (walk lengths differ 20x on the 1 M-triangle scene: 11-15 of 32 lanes were busy).  The warp owns the items of its grid-stride
+ * batches in sequence; a refill event -- at most LYS_TRACE_REFILL lanes busy -- writes the finished hits and hands the next items to
+ * the idle lanes, rays straight from global memory (the next batch's lines are requested into L1 when a batch is started).
+ * The hits-first order list of shade(bounce + 1) is appended 32 finished items at a time from a warp-private list in shared memory:
+ * one pair of atomics per 32 items as in the batch loop.  Per-ray arithmetic and decisions are traverse<>'s; only which lane
+ * walks which ray, and when, differs.  Measured (profiles/README.md 8.11): +6 % on the 1 M-triangle scene; -2.5 % on CornellBox,
+ * where the walks are short and the refill's divisions and votes cost more than the idle lanes -- so LAY_OCT keeps the batch loop. */
+#ifndef LYS_TRACE_REFILL
+#define LYS_TRACE_REFILL 24
+#endif
+template <int LAY>
+LYS_D void trace_ext_refill(const SceneDev &sc, const PassBuffers &b, int bounce, int n_ext, int stride, int ordered) {
+    __shared__ int s_fin[4][64];                          /* per warp: finished items waiting for their order-list slot, (item << 1) | hit */
+    constexpr bool CS = LAY == LAY_SEL;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    const int n_nodes = (int)sc.n_tris - 1;
+    const int wbase = (blockIdx.x * blockDim.x + (threadIdx.x & ~31));          /* first item of the warp's batch 0 */
+    if (wbase >= n_ext) return;
+    const int n_batches = (n_ext - wbase - 1) / stride + 1;                       /* batches j with wbase + j * stride < n_ext */
+    const int s_end = n_batches * 32;
+    const float4 *__restrict__ ray_o = b.ray_o[(bounce + 1) & 1], *__restrict__ ray_d = b.ray_d[(bounce + 1) & 1];
+    int *fin = s_fin[(threadIdx.x >> 5) & 3];
+    int fn = 0;                                           /* warp-uniform */
+    int s_next = 0;                                       /* warp-uniform: next position of the warp's item sequence */
+    int it = -1, cur = TRAV_DONE, closest = -1;
+    float tmax = 0.0f;
+    RayInv r; r.o = v3(0.0f, 0.0f, 0.0f); r.d = v3(1.0f, 1.0f, 1.0f); r.inv = r.d;
+    unsigned long long nbase = reinterpret_cast<unsigned long long>(sc.nodes);
+    /* order list of shade(bounce + 1): hits from the front, misses from the back; the last cnt <= 32 entries of the warp's list */
+    auto flush = [&](int cnt) {
+        const int code = (lane < cnt) ? fin[fn - cnt + lane] : 0;
+        __syncwarp();
+        fn -= cnt;
+        const bool isH = lane < cnt && (code & 1), isM = lane < cnt && !(code & 1);
+        const unsigned mh = __ballot_sync(0xffffffffu, isH), mm = __ballot_sync(0xffffffffu, isM);
+        int bh = 0, bm = 0;
+        if (lane == 0) { if (mh) bh = atomicAdd(&b.split[2 * (bounce + 1)], __popc(mh)); if (mm) bm = atomicAdd(&b.split[2 * (bounce + 1) + 1], __popc(mm)); }
+        bh = __shfl_sync(0xffffffffu, bh, 0); bm = __shfl_sync(0xffffffffu, bm, 0);
+        if (isH) st_state<CS>(&b.order[(bounce + 1) & 1][bh + __popc(mh & lt)], code >> 1);
+        if (isM) st_state<CS>(&b.order[(bounce + 1) & 1][n_ext - 1 - (bm + __popc(mm & lt))], code >> 1);
+    };
+    for (;;) {
+        const unsigned busy = __ballot_sync(0xffffffffu, cur != TRAV_DONE);
+        if (__popc(busy) <= LYS_TRACE_REFILL && (s_next < s_end || busy == 0u)) {
+            const bool fin_now = cur == TRAV_DONE && it >= 0;
+            if (fin_now) st_state<CS>(&b.hit[it], closest);
+            if (ordered) {
+                const unsigned mf = __ballot_sync(0xffffffffu, fin_now);
+                if (mf) {
+                    if (fin_now) fin[fn + __popc(mf & lt)] = (it << 1) | (closest >= 0 ? 1 : 0);
+                    fn += __popc(mf);
+                    __syncwarp();
+                    if (fn >= 32) flush(32);
+                }
+            }
+            if (fin_now) it = -1;
+            if (s_next >= s_end) { if (busy == 0u) break; }
+            else {
+                const unsigned idle = ~busy;
+                const int s = s_next + __popc(idle & lt);
+                s_next = min(s_next + __popc(idle), s_end);
+                if (cur == TRAV_DONE && s < s_end) {
+                    const int g = wbase + (s >> 5) * stride + (s & 31);
+                    if (g < n_ext) {
+                        const float4 ro = ld_state<CS>(&ray_o[g]), rd = ld_state<CS>(&ray_d[g]);
+                        r.o = v3(ro.x, ro.y, ro.z); r.d = v3(rd.x, rd.y, rd.z); r.inv = v3(1.0f / rd.x, 1.0f / rd.y, 1.0f / rd.z);
+                        nbase = reinterpret_cast<unsigned long long>(sc.nodes);
+                        if (LAY == LAY_OCT) nbase += 32ull * (unsigned)n_nodes * (unsigned)(((r.inv.x < 0.0f) ? 4 : 0) | ((r.inv.y < 0.0f) ? 2 : 0) | ((r.inv.z < 0.0f) ? 1 : 0));
+                        it = g; cur = 0; closest = -1; tmax = FLT_MAX;
+#ifdef __CUDACC__
+                        if ((s & 7) == 0) {       /* one lane per 128-byte line of the batch started: request the next batch's records */
+                            const int gn = g + stride;
+                            if (gn < n_ext) { asm volatile("prefetch.global.L1 [%0];" :: "l"(&ray_o[gn])); asm volatile("prefetch.global.L1 [%0];" :: "l"(&ray_d[gn])); }
+                        }
+#endif
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < TRAV_NB; k++) {
+            if (cur >= 0) {
+                const float4 *q = reinterpret_cast<const float4 *>(nbase + 32ull * (unsigned)cur);
+                float4 lo, hi; ld_sector(q, lo, hi);
+                float tn;
+                cur = __float_as_int(((LAY == LAY_OCT) ? slab_test_oct(r, lo, hi, tmax, tn) : slab_test(r, lo, hi, tmax, tn)) ? lo.w : hi.w);
+            }
+        }
+        if ((unsigned)cur > (unsigned)TRAV_DONE) {
+            float t; int next;
+            if (leaf_test(r, sc.leaf_tri, ~cur, tmax, t, next)) { closest = ~cur; tmax = t; }
+            cur = next;
+        }
+    }
+    if (ordered && fn > 0) flush(fn);
+}
 template <int LAY>
 __global__ void __launch_bounds__(128, LYS_TRACE_MINB(LAY)) k_trace(SceneDev sc, const __grid_constant__ FrameParams fp, PassBuffers b, int bounce, int ordered) {
     const int n_ext = (bounce + 1 < fp.path_len) ? b.counts[bounce + 1] : 0;
@@ -535,8 +634,11 @@ __global__ void __launch_bounds__(128, LYS_TRACE_MINB(LAY)) k_trace(SceneDev sc,
     const int lane = threadIdx.x & 31;
     const float4 *__restrict__ nodes = sc.nodes;
     constexpr bool CS = LAY == LAY_SEL;      /* large scenes: path-state records bypass L2 residency (lys_device.cuh: ld_state) */
+    /* large scenes: the closest hits first, with lane refill; the loop below is then left with the shadow rays */
+    constexpr bool refill_ext = LAY == LAY_SEL;
+    if (refill_ext) trace_ext_refill<LAY>(sc, b, bounce, n_ext, stride, ordered);
     /* warp-uniform loop (traverse<> votes): a warp owns 32 consecutive items; only the warp that straddles n_ext mixes kinds */
-    for (int i0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31); i0 < total; i0 += stride) {
+    for (int i0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31) + (refill_ext ? n_ext : 0); i0 < total; i0 += stride) {
         const int i = i0 + lane;
         const bool is_ext = i < n_ext, is_con = !is_ext && i < total;
         if (i0 < n_ext) {
