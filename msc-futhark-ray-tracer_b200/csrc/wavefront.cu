@@ -109,7 +109,8 @@ LYS_D bool leaf_test(const RayInv &r, const float4 *__restrict__ leaf_tri, int l
  * time) were the round-2 layout for scenes above 1024 triangles until the escape links made the stack unnecessary: single-box
  * records now win on every scene size (profiles/README.md 8.10) and the pair code is gone (history: commit 3c87084). */
 #define TRAV_DONE ((int)0x80000000)
-enum { LAY_OCT = 0, LAY_SEL = 1 };
+enum { LAY_OCT = 0, LAY_SEL = 1, LAY_OCT_RF = 2 };      /* LAY_OCT_RF: LAY_OCT records, k_trace with lane refill (scene size, launch_trace) */
+#define LYS_LAY_IS_OCT(LAY) ((LAY) != LAY_SEL)
 #ifndef TRAV_NB
 #define TRAV_NB 2          /* node stages per loop iteration: 2 measured best on every layout and scene size (profiles/README.md 8.2, 8.10) */
 #endif
@@ -119,7 +120,7 @@ LYS_D int traverse(const float4 *__restrict__ nodes, const float4 *__restrict__ 
     RayInv r; r.o = o; r.d = d; r.inv = v3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
     int closest = -1;
     unsigned long long nbase = reinterpret_cast<unsigned long long>(nodes);        /* per-lane base: node i at nbase + 32 i */
-    if (LAY == LAY_OCT) nbase += 32ull * (unsigned)n_nodes * (unsigned)(((r.inv.x < 0.0f) ? 4 : 0) | ((r.inv.y < 0.0f) ? 2 : 0) | ((r.inv.z < 0.0f) ? 1 : 0));
+    if (LYS_LAY_IS_OCT(LAY)) nbase += 32ull * (unsigned)n_nodes * (unsigned)(((r.inv.x < 0.0f) ? 4 : 0) | ((r.inv.y < 0.0f) ? 2 : 0) | ((r.inv.z < 0.0f) ? 1 : 0));
     asm volatile("" : "+l"(nbase));      /* keep the sum in a register pair: one IMAD.WIDE per node address */
     int cur = (active && n_nodes > 0) ? 0 : TRAV_DONE;       /* internal node to enter (>= 0), leaf pointer (~leaf) or TRAV_DONE */
     do {
@@ -129,7 +130,7 @@ LYS_D int traverse(const float4 *__restrict__ nodes, const float4 *__restrict__ 
                 const float4 *q = reinterpret_cast<const float4 *>(nbase + 32ull * (unsigned)cur);
                 float4 lo, hi; ld_sector(q, lo, hi);
                 float tn;
-                cur = __float_as_int(((LAY == LAY_OCT) ? slab_test_oct(r, lo, hi, tmax, tn) : slab_test(r, lo, hi, tmax, tn)) ? lo.w : hi.w);      /* left child, or the escape link */
+                cur = __float_as_int((LYS_LAY_IS_OCT(LAY) ? slab_test_oct(r, lo, hi, tmax, tn) : slab_test(r, lo, hi, tmax, tn)) ? lo.w : hi.w);      /* left child, or the escape link */
             }
         }
         if ((unsigned)cur > (unsigned)TRAV_DONE) {            /* a leaf pointer */
@@ -525,6 +526,9 @@ LYS_D void connect_finish(const FrameParams &fp, const PassBuffers &b, int bounc
 #ifndef LYS_TRACE_MINB
 #define LYS_TRACE_MINB(LAY) ((LAY) == LAY_SEL ? 16 : 12)
 #endif
+#ifndef LYS_REFILL_MIN_TRIS
+#define LYS_REFILL_MIN_TRIS 1024     /* lane refill from here on: +2.4 / +2.9 % on SpectrumSphere / High, -2 % on CornellBox (profiles/README.md 8.11) */
+#endif
 /* Closest hits with LANE REFILL (large scenes, LAY_SEL).  The stackless walk's state is (cur, tmax, closest) plus the ray, so a
  * lane that has finished its walk can take the warp's next item instead of idling until the longest walk of its batch of 32 ends
  * (walk lengths differ 20x on the 1 M-triangle scene: 11-15 of 32 lanes were busy).  The warp owns the items of its grid-stride
@@ -595,7 +599,7 @@ LYS_D void trace_ext_refill(const SceneDev &sc, const PassBuffers &b, int bounce
                         const float4 ro = ld_state<CS>(&ray_o[g]), rd = ld_state<CS>(&ray_d[g]);
                         r.o = v3(ro.x, ro.y, ro.z); r.d = v3(rd.x, rd.y, rd.z); r.inv = v3(1.0f / rd.x, 1.0f / rd.y, 1.0f / rd.z);
                         nbase = reinterpret_cast<unsigned long long>(sc.nodes);
-                        if (LAY == LAY_OCT) nbase += 32ull * (unsigned)n_nodes * (unsigned)(((r.inv.x < 0.0f) ? 4 : 0) | ((r.inv.y < 0.0f) ? 2 : 0) | ((r.inv.z < 0.0f) ? 1 : 0));
+                        if (LYS_LAY_IS_OCT(LAY)) nbase += 32ull * (unsigned)n_nodes * (unsigned)(((r.inv.x < 0.0f) ? 4 : 0) | ((r.inv.y < 0.0f) ? 2 : 0) | ((r.inv.z < 0.0f) ? 1 : 0));
                         it = g; cur = 0; closest = -1; tmax = FLT_MAX;
 #ifdef __CUDACC__
                         if ((s & 7) == 0) {       /* one lane per 128-byte line of the batch started: request the next batch's records */
@@ -613,7 +617,7 @@ LYS_D void trace_ext_refill(const SceneDev &sc, const PassBuffers &b, int bounce
                 const float4 *q = reinterpret_cast<const float4 *>(nbase + 32ull * (unsigned)cur);
                 float4 lo, hi; ld_sector(q, lo, hi);
                 float tn;
-                cur = __float_as_int(((LAY == LAY_OCT) ? slab_test_oct(r, lo, hi, tmax, tn) : slab_test(r, lo, hi, tmax, tn)) ? lo.w : hi.w);
+                cur = __float_as_int((LYS_LAY_IS_OCT(LAY) ? slab_test_oct(r, lo, hi, tmax, tn) : slab_test(r, lo, hi, tmax, tn)) ? lo.w : hi.w);
             }
         }
         if ((unsigned)cur > (unsigned)TRAV_DONE) {
@@ -635,7 +639,7 @@ __global__ void __launch_bounds__(128, LYS_TRACE_MINB(LAY)) k_trace(SceneDev sc,
     const float4 *__restrict__ nodes = sc.nodes;
     constexpr bool CS = LAY == LAY_SEL;      /* large scenes: path-state records bypass L2 residency (lys_device.cuh: ld_state) */
     /* large scenes: the closest hits first, with lane refill; the loop below is then left with the shadow rays */
-    constexpr bool refill_ext = LAY == LAY_SEL;
+    constexpr bool refill_ext = LAY != LAY_OCT;
     if (refill_ext) trace_ext_refill<LAY>(sc, b, bounce, n_ext, stride, ordered);
     /* warp-uniform loop (traverse<> votes): a warp owns 32 consecutive items; only the warp that straddles n_ext mixes kinds */
     for (int i0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31) + (refill_ext ? n_ext : 0); i0 < total; i0 += stride) {
@@ -943,9 +947,9 @@ static inline int cdiv(long long a, int b) { return (int)((a + b - 1) / b); }
 
 /* persistent grids: SM count x resident CTAs per SM of each kernel (queried once per device).  The environment knobs
  * force what is otherwise chosen by scene size or by the previous pass (tests/test_gpu_parity.py::test_kernel_variants_bit_exact
- * runs each setting against the oracle): LYS_OCT_ONE_COPY (abi.cu), LYS_TAIL_MAX, LYS_ADAPTIVE_GRIDS, LYS_SHADE_ORDER,
+ * runs each setting against the oracle): LYS_OCT_ONE_COPY (abi.cu), LYS_REFILL_MIN, LYS_TAIL_MAX, LYS_ADAPTIVE_GRIDS, LYS_SHADE_ORDER,
  * LYS_FUSE_GENERATE; LYS_PROFILE_TAIL keeps the fused tail under per-class timing. */
-struct GridSizes { int trace[2] = {0, 0}, shade = 0, adaptive = 1, sms = 148, tail_max = 8192, tail_items = 128, profile_tail = 0, order = 1, fuse_gen = 1; };
+struct GridSizes { int trace[2] = {0, 0}, shade = 0, refill_min = LYS_REFILL_MIN_TRIS, adaptive = 1, sms = 148, tail_max = 8192, tail_items = 128, profile_tail = 0, order = 1, fuse_gen = 1; };
 static GridSizes grid_sizes() {
     static GridSizes g[64];
     int dev = 0; cudaGetDevice(&dev);
@@ -959,6 +963,7 @@ static GridSizes grid_sizes() {
         for (int k = 0; k < 2; k++) g[dev].trace[k] = sms * (bt[k] > 0 ? bt[k] : 1);
         g[dev].shade = sms * (bs > 0 ? bs : 1);
         g[dev].sms = sms;
+        const char *rfm = getenv("LYS_REFILL_MIN"); if (rfm) g[dev].refill_min = atoi(rfm);        /* tests: lane refill on small scenes too */
         const char *ord = getenv("LYS_SHADE_ORDER"); if (ord) g[dev].order = atoi(ord) ? 1 : 0;      /* 0: k_shade walks the slots in queue order */
         const char *fg = getenv("LYS_FUSE_GENERATE"); if (fg) g[dev].fuse_gen = atoi(fg) ? 1 : 0;    /* 0: k_generate and k_trace(-1) as two launches */
         const char *ptl = getenv("LYS_PROFILE_TAIL"); if (ptl) g[dev].profile_tail = atoi(ptl) ? 1 : 0;
@@ -972,9 +977,10 @@ static int trace_layout(const SceneDev &sc) { return sc.oct_copies == 8 ? LAY_OC
 #define LYS_TRAV_DISPATCH(lay, CALL) do { if ((lay) == LAY_OCT) { CALL(LAY_OCT); } else { CALL(LAY_SEL); } } while (0)
 static void launch_trace(const GridSizes &gs, int grid, const SceneDev &sc, const FrameParams &fp, PassBuffers &bufs, int bounce, cudaStream_t stream) {
     const int ordered = (gs.order && bounce >= 0) ? 1 : 0;      /* write the hits-first order of bounce + 1, walk the one of bounce */
-#define LYS_CALL(LAY) k_trace<LAY><<<grid, 128, 0, stream>>>(sc, fp, bufs, bounce, ordered)
-    LYS_TRAV_DISPATCH(trace_layout(sc), LYS_CALL);
-#undef LYS_CALL
+    const int lay = trace_layout(sc);
+    if (lay == LAY_SEL) k_trace<LAY_SEL><<<grid, 128, 0, stream>>>(sc, fp, bufs, bounce, ordered);
+    else if (sc.n_tris >= gs.refill_min) k_trace<LAY_OCT_RF><<<grid, 128, 0, stream>>>(sc, fp, bufs, bounce, ordered);
+    else k_trace<LAY_OCT><<<grid, 128, 0, stream>>>(sc, fp, bufs, bounce, ordered);
 }
 cudaError_t run_sample_pass(const SceneDev &sc, const FrameParams &fp, PassBuffers &bufs, cudaStream_t stream, uint64_t *launches, LaunchTimer *timer,
                             int *est_counts) {

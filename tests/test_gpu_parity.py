@@ -471,6 +471,9 @@ def test_init_light_capacity_regrow(orc, pkg, gpu, scenes):
 
 @pytest.mark.parametrize('env', [
     {'LYS_OCT_ONE_COPY': '1'},         # one copy of the traversal records, select-based box test (LAY_SEL: what scenes above 64K nodes run)
+    {'LYS_REFILL_MIN': '1'},           # lane refill of the closest-hit walk on the small scene too (octant copies; default from 1024 triangles)
+    {'LYS_REFILL_MIN': '1', 'LYS_SHADE_ORDER': '0'},
+    {'LYS_REFILL_MIN': '100000000'},   # no lane refill with octant copies (spectrumsphere: the batch loop)
     {'LYS_SHADE_ORDER': '0'},          # k_shade walks the queue in slot order instead of hits first
     {'LYS_FUSE_GENERATE': '0'},        # k_generate and k_trace(-1) as two launches (the per-class timing sequence)
     {'LYS_TAIL_MAX': '0'},             # no fused tail kernel: one launch per stage and bounce

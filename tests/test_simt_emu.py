@@ -46,6 +46,8 @@ def test_emulated_library_equals_the_oracle(emu_lib):
 
 @pytest.mark.parametrize('env', [
     {'LYS_OCT_ONE_COPY': '1'},                           # what scenes above 64K nodes run: one copy of the records, select-based box test
+    {'LYS_REFILL_MIN': '1'},                             # lane refill of the closest-hit walk with octant copies (scenes from 1024 triangles run it)
+    {'LYS_REFILL_MIN': '1', 'LYS_TAIL_MAX': '0', 'LYS_EMU_SCHEDULE': '55'},
     {'LYS_TAIL_MAX': '100000000'},                     # fused tail kernel from bounce 1 on
     {'LYS_TAIL_MAX': '0', 'LYS_SHADE_ORDER': '0', 'LYS_FUSE_GENERATE': '0', 'LYS_EMU_SMS': '32'},
     {'LYS_EMU_SCHEDULE': '1'},                         # CTAs, warps and lanes run in reverse order: results must not depend on the schedule
