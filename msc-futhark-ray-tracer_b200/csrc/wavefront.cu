@@ -628,6 +628,106 @@ LYS_D void trace_ext_refill(const SceneDev &sc, const PassBuffers &b, int bounce
     }
     if (ordered && fn > 0) flush(fn);
 }
+/* Shadow rays with LANE REFILL (large scenes, LAY_SEL).  A lane owns one vertex of shade(bounce) at a time and takes it through
+ * light-sample ray -> BSDF-sample ray -> radiance (connect_finish); at a refill event (at most LYS_CON_REFILL lanes walking) every lane
+ * whose walk has ended moves its vertex on -- starts its second ray, or finishes it and takes the warp's next vertex.  Which lane walks
+ * which ray differs from the batch loop, nothing else: a vertex is finished exactly once, with the same L and B.  Measured
+ * (profiles/README.md 8.11): 1 M triangles +4 % (threshold 16); -1 ... -3 % with octant copies from 2 K to 9 K triangles, which keep the
+ * batch loop for their shadow rays. */
+#ifndef LYS_CON_REFILL
+#define LYS_CON_REFILL 16
+#endif
+template <int LAY>
+LYS_D void trace_con_refill(const SceneDev &sc, const FrameParams &fp, const PassBuffers &b, int bounce, int n_con, int stride, int ordered) {
+    constexpr bool CS = LAY == LAY_SEL;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    const int n_nodes = (int)sc.n_tris - 1;
+    const int wbase = (blockIdx.x * blockDim.x + (threadIdx.x & ~31));
+    if (wbase >= n_con) return;
+    const int n_batches = (n_con - wbase - 1) / stride + 1;
+    const int s_end = n_batches * 32;
+    const bool via_order = ordered && bounce >= 1;
+    const int *__restrict__ order = b.order[bounce & 1];
+    int s_next = 0;
+    int slot = -1, st = 0, cur = TRAV_DONE;            /* st: bit 0 second ray still to walk, bit 1 first ray unoccluded, bit 2 walking the second ray, bit 3 this walk hit */
+    float tmax = 0.0f;
+    RayInv r; r.o = v3(0.0f, 0.0f, 0.0f); r.d = v3(1.0f, 1.0f, 1.0f); r.inv = r.d;
+    unsigned long long nbase = reinterpret_cast<unsigned long long>(sc.nodes);
+    for (;;) {
+        const unsigned busy = __ballot_sync(0xffffffffu, cur != TRAV_DONE);
+        if (__popc(busy) <= LYS_CON_REFILL && (s_next < s_end || busy == 0u)) {
+            const float4 *dir_from = nullptr;                                   /* the ray this lane starts in this event */
+            if (cur == TRAV_DONE && slot >= 0) {                                /* a walk has ended */
+                bool finish = true;
+                if (!(st & 4)) {                                                /* ... the light-sample ray */
+                    if (!(st & 8)) st |= 2;
+                    if (st & 1) { st = (st & 2) | 4; dir_from = &b.sh_d2[slot]; finish = false; }
+                }
+                if (finish) {
+                    const float4 rc = ld_state<CS>(&b.sh_c[slot]);
+                    const float L = (st & 2) ? rc.x : 0.0f, B = ((st & 4) && !(st & 8)) ? rc.y : 0.0f;
+                    connect_finish(fp, b, bounce, slot, 0, L, B, rc.z, rc.w, rc.z);
+                    slot = -1;
+                }
+            }
+            /* idle lanes take the warp's next vertices */
+            const unsigned idle = __ballot_sync(0xffffffffu, cur == TRAV_DONE && slot < 0);
+            if (s_next < s_end && idle) {
+                const int s = s_next + __popc(idle & lt);
+                s_next = min(s_next + __popc(idle), s_end);
+                if (cur == TRAV_DONE && slot < 0 && s < s_end) {
+                    const int c = wbase + (s >> 5) * stride + (s & 31);
+                    if (c < n_con) {
+                        const int sl = via_order ? ld_state<CS>(&order[c]) : c;
+                        const float4 ro = ld_state<CS>(&b.sh_o[sl]);
+                        const int flags = __float_as_int(ro.w);
+                        const bool need1 = !(flags & 4) && (flags & 1), need2 = !(flags & 4) && (flags & 2);
+                        if (!need1 && !need2) {
+                            const float4 rc = ld_state<CS>(&b.sh_c[sl]);
+                            connect_finish(fp, b, bounce, sl, flags, 0.0f, 0.0f, rc.z, rc.w, rc.z);
+                        } else {
+                            slot = sl; r.o = v3(ro.x, ro.y, ro.z);
+                            if (need1) { st = need2 ? 1 : 0; dir_from = &b.sh_d1[sl]; }
+                            else { st = 4; dir_from = &b.sh_d2[sl]; }
+                        }
+#ifdef __CUDACC__
+                        if ((s & 7) == 0) {                                     /* next batch: its order entries, or its records */
+                            const int cn = c + stride;
+                            if (cn < n_con) {
+                                if (via_order) asm volatile("prefetch.global.L1 [%0];" :: "l"(&order[cn]));
+                                else { asm volatile("prefetch.global.L1 [%0];" :: "l"(&b.sh_o[cn])); asm volatile("prefetch.global.L1 [%0];" :: "l"(&b.sh_d1[cn])); }
+                            }
+                        }
+#endif
+                    }
+                }
+            }
+            if (dir_from) {
+                const float4 d = ld_state<CS>(dir_from);
+                r.d = v3(d.x, d.y, d.z); r.inv = v3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+                nbase = reinterpret_cast<unsigned long long>(sc.nodes);
+                if (LYS_LAY_IS_OCT(LAY)) nbase += 32ull * (unsigned)n_nodes * (unsigned)(((r.inv.x < 0.0f) ? 4 : 0) | ((r.inv.y < 0.0f) ? 2 : 0) | ((r.inv.z < 0.0f) ? 1 : 0));
+                tmax = d.w; cur = 0; st &= ~8;
+            }
+            if (s_next >= s_end && __ballot_sync(0xffffffffu, cur != TRAV_DONE || slot >= 0) == 0u) break;
+        }
+#pragma unroll
+        for (int k = 0; k < TRAV_NB; k++) {
+            if (cur >= 0) {
+                const float4 *q = reinterpret_cast<const float4 *>(nbase + 32ull * (unsigned)cur);
+                float4 lo, hi; ld_sector(q, lo, hi);
+                float tn;
+                cur = __float_as_int((LYS_LAY_IS_OCT(LAY) ? slab_test_oct(r, lo, hi, tmax, tn) : slab_test(r, lo, hi, tmax, tn)) ? lo.w : hi.w);
+            }
+        }
+        if ((unsigned)cur > (unsigned)TRAV_DONE) {
+            float t; int next;
+            if (leaf_test(r, sc.leaf_tri, ~cur, tmax, t, next)) { st |= 8; cur = TRAV_DONE; }       /* any_hit stops at the first hit (bvh.fut:152) */
+            else cur = next;
+        }
+    }
+}
 template <int LAY>
 __global__ void __launch_bounds__(128, LYS_TRACE_MINB(LAY)) k_trace(SceneDev sc, const __grid_constant__ FrameParams fp, PassBuffers b, int bounce, int ordered) {
     const int n_ext = (bounce + 1 < fp.path_len) ? b.counts[bounce + 1] : 0;
@@ -641,6 +741,7 @@ __global__ void __launch_bounds__(128, LYS_TRACE_MINB(LAY)) k_trace(SceneDev sc,
     /* large scenes: the closest hits first, with lane refill; the loop below is then left with the shadow rays */
     constexpr bool refill_ext = LAY != LAY_OCT;
     if (refill_ext) trace_ext_refill<LAY>(sc, b, bounce, n_ext, stride, ordered);
+    if (LAY == LAY_SEL) { trace_con_refill<LAY>(sc, fp, b, bounce, n_con, stride, ordered); return; }      /* ... and the shadow rays */
     /* warp-uniform loop (traverse<> votes): a warp owns 32 consecutive items; only the warp that straddles n_ext mixes kinds */
     for (int i0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31) + (refill_ext ? n_ext : 0); i0 < total; i0 += stride) {
         const int i = i0 + lane;
