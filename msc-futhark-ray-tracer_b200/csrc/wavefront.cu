@@ -541,6 +541,9 @@ LYS_D void connect_finish(const FrameParams &fp, const PassBuffers &b, int bounc
 #ifndef LYS_TRACE_REFILL
 #define LYS_TRACE_REFILL 24
 #endif
+#ifndef LYS_REFILL_NB
+#define LYS_REFILL_NB 4         /* node stages per iteration of the refill loops: 1 / 2 / 3 / 4 -> 1185 / 1286 / 1284 / 1296 Mpaths/s on the 1 M-triangle scene (an iteration also pays the refill vote) */
+#endif
 template <int LAY>
 LYS_D void trace_ext_refill(const SceneDev &sc, const PassBuffers &b, int bounce, int n_ext, int stride, int ordered) {
     __shared__ int s_fin[4][64];                          /* per warp: finished items waiting for their order-list slot, (item << 1) | hit */
@@ -612,7 +615,7 @@ LYS_D void trace_ext_refill(const SceneDev &sc, const PassBuffers &b, int bounce
             }
         }
 #pragma unroll
-        for (int k = 0; k < TRAV_NB; k++) {
+        for (int k = 0; k < LYS_REFILL_NB; k++) {
             if (cur >= 0) {
                 const float4 *q = reinterpret_cast<const float4 *>(nbase + 32ull * (unsigned)cur);
                 float4 lo, hi; ld_sector(q, lo, hi);
@@ -713,7 +716,7 @@ LYS_D void trace_con_refill(const SceneDev &sc, const FrameParams &fp, const Pas
             if (s_next >= s_end && __ballot_sync(0xffffffffu, cur != TRAV_DONE || slot >= 0) == 0u) break;
         }
 #pragma unroll
-        for (int k = 0; k < TRAV_NB; k++) {
+        for (int k = 0; k < LYS_REFILL_NB; k++) {
             if (cur >= 0) {
                 const float4 *q = reinterpret_cast<const float4 *>(nbase + 32ull * (unsigned)cur);
                 float4 lo, hi; ld_sector(q, lo, hi);
