@@ -514,10 +514,10 @@ LYS_D void connect_finish(const FrameParams &fp, const PassBuffers &b, int bounc
     b.acc[pid] = a;
     if (b.probe_rad) { const size_t ix = probe_index(fp, pid); b.probe_rad[ix * 16 + bounce] = r; b.probe_dist[ix * 16 + bounce] = dist; }
 }
-/* A warp owns 32 consecutive items per grid-stride step and runs the vote-synchronised traverse<> loops on them.  Two
- * lane-refill variants (a one-visit-per-step state machine, and this staged loop with a refill round between iterations)
- * were built, parity-tested and measured: -38 % and +3 % on the 1 M-triangle scene, slower on every bundled scene
- * (profiles/README.md 7.2, 8.1); they are no longer part of the build.
+/* Batch loop (LAY_OCT, and the shadow rays of LAY_OCT_RF): a warp owns 32 consecutive items per grid-stride step and runs the
+ * vote-synchronised traverse<> loops on them.  With a per-ray stack, refilling idle lanes inside the loop did not pay (round 1 and
+ * early round 2: -38 % and +3 % on the 1 M-triangle scene, profiles/README.md 7.2, 8.1); with the stackless walk it does on scenes
+ * whose walks are long -- trace_ext_refill / trace_con_refill below, selected by scene size (profiles/README.md 8.11).
  * `ordered` bit 0: append the slots of bounce + 1 to the hits-first order list and walk this bounce's vertices in theirs. */
 /* resident CTAs of 128 threads per SM the traversal kernels are compiled for.  The walk waits on dependent record loads, so
  * more warps in flight win even with a few registers spilled to L1: with octant copies 12 CTAs (40 registers) against 10 (48, no
