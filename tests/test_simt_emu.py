@@ -92,6 +92,7 @@ def test_product_binding_has_no_library_override(emu_lib):
     ('lbvh', 1, 40, {'LYS_EMU_SCHEDULE': '3'}),        # hostile geometry: inf / NaN / denormals / duplicates / identical triangles
     ('soup', 2, 10, {}),                               # random scenes, materials, camera presets, poses, frame sizes, seeds
     ('soup', 3, 8, {'LYS_OCT_ONE_COPY': '1', 'LYS_EMU_SCHEDULE': '7'}),
+    ('soup', 5, 8, {'LYS_REFILL_MIN': '1', 'LYS_EMU_SCHEDULE': '11'}),      # lane refill of the closest-hit walks on small random scenes
     ('keys', 4, 12, {}),                               # random host sessions: key events, resizes, steps -> scalars, image, ARGB frame
 ], ids=lambda v: str(v) if not isinstance(v, dict) else ','.join(f'{k}={x}' for k, x in v.items()) or 'default')
 def test_fuzzed_parity_on_the_emulator(emu_lib, what, seed, count, env):
